@@ -1,0 +1,126 @@
+/* sfx.h -- C ABI of the B200 SMPL-X fitting engine (libsfx.so).
+ *
+ * The reference (xiyichen/smplify-x-partial) has no FFI: its seam is the Python API of
+ * smplifyx/fitting.py, camera.py, prior.py, optimizers/ (SURVEY.md section 8b).  Each entry
+ * point below names the reference interface it stands in for; the Python mirror in
+ * smplify-x-partial_b200/ binds them with ctypes (see INTEGRATION.md for the stub a
+ * maintainer of the reference would add).
+ *
+ * Conventions: plain pointers and sizes, no torch types.  Every function returns 0 on success
+ * or a negative sfx_status; sfx_last_error() gives the message of the last failure on the
+ * calling thread.  "dev" pointers are CUDA device pointers owned by the caller, row-major
+ * contiguous; "host" pointers are ordinary memory.  `stream` is a cudaStream_t passed as
+ * void*.  A model handle is immutable and may be shared by several batches; a batch handle is
+ * not re-entrant.  Nothing allocates after sfx_batch_create.
+ */
+#ifndef SFX_H
+#define SFX_H
+#include <stdint.h>
+#include "../smplify-x-partial_b200/csrc/sfx_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SFX_OK = 0,
+    SFX_ERR_ARG = -1,
+    SFX_ERR_CUDA = -2,
+    SFX_ERR_UNSUPPORTED = -3
+} sfx_status;
+
+typedef struct sfx_model sfx_model;
+typedef struct sfx_batch sfx_batch;
+
+/* Raw SMPL-X arrays as stored in SMPLX_{NEUTRAL,MALE,FEMALE}.npz (host pointers, float32 /
+ * int32).  Stands in for the constructor arguments of smplx.create (reference
+ * smplifyx/main.py:109-127) plus JointMapper(dataset.get_model2data()) (main.py:107). */
+typedef struct {
+    int32_t num_verts, num_faces;
+    const float* v_template;         /* [V,3] */
+    const float* shapedirs;          /* [V,3,shape_stride] */
+    int32_t shape_stride;            /* 400 in the shipped files */
+    int32_t num_betas;               /* columns [0, num_betas) */
+    int32_t expr_offset, num_expr;   /* columns [expr_offset, expr_offset + num_expr) */
+    const float* posedirs;           /* [V,3,486] */
+    const float* J_regressor;        /* [55,V] */
+    const float* lbs_weights;        /* [V,55] */
+    const int32_t* parents;          /* [55], root = -1 */
+    const int32_t* faces;            /* [F,3] */
+    int32_t n_hand;                  /* num_pca_comps, or 45 when use_pca is False */
+    const float* hand_components_l;  /* [n_hand,45] (identity rows when use_pca is False) */
+    const float* hand_components_r;  /* [n_hand,45] */
+    const float* hand_mean_l;        /* [45] (zeros when flat_hand_mean) */
+    const float* hand_mean_r;        /* [45] */
+    const int32_t* extra_vertex_ids; /* [21] smplx vertex_ids['smplx'] in selector order */
+    const int32_t* lmk_faces_idx;    /* [51] */
+    const float* lmk_bary_coords;    /* [51,3] */
+    int32_t use_face_contour;
+    const int32_t* dyn_lmk_faces_idx;   /* [79,17] or NULL */
+    const float* dyn_lmk_bary_coords;   /* [79,17,3] or NULL */
+    const int32_t* joint_map;        /* [num_keypoints] model joint index per keypoint */
+    int32_t num_keypoints;
+    int32_t use_double;              /* float_dtype float64 (reference main.py:99-105) */
+} sfx_model_desc;
+
+/* smplx.create(...).to(device) -- copies and re-lays the constants on the current device. */
+int sfx_model_create(const sfx_model_desc* desc, sfx_model** out);
+void sfx_model_destroy(sfx_model* m);
+
+/* Per-batch workspace: parameters, targets, L-BFGS history for B independent frames.
+ * use_vposer selects a 32-D latent pose block instead of the 63-D axis-angle one. */
+int sfx_batch_create(const sfx_model* m, int32_t num_frames, int32_t use_vposer, sfx_batch** out);
+void sfx_batch_destroy(sfx_batch* b);
+int sfx_batch_layout(const sfx_batch* b, SfxLayout* out);
+
+/* Targets of every frame (host pointers; copied with cudaMemcpyAsync on `stream`):
+ *   keypoints [B,K,3] (x, y, conf)        fit_single_frame.py:276-284
+ *   joint_weights [B,K]                   main.py:191-195 after data_parser.py:159-171
+ *   lowconf [B,K] (uint8)                 fit_single_frame.py:285-287
+ *   init_mask [B,K] (uint8)               fit_single_frame.py:289-294 (trimmed init joints)
+ *   cam [B,16]: fx fy cx cy R[9] data_weight trans_est_z pad
+ *   reg_pose [B,n_pose] or NULL           fit_single_frame.py:442 (regression_pose) */
+int sfx_batch_set_targets(sfx_batch* b, const void* keypoints, const void* joint_weights,
+                          const uint8_t* lowconf, const uint8_t* init_mask, const void* cam,
+                          const void* reg_pose, void* stream);
+/* Same, all pointers on the device (elements in the batch dtype). */
+int sfx_batch_set_targets_dev(sfx_batch* b, const void* gt, const void* conf,
+                              const void* joint_weights, const uint8_t* lowconf,
+                              const uint8_t* init_mask, const void* cam, const void* reg_pose);
+
+/* Parameter vectors [B,np] in the batch dtype (layout: sfx_batch_layout). */
+int sfx_batch_set_params(sfx_batch* b, const void* host_params, void* stream);
+int sfx_batch_get_params(const sfx_batch* b, void* host_params, void* stream);
+void* sfx_batch_params_dev(sfx_batch* b);
+
+/* One closure evaluation for every frame: loss [B] and gradient [B,np] w.r.t. the whole
+ * parameter vector.  Stands in for FittingMonitor.create_fitting_closure's fitting_func
+ * (fitting.py:232-273): SMPL-X forward + SMPLifyLoss / SMPLifyCameraInitLoss + backward.
+ * Also writes the mapped joints [B,K,3] when joints_dev != NULL. */
+int sfx_eval(sfx_batch* b, const SfxStage* stage, void* loss_dev, void* grad_dev,
+             void* joints_dev, void* stream);
+
+/* FittingMonitor.run_fitting (fitting.py:147-217) with the optimiser of
+ * optim_factory.create_optimizer (lbfgsls or adam) for every frame, entirely on the device:
+ * one launch, no host synchronisation.  frame_ids_dev (int32 [n]) restricts the launch to a
+ * subset (second orientation, fit_single_frame.py:527-538) or NULL for all frames.
+ * final_loss_dev [B] receives run_fitting's return value per frame. */
+int sfx_fit_stage(sfx_batch* b, const SfxStage* stage, const int32_t* frame_ids_dev,
+                  int32_t n_ids, void* final_loss_dev, void* stream);
+
+/* body_model(return_verts=True) for every frame (fit_single_frame.py:611): full-mesh
+ * vertices [B,V,3] and mapped joints [B,K,3] from the current parameters. */
+int sfx_forward_mesh(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream);
+
+/* Diagnostics: closure evaluations and status flags per frame ([B] int32, device). */
+int32_t* sfx_batch_evals_dev(sfx_batch* b);
+int32_t* sfx_batch_flags_dev(sfx_batch* b);
+int sfx_batch_reset_counters(sfx_batch* b, void* stream);
+
+const char* sfx_last_error(void);
+int sfx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFX_H */

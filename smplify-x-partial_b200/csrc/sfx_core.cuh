@@ -1,0 +1,1116 @@
+// Core of the per-frame fitting engine: SMPL-X sparse-support forward pass, loss stack and
+// analytic adjoint, strong-Wolfe L-BFGS / Adam and the run_fitting loop -- one CUDA block per
+// frame, the whole optimisation stage inside one kernel launch (no host synchronisation).
+//
+// The same source compiles twice:
+//   * nvcc, device pass: the product (threads of one block cooperate; SFX_FOR strides by
+//     blockDim.x, SFX_SYNC is __syncthreads);
+//   * g++, single-threaded "host simulation" used ONLY by tests/hostsim to debug the maths and
+//     the control flow without a GPU.  It is never linked into the product library.
+//
+// Reference behaviour restated here (file:line in /root/reference/smplifyx unless noted):
+//   SMPL-X forward ............ smplx 0.1.x lbs.py / body_models.py [third party, un-vendored]
+//   PerspectiveCamera.forward . camera.py:93-117
+//   GMoF ...................... utils.py:84-95
+//   SMPLifyLoss.forward ....... fitting.py:375-461
+//   SMPLifyCameraInitLoss ..... fitting.py:499-520
+//   SMPLifyAnglePrior, L2Prior  prior.py:53-97
+//   LBFGS.step / strong Wolfe . optimizers/lbfgs_ls.py:39-167, :256-445
+//   FittingMonitor.run_fitting  fitting.py:147-217
+#pragma once
+#include <math.h>
+#include "sfx_types.h"
+
+#ifdef __CUDACC__
+#define SFX_FN __device__ __forceinline__
+#define SFX_MFN __device__ __forceinline__
+#define SFX_FN_NOINLINE __device__ __noinline__
+#define SFX_TID ((int)threadIdx.x)
+#define SFX_NT ((int)blockDim.x)
+#define SFX_SYNC() __syncthreads()
+#else
+#define SFX_FN static inline
+#define SFX_MFN inline
+#define SFX_FN_NOINLINE static
+#define SFX_TID 0
+#define SFX_NT 1
+#define SFX_SYNC() ((void)0)
+#endif
+#define SFX_FOR(i, n) for (int i = SFX_TID; i < (n); i += SFX_NT)
+
+namespace sfx {
+
+// ------------------------------------------------------------------------------ views
+template <typename T>
+struct ModelView {
+    int V, NS, NB, NE, NH, K, NJOUT, use_contour, n_neck, nlev;
+    const T* PK;         // [3V][SFX_KPAD]  row 3v+c: 486 pose-corrective dirs | NS shape dirs | 0
+    const T* vt;         // [3V]            template
+    const T* J0;         // [165]           J_regressor . v_template
+    const T* JS;         // [165][32]       J_regressor . shapedirs
+    const T* Wd;         // [V][SFX_WROW]   dense skinning weights
+    const T* hand_l;     // [NH][45]
+    const T* hand_r;     // [NH][45]
+    const T* pose_mean;  // [165]
+    const int* sv_vid;   // [SFX_NSTATIC]   vertex id of every static support slot
+    const T* lmk_bary;   // [51*3]
+    const int* dyn_vid;  // [79][51]        vertex ids of the contour landmarks per yaw row
+    const T* dyn_bary;   // [79][51]
+    const int* joint_map;   // [K]  keypoint -> model joint (JointMapper, utils.py:68-81)
+    const int* inv_ptr;     // [NJOUT+1]  model joint -> keypoints (CSR)
+    const int* inv_idx;     // [K]
+    int parents[SFX_NJ];
+    int order[SFX_NJ];      // joints sorted by depth
+    int level_off[16];
+    int child_off[SFX_NJ + 1];
+    int child_idx[SFX_NJ];
+    int neck[8];            // neck kinematic chain (neck -> root)
+};
+
+template <typename T>
+struct BatchView {
+    int B;
+    SfxLayout lay;
+    T* params;           // [B][np]       in/out
+    const T* gt;         // [B][K][2]
+    const T* conf;       // [B][K]
+    const T* jw_base;    // [B][K]   joint weights after joints_to_ign / low-confidence zeroing
+    const unsigned char* lowconf;    // [B][K]
+    const unsigned char* init_mask;  // [B][K]  camera-init joints (trimmed)
+    const T* cam;        // [B][16]
+    const T* reg_pose;   // [B][n_pose] or nullptr
+    T* hist_s;           // [B][HIST][SFX_NP_MAX]
+    T* hist_y;           // [B][HIST][SFX_NP_MAX]
+    T* final_loss;       // [B]
+    int* n_evals;        // [B]  (accumulated)
+    int* flags;          // [B]
+    const int* frame_ids;   // optional indirection (nullptr: block b -> frame b)
+};
+
+// per-frame working set (shared memory on the device)
+template <typename T>
+struct Scratch {
+    T x[SFX_NP_MAX];          // full parameter vector
+    T gfull[SFX_NP_MAX];      // gradient wrt the full parameter vector
+    T fp[SFX_NPOSE], dfp[SFX_NPOSE];
+    T hand[90];
+    T shape[32], dshape[32];
+    T R[SFX_NJ * 9], Rw[SFX_NJ * 9], tw[SFX_NJ * 3], Jr[SFX_NJ * 3], rel[SFX_NJ * 3];
+    T dRw[SFX_NJ * 9], dtw[SFX_NJ * 3], dR[SFX_NJ * 9], dJ[SFX_NJ * 3], drel[SFX_NJ * 3];
+    T A[SFX_NJ * 12], dA[SFX_NJ * 12];
+    T c[SFX_KPAD], dc[SFX_KPAD];
+    T vp[SFX_NSLOT * 3], vert[SFX_NSLOT * 3], dvert[SFX_NSLOT * 3], dvp[SFX_NSLOT * 3];
+    T Trot[SFX_NSLOT * 9];
+    int vid[SFX_NSLOT];
+    T bary[SFX_NSLOT];
+    T X[SFX_NJOUT_MAX * 3], dX[SFX_NJOUT_MAX * 3];
+    T kl[SFX_KMAX];           // per-keypoint data term
+    T dp[SFX_KMAX * 3];       // per-keypoint dL/d(camera-space point)
+    T jw[SFX_KMAX];           // per-stage effective joint weights
+    // optimiser vectors (compact, length D)
+    T xa[SFX_NP_MAX], g[SFX_NP_MAX], d[SFX_NP_MAX], prev_g[SFX_NP_MAX], x0[SFX_NP_MAX];
+    T g_prev[SFX_NP_MAX], bg0[SFX_NP_MAX], bg1[SFX_NP_MAX], q[SFX_NP_MAX], gl[SFX_NP_MAX];
+    T m1[SFX_NP_MAX], m2[SFX_NP_MAX];   // Adam moments
+    T al[SFX_HIST], ro[SFX_HIST];
+    int act[SFX_NP_MAX];      // compact index -> full parameter index
+    T red[4];
+    T loss;
+    int dynrow;
+    int n_evals;
+};
+
+// ------------------------------------------------------------------------------ math
+SFX_FN float sfx_sin(float x) { return sinf(x); }
+SFX_FN double sfx_sin(double x) { return sin(x); }
+SFX_FN float sfx_cos(float x) { return cosf(x); }
+SFX_FN double sfx_cos(double x) { return cos(x); }
+SFX_FN float sfx_sqrt(float x) { return sqrtf(x); }
+SFX_FN double sfx_sqrt(double x) { return sqrt(x); }
+SFX_FN float sfx_exp(float x) { return expf(x); }
+SFX_FN double sfx_exp(double x) { return exp(x); }
+SFX_FN float sfx_atan2(float y, float x) { return atan2f(y, x); }
+SFX_FN double sfx_atan2(double y, double x) { return atan2(y, x); }
+SFX_FN float sfx_rint(float x) { return rintf(x); }
+SFX_FN double sfx_rint(double x) { return rint(x); }
+SFX_FN float sfx_abs(float x) { return fabsf(x); }
+SFX_FN double sfx_abs(double x) { return fabs(x); }
+
+// C = A * B (3x3, row major)
+template <typename T>
+SFX_FN void mat3_mul(const T* a, const T* b, T* c) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+
+// Rodrigues as smplx.lbs.batch_rodrigues writes it: angle = ||r + 1e-8||, dir = r / angle.
+template <typename T>
+SFX_FN void rodrigues(const T* r, T* R) {
+    const T e = (T)1e-8;
+    T a0 = r[0] + e, a1 = r[1] + e, a2 = r[2] + e;
+    T th = sfx_sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+    T x = r[0] / th, y = r[1] / th, z = r[2] / th;
+    T s = sfx_sin(th), c1 = (T)1 - sfx_cos(th);
+    // K = [0 -z y; z 0 -x; -y x 0],  K^2 = dir dir^T - |dir|^2 I
+    T xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+    R[0] = (T)1 + c1 * (-(yy + zz));
+    R[1] = -s * z + c1 * xy;
+    R[2] = s * y + c1 * xz;
+    R[3] = s * z + c1 * xy;
+    R[4] = (T)1 + c1 * (-(xx + zz));
+    R[5] = -s * x + c1 * yz;
+    R[6] = -s * y + c1 * xz;
+    R[7] = s * x + c1 * yz;
+    R[8] = (T)1 + c1 * (-(xx + yy));
+}
+
+// Adjoint of rodrigues(): G = dL/dR (row major 3x3) -> dr = dL/dr.
+template <typename T>
+SFX_FN void rodrigues_bwd(const T* r, const T* G, T* dr) {
+    const T e = (T)1e-8;
+    T a0 = r[0] + e, a1 = r[1] + e, a2 = r[2] + e;
+    T th = sfx_sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+    T inv = (T)1 / th;
+    T x = r[0] * inv, y = r[1] * inv, z = r[2] * inv;
+    T s = sfx_sin(th), c = sfx_cos(th), c1 = (T)1 - c;
+    T K[9] = {0, -z, y, z, 0, -x, -y, x, 0};
+    T K2[9];
+    mat3_mul(K, K, K2);
+    // dL/dtheta = <G, cos K + sin K^2>
+    T dth = 0;
+    for (int i = 0; i < 9; ++i) dth += G[i] * (c * K[i] + s * K2[i]);
+    // dL/dK = sin G + (1 - cos)(G K^T + K^T G)
+    T GKt[9], KtG[9], Kt[9] = {K[0], K[3], K[6], K[1], K[4], K[7], K[2], K[5], K[8]};
+    mat3_mul(G, Kt, GKt);
+    mat3_mul(Kt, G, KtG);
+    T dK[9];
+    for (int i = 0; i < 9; ++i) dK[i] = s * G[i] + c1 * (GKt[i] + KtG[i]);
+    T dx = dK[7] - dK[5], dy = dK[2] - dK[6], dz = dK[3] - dK[1];
+    // dir = r / th ; th = ||r + e||
+    T dot = dx * r[0] + dy * r[1] + dz * r[2];
+    T k = dth * inv - dot * inv * inv * inv;
+    dr[0] = dx * inv + k * a0;
+    dr[1] = dy * inv + k * a1;
+    dr[2] = dz * inv + k * a2;
+}
+
+// ------------------------------------------------------------------------ reductions
+// Fixed-order reductions so a frame's trajectory is reproducible run to run: lane l of warp 0
+// accumulates elements l, l+32, ... then an xor butterfly combines the 32 partials.
+template <typename T, typename F, typename Op>
+SFX_FN T block_reduce(int n, F f, Op op, T init, T* slot) {
+    SFX_SYNC();
+#ifdef __CUDACC__
+    if (threadIdx.x < 32) {
+        T p = init;
+        for (int i = threadIdx.x; i < n; i += 32) p = op(p, f(i));
+        for (int o = 16; o > 0; o >>= 1) p = op(p, __shfl_xor_sync(0xffffffffu, p, o));
+        if (threadIdx.x == 0) *slot = p;
+    }
+#else
+    T part[32];
+    for (int l = 0; l < 32; ++l) {
+        T p = init;
+        for (int i = l; i < n; i += 32) p = op(p, f(i));
+        part[l] = p;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        T nxt[32];
+        for (int l = 0; l < 32; ++l) nxt[l] = op(part[l], part[l ^ o]);
+        for (int l = 0; l < 32; ++l) part[l] = nxt[l];
+    }
+    *slot = part[0];
+#endif
+    SFX_SYNC();
+    return *slot;
+}
+
+template <typename T>
+struct OpAdd { SFX_MFN T operator()(T a, T b) const { return a + b; } };
+template <typename T>
+struct OpMax { SFX_MFN T operator()(T a, T b) const { return a > b ? a : b; } };
+
+template <typename T>
+SFX_FN T block_dot(const T* a, const T* b, int n, T* slot) {
+    return block_reduce<T>(n, [=](int i) { return a[i] * b[i]; }, OpAdd<T>(), (T)0, slot);
+}
+template <typename T>
+SFX_FN T block_absmax(const T* a, int n, T* slot) {
+    return block_reduce<T>(n, [=](int i) { return sfx_abs(a[i]); }, OpMax<T>(), (T)0, slot);
+}
+template <typename T>
+SFX_FN T block_abssum(const T* a, int n, T* slot) {
+    return block_reduce<T>(n, [=](int i) { return sfx_abs(a[i]); }, OpAdd<T>(), (T)0, slot);
+}
+
+// ------------------------------------------------------------------- blend streaming
+// vp[r] = vt[row] + PK[row] . c   for the 3 rows of every support slot     (forward)
+// dc[k] = sum_r PK[row][k] * dvp[r]                                         (adjoint)
+// These two passes move 225*3*512 values each and dominate the evaluation; the device
+// version lives in sfx_stream.cuh (TMA bulk copies into per-warp shared-memory rings).
+#ifndef __CUDACC__
+template <typename T>
+static void blend_forward(const ModelView<T>& M, Scratch<T>& S, void*) {
+    for (int r = 0; r < SFX_NSLOT * 3; ++r) {
+        long row = (long)S.vid[r / 3] * 3 + (r % 3);
+        const T* p = M.PK + row * SFX_KPAD;
+        T acc = 0;
+        for (int k = 0; k < SFX_KPAD; ++k) acc += p[k] * S.c[k];
+        S.vp[r] = M.vt[row] + acc;
+    }
+}
+template <typename T>
+static void blend_adjoint(const ModelView<T>& M, Scratch<T>& S, void*) {
+    for (int k = 0; k < SFX_KPAD; ++k) S.dc[k] = 0;
+    for (int r = 0; r < SFX_NSLOT * 3; ++r) {
+        long row = (long)S.vid[r / 3] * 3 + (r % 3);
+        const T* p = M.PK + row * SFX_KPAD;
+        T w = S.dvp[r];
+        for (int k = 0; k < SFX_KPAD; ++k) S.dc[k] += p[k] * w;
+    }
+}
+#endif
+
+// --------------------------------------------------------------------- evaluation
+struct FrameConst {          // per-frame constants decoded from the BatchView "cam" row
+    double fx, fy, cx, cy, Rc[9], dw, tz_est;
+};
+
+// One evaluation of the stage objective and its gradient for one frame (the reference's
+// closure, fitting.py:232-273).  Reads S.x, writes S.loss and S.gfull.
+template <typename T>
+SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const SfxStage& st,
+                                const T* gt, const T* conf, const unsigned char* init_mask,
+                                const T* cam, const T* reg_pose, Scratch<T>& S, void* stream_ws) {
+    const int NS = M.NS;
+    const int nj = M.NJOUT;
+    const int K = M.K;
+    // ---- 0. full pose, hand PCA, shape vector ------------------------------------------
+    SFX_FOR(i, SFX_NPOSE) {
+        T v;
+        if (i < 3) v = S.x[L.off_go + i];
+        else if (i < 66) v = S.x[L.off_pose + i - 3];      // VPoser decode replaces this block
+        else if (i < 69) v = S.x[L.off_jaw + i - 66];
+        else if (i < 72) v = S.x[L.off_leye + i - 69];
+        else if (i < 75) v = S.x[L.off_reye + i - 72];
+        else {
+            int h = (i - 75) / 45, e = (i - 75) % 45;
+            const T* C = h ? M.hand_r : M.hand_l;
+            const T* pc = S.x + (h ? L.off_rh : L.off_lh);
+            T acc = 0;
+            for (int k = 0; k < L.n_hand; ++k) acc += pc[k] * C[k * 45 + e];
+            S.hand[h * 45 + e] = acc;
+            v = acc;
+        }
+        S.fp[i] = v + M.pose_mean[i];
+    }
+    SFX_FOR(i, 32) {
+        T v = 0;
+        if (i < L.n_betas) v = S.x[L.off_betas + i];
+        else if (i < L.n_betas + L.n_expr) v = S.x[L.off_expr + i - L.n_betas];
+        S.shape[i] = v;
+    }
+    SFX_SYNC();
+    // ---- 1. joint rotations, rest joints ------------------------------------------------
+    SFX_FOR(j, SFX_NJ) rodrigues(S.fp + 3 * j, S.R + 9 * j);
+    SFX_FOR(i, SFX_NJ * 3) {
+        T acc = M.J0[i];
+        const T* js = M.JS + i * 32;
+        for (int s = 0; s < NS; ++s) acc += js[s] * S.shape[s];
+        S.Jr[i] = acc;
+    }
+    SFX_SYNC();
+    // blend coefficients: pose feature (R_j - I for j >= 1) | shape | 0
+    SFX_FOR(i, SFX_KPAD) {
+        T v = 0;
+        if (i < SFX_NPF) {
+            int e = i % 9;
+            v = S.R[9 + i] - ((e == 0 || e == 4 || e == 8) ? (T)1 : (T)0);
+        } else if (i < SFX_NPF + NS) {
+            v = S.shape[i - SFX_NPF];
+        }
+        S.c[i] = v;
+    }
+    SFX_FOR(i, SFX_NJ * 3) {
+        int j = i / 3, p = M.parents[j];
+        S.rel[i] = p < 0 ? S.Jr[i] : S.Jr[i] - S.Jr[3 * p + (i % 3)];
+    }
+    // dynamic-contour look-up row (smplx lbs.find_dynamic_lmk_idx_and_bcoords)
+    if (SFX_TID == 0) {
+        int row = 0;
+        if (M.use_contour) {
+            T rel[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tmp[9], Rn[9];
+            for (int i = 0; i < M.n_neck; ++i) {
+                rodrigues(S.fp + 3 * M.neck[i], Rn);
+                mat3_mul(Rn, rel, tmp);
+                for (int k = 0; k < 9; ++k) rel[k] = tmp[k];
+            }
+            T sy = sfx_sqrt(rel[0] * rel[0] + rel[3] * rel[3]);
+            T ang = sfx_atan2(-rel[6], sy);
+            T deg = (-ang * (T)180.0) / (T)3.14159265358979323846;
+            if (deg > (T)39) deg = (T)39;
+            long y = (long)sfx_rint(deg);
+            if (y < 0) y = (y < -39) ? 78 : (39 - y);
+            row = (int)y;
+        }
+        S.dynrow = row;
+    }
+    SFX_SYNC();
+    SFX_FOR(s, SFX_NSLOT) {
+        if (s < SFX_NSTATIC) {
+            S.vid[s] = M.sv_vid[s];
+            S.bary[s] = s < SFX_NEXTRA ? (T)1 : M.lmk_bary[s - SFX_NEXTRA];
+        } else if (M.use_contour) {
+            S.vid[s] = M.dyn_vid[S.dynrow * 51 + s - SFX_NSTATIC];
+            S.bary[s] = M.dyn_bary[S.dynrow * 51 + s - SFX_NSTATIC];
+        } else {
+            S.vid[s] = M.sv_vid[0];
+            S.bary[s] = 0;
+        }
+    }
+    // ---- 2. kinematic chain, level by level -------------------------------------------
+    for (int lv = 0; lv < M.nlev; ++lv) {
+        int a = M.level_off[lv], b = M.level_off[lv + 1];
+        SFX_FOR(i, b - a) {
+            int j = M.order[a + i], p = M.parents[j];
+            if (p < 0) {
+                for (int k = 0; k < 9; ++k) S.Rw[9 * j + k] = S.R[9 * j + k];
+                for (int k = 0; k < 3; ++k) S.tw[3 * j + k] = S.Jr[3 * j + k];
+            } else {
+                mat3_mul(S.Rw + 9 * p, S.R + 9 * j, S.Rw + 9 * j);
+                const T* Rp = S.Rw + 9 * p;
+                const T* rl = S.rel + 3 * j;
+                for (int k = 0; k < 3; ++k)
+                    S.tw[3 * j + k] = Rp[3 * k] * rl[0] + Rp[3 * k + 1] * rl[1] +
+                                      Rp[3 * k + 2] * rl[2] + S.tw[3 * p + k];
+            }
+        }
+        SFX_SYNC();
+    }
+    SFX_FOR(j, SFX_NJ) {
+        const T* Rj = S.Rw + 9 * j;
+        const T* J = S.Jr + 3 * j;
+        T* A = S.A + 12 * j;
+        for (int r = 0; r < 3; ++r) {
+            A[4 * r] = Rj[3 * r];
+            A[4 * r + 1] = Rj[3 * r + 1];
+            A[4 * r + 2] = Rj[3 * r + 2];
+            A[4 * r + 3] = S.tw[3 * j + r] -
+                           (Rj[3 * r] * J[0] + Rj[3 * r + 1] * J[1] + Rj[3 * r + 2] * J[2]);
+        }
+        for (int k = 0; k < 3; ++k) S.X[3 * j + k] = S.tw[3 * j + k];
+    }
+    SFX_SYNC();
+    // ---- 3. blendshapes on the support vertices (streams 225*3 rows of PK) -----------
+    blend_forward(M, S, stream_ws);
+    SFX_SYNC();
+    // ---- 4. skinning of the support vertices ------------------------------------------
+    SFX_FOR(s, SFX_NSLOT) {
+        const T* w = M.Wd + (long)S.vid[s] * SFX_WROW;
+        T Tm[12];
+        for (int k = 0; k < 12; ++k) Tm[k] = 0;
+        for (int j = 0; j < SFX_NJ; ++j) {
+            T wj = w[j];
+            if (wj != (T)0) {
+                const T* A = S.A + 12 * j;
+                for (int k = 0; k < 12; ++k) Tm[k] += wj * A[k];
+            }
+        }
+        const T* v = S.vp + 3 * s;
+        for (int r = 0; r < 3; ++r) {
+            S.vert[3 * s + r] = Tm[4 * r] * v[0] + Tm[4 * r + 1] * v[1] + Tm[4 * r + 2] * v[2] +
+                                Tm[4 * r + 3];
+            S.Trot[9 * s + 3 * r] = Tm[4 * r];
+            S.Trot[9 * s + 3 * r + 1] = Tm[4 * r + 1];
+            S.Trot[9 * s + 3 * r + 2] = Tm[4 * r + 2];
+        }
+    }
+    SFX_SYNC();
+    // ---- 5. extra joints and landmarks ------------------------------------------------
+    SFX_FOR(i, (nj - SFX_NJ) * 3) {
+        int j = SFX_NJ + i / 3, k = i % 3;
+        T v;
+        if (j < SFX_NJ + SFX_NEXTRA) {
+            v = S.vert[3 * (j - SFX_NJ) + k];
+        } else {
+            int s0 = SFX_NEXTRA + 3 * (j - SFX_NJ - SFX_NEXTRA);
+            v = S.bary[s0] * S.vert[3 * s0 + k] + S.bary[s0 + 1] * S.vert[3 * (s0 + 1) + k] +
+                S.bary[s0 + 2] * S.vert[3 * (s0 + 2) + k];
+        }
+        S.X[3 * j + k] = v;
+    }
+    SFX_SYNC();
+    // ---- 6. projection + data term per keypoint ---------------------------------------
+    const T fx = cam[SFX_CAM_FX], fy = cam[SFX_CAM_FY], cx = cam[SFX_CAM_CX], cy = cam[SFX_CAM_CY];
+    const T* Rc = cam + SFX_CAM_R;
+    const T dw = cam[SFX_CAM_DW];
+    const T dw2 = dw * dw;
+    const T* ct = S.x + L.off_camt;
+    const T rho2 = (T)(st.rho * st.rho);
+    T confsq = 1;
+    if (st.loss_kind == SFX_LOSS_CAMERA_INIT && st.use_conf_camera) {
+        // fitting.py:510-511: conf [1,n,1,1]^2 broadcast against err [1,n,2] -> (sum conf^2)(sum err)
+        confsq = block_reduce<T>(K, [=](int k) { return init_mask[k] ? conf[k] * conf[k] : (T)0; },
+                                 OpAdd<T>(), (T)0, &S.red[0]);
+    }
+    SFX_FOR(k, K) {
+        const T* Xj = S.X + 3 * M.joint_map[k];
+        T px = Rc[0] * Xj[0] + Rc[1] * Xj[1] + Rc[2] * Xj[2] + ct[0];
+        T py = Rc[3] * Xj[0] + Rc[4] * Xj[1] + Rc[5] * Xj[2] + ct[1];
+        T pz = Rc[6] * Xj[0] + Rc[7] * Xj[1] + Rc[8] * Xj[2] + ct[2];
+        T ix = px / pz, iy = py / pz;
+        T u = fx * ix + cx, v = fy * iy + cy;
+        T ru = gt[2 * k] - u, rv = gt[2 * k + 1] - v;
+        T lk, du, dv;       // loss of this keypoint, dL/du, dL/dv
+        if (st.loss_kind == SFX_LOSS_CAMERA_INIT) {
+            T w = init_mask[k] ? confsq * dw2 : (T)0;
+            lk = w * (ru * ru + rv * rv);
+            du = -(T)2 * w * ru;
+            dv = -(T)2 * w * rv;
+        } else {
+            T wk = st.use_joints_conf ? S.jw[k] * conf[k] : S.jw[k];
+            T w = wk * wk * dw2;
+            T su = ru * ru, sv = rv * rv;
+            T qu = su + rho2, qv = sv + rho2;
+            lk = w * (rho2 * (su / qu) + rho2 * (sv / qv));
+            // d/dr [rho2 r^2/(r^2+rho2)] = 2 r rho2^2 / (r^2+rho2)^2
+            du = -w * ((T)2 * ru * rho2 * rho2 / (qu * qu));
+            dv = -w * ((T)2 * rv * rho2 * rho2 / (qv * qv));
+        }
+        S.kl[k] = lk;
+        // back through the projection
+        T dix = du * fx, diy = dv * fy;
+        T dpx = dix / pz, dpy = diy / pz;
+        T dpz = -(dix * ix + diy * iy) / pz;
+        S.dp[3 * k] = dpx;
+        S.dp[3 * k + 1] = dpy;
+        S.dp[3 * k + 2] = dpz;
+    }
+    T data_loss = block_reduce<T>(K, [&](int k) { return S.kl[k]; }, OpAdd<T>(), (T)0, &S.red[0]);
+    // camera translation gradient = sum_k dL/dp_k
+    T gct[3];
+    for (int a = 0; a < 3; ++a)
+        gct[a] = block_reduce<T>(K, [&](int k) { return S.dp[3 * k + a]; }, OpAdd<T>(), (T)0,
+                                 &S.red[1]);
+    // ---- 7. adjoint: keypoints -> model joints -> support vertices ---------------------
+    SFX_FOR(i, nj * 3) {
+        int j = i / 3, a = i % 3;
+        T acc = 0;
+        for (int e = M.inv_ptr[j]; e < M.inv_ptr[j + 1]; ++e) {
+            const T* d = S.dp + 3 * M.inv_idx[e];
+            acc += Rc[a] * d[0] + Rc[3 + a] * d[1] + Rc[6 + a] * d[2];     // Rc^T dp
+        }
+        S.dX[i] = acc;
+    }
+    SFX_SYNC();
+    SFX_FOR(i, SFX_NSLOT * 3) {
+        int s = i / 3, k = i % 3;
+        int j = s < SFX_NEXTRA ? SFX_NJ + s : SFX_NJ + SFX_NEXTRA + (s - SFX_NEXTRA) / 3;
+        S.dvert[i] = j < nj ? S.bary[s] * S.dX[3 * j + k] : (T)0;
+    }
+    SFX_SYNC();
+    SFX_FOR(i, SFX_NSLOT * 3) {
+        int s = i / 3, k = i % 3;
+        const T* Tr = S.Trot + 9 * s;
+        const T* dv = S.dvert + 3 * s;
+        S.dvp[i] = Tr[k] * dv[0] + Tr[3 + k] * dv[1] + Tr[6 + k] * dv[2];
+    }
+    // dA[j][r][cc] = sum_s W[vid_s][j] * dvert[s][r] * (cc < 3 ? vp[s][cc] : 1)
+    SFX_FOR(i, SFX_NJ * 12) {
+        int j = i / 12, r = (i % 12) / 4, cc = i % 4;
+        T acc = 0;
+        for (int s = 0; s < SFX_NSLOT; ++s) {
+            T w = M.Wd[(long)S.vid[s] * SFX_WROW + j];
+            if (w != (T)0) acc += w * S.dvert[3 * s + r] * (cc < 3 ? S.vp[3 * s + cc] : (T)1);
+        }
+        S.dA[i] = acc;
+    }
+    SFX_SYNC();
+    // ---- 8. adjoint of the blendshapes (second stream over the PK rows) ---------------
+    if (st.need_blend_grad) {
+        blend_adjoint(M, S, stream_ws);
+    } else {
+        SFX_FOR(i, SFX_KPAD) S.dc[i] = 0;
+    }
+    SFX_SYNC();
+    // ---- 9. adjoint of the kinematic chain --------------------------------------------
+    SFX_FOR(j, SFX_NJ) {
+        const T* dA = S.dA + 12 * j;
+        const T* J = S.Jr + 3 * j;
+        const T* Rj = S.Rw + 9 * j;
+        for (int r = 0; r < 3; ++r) {
+            T dat = dA[4 * r + 3];
+            for (int k = 0; k < 3; ++k) S.dRw[9 * j + 3 * r + k] = dA[4 * r + k] - dat * J[k];
+            S.dtw[3 * j + r] = dat + S.dX[3 * j + r];
+        }
+        for (int k = 0; k < 3; ++k)
+            S.dJ[3 * j + k] = -(Rj[k] * dA[3] + Rj[3 + k] * dA[7] + Rj[6 + k] * dA[11]);
+        for (int k = 0; k < 9; ++k) S.dR[9 * j + k] = j >= 1 ? S.dc[9 * (j - 1) + k] : (T)0;
+    }
+    SFX_SYNC();
+    for (int lv = M.nlev - 1; lv >= 0; --lv) {
+        int a = M.level_off[lv], b = M.level_off[lv + 1];
+        SFX_FOR(i, b - a) {
+            int j = M.order[a + i], p = M.parents[j];
+            T* dRwj = S.dRw + 9 * j;
+            T* dtwj = S.dtw + 3 * j;
+            for (int e = M.child_off[j]; e < M.child_off[j + 1]; ++e) {
+                int ch = M.child_idx[e];
+                const T* dRc = S.dRw + 9 * ch;
+                const T* Rch = S.R + 9 * ch;
+                const T* dtc = S.dtw + 3 * ch;
+                const T* rl = S.rel + 3 * ch;
+                for (int r = 0; r < 3; ++r)
+                    for (int k = 0; k < 3; ++k)
+                        dRwj[3 * r + k] += dRc[3 * r] * Rch[3 * k] + dRc[3 * r + 1] * Rch[3 * k + 1] +
+                                           dRc[3 * r + 2] * Rch[3 * k + 2] + dtc[r] * rl[k];
+                for (int r = 0; r < 3; ++r) dtwj[r] += dtc[r];
+            }
+            if (p < 0) {
+                for (int k = 0; k < 9; ++k) S.dR[9 * j + k] += dRwj[k];
+                for (int k = 0; k < 3; ++k) S.drel[3 * j + k] = dtwj[k];
+            } else {
+                const T* Rp = S.Rw + 9 * p;
+                for (int r = 0; r < 3; ++r)
+                    for (int k = 0; k < 3; ++k)
+                        S.dR[9 * j + 3 * r + k] += Rp[r] * dRwj[k] + Rp[3 + r] * dRwj[3 + k] +
+                                                   Rp[6 + r] * dRwj[6 + k];
+                for (int r = 0; r < 3; ++r)
+                    S.drel[3 * j + r] = Rp[r] * dtwj[0] + Rp[3 + r] * dtwj[1] + Rp[6 + r] * dtwj[2];
+            }
+        }
+        SFX_SYNC();
+    }
+    // rel_j = J_j - J_parent(j)
+    SFX_FOR(i, SFX_NJ * 3) {
+        int j = i / 3, k = i % 3;
+        T acc = S.dJ[i] + S.drel[i];
+        for (int e = M.child_off[j]; e < M.child_off[j + 1]; ++e) acc -= S.drel[3 * M.child_idx[e] + k];
+        S.dJ[i] = acc;
+    }
+    SFX_SYNC();
+    SFX_FOR(s, 32) {
+        T acc = 0;
+        if (s < NS) {
+            acc = S.dc[SFX_NPF + s];
+            for (int i = 0; i < SFX_NJ * 3; ++i) acc += M.JS[i * 32 + s] * S.dJ[i];
+        }
+        S.dshape[s] = acc;
+    }
+    SFX_FOR(j, SFX_NJ) rodrigues_bwd(S.fp + 3 * j, S.dR + 9 * j, S.dfp + 3 * j);
+    SFX_SYNC();
+    // ---- 10. priors + gradient wrt the parameter vector --------------------------------
+    const T bpw2 = (T)st.body_pose_weight * (T)st.body_pose_weight;
+    const T sw2 = (T)st.shape_weight * (T)st.shape_weight;
+    const T hw2 = (T)st.hand_prior_weight * (T)st.hand_prior_weight;
+    const T ew2 = (T)st.expr_prior_weight * (T)st.expr_prior_weight;
+    const T bendw = (T)st.bending_prior_weight;
+    const bool body = st.loss_kind == SFX_LOSS_SMPLIFY;
+    SFX_FOR(i, L.np) {
+        T gv = 0;
+        if (i >= L.off_camt && i < L.off_camt + 3) {
+            gv = gct[i - L.off_camt];
+            if (!body && st.depth_loss_weight > 0 && i == L.off_camt + 2) {
+                T dlw = (T)st.depth_loss_weight;
+                gv += (T)2 * dlw * dlw * (S.x[i] - cam[SFX_CAM_TZ]);
+            }
+        } else if (i >= L.off_go && i < L.off_go + 3) {
+            gv = S.dfp[i - L.off_go];
+        } else if (i >= L.off_pose && i < L.off_pose + L.n_pose) {
+            int e = i - L.off_pose;
+            gv = S.dfp[3 + e];
+            if (body) {
+                if (st.pprior_kind == SFX_PPRIOR_REGRESSION)
+                    gv += (T)2 * bpw2 * (S.x[i] - reg_pose[e]);
+                else if (st.pprior_kind == SFX_PPRIOR_L2)
+                    gv += (T)2 * bpw2 * S.x[i];
+                // bending prior on full_pose[3:66][52, 55, 9, 12] with signs (+ - - -)
+                if (e == 52 || e == 55 || e == 9 || e == 12) {
+                    T sg = e == 52 ? (T)1 : (T)-1;
+                    T ex = sfx_exp(S.fp[3 + e] * sg);
+                    gv += bendw * (T)2 * ex * ex * sg;
+                }
+            }
+        } else if (i >= L.off_jaw && i < L.off_jaw + 3) {
+            int e = i - L.off_jaw;
+            gv = S.dfp[66 + e];
+            if (body) {
+                T jw = (T)st.jaw_prior_weight[e];
+                gv += (T)2 * jw * jw * S.x[i];
+            }
+        } else if (i >= L.off_leye && i < L.off_leye + 3) {
+            gv = S.dfp[69 + i - L.off_leye];
+        } else if (i >= L.off_reye && i < L.off_reye + 3) {
+            gv = S.dfp[72 + i - L.off_reye];
+        } else if (i >= L.off_betas && i < L.off_betas + L.n_betas) {
+            gv = S.dshape[i - L.off_betas];
+            if (body) gv += (T)2 * sw2 * S.x[i];
+        } else if (i >= L.off_expr && i < L.off_expr + L.n_expr) {
+            gv = S.dshape[L.n_betas + i - L.off_expr];
+            if (body) gv += (T)2 * ew2 * S.x[i];
+        } else if (i >= L.off_lh && i < L.off_lh + 2 * L.n_hand) {
+            int h = (i - L.off_lh) / L.n_hand, k = (i - L.off_lh) % L.n_hand;
+            const T* C = (h ? M.hand_r : M.hand_l) + k * 45;
+            const T* dh = S.dfp + 75 + 45 * h;
+            const T* hv = S.hand + 45 * h;
+            T acc = 0;
+            for (int e = 0; e < 45; ++e)
+                acc += C[e] * (dh[e] + (body ? (T)2 * hw2 * hv[e] : (T)0));
+            gv = acc;
+        }
+        S.gfull[i] = gv;
+    }
+    // ---- 11. total loss, summed in the order of fitting.py:457-460 ----------------------
+    T total = data_loss;
+    if (body) {
+        T pp;
+        const T* pe = S.x + L.off_pose;
+        if (st.pprior_kind == SFX_PPRIOR_REGRESSION)
+            pp = block_reduce<T>(L.n_pose, [=](int i) { T d = pe[i] - reg_pose[i]; return d * d; },
+                                 OpAdd<T>(), (T)0, &S.red[0]);
+        else
+            pp = block_reduce<T>(L.n_pose, [=](int i) { return pe[i] * pe[i]; }, OpAdd<T>(), (T)0,
+                                 &S.red[0]);
+        total += pp * bpw2;
+        const T* be = S.x + L.off_betas;
+        T sh = block_reduce<T>(L.n_betas, [=](int i) { return be[i] * be[i]; }, OpAdd<T>(), (T)0,
+                               &S.red[1]);
+        total += sh * sw2;
+        T ang = 0;
+        {
+            const int idx[4] = {52, 55, 9, 12};
+            for (int a = 0; a < 4; ++a) {
+                T ex = sfx_exp(S.fp[3 + idx[a]] * (a == 0 ? (T)1 : (T)-1));
+                ang += ex * ex;
+            }
+        }
+        total += ang * bendw;
+        T jaw = 0;
+        for (int e = 0; e < 3; ++e) {
+            T v = S.x[L.off_jaw + e] * (T)st.jaw_prior_weight[e];
+            jaw += v * v;
+        }
+        total += jaw;
+        const T* ex = S.x + L.off_expr;
+        T el = block_reduce<T>(L.n_expr, [=](int i) { return ex[i] * ex[i]; }, OpAdd<T>(), (T)0,
+                               &S.red[0]);
+        total += el * ew2;
+        const T* hv = S.hand;
+        T lh = block_reduce<T>(45, [=](int i) { return hv[i] * hv[i]; }, OpAdd<T>(), (T)0, &S.red[1]);
+        total += lh * hw2;
+        T rh = block_reduce<T>(45, [=](int i) { return hv[45 + i] * hv[45 + i]; }, OpAdd<T>(), (T)0,
+                               &S.red[0]);
+        total += rh * hw2;
+    } else if (st.depth_loss_weight > 0) {
+        T dlw = (T)st.depth_loss_weight;
+        T dz = ct[2] - cam[SFX_CAM_TZ];
+        total += dlw * dlw * (dz * dz);
+    }
+    SFX_SYNC();
+    if (SFX_TID == 0) {
+        S.loss = total;
+        S.n_evals += 1;
+    }
+    SFX_SYNC();
+}
+
+// Per-stage effective joint weights (fit_single_frame.py:569-574): body block keeps the base
+// weights, the 42 hand keypoints take hand_joint_weight, the face block face_joint_weight, and
+// low-confidence keypoints are zeroed again.
+template <typename T>
+SFX_FN void stage_joint_weights(const SfxStage& st, const T* jw_base, const unsigned char* lowconf,
+                                int K, Scratch<T>& S) {
+    SFX_FOR(k, K) {
+        T w = jw_base[k];
+        if (k >= st.n_body_kpts + 42) w = (T)st.face_joint_weight;
+        else if (k >= st.n_body_kpts) w = (T)st.hand_joint_weight;
+        if (lowconf[k]) w = 0;
+        S.jw[k] = w;
+    }
+    SFX_SYNC();
+}
+
+// ------------------------------------------------------- optimiser plumbing (compact <-> full)
+template <typename T>
+SFX_FN void scatter_active(Scratch<T>& S, int D) {        // xa -> x
+    SFX_FOR(i, D) S.x[S.act[i]] = S.xa[i];
+    SFX_SYNC();
+}
+template <typename T>
+SFX_FN void gather_grad(Scratch<T>& S, int D, T* dst) {   // gfull -> dst (compact)
+    SFX_FOR(i, D) dst[i] = S.gfull[S.act[i]];
+    SFX_SYNC();
+}
+
+template <typename T>
+struct EvalCtx {
+    const ModelView<T>* M;
+    const SfxLayout* L;
+    const SfxStage* st;
+    const T* gt;
+    const T* conf;
+    const unsigned char* init_mask;
+    const T* cam;
+    const T* reg_pose;
+    void* stream_ws;
+};
+
+// closure(): evaluate at S.xa, leave loss in S.loss and the compact gradient in S.gl
+// ("last evaluated gradient" -- what run_fitting's gtol test reads, fitting.py:191-193).
+template <typename T>
+SFX_FN double closure(const EvalCtx<T>& E, Scratch<T>& S) {
+    const int D = E.st->n_active;
+    scatter_active(S, D);
+    eval_frame(*E.M, *E.L, *E.st, E.gt, E.conf, E.init_mask, E.cam, E.reg_pose, S, E.stream_ws);
+    gather_grad(S, D, S.gl);
+    return (double)S.loss;
+}
+
+// lswolfe cubic interpolation (lbfgs_ls.py:11-36); all scalars in double
+SFX_FN double cubic_min(double x1, double f1, double g1, double x2, double f2, double g2,
+                        bool has_bounds, double lo, double hi) {
+    if (!has_bounds) {
+        lo = x1 <= x2 ? x1 : x2;
+        hi = x1 <= x2 ? x2 : x1;
+    }
+    double d1 = g1 + g2 - 3 * (f1 - f2) / (x1 - x2);
+    double disc = d1 * d1 - g1 * g2;
+    if (disc >= 0) {
+        double d2 = sqrt(disc);
+        double pos = x1 <= x2 ? x2 - (x2 - x1) * ((g2 + d2 - d1) / (g2 - g1 + 2 * d2))
+                              : x1 - (x1 - x2) * ((g1 + d2 - d1) / (g1 - g2 + 2 * d2));
+        return fmin(fmax(pos, lo), hi);
+    }
+    return (lo + hi) / 2.;
+}
+
+SFX_FN double dmax(double a, double b) { return a > b ? a : b; }
+SFX_FN double dmin(double a, double b) { return a < b ? a : b; }
+
+// Evaluate the objective at x0 + t d (lbfgs_ls.py:249-254); x is restored by the caller's
+// next write of xa, so only xa is touched here.
+template <typename T>
+SFX_FN double probe(const EvalCtx<T>& E, Scratch<T>& S, double t, T* gdst, double* gtd_out) {
+    const int D = E.st->n_active;
+    const T tt = (T)t;
+    SFX_FOR(i, D) S.xa[i] = S.x0[i] + tt * S.d[i];
+    SFX_SYNC();
+    double f = closure(E, S);
+    SFX_FOR(i, D) gdst[i] = S.gl[i];
+    *gtd_out = (double)block_dot(S.gl, S.d, D, &S.red[2]);
+    return f;
+}
+
+template <typename T>
+SFX_FN void vcopy(T* dst, const T* src, int n) {
+    SFX_FOR(i, n) dst[i] = src[i];
+    SFX_SYNC();
+}
+
+// Strong-Wolfe line search (lbfgs_ls.py:39-167).  On entry S.g = gradient at x0, on exit
+// S.g = gradient at the accepted point; returns f there and the step in *t_io.
+// Gradient slots: g_prev (bracket phase "previous"), bg0 / bg1 (bracket ends), q (new probe).
+template <typename T>
+SFX_FN double strong_wolfe(const EvalCtx<T>& E, Scratch<T>& S, double* t_io, double f, double gtd,
+                           int* n_evals_out) {
+    const SfxStage& st = *E.st;
+    const int D = st.n_active;
+    const double c1 = 1e-4, c2 = 0.9;
+    const int max_ls = 25;
+    const int max_iter = st.max_iter;
+    double t = *t_io;
+    const double d_norm = (double)block_absmax(S.d, D, &S.red[2]);
+    double gtd_new;
+    double f_new = probe(E, S, t, S.q, &gtd_new);
+    int evals = 1;
+    double t_prev = 0, f_prev = f, gtd_prev = gtd;
+    vcopy(S.g_prev, S.g, D);
+    bool done = false;
+    int it = 0;
+    // bracket: positions bt, values bf, directional derivatives bd; gradients in bg0 / bg1
+    double bt[2] = {0, 0}, bf[2] = {0, 0}, bd[2] = {0, 0};
+    int nb = 0;
+    while (it < max_ls) {
+        if (f_new > (f + c1 * t * gtd) || (it > 1 && f_new >= f_prev)) {
+            bt[0] = t_prev; bt[1] = t; bf[0] = f_prev; bf[1] = f_new; bd[0] = gtd_prev; bd[1] = gtd_new;
+            vcopy(S.bg0, S.g_prev, D); vcopy(S.bg1, S.q, D);
+            nb = 2;
+            break;
+        }
+        if (fabs(gtd_new) <= -c2 * gtd) {
+            bt[0] = t; bf[0] = f_new; bd[0] = gtd_new;
+            vcopy(S.bg0, S.q, D);
+            nb = 1;
+            done = true;
+            break;
+        }
+        if (gtd_new >= 0) {
+            bt[0] = t_prev; bt[1] = t; bf[0] = f_prev; bf[1] = f_new; bd[0] = gtd_prev; bd[1] = gtd_new;
+            vcopy(S.bg0, S.g_prev, D); vcopy(S.bg1, S.q, D);
+            nb = 2;
+            break;
+        }
+        double lo = t + 0.01 * (t - t_prev), hi = t * 10;
+        double tmp = t;
+        t = cubic_min(t_prev, f_prev, gtd_prev, t, f_new, gtd_new, true, lo, hi);
+        t_prev = tmp; f_prev = f_new; gtd_prev = gtd_new;
+        vcopy(S.g_prev, S.q, D);
+        f_new = probe(E, S, t, S.q, &gtd_new);
+        evals += 1;
+        it += 1;
+    }
+    if (it == max_ls) {
+        bt[0] = 0; bt[1] = t; bf[0] = f; bf[1] = f_new; bd[0] = gtd; bd[1] = gtd_new;
+        vcopy(S.bg0, S.g, D); vcopy(S.bg1, S.q, D);
+        nb = 2;
+    }
+    bool stalled = false;
+    int lo_i = 0, hi_i = 1;
+    if (nb == 2 && !(bf[0] <= bf[1])) { lo_i = 1; hi_i = 0; }
+    if (nb == 1) { lo_i = 0; hi_i = 0; }
+    while (!done && it < max_iter) {
+        t = cubic_min(bt[0], bf[0], bd[0], bt[1], bf[1], bd[1], false, 0, 0);
+        double bmax = dmax(bt[0], bt[1]), bmin = dmin(bt[0], bt[1]);
+        double eps = 0.1 * (bmax - bmin);
+        if (dmin(bmax - t, t - bmin) < eps) {
+            if (stalled || t >= bmax || t <= bmin) {
+                t = fabs(t - bmax) < fabs(t - bmin) ? bmax - eps : bmin + eps;
+                stalled = false;
+            } else {
+                stalled = true;
+            }
+        } else {
+            stalled = false;
+        }
+        f_new = probe(E, S, t, S.q, &gtd_new);
+        evals += 1;
+        it += 1;
+        if (f_new > (f + c1 * t * gtd) || f_new >= bf[lo_i]) {
+            bt[hi_i] = t; bf[hi_i] = f_new; bd[hi_i] = gtd_new;
+            vcopy(hi_i ? S.bg1 : S.bg0, S.q, D);
+            if (bf[0] <= bf[1]) { lo_i = 0; hi_i = 1; } else { lo_i = 1; hi_i = 0; }
+        } else {
+            if (fabs(gtd_new) <= -c2 * gtd) {
+                done = true;
+            } else if (gtd_new * (bt[hi_i] - bt[lo_i]) >= 0) {
+                bt[hi_i] = bt[lo_i]; bf[hi_i] = bf[lo_i]; bd[hi_i] = bd[lo_i];
+                vcopy(hi_i ? S.bg1 : S.bg0, lo_i ? S.bg1 : S.bg0, D);
+            }
+            bt[lo_i] = t; bf[lo_i] = f_new; bd[lo_i] = gtd_new;
+            vcopy(lo_i ? S.bg1 : S.bg0, S.q, D);
+        }
+        if (fabs(bt[1] - bt[0]) * d_norm < st.tol_change) break;
+    }
+    vcopy(S.g, lo_i ? S.bg1 : S.bg0, D);
+    *t_io = bt[lo_i];
+    *n_evals_out = evals;
+    return bf[lo_i];
+}
+
+// persistent optimiser state of one frame within a stage (lbfgs_ls.py:292-300, :436-443)
+template <typename T>
+struct LbfgsState {
+    int n_iter;          // global iteration counter
+    int num_old;         // stored (s, y) pairs
+    int head;            // ring start
+    double t;
+    T H_diag;
+    double prev_loss;
+};
+
+// One LBFGS.step (lbfgs_ls.py:256-445).  Returns the loss at entry ("orig_loss").
+template <typename T>
+SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, T* hist_s, T* hist_y) {
+    const SfxStage& st = *E.st;
+    const int D = st.n_active;
+    const int H = st.history;
+    double orig_loss = closure(E, S);
+    double loss = orig_loss;
+    int current_evals = 1;
+    vcopy(S.g, S.gl, D);
+    if ((double)block_absmax(S.g, D, &S.red[2]) <= st.tol_grad) return orig_loss;
+    int n_iter = 0;
+    while (n_iter < st.max_iter) {
+        n_iter += 1;
+        ls.n_iter += 1;
+        if (ls.n_iter == 1) {
+            SFX_FOR(i, D) S.d[i] = -S.g[i];
+            SFX_SYNC();
+            ls.num_old = 0;
+            ls.head = 0;
+            ls.H_diag = 1;
+        } else {
+            // y = g - prev_g ; s = d * t   (staged in q / x0 until accepted)
+            const T tt = (T)ls.t;
+            SFX_FOR(i, D) {
+                S.q[i] = S.g[i] - S.prev_g[i];
+                S.x0[i] = S.d[i] * tt;
+            }
+            T ys = block_dot(S.q, S.x0, D, &S.red[2]);
+            if (ys > (T)1e-10) {
+                int slot;
+                if (ls.num_old == H) {
+                    slot = ls.head;
+                    ls.head = (ls.head + 1) % H;
+                    // shift of the per-pair scalars (history pops the oldest pair)
+                    SFX_SYNC();
+                    if (SFX_TID == 0)
+                        for (int i = 0; i + 1 < H; ++i) S.ro[i] = S.ro[i + 1];
+                    SFX_SYNC();
+                } else {
+                    slot = (ls.head + ls.num_old) % H;
+                    ls.num_old += 1;
+                }
+                T* ys_row = hist_y + (long)slot * SFX_NP_MAX;
+                T* ss_row = hist_s + (long)slot * SFX_NP_MAX;
+                SFX_FOR(i, D) {
+                    ys_row[i] = S.q[i];
+                    ss_row[i] = S.x0[i];
+                }
+                if (SFX_TID == 0) S.ro[ls.num_old - 1] = (T)1 / ys;
+                T yy = block_dot(S.q, S.q, D, &S.red[2]);
+                ls.H_diag = ys / yy;
+            }
+            // two-loop recursion
+            const int k = ls.num_old;
+            SFX_FOR(i, D) S.q[i] = -S.g[i];
+            SFX_SYNC();
+            for (int i = k - 1; i >= 0; --i) {
+                const T* srow = hist_s + (long)((ls.head + i) % H) * SFX_NP_MAX;
+                const T* yrow = hist_y + (long)((ls.head + i) % H) * SFX_NP_MAX;
+                T a = block_dot(srow, S.q, D, &S.red[2]) * S.ro[i];
+                if (SFX_TID == 0) S.al[i] = a;
+                SFX_FOR(e, D) S.q[e] += -a * yrow[e];
+            }
+            SFX_SYNC();
+            const T hd = ls.H_diag;
+            SFX_FOR(i, D) S.d[i] = S.q[i] * hd;
+            SFX_SYNC();
+            for (int i = 0; i < k; ++i) {
+                const T* srow = hist_s + (long)((ls.head + i) % H) * SFX_NP_MAX;
+                const T* yrow = hist_y + (long)((ls.head + i) % H) * SFX_NP_MAX;
+                T be = block_dot(yrow, S.d, D, &S.red[2]) * S.ro[i];
+                T co = S.al[i] - be;
+                SFX_FOR(e, D) S.d[e] += co * srow[e];
+            }
+            SFX_SYNC();
+        }
+        vcopy(S.prev_g, S.g, D);
+        ls.prev_loss = loss;
+        double t;
+        if (ls.n_iter == 1) {
+            T gs = block_abssum(S.g, D, &S.red[2]);
+            T inv = (T)1 / gs;
+            t = (inv < (T)1 ? (double)inv : 1.0) * st.lr;
+        } else {
+            t = st.lr;
+        }
+        double gtd = (double)block_dot(S.g, S.d, D, &S.red[2]);
+        if (gtd > -st.tol_change) {
+            ls.t = t;
+            break;
+        }
+        vcopy(S.x0, S.xa, D);      // x_init
+        int ls_evals = 0;
+        loss = strong_wolfe(E, S, &t, loss, gtd, &ls_evals);
+        {
+            const T tt = (T)t;
+            SFX_FOR(i, D) S.xa[i] = S.x0[i] + tt * S.d[i];
+            SFX_SYNC();
+        }
+        ls.t = t;
+        bool opt_cond = (double)block_absmax(S.g, D, &S.red[2]) <= st.tol_grad;
+        current_evals += ls_evals;
+        if (n_iter == st.max_iter) break;
+        if (current_evals >= st.max_eval) break;
+        if (opt_cond) break;
+        {
+            const T tt = (T)t;
+            const T* dd = S.d;
+            T mx = block_reduce<T>(D, [=](int i) { return sfx_abs(dd[i] * tt); }, OpMax<T>(), (T)0,
+                                   &S.red[2]);
+            if ((double)mx <= st.tol_change) break;
+        }
+        if (fabs(loss - ls.prev_loss) < st.tol_change) break;
+    }
+    scatter_active(S, D);
+    return orig_loss;
+}
+
+// torch.optim.Adam step (optim_factory.py:45-48; no weight decay, no amsgrad)
+template <typename T>
+SFX_FN double adam_step(const EvalCtx<T>& E, Scratch<T>& S, int* step_count) {
+    const SfxStage& st = *E.st;
+    const int D = st.n_active;
+    double loss = closure(E, S);
+    *step_count += 1;
+    const double b1 = st.adam_beta1, b2 = st.adam_beta2;
+    const double bc1 = 1.0 - pow(b1, (double)*step_count);
+    const double bc2 = 1.0 - pow(b2, (double)*step_count);
+    const T step_size = (T)(st.lr / bc1);
+    const T bc2s = (T)sqrt(bc2);
+    SFX_FOR(i, D) {
+        T gi = S.gl[i];
+        T m = S.m1[i] = (T)b1 * S.m1[i] + (T)(1.0 - b1) * gi;
+        T v = S.m2[i] = (T)b2 * S.m2[i] + (T)(1.0 - b2) * gi * gi;
+        T denom = sfx_sqrt(v) / bc2s + (T)st.adam_eps;
+        S.xa[i] = S.xa[i] - step_size * (m / denom);
+    }
+    SFX_SYNC();
+    scatter_active(S, D);
+    return loss;
+}
+
+SFX_FN double rel_change(double prev, double cur) {
+    double m = fabs(prev);
+    if (fabs(cur) > m) m = fabs(cur);
+    if (1.0 > m) m = 1.0;
+    return (prev - cur) / m;
+}
+
+// FittingMonitor.run_fitting (fitting.py:147-217) for one frame.  S.x holds the frame's
+// parameters on entry and on exit.  Returns the reference's return value (prev_loss; NaN when
+// the reference would return None).
+template <typename T>
+SFX_FN_NOINLINE double run_fitting(const EvalCtx<T>& E, Scratch<T>& S, T* hist_s, T* hist_y, int* flags) {
+    const SfxStage& st = *E.st;
+    const int D = st.n_active;
+    // compact index list
+    SFX_FOR(b, st.n_blocks)
+        for (int i = 0; i < st.block_len[b]; ++i) S.act[st.block_start[b] + i] = st.block_off[b] + i;
+    SFX_SYNC();
+    SFX_FOR(i, D) {
+        S.xa[i] = S.x[S.act[i]];
+        S.m1[i] = 0;
+        S.m2[i] = 0;
+    }
+    SFX_SYNC();
+    LbfgsState<T> ls;
+    ls.n_iter = 0; ls.num_old = 0; ls.head = 0; ls.t = 0; ls.H_diag = 1; ls.prev_loss = 0;
+    int adam_steps = 0;
+    double prev_loss = NAN;
+    bool have_prev = false;
+    for (int n = 0; n < st.maxiters; ++n) {
+        double loss = st.opt_kind == SFX_OPT_ADAM ? adam_step(E, S, &adam_steps)
+                                                  : lbfgs_step(E, S, ls, hist_s, hist_y);
+        if (loss != loss) { if (SFX_TID == 0) *flags |= SFX_FLAG_NAN; break; }
+        if (isinf(loss)) { if (SFX_TID == 0) *flags |= SFX_FLAG_INF; break; }
+        if (n > 0 && have_prev && st.ftol > 0) {
+            if (rel_change(prev_loss, loss) <= st.ftol) break;
+        }
+        // all(|max(grad of block)| < gtol) over the live parameter blocks (signed max!)
+        bool all_small = true;
+        for (int b = 0; b < st.n_blocks; ++b) {
+            const T* gb = S.gl + st.block_start[b];
+            T mx = block_reduce<T>(st.block_len[b], [=](int i) { return gb[i]; }, OpMax<T>(),
+                                   (T)-INFINITY, &S.red[2]);
+            if (!(fabs((double)mx) < st.gtol)) all_small = false;
+        }
+        if (all_small) break;
+        prev_loss = loss;
+        have_prev = true;
+    }
+    return prev_loss;
+}
+
+}  // namespace sfx

@@ -1,0 +1,212 @@
+// Host-side re-layout of the raw SMPL-X arrays (sfx_model_desc) into the tables the kernels
+// read.  Pure C++ (no CUDA) so the library and the host-simulation tests share it.
+#pragma once
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sfx.h"
+#include "sfx_core.cuh"
+
+namespace sfx {
+
+template <typename T>
+struct HostModel {
+    int V = 0, F = 0, NS = 0, NB = 0, NE = 0, NH = 0, K = 0, NJOUT = 0, use_contour = 0;
+    std::vector<T> PK, vt, J0, JS, Wd, hand_l, hand_r, pose_mean, lmk_bary, dyn_bary;
+    std::vector<int> sv_vid, dyn_vid, joint_map, inv_ptr, inv_idx, faces;
+    int parents[SFX_NJ], order[SFX_NJ], level_off[16], nlev = 0;
+    int child_off[SFX_NJ + 1], child_idx[SFX_NJ], neck[8], n_neck = 0;
+
+    // fills everything except the array pointers (those point at host or device copies)
+    void fill_scalars(ModelView<T>& m) const {
+        m.V = V; m.NS = NS; m.NB = NB; m.NE = NE; m.NH = NH; m.K = K; m.NJOUT = NJOUT;
+        m.use_contour = use_contour; m.n_neck = n_neck; m.nlev = nlev;
+        for (int i = 0; i < SFX_NJ; ++i) { m.parents[i] = parents[i]; m.order[i] = order[i]; }
+        for (int i = 0; i < 16; ++i) m.level_off[i] = level_off[i];
+        for (int i = 0; i <= SFX_NJ; ++i) m.child_off[i] = child_off[i];
+        for (int i = 0; i < SFX_NJ; ++i) m.child_idx[i] = child_idx[i];
+        for (int i = 0; i < 8; ++i) m.neck[i] = neck[i];
+    }
+    ModelView<T> host_view() const {
+        ModelView<T> m;
+        fill_scalars(m);
+        m.PK = PK.data(); m.vt = vt.data(); m.J0 = J0.data(); m.JS = JS.data(); m.Wd = Wd.data();
+        m.hand_l = hand_l.data(); m.hand_r = hand_r.data(); m.pose_mean = pose_mean.data();
+        m.sv_vid = sv_vid.data(); m.lmk_bary = lmk_bary.data(); m.dyn_vid = dyn_vid.data();
+        m.dyn_bary = dyn_bary.data(); m.joint_map = joint_map.data();
+        m.inv_ptr = inv_ptr.data(); m.inv_idx = inv_idx.data();
+        return m;
+    }
+};
+
+template <typename T>
+std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
+    const int V = d.num_verts;
+    if (V <= 0 || !d.v_template || !d.shapedirs || !d.posedirs || !d.J_regressor ||
+        !d.lbs_weights || !d.parents || !d.faces || !d.joint_map || !d.extra_vertex_ids ||
+        !d.lmk_faces_idx || !d.lmk_bary_coords)
+        return "sfx_model_desc: missing array";
+    if (d.num_betas + d.num_expr > SFX_NSHAPE_MAX) return "num_betas + num_expr exceeds 26";
+    if (d.n_hand < 1 || d.n_hand > 45) return "n_hand must be in 1..45";
+    if (d.num_keypoints < 1 || d.num_keypoints > SFX_KMAX) return "num_keypoints out of range";
+    if (d.use_face_contour && (!d.dyn_lmk_faces_idx || !d.dyn_lmk_bary_coords))
+        return "use_face_contour needs the dynamic landmark tables";
+    h.V = V; h.F = d.num_faces; h.NB = d.num_betas; h.NE = d.num_expr; h.NS = h.NB + h.NE;
+    h.NH = d.n_hand; h.K = d.num_keypoints; h.use_contour = d.use_face_contour ? 1 : 0;
+    h.NJOUT = SFX_NJ + SFX_NEXTRA + SFX_NLMK + (h.use_contour ? SFX_NDYN : 0);
+    const int NS = h.NS;
+    // --- kinematic tree ---
+    int depth[SFX_NJ];
+    for (int j = 0; j < SFX_NJ; ++j) {
+        h.parents[j] = d.parents[j];
+        if (j == 0 ? h.parents[j] >= 0 : (h.parents[j] < 0 || h.parents[j] >= j))
+            return "parents must be a topologically ordered tree rooted at joint 0";
+        depth[j] = j == 0 ? 0 : depth[h.parents[j]] + 1;
+    }
+    int maxd = *std::max_element(depth, depth + SFX_NJ);
+    if (maxd + 1 > 15) return "kinematic tree too deep";
+    h.nlev = maxd + 1;
+    int pos = 0;
+    for (int lv = 0; lv <= maxd; ++lv) {
+        h.level_off[lv] = pos;
+        for (int j = 0; j < SFX_NJ; ++j)
+            if (depth[j] == lv) h.order[pos++] = j;
+    }
+    for (int lv = maxd + 1; lv < 16; ++lv) h.level_off[lv] = pos;
+    pos = 0;
+    for (int j = 0; j < SFX_NJ; ++j) {
+        h.child_off[j] = pos;
+        for (int c = 0; c < SFX_NJ; ++c)
+            if (h.parents[c] == j) h.child_idx[pos++] = c;
+    }
+    h.child_off[SFX_NJ] = pos;
+    for (; pos < SFX_NJ; ++pos) h.child_idx[pos] = 0;
+    h.n_neck = 0;
+    for (int cur = 12; cur != -1 && h.n_neck < 8; cur = h.parents[cur]) h.neck[h.n_neck++] = cur;
+    for (int i = h.n_neck; i < 8; ++i) h.neck[i] = 0;
+    // --- blend matrix PK [3V][512]: pose dirs | shape dirs | 0 ---
+    h.PK.assign((size_t)3 * V * SFX_KPAD, (T)0);
+    h.vt.resize((size_t)3 * V);
+    for (long r = 0; r < 3L * V; ++r) {
+        T* row = h.PK.data() + r * SFX_KPAD;
+        const float* pd = d.posedirs + r * SFX_NPF;
+        for (int k = 0; k < SFX_NPF; ++k) row[k] = (T)pd[k];
+        const float* sd = d.shapedirs + r * d.shape_stride;
+        for (int s = 0; s < h.NB; ++s) row[SFX_NPF + s] = (T)sd[s];
+        for (int s = 0; s < h.NE; ++s) row[SFX_NPF + h.NB + s] = (T)sd[d.expr_offset + s];
+        h.vt[r] = (T)d.v_template[r];
+    }
+    // --- rest joints: J0 = Jreg . v_template, JS = Jreg . shapedirs (accumulated in double) ---
+    h.J0.assign(SFX_NJ * 3, (T)0);
+    h.JS.assign(SFX_NJ * 3 * 32, (T)0);
+    {
+        std::vector<double> acc(SFX_NJ * 3 * 33);
+        std::fill(acc.begin(), acc.end(), 0.0);
+        for (int j = 0; j < SFX_NJ; ++j) {
+            const float* jr = d.J_regressor + (long)j * V;
+            for (int v = 0; v < V; ++v) {
+                double w = jr[v];
+                if (w == 0.0) continue;
+                for (int c = 0; c < 3; ++c) {
+                    long r = 3L * v + c;
+                    double* a = acc.data() + (j * 3 + c) * 33;
+                    a[32] += w * d.v_template[r];
+                    const float* sd = d.shapedirs + r * d.shape_stride;
+                    for (int s = 0; s < h.NB; ++s) a[s] += w * sd[s];
+                    for (int s = 0; s < h.NE; ++s) a[h.NB + s] += w * sd[d.expr_offset + s];
+                }
+            }
+        }
+        for (int i = 0; i < SFX_NJ * 3; ++i) {
+            h.J0[i] = (T)acc[i * 33 + 32];
+            for (int s = 0; s < NS; ++s) h.JS[i * 32 + s] = (T)acc[i * 33 + s];
+        }
+    }
+    // --- dense skinning weights, padded rows ---
+    h.Wd.assign((size_t)V * SFX_WROW, (T)0);
+    for (long v = 0; v < V; ++v)
+        for (int j = 0; j < SFX_NJ; ++j) h.Wd[v * SFX_WROW + j] = (T)d.lbs_weights[v * SFX_NJ + j];
+    // --- hands ---
+    h.hand_l.resize((size_t)h.NH * 45);
+    h.hand_r.resize((size_t)h.NH * 45);
+    for (int i = 0; i < h.NH * 45; ++i) {
+        h.hand_l[i] = (T)d.hand_components_l[i];
+        h.hand_r[i] = (T)d.hand_components_r[i];
+    }
+    h.pose_mean.assign(SFX_NPOSE, (T)0);
+    for (int i = 0; i < 45; ++i) {
+        h.pose_mean[75 + i] = d.hand_mean_l ? (T)d.hand_mean_l[i] : (T)0;
+        h.pose_mean[120 + i] = d.hand_mean_r ? (T)d.hand_mean_r[i] : (T)0;
+    }
+    // --- support vertices ---
+    h.faces.resize((size_t)3 * h.F);
+    for (long i = 0; i < 3L * h.F; ++i) {
+        h.faces[i] = d.faces[i];
+        if (h.faces[i] < 0 || h.faces[i] >= V) return "face index out of range";
+    }
+    h.sv_vid.resize(SFX_NSTATIC);
+    h.lmk_bary.resize(SFX_NLMK * 3);
+    for (int i = 0; i < SFX_NEXTRA; ++i) {
+        h.sv_vid[i] = d.extra_vertex_ids[i];
+        if (h.sv_vid[i] < 0 || h.sv_vid[i] >= V) return "extra vertex id out of range";
+    }
+    for (int l = 0; l < SFX_NLMK; ++l) {
+        int f = d.lmk_faces_idx[l];
+        if (f < 0 || f >= h.F) return "lmk_faces_idx out of range";
+        for (int k = 0; k < 3; ++k) {
+            h.sv_vid[SFX_NEXTRA + 3 * l + k] = h.faces[3L * f + k];
+            h.lmk_bary[3 * l + k] = (T)d.lmk_bary_coords[3 * l + k];
+        }
+    }
+    h.dyn_vid.assign(SFX_NDYNROWS * 51, 0);
+    h.dyn_bary.assign(SFX_NDYNROWS * 51, (T)0);
+    if (h.use_contour) {
+        for (int y = 0; y < SFX_NDYNROWS; ++y)
+            for (int i = 0; i < SFX_NDYN; ++i) {
+                int f = d.dyn_lmk_faces_idx[y * SFX_NDYN + i];
+                if (f < 0 || f >= h.F) return "dynamic_lmk_faces_idx out of range";
+                for (int k = 0; k < 3; ++k) {
+                    h.dyn_vid[y * 51 + 3 * i + k] = h.faces[3L * f + k];
+                    h.dyn_bary[y * 51 + 3 * i + k] =
+                        (T)d.dyn_lmk_bary_coords[(y * SFX_NDYN + i) * 3 + k];
+                }
+            }
+    }
+    // --- joint mapper and its inverse ---
+    h.joint_map.resize(h.K);
+    std::vector<int> cnt(h.NJOUT + 1, 0);
+    for (int k = 0; k < h.K; ++k) {
+        int j = d.joint_map[k];
+        if (j < 0 || j >= h.NJOUT) return "joint_map entry out of range";
+        h.joint_map[k] = j;
+        cnt[j + 1]++;
+    }
+    h.inv_ptr.assign(h.NJOUT + 1, 0);
+    for (int j = 0; j < h.NJOUT; ++j) h.inv_ptr[j + 1] = h.inv_ptr[j] + cnt[j + 1];
+    h.inv_idx.resize(h.K);
+    std::vector<int> fillp(h.inv_ptr.begin(), h.inv_ptr.end() - 1);
+    for (int k = 0; k < h.K; ++k) h.inv_idx[fillp[h.joint_map[k]]++] = k;
+    return "";
+}
+
+inline SfxLayout make_layout(int n_betas, int n_expr, int n_hand, int use_vposer) {
+    SfxLayout L;
+    L.n_betas = n_betas; L.n_expr = n_expr; L.n_hand = n_hand;
+    L.n_pose = use_vposer ? SFX_NLATENT : 63;
+    int o = 0;
+    L.off_betas = o; o += n_betas;
+    L.off_go = o; o += 3;
+    L.off_lh = o; o += n_hand;
+    L.off_rh = o; o += n_hand;
+    L.off_jaw = o; o += 3;
+    L.off_leye = o; o += 3;
+    L.off_reye = o; o += 3;
+    L.off_expr = o; o += n_expr;
+    L.off_pose = o; o += L.n_pose;
+    L.off_camt = o; o += 3;
+    L.np = o;
+    return L;
+}
+
+}  // namespace sfx

@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE: ctypes wrapper of the single-threaded host build of csrc/sfx_core.cuh
+(tests/hostsim/sfx_hostsim.cpp).  Used to check the evaluation maths and the optimiser control
+flow against the oracle without a GPU.  Not part of the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from smplifyx_b200 import _native as N
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, 'libsfx_hostsim.so')
+_SRC = os.path.join(_HERE, 'sfx_hostsim.cpp')
+_CORE = os.path.join(_HERE, '..', '..', 'smplify-x-partial_b200', 'csrc')
+
+
+def build(force=False):
+    deps = [_SRC] + [os.path.join(_CORE, f) for f in
+                     ('sfx_core.cuh', 'sfx_types.h', 'sfx_model_prep.h')]
+    if (not force and os.path.isfile(_SO) and
+            all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps)):
+        return _SO
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-o', _SO, _SRC])
+    return _SO
+
+
+class HostSim(object):
+    def __init__(self, model_data, joint_map, use_double=True, use_vposer=False, **model_kw):
+        self.lib = C.CDLL(build())
+        self.lib.hs_model_create.restype = C.c_void_p
+        self.lib.hs_model_create.argtypes = [C.POINTER(N.SfxModelDesc), C.c_char_p, C.c_int]
+        self.lib.hs_model_destroy.argtypes = [C.c_void_p]
+        self.lib.hs_layout.argtypes = [C.c_void_p, C.c_int, C.POINTER(N.SfxLayout)]
+        self.lib.hs_run.argtypes = [C.c_void_p, C.POINTER(N.SfxStage), C.c_int, C.c_int] + \
+            [C.c_void_p] * 11 + [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        desc, keep = N.build_model_desc(model_data, joint_map, use_double=use_double, **model_kw)
+        err = C.create_string_buffer(256)
+        self.h = self.lib.hs_model_create(C.byref(desc), err, 256)
+        if not self.h:
+            raise RuntimeError(err.value.decode())
+        self.dt = np.float64 if use_double else np.float32
+        self.use_vposer = use_vposer
+        self.K = len(joint_map)
+        self.L = N.SfxLayout()
+        self.lib.hs_layout(self.h, int(use_vposer), C.byref(self.L))
+
+    def __del__(self):
+        try:
+            self.lib.hs_model_destroy(self.h)
+        except Exception:
+            pass
+
+    def _run(self, stage, do_fit, params, gt, conf, jw, lowconf, init_mask, cam, reg_pose):
+        a = lambda x, dt=None: np.ascontiguousarray(x, dtype=dt or self.dt)
+        params = a(params).copy()
+        gt, conf, jw, cam = a(gt), a(conf), a(jw), a(cam)
+        lowconf = a(lowconf if lowconf is not None else np.zeros(self.K), np.uint8)
+        init_mask = a(init_mask if init_mask is not None else np.zeros(self.K), np.uint8)
+        reg = a(reg_pose) if reg_pose is not None else None
+        loss = np.zeros(1, self.dt)
+        grad = np.zeros(self.L.np, self.dt)
+        joints = np.zeros((self.K, 3), self.dt)
+        ne, fl = C.c_int(0), C.c_int(0)
+        p = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None
+        self.lib.hs_run(self.h, C.byref(stage), int(self.use_vposer), int(do_fit), p(params), p(gt),
+                        p(conf), p(jw), p(lowconf), p(init_mask), p(cam), p(reg), p(loss), p(grad),
+                        p(joints), C.byref(ne), C.byref(fl))
+        return dict(loss=float(loss[0]), grad=grad, joints=joints, params=params,
+                    n_evals=ne.value, flags=fl.value)
+
+    def eval(self, stage, params, gt, conf, jw, cam, lowconf=None, init_mask=None, reg_pose=None):
+        return self._run(stage, 0, params, gt, conf, jw, lowconf, init_mask, cam, reg_pose)
+
+    def fit(self, stage, params, gt, conf, jw, cam, lowconf=None, init_mask=None, reg_pose=None):
+        return self._run(stage, 1, params, gt, conf, jw, lowconf, init_mask, cam, reg_pose)

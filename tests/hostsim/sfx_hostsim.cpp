@@ -1,0 +1,93 @@
+// TEST INFRASTRUCTURE ONLY -- single-threaded host build of smplify-x-partial_b200/csrc/
+// sfx_core.cuh, used by tests/test_hostsim_*.py to debug the evaluation maths and the
+// optimiser control flow without a GPU.  It is never linked into, or reachable from, the
+// product library (libsfx.so has no CPU path: it fails when CUDA is unavailable).
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../smplify-x-partial_b200/csrc/sfx_model_prep.h"
+
+using namespace sfx;
+
+template <typename T>
+struct SimModel {
+    HostModel<T> h;
+};
+struct SimHandle {
+    int use_double;
+    SimModel<float> f;
+    SimModel<double> d;
+};
+
+template <typename T>
+static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit, T* params,
+                const T* gt, const T* conf, const T* jw, const unsigned char* lowconf,
+                const unsigned char* init_mask, const T* cam, const T* reg_pose, T* loss_out,
+                T* grad_out, T* joints_out, int* n_evals, int* flags) {
+    ModelView<T> M = sm.h.host_view();
+    SfxLayout L = make_layout(sm.h.NB, sm.h.NE, sm.h.NH, use_vposer);
+    std::unique_ptr<Scratch<T>> Sp(new Scratch<T>());
+    Scratch<T>& S = *Sp;
+    std::memset(&S, 0, sizeof(S));
+    for (int i = 0; i < L.np; ++i) S.x[i] = params[i];
+    stage_joint_weights(*st, jw, lowconf, M.K, S);
+    std::vector<T> hs((size_t)SFX_HIST * SFX_NP_MAX), hy((size_t)SFX_HIST * SFX_NP_MAX);
+    EvalCtx<T> E{&M, &L, st, gt, conf, init_mask, cam, reg_pose, nullptr};
+    if (!do_fit) {
+        eval_frame(M, L, *st, gt, conf, init_mask, cam, reg_pose, S, nullptr);
+        *loss_out = S.loss;
+        for (int i = 0; i < L.np; ++i) grad_out[i] = S.gfull[i];
+    } else {
+        double r = run_fitting(E, S, hs.data(), hy.data(), flags);
+        *loss_out = (T)r;
+        for (int i = 0; i < L.np; ++i) params[i] = S.x[i];
+    }
+    if (joints_out)
+        for (int k = 0; k < M.K; ++k)
+            for (int a = 0; a < 3; ++a) joints_out[3 * k + a] = S.X[3 * M.joint_map[k] + a];
+    *n_evals = S.n_evals;
+}
+
+extern "C" {
+
+void* hs_model_create(const sfx_model_desc* desc, char* err, int errlen) {
+    SimHandle* h = new SimHandle();
+    h->use_double = desc->use_double;
+    std::string e = desc->use_double ? prepare_model(*desc, h->d.h) : prepare_model(*desc, h->f.h);
+    if (!e.empty()) {
+        std::strncpy(err, e.c_str(), errlen - 1);
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void hs_model_destroy(void* p) { delete (SimHandle*)p; }
+
+int hs_layout(void* p, int use_vposer, SfxLayout* out) {
+    SimHandle* h = (SimHandle*)p;
+    if (h->use_double) *out = make_layout(h->d.h.NB, h->d.h.NE, h->d.h.NH, use_vposer);
+    else *out = make_layout(h->f.h.NB, h->f.h.NE, h->f.h.NH, use_vposer);
+    return 0;
+}
+
+// one frame; all arrays in the model dtype
+int hs_run(void* p, const SfxStage* st, int use_vposer, int do_fit, void* params, const void* gt,
+           const void* conf, const void* jw, const unsigned char* lowconf,
+           const unsigned char* init_mask, const void* cam, const void* reg_pose, void* loss_out,
+           void* grad_out, void* joints_out, int* n_evals, int* flags) {
+    SimHandle* h = (SimHandle*)p;
+    if (h->use_double)
+        run<double>(h->d, st, use_vposer, do_fit, (double*)params, (const double*)gt,
+                    (const double*)conf, (const double*)jw, lowconf, init_mask, (const double*)cam,
+                    (const double*)reg_pose, (double*)loss_out, (double*)grad_out,
+                    (double*)joints_out, n_evals, flags);
+    else
+        run<float>(h->f, st, use_vposer, do_fit, (float*)params, (const float*)gt,
+                   (const float*)conf, (const float*)jw, lowconf, init_mask, (const float*)cam,
+                   (const float*)reg_pose, (float*)loss_out, (float*)grad_out, (float*)joints_out,
+                   n_evals, flags);
+    return 0;
+}
+}
