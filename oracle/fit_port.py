@@ -137,6 +137,28 @@ def euler_xyz_from_matrix(R):
 
 
 # --------------------------------------------------------------------- L-BFGS (strong Wolfe)
+class TorchOps(object):
+    """Vector primitives of the optimiser exactly as the reference spells them (ATen dot,
+    add_ with alpha).  Tests may substitute an implementation with another summation order
+    to replay the engine's arithmetic bit for bit (tests/test_control_flow.py)."""
+
+    @staticmethod
+    def dot(a, b):
+        return a.dot(b)
+
+    @staticmethod
+    def absmax(a):
+        return a.abs().max()
+
+    @staticmethod
+    def abssum(a):
+        return a.abs().sum()
+
+    @staticmethod
+    def axpy_(x, alpha, y):          # x += alpha * y
+        return x.add_(y, alpha=float(alpha))
+
+
 def _cubic_min(x1, f1, g1, x2, f2, g2, bounds=None):
     lo, hi = bounds if bounds is not None else ((x1, x2) if x1 <= x2 else (x2, x1))
     d1 = g1 + g2 - 3 * (f1 - f2) / (x1 - x2)
@@ -151,13 +173,14 @@ def _cubic_min(x1, f1, g1, x2, f2, g2, bounds=None):
     return (lo + hi) / 2.
 
 
-def _strong_wolfe(phi, t, d, f, g, gtd, c1=1e-4, c2=0.9, tol_change=1e-9, max_iter=20, max_ls=25):
+def _strong_wolfe(phi, t, d, f, g, gtd, c1=1e-4, c2=0.9, tol_change=1e-9, max_iter=20, max_ls=25,
+                  ops=TorchOps):
     """phi(t) -> (loss float, flat grad).  Returns (f, g, t, n_evals)."""
-    d_norm = d.abs().max()
+    d_norm = ops.absmax(d)
     g = g.clone()
     f_new, g_new = phi(t)
     n_evals = 1
-    gtd_new = g_new.dot(d)
+    gtd_new = ops.dot(g_new, d)
     t_prev, f_prev, g_prev, gtd_prev = 0, f, g, gtd
     done = False
     it = 0
@@ -180,7 +203,7 @@ def _strong_wolfe(phi, t, d, f, g, gtd, c1=1e-4, c2=0.9, tol_change=1e-9, max_it
         t_prev, f_prev, g_prev, gtd_prev = t_old, f_new, g_new.clone(), gtd_new
         f_new, g_new = phi(t)
         n_evals += 1
-        gtd_new = g_new.dot(d)
+        gtd_new = ops.dot(g_new, d)
         it += 1
     if it == max_ls:
         br = ([0, t], [f, f_new], [g, g_new], [gtd, gtd_new])
@@ -204,7 +227,7 @@ def _strong_wolfe(phi, t, d, f, g, gtd, c1=1e-4, c2=0.9, tol_change=1e-9, max_it
             stalled = False
         f_new, g_new = phi(t)
         n_evals += 1
-        gtd_new = g_new.dot(d)
+        gtd_new = ops.dot(g_new, d)
         it += 1
         if f_new > (f + c1 * t * gtd) or f_new >= bf[lo_i]:
             bt[hi_i], bf[hi_i], bg[hi_i], bgtd[hi_i] = t, f_new, g_new.clone(), gtd_new
@@ -226,8 +249,9 @@ class StrongWolfeLBFGS(object):
     reference optimiser's."""
 
     def __init__(self, x, lr=1.0, max_iter=20, max_eval=None, tol_grad=1e-5, tol_change=1e-9,
-                 history=100):
+                 history=100, ops=TorchOps):
         self.x = x
+        self.ops = ops
         self.lr = lr
         self.max_iter = max_iter
         self.max_eval = max_eval if max_eval is not None else max_iter * 5 // 4
@@ -242,7 +266,7 @@ class StrongWolfeLBFGS(object):
 
     def _probe(self, closure, x0, t, d):
         with torch.no_grad():
-            self.x.add_(d, alpha=float(t))
+            self.ops.axpy_(self.x, t, d)
         loss, g = closure()
         loss = float(loss)
         with torch.no_grad():
@@ -250,11 +274,12 @@ class StrongWolfeLBFGS(object):
         return loss, g
 
     def step(self, closure):
+        ops = self.ops
         orig_loss, g = closure()
         loss = float(orig_loss)
         evals = 1
         self.func_evals += 1
-        if g.abs().max() <= self.tol_grad:
+        if ops.absmax(g) <= self.tol_grad:
             return orig_loss
         d, t, H_diag, prev_g, prev_loss = self.d, self.t, self.H_diag, self.prev_g, self.prev_loss
         it = 0
@@ -268,7 +293,7 @@ class StrongWolfeLBFGS(object):
             else:
                 y = g.sub(prev_g)
                 s = d.mul(t)
-                ys = y.dot(s)
+                ys = ops.dot(y, s)
                 if ys > 1e-10:
                     if len(self.Y) == self.history:
                         self.Y.pop(0)
@@ -277,32 +302,32 @@ class StrongWolfeLBFGS(object):
                     self.Y.append(y)
                     self.S.append(s)
                     self.rho.append(1. / ys)
-                    H_diag = ys / y.dot(y)
+                    H_diag = ys / ops.dot(y, y)
                 k = len(self.Y)
                 q = g.neg()
                 for i in range(k - 1, -1, -1):
-                    self.al[i] = self.S[i].dot(q) * self.rho[i]
-                    q.add_(self.Y[i], alpha=-float(self.al[i]))
+                    self.al[i] = ops.dot(self.S[i], q) * self.rho[i]
+                    ops.axpy_(q, -self.al[i], self.Y[i])
                 d = r = torch.mul(q, H_diag)
                 for i in range(k):
-                    be = self.Y[i].dot(r) * self.rho[i]
-                    r.add_(self.S[i], alpha=float(self.al[i] - be))
+                    be = ops.dot(self.Y[i], r) * self.rho[i]
+                    ops.axpy_(r, self.al[i] - be, self.S[i])
             prev_g = g.clone() if prev_g is None else prev_g.copy_(g)
             prev_loss = loss
             if self.n_iter == 1:
-                t = min(1., 1. / g.abs().sum()) * self.lr
+                t = min(1., 1. / ops.abssum(g)) * self.lr
             else:
                 t = self.lr
-            gtd = g.dot(d)
+            gtd = ops.dot(g, d)
             if gtd > -self.tol_change:
                 break
             x0 = self.x.detach().clone()
             loss, g, t, ls_evals = _strong_wolfe(
                 lambda tt: self._probe(closure, x0, tt, d), t, d, loss, g, gtd,
-                max_iter=self.max_iter)
+                max_iter=self.max_iter, ops=ops)
             with torch.no_grad():
-                self.x.add_(d, alpha=float(t))
-            opt = g.abs().max() <= self.tol_grad
+                ops.axpy_(self.x, t, d)
+            opt = ops.absmax(g) <= self.tol_grad
             evals += ls_evals
             self.func_evals += ls_evals
             if it == self.max_iter:
@@ -311,7 +336,7 @@ class StrongWolfeLBFGS(object):
                 break
             if opt:
                 break
-            if d.mul(t).abs().max() <= self.tol_change:
+            if ops.absmax(d.mul(t)) <= self.tol_change:
                 break
             if abs(loss - prev_loss) < self.tol_change:
                 break

@@ -248,7 +248,12 @@ SFX_FN T block_abssum(const T* a, int n, T* slot) {
 // dc[k] = sum_r PK[row][k] * dvp[r]                                         (adjoint)
 // These two passes move 225*3*512 values each and dominate the evaluation; the device
 // version lives in sfx_stream.cuh (TMA bulk copies into per-warp shared-memory rings).
-#ifndef __CUDACC__
+#ifdef __CUDACC__
+template <typename T>
+__device__ __forceinline__ void blend_forward(const ModelView<T>& M, Scratch<T>& S, void* wsp);
+template <typename T>
+__device__ __forceinline__ void blend_adjoint(const ModelView<T>& M, Scratch<T>& S, void* wsp);
+#else
 template <typename T>
 static void blend_forward(const ModelView<T>& M, Scratch<T>& S, void*) {
     for (int r = 0; r < SFX_NSLOT * 3; ++r) {
@@ -276,15 +281,12 @@ struct FrameConst {          // per-frame constants decoded from the BatchView "
     double fx, fy, cx, cy, Rc[9], dw, tz_est;
 };
 
-// One evaluation of the stage objective and its gradient for one frame (the reference's
-// closure, fitting.py:232-273).  Reads S.x, writes S.loss and S.gfull.
+// Pose prologue of one frame: full pose (hand PCA + mean), Rodrigues, rest joints from the
+// shape, blend coefficients, yaw row of the contour table, kinematic chain, skinning
+// transforms A and the 55 posed skeleton joints.  Reads S.x.
 template <typename T>
-SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const SfxStage& st,
-                                const T* gt, const T* conf, const unsigned char* init_mask,
-                                const T* cam, const T* reg_pose, Scratch<T>& S, void* stream_ws) {
+SFX_FN_NOINLINE void pose_forward(const ModelView<T>& M, const SfxLayout& L, Scratch<T>& S) {
     const int NS = M.NS;
-    const int nj = M.NJOUT;
-    const int K = M.K;
     // ---- 0. full pose, hand PCA, shape vector ------------------------------------------
     SFX_FOR(i, SFX_NPOSE) {
         T v;
@@ -401,6 +403,18 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         for (int k = 0; k < 3; ++k) S.X[3 * j + k] = S.tw[3 * j + k];
     }
     SFX_SYNC();
+}
+
+// One evaluation of the stage objective and its gradient for one frame (the reference's
+// closure, fitting.py:232-273).  Reads S.x, writes S.loss and S.gfull.
+template <typename T>
+SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const SfxStage& st,
+                                const T* gt, const T* conf, const unsigned char* init_mask,
+                                const T* cam, const T* reg_pose, Scratch<T>& S, void* stream_ws) {
+    const int NS = M.NS;
+    const int nj = M.NJOUT;
+    const int K = M.K;
+    pose_forward(M, L, S);
     // ---- 3. blendshapes on the support vertices (streams 225*3 rows of PK) -----------
     blend_forward(M, S, stream_ws);
     SFX_SYNC();
@@ -712,6 +726,9 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.n_evals += 1;
     }
     SFX_SYNC();
+#ifdef SFX_TRACE
+    SFX_TRACE((double)total);
+#endif
 }
 
 // Per-stage effective joint weights (fit_single_frame.py:569-574): body block keeps the base
@@ -793,6 +810,9 @@ template <typename T>
 SFX_FN double probe(const EvalCtx<T>& E, Scratch<T>& S, double t, T* gdst, double* gtd_out) {
     const int D = E.st->n_active;
     const T tt = (T)t;
+#ifdef SFX_TRACE_STEP
+    SFX_TRACE_STEP(t);
+#endif
     SFX_FOR(i, D) S.xa[i] = S.x0[i] + tt * S.d[i];
     SFX_SYNC();
     double f = closure(E, S);

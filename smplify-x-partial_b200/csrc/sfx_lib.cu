@@ -1,0 +1,499 @@
+// libsfx.so -- kernels and C ABI (include/sfx.h) of the B200 SMPL-X fitting engine.
+//
+//   fit_stage_kernel   one block per frame; the whole FittingMonitor.run_fitting stage
+//                      (closure evaluations + strong-Wolfe L-BFGS or Adam) in one launch
+//   eval_kernel        one closure evaluation per frame (loss, gradient, mapped joints)
+//   mesh path          full-mesh vertices for output (see sfx_mesh.cuh)
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see __graft_entry__.build)
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sfx.h"
+#include "sfx_core.cuh"
+#include "sfx_model_prep.h"
+#include "sfx_stream.cuh"
+#include "sfx_mesh.cuh"
+
+using namespace sfx;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(SFX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+// ------------------------------------------------------------------------------ kernels
+#define SFX_THREADS 512
+
+template <typename T>
+__device__ __forceinline__ StreamWS carve_stream(unsigned char* base, int ring_mode) {
+    StreamWS ws;
+    size_t ring = ring_mode ? (size_t)SFX_NWARP * SFX_NBUF * SFX_KPAD * sizeof(T)
+                            : (size_t)SFX_NWARP * SFX_KPAD * sizeof(T);
+    ws.ring = base;
+    ws.bars = reinterpret_cast<uint64_t*>(base + ring);
+    ws.fills = reinterpret_cast<unsigned int*>(base + ring + SFX_NWARP * SFX_NBUF * sizeof(uint64_t));
+    ws.ring_mode = ring_mode;
+    return ws;
+}
+
+template <typename T>
+__host__ __device__ constexpr size_t scratch_bytes() {
+    return (sizeof(Scratch<T>) + 1023) / 1024 * 1024;
+}
+
+template <typename T>
+__device__ __forceinline__ void load_frame(const BatchView<T>& Bv, int f, Scratch<T>& S) {
+    const int np = Bv.lay.np;
+    for (int i = threadIdx.x; i < SFX_NP_MAX; i += blockDim.x)
+        S.x[i] = i < np ? Bv.params[(size_t)f * np + i] : (T)0;
+    if (threadIdx.x == 0) S.n_evals = 0;
+    __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SFX_THREADS, 1)
+fit_stage_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ BatchView<T> Bv,
+                 const __grid_constant__ SfxStage st, int ring_mode, T* final_loss_out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(smem);
+    __shared__ StreamWS ws;
+    __shared__ int flags;
+    const int f = Bv.frame_ids ? Bv.frame_ids[blockIdx.x] : (int)blockIdx.x;
+    const int K = M.K;
+    if (threadIdx.x == 0) {
+        ws = carve_stream<T>(smem + scratch_bytes<T>(), ring_mode);
+        flags = 0;
+    }
+    __syncthreads();
+    stream_init<T>(ws);
+    load_frame(Bv, f, S);
+    stage_joint_weights(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, K, S);
+    EvalCtx<T> E;
+    E.M = &M; E.L = &Bv.lay; E.st = &st;
+    E.gt = Bv.gt + (size_t)f * K * 2;
+    E.conf = Bv.conf + (size_t)f * K;
+    E.init_mask = Bv.init_mask + (size_t)f * K;
+    E.cam = Bv.cam + (size_t)f * SFX_CAM_STRIDE;
+    E.reg_pose = Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr;
+    E.stream_ws = &ws;
+    double r = run_fitting(E, S, Bv.hist_s + (size_t)f * SFX_HIST * SFX_NP_MAX,
+                           Bv.hist_y + (size_t)f * SFX_HIST * SFX_NP_MAX, &flags);
+    __syncthreads();
+    const int np = Bv.lay.np;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) Bv.params[(size_t)f * np + i] = S.x[i];
+    if (threadIdx.x == 0) {
+        Bv.final_loss[f] = (T)r;
+        if (final_loss_out) final_loss_out[f] = (T)r;
+        Bv.n_evals[f] += S.n_evals;
+        Bv.flags[f] |= flags;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SFX_THREADS, 1)
+eval_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ BatchView<T> Bv,
+            const __grid_constant__ SfxStage st, int ring_mode, T* loss_out, T* grad_out,
+            T* joints_out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(smem);
+    __shared__ StreamWS ws;
+    const int f = blockIdx.x;
+    const int K = M.K;
+    if (threadIdx.x == 0) ws = carve_stream<T>(smem + scratch_bytes<T>(), ring_mode);
+    __syncthreads();
+    stream_init<T>(ws);
+    load_frame(Bv, f, S);
+    stage_joint_weights(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, K, S);
+    eval_frame(M, Bv.lay, st, Bv.gt + (size_t)f * K * 2, Bv.conf + (size_t)f * K,
+               Bv.init_mask + (size_t)f * K, Bv.cam + (size_t)f * SFX_CAM_STRIDE,
+               Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr, S, &ws);
+    const int np = Bv.lay.np;
+    if (loss_out && threadIdx.x == 0) loss_out[f] = S.loss;
+    if (grad_out)
+        for (int i = threadIdx.x; i < np; i += blockDim.x) grad_out[(size_t)f * np + i] = S.gfull[i];
+    if (joints_out)
+        for (int i = threadIdx.x; i < K * 3; i += blockDim.x)
+            joints_out[(size_t)f * K * 3 + i] = S.X[3 * M.joint_map[i / 3] + (i % 3)];
+    if (threadIdx.x == 0) Bv.n_evals[f] += 1;
+}
+
+// Pose prologue only: skinning transforms A [B][55*12] and blend coefficients c [B][512] for the
+// full-mesh path.
+template <typename T>
+__global__ void __launch_bounds__(256, 1)
+mesh_coef_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ BatchView<T> Bv,
+                 T* Aout, T* Cout) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(smem);
+    const int f = blockIdx.x;
+    load_frame(Bv, f, S);
+    pose_forward(M, Bv.lay, S);
+    for (int i = threadIdx.x; i < SFX_NJ * 12; i += blockDim.x) Aout[(size_t)f * SFX_NJ * 12 + i] = S.A[i];
+    for (int i = threadIdx.x; i < SFX_KPAD; i += blockDim.x) Cout[(size_t)f * SFX_KPAD + i] = S.c[i];
+}
+
+// ------------------------------------------------------------------------------ handles
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = n;
+        return n ? cudaMalloc(&p, n) : cudaSuccess;
+    }
+    template <typename U>
+    cudaError_t upload(const std::vector<U>& v) {
+        cudaError_t e = alloc(v.size() * sizeof(U));
+        if (e != cudaSuccess) return e;
+        return v.empty() ? cudaSuccess : cudaMemcpy(p, v.data(), bytes, cudaMemcpyHostToDevice);
+    }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct sfx_model {
+    int use_double = 0;
+    int V = 0, F = 0, K = 0, NB = 0, NE = 0, NH = 0;
+    ModelView<float> vf;
+    ModelView<double> vd;
+    DevBuf PK, vt, J0, JS, Wd, hand_l, hand_r, pose_mean, sv_vid, lmk_bary, dyn_vid, dyn_bary,
+        joint_map, inv_ptr, inv_idx, faces;
+    int device = 0;
+    int num_sms = 0;
+};
+
+template <typename T>
+static int upload_model(const sfx_model_desc& d, sfx_model* m, ModelView<T>& view) {
+    HostModel<T> h;
+    std::string e = prepare_model(d, h);
+    if (!e.empty()) return fail(SFX_ERR_ARG, e);
+    m->V = h.V; m->F = h.F; m->K = h.K; m->NB = h.NB; m->NE = h.NE; m->NH = h.NH;
+    h.fill_scalars(view);
+    CUDA_TRY(m->PK.upload(h.PK));
+    CUDA_TRY(m->vt.upload(h.vt));
+    CUDA_TRY(m->J0.upload(h.J0));
+    CUDA_TRY(m->JS.upload(h.JS));
+    CUDA_TRY(m->Wd.upload(h.Wd));
+    CUDA_TRY(m->hand_l.upload(h.hand_l));
+    CUDA_TRY(m->hand_r.upload(h.hand_r));
+    CUDA_TRY(m->pose_mean.upload(h.pose_mean));
+    CUDA_TRY(m->sv_vid.upload(h.sv_vid));
+    CUDA_TRY(m->lmk_bary.upload(h.lmk_bary));
+    CUDA_TRY(m->dyn_vid.upload(h.dyn_vid));
+    CUDA_TRY(m->dyn_bary.upload(h.dyn_bary));
+    CUDA_TRY(m->joint_map.upload(h.joint_map));
+    CUDA_TRY(m->inv_ptr.upload(h.inv_ptr));
+    CUDA_TRY(m->inv_idx.upload(h.inv_idx));
+    CUDA_TRY(m->faces.upload(h.faces));
+    view.PK = (const T*)m->PK.p; view.vt = (const T*)m->vt.p; view.J0 = (const T*)m->J0.p;
+    view.JS = (const T*)m->JS.p; view.Wd = (const T*)m->Wd.p;
+    view.hand_l = (const T*)m->hand_l.p; view.hand_r = (const T*)m->hand_r.p;
+    view.pose_mean = (const T*)m->pose_mean.p; view.sv_vid = (const int*)m->sv_vid.p;
+    view.lmk_bary = (const T*)m->lmk_bary.p; view.dyn_vid = (const int*)m->dyn_vid.p;
+    view.dyn_bary = (const T*)m->dyn_bary.p; view.joint_map = (const int*)m->joint_map.p;
+    view.inv_ptr = (const int*)m->inv_ptr.p; view.inv_idx = (const int*)m->inv_idx.p;
+    return SFX_OK;
+}
+
+struct sfx_batch {
+    const sfx_model* m = nullptr;
+    int B = 0, use_vposer = 0;
+    SfxLayout lay;
+    size_t es = 4;        // element size of the batch dtype
+    DevBuf params, gt, conf, jw, lowconf, init_mask, cam, reg_pose, hist_s, hist_y, final_loss,
+        n_evals, flags, Acoef, Ccoef, vposed;
+    bool has_reg = false;
+    std::vector<unsigned char> stage_host;     // host staging for set_targets
+    template <typename T>
+    BatchView<T> view(const int* frame_ids) const {
+        BatchView<T> v;
+        v.B = B; v.lay = lay;
+        v.params = (T*)params.p; v.gt = (const T*)gt.p; v.conf = (const T*)conf.p;
+        v.jw_base = (const T*)jw.p; v.lowconf = (const unsigned char*)lowconf.p;
+        v.init_mask = (const unsigned char*)init_mask.p; v.cam = (const T*)cam.p;
+        v.reg_pose = has_reg ? (const T*)reg_pose.p : nullptr;
+        v.hist_s = (T*)hist_s.p; v.hist_y = (T*)hist_y.p; v.final_loss = (T*)final_loss.p;
+        v.n_evals = (int*)n_evals.p; v.flags = (int*)flags.p; v.frame_ids = frame_ids;
+        return v;
+    }
+};
+
+template <typename T>
+static size_t fit_smem(int ring_mode) {
+    return scratch_bytes<T>() + stream_smem_bytes<T>(ring_mode);
+}
+
+static int ring_mode_for(const sfx_model* m) {
+    const char* e = getenv("SFX_STREAM_DIRECT");
+    if (e && e[0] == '1') return 0;
+    return m->use_double ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* sfx_last_error(void) { return g_err.c_str(); }
+int sfx_version(void) { return 100; }
+
+int sfx_model_create(const sfx_model_desc* desc, sfx_model** out) {
+    if (!desc || !out) return fail(SFX_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SFX_ERR_CUDA, "no CUDA device visible: libsfx has no CPU path");
+    sfx_model* m = new sfx_model();
+    m->use_double = desc->use_double ? 1 : 0;
+    cudaGetDevice(&m->device);
+    cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device);
+    int rc = m->use_double ? upload_model<double>(*desc, m, m->vd) : upload_model<float>(*desc, m, m->vf);
+    if (rc != SFX_OK) {
+        delete m;
+        return rc;
+    }
+    *out = m;
+    return SFX_OK;
+}
+
+void sfx_model_destroy(sfx_model* m) { delete m; }
+
+int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batch** out) {
+    if (!m || !out || B < 1) return fail(SFX_ERR_ARG, "bad argument");
+    if (use_vposer) return fail(SFX_ERR_UNSUPPORTED, "VPoser latent pose is not built yet");
+    sfx_batch* b = new sfx_batch();
+    b->m = m; b->B = B; b->use_vposer = use_vposer;
+    b->lay = make_layout(m->NB, m->NE, m->NH, use_vposer);
+    b->es = m->use_double ? 8 : 4;
+    const size_t es = b->es, K = m->K;
+#define ALLOC(buf, n)                                                         \
+    do {                                                                      \
+        cudaError_t _e = b->buf.alloc(n);                                     \
+        if (_e == cudaSuccess && (n)) _e = cudaMemset(b->buf.p, 0, n);        \
+        if (_e != cudaSuccess) {                                              \
+            delete b;                                                         \
+            return fail(SFX_ERR_CUDA, std::string("alloc " #buf ": ") + cudaGetErrorString(_e)); \
+        }                                                                     \
+    } while (0)
+    ALLOC(params, (size_t)B * b->lay.np * es);
+    ALLOC(gt, (size_t)B * K * 2 * es);
+    ALLOC(conf, (size_t)B * K * es);
+    ALLOC(jw, (size_t)B * K * es);
+    ALLOC(lowconf, (size_t)B * K);
+    ALLOC(init_mask, (size_t)B * K);
+    ALLOC(cam, (size_t)B * SFX_CAM_STRIDE * es);
+    ALLOC(reg_pose, (size_t)B * b->lay.n_pose * es);
+    ALLOC(hist_s, (size_t)B * SFX_HIST * SFX_NP_MAX * es);
+    ALLOC(hist_y, (size_t)B * SFX_HIST * SFX_NP_MAX * es);
+    ALLOC(final_loss, (size_t)B * es);
+    ALLOC(n_evals, (size_t)B * sizeof(int));
+    ALLOC(flags, (size_t)B * sizeof(int));
+    ALLOC(Acoef, (size_t)B * SFX_NJ * 12 * es);
+    ALLOC(Ccoef, (size_t)mesh_padded_frames(B) * SFX_KPAD * es);
+    ALLOC(vposed, (size_t)mesh_padded_frames(B) * 3 * m->V * es);
+#undef ALLOC
+    *out = b;
+    return SFX_OK;
+}
+
+void sfx_batch_destroy(sfx_batch* b) { delete b; }
+
+int sfx_batch_layout(const sfx_batch* b, SfxLayout* out) {
+    if (!b || !out) return fail(SFX_ERR_ARG, "null argument");
+    *out = b->lay;
+    return SFX_OK;
+}
+
+int sfx_batch_set_targets(sfx_batch* b, const void* keypoints, const void* joint_weights,
+                          const uint8_t* lowconf, const uint8_t* init_mask, const void* cam,
+                          const void* reg_pose, void* stream) {
+    if (!b || !keypoints || !joint_weights || !lowconf || !init_mask || !cam)
+        return fail(SFX_ERR_ARG, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t es = b->es, K = b->m->K, B = b->B;
+    // split [B,K,3] keypoints into gt [B,K,2] and conf [B,K] on the host (tiny), then copy
+    b->stage_host.resize(B * K * 3 * es);
+    unsigned char* gt_h = b->stage_host.data();
+    unsigned char* conf_h = gt_h + B * K * 2 * es;
+    for (size_t i = 0; i < B * K; ++i) {
+        const unsigned char* src = (const unsigned char*)keypoints + i * 3 * es;
+        memcpy(gt_h + i * 2 * es, src, 2 * es);
+        memcpy(conf_h + i * es, src + 2 * es, es);
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->gt.p, gt_h, B * K * 2 * es, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->conf.p, conf_h, B * K * es, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->jw.p, joint_weights, B * K * es, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->lowconf.p, lowconf, B * K, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->init_mask.p, init_mask, B * K, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->cam.p, cam, B * SFX_CAM_STRIDE * es, cudaMemcpyHostToDevice, s));
+    b->has_reg = reg_pose != nullptr;
+    if (reg_pose)
+        CUDA_TRY(cudaMemcpyAsync(b->reg_pose.p, reg_pose, B * b->lay.n_pose * es,
+                                 cudaMemcpyHostToDevice, s));
+    return SFX_OK;
+}
+
+int sfx_batch_set_targets_dev(sfx_batch* b, const void* gt, const void* conf,
+                              const void* joint_weights, const uint8_t* lowconf,
+                              const uint8_t* init_mask, const void* cam, const void* reg_pose) {
+    if (!b || !gt || !conf || !joint_weights || !lowconf || !init_mask || !cam)
+        return fail(SFX_ERR_ARG, "null argument");
+    const size_t es = b->es, K = b->m->K, B = b->B;
+    CUDA_TRY(cudaMemcpy(b->gt.p, gt, B * K * 2 * es, cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaMemcpy(b->conf.p, conf, B * K * es, cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaMemcpy(b->jw.p, joint_weights, B * K * es, cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaMemcpy(b->lowconf.p, lowconf, B * K, cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaMemcpy(b->init_mask.p, init_mask, B * K, cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaMemcpy(b->cam.p, cam, B * SFX_CAM_STRIDE * es, cudaMemcpyDeviceToDevice));
+    b->has_reg = reg_pose != nullptr;
+    if (reg_pose)
+        CUDA_TRY(cudaMemcpy(b->reg_pose.p, reg_pose, B * b->lay.n_pose * es, cudaMemcpyDeviceToDevice));
+    return SFX_OK;
+}
+
+int sfx_batch_set_params(sfx_batch* b, const void* host_params, void* stream) {
+    if (!b || !host_params) return fail(SFX_ERR_ARG, "null argument");
+    CUDA_TRY(cudaMemcpyAsync(b->params.p, host_params, (size_t)b->B * b->lay.np * b->es,
+                             cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return SFX_OK;
+}
+
+int sfx_batch_get_params(const sfx_batch* b, void* host_params, void* stream) {
+    if (!b || !host_params) return fail(SFX_ERR_ARG, "null argument");
+    CUDA_TRY(cudaMemcpyAsync(host_params, b->params.p, (size_t)b->B * b->lay.np * b->es,
+                             cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return SFX_OK;
+}
+
+void* sfx_batch_params_dev(sfx_batch* b) { return b ? b->params.p : nullptr; }
+int32_t* sfx_batch_evals_dev(sfx_batch* b) { return b ? (int32_t*)b->n_evals.p : nullptr; }
+int32_t* sfx_batch_flags_dev(sfx_batch* b) { return b ? (int32_t*)b->flags.p : nullptr; }
+
+int sfx_batch_reset_counters(sfx_batch* b, void* stream) {
+    if (!b) return fail(SFX_ERR_ARG, "null argument");
+    CUDA_TRY(cudaMemsetAsync(b->n_evals.p, 0, (size_t)b->B * sizeof(int), (cudaStream_t)stream));
+    CUDA_TRY(cudaMemsetAsync(b->flags.p, 0, (size_t)b->B * sizeof(int), (cudaStream_t)stream));
+    return SFX_OK;
+}
+
+static int check_stage(const sfx_batch* b, const SfxStage* st) {
+    if (!b || !st) return fail(SFX_ERR_ARG, "null argument");
+    if (st->n_active < 1 || st->n_active > SFX_NP_MAX || st->n_blocks < 1 ||
+        st->n_blocks > SFX_MAX_BLOCKS)
+        return fail(SFX_ERR_ARG, "stage: bad active parameter set");
+    int pos = 0;
+    for (int i = 0; i < st->n_blocks; ++i) {
+        if (st->block_start[i] != pos || st->block_len[i] < 1 || st->block_off[i] < 0 ||
+            st->block_off[i] + st->block_len[i] > b->lay.np)
+            return fail(SFX_ERR_ARG, "stage: bad parameter block");
+        pos += st->block_len[i];
+    }
+    if (pos != st->n_active) return fail(SFX_ERR_ARG, "stage: blocks do not add up to n_active");
+    if (st->history < 1 || st->history > SFX_HIST) return fail(SFX_ERR_ARG, "stage: history out of range");
+    if (st->pprior_kind == SFX_PPRIOR_REGRESSION && !b->has_reg)
+        return fail(SFX_ERR_ARG, "stage: regression prior requested but no reg_pose was set");
+    if (st->pprior_kind == SFX_PPRIOR_GMM || st->pprior_kind == SFX_PPRIOR_LATENT || st->use_vposer)
+        return fail(SFX_ERR_UNSUPPORTED, "GMM / VPoser pose priors are not built yet");
+    if (st->opt_kind != SFX_OPT_LBFGSLS && st->opt_kind != SFX_OPT_ADAM)
+        return fail(SFX_ERR_UNSUPPORTED, "optimiser kind not supported on the device");
+    return SFX_OK;
+}
+
+int sfx_eval(sfx_batch* b, const SfxStage* st, void* loss_dev, void* grad_dev, void* joints_dev,
+             void* stream) {
+    int rc = check_stage(b, st);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int rm = ring_mode_for(b->m);
+    if (b->m->use_double) {
+        size_t smem = fit_smem<double>(rm);
+        CUDA_TRY(cudaFuncSetAttribute(eval_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_kernel<double><<<b->B, SFX_THREADS, smem, s>>>(b->m->vd, b->view<double>(nullptr), *st, rm,
+                                                            (double*)loss_dev, (double*)grad_dev,
+                                                            (double*)joints_dev);
+    } else {
+        size_t smem = fit_smem<float>(rm);
+        CUDA_TRY(cudaFuncSetAttribute(eval_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_kernel<float><<<b->B, SFX_THREADS, smem, s>>>(b->m->vf, b->view<float>(nullptr), *st, rm,
+                                                          (float*)loss_dev, (float*)grad_dev,
+                                                          (float*)joints_dev);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SFX_OK;
+}
+
+int sfx_fit_stage(sfx_batch* b, const SfxStage* st, const int32_t* frame_ids_dev, int32_t n_ids,
+                  void* final_loss_dev, void* stream) {
+    int rc = check_stage(b, st);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = frame_ids_dev ? n_ids : b->B;
+    if (grid < 1) return SFX_OK;
+    const int rm = ring_mode_for(b->m);
+    if (b->m->use_double) {
+        size_t smem = fit_smem<double>(rm);
+        CUDA_TRY(cudaFuncSetAttribute(fit_stage_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fit_stage_kernel<double><<<grid, SFX_THREADS, smem, s>>>(
+            b->m->vd, b->view<double>(frame_ids_dev), *st, rm, (double*)final_loss_dev);
+    } else {
+        size_t smem = fit_smem<float>(rm);
+        CUDA_TRY(cudaFuncSetAttribute(fit_stage_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fit_stage_kernel<float><<<grid, SFX_THREADS, smem, s>>>(
+            b->m->vf, b->view<float>(frame_ids_dev), *st, rm, (float*)final_loss_dev);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SFX_OK;
+}
+
+int sfx_forward_mesh(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream) {
+    if (!b || !vertices_dev) return fail(SFX_ERR_ARG, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const sfx_model* m = b->m;
+    if (m->use_double) {
+        size_t smem = scratch_bytes<double>();
+        CUDA_TRY(cudaFuncSetAttribute(mesh_coef_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mesh_coef_kernel<double><<<b->B, 256, smem, s>>>(m->vd, b->view<double>(nullptr),
+                                                         (double*)b->Acoef.p, (double*)b->Ccoef.p);
+        CUDA_TRY(cudaGetLastError());
+        std::string e = mesh_forward_simt<double>(m->vd, b->B, (const double*)b->Acoef.p,
+                                                  (const double*)b->Ccoef.p, (double*)b->vposed.p,
+                                                  (double*)vertices_dev, s);
+        if (!e.empty()) return fail(SFX_ERR_CUDA, e);
+    } else {
+        size_t smem = scratch_bytes<float>();
+        CUDA_TRY(cudaFuncSetAttribute(mesh_coef_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mesh_coef_kernel<float><<<b->B, 256, smem, s>>>(m->vf, b->view<float>(nullptr),
+                                                       (float*)b->Acoef.p, (float*)b->Ccoef.p);
+        CUDA_TRY(cudaGetLastError());
+        std::string e = mesh_forward_simt<float>(m->vf, b->B, (const float*)b->Acoef.p,
+                                                 (const float*)b->Ccoef.p, (float*)b->vposed.p,
+                                                 (float*)vertices_dev, s);
+        if (!e.empty()) return fail(SFX_ERR_CUDA, e);
+    }
+    if (joints_dev) {
+        // mapped joints through the sparse-support evaluation (forward part only matters)
+        SfxStage st;
+        memset(&st, 0, sizeof(st));
+        st.loss_kind = SFX_LOSS_CAMERA_INIT;
+        st.rho = 100;
+        st.n_active = 3; st.n_blocks = 1; st.block_start[0] = 0; st.block_len[0] = 3;
+        st.block_off[0] = b->lay.off_go; st.history = SFX_HIST; st.opt_kind = SFX_OPT_LBFGSLS;
+        int rc = sfx_eval(b, &st, nullptr, nullptr, joints_dev, stream);
+        if (rc) return rc;
+    }
+    return SFX_OK;
+}
+
+}  // extern "C"

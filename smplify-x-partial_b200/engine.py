@@ -1,0 +1,198 @@
+"""Thin host-side owner of the C-ABI handles (``include/sfx.h``): one ``Model`` per SMPL-X
+file and device, one ``FrameBatch`` per set of B frames fitted in lock-step.
+
+torch is used for device memory and streams only; every computation is a ``libsfx.so`` call.
+There is no CPU path: constructing a ``Model`` without a CUDA device raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Model(object):
+    """smplx.create(...) + JointMapper on the device (reference main.py:107-127)."""
+
+    def __init__(self, model_data, joint_map, dtype=torch.float32, device=None, **model_kw):
+        if not torch.cuda.is_available():
+            raise RuntimeError('smplifyx_b200 needs a CUDA device (sm_100a); there is no CPU path')
+        self.lib = N.load_library()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.dtype = dtype
+        self.np_dtype = np.float64 if dtype == torch.float64 else np.float32
+        self.K = int(len(joint_map))
+        self.model_kw = dict(model_kw)
+        faces = np.asarray(model_data['f']).astype(np.int64)
+        self.faces = faces
+        self.V = int(np.asarray(model_data['v_template']).shape[0])
+        desc, keep = N.build_model_desc(model_data, joint_map, use_double=dtype == torch.float64,
+                                        **model_kw)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(self.lib, self.lib.sfx_model_create(C.byref(desc), C.byref(h)))
+        del keep
+        self.h = h
+        self.n_hand = int(desc.n_hand)
+        self.n_betas = int(desc.num_betas)
+        self.n_expr = int(desc.num_expr)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.sfx_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FrameBatch(object):
+    """B independent frames: parameters, targets and optimiser workspace on the device."""
+
+    def __init__(self, model, num_frames, use_vposer=False):
+        self.model = model
+        self.lib = model.lib
+        self.B = int(num_frames)
+        self.use_vposer = bool(use_vposer)
+        h = C.c_void_p()
+        with torch.cuda.device(model.device):
+            N.check(self.lib, self.lib.sfx_batch_create(model.h, self.B, int(use_vposer),
+                                                        C.byref(h)))
+        self.h = h
+        self.L = N.SfxLayout()
+        N.check(self.lib, self.lib.sfx_batch_layout(self.h, C.byref(self.L)))
+        self.blocks = N.param_blocks(self.L)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.sfx_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ host <-> device
+    def _host(self, a, shape, dtype=None):
+        a = np.ascontiguousarray(np.asarray(a), dtype=dtype or self.model.np_dtype)
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError('expected shape {}, got {}'.format(tuple(shape), a.shape))
+        return a
+
+    def set_targets(self, keypoints, joint_weights, lowconf, init_mask, cam, reg_pose=None):
+        """Host arrays (numpy, or pinned CPU tensors) -> device, asynchronously on the current
+        stream.  Shapes as in ``sfx_batch_set_targets`` (include/sfx.h)."""
+        B, K = self.B, self.model.K
+        kp = self._host(keypoints, (B, K, 3))
+        jw = self._host(joint_weights, (B, K))
+        lc = self._host(lowconf, (B, K), np.uint8)
+        im = self._host(init_mask, (B, K), np.uint8)
+        cm = self._host(cam, (B, N.SFX_CAM_STRIDE))
+        rp = None if reg_pose is None else self._host(reg_pose, (B, self.L.n_pose))
+        self._keep = (kp, jw, lc, im, cm, rp)
+        p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_batch_set_targets(self.h, p(kp), p(jw), p(lc), p(im),
+                                                             p(cm), p(rp), _stream()))
+        return kp.nbytes + jw.nbytes + lc.nbytes + im.nbytes + cm.nbytes + \
+            (0 if rp is None else rp.nbytes)
+
+    def set_params(self, params):
+        x = self._host(params, (self.B, self.L.np))
+        self._keep_x = x
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_batch_set_params(self.h, C.c_void_p(x.ctypes.data),
+                                                            _stream()))
+        return x.nbytes
+
+    def get_params(self):
+        out = np.empty((self.B, self.L.np), dtype=self.model.np_dtype)
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_batch_get_params(self.h, C.c_void_p(out.ctypes.data),
+                                                            _stream()))
+            torch.cuda.current_stream().synchronize()
+        return out
+
+    def params_tensor(self):
+        """Device view [B, np] of the live parameters (no copy)."""
+        ptr = self.lib.sfx_batch_params_dev(self.h)
+        return _wrap(ptr, (self.B, self.L.np), self.model.dtype, self.model.device, self)
+
+    def _new(self, *shape, dtype=None):
+        return torch.empty(shape, dtype=dtype or self.model.dtype, device=self.model.device)
+
+    # ------------------------------------------------------------------ compute
+    def eval(self, stage, want_joints=False):
+        """One closure evaluation per frame -> (loss [B], grad [B, np], joints [B, K, 3]|None)."""
+        loss = self._new(self.B)
+        grad = self._new(self.B, self.L.np)
+        joints = self._new(self.B, self.model.K, 3) if want_joints else None
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_eval(self.h, C.byref(stage), _ptr(loss), _ptr(grad),
+                                                _ptr(joints), _stream()))
+        return loss, grad, joints
+
+    def fit_stage(self, stage, frame_ids=None, out=None):
+        """FittingMonitor.run_fitting for every frame (or the int32 device tensor
+        ``frame_ids``) in one launch; returns the per-frame return values [B] (device)."""
+        final = out if out is not None else self._new(self.B)
+        n = 0
+        if frame_ids is not None:
+            if frame_ids.dtype != torch.int32 or not frame_ids.is_cuda:
+                raise ValueError('frame_ids must be an int32 CUDA tensor')
+            n = int(frame_ids.numel())
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_fit_stage(self.h, C.byref(stage), _ptr(frame_ids), n,
+                                                     _ptr(final), _stream()))
+        return final
+
+    def forward_mesh(self, want_joints=True):
+        """body_model(return_verts=True): vertices [B, V, 3] (+ mapped joints [B, K, 3])."""
+        verts = self._new(self.B, self.model.V, 3)
+        joints = self._new(self.B, self.model.K, 3) if want_joints else None
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_forward_mesh(self.h, _ptr(verts), _ptr(joints),
+                                                        _stream()))
+        return verts, joints
+
+    def evals(self):
+        ptr = self.lib.sfx_batch_evals_dev(self.h)
+        return _wrap(ptr, (self.B,), torch.int32, self.model.device, self)
+
+    def flags(self):
+        ptr = self.lib.sfx_batch_flags_dev(self.h)
+        return _wrap(ptr, (self.B,), torch.int32, self.model.device, self)
+
+    def reset_counters(self):
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_batch_reset_counters(self.h, _stream()))
+
+
+class _CudaArray(object):
+    """__cuda_array_interface__ holder so torch can view library-owned device memory."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {
+            'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False), 'version': 2}
+
+
+def _wrap(ptr, shape, dtype, device, owner):
+    typestr = {torch.float32: '<f4', torch.float64: '<f8', torch.int32: '<i4'}[dtype]
+    with torch.cuda.device(device):
+        return torch.as_tensor(_CudaArray(ptr, shape, typestr, owner), device=device)

@@ -1,0 +1,386 @@
+"""Batched per-frame driver: the flow of the reference's ``fit_single_frame``
+(smplifyx/fit_single_frame.py:59-676) for B independent frames fitted in lock-step on the
+device.  The reference asserts ``batch_size == 1`` (fit_single_frame.py:119); here every frame
+keeps its own optimiser state, line search and termination tests, so a batch gives the same
+per-frame flow as B separate calls.
+
+Split in two so the host logic is testable without a GPU:
+
+* planning (pure numpy): weight schedules -> ``SfxStage`` list, regression-prior pose,
+  keypoint masks, camera initialisation, orientation flip;
+* execution: a handful of ``libsfx`` launches -- camera stage, then every annealing stage, one
+  launch each, with no host synchronisation inside a stage.
+"""
+import numpy as np
+
+from . import _native as N
+from . import utils as U
+
+
+# ------------------------------------------------------------------------------ planning
+def stage_weights(cfg):
+    """Per-stage weight dicts with the reference's defaults and validation
+    (fit_single_frame.py:136-207, :331-348)."""
+    bpw = cfg.get('body_pose_prior_weights')
+    if bpw is None:
+        bpw = [4.04 * 1e2, 4.04 * 1e2, 57.4, 4.78]
+    S = len(bpw)
+    dflt4 = [1e2, 5 * 1e1, 1e1, .5 * 1e1]
+
+    def get(key, default, what):
+        v = cfg.get(key)
+        v = list(default) if v is None else list(v)
+        if len(v) != S:
+            raise AssertionError('Number of Body pose prior weights does not match the number '
+                                 'of {}'.format(what))
+        return v
+    data_w = get('data_weights', [1] * S, 'data term weights')
+    shape_w = get('shape_weights', dflt4, 'Shape prior weights')
+    use_hands = cfg.get('use_hands', True)
+    use_face = cfg.get('use_face', True)
+    hand_prior_w = get('hand_pose_prior_weights', dflt4, 'hand pose prior weights') \
+        if use_hands else [0.0] * S
+    hand_joint_w = get('hand_joints_weights', [0.0, 0.0, 0.0, 1.0],
+                       'hand joint distance weights') if use_hands else [0.0] * S
+    if use_face:
+        jaw = cfg.get('jaw_pose_prior_weights')
+        if jaw is None:
+            jaw = [[x] * 3 for x in shape_w]
+        else:
+            jaw = [[float(v) for v in s.split(',')] if isinstance(s, str) else
+                   [float(v) for v in s] for s in jaw]
+        if len(jaw) != S:
+            raise AssertionError('Number of Body pose prior weights does not match the number '
+                                 'of jaw pose prior weights')
+        expr_w = get('expr_weights', dflt4, 'Expression prior weights')
+        face_joint_w = get('face_joints_weights', [0.0, 0.0, 0.0, 1.0],
+                           'face joint distance weights')
+    else:
+        jaw, expr_w, face_joint_w = [[0.0] * 3] * S, [0.0] * S, [0.0] * S
+    coll_w = get('coll_loss_weights', [0.0] * S, 'collision loss weights')
+    out = []
+    for i in range(S):
+        out.append(dict(data_weight=data_w[i], body_pose_weight=bpw[i], shape_weight=shape_w[i],
+                        expr_prior_weight=expr_w[i], jaw_prior_weight=jaw[i],
+                        hand_prior_weight=hand_prior_w[i], hand_weight=hand_joint_w[i],
+                        face_weight=face_joint_w[i], coll_loss_weight=coll_w[i]))
+    return out
+
+
+_OPT_KIND = {'lbfgsls': N.OPT_LBFGSLS, 'adam': N.OPT_ADAM}
+
+
+def _opt_kw(cfg):
+    kind = cfg.get('optim_type', 'lbfgsls')
+    if kind not in _OPT_KIND:
+        raise ValueError('Optimizer {} not supported on the device (lbfgsls, adam)'.format(kind))
+    return dict(opt_kind=_OPT_KIND[kind], lr=cfg.get('lr', 1.0), maxiters=cfg.get('maxiters', 30),
+                ftol=cfg.get('ftol', 1e-9), gtol=cfg.get('gtol', 1e-9),
+                adam_beta1=cfg.get('beta1', 0.9), adam_beta2=cfg.get('beta2', 0.999))
+
+
+def body_pose_prior_kind(cfg):
+    """Which branch of SMPLifyLoss.forward's pose prior applies (fitting.py:389-401)."""
+    if cfg.get('use_vposer', False):
+        return N.PPRIOR_LATENT
+    if cfg.get('regression_prior'):
+        return N.PPRIOR_REGRESSION
+    kind = cfg.get('body_prior_type', 'l2')
+    if kind == 'l2':
+        return N.PPRIOR_L2
+    if kind == 'gmm':
+        return N.PPRIOR_GMM
+    raise ValueError('Prior {} is not implemented'.format(kind))
+
+
+def make_stages(cfg, L):
+    """-> (camera SfxStage, [body SfxStage per annealing stage])."""
+    fmt = cfg.get('format', 'coco25')
+    nb = U.NUM_BODY_KEYPOINTS[fmt]
+    okw = _opt_kw(cfg)
+    cam = N.make_stage(L, N.CAMERA_STAGE_BLOCKS, loss_kind=N.LOSS_CAMERA_INIT,
+                       use_conf_camera=bool(cfg.get('use_conf_for_camera_init', False)),
+                       depth_loss_weight=cfg.get('depth_loss_weight', 1e2), n_body_kpts=nb,
+                       rho=cfg.get('rho', 100), use_vposer=cfg.get('use_vposer', False), **okw)
+    weights = stage_weights(cfg)
+    pk = body_pose_prior_kind(cfg)
+    stages = []
+    for i, w in enumerate(weights):
+        stages.append(N.make_stage(
+            L, N.BODY_STAGE_BLOCKS, loss_kind=N.LOSS_SMPLIFY, pprior_kind=pk, stage_index=i,
+            num_stages=len(weights), use_joints_conf=cfg.get('use_joints_conf', True),
+            use_vposer=cfg.get('use_vposer', False), n_body_kpts=nb, rho=cfg.get('rho', 100),
+            body_pose_weight=w['body_pose_weight'], shape_weight=w['shape_weight'],
+            bending_prior_weight=3.17 * w['body_pose_weight'],
+            hand_prior_weight=w['hand_prior_weight'], expr_prior_weight=w['expr_prior_weight'],
+            jaw_prior_weight=w['jaw_prior_weight'], hand_joint_weight=w['hand_weight'],
+            face_joint_weight=w['face_weight'], **okw))
+    return cam, stages
+
+
+def base_joint_weights(cfg, K):
+    """dataset.get_joint_weights() (data_parser.py:159-171)."""
+    jw = np.ones(K, dtype=np.float64)
+    ign = cfg.get('joints_to_ign')
+    if ign is not None and -1 not in ign:
+        jw[np.asarray(ign, dtype=np.int64)] = 0
+    return jw
+
+
+def keypoint_masks(keypoints, cfg, base_jw):
+    """keypoints [B,K,3] -> (joint_weights [B,K], lowconf [B,K] u8, init_mask [B,K] u8)
+    (fit_single_frame.py:285-294)."""
+    B, K, _ = keypoints.shape
+    nb = U.NUM_BODY_KEYPOINTS[cfg.get('format', 'coco25')]
+    if K < nb + 42:
+        raise ValueError('keypoints need the body, hand and face blocks (use_hands, use_face)')
+    thr = np.zeros(K)
+    thr[:nb] = cfg.get('confidence_threshold', 0)
+    conf = keypoints[:, :, 2]
+    lowconf = conf < thr[None]
+    jw = np.repeat(np.asarray(base_jw, dtype=np.float64)[None], B, axis=0)
+    jw[lowconf] = 0
+    init = np.zeros((B, K), dtype=bool)
+    idx = np.asarray(cfg.get('init_joints_idxs', (9, 12, 2, 5)), dtype=np.int64)
+    init[:, idx] = True
+    init &= (keypoints[:, :, 0] != 0) & (keypoints[:, :, 1] != 0) & ~lowconf
+    return jw, lowconf.astype(np.uint8), init.astype(np.uint8)
+
+
+def regression_pose(cfg, expose=None, pixie=None, dtype=np.float32):
+    """Regression prior -> (pose [63], global_orient [3]) as xyz-Euler angles used *as if*
+    they were axis-angle, exactly like the reference (fit_single_frame.py:209-235)."""
+    kind = cfg.get('regression_prior')
+    if not kind:
+        return None, None
+    pix = exp = gp = None
+    if kind in ('PIXIE', 'combined'):
+        pix = U.euler_xyz_from_matrix(np.asarray(pixie['body_pose'], dtype=dtype))
+        gp = U.euler_xyz_from_matrix(np.asarray(pixie['global_pose'], dtype=dtype))[0]
+    if kind in ('ExPose', 'combined'):
+        exp = U.euler_xyz_from_matrix(np.asarray(expose['body_pose'], dtype=dtype))
+        gp = U.euler_xyz_from_matrix(np.asarray(expose['global_orient'], dtype=dtype))[0]
+    if kind == 'PIXIE':
+        full = pix
+    elif kind == 'ExPose':
+        full = exp
+    elif kind == 'combined':
+        full = np.concatenate([exp[:19], pix[19:]])
+    else:
+        raise ValueError('unknown regression prior {}'.format(kind))
+    return full.reshape(-1).astype(dtype), gp.reshape(-1).astype(dtype)
+
+
+def camera_prior(cfg, focal, expose=None, pixie=None):
+    """-> (translation [3], centre [2]) or None when guess_init applies
+    (fit_single_frame.py:359-411)."""
+    kind = cfg.get('regression_prior')
+    if not cfg.get('use_camera_prior') or not kind:
+        return None
+    if kind in ('ExPose', 'combined'):
+        t = np.array(expose['transl'], dtype=np.float64).copy()
+        t[-1] /= (5000 / focal)
+        return t, np.asarray(expose['center'], dtype=np.float64)
+    if kind == 'PIXIE':
+        left, top, right, bottom = [float(v) for v in pixie['bbox']]
+        old = max(right - left, bottom - top)
+        cen = np.array([right - (right - left) / 2.0, bottom - (bottom - top) / 2.0])
+        size = int(old * 1.1)
+        cam = pixie['body_cam']
+        return np.array([cam[1], cam[2], 2 * focal / (cam[0] * size + 1e-9)]), cen
+    return None
+
+
+def guess_init_depth(joints3d, gt2d, edge_idxs, focal):
+    """fitting.guess_init (fitting.py:36-110): similar-triangles depth from the mean 3-D and
+    2-D edge lengths.  joints3d [B,K,3], gt2d [B,K,2] -> translation [B,3]."""
+    e = np.asarray(edge_idxs, dtype=np.int64).reshape(-1, 2)
+    d3 = joints3d[:, e[:, 0]] - joints3d[:, e[:, 1]]
+    d2 = gt2d[:, e[:, 0]] - gt2d[:, e[:, 1]]
+    l3 = np.sqrt((d3 ** 2).sum(-1))
+    l2 = np.sqrt((d2 ** 2).sum(-1))
+    est = focal * (l3.mean(axis=1) / l2.mean(axis=1))
+    t = np.zeros((joints3d.shape[0], 3), dtype=joints3d.dtype)
+    t[:, 2] = est
+    return t
+
+
+def flipped_orientation(go):
+    """Rodrigues(go) . R_y(pi) back to axis-angle (fit_single_frame.py:527-538)."""
+    R = U.rodrigues(go).dot(U.rodrigues([0.0, np.pi, 0.0]))
+    return U.inv_rodrigues(R)
+
+
+# ------------------------------------------------------------------------------ execution
+class FitResult(object):
+    """Per-batch output: ``results[b]`` is the reference's result dict of frame b
+    (fit_single_frame.py:644-660), ``vertices`` [B,V,3] the mesh written to vertices.ply."""
+
+    def __init__(self):
+        self.results = []
+        self.vertices = None
+        self.joints = None
+        self.loss = None
+        self.cam_loss = None
+        self.n_evals = None
+        self.flags = None
+        self.n_orient = None
+        self.params = None
+
+
+def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_verts=True,
+               body_mean_pose=None):
+    """Fits every frame of ``batch`` (an ``engine.FrameBatch``).
+
+    keypoints [B,K,3] (x, y, confidence) in the reference's row order; ``H``, ``W`` scalars or
+    [B]; ``cfg`` the flat config dict of ``cmd_parser.parse_config`` (same keys as the
+    reference's YAML files); ``expose`` / ``pixie`` lists of per-frame regression results.
+    """
+    import torch
+    B, K = batch.B, batch.model.K
+    L = batch.L
+    npd = batch.model.np_dtype
+    keypoints = np.asarray(keypoints, dtype=np.float64).reshape(B, K, 3)
+    H = np.broadcast_to(np.asarray(H, dtype=np.float64), (B,))
+    W = np.broadcast_to(np.asarray(W, dtype=np.float64), (B,))
+    fl = cfg.get('focal_length')
+    focal = np.sqrt(W ** 2 + H ** 2) if fl is None else np.broadcast_to(float(fl), (B,))
+    if cfg.get('interpenetration', False) and any(
+            w['coll_loss_weight'] > 0 for w in stage_weights(cfg)):
+        raise NotImplementedError('interpenetration term: not built yet (SURVEY.md 8a, a16)')
+    cam_stage, stages = make_stages(cfg, L)
+    jw, lowconf, init_mask = keypoint_masks(keypoints, cfg, base_joint_weights(cfg, K))
+
+    # --- initial parameters (fit_single_frame.py:209-274) ---
+    x = np.zeros((B, L.np), dtype=np.float64)
+    reg = None
+    if cfg.get('regression_prior'):
+        reg = np.zeros((B, L.n_pose), dtype=np.float64)
+        for b in range(B):
+            pose, go = regression_pose(cfg, None if expose is None else expose[b],
+                                       None if pixie is None else pixie[b], dtype=npd)
+            if cfg.get('use_vposer', False):
+                raise NotImplementedError('VPoser encode of the regression prior')
+            reg[b] = pose
+            x[b, L.off_pose:L.off_pose + L.n_pose] = pose
+            x[b, L.off_go:L.off_go + 3] = go
+    elif not cfg.get('use_vposer', False):
+        if body_mean_pose is not None:
+            x[:, L.off_pose:L.off_pose + L.n_pose] = np.asarray(body_mean_pose).reshape(1, -1)
+
+    # --- camera initialisation (fit_single_frame.py:359-411) ---
+    cam = np.zeros((B, N.SFX_CAM_STRIDE), dtype=np.float64)
+    cam[:, N_CAM_FX] = focal
+    cam[:, N_CAM_FY] = focal
+    cam[:, 4:13] = np.eye(3).reshape(-1)
+    cam[:, 13] = 1000.0 / H
+    need_guess = []
+    for b in range(B):
+        pr = camera_prior(cfg, focal[b], None if expose is None else expose[b],
+                          None if pixie is None else pixie[b])
+        if pr is None:
+            need_guess.append(b)
+            cam[b, 2:4] = (W[b] * 0.5, H[b] * 0.5)
+        else:
+            x[b, L.off_camt:L.off_camt + 3] = np.asarray(pr[0], dtype=npd)
+            cam[b, 2:4] = np.asarray(pr[1], dtype=npd)
+    h2d = batch.set_targets(keypoints, jw, lowconf, init_mask, cam, reg)
+    h2d += batch.set_params(x)
+    if need_guess:
+        _, _, j3 = batch.eval(cam_stage, want_joints=True)
+        t = guess_init_depth(j3.cpu().numpy().astype(np.float64), keypoints[:, :, :2],
+                             cfg.get('body_tri_idxs', [(5, 12), (2, 9)]), focal)
+        x[need_guess, L.off_camt:L.off_camt + 3] = t[need_guess].astype(npd)
+        h2d += batch.set_params(x)
+    cam[:, 14] = x[:, L.off_camt + 2].astype(npd)      # trans_estimation z
+    h2d += batch.set_targets(keypoints, jw, lowconf, init_mask, cam, reg)
+    batch.reset_counters()
+
+    # --- stage C: camera translation + global orientation (fit_single_frame.py:473-496) ---
+    cam_loss = batch.fit_stage(cam_stage)
+    after_cam = batch.get_params().astype(np.float64)
+    cam_loss = cam_loss.cpu().numpy()
+
+    # --- orientations (fit_single_frame.py:461-463, :527-551) ---
+    li, ri = cfg.get('left_shoulder_idx', 2), cfg.get('right_shoulder_idx', 5)
+    sh = np.sqrt(((keypoints[:, li, :2].astype(npd) - keypoints[:, ri, :2].astype(npd)) ** 2)
+                 .sum(-1))
+    both = np.flatnonzero(sh < cfg.get('side_view_thsh', 25.))
+
+    def start_params(flip, pose_from):
+        # body_model.reset_params(global_orient=orient, body_pose=pose_embedding): everything
+        # else restarts from zero; pose_embedding is NOT reset between orientations, the second
+        # orientation continues from the first one's fitted pose (fit_single_frame.py:546-551)
+        p = np.zeros_like(after_cam)
+        p[:, L.off_camt:L.off_camt + 3] = after_cam[:, L.off_camt:L.off_camt + 3]
+        p[:, L.off_pose:L.off_pose + L.n_pose] = pose_from[:, L.off_pose:L.off_pose + L.n_pose]
+        go = after_cam[:, L.off_go:L.off_go + 3]
+        if flip:
+            go = go.copy()
+            for b in both:
+                go[b] = flipped_orientation(go[b]).astype(np.float32)
+        p[:, L.off_go:L.off_go + 3] = go
+        return p
+
+    def run_stages(frame_ids):
+        final = None
+        for st in stages:
+            final = batch.fit_stage(st, frame_ids=frame_ids)
+        verts = joints = None
+        if return_verts:
+            verts, joints = batch.forward_mesh()
+        return final, verts, joints
+
+    batch.set_params(start_params(False, x))
+    loss0, verts, joints = run_stages(None)
+    params = batch.get_params()
+    loss = loss0.cpu().numpy().astype(np.float64)
+    n_orient = np.ones(B, dtype=np.int64)
+    if len(both):
+        ids = torch.as_tensor(both.astype(np.int32), device=batch.model.device)
+        p1 = start_params(True, params.astype(np.float64))
+        keep = params.copy()
+        batch.set_params(np.where(np.isin(np.arange(B), both)[:, None], p1, keep))
+        loss1, verts1, joints1 = run_stages(ids)
+        params1 = batch.get_params()
+        loss1 = loss1.cpu().numpy().astype(np.float64)
+        n_orient[both] = 2
+        for b in both:
+            # results[argmin loss] (fit_single_frame.py:662-668); the mesh written to
+            # vertices.ply is the LAST orientation's (fit_single_frame.py:671-676)
+            if not (loss[b] < loss1[b]):
+                params[b] = params1[b]
+                loss[b] = loss1[b]
+            if return_verts:
+                verts[b] = verts1[b]
+                joints[b] = joints1[b]
+        batch.set_params(params)
+
+    out = FitResult()
+    out.params = params
+    out.loss = loss
+    out.cam_loss = cam_loss
+    out.n_evals = batch.evals().cpu().numpy()
+    out.flags = batch.flags().cpu().numpy()
+    out.n_orient = n_orient
+    out.h2d_bytes = h2d
+    if return_verts:
+        out.vertices = verts.cpu().numpy()
+        out.joints = joints.cpu().numpy()
+    blocks = batch.blocks
+    for b in range(B):
+        r = {'camera_rotation': cam[b, 4:13].reshape(1, 3, 3).astype(npd),
+             'camera_translation': params[b, L.off_camt:L.off_camt + 3].reshape(1, 3).copy(),
+             'camera_center': cam[b, 2:4].reshape(1, 2).astype(npd),
+             'H': int(H[b]), 'W': int(W[b]), 'focal_length': float(focal[b])}
+        for name in ('betas', 'global_orient', 'left_hand_pose', 'right_hand_pose', 'jaw_pose',
+                     'leye_pose', 'reye_pose', 'expression'):
+            off, n = blocks[name]
+            r[name] = params[b, off:off + n].reshape(1, n).copy()
+        off, n = blocks['pose_embedding']
+        r['body_pose'] = params[b, off:off + n].reshape(1, n).copy()
+        out.results.append(r)
+    return out
+
+
+N_CAM_FX, N_CAM_FY = 0, 1

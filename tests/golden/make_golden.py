@@ -1,0 +1,330 @@
+"""Generates the committed fixtures under tests/golden/ by running the UNMODIFIED reference
+(``/root/reference/smplifyx``, imported in place through ``oracle/ref_bridge.py``) in the
+authoring container.  ``/root/reference`` does not exist on the GPU box, so the tests only
+read the ``.npz`` files this script wrote.
+
+    python tests/golden/make_golden.py            # all fixtures (about 2-3 minutes of CPU)
+
+Fixtures
+--------
+demo_inputs.npz      the reference's demo/ inputs for the two frames: blended keypoints
+                     [135,3] in reference row order (data_parser.py:57-104), image size, the
+                     ExPose / PIXIE regression results the combined prior reads
+                     (fit_single_frame.py:209-235, :370-401).  Inputs only, no code.
+ref_eval_<case>.npz  one closure evaluation of the reference (fitting.py:232-273): reference
+                     SMPLifyLoss / SMPLifyCameraInitLoss + reference PerspectiveCamera on the
+                     restated smplx forward; loss and gradients w.r.t. every parameter.
+ref_fit_02.npz       reference fit_single_frame end to end on demo frame 02 (combined
+                     regression prior, camera prior, 3 stages, lbfgsls, no interpenetration):
+                     result dict, final vertices, closure-evaluation count.
+ref_stage_*.npz      reference FittingMonitor.run_fitting on one stage from a fixed start.
+
+The SMPL-X model is the seeded synthetic one (``smplifyx_b200.synthetic``); the licensed model
+files are not available.
+"""
+import os
+import pickle
+import sys
+import tempfile
+import json
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_bridge, smplx_shim          # noqa: E402
+from smplifyx_b200 import synthetic                # noqa: E402
+from smplifyx_b200 import utils as U               # noqa: E402
+
+REF = ref_bridge.REF_ROOT
+FRAMES = ['02_cropped', '18_cropped']
+
+
+def cfg_combined():
+    """cfg_files/fit_smplx_combined_coco25.yaml with the switches of BASELINE config 1."""
+    from smplifyx_b200.cmd_parser import parse_config
+    cfg = parse_config(['-c', os.path.join(REF, 'cfg_files', 'fit_smplx_combined_coco25.yaml')])
+    cfg.pop('config')
+    cfg.update(interpenetration=False, visualize=False, interactive=False, use_cuda=False,
+               use_gender_classifier=False, gender='neutral', use_vposer=False)
+    return cfg
+
+
+def demo_inputs():
+    import cv2
+    import joblib
+    ref = ref_bridge.load()
+    out = {}
+    for fr in FRAMES:
+        kp = ref.data_parser.read_keypoints(
+            os.path.join(REF, 'demo', 'keypoints', fr + '_blended.json'),
+            use_hands=True, use_face=True, use_face_contour=True).keypoints
+        out[fr + '/keypoints'] = np.stack(kp)[0].astype(np.float32)
+        img = cv2.imread(os.path.join(REF, 'demo', 'images', fr + '.jpg'))
+        out[fr + '/HW'] = np.array(img.shape[:2], dtype=np.int64)
+        ex = np.load(os.path.join(REF, 'demo', 'ExPose_results', fr + '.jpg',
+                                  fr + '.jpg_params.npz'), allow_pickle=True)
+        for k in ['global_orient', 'body_pose', 'betas', 'expression', 'transl', 'center',
+                  'jaw_pose']:
+            out[fr + '/expose/' + k] = np.asarray(ex[k])
+        px = joblib.load(os.path.join(REF, 'demo', 'PIXIE_results', fr, fr + '_param.pkl'))
+        for k in ['body_pose', 'global_pose', 'body_cam', 'bbox']:
+            out[fr + '/pixie/' + k] = np.asarray(px[k])
+    np.savez_compressed(os.path.join(HERE, 'demo_inputs.npz'), **out)
+    return out
+
+
+def build_reference_objects(cfg, dtype=torch.float32, use_vposer=False):
+    """Body model (restated smplx), reference priors, reference joint weights."""
+    ref = ref_bridge.load()
+    md = synthetic.cached_smplx_like(0)
+    jm = U.smpl_to_annotation('smplx', use_hands=True, use_face=True,
+                              use_face_contour=cfg.get('use_face_contour', True),
+                              format=cfg.get('format', 'coco25'))
+    ref_jm = ref.utils.smpl_to_annotation('smplx', use_hands=True, use_face=True,
+                                          use_face_contour=cfg.get('use_face_contour', True),
+                                          format=cfg.get('format', 'coco25'))
+    assert np.array_equal(np.asarray(ref_jm), jm), 'joint map differs from the reference'
+    joint_mapper = ref.utils.JointMapper(jm.astype(np.int64))
+    body_model = smplx_shim.create(
+        model_data=md, joint_mapper=joint_mapper, create_body_pose=not use_vposer,
+        use_pca=cfg.get('use_pca', True), num_pca_comps=cfg.get('num_pca_comps', 12),
+        flat_hand_mean=cfg.get('flat_hand_mean', False), num_betas=cfg.get('num_betas', 10),
+        num_expression_coeffs=cfg.get('num_expression_coeffs', 10),
+        use_face_contour=cfg.get('use_face_contour', True), dtype=dtype)
+    args = dict(cfg)
+    args.pop('dtype', None)
+    pri = {}
+    mk = ref.prior.create_prior
+    pri['body_pose_prior'] = mk(prior_type=args.get('body_prior_type'), dtype=dtype, **args)
+    pri['jaw_prior'] = mk(prior_type=args.get('jaw_prior_type'), dtype=dtype, **args)
+    pri['expr_prior'] = mk(prior_type='l2', dtype=dtype, **args)
+    pri['left_hand_prior'] = mk(prior_type=args.get('left_hand_prior_type'), dtype=dtype, **args)
+    pri['right_hand_prior'] = mk(prior_type=args.get('right_hand_prior_type'), dtype=dtype, **args)
+    pri['shape_prior'] = mk(prior_type='l2', dtype=dtype, **args)
+    pri['angle_prior'] = mk(prior_type='angle', dtype=dtype)
+    nb = U.NUM_BODY_KEYPOINTS[cfg.get('format', 'coco25')]
+    jw = np.ones(nb + 2 * 20 + 2 + 51 + 17 * int(cfg.get('use_face_contour', True)),
+                 dtype=np.float32)
+    ign = cfg.get('joints_to_ign')
+    if ign is not None and -1 not in ign:
+        jw[ign] = 0
+    return body_model, pri, torch.tensor(jw, dtype=dtype).unsqueeze(0), jm
+
+
+class _Counter(object):
+    """Counts closure evaluations by wrapping body_model.forward."""
+
+    def __init__(self, bm):
+        self.n = 0
+        self.bm = bm
+        self.orig = bm.forward
+
+        def fwd(*a, **k):
+            self.n += 1
+            return self.orig(*a, **k)
+        bm.forward = fwd
+
+
+def ref_fit(frame='02_cropped', inputs=None, cfg=None, tag='ref_fit_02'):
+    ref = ref_bridge.load()
+    cfg = cfg or cfg_combined()
+    dtype = torch.float32
+    torch.manual_seed(0)
+    torch.set_num_threads(1)          # bit-stable reductions
+    body_model, pri, jw, _ = build_reference_objects(cfg, dtype)
+    H, W = [int(v) for v in inputs[frame + '/HW']]
+    focal = (W ** 2 + H ** 2) ** 0.5
+    args = dict(cfg)
+    camera = ref.camera.create_camera(focal_length_x=focal, focal_length_y=focal, dtype=dtype,
+                                      **args)
+    camera.rotation.requires_grad = False
+    args['focal_length'] = focal
+    expose = {k.split('/')[-1]: inputs[k] for k in inputs if k.startswith(frame + '/expose/')}
+    pixie = {k.split('/')[-1]: inputs[k] for k in inputs if k.startswith(frame + '/pixie/')}
+    kp = inputs[frame + '/keypoints'][None]
+    counter = _Counter(body_model)
+    tmp = tempfile.mkdtemp()
+    res_fn = os.path.join(tmp, '000.pkl')
+    for k in ('dtype', 'output_folder', 'result_folder'):
+        args.pop(k, None)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref.fit_single_frame.fit_single_frame(
+            np.zeros((H, W, 3), np.float32), kp, body_model=body_model, camera=camera,
+            joint_weights=jw.clone(), dtype=dtype, output_folder=tmp, result_folder=tmp,
+            out_img_fn=os.path.join(tmp, 'o.png'), result_fn=res_fn,
+            mesh_fn=os.path.join(tmp, 'o.obj'), img_name=frame, pixie_results=pixie,
+            expose_results=expose, pare_results=None, smplx_path='', curr_img_folder=tmp,
+            **pri, **args)
+    with open(res_fn, 'rb') as f:
+        result = pickle.load(f)
+    verts = np.load(os.path.join(tmp, 'vertices.ply.npy'))
+    out = {'result/' + k: np.asarray(v) for k, v in result.items()}
+    out['vertices'] = verts.astype(np.float32)
+    out['n_forward_calls'] = np.array(counter.n)
+    out['cfg_json'] = np.array(json.dumps({k: v for k, v in cfg.items()}))
+    np.savez_compressed(os.path.join(HERE, tag + '.npz'), **out)
+    print(tag, 'forward calls', counter.n)
+    return out
+
+
+def _rand_params(rng, n_hand=12, scale=1.0):
+    return dict(betas=rng.normal(size=(1, 10)) * scale,
+                global_orient=rng.normal(size=(1, 3)) * 0.3 * scale + np.array([[3.0, 0.1, -0.1]]),
+                left_hand_pose=rng.normal(size=(1, n_hand)) * 0.5 * scale,
+                right_hand_pose=rng.normal(size=(1, n_hand)) * 0.5 * scale,
+                jaw_pose=rng.normal(size=(1, 3)) * 0.1 * scale,
+                leye_pose=rng.normal(size=(1, 3)) * 0.1 * scale,
+                reye_pose=rng.normal(size=(1, 3)) * 0.1 * scale,
+                expression=rng.normal(size=(1, 10)) * scale,
+                pose_embedding=rng.normal(size=(1, 63)) * 0.2 * scale)
+
+
+def ref_eval(inputs, dtype=torch.float64, tag='f64'):
+    """One reference closure evaluation per loss kind at a random parameter point."""
+    ref = ref_bridge.load()
+    cfg = cfg_combined()
+    frame = '18_cropped'
+    body_model, pri, jw, _ = build_reference_objects(cfg, dtype)
+    rng = np.random.default_rng(7)
+    P = _rand_params(rng)
+    H, W = [int(v) for v in inputs[frame + '/HW']]
+    focal = (W ** 2 + H ** 2) ** 0.5
+    camera = ref.camera.create_camera(focal_length_x=focal, focal_length_y=focal, dtype=dtype)
+    with torch.no_grad():
+        camera.translation[:] = torch.tensor([[0.05, 0.25, 3.2]], dtype=dtype)
+        camera.center[:] = torch.tensor([[W * 0.5 + 3, H * 0.5 - 5]], dtype=dtype)
+    camera.rotation.requires_grad = False
+    camera.translation.requires_grad = True
+    kp = torch.tensor(inputs[frame + '/keypoints'][None], dtype=dtype)
+    gt, conf = kp[:, :, :2], kp[:, :, 2]
+    reg = torch.tensor(rng.normal(size=(1, 63)) * 0.2, dtype=dtype)
+    body_model.reset_params(**{k: v for k, v in P.items() if k != 'pose_embedding'})
+    emb = torch.tensor(P['pose_embedding'], dtype=dtype, requires_grad=True)
+    jw = jw.clone()
+    jw[:, 25:67] = 0.1
+    jw[:, 67:] = 2.0
+    low = [i for i in range(25) if float(conf[0, i]) < 0.2]
+    jw[:, low] = 0
+    out = {'jw': jw.numpy(), 'keypoints': kp.numpy()[0], 'reg_pose': reg.numpy(),
+           'cam_t': camera.translation.detach().numpy().copy(),
+           'center': camera.center.numpy().copy(), 'focal': np.array(focal),
+           'HW': np.array([H, W])}
+    for k, v in P.items():
+        out['param/' + k] = np.asarray(v)
+    weights = dict(data_weight=1000.0 / H, body_pose_weight=300.0, shape_weight=50.0,
+                   bending_prior_weight=3.17 * 300.0, hand_prior_weight=4.78,
+                   expr_prior_weight=5.0, jaw_prior_weight=[100.0, 1000.0, 1000.0],
+                   coll_loss_weight=0.0)
+    out['weights_json'] = np.array(json.dumps(weights))
+    for case, regression in (('l2', None), ('reg', reg)):
+        loss = ref.fitting.create_loss(
+            loss_type='smplify', rho=100, use_joints_conf=True, use_face=True, use_hands=True,
+            vposer=None, interpenetration=False, dtype=dtype, regression_pose=regression,
+            num_stages=3, **pri)
+        loss.reset_loss_weights({k: v for k, v in weights.items()})
+        for p in list(body_model.parameters()) + [emb, camera.translation]:
+            p.grad = None
+        o = body_model(return_verts=True, body_pose=emb, return_full_pose=True)
+        val = loss(o, camera=camera, gt_joints=gt, body_model_faces=None, joints_conf=conf,
+                   joint_weights=jw, pose_embedding=emb, use_vposer=False, stage=1)
+        val.backward()
+        out[case + '/loss'] = val.detach().numpy()
+        out[case + '/joints'] = o.joints.detach().numpy()[0]
+        if case == 'l2':
+            out['vertices'] = o.vertices.detach().numpy()[0]
+        for name, p in body_model.named_parameters():
+            if name != 'body_pose':
+                out[case + '/grad/' + name] = p.grad.numpy().copy()
+        out[case + '/grad/pose_embedding'] = emb.grad.numpy().copy()
+        out[case + '/grad/camera_translation'] = camera.translation.grad.numpy().copy()
+    # camera-init loss, both confidence modes
+    init_idxs = [i for i in cfg['init_joints_idxs'] if i not in low]
+    out['init_idxs'] = np.array(init_idxs)
+    for case, use_conf in (('cam', False), ('camconf', True)):
+        closs = ref.fitting.create_loss(
+            loss_type='camera_init', trans_estimation=torch.tensor([[0., 0., 3.5]], dtype=dtype),
+            init_joints_idxs=torch.tensor(init_idxs), depth_loss_weight=100.0,
+            camera_mode='moving', dtype=dtype, use_conf=use_conf, joints_conf=conf)
+        closs.reset_loss_weights({'data_weight': 1000.0 / H})
+        for p in list(body_model.parameters()) + [emb, camera.translation]:
+            p.grad = None
+        o = body_model(return_verts=False, body_pose=emb, return_full_pose=False)
+        val = closs(o, camera, gt, body_model=body_model, joints_conf=conf)
+        val.backward()
+        out[case + '/loss'] = val.detach().numpy()
+        out[case + '/grad/global_orient'] = body_model.global_orient.grad.numpy().copy()
+        out[case + '/grad/camera_translation'] = camera.translation.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, 'ref_eval_{}.npz'.format(tag)), **out)
+    print('ref_eval', tag, {k: float(out[k]) for k in out if k.endswith('/loss')})
+    return out
+
+
+def ref_stage(inputs, dtype=torch.float64, tag='f64'):
+    """Reference run_fitting + reference LBFGS on one body stage from the ref_eval start."""
+    ref = ref_bridge.load()
+    ev = dict(np.load(os.path.join(HERE, 'ref_eval_{}.npz'.format(tag))))
+    cfg = cfg_combined()
+    body_model, pri, _, _ = build_reference_objects(cfg, dtype)
+    H, W = [int(v) for v in ev['HW']]
+    focal = float(ev['focal'])
+    camera = ref.camera.create_camera(focal_length_x=focal, focal_length_y=focal, dtype=dtype)
+    with torch.no_grad():
+        camera.translation[:] = torch.tensor(ev['cam_t'], dtype=dtype)
+        camera.center[:] = torch.tensor(ev['center'], dtype=dtype)
+    camera.rotation.requires_grad = False
+    camera.translation.requires_grad = False
+    kp = torch.tensor(ev['keypoints'][None], dtype=dtype)
+    gt, conf = kp[:, :, :2], kp[:, :, 2]
+    jw = torch.tensor(ev['jw'], dtype=dtype)
+    P = {k[6:]: ev[k] for k in ev if k.startswith('param/')}
+    body_model.reset_params(**{k: v for k, v in P.items() if k != 'pose_embedding'})
+    emb = torch.tensor(P['pose_embedding'], dtype=dtype, requires_grad=True)
+    weights = json.loads(str(ev['weights_json']))
+    loss = ref.fitting.create_loss(
+        loss_type='smplify', rho=100, use_joints_conf=True, use_face=True, use_hands=True,
+        vposer=None, interpenetration=False, dtype=dtype,
+        regression_pose=torch.tensor(ev['reg_pose'], dtype=dtype), num_stages=3, **pri)
+    loss.reset_loss_weights(weights)
+    counter = _Counter(body_model)
+    params = [p for p in body_model.parameters() if p.requires_grad] + [emb]
+    import warnings
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        with ref.fitting.FittingMonitor(batch_size=1, visualize=False, maxiters=30, ftol=1e-9,
+                                        gtol=1e-9, model_type='smplx') as monitor:
+            opt, cg = ref.optim_factory.create_optimizer(params, optim_type='lbfgsls', lr=1.0,
+                                                         maxiters=30)
+            closure = monitor.create_fitting_closure(
+                opt, body_model, camera=camera, gt_joints=gt, joints_conf=conf,
+                joint_weights=jw, loss=loss, create_graph=cg, use_vposer=False, vposer=None,
+                pose_embedding=emb, return_verts=True, return_full_pose=True)
+            final = monitor.run_fitting(opt, closure, params, body_model, pose_embedding=emb,
+                                        vposer=None, use_vposer=False, stage=1)
+    out['final_loss'] = np.array(final)
+    out['n_forward_calls'] = np.array(counter.n)
+    for name, p in body_model.named_parameters():
+        out['param/' + name] = p.detach().numpy().copy()
+    out['param/pose_embedding'] = emb.detach().numpy().copy()
+    with torch.no_grad():
+        o = body_model(return_verts=True, body_pose=emb)
+    out['vertices'] = o.vertices.numpy()[0].astype(np.float32)
+    out['joints'] = o.joints.numpy()[0]
+    np.savez_compressed(os.path.join(HERE, 'ref_stage_{}.npz'.format(tag)), **out)
+    print('ref_stage', tag, 'final', final, 'forward calls', counter.n)
+
+
+if __name__ == '__main__':
+    if not ref_bridge.available():
+        raise SystemExit('reference tree not found at ' + REF)
+    inp = demo_inputs()
+    ref_eval(inp, torch.float64, 'f64')
+    ref_eval(inp, torch.float32, 'f32')
+    ref_stage(inp, torch.float64, 'f64')
+    ref_fit('02_cropped', inp)

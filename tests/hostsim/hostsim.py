@@ -69,6 +69,18 @@ class HostSim(object):
         return dict(loss=float(loss[0]), grad=grad, joints=joints, params=params,
                     n_evals=ne.value, flags=fl.value)
 
+    def trace(self, cap=100000):
+        """Loss of every closure evaluation since the last call."""
+        buf = np.zeros(cap)
+        n = self.lib.hs_trace(buf.ctypes.data_as(C.c_void_p), cap)
+        return buf[:min(n, cap)].copy()
+
+    def steps(self, cap=100000):
+        """Step length of every line-search probe since the last call."""
+        buf = np.zeros(cap)
+        n = self.lib.hs_steps(buf.ctypes.data_as(C.c_void_p), cap)
+        return buf[:min(n, cap)].copy()
+
     def eval(self, stage, params, gt, conf, jw, cam, lowconf=None, init_mask=None, reg_pose=None):
         return self._run(stage, 0, params, gt, conf, jw, lowconf, init_mask, cam, reg_pose)
 

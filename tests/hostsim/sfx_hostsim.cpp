@@ -7,6 +7,10 @@
 #include <string>
 #include <vector>
 
+static std::vector<double> g_trace;
+#define SFX_TRACE(v) g_trace.push_back(v)
+static std::vector<double> g_steps;
+#define SFX_TRACE_STEP(t) g_steps.push_back(t)
 #include "../../smplify-x-partial_b200/csrc/sfx_model_prep.h"
 
 using namespace sfx;
@@ -51,6 +55,19 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
 }
 
 extern "C" {
+int hs_trace(double* out, int cap) {
+    int n = (int)g_trace.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = g_trace[i];
+    g_trace.clear();
+    return n;
+}
+
+int hs_steps(double* out, int cap) {
+    int n = (int)g_steps.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = g_steps[i];
+    g_steps.clear();
+    return n;
+}
 
 void* hs_model_create(const sfx_model_desc* desc, char* err, int errlen) {
     SimHandle* h = new SimHandle();
