@@ -108,6 +108,22 @@ int sfx_eval(sfx_batch* b, const SfxStage* stage, void* loss_dev, void* grad_dev
 int sfx_fit_stage(sfx_batch* b, const SfxStage* stage, const int32_t* frame_ids_dev,
                   int32_t n_ids, void* final_loss_dev, void* stream);
 
+/* Orientation bookkeeping of fit_single_frame.py:527-551 on the device, between the camera
+ * stage and the body stages.  Both stand in for body_model.reset_params(global_orient=orient,
+ * body_pose=pose_embedding): every block except the orientation, the pose embedding and the
+ * camera translation restarts from zero.
+ *   flip = 0: remembers each selected frame's camera-stage orientation and starts from it;
+ *   flip = 1: snapshots the first orientation's fitted parameters and loss, then starts from
+ *             Rodrigues(saved orientation) . R_y(pi) (cv2.Rodrigues both ways, float32 result). */
+int sfx_batch_begin_orientation(sfx_batch* b, int32_t flip, const int32_t* frame_ids_dev,
+                                int32_t n_ids, void* stream);
+/* results[argmin loss] (fit_single_frame.py:662-668): restores the snapshot of a frame when the
+ * first orientation's loss is strictly lower than the second's. */
+int sfx_batch_select_orientation(sfx_batch* b, const int32_t* frame_ids_dev, int32_t n_ids,
+                                 void* stream);
+/* run_fitting's return value of the last stage per frame ([B], batch dtype, device). */
+void* sfx_batch_final_loss_dev(sfx_batch* b);
+
 /* body_model(return_verts=True) for every frame (fit_single_frame.py:611): full-mesh
  * vertices [B,V,3] and mapped joints [B,K,3] from the current parameters. */
 int sfx_forward_mesh(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream);

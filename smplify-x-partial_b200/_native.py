@@ -14,6 +14,7 @@ SFX_MAX_BLOCKS = 12
 SFX_NP_MAX = 192
 SFX_KMAX = 160
 SFX_CAM_STRIDE = 16
+SFX_CAM_FX, SFX_CAM_FY, SFX_CAM_CX, SFX_CAM_CY, SFX_CAM_R, SFX_CAM_DW, SFX_CAM_TZ = 0, 1, 2, 3, 4, 13, 14
 
 LOSS_SMPLIFY, LOSS_CAMERA_INIT = 0, 1
 OPT_LBFGSLS, OPT_ADAM = 0, 1
@@ -238,6 +239,10 @@ def load_library(path=None):
     lib.sfx_eval.argtypes = [vp, C.POINTER(SfxStage), vp, vp, vp, vp]
     lib.sfx_fit_stage.argtypes = [vp, C.POINTER(SfxStage), vp, i32, vp, vp]
     lib.sfx_forward_mesh.argtypes = [vp, vp, vp, vp]
+    lib.sfx_batch_begin_orientation.argtypes = [vp, i32, vp, i32, vp]
+    lib.sfx_batch_select_orientation.argtypes = [vp, vp, i32, vp]
+    lib.sfx_batch_final_loss_dev.argtypes = [vp]
+    lib.sfx_batch_final_loss_dev.restype = vp
     lib.sfx_batch_evals_dev.argtypes = [vp]
     lib.sfx_batch_evals_dev.restype = vp
     lib.sfx_batch_flags_dev.argtypes = [vp]

@@ -144,6 +144,96 @@ mesh_coef_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__
     for (int i = threadIdx.x; i < SFX_KPAD; i += blockDim.x) Cout[(size_t)f * SFX_KPAD + i] = S.c[i];
 }
 
+
+// ---- orientation bookkeeping between the camera stage and the body stages -------------------
+// cv2.Rodrigues both ways, in double (reference fit_single_frame.py:527-538 runs it on the host)
+__device__ void cv_rodrigues(const double* r, double* R) {
+    double th = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    if (th < 2.220446049250313e-16) {
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        return;
+    }
+    double x = r[0] / th, y = r[1] / th, z = r[2] / th, c = cos(th), s = sin(th), c1 = 1.0 - c;
+    R[0] = c + c1 * x * x;     R[1] = c1 * x * y - s * z; R[2] = c1 * x * z + s * y;
+    R[3] = c1 * x * y + s * z; R[4] = c + c1 * y * y;     R[5] = c1 * y * z - s * x;
+    R[6] = c1 * x * z - s * y; R[7] = c1 * y * z + s * x; R[8] = c + c1 * z * z;
+}
+__device__ void cv_inv_rodrigues(const double* R, double* r) {
+    double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+    double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = (R[0] + R[4] + R[8] - 1.0) * 0.5;
+    c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+    double th = acos(c);
+    if (s < 1e-5) {
+        if (c > 0) { r[0] = r[1] = r[2] = 0; return; }
+        double t = (R[0] + 1) * 0.5;
+        double x = sqrt(t > 0 ? t : 0.0);
+        t = (R[4] + 1) * 0.5;
+        double y = sqrt(t > 0 ? t : 0.0) * (R[1] < 0 ? -1.0 : 1.0);
+        t = (R[8] + 1) * 0.5;
+        double z = sqrt(t > 0 ? t : 0.0) * (R[2] < 0 ? -1.0 : 1.0);
+        if (fabs(x) < fabs(y) && fabs(x) < fabs(z) && ((R[5] > 0) != (y * z > 0))) z = -z;
+        double k = th / sqrt(x * x + y * y + z * z);
+        r[0] = x * k; r[1] = y * k; r[2] = z * k;
+        return;
+    }
+    double k = th / (2 * s);
+    r[0] = rx * k; r[1] = ry * k; r[2] = rz * k;
+}
+
+// body_model.reset_params(global_orient=orient, body_pose=pose_embedding)
+// (fit_single_frame.py:546-551): every block except the orientation, the pose embedding and the
+// camera translation restarts from zero.  flip = 0 remembers the camera-stage orientation;
+// flip = 1 snapshots the first orientation's result and starts from Rodrigues(saved).R_y(pi).
+template <typename T>
+__global__ void begin_orientation_kernel(BatchView<T> Bv, int flip, T* go_saved, T* params_alt,
+                                         T* loss_alt) {
+    const int f = Bv.frame_ids ? Bv.frame_ids[blockIdx.x] : (int)blockIdx.x;
+    const SfxLayout& L = Bv.lay;
+    T* x = Bv.params + (size_t)f * L.np;
+    if (flip) {
+        for (int i = threadIdx.x; i < L.np; i += blockDim.x) params_alt[(size_t)f * L.np + i] = x[i];
+        if (threadIdx.x == 0) loss_alt[f] = Bv.final_loss[f];
+    } else if (threadIdx.x < 3) {
+        go_saved[3 * f + threadIdx.x] = x[L.off_go + threadIdx.x];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L.np; i += blockDim.x) {
+        const bool keep = (i >= L.off_go && i < L.off_go + 3) ||
+                          (i >= L.off_pose && i < L.off_pose + L.n_pose) ||
+                          (i >= L.off_camt && i < L.off_camt + 3);
+        if (!keep) x[i] = 0;
+    }
+    if (threadIdx.x == 0) {
+        if (flip) {
+            double r[3] = {(double)go_saved[3 * f], (double)go_saved[3 * f + 1], (double)go_saved[3 * f + 2]};
+            const double ry[3] = {0.0, 3.14159265358979323846, 0.0};
+            double Ra[9], Rb[9], Rc[9], out[3];
+            cv_rodrigues(r, Ra);
+            cv_rodrigues(ry, Rb);
+            mat3_mul(Ra, Rb, Rc);
+            cv_inv_rodrigues(Rc, out);
+            for (int k = 0; k < 3; ++k) x[L.off_go + k] = (T)(float)out[k];   // torch.tensor(.., float32)
+        } else {
+            for (int k = 0; k < 3; ++k) x[L.off_go + k] = go_saved[3 * f + k];
+        }
+    }
+}
+
+// results[argmin loss] (fit_single_frame.py:662-668): first orientation wins only if its loss
+// is strictly lower.
+template <typename T>
+__global__ void select_orientation_kernel(BatchView<T> Bv, const T* params_alt, const T* loss_alt) {
+    const int f = Bv.frame_ids ? Bv.frame_ids[blockIdx.x] : (int)blockIdx.x;
+    const SfxLayout& L = Bv.lay;
+    if (loss_alt[f] < Bv.final_loss[f]) {
+        for (int i = threadIdx.x; i < L.np; i += blockDim.x)
+            Bv.params[(size_t)f * L.np + i] = params_alt[(size_t)f * L.np + i];
+        __syncthreads();
+        if (threadIdx.x == 0) Bv.final_loss[f] = loss_alt[f];
+    }
+}
+
 // ------------------------------------------------------------------------------ handles
 struct DevBuf {
     void* p = nullptr;
@@ -216,7 +306,7 @@ struct sfx_batch {
     SfxLayout lay;
     size_t es = 4;        // element size of the batch dtype
     DevBuf params, gt, conf, jw, lowconf, init_mask, cam, reg_pose, hist_s, hist_y, final_loss,
-        n_evals, flags, Acoef, Ccoef, vposed;
+        n_evals, flags, Acoef, Ccoef, vposed, go_saved, params_alt, loss_alt;
     bool has_reg = false;
     std::vector<unsigned char> stage_host;     // host staging for set_targets
     template <typename T>
@@ -303,6 +393,9 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     ALLOC(Acoef, (size_t)B * SFX_NJ * 12 * es);
     ALLOC(Ccoef, (size_t)mesh_padded_frames(B) * SFX_KPAD * es);
     ALLOC(vposed, (size_t)mesh_padded_frames(B) * 3 * m->V * es);
+    ALLOC(go_saved, (size_t)B * 3 * es);
+    ALLOC(params_alt, (size_t)B * b->lay.np * es);
+    ALLOC(loss_alt, (size_t)B * es);
 #undef ALLOC
     *out = b;
     return SFX_OK;
@@ -456,6 +549,42 @@ int sfx_fit_stage(sfx_batch* b, const SfxStage* st, const int32_t* frame_ids_dev
     CUDA_TRY(cudaGetLastError());
     return SFX_OK;
 }
+
+int sfx_batch_begin_orientation(sfx_batch* b, int32_t flip, const int32_t* frame_ids_dev,
+                                int32_t n_ids, void* stream) {
+    if (!b) return fail(SFX_ERR_ARG, "null argument");
+    const int grid = frame_ids_dev ? n_ids : b->B;
+    if (grid < 1) return SFX_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (b->m->use_double)
+        begin_orientation_kernel<double><<<grid, 128, 0, s>>>(
+            b->view<double>(frame_ids_dev), flip, (double*)b->go_saved.p, (double*)b->params_alt.p,
+            (double*)b->loss_alt.p);
+    else
+        begin_orientation_kernel<float><<<grid, 128, 0, s>>>(
+            b->view<float>(frame_ids_dev), flip, (float*)b->go_saved.p, (float*)b->params_alt.p,
+            (float*)b->loss_alt.p);
+    CUDA_TRY(cudaGetLastError());
+    return SFX_OK;
+}
+
+int sfx_batch_select_orientation(sfx_batch* b, const int32_t* frame_ids_dev, int32_t n_ids,
+                                 void* stream) {
+    if (!b) return fail(SFX_ERR_ARG, "null argument");
+    const int grid = frame_ids_dev ? n_ids : b->B;
+    if (grid < 1) return SFX_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (b->m->use_double)
+        select_orientation_kernel<double><<<grid, 128, 0, s>>>(
+            b->view<double>(frame_ids_dev), (const double*)b->params_alt.p, (const double*)b->loss_alt.p);
+    else
+        select_orientation_kernel<float><<<grid, 128, 0, s>>>(
+            b->view<float>(frame_ids_dev), (const float*)b->params_alt.p, (const float*)b->loss_alt.p);
+    CUDA_TRY(cudaGetLastError());
+    return SFX_OK;
+}
+
+void* sfx_batch_final_loss_dev(sfx_batch* b) { return b ? b->final_loss.p : nullptr; }
 
 int sfx_forward_mesh(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream) {
     if (!b || !vertices_dev) return fail(SFX_ERR_ARG, "null argument");

@@ -170,6 +170,24 @@ class FrameBatch(object):
                                                         _stream()))
         return verts, joints
 
+    def begin_orientation(self, flip, frame_ids=None):
+        """reset_params(global_orient=orient, body_pose=pose_embedding) on the device
+        (fit_single_frame.py:546-551); ``flip`` starts from the 180-degree rotated orientation."""
+        n = 0 if frame_ids is None else int(frame_ids.numel())
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_batch_begin_orientation(
+                self.h, int(bool(flip)), _ptr(frame_ids), n, _stream()))
+
+    def select_orientation(self, frame_ids):
+        """Keeps, per frame, the orientation with the lower final loss."""
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_batch_select_orientation(
+                self.h, _ptr(frame_ids), int(frame_ids.numel()), _stream()))
+
+    def final_loss(self):
+        ptr = self.lib.sfx_batch_final_loss_dev(self.h)
+        return _wrap(ptr, (self.B,), self.model.dtype, self.model.device, self)
+
     def evals(self):
         ptr = self.lib.sfx_batch_evals_dev(self.h)
         return _wrap(ptr, (self.B,), torch.int32, self.model.device, self)

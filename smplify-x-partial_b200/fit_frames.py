@@ -218,161 +218,147 @@ class FitResult(object):
 
     def __init__(self):
         self.results = []
-        self.vertices = None
-        self.joints = None
-        self.loss = None
-        self.cam_loss = None
-        self.n_evals = None
-        self.flags = None
-        self.n_orient = None
-        self.params = None
+        self.vertices = self.joints = self.loss = self.cam_loss = None
+        self.n_evals = self.flags = self.n_orient = self.params = None
+        self.h2d_bytes = self.d2h_bytes = 0
 
 
-def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_verts=True,
-               body_mean_pose=None):
-    """Fits every frame of ``batch`` (an ``engine.FrameBatch``).
+class FitPlan(object):
+    """Host-side plan of one batch: initial parameters, targets, stage list, which frames get
+    the second (flipped) orientation.  Pure numpy; built without touching the device."""
 
-    keypoints [B,K,3] (x, y, confidence) in the reference's row order; ``H``, ``W`` scalars or
-    [B]; ``cfg`` the flat config dict of ``cmd_parser.parse_config`` (same keys as the
-    reference's YAML files); ``expose`` / ``pixie`` lists of per-frame regression results.
-    """
-    import torch
-    B, K = batch.B, batch.model.K
-    L = batch.L
-    npd = batch.model.np_dtype
-    keypoints = np.asarray(keypoints, dtype=np.float64).reshape(B, K, 3)
-    H = np.broadcast_to(np.asarray(H, dtype=np.float64), (B,))
-    W = np.broadcast_to(np.asarray(W, dtype=np.float64), (B,))
-    fl = cfg.get('focal_length')
-    focal = np.sqrt(W ** 2 + H ** 2) if fl is None else np.broadcast_to(float(fl), (B,))
-    if cfg.get('interpenetration', False) and any(
-            w['coll_loss_weight'] > 0 for w in stage_weights(cfg)):
-        raise NotImplementedError('interpenetration term: not built yet (SURVEY.md 8a, a16)')
-    cam_stage, stages = make_stages(cfg, L)
-    jw, lowconf, init_mask = keypoint_masks(keypoints, cfg, base_joint_weights(cfg, K))
-
-    # --- initial parameters (fit_single_frame.py:209-274) ---
-    x = np.zeros((B, L.np), dtype=np.float64)
-    reg = None
-    if cfg.get('regression_prior'):
-        reg = np.zeros((B, L.n_pose), dtype=np.float64)
-        for b in range(B):
-            pose, go = regression_pose(cfg, None if expose is None else expose[b],
-                                       None if pixie is None else pixie[b], dtype=npd)
+    def __init__(self, L, K, keypoints, H, W, cfg, expose=None, pixie=None, body_mean_pose=None,
+                 np_dtype=np.float32):
+        B = keypoints.shape[0]
+        self.B, self.K, self.L, self.cfg = B, K, L, cfg
+        npd = self.np_dtype = np_dtype
+        self.keypoints = keypoints = np.asarray(keypoints, dtype=np.float64).reshape(B, K, 3)
+        self.H = H = np.broadcast_to(np.asarray(H, dtype=np.float64), (B,))
+        self.W = W = np.broadcast_to(np.asarray(W, dtype=np.float64), (B,))
+        fl = cfg.get('focal_length')
+        self.focal = focal = (np.sqrt(W ** 2 + H ** 2) if fl is None
+                              else np.broadcast_to(float(fl), (B,)))
+        if cfg.get('interpenetration', False) and any(
+                w['coll_loss_weight'] > 0 for w in stage_weights(cfg)):
+            raise NotImplementedError('interpenetration term: not built yet (SURVEY.md 8a, a16)')
+        self.cam_stage, self.stages = make_stages(cfg, L)
+        self.jw, self.lowconf, self.init_mask = keypoint_masks(
+            keypoints, cfg, base_joint_weights(cfg, K))
+        # --- initial parameters (fit_single_frame.py:209-274) ---
+        x = np.zeros((B, L.np), dtype=np.float64)
+        self.reg = None
+        if cfg.get('regression_prior'):
             if cfg.get('use_vposer', False):
                 raise NotImplementedError('VPoser encode of the regression prior')
-            reg[b] = pose
-            x[b, L.off_pose:L.off_pose + L.n_pose] = pose
-            x[b, L.off_go:L.off_go + 3] = go
-    elif not cfg.get('use_vposer', False):
-        if body_mean_pose is not None:
+            self.reg = np.zeros((B, L.n_pose), dtype=np.float64)
+            for b in range(B):
+                pose, go = regression_pose(cfg, None if expose is None else expose[b],
+                                           None if pixie is None else pixie[b], dtype=npd)
+                self.reg[b] = pose
+                x[b, L.off_pose:L.off_pose + L.n_pose] = pose
+                x[b, L.off_go:L.off_go + 3] = go
+        elif not cfg.get('use_vposer', False) and body_mean_pose is not None:
             x[:, L.off_pose:L.off_pose + L.n_pose] = np.asarray(body_mean_pose).reshape(1, -1)
+        # --- camera initialisation (fit_single_frame.py:359-411) ---
+        cam = np.zeros((B, N.SFX_CAM_STRIDE), dtype=np.float64)
+        cam[:, N.SFX_CAM_FX] = focal
+        cam[:, N.SFX_CAM_FY] = focal
+        cam[:, N.SFX_CAM_R:N.SFX_CAM_R + 9] = np.eye(3).reshape(-1)
+        cam[:, N.SFX_CAM_DW] = 1000.0 / H
+        self.need_guess = []
+        for b in range(B):
+            pr = camera_prior(cfg, focal[b], None if expose is None else expose[b],
+                              None if pixie is None else pixie[b])
+            if pr is None:
+                self.need_guess.append(b)
+                cam[b, 2:4] = (W[b] * 0.5, H[b] * 0.5)
+            else:
+                x[b, L.off_camt:L.off_camt + 3] = np.asarray(pr[0], dtype=npd)
+                cam[b, 2:4] = np.asarray(pr[1], dtype=npd)
+        cam[:, N.SFX_CAM_TZ] = x[:, L.off_camt + 2]
+        self.x0, self.cam = x, cam
+        # --- orientations (fit_single_frame.py:461-463): decided by the 2-D shoulders alone ---
+        li, ri = cfg.get('left_shoulder_idx', 2), cfg.get('right_shoulder_idx', 5)
+        kp32 = keypoints[:, :, :2].astype(npd)
+        sh = np.sqrt(((kp32[:, li] - kp32[:, ri]) ** 2).sum(-1))
+        self.flip_ids = np.flatnonzero(sh < cfg.get('side_view_thsh', 25.)).astype(np.int32)
 
-    # --- camera initialisation (fit_single_frame.py:359-411) ---
-    cam = np.zeros((B, N.SFX_CAM_STRIDE), dtype=np.float64)
-    cam[:, N_CAM_FX] = focal
-    cam[:, N_CAM_FY] = focal
-    cam[:, 4:13] = np.eye(3).reshape(-1)
-    cam[:, 13] = 1000.0 / H
-    need_guess = []
-    for b in range(B):
-        pr = camera_prior(cfg, focal[b], None if expose is None else expose[b],
-                          None if pixie is None else pixie[b])
-        if pr is None:
-            need_guess.append(b)
-            cam[b, 2:4] = (W[b] * 0.5, H[b] * 0.5)
-        else:
-            x[b, L.off_camt:L.off_camt + 3] = np.asarray(pr[0], dtype=npd)
-            cam[b, 2:4] = np.asarray(pr[1], dtype=npd)
-    h2d = batch.set_targets(keypoints, jw, lowconf, init_mask, cam, reg)
-    h2d += batch.set_params(x)
-    if need_guess:
-        _, _, j3 = batch.eval(cam_stage, want_joints=True)
-        t = guess_init_depth(j3.cpu().numpy().astype(np.float64), keypoints[:, :, :2],
-                             cfg.get('body_tri_idxs', [(5, 12), (2, 9)]), focal)
-        x[need_guess, L.off_camt:L.off_camt + 3] = t[need_guess].astype(npd)
-        h2d += batch.set_params(x)
-    cam[:, 14] = x[:, L.off_camt + 2].astype(npd)      # trans_estimation z
-    h2d += batch.set_targets(keypoints, jw, lowconf, init_mask, cam, reg)
+
+def upload(batch, plan):
+    """Host -> device copies of one batch (async on the current stream); returns the byte count."""
+    import torch
+    n = batch.set_targets(plan.keypoints, plan.jw, plan.lowconf, plan.init_mask, plan.cam, plan.reg)
+    n += batch.set_params(plan.x0)
+    if plan.need_guess:
+        # guess_init needs the model joints at the initial parameters (fitting.py:36-110)
+        L = plan.L
+        _, _, j3 = batch.eval(plan.cam_stage, want_joints=True)
+        t = guess_init_depth(j3.cpu().numpy().astype(np.float64), plan.keypoints[:, :, :2],
+                             plan.cfg.get('body_tri_idxs', [(5, 12), (2, 9)]), plan.focal)
+        g = plan.need_guess
+        plan.x0[g, L.off_camt:L.off_camt + 3] = t[g].astype(plan.np_dtype)
+        plan.cam[:, N.SFX_CAM_TZ] = plan.x0[:, L.off_camt + 2]
+        n += batch.set_targets(plan.keypoints, plan.jw, plan.lowconf, plan.init_mask, plan.cam,
+                               plan.reg)
+        n += batch.set_params(plan.x0)
+    plan.flip_dev = None
+    if len(plan.flip_ids):
+        plan.flip_dev = torch.as_tensor(plan.flip_ids, device=batch.model.device)
+        n += plan.flip_ids.nbytes
     batch.reset_counters()
+    return n
 
-    # --- stage C: camera translation + global orientation (fit_single_frame.py:473-496) ---
-    cam_loss = batch.fit_stage(cam_stage)
-    after_cam = batch.get_params().astype(np.float64)
-    cam_loss = cam_loss.cpu().numpy()
 
-    # --- orientations (fit_single_frame.py:461-463, :527-551) ---
-    li, ri = cfg.get('left_shoulder_idx', 2), cfg.get('right_shoulder_idx', 5)
-    sh = np.sqrt(((keypoints[:, li, :2].astype(npd) - keypoints[:, ri, :2].astype(npd)) ** 2)
-                 .sum(-1))
-    both = np.flatnonzero(sh < cfg.get('side_view_thsh', 25.))
+def run(batch, plan, return_verts=True):
+    """The whole multi-stage fit as a fixed sequence of launches on the current stream; nothing
+    in here synchronises with the host.  Returns (cam_loss, verts, joints, n_launches)."""
+    launches = 0
+    cam_loss = batch.fit_stage(plan.cam_stage)                 # stage C (:473-496)
+    batch.begin_orientation(False)                             # reset_params (:546-551)
+    launches += 2
+    for st in plan.stages:
+        batch.fit_stage(st)
+        launches += 1
+    if plan.flip_dev is not None:
+        batch.begin_orientation(True, plan.flip_dev)
+        launches += 1
+        for st in plan.stages:
+            batch.fit_stage(st, frame_ids=plan.flip_dev)
+            launches += 1
+    verts = joints = None
+    if return_verts:
+        # body_model(return_verts=True) after the LAST orientation (:611, :671-676)
+        verts, joints = batch.forward_mesh()
+        launches += 4
+    if plan.flip_dev is not None:
+        batch.select_orientation(plan.flip_dev)                # results[argmin] (:662-668)
+        launches += 1
+    return cam_loss, verts, joints, launches
 
-    def start_params(flip, pose_from):
-        # body_model.reset_params(global_orient=orient, body_pose=pose_embedding): everything
-        # else restarts from zero; pose_embedding is NOT reset between orientations, the second
-        # orientation continues from the first one's fitted pose (fit_single_frame.py:546-551)
-        p = np.zeros_like(after_cam)
-        p[:, L.off_camt:L.off_camt + 3] = after_cam[:, L.off_camt:L.off_camt + 3]
-        p[:, L.off_pose:L.off_pose + L.n_pose] = pose_from[:, L.off_pose:L.off_pose + L.n_pose]
-        go = after_cam[:, L.off_go:L.off_go + 3]
-        if flip:
-            go = go.copy()
-            for b in both:
-                go[b] = flipped_orientation(go[b]).astype(np.float32)
-        p[:, L.off_go:L.off_go + 3] = go
-        return p
 
-    def run_stages(frame_ids):
-        final = None
-        for st in stages:
-            final = batch.fit_stage(st, frame_ids=frame_ids)
-        verts = joints = None
-        if return_verts:
-            verts, joints = batch.forward_mesh()
-        return final, verts, joints
-
-    batch.set_params(start_params(False, x))
-    loss0, verts, joints = run_stages(None)
-    params = batch.get_params()
-    loss = loss0.cpu().numpy().astype(np.float64)
-    n_orient = np.ones(B, dtype=np.int64)
-    if len(both):
-        ids = torch.as_tensor(both.astype(np.int32), device=batch.model.device)
-        p1 = start_params(True, params.astype(np.float64))
-        keep = params.copy()
-        batch.set_params(np.where(np.isin(np.arange(B), both)[:, None], p1, keep))
-        loss1, verts1, joints1 = run_stages(ids)
-        params1 = batch.get_params()
-        loss1 = loss1.cpu().numpy().astype(np.float64)
-        n_orient[both] = 2
-        for b in both:
-            # results[argmin loss] (fit_single_frame.py:662-668); the mesh written to
-            # vertices.ply is the LAST orientation's (fit_single_frame.py:671-676)
-            if not (loss[b] < loss1[b]):
-                params[b] = params1[b]
-                loss[b] = loss1[b]
-            if return_verts:
-                verts[b] = verts1[b]
-                joints[b] = joints1[b]
-        batch.set_params(params)
-
+def download(batch, plan, cam_loss, verts, joints):
+    """Device -> host: fitted parameters, losses, counters and (optionally) the meshes."""
     out = FitResult()
-    out.params = params
-    out.loss = loss
-    out.cam_loss = cam_loss
+    L, B = plan.L, plan.B
+    npd = plan.np_dtype
+    out.params = params = batch.get_params()
+    out.loss = batch.final_loss().cpu().numpy().astype(np.float64)
+    out.cam_loss = cam_loss.cpu().numpy()
     out.n_evals = batch.evals().cpu().numpy()
     out.flags = batch.flags().cpu().numpy()
-    out.n_orient = n_orient
-    out.h2d_bytes = h2d
-    if return_verts:
+    out.n_orient = np.ones(B, dtype=np.int64)
+    out.n_orient[plan.flip_ids] = 2
+    out.d2h_bytes = params.nbytes + 4 * B * 4
+    if verts is not None:
         out.vertices = verts.cpu().numpy()
         out.joints = joints.cpu().numpy()
+        out.d2h_bytes += out.vertices.nbytes + out.joints.nbytes
     blocks = batch.blocks
     for b in range(B):
-        r = {'camera_rotation': cam[b, 4:13].reshape(1, 3, 3).astype(npd),
+        r = {'camera_rotation': plan.cam[b, 4:13].reshape(1, 3, 3).astype(npd),
              'camera_translation': params[b, L.off_camt:L.off_camt + 3].reshape(1, 3).copy(),
-             'camera_center': cam[b, 2:4].reshape(1, 2).astype(npd),
-             'H': int(H[b]), 'W': int(W[b]), 'focal_length': float(focal[b])}
+             'camera_center': plan.cam[b, 2:4].reshape(1, 2).astype(npd),
+             'H': int(plan.H[b]), 'W': int(plan.W[b]), 'focal_length': float(plan.focal[b])}
         for name in ('betas', 'global_orient', 'left_hand_pose', 'right_hand_pose', 'jaw_pose',
                      'leye_pose', 'reye_pose', 'expression'):
             off, n = blocks[name]
@@ -383,4 +369,19 @@ def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_vert
     return out
 
 
-N_CAM_FX, N_CAM_FY = 0, 1
+def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_verts=True,
+               body_mean_pose=None):
+    """Fits every frame of ``batch`` (an ``engine.FrameBatch``).
+
+    keypoints [B,K,3] (x, y, confidence) in the reference's row order; ``H``, ``W`` scalars or
+    [B]; ``cfg`` the flat config dict of ``cmd_parser.parse_config`` (same keys as the
+    reference's YAML files); ``expose`` / ``pixie`` lists of per-frame regression results.
+    """
+    plan = FitPlan(batch.L, batch.model.K, np.asarray(keypoints), H, W, cfg, expose, pixie,
+                   body_mean_pose, batch.model.np_dtype)
+    h2d = upload(batch, plan)
+    cam_loss, verts, joints, launches = run(batch, plan, return_verts)
+    out = download(batch, plan, cam_loss, verts, joints)
+    out.h2d_bytes = h2d
+    out.gpu_launches = launches
+    return out

@@ -129,7 +129,7 @@ class _Counter(object):
         bm.forward = fwd
 
 
-def ref_fit(frame='02_cropped', inputs=None, cfg=None, tag='ref_fit_02'):
+def ref_fit(frame='02_cropped', inputs=None, cfg=None, tag='ref_fit_02', save=True):
     ref = ref_bridge.load()
     cfg = cfg or cfg_combined()
     dtype = torch.float32
@@ -168,7 +168,8 @@ def ref_fit(frame='02_cropped', inputs=None, cfg=None, tag='ref_fit_02'):
     out['vertices'] = verts.astype(np.float32)
     out['n_forward_calls'] = np.array(counter.n)
     out['cfg_json'] = np.array(json.dumps({k: v for k, v in cfg.items()}))
-    np.savez_compressed(os.path.join(HERE, tag + '.npz'), **out)
+    if save:
+        np.savez_compressed(os.path.join(HERE, tag + '.npz'), **out)
     print(tag, 'forward calls', counter.n)
     return out
 
@@ -265,10 +266,12 @@ def ref_eval(inputs, dtype=torch.float64, tag='f64'):
     return out
 
 
-def ref_stage(inputs, dtype=torch.float64, tag='f64'):
-    """Reference run_fitting + reference LBFGS on one body stage from the ref_eval start."""
+def ref_stage(inputs, dtype=torch.float64, tag='f64', perturb=None, save=True):
+    """Reference run_fitting + reference LBFGS on one body stage from the ref_eval start.
+    ``perturb=(eps, seed)`` multiplies the start by 1 + eps * N(0,1) (envelope runs)."""
     ref = ref_bridge.load()
-    ev = dict(np.load(os.path.join(HERE, 'ref_eval_{}.npz'.format(tag))))
+    ev = dict(np.load(os.path.join(HERE, 'ref_eval_{}.npz'.format(
+        'f64' if dtype == torch.float64 else 'f32'))))
     cfg = cfg_combined()
     body_model, pri, _, _ = build_reference_objects(cfg, dtype)
     H, W = [int(v) for v in ev['HW']]
@@ -283,6 +286,9 @@ def ref_stage(inputs, dtype=torch.float64, tag='f64'):
     gt, conf = kp[:, :, :2], kp[:, :, 2]
     jw = torch.tensor(ev['jw'], dtype=dtype)
     P = {k[6:]: ev[k] for k in ev if k.startswith('param/')}
+    if perturb is not None:
+        prng = np.random.default_rng(perturb[1])
+        P = {k: v * (1 + perturb[0] * prng.normal(size=v.shape)) for k, v in P.items()}
     body_model.reset_params(**{k: v for k, v in P.items() if k != 'pose_embedding'})
     emb = torch.tensor(P['pose_embedding'], dtype=dtype, requires_grad=True)
     weights = json.loads(str(ev['weights_json']))
@@ -316,14 +322,73 @@ def ref_stage(inputs, dtype=torch.float64, tag='f64'):
         o = body_model(return_verts=True, body_pose=emb)
     out['vertices'] = o.vertices.numpy()[0].astype(np.float32)
     out['joints'] = o.joints.numpy()[0]
-    np.savez_compressed(os.path.join(HERE, 'ref_stage_{}.npz'.format(tag)), **out)
-    print('ref_stage', tag, 'final', final, 'forward calls', counter.n)
+    if save:
+        np.savez_compressed(os.path.join(HERE, 'ref_stage_{}.npz'.format(tag)), **out)
+    print('ref_stage', tag, perturb, 'final', final, 'forward calls', counter.n)
+    return out
+
+
+def _pairwise(vs):
+    mx, mean = 0.0, 0.0
+    for i in range(len(vs)):
+        for j in range(i + 1, len(vs)):
+            d = np.abs(vs[i] - vs[j])
+            mx, mean = max(mx, float(d.max())), max(mean, float(d.mean()))
+    return mx, mean
+
+
+def ref_envelope(inputs):
+    """Run-to-run envelope of the reference itself: the same float32 problems started from
+    points that differ by one float32 ulp (relative 6e-8).  The fitting problem is chaotic
+    (line-search branch flips), so these runs end at visibly different points; the spread is
+    the yardstick the engine's fitted results are held to."""
+    torch.set_num_threads(1)
+    runs = [ref_stage(inputs, torch.float32, 'f32', perturb=(6e-8, s), save=False)
+            for s in range(1, 7)]
+    base = ref_stage(inputs, torch.float32, 'f32', save=False)
+    allr = [base] + runs
+    out = {'stage/final_loss': np.array([float(r['final_loss']) for r in allr]),
+           'stage/n_forward_calls': np.array([int(r['n_forward_calls']) for r in allr]),
+           'stage/vertices_base': base['vertices']}
+    mx, mean = _pairwise([r['vertices'] for r in allr])
+    out['stage/vertex_pairwise_max'] = np.array(mx)
+    out['stage/vertex_pairwise_mean'] = np.array(mean)
+    for k in base:
+        if k.startswith('param/'):
+            st = np.stack([r[k] for r in allr])
+            out['stage/spread/' + k[6:]] = np.array(float((st.max(0) - st.min(0)).max()))
+    fits = []
+    for s in range(1, 6):
+        prng = np.random.default_rng(100 + s)
+        inp = dict(inputs)
+        kp = inp['02_cropped/keypoints'].copy()
+        kp[:, :2] *= (1 + 6e-8 * prng.normal(size=kp[:, :2].shape)).astype(np.float32)
+        inp['02_cropped/keypoints'] = kp
+        fits.append(ref_fit('02_cropped', inp, save=False))
+    fits.append(dict(np.load(os.path.join(HERE, 'ref_fit_02.npz'))))
+    out['fit/n_runs_nan'] = np.array(sum(1 for f in fits if not np.isfinite(f['vertices']).all()))
+    fits = [f for f in fits if np.isfinite(f['vertices']).all()]
+    mx, mean = _pairwise([f['vertices'] for f in fits])
+    out['fit/vertex_pairwise_max'] = np.array(mx)
+    out['fit/vertex_pairwise_mean'] = np.array(mean)
+    out['fit/n_forward_calls'] = np.array([int(f['n_forward_calls']) for f in fits])
+    for k in fits[0]:
+        if k.startswith('result/') and np.asarray(fits[0][k]).ndim == 2:
+            st = np.stack([f[k] for f in fits])
+            out['fit/spread/' + k[7:]] = np.array(float((st.max(0) - st.min(0)).max()))
+    np.savez_compressed(os.path.join(HERE, 'ref_envelope.npz'), **out)
+    for k, v in out.items():
+        if np.asarray(v).size < 10:
+            print(k, v)
 
 
 if __name__ == '__main__':
     if not ref_bridge.available():
         raise SystemExit('reference tree not found at ' + REF)
     inp = demo_inputs()
+    if len(sys.argv) > 1 and sys.argv[1] == 'envelope':
+        ref_envelope(inp)
+        raise SystemExit(0)
     ref_eval(inp, torch.float64, 'f64')
     ref_eval(inp, torch.float32, 'f32')
     ref_stage(inp, torch.float64, 'f64')

@@ -24,6 +24,7 @@ def test_demo_frames_against_reference_fit():
     from smplifyx_b200 import engine, fit_frames as FF
     inp = Cm.golden('demo_inputs.npz')
     ref = Cm.golden('ref_fit_02.npz')
+    env = Cm.golden('ref_envelope.npz')
     cfg = json.loads(str(ref['cfg_json']))
     model = engine.Model(Cm.model_data(), Cm.joint_map(), dtype=torch.float32, **Cm.MODEL_KW)
     frames = ['02_cropped', '18_cropped', '02_cropped']
@@ -47,7 +48,13 @@ def test_demo_frames_against_reference_fit():
     err = np.abs(out.vertices[0] - ref['vertices'])
     print('vertex error vs reference fit: max %.4g m, mean %.4g m' % (err.max(), err.mean()))
     print('evals', out.n_evals, 'reference', int(ref['n_forward_calls']))
-    assert err.mean() < 5e-3 and err.max() < 5e-2
-    for k in ('betas', 'global_orient', 'body_pose', 'expression', 'jaw_pose'):
+    # yardstick: how far apart the reference's own float32 runs end when the keypoints differ by
+    # one ulp (tests/golden/ref_envelope.npz: max 7.8 cm, mean 9.8 mm, 396..481 evaluations)
+    assert err.max() <= float(env['fit/vertex_pairwise_max'])
+    assert err.mean() <= float(env['fit/vertex_pairwise_mean'])
+    lo, hi = env['fit/n_forward_calls'].min(), env['fit/n_forward_calls'].max()
+    assert 0.7 * lo <= out.n_evals[0] <= 1.3 * hi
+    for k in ('betas', 'global_orient', 'body_pose', 'jaw_pose', 'camera_translation'):
         d = np.abs(r[k] - ref['result/' + k]).max()
-        print(k, 'max abs diff', d)
+        print(k, 'max abs diff', d, 'reference spread', float(env['fit/spread/' + k]))
+        assert d <= 1.5 * float(env['fit/spread/' + k]) + 1e-6

@@ -132,19 +132,23 @@ def test_stage_fit_f64_matches_host_build(model64):
 
 
 def test_stage_fit_f32_envelope(model32):
+    """A float32 stage from a far-away random start: the reference's own float32 runs started
+    one ulp apart end with final losses 403k .. 528k and meshes up to 39 cm apart
+    (tests/golden/ref_envelope.npz).  The engine must land inside that envelope."""
     ev = Cm.golden('ref_eval_f32.npz')
-    sg = Cm.golden('ref_stage_f64.npz')
+    env = Cm.golden('ref_envelope.npz')
     I = Cm.eval_case_inputs(ev, 'reg')
     batch = _engine().FrameBatch(model32, 4)
     _load(batch, I, 4)
     final = batch.fit_stage(I['stage']).cpu().numpy()
-    ref_final = float(sg['final_loss'])
-    assert np.all(np.abs(final - ref_final) < 5e-3 * ref_final), (final, ref_final)
+    lo, hi = env['stage/final_loss'].min(), env['stage/final_loss'].max()
+    assert np.all((final > lo - 0.1 * (hi - lo)) & (final < hi + 0.1 * (hi - lo))), (final, lo, hi)
     assert int(batch.flags().cpu().numpy().max()) == 0
-    # fitted mesh against the reference's fitted mesh (metres; body is ~1.7 m tall)
+    assert np.all(final == final[0])
     verts, _ = batch.forward_mesh()
-    err = np.abs(verts.cpu().numpy()[0] - sg['vertices']).max()
-    assert err < 2e-2, err
+    err = np.abs(verts.cpu().numpy()[0] - env['stage/vertices_base'])
+    assert err.max() <= float(env['stage/vertex_pairwise_max']), err.max()
+    assert err.mean() <= float(env['stage/vertex_pairwise_mean']), err.mean()
 
 
 def test_frame_subset_launch(model32):
