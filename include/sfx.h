@@ -124,6 +124,20 @@ int sfx_batch_select_orientation(sfx_batch* b, const int32_t* frame_ids_dev, int
 /* run_fitting's return value of the last stage per frame ([B], batch dtype, device). */
 void* sfx_batch_final_loss_dev(sfx_batch* b);
 
+/* The whole per-frame flow of fit_single_frame.py:447-668 in ONE launch: camera stage, the
+ * annealing stages, and for frames with flip_dev[f] != 0 (2-D shoulder distance below
+ * side_view_thsh, :461-463) the second, 180-degree flipped orientation followed by the argmin
+ * selection.  Persistent blocks pull frames in the order given by order_dev (int32 [B]; NULL =
+ * 0..B-1; list the flipped frames first).  Results: parameters (sfx_batch_get_params), final
+ * loss (sfx_batch_final_loss_dev), camera-stage loss (sfx_batch_cam_loss_dev), and the last
+ * orientation's parameters for sfx_forward_mesh_last. */
+int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order_dev,
+                     const uint8_t* flip_dev, void* stream);
+void* sfx_batch_cam_loss_dev(sfx_batch* b);
+/* body_model(return_verts=True) at the LAST fitted orientation of every frame -- the mesh the
+ * reference writes to vertices.ply (fit_single_frame.py:611, :671-676). */
+int sfx_forward_mesh_last(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream);
+
 /* body_model(return_verts=True) for every frame (fit_single_frame.py:611): full-mesh
  * vertices [B,V,3] and mapped joints [B,K,3] from the current parameters. */
 int sfx_forward_mesh(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream);
@@ -131,6 +145,8 @@ int sfx_forward_mesh(sfx_batch* b, void* vertices_dev, void* joints_dev, void* s
 /* Diagnostics: closure evaluations and status flags per frame ([B] int32, device). */
 int32_t* sfx_batch_evals_dev(sfx_batch* b);
 int32_t* sfx_batch_flags_dev(sfx_batch* b);
+/* passes over the support rows of the blend matrix per frame (1 per forward, 1 per adjoint). */
+int32_t* sfx_batch_passes_dev(sfx_batch* b);
 int sfx_batch_reset_counters(sfx_batch* b, void* stream);
 
 const char* sfx_last_error(void);

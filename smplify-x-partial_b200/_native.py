@@ -51,7 +51,27 @@ class SfxStage(C.Structure):
         ('n_active', C.c_int), ('n_blocks', C.c_int),
         ('block_start', C.c_int * SFX_MAX_BLOCKS), ('block_len', C.c_int * SFX_MAX_BLOCKS),
         ('block_off', C.c_int * SFX_MAX_BLOCKS), ('need_blend_grad', C.c_int),
+        ('generic_two_loop', C.c_int),
     ]
+
+
+SFX_MAX_STAGES = 8
+
+
+class SfxPipeline(C.Structure):
+    _fields_ = [('n_stages', C.c_int), ('reserved', C.c_int), ('cam', SfxStage),
+                ('body', SfxStage * SFX_MAX_STAGES)]
+
+
+def make_pipeline(cam_stage, body_stages):
+    if not 1 <= len(body_stages) <= SFX_MAX_STAGES:
+        raise ValueError('between 1 and {} annealing stages are supported'.format(SFX_MAX_STAGES))
+    P = SfxPipeline()
+    P.n_stages = len(body_stages)
+    P.cam = cam_stage
+    for i, st in enumerate(body_stages):
+        P.body[i] = st
+    return P
 
 
 class SfxModelDesc(C.Structure):
@@ -239,6 +259,10 @@ def load_library(path=None):
     lib.sfx_eval.argtypes = [vp, C.POINTER(SfxStage), vp, vp, vp, vp]
     lib.sfx_fit_stage.argtypes = [vp, C.POINTER(SfxStage), vp, i32, vp, vp]
     lib.sfx_forward_mesh.argtypes = [vp, vp, vp, vp]
+    lib.sfx_fit_pipeline.argtypes = [vp, C.POINTER(SfxPipeline), vp, vp, vp]
+    lib.sfx_batch_cam_loss_dev.argtypes = [vp]
+    lib.sfx_batch_cam_loss_dev.restype = vp
+    lib.sfx_forward_mesh_last.argtypes = [vp, vp, vp, vp]
     lib.sfx_batch_begin_orientation.argtypes = [vp, i32, vp, i32, vp]
     lib.sfx_batch_select_orientation.argtypes = [vp, vp, i32, vp]
     lib.sfx_batch_final_loss_dev.argtypes = [vp]
@@ -247,6 +271,8 @@ def load_library(path=None):
     lib.sfx_batch_evals_dev.restype = vp
     lib.sfx_batch_flags_dev.argtypes = [vp]
     lib.sfx_batch_flags_dev.restype = vp
+    lib.sfx_batch_passes_dev.argtypes = [vp]
+    lib.sfx_batch_passes_dev.restype = vp
     lib.sfx_batch_reset_counters.argtypes = [vp, vp]
     lib.sfx_last_error.restype = C.c_char_p
     lib.sfx_version.restype = C.c_int

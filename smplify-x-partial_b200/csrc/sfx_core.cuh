@@ -83,6 +83,7 @@ struct BatchView {
     T* hist_y;           // [B][HIST][SFX_NP_MAX]
     T* final_loss;       // [B]
     int* n_evals;        // [B]  (accumulated)
+    int* n_passes;       // [B]  blend-matrix passes streamed (1 per forward, 1 per adjoint)
     int* flags;          // [B]
     const int* frame_ids;   // optional indirection (nullptr: block b -> frame b)
 };
@@ -117,6 +118,7 @@ struct Scratch {
     T loss;
     int dynrow;
     int n_evals;
+    int n_passes;
 };
 
 // ------------------------------------------------------------------------------ math
@@ -724,6 +726,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     if (SFX_TID == 0) {
         S.loss = total;
         S.n_evals += 1;
+        S.n_passes += st.need_blend_grad ? 2 : 1;
     }
     SFX_SYNC();
 #ifdef SFX_TRACE
@@ -938,6 +941,76 @@ struct LbfgsState {
     double prev_loss;
 };
 
+
+#ifdef __CUDACC__
+// Two-loop recursion of one L-BFGS iteration (lbfgs_ls.py:336-358) by warp 0 alone: the
+// direction lives in registers (element e <-> lane e % 32, register e / 32), the (s, y) pairs
+// stream from global memory one pair ahead of use, and nothing synchronises the block.  The
+// arithmetic -- per-lane partial sums over e = lane, lane + 32, ... followed by an xor
+// butterfly -- is the one block_reduce() performs, so both paths produce the same bits.
+template <typename T>
+__device__ __forceinline__ void two_loop_warp(Scratch<T>& S, int k, int head, int H, T hd,
+                                              const T* hist_s, const T* hist_y, int D) {
+    constexpr int NR = SFX_NP_MAX / 32;
+    const int lane = threadIdx.x;
+    T q[NR], sc[NR], yc[NR], sn[NR], yn[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int e = 32 * r + lane;
+        q[r] = e < D ? -S.g[e] : (T)0;
+        sn[r] = yn[r] = 0;
+    }
+    auto fetch = [&](int i) {
+        const long row = (long)((head + i) % H) * SFX_NP_MAX;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int e = 32 * r + lane;
+            sn[r] = e < D ? hist_s[row + e] : (T)0;
+            yn[r] = e < D ? hist_y[row + e] : (T)0;
+        }
+    };
+    if (k > 0) fetch(k - 1);
+    for (int i = k - 1; i >= 0; --i) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { sc[r] = sn[r]; yc[r] = yn[r]; }
+        if (i > 0) fetch(i - 1);
+        T p = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+            if (32 * r < D) p = p + sc[r] * q[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p = p + __shfl_xor_sync(0xffffffffu, p, o);
+        const T a = p * S.ro[i];
+        if (lane == 0) S.al[i] = a;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) q[r] += -a * yc[r];
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) q[r] = q[r] * hd;       // q now holds the direction d
+    __syncwarp();
+    if (k > 0) fetch(0);
+    for (int i = 0; i < k; ++i) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { sc[r] = sn[r]; yc[r] = yn[r]; }
+        if (i + 1 < k) fetch(i + 1);
+        T p = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+            if (32 * r < D) p = p + yc[r] * q[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p = p + __shfl_xor_sync(0xffffffffu, p, o);
+        const T co = S.al[i] - p * S.ro[i];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) q[r] += co * sc[r];
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int e = 32 * r + lane;
+        if (e < D) S.d[e] = q[r];
+    }
+}
+#endif
+
 // One LBFGS.step (lbfgs_ls.py:256-445).  Returns the loss at entry ("orig_loss").
 template <typename T>
 SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, T* hist_s, T* hist_y) {
@@ -993,6 +1066,15 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
             }
             // two-loop recursion
             const int k = ls.num_old;
+#ifdef __CUDACC__
+            if (!E.st->generic_two_loop) {
+                SFX_SYNC();
+                if (threadIdx.x < 32)
+                    two_loop_warp(S, k, ls.head, H, ls.H_diag, hist_s, hist_y, D);
+                SFX_SYNC();
+            } else
+#endif
+            {
             SFX_FOR(i, D) S.q[i] = -S.g[i];
             SFX_SYNC();
             for (int i = k - 1; i >= 0; --i) {
@@ -1014,6 +1096,7 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
                 SFX_FOR(e, D) S.d[e] += co * srow[e];
             }
             SFX_SYNC();
+            }
         }
         vcopy(S.prev_g, S.g, D);
         ls.prev_loss = loss;

@@ -58,7 +58,7 @@ __device__ __forceinline__ void load_frame(const BatchView<T>& Bv, int f, Scratc
     const int np = Bv.lay.np;
     for (int i = threadIdx.x; i < SFX_NP_MAX; i += blockDim.x)
         S.x[i] = i < np ? Bv.params[(size_t)f * np + i] : (T)0;
-    if (threadIdx.x == 0) S.n_evals = 0;
+    if (threadIdx.x == 0) S.n_evals = S.n_passes = 0;
     __syncthreads();
 }
 
@@ -97,6 +97,7 @@ fit_stage_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__
         Bv.final_loss[f] = (T)r;
         if (final_loss_out) final_loss_out[f] = (T)r;
         Bv.n_evals[f] += S.n_evals;
+        Bv.n_passes[f] += S.n_passes;
         Bv.flags[f] |= flags;
     }
 }
@@ -234,6 +235,117 @@ __global__ void select_orientation_kernel(BatchView<T> Bv, const T* params_alt, 
     }
 }
 
+// ---- the whole per-frame pipeline in one launch -----------------------------------------------
+// Persistent blocks pull frames from a counter (frames that need the second orientation are
+// listed first by the host); a frame never waits for the slowest frame of a stage, and the
+// second orientation of a side-view frame overlaps other frames' work.
+template <typename T>
+__device__ void reset_for_orientation(const SfxLayout& L, Scratch<T>& S) {
+    for (int i = threadIdx.x; i < L.np; i += blockDim.x) {
+        const bool keep = (i >= L.off_go && i < L.off_go + 3) ||
+                          (i >= L.off_pose && i < L.off_pose + L.n_pose) ||
+                          (i >= L.off_camt && i < L.off_camt + 3);
+        if (!keep) S.x[i] = 0;
+    }
+    __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SFX_THREADS, 1)
+fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ BatchView<T> Bv,
+                    const SfxPipeline* __restrict__ P, const unsigned char* __restrict__ flip,
+                    int n_frames, int* counter, int ring_mode, T* cam_loss_out, T* params_last) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(smem);
+    __shared__ StreamWS ws;
+    __shared__ SfxStage st;
+    __shared__ int flags, s_idx;
+    __shared__ T alt[SFX_NP_MAX];
+    const int K = M.K;
+    const int np = Bv.lay.np;
+    const SfxLayout& L = Bv.lay;
+    if (threadIdx.x == 0) ws = carve_stream<T>(smem + scratch_bytes<T>(), ring_mode);
+    __syncthreads();
+    stream_init<T>(ws);
+    auto load_stage = [&](const SfxStage* src) {
+        __syncthreads();
+        const int* s32 = reinterpret_cast<const int*>(src);
+        int* d32 = reinterpret_cast<int*>(&st);
+        for (int i = threadIdx.x; i < (int)(sizeof(SfxStage) / 4); i += blockDim.x) d32[i] = s32[i];
+        __syncthreads();
+    };
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_idx = atomicAdd(counter, 1);
+            flags = 0;
+        }
+        __syncthreads();
+        const int idx = s_idx;
+        if (idx >= n_frames) break;
+        const int f = Bv.frame_ids ? Bv.frame_ids[idx] : idx;
+        load_frame(Bv, f, S);
+        EvalCtx<T> E;
+        E.M = &M; E.L = &Bv.lay; E.st = &st;
+        E.gt = Bv.gt + (size_t)f * K * 2;
+        E.conf = Bv.conf + (size_t)f * K;
+        E.init_mask = Bv.init_mask + (size_t)f * K;
+        E.cam = Bv.cam + (size_t)f * SFX_CAM_STRIDE;
+        E.reg_pose = Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr;
+        E.stream_ws = &ws;
+        T* hs = Bv.hist_s + (size_t)f * SFX_HIST * SFX_NP_MAX;
+        T* hy = Bv.hist_y + (size_t)f * SFX_HIST * SFX_NP_MAX;
+        // stage C: camera translation + global orientation (fit_single_frame.py:473-496)
+        load_stage(&P->cam);
+        stage_joint_weights(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, K, S);
+        double r = run_fitting(E, S, hs, hy, &flags);
+        __syncthreads();
+        if (threadIdx.x == 0 && cam_loss_out) cam_loss_out[f] = (T)r;
+        T go0[3] = {S.x[L.off_go], S.x[L.off_go + 1], S.x[L.off_go + 2]};
+        const int n_orient = flip && flip[f] ? 2 : 1;
+        double loss0 = 0;
+        for (int o = 0; o < n_orient; ++o) {
+            __syncthreads();
+            if (o == 1) {
+                for (int i = threadIdx.x; i < np; i += blockDim.x) alt[i] = S.x[i];
+                loss0 = r;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double rv[3] = {(double)go0[0], (double)go0[1], (double)go0[2]};
+                    const double ry[3] = {0.0, 3.14159265358979323846, 0.0};
+                    double Ra[9], Rb[9], Rc[9], out[3];
+                    cv_rodrigues(rv, Ra);
+                    cv_rodrigues(ry, Rb);
+                    mat3_mul(Ra, Rb, Rc);
+                    cv_inv_rodrigues(Rc, out);
+                    for (int k = 0; k < 3; ++k) S.x[L.off_go + k] = (T)(float)out[k];
+                }
+                __syncthreads();
+            }
+            reset_for_orientation(L, S);
+            for (int si = 0; si < P->n_stages; ++si) {
+                load_stage(&P->body[si]);
+                stage_joint_weights(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, K, S);
+                r = run_fitting(E, S, hs, hy, &flags);
+            }
+        }
+        __syncthreads();
+        // the mesh written to vertices.ply is the LAST orientation's (fit_single_frame.py:671-676)
+        if (params_last)
+            for (int i = threadIdx.x; i < np; i += blockDim.x) params_last[(size_t)f * np + i] = S.x[i];
+        // results[argmin loss] (fit_single_frame.py:662-668)
+        const bool restore = n_orient == 2 && (loss0 < r);
+        for (int i = threadIdx.x; i < np; i += blockDim.x)
+            Bv.params[(size_t)f * np + i] = restore ? alt[i] : S.x[i];
+        if (threadIdx.x == 0) {
+            Bv.final_loss[f] = (T)(restore ? loss0 : r);
+            Bv.n_evals[f] += S.n_evals;
+            Bv.n_passes[f] += S.n_passes;
+            Bv.flags[f] |= flags;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ handles
 struct DevBuf {
     void* p = nullptr;
@@ -306,7 +418,9 @@ struct sfx_batch {
     SfxLayout lay;
     size_t es = 4;        // element size of the batch dtype
     DevBuf params, gt, conf, jw, lowconf, init_mask, cam, reg_pose, hist_s, hist_y, final_loss,
-        n_evals, flags, Acoef, Ccoef, vposed, go_saved, params_alt, loss_alt;
+        n_evals, n_passes, flags, Acoef, Ccoef, vposed, go_saved, params_alt, loss_alt, pipe, counter,
+        cam_loss, params_last;
+    bool last_valid = false;
     bool has_reg = false;
     std::vector<unsigned char> stage_host;     // host staging for set_targets
     template <typename T>
@@ -318,7 +432,7 @@ struct sfx_batch {
         v.init_mask = (const unsigned char*)init_mask.p; v.cam = (const T*)cam.p;
         v.reg_pose = has_reg ? (const T*)reg_pose.p : nullptr;
         v.hist_s = (T*)hist_s.p; v.hist_y = (T*)hist_y.p; v.final_loss = (T*)final_loss.p;
-        v.n_evals = (int*)n_evals.p; v.flags = (int*)flags.p; v.frame_ids = frame_ids;
+        v.n_evals = (int*)n_evals.p; v.n_passes = (int*)n_passes.p; v.flags = (int*)flags.p; v.frame_ids = frame_ids;
         return v;
     }
 };
@@ -389,6 +503,7 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     ALLOC(hist_y, (size_t)B * SFX_HIST * SFX_NP_MAX * es);
     ALLOC(final_loss, (size_t)B * es);
     ALLOC(n_evals, (size_t)B * sizeof(int));
+    ALLOC(n_passes, (size_t)B * sizeof(int));
     ALLOC(flags, (size_t)B * sizeof(int));
     ALLOC(Acoef, (size_t)B * SFX_NJ * 12 * es);
     ALLOC(Ccoef, (size_t)mesh_padded_frames(B) * SFX_KPAD * es);
@@ -396,6 +511,10 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     ALLOC(go_saved, (size_t)B * 3 * es);
     ALLOC(params_alt, (size_t)B * b->lay.np * es);
     ALLOC(loss_alt, (size_t)B * es);
+    ALLOC(pipe, sizeof(SfxPipeline));
+    ALLOC(counter, 64);
+    ALLOC(cam_loss, (size_t)B * es);
+    ALLOC(params_last, (size_t)B * b->lay.np * es);
 #undef ALLOC
     *out = b;
     return SFX_OK;
@@ -473,10 +592,12 @@ int sfx_batch_get_params(const sfx_batch* b, void* host_params, void* stream) {
 void* sfx_batch_params_dev(sfx_batch* b) { return b ? b->params.p : nullptr; }
 int32_t* sfx_batch_evals_dev(sfx_batch* b) { return b ? (int32_t*)b->n_evals.p : nullptr; }
 int32_t* sfx_batch_flags_dev(sfx_batch* b) { return b ? (int32_t*)b->flags.p : nullptr; }
+int32_t* sfx_batch_passes_dev(sfx_batch* b) { return b ? (int32_t*)b->n_passes.p : nullptr; }
 
 int sfx_batch_reset_counters(sfx_batch* b, void* stream) {
     if (!b) return fail(SFX_ERR_ARG, "null argument");
     CUDA_TRY(cudaMemsetAsync(b->n_evals.p, 0, (size_t)b->B * sizeof(int), (cudaStream_t)stream));
+    CUDA_TRY(cudaMemsetAsync(b->n_passes.p, 0, (size_t)b->B * sizeof(int), (cudaStream_t)stream));
     CUDA_TRY(cudaMemsetAsync(b->flags.p, 0, (size_t)b->B * sizeof(int), (cudaStream_t)stream));
     return SFX_OK;
 }
@@ -586,7 +707,58 @@ int sfx_batch_select_orientation(sfx_batch* b, const int32_t* frame_ids_dev, int
 
 void* sfx_batch_final_loss_dev(sfx_batch* b) { return b ? b->final_loss.p : nullptr; }
 
+int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order_dev,
+                     const uint8_t* flip_dev, void* stream) {
+    if (!b || !pipe) return fail(SFX_ERR_ARG, "null argument");
+    if (pipe->n_stages < 1 || pipe->n_stages > SFX_MAX_STAGES)
+        return fail(SFX_ERR_ARG, "pipeline: number of stages out of range");
+    int rc = check_stage(b, &pipe->cam);
+    for (int i = 0; i < pipe->n_stages && !rc; ++i) rc = check_stage(b, &pipe->body[i]);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(b->pipe.p, pipe, sizeof(SfxPipeline), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(b->counter.p, 0, sizeof(int), s));
+    const int rm = ring_mode_for(b->m);
+    const int grid = b->B < b->m->num_sms ? b->B : b->m->num_sms;
+    if (b->m->use_double) {
+        size_t smem = fit_smem<double>(rm);
+        CUDA_TRY(cudaFuncSetAttribute(fit_pipeline_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fit_pipeline_kernel<double><<<grid, SFX_THREADS, smem, s>>>(
+            b->m->vd, b->view<double>(order_dev), (const SfxPipeline*)b->pipe.p, flip_dev, b->B,
+            (int*)b->counter.p, rm, (double*)b->cam_loss.p, (double*)b->params_last.p);
+    } else {
+        size_t smem = fit_smem<float>(rm);
+        CUDA_TRY(cudaFuncSetAttribute(fit_pipeline_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fit_pipeline_kernel<float><<<grid, SFX_THREADS, smem, s>>>(
+            b->m->vf, b->view<float>(order_dev), (const SfxPipeline*)b->pipe.p, flip_dev, b->B,
+            (int*)b->counter.p, rm, (float*)b->cam_loss.p, (float*)b->params_last.p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    b->last_valid = true;
+    return SFX_OK;
+}
+
+void* sfx_batch_cam_loss_dev(sfx_batch* b) { return b ? b->cam_loss.p : nullptr; }
+
+static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream);
+
 int sfx_forward_mesh(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream) {
+    return forward_mesh_impl(b, vertices_dev, joints_dev, stream);
+}
+
+int sfx_forward_mesh_last(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream) {
+    if (!b) return fail(SFX_ERR_ARG, "null argument");
+    if (!b->last_valid) return fail(SFX_ERR_ARG, "no pipeline launch has run on this batch");
+    // evaluate at the last orientation's parameters, then put the selected ones back
+    std::swap(b->params.p, b->params_last.p);
+    int rc = forward_mesh_impl(b, vertices_dev, joints_dev, stream);
+    std::swap(b->params.p, b->params_last.p);
+    return rc;
+}
+
+}  // extern "C"
+
+static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream) {
     if (!b || !vertices_dev) return fail(SFX_ERR_ARG, "null argument");
     cudaStream_t s = (cudaStream_t)stream;
     const sfx_model* m = b->m;
@@ -624,5 +796,3 @@ int sfx_forward_mesh(sfx_batch* b, void* vertices_dev, void* joints_dev, void* s
     }
     return SFX_OK;
 }
-
-}  // extern "C"

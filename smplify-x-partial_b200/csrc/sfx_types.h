@@ -73,6 +73,17 @@ struct SfxStage {
     int block_len[SFX_MAX_BLOCKS];
     int block_off[SFX_MAX_BLOCKS];             // into the full parameter vector
     int need_blend_grad;                       // 0 when only global_orient / camera are optimised
+    int generic_two_loop;                      // debug: block-wide two-loop recursion (A/B test)
+};
+
+// The whole per-frame flow of fit_single_frame.py:447-668 as one launch: camera stage, then the
+// annealing stages for the first orientation and, for frames flagged for it, for the flipped one.
+#define SFX_MAX_STAGES 8
+struct SfxPipeline {
+    int n_stages;
+    int reserved;
+    SfxStage cam;
+    SfxStage body[SFX_MAX_STAGES];
 };
 
 // Per-frame constants, struct-of-arrays over frames.  "cam" row: fx fy cx cy R[9] data_weight

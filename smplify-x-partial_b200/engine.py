@@ -161,13 +161,27 @@ class FrameBatch(object):
                                                      _ptr(final), _stream()))
         return final
 
-    def forward_mesh(self, want_joints=True):
-        """body_model(return_verts=True): vertices [B, V, 3] (+ mapped joints [B, K, 3])."""
-        verts = self._new(self.B, self.model.V, 3)
-        joints = self._new(self.B, self.model.K, 3) if want_joints else None
+    def fit_pipeline(self, pipeline, order=None, flip=None):
+        """Camera stage + every annealing stage (+ flipped orientation and argmin selection for
+        the frames flagged in the uint8 device tensor ``flip``) in ONE launch."""
         with torch.cuda.device(self.model.device):
-            N.check(self.lib, self.lib.sfx_forward_mesh(self.h, _ptr(verts), _ptr(joints),
-                                                        _stream()))
+            N.check(self.lib, self.lib.sfx_fit_pipeline(self.h, C.byref(pipeline), _ptr(order),
+                                                        _ptr(flip), _stream()))
+
+    def cam_loss(self):
+        ptr = self.lib.sfx_batch_cam_loss_dev(self.h)
+        return _wrap(ptr, (self.B,), self.model.dtype, self.model.device, self)
+
+    def forward_mesh(self, want_joints=True, last_orientation=False, out=None):
+        """body_model(return_verts=True): vertices [B, V, 3] (+ mapped joints [B, K, 3]).
+        ``last_orientation``: at the parameters of the last fitted orientation of a pipeline
+        launch (what the reference writes to vertices.ply)."""
+        verts = out[0] if out is not None else self._new(self.B, self.model.V, 3)
+        joints = (out[1] if out is not None else self._new(self.B, self.model.K, 3)) \
+            if want_joints else None
+        fn = self.lib.sfx_forward_mesh_last if last_orientation else self.lib.sfx_forward_mesh
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, fn(self.h, _ptr(verts), _ptr(joints), _stream()))
         return verts, joints
 
     def begin_orientation(self, flip, frame_ids=None):
@@ -190,6 +204,10 @@ class FrameBatch(object):
 
     def evals(self):
         ptr = self.lib.sfx_batch_evals_dev(self.h)
+        return _wrap(ptr, (self.B,), torch.int32, self.model.device, self)
+
+    def passes(self):
+        ptr = self.lib.sfx_batch_passes_dev(self.h)
         return _wrap(ptr, (self.B,), torch.int32, self.model.device, self)
 
     def flags(self):

@@ -301,17 +301,38 @@ def upload(batch, plan):
         n += batch.set_targets(plan.keypoints, plan.jw, plan.lowconf, plan.init_mask, plan.cam,
                                plan.reg)
         n += batch.set_params(plan.x0)
-    plan.flip_dev = None
+    plan.flip_dev = plan.flip_mask_dev = plan.order_dev = None
     if len(plan.flip_ids):
-        plan.flip_dev = torch.as_tensor(plan.flip_ids, device=batch.model.device)
-        n += plan.flip_ids.nbytes
+        dev = batch.model.device
+        plan.flip_dev = torch.as_tensor(plan.flip_ids, device=dev)
+        mask = np.zeros(plan.B, dtype=np.uint8)
+        mask[plan.flip_ids] = 1
+        # longest frames first: the ones that fit two orientations
+        order = np.concatenate([plan.flip_ids, np.flatnonzero(mask == 0)]).astype(np.int32)
+        plan.flip_mask_dev = torch.as_tensor(mask, device=dev)
+        plan.order_dev = torch.as_tensor(order, device=dev)
+        n += plan.flip_ids.nbytes + mask.nbytes + order.nbytes
+    plan.pipeline = N.make_pipeline(plan.cam_stage, plan.stages)
     batch.reset_counters()
     return n
 
 
-def run(batch, plan, return_verts=True):
-    """The whole multi-stage fit as a fixed sequence of launches on the current stream; nothing
-    in here synchronises with the host.  Returns (cam_loss, verts, joints, n_launches)."""
+def run(batch, plan, return_verts=True, out=None):
+    """The whole multi-stage fit: ONE launch of the per-frame pipeline kernel (camera stage,
+    annealing stages, flipped orientation + selection) and the full-mesh forward; nothing in
+    here synchronises with the host.  Returns (cam_loss, verts, joints, n_launches)."""
+    batch.fit_pipeline(plan.pipeline, plan.order_dev, plan.flip_mask_dev)
+    verts = joints = None
+    launches = 1
+    if return_verts:
+        verts, joints = batch.forward_mesh(last_orientation=True, out=out)
+        launches += 4
+    return batch.cam_loss(), verts, joints, launches
+
+
+def run_staged(batch, plan, return_verts=True):
+    """Same flow, one launch per stage (the path the FittingMonitor.run_fitting mirror uses);
+    kept as the cross-check of the pipeline kernel."""
     launches = 0
     cam_loss = batch.fit_stage(plan.cam_stage)                 # stage C (:473-496)
     batch.begin_orientation(False)                             # reset_params (:546-551)

@@ -58,3 +58,38 @@ def test_demo_frames_against_reference_fit():
         d = np.abs(r[k] - ref['result/' + k]).max()
         print(k, 'max abs diff', d, 'reference spread', float(env['fit/spread/' + k]))
         assert d <= 1.5 * float(env['fit/spread/' + k]) + 1e-6
+
+
+def test_pipeline_launch_equals_staged_launches():
+    """One persistent launch for the whole per-frame flow == one launch per stage, bit for bit
+    (parameters, losses, evaluation counts, last-orientation meshes), including frames that
+    take the flipped second orientation."""
+    from smplifyx_b200 import engine, fit_frames as FF
+    inp = Cm.golden('demo_inputs.npz')
+    ref = Cm.golden('ref_fit_02.npz')
+    cfg = json.loads(str(ref['cfg_json']))
+    cfg['side_view_thsh'] = 1e6            # every frame fits both orientations
+    model = engine.Model(Cm.model_data(), Cm.joint_map(), dtype=torch.float32, **Cm.MODEL_KW)
+    frames = ['02_cropped', '18_cropped']
+    data = [_frame_inputs(inp, f) for f in frames]
+    kp = np.stack([d[0] for d in data])
+    # make frame 1 a single-orientation frame: move its shoulders apart beyond the threshold
+    cfg['side_view_thsh'] = float(np.hypot(*(kp[0, 2, :2] - kp[0, 5, :2]))) + 1.0
+    assert np.hypot(*(kp[1, 2, :2] - kp[1, 5, :2])) > cfg['side_view_thsh']
+    res = []
+    for runner in (FF.run, FF.run_staged):
+        batch = engine.FrameBatch(model, 2)
+        plan = FF.FitPlan(batch.L, model.K, kp, [d[1] for d in data], [d[2] for d in data], cfg,
+                          [d[3] for d in data], [d[4] for d in data], None, np.float32)
+        assert list(plan.flip_ids) == [0]
+        FF.upload(batch, plan)
+        cam_loss, verts, joints, _ = runner(batch, plan, True)
+        out = FF.download(batch, plan, cam_loss, verts, joints)
+        res.append(out)
+    a, b = res
+    assert np.array_equal(a.params, b.params)
+    assert np.array_equal(a.loss, b.loss)
+    assert np.array_equal(a.cam_loss, b.cam_loss)
+    assert np.array_equal(a.n_evals, b.n_evals)
+    assert np.array_equal(a.vertices, b.vertices)
+    assert a.n_evals[0] > 1.5 * a.n_evals[1]          # frame 0 really ran two orientations

@@ -151,6 +151,25 @@ def test_stage_fit_f32_envelope(model32):
     assert err.mean() <= float(env['stage/vertex_pairwise_mean']), err.mean()
 
 
+def test_two_loop_fast_path_bit_identical(model32):
+    """The single-warp, register-resident two-loop recursion gives the same bits as the
+    block-wide one (same summation order by construction)."""
+    import copy
+    ev = Cm.golden('ref_eval_f32.npz')
+    I = Cm.eval_case_inputs(ev, 'reg')
+    outs = []
+    for generic in (0, 1):
+        st = copy.copy(I['stage'])
+        st.generic_two_loop = generic
+        batch = _engine().FrameBatch(model32, 2)
+        _load(batch, I, 2)
+        final = batch.fit_stage(st).cpu().numpy()
+        outs.append((final, batch.get_params(), batch.evals().cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+
+
 def test_frame_subset_launch(model32):
     """frame_ids restricts a stage to a subset; the other frames keep their parameters."""
     ev = Cm.golden('ref_eval_f32.npz')
