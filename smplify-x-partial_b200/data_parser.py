@@ -1,0 +1,122 @@
+"""Dataset reader with the reference's contract (smplifyx/data_parser.py:46-282):
+``create_dataset(format, data_folder, **kw)`` -> iterable of
+``{'fn', 'img_path', 'keypoints' [P,K,3], 'img' [H,W,3] float32 in 0..1}`` over
+``<data_folder>/images/*.{png,jpg}`` with OpenPose-style JSON in ``<data_folder>/keypoints/``
+(``<name>_*.json``), plus ``get_model2data()``, ``get_joint_weights()`` and the shoulder
+indices.  Keypoint row order: body, left hand, right hand, face[17:68], contour face[0:17].
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import utils as U
+
+
+def read_keypoints(keypoint_fn, use_hands=True, use_face=True, use_face_contour=False):
+    """-> (keypoints list of [K,3] float32 per person, gender_pd, gender_gt)."""
+    with open(keypoint_fn) as f:
+        data = json.load(f)
+    people, gender_pd, gender_gt = [], [], []
+
+    def block(person, key):
+        return np.array(person[key], dtype=np.float32).reshape(-1, 3)
+    for person in data['people']:
+        rows = [block(person, 'pose_keypoints_2d')]
+        if use_hands:
+            rows += [block(person, 'hand_left_keypoints_2d'),
+                     block(person, 'hand_right_keypoints_2d')]
+        if use_face:
+            face = block(person, 'face_keypoints_2d')
+            rows.append(face[17:17 + 51])
+            if use_face_contour:
+                rows.append(face[:17])
+        people.append(np.concatenate(rows, axis=0))
+        if 'gender_pd' in person:
+            gender_pd.append(person['gender_pd'])
+        if 'gender_gt' in person:
+            gender_gt.append(person['gender_gt'])
+    return people, gender_pd, gender_gt
+
+
+class KeypointDataset(object):
+    def __init__(self, data_folder, fmt='coco25', img_folder='images', keyp_folder='keypoints',
+                 use_hands=False, use_face=False, dtype=torch.float32, model_type='smplx',
+                 joints_to_ign=None, use_face_contour=False, **kwargs):
+        fmt = fmt.lower()
+        if fmt not in U.NUM_BODY_KEYPOINTS:
+            raise ValueError('Unknown dataset: {}'.format(fmt))
+        self.format = fmt
+        self.num_joints = U.NUM_BODY_KEYPOINTS[fmt] + 2 * 20 * bool(use_hands)
+        self.use_hands, self.use_face = use_hands, use_face
+        self.use_face_contour = use_face_contour
+        self.model_type, self.dtype = model_type, dtype
+        self.joints_to_ign = joints_to_ign
+        self.img_folder = os.path.join(data_folder, img_folder)
+        self.keyp_folder = os.path.join(data_folder, keyp_folder)
+        self.img_paths = sorted(
+            os.path.join(self.img_folder, fn) for fn in os.listdir(self.img_folder)
+            if fn.endswith('.png') or (fn.endswith('.jpg') and not fn.startswith('.')))
+        self.cnt = 0
+
+    def get_model2data(self):
+        return U.smpl_to_annotation(self.model_type, use_hands=self.use_hands,
+                                    use_face=self.use_face,
+                                    use_face_contour=self.use_face_contour, format=self.format)
+
+    def get_left_shoulder(self):
+        return 2
+
+    def get_right_shoulder(self):
+        return 5
+
+    def get_joint_weights(self):
+        w = np.ones(self.num_joints + 2 * self.use_hands + 51 * self.use_face +
+                    17 * self.use_face_contour, dtype=np.float32)
+        if self.joints_to_ign is not None and -1 not in self.joints_to_ign:
+            w[self.joints_to_ign] = 0.
+        return torch.tensor(w, dtype=self.dtype)
+
+    def __len__(self):
+        return len(self.img_paths)
+
+    def read_item(self, img_path):
+        import cv2
+        img = cv2.imread(img_path).astype(np.float32)[:, :, ::-1] / 255.0
+        fn = os.path.splitext(os.path.basename(img_path))[0]
+        matches = glob.glob(os.path.join(self.keyp_folder, fn + '_*.json'))
+        if not matches:
+            return {}
+        people, gpd, ggt = read_keypoints(matches[0], use_hands=self.use_hands,
+                                          use_face=self.use_face,
+                                          use_face_contour=self.use_face_contour)
+        if len(people) < 1:
+            return {}
+        out = {'fn': fn, 'img_path': img_path, 'keypoints': np.stack(people), 'img': img}
+        if gpd:
+            out['gender_pd'] = gpd
+        if ggt:
+            out['gender_gt'] = ggt
+        return out
+
+    def __getitem__(self, idx):
+        return self.read_item(self.img_paths[idx])
+
+    def __iter__(self):
+        self.cnt = 0
+        return self
+
+    def __next__(self):
+        if self.cnt >= len(self.img_paths):
+            raise StopIteration
+        path = self.img_paths[self.cnt]
+        self.cnt += 1
+        return self.read_item(path)
+
+    next = __next__
+
+
+def create_dataset(format='coco25', data_folder='data', **kwargs):
+    return KeypointDataset(data_folder, fmt=format, **kwargs)

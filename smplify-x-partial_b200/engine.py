@@ -112,6 +112,13 @@ class FrameBatch(object):
         return kp.nbytes + jw.nbytes + lc.nbytes + im.nbytes + cm.nbytes + \
             (0 if rp is None else rp.nbytes)
 
+    def set_targets_dev(self, gt, conf, joint_weights, lowconf, init_mask, cam, reg_pose=None):
+        """Same as set_targets with CUDA tensors in the batch dtype (gt [B,K,2], conf [B,K])."""
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_batch_set_targets_dev(
+                self.h, _ptr(gt), _ptr(conf), _ptr(joint_weights), _ptr(lowconf), _ptr(init_mask),
+                _ptr(cam), _ptr(reg_pose)))
+
     def set_params(self, params):
         x = self._host(params, (self.B, self.L.np))
         self._keep_x = x

@@ -1,0 +1,107 @@
+"""Command line of the reference (smplifyx/main.py:51-323) on the batched CUDA engine:
+
+    python -m smplifyx_b200.main -c cfg_files/fit_smplx_combined_coco25.yaml \\
+        --data_folder DATA --output_folder OUT [--model_folder MODELS] [--batch_size 128]
+
+Same YAML keys / flags, same outputs (``<output>/results/<fn>/000.pkl``, ``vertices.ply``,
+``conf.yaml``).  Unlike the reference, which fits image after image, the frames of the data
+folder are packed ``batch_size`` at a time and each batch is fitted in one persistent CUDA
+launch (``fit_frames.fit_frames``); with ``torchrun`` the batches are sharded over the ranks
+and the fitted parameters are all-gathered once at the end (``sharding``).
+"""
+import os
+import pickle
+import sys
+import time
+
+import numpy as np
+import torch
+import yaml
+
+from . import body_model as BM
+from . import fit_frames as FF
+from . import sharding
+from . import utils as U
+from .cmd_parser import parse_config
+from .data_parser import create_dataset
+from .fit_single_frame import write_ply_vertices
+
+
+def _load_regression(args, img_name):
+    import joblib
+    pixie = expose = None
+    if args.get('regression_prior'):
+        d = args.get('pixie_results_directory')
+        if d:
+            pixie = joblib.load(os.path.join(d, img_name, img_name + '_param.pkl'))
+        d = args.get('expose_results_directory')
+        if d:
+            expose = dict(np.load(os.path.join(d, img_name + '.jpg', img_name + '.jpg_params.npz'),
+                                  allow_pickle=True))
+        if args.get('pare_results_directory'):
+            raise NotImplementedError('PARE regression prior')
+    return pixie, expose
+
+
+def main(**args):
+    output_folder = os.path.expandvars(args.pop('output_folder'))
+    os.makedirs(output_folder, exist_ok=True)
+    with open(os.path.join(output_folder, 'conf.yaml'), 'w') as f:
+        yaml.dump(args, f)
+    result_folder = os.path.join(output_folder, args.pop('result_folder', 'results'))
+    os.makedirs(result_folder, exist_ok=True)
+    if args.get('use_gender_classifier'):
+        raise NotImplementedError('gender classifier (TF1 Homogenus) is out of scope; pass '
+                                  '--use_gender_classifier False --gender <g>')
+    if args.get('use_vposer'):
+        raise NotImplementedError('use_vposer: VPoser decode is not built yet')
+    float_dtype = args.get('float_dtype', 'float32')
+    if float_dtype not in ('float32', 'float64'):
+        raise ValueError('Unknown float type {}, exiting!'.format(float_dtype))
+    dtype = torch.float64 if float_dtype == 'float64' else torch.float32
+    rank, world = sharding.init_from_env()
+    start = time.time()
+    dataset = create_dataset(img_folder=args.pop('img_folder', 'images'),
+                             keyp_folder=args.pop('keyp_folder', 'keypoints'),
+                             data_folder=args.pop('data_folder'), dtype=dtype, **args)
+    joint_map = dataset.get_model2data()
+    gender = args.get('gender', 'neutral')
+    md = BM.load_model(args.get('model_folder'), gender)
+    from . import engine
+    model = engine.Model(md, joint_map, dtype=dtype, num_betas=args.get('num_betas', 10),
+                         num_expression_coeffs=args.get('num_expression_coeffs', 10),
+                         use_pca=args.get('use_pca', True),
+                         num_pca_comps=args.get('num_pca_comps', 6),
+                         flat_hand_mean=args.get('flat_hand_mean', False),
+                         use_face_contour=args.get('use_face_contour', False))
+    items = [d for d in dataset if d]
+    mine = sharding.shard_range(len(items), rank, world)
+    items = items[mine.start:mine.stop]
+    bs = max(1, int(args.get('batch_size', 1)))
+    for lo in range(0, len(items), bs):
+        chunk = items[lo:lo + bs]
+        B = len(chunk)
+        kp = np.stack([d['keypoints'][0] for d in chunk])          # person 0 only (main.py:242-246)
+        H = [d['img'].shape[0] for d in chunk]
+        W = [d['img'].shape[1] for d in chunk]
+        reg = [_load_regression(args, d['fn']) for d in chunk]
+        batch = engine.FrameBatch(model, B)
+        out = FF.fit_frames(batch, kp, H, W, args, expose=[r[1] for r in reg],
+                            pixie=[r[0] for r in reg],
+                            return_verts=bool(args.get('save_vertices')))
+        for b, d in enumerate(chunk):
+            folder = os.path.join(result_folder, d['fn'])
+            os.makedirs(folder, exist_ok=True)
+            with open(os.path.join(folder, '000.pkl'), 'wb') as f:
+                pickle.dump(out.results[b], f, protocol=2)
+            if args.get('save_vertices'):
+                write_ply_vertices(os.path.join(folder, 'vertices.ply'), out.vertices[b])
+        batch.close()
+    sharding.finalize()
+    if rank == 0:
+        print('Processing the data took: {}'.format(
+            time.strftime('%H hours, %M minutes, %S seconds', time.gmtime(time.time() - start))))
+
+
+if __name__ == '__main__':
+    main(**parse_config())

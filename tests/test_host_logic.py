@@ -1,0 +1,180 @@
+"""Host-side logic of the drop-in surface (no GPU): config parsing, stage schedules, keypoint
+masks, regression-prior pose, camera prior, orientation flip, result writers, sharding."""
+import glob
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from tests import common as Cm
+from smplifyx_b200 import _native as N
+from smplifyx_b200 import fit_frames as FF
+from smplifyx_b200 import utils as U
+from smplifyx_b200.cmd_parser import parse_config
+
+CFG_DIR = os.path.join(Cm.ROOT, 'cfg_files')
+
+
+@pytest.mark.parametrize('fn', sorted(os.path.basename(p) for p in glob.glob(os.path.join(CFG_DIR, '*.yaml'))))
+def test_every_shipped_profile_parses_and_schedules(fn):
+    cfg = parse_config(['-c', os.path.join(CFG_DIR, fn)])
+    assert isinstance(cfg['ftol'], float) and isinstance(cfg['maxiters'], int)
+    assert all(isinstance(p, tuple) and len(p) == 2 for p in cfg['body_tri_idxs'])
+    w = FF.stage_weights(cfg)
+    assert len(w) == len(cfg['body_pose_prior_weights'])
+    assert all(len(x['jaw_prior_weight']) == 3 for x in w)
+    if not cfg['use_vposer'] and cfg['body_prior_type'] == 'l2':
+        cam, stages = FF.make_stages(cfg, Cm.layout(n_hand=cfg['num_pca_comps']))
+        assert cam.loss_kind == N.LOSS_CAMERA_INIT and cam.n_active == 6
+        for i, st in enumerate(stages):
+            assert st.stage_index == i and st.num_stages == len(stages)
+            assert st.bending_prior_weight == pytest.approx(3.17 * st.body_pose_weight)
+            assert st.opt_kind == N.OPT_LBFGSLS and st.max_iter == cfg['maxiters']
+            assert st.max_eval == cfg['maxiters'] * 5 // 4
+
+
+def test_cli_overrides_yaml(tmp_path):
+    cfg = parse_config(['-c', os.path.join(CFG_DIR, 'fit_smplx_combined_coco25.yaml'),
+                        '--maxiters', '7', '--use_vposer', 'True', '--data_folder', 'D',
+                        '--joints_to_ign', '3', '4'])
+    assert cfg['maxiters'] == 7 and cfg['use_vposer'] is True and cfg['data_folder'] == 'D'
+    assert cfg['joints_to_ign'] == [3, 4]
+    assert cfg['rho'] == 100 and cfg['regression_prior'] == 'combined'
+    bad = tmp_path / 'bad.yaml'
+    bad.write_text('body_tri_idxs: [1, 2, 3]\n')
+    with pytest.raises(AssertionError):
+        parse_config(['-c', str(bad)])
+
+
+def test_stage_weight_validation():
+    cfg = dict(body_pose_prior_weights=[1, 2, 3], shape_weights=[1, 2])
+    with pytest.raises(AssertionError):
+        FF.stage_weights(cfg)
+    w = FF.stage_weights(dict(body_pose_prior_weights=[1, 2, 3, 4]))
+    assert [x['shape_weight'] for x in w] == [1e2, 5e1, 1e1, 5.0]
+    assert w[2]['jaw_prior_weight'] == [1e1] * 3         # defaults to the shape weights
+
+
+def test_keypoint_masks_follow_reference_rules():
+    inp = Cm.golden('demo_inputs.npz')
+    kp = np.stack([inp['02_cropped/keypoints'], inp['18_cropped/keypoints']]).astype(np.float64)
+    cfg = dict(format='coco25', confidence_threshold=0.2, joints_to_ign=[1, 9, 12],
+               init_joints_idxs=[0, 1, 2, 3, 5, 6, 8, 9, 12, 15, 16, 17, 18])
+    jw, low, init = FF.keypoint_masks(kp, cfg, FF.base_joint_weights(cfg, 135))
+    for b in range(2):
+        exp_low = np.zeros(135, bool)
+        exp_low[:25] = kp[b, :25, 2] < 0.2
+        assert np.array_equal(low[b].astype(bool), exp_low)       # hands / face never "low"
+        assert np.all(jw[b][exp_low] == 0) and np.all(jw[b][[1, 9, 12]] == 0)
+        idx = [i for i in cfg['init_joints_idxs']
+               if kp[b, i, 0] != 0 and kp[b, i, 1] != 0 and not exp_low[i]]
+        assert list(np.flatnonzero(init[b])) == sorted(idx)
+
+
+def test_regression_pose_and_camera_prior():
+    from oracle import fit_port as FP
+    inp = Cm.golden('demo_inputs.npz')
+    fr = '18_cropped'
+    expose = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr + '/expose/')}
+    pixie = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr + '/pixie/')}
+    for kind in ('ExPose', 'PIXIE', 'combined'):
+        pose, go = FF.regression_pose(dict(regression_prior=kind), expose, pixie)
+        e = [FP.euler_xyz_from_matrix(torch.tensor(m)) for m in expose['body_pose']]
+        p = [FP.euler_xyz_from_matrix(torch.tensor(m)) for m in pixie['body_pose']]
+        want = {'ExPose': e, 'PIXIE': p, 'combined': e[:19] + p[19:]}[kind]
+        assert np.allclose(pose, torch.cat(want).reshape(-1).numpy(), atol=2e-6)
+        src = pixie['global_pose'] if kind == 'PIXIE' else expose['global_orient']
+        assert np.allclose(go, FP.euler_xyz_from_matrix(torch.tensor(src[0])).numpy()[0], atol=2e-6)
+    t, c = FF.camera_prior(dict(regression_prior='combined', use_camera_prior=True), 1000.0,
+                           expose, pixie)
+    assert np.allclose(t[:2], expose['transl'][:2]) and t[2] == pytest.approx(expose['transl'][2] / 5.0)
+    assert np.allclose(c, expose['center'])
+    t, c = FF.camera_prior(dict(regression_prior='PIXIE', use_camera_prior=True), 1000.0,
+                           expose, pixie)
+    l, tp, r, b = [float(v) for v in pixie['bbox']]
+    size = int(max(r - l, b - tp) * 1.1)
+    assert t[2] == pytest.approx(2000.0 / (float(pixie['body_cam'][0]) * size + 1e-9))
+    assert FF.camera_prior(dict(regression_prior=None, use_camera_prior=True), 1000.0) is None
+
+
+def test_flipped_orientation_matches_cv2():
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(5)
+    cases = [rng.normal(size=3) for _ in range(20)] + [np.zeros(3), np.array([0, 1e-9, 0]),
+                                                       np.array([0., np.pi, 0.]), np.array([np.pi, 0, 0])]
+    for go in cases:
+        want = cv2.Rodrigues(cv2.Rodrigues(go.reshape(3, 1))[0].dot(
+            cv2.Rodrigues(np.array([0., np.pi, 0]))[0]))[0].ravel()
+        got = FF.flipped_orientation(go)
+        Rw, Rg = cv2.Rodrigues(want)[0], cv2.Rodrigues(got)[0]
+        assert np.allclose(Rw, Rg, atol=1e-9)
+        if np.linalg.norm(want) < np.pi - 1e-3:
+            assert np.allclose(want, got, atol=1e-7)
+
+
+def test_guess_init_depth_formula():
+    rng = np.random.default_rng(1)
+    j3 = rng.normal(size=(3, 20, 3))
+    g2 = rng.normal(size=(3, 20, 2)) * 50
+    t = FF.guess_init_depth(j3, g2, [(5, 12), (2, 9)], 1000.0)
+    for b in range(3):
+        l3 = np.mean([np.linalg.norm(j3[b, 5] - j3[b, 12]), np.linalg.norm(j3[b, 2] - j3[b, 9])])
+        l2 = np.mean([np.linalg.norm(g2[b, 5] - g2[b, 12]), np.linalg.norm(g2[b, 2] - g2[b, 9])])
+        assert t[b, 2] == pytest.approx(1000.0 * l3 / l2) and t[b, 0] == 0 and t[b, 1] == 0
+
+
+def test_fit_plan_matches_reference_initialisation():
+    """Initial parameters / camera of the plan == what the reference set up for demo frame 02
+    (golden result keeps camera_center; the start translation is the ExPose prior)."""
+    inp = Cm.golden('demo_inputs.npz')
+    ref = Cm.golden('ref_fit_02.npz')
+    cfg = json.loads(str(ref['cfg_json']))
+    fr = '02_cropped'
+    expose = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr + '/expose/')}
+    pixie = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr + '/pixie/')}
+    L = Cm.layout()
+    plan = FF.FitPlan(L, 135, inp[fr + '/keypoints'][None], 600, 800, cfg, [expose], [pixie])
+    assert np.allclose(plan.cam[0, 2:4], ref['result/camera_center'][0])
+    assert plan.cam[0, N.SFX_CAM_DW] == pytest.approx(1000 / 600)
+    assert plan.cam[0, 0] == pytest.approx(1000.0)
+    assert plan.cam[0, N.SFX_CAM_TZ] == pytest.approx(float(expose['transl'][2]) / 5.0, rel=1e-6)
+    assert len(plan.stages) == 3 and len(plan.flip_ids) == 0 and not plan.need_guess
+    assert np.all(plan.x0[0, L.off_betas:L.off_betas + 10] == 0)
+    assert np.abs(plan.x0[0, L.off_pose:L.off_pose + 63]).max() > 0.1
+    assert plan.stages[2].pprior_kind == N.PPRIOR_REGRESSION
+
+
+def test_ply_writer_roundtrip(tmp_path):
+    from smplifyx_b200.fit_single_frame import write_ply_vertices
+    v = np.random.default_rng(0).normal(size=(10475, 3)).astype(np.float32)
+    p = tmp_path / 'vertices.ply'
+    write_ply_vertices(str(p), v)
+    raw = p.read_bytes()
+    head, body = raw.split(b'end_header\n', 1)
+    assert b'format binary_little_endian 1.0' in head and b'element vertices 10475' in head
+    assert head.count(b'property float') == 3
+    assert np.array_equal(np.frombuffer(body, dtype='<f4').reshape(-1, 3), v)
+
+
+def test_joint_maps_have_reference_sizes():
+    assert len(U.smpl_to_annotation('smplx', True, True, True, 'coco25')) == 135
+    assert len(U.smpl_to_annotation('smplx', True, True, False, 'coco25')) == 118
+    assert len(U.smpl_to_annotation('smplx', True, True, True, 'halpe')) == 136
+    assert len(U.smpl_to_annotation('smplx', True, True, True, 'coco_wholebody')) == 133
+    with pytest.raises(ValueError):
+        U.smpl_to_annotation('smplx', format='mpii')
+
+
+def test_shard_ranges_partition_the_frames():
+    from smplifyx_b200 import sharding
+    for n in (0, 1, 7, 128, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                rg = sharding.shard_range(n, r, world)
+                seen += list(rg)
+                assert abs(len(rg) - n / world) < 1
+            assert seen == list(range(n))

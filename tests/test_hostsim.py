@@ -1,0 +1,110 @@
+"""The kernel source (csrc/sfx_core.cuh) compiled for the host, single-threaded, against the
+golden vectors of the unmodified reference.  This checks the evaluation maths (forward pass,
+loss stack, analytic adjoint) of the exact code the GPU runs, without a GPU."""
+import numpy as np
+import pytest
+
+from tests import common as Cm
+from tests.hostsim.hostsim import HostSim
+from smplifyx_b200 import _native as N
+
+
+@pytest.fixture(scope='module')
+def hs64():
+    return HostSim(Cm.model_data(), Cm.joint_map(), use_double=True, **Cm.MODEL_KW)
+
+
+@pytest.fixture(scope='module')
+def hs32():
+    return HostSim(Cm.model_data(), Cm.joint_map(), use_double=False, **Cm.MODEL_KW)
+
+
+def _eval(hs, I):
+    return hs.eval(I['stage'], I['x'], I['gt'], I['conf'], I['jw'], I['cam'], I['lowconf'],
+                   I['init_mask'], I['reg_pose'])
+
+
+@pytest.mark.parametrize('case', ['l2', 'reg', 'cam', 'camconf'])
+def test_eval_f64(hs64, case):
+    ev = Cm.golden('ref_eval_f64.npz')
+    I = Cm.eval_case_inputs(ev, case)
+    r = _eval(hs64, I)
+    ref = float(ev[case + '/loss'])
+    assert abs(r['loss'] - ref) <= 1e-13 * abs(ref)
+    g_ref = Cm.golden_grad_vector(I['L'], ev, case)
+    live = g_ref != 0
+    assert np.abs(r['grad'][live] - g_ref[live]).max() <= 1e-12 * np.abs(g_ref).max()
+    if case == 'l2':
+        assert np.abs(r['joints'] - ev['l2/joints']).max() < 1e-14
+        # every parameter block the reference differentiates is live in the engine too
+        assert live.sum() == I['L'].np
+
+
+@pytest.mark.parametrize('case', ['l2', 'reg', 'cam', 'camconf'])
+def test_eval_f32(hs32, case):
+    ev = Cm.golden('ref_eval_f32.npz')
+    I = Cm.eval_case_inputs(ev, case)
+    r = _eval(hs32, I)
+    ref = float(ev[case + '/loss'])
+    assert abs(r['loss'] - ref) <= 1e-5 * abs(ref)
+    g_ref = Cm.golden_grad_vector(I['L'], ev, case)
+    live = g_ref != 0
+    assert np.abs(r['grad'][live] - g_ref[live]).max() <= 5e-4 * np.abs(g_ref).max()
+
+
+def test_gradient_against_finite_differences(hs64):
+    ev = Cm.golden('ref_eval_f64.npz')
+    I = Cm.eval_case_inputs(ev, 'reg')
+    r0 = _eval(hs64, I)
+    rng = np.random.default_rng(3)
+    for i in rng.choice(I['L'].np, size=12, replace=False):
+        h = 1e-6
+        xp, xm = I['x'].copy(), I['x'].copy()
+        xp[i] += h
+        xm[i] -= h
+        fp = hs64.eval(I['stage'], xp, I['gt'], I['conf'], I['jw'], I['cam'], I['lowconf'],
+                       I['init_mask'], I['reg_pose'])['loss']
+        fm = hs64.eval(I['stage'], xm, I['gt'], I['conf'], I['jw'], I['cam'], I['lowconf'],
+                       I['init_mask'], I['reg_pose'])['loss']
+        fd = (fp - fm) / (2 * h)
+        assert abs(fd - r0['grad'][i]) <= 1e-5 * max(1.0, abs(fd)), (i, fd, r0['grad'][i])
+
+
+def test_stage_fit_inside_reference_envelope(hs32):
+    """float32 stage fit of the host build lands inside the reference's own run-to-run
+    envelope (tests/golden/ref_envelope.npz)."""
+    ev = Cm.golden('ref_eval_f32.npz')
+    env = Cm.golden('ref_envelope.npz')
+    I = Cm.eval_case_inputs(ev, 'reg')
+    r = hs32.fit(I['stage'], I['x'], I['gt'], I['conf'], I['jw'], I['cam'], I['lowconf'],
+                 I['init_mask'], I['reg_pose'])
+    lo, hi = env['stage/final_loss'].min(), env['stage/final_loss'].max()
+    assert lo - 0.1 * (hi - lo) < r['loss'] < hi + 0.1 * (hi - lo)
+    assert r['flags'] == 0 and 40 < r['n_evals'] < 600
+
+
+def test_adam_matches_torch(hs64):
+    import torch
+    from oracle import fit_port as FP
+    ev = Cm.golden('ref_eval_f64.npz')
+    I = Cm.eval_case_inputs(ev, 'cam')
+    L = I['L']
+    st = N.make_stage(L, N.CAMERA_STAGE_BLOCKS, loss_kind=N.LOSS_CAMERA_INIT, opt_kind=N.OPT_ADAM,
+                      lr=1e-2, depth_loss_weight=100.0, maxiters=30)
+    r = hs64.fit(st, I['x'], I['gt'], I['conf'], I['jw'], I['cam'], I['lowconf'], I['init_mask'],
+                 I['reg_pose'])
+    pb = N.param_blocks(L)
+    act = np.concatenate([np.arange(pb[n][0], pb[n][0] + pb[n][1]) for n in N.CAMERA_STAGE_BLOCKS])
+    x = torch.tensor(I['x'][act], dtype=torch.float64)
+    full = I['x'].copy()
+    last = {}
+
+    def closure():
+        full[act] = x.detach().numpy()
+        e = hs64.eval(st, full, I['gt'], I['conf'], I['jw'], I['cam'], I['lowconf'],
+                      I['init_mask'], I['reg_pose'])
+        last['g'] = torch.tensor(e['grad'][act], dtype=torch.float64)
+        return torch.tensor(e['loss'], dtype=torch.float64), last['g']
+    FP.run_fitting(FP.AdamPort(x, lr=1e-2), closure, [(0, 3), (3, 6)], lambda: last['g'],
+                   maxiters=30)
+    assert np.abs(r['params'][act] - x.numpy()).max() < 1e-12
