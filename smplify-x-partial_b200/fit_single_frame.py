@@ -146,10 +146,9 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
         cam_params = [camera.translation, body_model.global_orient]
         cam_opt, cam_graph = optim_factory.create_optimizer(cam_params, **kwargs)
         closure = monitor.create_fitting_closure(
-            cam_opt, body_model, camera, gt_joints, camera_loss, joints_conf=joints_conf,
-            create_graph=cam_graph, use_vposer=False, vposer=None, pose_embedding=pose_embedding,
+            cam_opt, body_model, camera, gt_joints, camera_loss, create_graph=cam_graph, use_vposer=False, vposer=None, pose_embedding=pose_embedding,
             return_full_pose=False, return_verts=False)
-        monitor.run_fitting(cam_opt, closure, cam_params, body_model, use_vposer=False,
+        monitor.run_fitting(cam_opt, closure, cam_params, body_model, stage=0, use_vposer=False,
                             pose_embedding=pose_embedding, vposer=None)
         camera.translation.requires_grad = False
 

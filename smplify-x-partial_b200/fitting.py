@@ -4,8 +4,9 @@
   with ``forward(body_model_output, camera, gt_joints, joints_conf, body_model_faces,
   joint_weights, use_vposer, pose_embedding, stage)`` and ``reset_loss_weights(dict)``
   (fitting.py:278-520);
-* ``FittingMonitor(...)`` context manager with ``create_fitting_closure(...)`` and
-  ``run_fitting(optimizer, closure, params, body_model, ...) -> final loss`` (fitting.py:113-275);
+* ``FittingMonitor(...)`` context manager with ``create_fitting_closure(...)`` ->
+  ``fitting_func(stage=0, backward=True)`` and ``run_fitting(optimizer, closure, params,
+  body_model, stage, ...) -> final loss`` (fitting.py:113-275);
 * ``guess_init`` (fitting.py:36-110).
 
 Same names, arguments and return values; batch sizes > 1 are accepted (every frame is an
@@ -321,12 +322,10 @@ class FittingMonitor(object):
         bundle = _FitBundle(body_model, camera, gt_joints, joints_conf, joint_weights, loss,
                             use_vposer, pose_embedding)
         _FitBundle._last_model = body_model
-        stage_box = {'stage': 0}
-
-        def fitting_func(backward=True):
+        def fitting_func(stage=0, backward=True):
             if backward:
                 optimizer.zero_grad()
-            loss_b, (grad, _) = bundle.evaluate(stage_box['stage'], None)
+            loss_b, (grad, _) = bundle.evaluate(stage, None)
             if backward:
                 bm = bundle.body_model
                 for name, (off, n) in bundle.batch.blocks.items():
@@ -341,15 +340,13 @@ class FittingMonitor(object):
             self.steps += 1
             return loss_b.sum()
         fitting_func.bundle = bundle
-        fitting_func.stage_box = stage_box
         return fitting_func
 
-    def run_fitting(self, optimizer, closure, params, body_model, use_vposer=True,
-                    pose_embedding=None, vposer=None, stage=0, **kwargs):
+    def run_fitting(self, optimizer, closure, params, body_model, stage, use_vposer=True,
+                    pose_embedding=None, vposer=None, **kwargs):
         """Runs the stage; returns the reference's value (loss at the start of the last completed
         iteration): a float for batch size 1, a list of floats otherwise (fitting.py:147-217)."""
         bundle = closure.bundle
-        closure.stage_box['stage'] = stage
         if isinstance(optimizer, DeviceOptimizer):
             bundle.push()
             st, blocks = bundle.make_stage(stage, optimizer, params, maxiters=self.maxiters,
@@ -368,7 +365,7 @@ class FittingMonitor(object):
         # behaviour, every closure call is a device evaluation
         prev_loss = None
         for n in range(self.maxiters):
-            loss = optimizer.step(closure)
+            loss = optimizer.step(lambda: closure(stage=stage))
             if torch.isnan(loss).sum() > 0:
                 print('NaN loss value, stopping!')
                 break

@@ -60,8 +60,7 @@ def test_closure_writes_reference_gradients():
             opt, bm, camera=cam, gt_joints=gt, joints_conf=conf, joint_weights=jw, loss=loss,
             create_graph=cg, use_vposer=False, vposer=None, pose_embedding=emb,
             return_verts=True, return_full_pose=True)
-        closure.stage_box['stage'] = 1
-        val = closure(backward=True)
+        val = closure(stage=1, backward=True)
         assert float(val) == pytest.approx(float(ev['reg/loss']), rel=1e-10)
         for name, p in bm.named_parameters():
             if name == 'body_pose':
@@ -79,8 +78,8 @@ def test_closure_writes_reference_gradients():
         assert np.abs(out.joints.cpu().numpy()[0] - ev['l2/joints']).max() < 1e-10
         # run_fitting: one launch for the stage, parameters written back
         before = emb.detach().clone()
-        final = monitor.run_fitting(opt, closure, params, bm, pose_embedding=emb, vposer=None,
-                                    use_vposer=False, stage=1)
+        final = monitor.run_fitting(opt, closure, params, bm, 1, pose_embedding=emb, vposer=None,
+                                    use_vposer=False)
         sg = Cm.golden('ref_stage_f64.npz')
         assert abs(final - float(sg['final_loss'])) < 2e-3 * float(sg['final_loss'])
         assert float((emb.detach() - before).abs().max()) > 1e-3
@@ -105,16 +104,15 @@ def test_torch_optimizer_through_device_closure():
     emb = torch.zeros([1, 63], dtype=dtype, device=dev, requires_grad=True)
     closs = fitting.create_loss('camera_init', trans_estimation=torch.tensor([[0., 0., 3.5]]),
                                 init_joints_idxs=torch.tensor(ev['init_idxs']),
-                                depth_loss_weight=100.0, dtype=dtype).to(dev)
+                                depth_loss_weight=100.0, dtype=dtype, joints_conf=conf).to(dev)
     closs.reset_loss_weights({'data_weight': 1000.0 / int(ev['HW'][0])})
     params = [cam.translation, bm.global_orient]
     with fitting.FittingMonitor(maxiters=5, ftol=0, gtol=0) as monitor:
         opt, cg = optim_factory.create_optimizer(params, optim_type='lbfgs', lr=1.0, maxiters=5)
-        closure = monitor.create_fitting_closure(opt, bm, cam, gt, closs, joints_conf=conf,
-                                                 create_graph=cg, use_vposer=False,
+        closure = monitor.create_fitting_closure(opt, bm, cam, gt, closs, create_graph=cg, use_vposer=False,
                                                  pose_embedding=emb, return_verts=False)
         first = float(closure(backward=False))
-        last = monitor.run_fitting(opt, closure, params, bm, use_vposer=False, pose_embedding=emb)
+        last = monitor.run_fitting(opt, closure, params, bm, 0, use_vposer=False, pose_embedding=emb)
         assert last is not None and last < first
 
 
