@@ -18,6 +18,7 @@
 #include "sfx_model_prep.h"
 #include "sfx_stream.cuh"
 #include "sfx_mesh.cuh"
+#include "sfx_mesh_tc.cuh"
 
 using namespace sfx;
 
@@ -377,6 +378,7 @@ struct sfx_model {
         joint_map, inv_ptr, inv_idx, faces;
     int device = 0;
     int num_sms = 0;
+    MeshPlan mesh;        // TMA descriptor of the blend matrix for the tensor-core mesh kernel
 };
 
 template <typename T>
@@ -464,6 +466,10 @@ int sfx_model_create(const sfx_model_desc* desc, sfx_model** out) {
     cudaGetDevice(&m->device);
     cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device);
     int rc = m->use_double ? upload_model<double>(*desc, m, m->vd) : upload_model<float>(*desc, m, m->vf);
+    if (rc == SFX_OK && !m->use_double) {
+        std::string e = mesh_plan_create(m->mesh, (const float*)m->PK.p, m->V);
+        if (!e.empty()) rc = fail(SFX_ERR_CUDA, e);
+    }
     if (rc != SFX_OK) {
         delete m;
         return rc;
@@ -778,9 +784,21 @@ static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev,
         mesh_coef_kernel<float><<<b->B, 256, smem, s>>>(m->vf, b->view<float>(nullptr),
                                                        (float*)b->Acoef.p, (float*)b->Ccoef.p);
         CUDA_TRY(cudaGetLastError());
-        std::string e = mesh_forward_simt<float>(m->vf, b->B, (const float*)b->Acoef.p,
-                                                 (const float*)b->Ccoef.p, (float*)b->vposed.p,
-                                                 (float*)vertices_dev, s);
+        // blend contraction: tcgen05 / TMA kernel (SFX_MESH_SIMT=1 selects the fp32 SIMT kernel,
+        // the accuracy reference of the tf32 path); skinning: SIMT epilogue kernel
+        const char* simt = getenv("SFX_MESH_SIMT");
+        std::string e;
+        if (simt && simt[0] == '1') {
+            e = mesh_forward_simt<float>(m->vf, b->B, (const float*)b->Acoef.p,
+                                         (const float*)b->Ccoef.p, (float*)b->vposed.p,
+                                         (float*)vertices_dev, s);
+        } else {
+            e = mesh_blend_tc(m->mesh, b->B, (const float*)b->Ccoef.p, (const float*)m->vt.p,
+                              (float*)b->vposed.p, s);
+            if (e.empty())
+                e = mesh_skin<float>(m->vf, b->B, (const float*)b->Acoef.p, (const float*)b->vposed.p,
+                                     (float*)vertices_dev, s);
+        }
         if (!e.empty()) return fail(SFX_ERR_CUDA, e);
     }
     if (joints_dev) {

@@ -93,10 +93,35 @@ def test_ring_and_direct_streams_agree(model32, monkeypatch):
     assert torch.equal(l0, l1) and torch.equal(g0, g1)
 
 
+def test_tensor_core_mesh_against_simt(model32, monkeypatch):
+    """tcgen05 / TMA blend kernel (tf32 inputs, fp32 accumulation) against the fp32 SIMT kernel
+    on 130 frames (two frame tiles, ragged) with distinct parameters: the tf32 rounding of the
+    inputs bounds the vertex error by ~1e-4 m; structure errors would be centimetres."""
+    ev = Cm.golden('ref_eval_f32.npz')
+    I = Cm.eval_case_inputs(ev, 'l2')
+    B = 130
+    rng = np.random.default_rng(11)
+    x = np.repeat(I['x'][None], B, axis=0)
+    x[:, :I['L'].off_camt] += rng.normal(size=(B, I['L'].off_camt)) * 0.2
+    batch = _engine().FrameBatch(model32, B)
+    _load(batch, I, B)
+    batch.set_params(x)
+    v_tc, j_tc = batch.forward_mesh()
+    monkeypatch.setenv('SFX_MESH_SIMT', '1')
+    v_simt, j_simt = batch.forward_mesh()
+    err = (v_tc - v_simt).abs().max().item()
+    assert torch.isfinite(v_tc).all()
+    assert err < 2e-4, err
+    assert (v_tc - v_simt).abs().mean().item() < 2e-5
+    assert torch.equal(j_tc, j_simt)
+    # frames are distinct: a tile / lane mix-up would not pass
+    assert (v_simt[0] - v_simt[129]).abs().max().item() > 1e-2
+
+
 def test_full_mesh_matches_reference(model32, model64):
     ev = Cm.golden('ref_eval_f64.npz')
     I = Cm.eval_case_inputs(ev, 'l2')
-    for model, tol in ((model64, 1e-11), (model32, 2e-5)):
+    for model, tol in ((model64, 1e-11), (model32, 1e-4)):
         batch = _engine().FrameBatch(model, 3)
         _load(batch, I, 3)
         verts, joints = batch.forward_mesh()
