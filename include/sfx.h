@@ -66,6 +66,11 @@ typedef struct {
 /* smplx.create(...).to(device) -- copies and re-lays the constants on the current device. */
 int sfx_model_create(const sfx_model_desc* desc, sfx_model** out);
 void sfx_model_destroy(sfx_model* m);
+/* MaxMixturePrior on the body pose (reference prior.py:100-231, created at main.py:133-136):
+ * means [M,D], precisions [M,D,D], log(nll_weights) [M] as the reference's buffers hold them, in
+ * the model dtype (host pointers).  Call before any batch of this model is evaluated. */
+int sfx_model_set_gmm(sfx_model* m, int32_t num_gaussians, int32_t dim, const void* means,
+                      const void* precisions, const void* log_nll_weights);
 
 /* Per-batch workspace: parameters, targets, L-BFGS history for B independent frames.
  * use_vposer selects a 32-D latent pose block instead of the 63-D axis-angle one. */

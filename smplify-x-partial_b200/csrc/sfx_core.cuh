@@ -59,6 +59,11 @@ struct ModelView {
     const int* joint_map;   // [K]  keypoint -> model joint (JointMapper, utils.py:68-81)
     const int* inv_ptr;     // [NJOUT+1]  model joint -> keypoints (CSR)
     const int* inv_idx;     // [K]
+    // MaxMixturePrior on the body pose (prior.py:100-231); gmm_M = 0 when not set
+    int gmm_M, gmm_D;
+    const T* gmm_means;     // [M][D]
+    const T* gmm_prec;      // [M][D][D]
+    const T* gmm_logw;      // [M]   log(nll_weights)
     int parents[SFX_NJ];
     int order[SFX_NJ];      // joints sorted by depth
     int level_off[16];
@@ -115,6 +120,7 @@ struct Scratch {
     T al[SFX_HIST], ro[SFX_HIST];
     int act[SFX_NP_MAX];      // compact index -> full parameter index
     T red[4];
+    T gq[16];                 // mixture prior: per-component negative log-likelihood
     T loss;
     int dynrow;
     int n_evals;
@@ -407,6 +413,45 @@ SFX_FN_NOINLINE void pose_forward(const ModelView<T>& M, const SfxLayout& L, Scr
     SFX_SYNC();
 }
 
+
+// MaxMixturePrior.merged_log_likelihood (prior.py:181-196) and its gradient for one frame:
+// value = min_m [ 0.5 (x - mu_m)^T P_m (x - mu_m) - log w_m ],  grad = 0.5 (P_m* + P_m*^T)(x - mu_m*).
+// Uses S.c (free after the blend passes) for the M x D products; returns the value, writes grad[D].
+template <typename T>
+SFX_FN T gmm_prior(const ModelView<T>& M, const T* pose, Scratch<T>& S, T* grad) {
+    const int Mg = M.gmm_M, D = M.gmm_D;
+    SFX_SYNC();
+    SFX_FOR(t, Mg * D) {
+        const int m = t / D;
+        const T* row = M.gmm_prec + (long)t * D;
+        const T* mu = M.gmm_means + m * D;
+        T acc = 0;
+        for (int j = 0; j < D; ++j) acc += row[j] * (pose[j] - mu[j]);
+        S.c[t] = acc;
+    }
+    SFX_SYNC();
+    SFX_FOR(m, Mg) {
+        const T* mu = M.gmm_means + m * D;
+        T q = 0;
+        for (int i = 0; i < D; ++i) q += S.c[m * D + i] * (pose[i] - mu[i]);
+        S.gq[m] = (T)0.5 * q - M.gmm_logw[m];
+    }
+    SFX_SYNC();
+    int best = 0;
+    for (int m = 1; m < Mg; ++m)
+        if (S.gq[m] < S.gq[best]) best = m;           // torch.min keeps the first minimum
+    const T val = S.gq[best];
+    SFX_FOR(i, D) {
+        const T* mu = M.gmm_means + best * D;
+        const T* P = M.gmm_prec + (long)best * D * D;
+        T acc = 0;
+        for (int j = 0; j < D; ++j) acc += P[j * D + i] * (pose[j] - mu[j]);
+        grad[i] = (T)0.5 * (S.c[best * D + i] + acc);
+    }
+    SFX_SYNC();
+    return val;
+}
+
 // One evaluation of the stage objective and its gradient for one frame (the reference's
 // closure, fitting.py:232-273).  Reads S.x, writes S.loss and S.gfull.
 template <typename T>
@@ -622,6 +667,9 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     const T ew2 = (T)st.expr_prior_weight * (T)st.expr_prior_weight;
     const T bendw = (T)st.bending_prior_weight;
     const bool body = st.loss_kind == SFX_LOSS_SMPLIFY;
+    T gmm_val = 0;
+    const bool use_gmm = body && st.pprior_kind == SFX_PPRIOR_GMM;
+    if (use_gmm) gmm_val = gmm_prior(M, S.x + L.off_pose, S, S.dvp);    // dvp is free by now
     SFX_FOR(i, L.np) {
         T gv = 0;
         if (i >= L.off_camt && i < L.off_camt + 3) {
@@ -640,6 +688,8 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
                     gv += (T)2 * bpw2 * (S.x[i] - reg_pose[e]);
                 else if (st.pprior_kind == SFX_PPRIOR_L2)
                     gv += (T)2 * bpw2 * S.x[i];
+                else if (st.pprior_kind == SFX_PPRIOR_GMM)
+                    gv += bpw2 * S.dvp[e];
                 // bending prior on full_pose[3:66][52, 55, 9, 12] with signs (+ - - -)
                 if (e == 52 || e == 55 || e == 9 || e == 12) {
                     T sg = e == 52 ? (T)1 : (T)-1;
@@ -684,6 +734,8 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         if (st.pprior_kind == SFX_PPRIOR_REGRESSION)
             pp = block_reduce<T>(L.n_pose, [=](int i) { T d = pe[i] - reg_pose[i]; return d * d; },
                                  OpAdd<T>(), (T)0, &S.red[0]);
+        else if (use_gmm)
+            pp = gmm_val;
         else
             pp = block_reduce<T>(L.n_pose, [=](int i) { return pe[i] * pe[i]; }, OpAdd<T>(), (T)0,
                                  &S.red[0]);

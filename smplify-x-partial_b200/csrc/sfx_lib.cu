@@ -375,7 +375,7 @@ struct sfx_model {
     ModelView<float> vf;
     ModelView<double> vd;
     DevBuf PK, vt, J0, JS, Wd, hand_l, hand_r, pose_mean, sv_vid, lmk_bary, dyn_vid, dyn_bary,
-        joint_map, inv_ptr, inv_idx, faces;
+        joint_map, inv_ptr, inv_idx, faces, gmm_means, gmm_prec, gmm_logw;
     int device = 0;
     int num_sms = 0;
     MeshPlan mesh;        // TMA descriptor of the blend matrix for the tensor-core mesh kernel
@@ -479,6 +479,30 @@ int sfx_model_create(const sfx_model_desc* desc, sfx_model** out) {
 }
 
 void sfx_model_destroy(sfx_model* m) { delete m; }
+
+int sfx_model_set_gmm(sfx_model* m, int32_t num_gaussians, int32_t dim, const void* means,
+                      const void* precisions, const void* log_nll_weights) {
+    if (!m || !means || !precisions || !log_nll_weights) return fail(SFX_ERR_ARG, "null argument");
+    if (num_gaussians < 1 || num_gaussians > 16 || dim < 1 || num_gaussians * dim > SFX_KPAD)
+        return fail(SFX_ERR_ARG, "mixture prior: need 1..16 components and components x dim <= 512");
+    const size_t es = m->use_double ? 8 : 4;
+    CUDA_TRY(m->gmm_means.alloc((size_t)num_gaussians * dim * es));
+    CUDA_TRY(m->gmm_prec.alloc((size_t)num_gaussians * dim * dim * es));
+    CUDA_TRY(m->gmm_logw.alloc((size_t)num_gaussians * es));
+    CUDA_TRY(cudaMemcpy(m->gmm_means.p, means, m->gmm_means.bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->gmm_prec.p, precisions, m->gmm_prec.bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->gmm_logw.p, log_nll_weights, m->gmm_logw.bytes, cudaMemcpyHostToDevice));
+    if (m->use_double) {
+        m->vd.gmm_M = num_gaussians; m->vd.gmm_D = dim;
+        m->vd.gmm_means = (const double*)m->gmm_means.p; m->vd.gmm_prec = (const double*)m->gmm_prec.p;
+        m->vd.gmm_logw = (const double*)m->gmm_logw.p;
+    } else {
+        m->vf.gmm_M = num_gaussians; m->vf.gmm_D = dim;
+        m->vf.gmm_means = (const float*)m->gmm_means.p; m->vf.gmm_prec = (const float*)m->gmm_prec.p;
+        m->vf.gmm_logw = (const float*)m->gmm_logw.p;
+    }
+    return SFX_OK;
+}
 
 int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batch** out) {
     if (!m || !out || B < 1) return fail(SFX_ERR_ARG, "bad argument");
@@ -624,8 +648,15 @@ static int check_stage(const sfx_batch* b, const SfxStage* st) {
     if (st->history < 1 || st->history > SFX_HIST) return fail(SFX_ERR_ARG, "stage: history out of range");
     if (st->pprior_kind == SFX_PPRIOR_REGRESSION && !b->has_reg)
         return fail(SFX_ERR_ARG, "stage: regression prior requested but no reg_pose was set");
-    if (st->pprior_kind == SFX_PPRIOR_GMM || st->pprior_kind == SFX_PPRIOR_LATENT || st->use_vposer)
-        return fail(SFX_ERR_UNSUPPORTED, "GMM / VPoser pose priors are not built yet");
+    if (st->pprior_kind == SFX_PPRIOR_GMM) {
+        const int gm = b->m->use_double ? b->m->vd.gmm_M : b->m->vf.gmm_M;
+        const int gd = b->m->use_double ? b->m->vd.gmm_D : b->m->vf.gmm_D;
+        if (gm < 1) return fail(SFX_ERR_ARG, "stage: mixture prior requested but sfx_model_set_gmm was not called");
+        if (gd != b->lay.n_pose || b->use_vposer)
+            return fail(SFX_ERR_ARG, "stage: mixture prior dimension does not match the body pose");
+    }
+    if (st->pprior_kind == SFX_PPRIOR_LATENT || st->use_vposer)
+        return fail(SFX_ERR_UNSUPPORTED, "VPoser latent pose is not built yet");
     if (st->opt_kind != SFX_OPT_LBFGSLS && st->opt_kind != SFX_OPT_ADAM)
         return fail(SFX_ERR_UNSUPPORTED, "optimiser kind not supported on the device");
     return SFX_OK;

@@ -47,6 +47,22 @@ class Model(object):
         self.n_betas = int(desc.num_betas)
         self.n_expr = int(desc.num_expr)
 
+    def set_gmm(self, prior):
+        """Installs a ``prior.MaxMixturePrior`` (or anything with ``means`` [M,D], ``precisions``
+        [M,D,D], ``nll_weights`` [1,M] tensors) as the body-pose mixture prior of this model."""
+        if getattr(self, '_gmm_id', None) == id(prior):
+            return
+        tt = self.dtype
+        means = prior.means.detach().to('cpu', tt).contiguous().numpy()
+        prec = prior.precisions.detach().to('cpu', tt).contiguous().numpy()
+        logw = torch.log(prior.nll_weights.detach().to('cpu', tt)).reshape(-1).contiguous().numpy()
+        M, D = means.shape
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            N.check(self.lib, self.lib.sfx_model_set_gmm(self.h, M, D, p(means), p(prec), p(logw)))
+        self._gmm_id = id(prior)
+
     def close(self):
         if getattr(self, 'h', None):
             self.lib.sfx_model_destroy(self.h)

@@ -228,7 +228,7 @@ class FitPlan(object):
     the second (flipped) orientation.  Pure numpy; built without touching the device."""
 
     def __init__(self, L, K, keypoints, H, W, cfg, expose=None, pixie=None, body_mean_pose=None,
-                 np_dtype=np.float32):
+                 np_dtype=np.float32, body_pose_prior=None):
         B = keypoints.shape[0]
         self.B, self.K, self.L, self.cfg = B, K, L, cfg
         npd = self.np_dtype = np_dtype
@@ -257,8 +257,15 @@ class FitPlan(object):
                 self.reg[b] = pose
                 x[b, L.off_pose:L.off_pose + L.n_pose] = pose
                 x[b, L.off_go:L.off_go + 3] = go
-        elif not cfg.get('use_vposer', False) and body_mean_pose is not None:
-            x[:, L.off_pose:L.off_pose + L.n_pose] = np.asarray(body_mean_pose).reshape(1, -1)
+        elif not cfg.get('use_vposer', False):
+            # body_mean_pose = body_pose_prior.get_mean() (fit_single_frame.py:250-252)
+            if body_mean_pose is None and hasattr(body_pose_prior, 'get_mean'):
+                body_mean_pose = body_pose_prior.get_mean().detach().cpu().numpy()
+            if body_mean_pose is not None:
+                x[:, L.off_pose:L.off_pose + L.n_pose] = np.asarray(body_mean_pose).reshape(1, -1)
+        self.body_pose_prior = body_pose_prior
+        if body_pose_prior_kind(cfg) == N.PPRIOR_GMM and getattr(body_pose_prior, 'kind', '') != 'gmm':
+            raise ValueError("body_prior_type 'gmm' needs body_pose_prior=prior.MaxMixturePrior(...)")
         # --- camera initialisation (fit_single_frame.py:359-411) ---
         cam = np.zeros((B, N.SFX_CAM_STRIDE), dtype=np.float64)
         cam[:, N.SFX_CAM_FX] = focal
@@ -287,6 +294,8 @@ class FitPlan(object):
 def upload(batch, plan):
     """Host -> device copies of one batch (async on the current stream); returns the byte count."""
     import torch
+    if getattr(plan.body_pose_prior, 'kind', '') == 'gmm':
+        batch.model.set_gmm(plan.body_pose_prior)
     n = batch.set_targets(plan.keypoints, plan.jw, plan.lowconf, plan.init_mask, plan.cam, plan.reg)
     n += batch.set_params(plan.x0)
     if plan.need_guess:
@@ -391,7 +400,7 @@ def download(batch, plan, cam_loss, verts, joints):
 
 
 def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_verts=True,
-               body_mean_pose=None):
+               body_mean_pose=None, body_pose_prior=None):
     """Fits every frame of ``batch`` (an ``engine.FrameBatch``).
 
     keypoints [B,K,3] (x, y, confidence) in the reference's row order; ``H``, ``W`` scalars or
@@ -399,7 +408,7 @@ def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_vert
     reference's YAML files); ``expose`` / ``pixie`` lists of per-frame regression results.
     """
     plan = FitPlan(batch.L, batch.model.K, np.asarray(keypoints), H, W, cfg, expose, pixie,
-                   body_mean_pose, batch.model.np_dtype)
+                   body_mean_pose, batch.model.np_dtype, body_pose_prior)
     h2d = upload(batch, plan)
     cam_loss, verts, joints, launches = run(batch, plan, return_verts)
     out = download(batch, plan, cam_loss, verts, joints)

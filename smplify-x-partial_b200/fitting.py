@@ -235,6 +235,8 @@ class _FitBundle(object):
                 camrow[:, N.SFX_CAM_TZ] = loss.trans_estimation.to(device=dev, dtype=dt)[:, 2]
         elif loss.regression_pose is not None:
             reg = loss.regression_pose.to(device=dev, dtype=dt).reshape(B, -1).contiguous()
+        if getattr(getattr(loss, 'body_pose_prior', None), 'kind', '') == 'gmm':
+            bm.engine_model.set_gmm(loss.body_pose_prior)
         self._keep = (gt, conf, jw, lowconf, init_mask, camrow, reg)
         batch.set_targets_dev(gt, conf, jw, lowconf, init_mask, camrow, reg)
 

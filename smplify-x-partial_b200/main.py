@@ -74,6 +74,10 @@ def main(**args):
                          num_pca_comps=args.get('num_pca_comps', 6),
                          flat_hand_mean=args.get('flat_hand_mean', False),
                          use_face_contour=args.get('use_face_contour', False))
+    body_pose_prior = None
+    if args.get('body_prior_type') == 'gmm':
+        from .prior import create_prior
+        body_pose_prior = create_prior(prior_type='gmm', dtype=dtype, **args)
     items = [d for d in dataset if d]
     mine = sharding.shard_range(len(items), rank, world)
     items = items[mine.start:mine.stop]
@@ -88,7 +92,8 @@ def main(**args):
         batch = engine.FrameBatch(model, B)
         out = FF.fit_frames(batch, kp, H, W, args, expose=[r[1] for r in reg],
                             pixie=[r[0] for r in reg],
-                            return_verts=bool(args.get('save_vertices')))
+                            return_verts=bool(args.get('save_vertices')),
+                            body_pose_prior=body_pose_prior)
         for b, d in enumerate(chunk):
             folder = os.path.join(result_folder, d['fn'])
             os.makedirs(folder, exist_ok=True)

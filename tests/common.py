@@ -76,10 +76,10 @@ def eval_case_inputs(ev, case):
     init_mask = np.zeros(K, np.uint8)
     init_mask[ev['init_idxs']] = 1
     cam = cam_row(float(ev['focal']), ev['center'], 1000.0 / H, tz_est=3.5)
-    if case in ('l2', 'reg'):
+    if case in ('l2', 'reg', 'gmm'):
         st = N.make_stage(
             L, N.BODY_STAGE_BLOCKS, loss_kind=N.LOSS_SMPLIFY,
-            pprior_kind=N.PPRIOR_REGRESSION if case == 'reg' else N.PPRIOR_L2,
+            pprior_kind={'reg': N.PPRIOR_REGRESSION, 'l2': N.PPRIOR_L2, 'gmm': N.PPRIOR_GMM}[case],
             stage_index=1, num_stages=3, body_pose_weight=w['body_pose_weight'],
             shape_weight=w['shape_weight'], bending_prior_weight=w['bending_prior_weight'],
             hand_prior_weight=w['hand_prior_weight'], expr_prior_weight=w['expr_prior_weight'],
@@ -102,3 +102,17 @@ def golden_grad_vector(L, ev, case):
     named = {k[len(case) + 6:]: ev[k] for k in ev if k.startswith(case + '/grad/')}
     cam = named.pop('camera_translation', None)
     return pack_params(L, named, cam_t=cam)
+
+
+def gmm_prior(dtype):
+    """The synthetic 8 x 63 mixture (same seed as make_golden.py) as a product MaxMixturePrior."""
+    from smplifyx_b200 import prior as P
+    return P.MaxMixturePrior(num_gaussians=8, dtype=dtype,
+                             gmm=synthetic.make_gmm_like(seed=1, num_gaussians=8, dim=63))
+
+
+def gmm_arrays(dtype):
+    import torch
+    pr = gmm_prior(dtype)
+    return (pr.means.numpy(), pr.precisions.numpy(),
+            torch.log(pr.nll_weights).reshape(-1).numpy())

@@ -223,11 +223,19 @@ def ref_eval(inputs, dtype=torch.float64, tag='f64'):
                    expr_prior_weight=5.0, jaw_prior_weight=[100.0, 1000.0, 1000.0],
                    coll_loss_weight=0.0)
     out['weights_json'] = np.array(json.dumps(weights))
-    for case, regression in (('l2', None), ('reg', reg)):
+    # synthetic 8-component mixture prior written in the gmm_08.pkl format the reference loads
+    gdir = tempfile.mkdtemp()
+    with open(os.path.join(gdir, 'gmm_08.pkl'), 'wb') as f:
+        pickle.dump(synthetic.make_gmm_like(seed=1, num_gaussians=8, dim=63), f)
+    gmm_prior = ref.prior.create_prior('gmm', prior_folder=gdir, num_gaussians=8, dtype=dtype)
+    for case, regression in (('l2', None), ('reg', reg), ('gmm', None)):
+        pri_case = dict(pri)
+        if case == 'gmm':
+            pri_case['body_pose_prior'] = gmm_prior
         loss = ref.fitting.create_loss(
             loss_type='smplify', rho=100, use_joints_conf=True, use_face=True, use_hands=True,
             vposer=None, interpenetration=False, dtype=dtype, regression_pose=regression,
-            num_stages=3, **pri)
+            num_stages=3, **pri_case)
         loss.reset_loss_weights({k: v for k, v in weights.items()})
         for p in list(body_model.parameters()) + [emb, camera.translation]:
             p.grad = None

@@ -45,6 +45,12 @@ class HostSim(object):
         self.L = N.SfxLayout()
         self.lib.hs_layout(self.h, int(use_vposer), C.byref(self.L))
 
+    def set_gmm(self, means, precisions, log_nll_weights):
+        a = [np.ascontiguousarray(x, dtype=self.dt) for x in (means, precisions, log_nll_weights)]
+        self.lib.hs_set_gmm.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3
+        self.lib.hs_set_gmm(self.h, a[0].shape[0], a[0].shape[1],
+                            *[x.ctypes.data_as(C.c_void_p) for x in a])
+
     def __del__(self):
         try:
             self.lib.hs_model_destroy(self.h)

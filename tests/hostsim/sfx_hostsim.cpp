@@ -18,6 +18,8 @@ using namespace sfx;
 template <typename T>
 struct SimModel {
     HostModel<T> h;
+    int gmm_M = 0, gmm_D = 0;
+    std::vector<T> gmm_means, gmm_prec, gmm_logw;
 };
 struct SimHandle {
     int use_double;
@@ -31,6 +33,8 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
                 const unsigned char* init_mask, const T* cam, const T* reg_pose, T* loss_out,
                 T* grad_out, T* joints_out, int* n_evals, int* flags) {
     ModelView<T> M = sm.h.host_view();
+    M.gmm_M = sm.gmm_M; M.gmm_D = sm.gmm_D;
+    M.gmm_means = sm.gmm_means.data(); M.gmm_prec = sm.gmm_prec.data(); M.gmm_logw = sm.gmm_logw.data();
     SfxLayout L = make_layout(sm.h.NB, sm.h.NE, sm.h.NH, use_vposer);
     std::unique_ptr<Scratch<T>> Sp(new Scratch<T>());
     Scratch<T>& S = *Sp;
@@ -54,6 +58,13 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
     *n_evals = S.n_evals;
 }
 
+template <typename T>
+static void set_gmm(SimModel<T>& sm, int M, int D, const T* means, const T* prec, const T* logw) {
+    sm.gmm_M = M; sm.gmm_D = D;
+    sm.gmm_means.assign(means, means + (size_t)M * D);
+    sm.gmm_prec.assign(prec, prec + (size_t)M * D * D);
+    sm.gmm_logw.assign(logw, logw + M);
+}
 extern "C" {
 int hs_trace(double* out, int cap) {
     int n = (int)g_trace.size();
@@ -81,6 +92,12 @@ void* hs_model_create(const sfx_model_desc* desc, char* err, int errlen) {
     return h;
 }
 void hs_model_destroy(void* p) { delete (SimHandle*)p; }
+
+void hs_set_gmm(void* p, int M, int D, const void* means, const void* prec, const void* logw) {
+    SimHandle* h = (SimHandle*)p;
+    if (h->use_double) set_gmm<double>(h->d, M, D, (const double*)means, (const double*)prec, (const double*)logw);
+    else set_gmm<float>(h->f, M, D, (const float*)means, (const float*)prec, (const float*)logw);
+}
 
 int hs_layout(void* p, int use_vposer, SfxLayout* out) {
     SimHandle* h = (SimHandle*)p;

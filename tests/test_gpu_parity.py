@@ -81,6 +81,23 @@ def test_eval_matches_reference_f32(model32, case):
         assert np.abs(joints.cpu().numpy()[0] - ev['l2/joints']).max() < 2e-5
 
 
+def test_mixture_prior_matches_reference(model32, model64):
+    ev64, ev32 = Cm.golden('ref_eval_f64.npz'), Cm.golden('ref_eval_f32.npz')
+    for model, ev, dt, tl, tg in ((model64, ev64, torch.float64, 1e-10, 1e-9),
+                                  (model32, ev32, torch.float32, 1e-5, 5e-4)):
+        model.set_gmm(Cm.gmm_prior(dt))
+        I = Cm.eval_case_inputs(ev, 'gmm')
+        batch = _engine().FrameBatch(model, 2)
+        _load(batch, I, 2)
+        loss, grad, _ = batch.eval(I['stage'])
+        ref = float(ev['gmm/loss'])
+        assert np.allclose(loss.cpu().numpy(), ref, rtol=tl, atol=0)
+        g_ref = Cm.golden_grad_vector(I['L'], ev, 'gmm')
+        assert np.abs(grad.cpu().numpy()[1] - g_ref).max() <= tg * np.abs(g_ref).max()
+        final = batch.fit_stage(I['stage']).cpu().numpy()
+        assert np.all(np.isfinite(final)) and np.all(final < 0.5 * ref)
+
+
 def test_ring_and_direct_streams_agree(model32, monkeypatch):
     """The TMA ring and the plain-load path of the blend passes give the same bits."""
     ev = Cm.golden('ref_eval_f32.npz')

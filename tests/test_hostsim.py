@@ -52,6 +52,21 @@ def test_eval_f32(hs32, case):
     assert np.abs(r['grad'][live] - g_ref[live]).max() <= 5e-4 * np.abs(g_ref).max()
 
 
+def test_mixture_prior_f64(hs64):
+    """MaxMixturePrior branch of the pose prior (prior.py:181-196) against the reference."""
+    import torch
+    ev = Cm.golden('ref_eval_f64.npz')
+    I = Cm.eval_case_inputs(ev, 'gmm')
+    hs64.set_gmm(*Cm.gmm_arrays(torch.float64))
+    r = _eval(hs64, I)
+    ref = float(ev['gmm/loss'])
+    assert abs(r['loss'] - ref) <= 1e-12 * abs(ref)
+    g_ref = Cm.golden_grad_vector(I['L'], ev, 'gmm')
+    assert np.abs(r['grad'] - g_ref).max() <= 1e-11 * np.abs(g_ref).max()
+    # the prior is what makes this case differ from plain L2
+    assert abs(ref - float(ev['l2/loss'])) > 1e3
+
+
 def test_gradient_against_finite_differences(hs64):
     ev = Cm.golden('ref_eval_f64.npz')
     I = Cm.eval_case_inputs(ev, 'reg')
