@@ -36,7 +36,29 @@
 #define SFX_NT 1
 #define SFX_SYNC() ((void)0)
 #endif
+#if defined(__CUDACC__) && defined(SFX_CYCLE_PROF)
+#define SFX_PROF_BEGIN(name) long long _t_##name = clock64()
+#define SFX_PROF_END(S, slot, name) do { if (threadIdx.x == 0) (S).prof[slot] += clock64() - _t_##name; } while (0)
+#else
+#define SFX_PROF_BEGIN(name) ((void)0)
+#define SFX_PROF_END(S, slot, name) ((void)0)
+#endif
 #define SFX_FOR(i, n) for (int i = SFX_TID; i < (n); i += SFX_NT)
+// same, the iteration space starting at thread `first` (spreads independent loops of one phase
+// over different warps)
+#define SFX_FOR_FROM(i, n, first) \
+    for (int i = (SFX_TID + SFX_NT - ((first) % SFX_NT)) % SFX_NT; i < (n); i += SFX_NT)
+#ifdef __CUDACC__
+#define SFX_IS_WARP0 (threadIdx.x < 32)
+#define SFX_ON_THREAD(t) ((int)threadIdx.x == ((t) % (int)blockDim.x))
+#define SFX_LANE_FOR(i, n) for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
+#define SFX_SYNCWARP() __syncwarp()
+#else
+#define SFX_IS_WARP0 true
+#define SFX_ON_THREAD(t) true
+#define SFX_LANE_FOR(i, n) for (int i = 0; i < (n); ++i)
+#define SFX_SYNCWARP() ((void)0)
+#endif
 
 namespace sfx {
 
@@ -91,6 +113,7 @@ struct BatchView {
     int* n_passes;       // [B]  blend-matrix passes streamed (1 per forward, 1 per adjoint)
     int* flags;          // [B]
     const int* frame_ids;   // optional indirection (nullptr: block b -> frame b)
+    long long* prof;        // [B][8] cycle counters (builds with -DSFX_CYCLE_PROF only)
 };
 
 // per-frame working set (shared memory on the device)
@@ -119,7 +142,15 @@ struct Scratch {
     T m1[SFX_NP_MAX], m2[SFX_NP_MAX];   // Adam moments
     T al[SFX_HIST], ro[SFX_HIST];
     int act[SFX_NP_MAX];      // compact index -> full parameter index
-    T red[4];
+    T red[12];
+    T confsq;                 // camera stage: sum of squared confidences of the init joints
+    T vt_s[SFX_NSLOT * 3];    // template position of the support rows
+    float ww[SFX_NSLOT * SFX_NW], jt_w[SFX_NSLOT * SFX_NW];    // skinning weights by slot / by joint
+    unsigned char wj[SFX_NSLOT * SFX_NW], jt_slot[SFX_NSLOT * SFX_NW], wn[SFX_NSLOT];
+    int jt_ptr[SFX_NJ + 1];
+    int w_overflow, dynrow_cached;
+    T tl_red[64];             // two-loop recursion: per-lane partial sums (double buffered)
+    long long prof[8];        // cycle counters: 0 eval, 1 two-loop, 2 blend fwd, 3 blend adj, 4 total
     T gq[16];                 // mixture prior: per-component negative log-likelihood
     T loss;
     int dynrow;
@@ -269,7 +300,7 @@ static void blend_forward(const ModelView<T>& M, Scratch<T>& S, void*) {
         const T* p = M.PK + row * SFX_KPAD;
         T acc = 0;
         for (int k = 0; k < SFX_KPAD; ++k) acc += p[k] * S.c[k];
-        S.vp[r] = M.vt[row] + acc;
+        S.vp[r] = S.vt_s[r] + acc;
     }
 }
 template <typename T>
@@ -289,13 +320,96 @@ struct FrameConst {          // per-frame constants decoded from the BatchView "
     double fx, fy, cx, cy, Rc[9], dw, tz_est;
 };
 
-// Pose prologue of one frame: full pose (hand PCA + mean), Rodrigues, rest joints from the
-// shape, blend coefficients, yaw row of the contour table, kinematic chain, skinning
-// transforms A and the 55 posed skeleton joints.  Reads S.x.
+// ------------------------------------------------------------------ support-vertex tables
+// The loss reads the mesh through <= 225 "support" vertex slots: 21 extra-joint vertices, 51 x 3
+// static landmark triangle corners and 17 x 3 dynamic-contour corners (these change with the yaw
+// row of the contour look-up table).  Per frame the kernel keeps, in shared memory, each slot's
+// vertex id, barycentric weight, template position and its non-zero skinning weights both by slot
+// (forward) and by joint (adjoint), so an evaluation touches global memory only for the blend rows.
 template <typename T>
-SFX_FN_NOINLINE void pose_forward(const ModelView<T>& M, const SfxLayout& L, Scratch<T>& S) {
+SFX_FN void support_slots(const ModelView<T>& M, Scratch<T>& S, int s_begin, int s_end) {
+    SFX_FOR(i, s_end - s_begin) {
+        const int s = s_begin + i;
+        int vid;
+        T b;
+        if (s < SFX_NSTATIC) {
+            vid = M.sv_vid[s];
+            b = s < SFX_NEXTRA ? (T)1 : M.lmk_bary[s - SFX_NEXTRA];
+        } else if (M.use_contour) {
+            vid = M.dyn_vid[S.dynrow * 51 + s - SFX_NSTATIC];
+            b = M.dyn_bary[S.dynrow * 51 + s - SFX_NSTATIC];
+        } else {
+            vid = M.sv_vid[0];
+            b = 0;
+        }
+        S.vid[s] = vid;
+        S.bary[s] = b;
+        for (int k = 0; k < 3; ++k) S.vt_s[3 * s + k] = M.vt[3L * vid + k];
+        const T* w = M.Wd + (long)vid * SFX_WROW;
+        int n = 0;
+        for (int j = 0; j < SFX_NJ; ++j) {
+            const T wj = w[j];
+            if (wj != (T)0) {
+                if (n < SFX_NW) {
+                    S.wj[s * SFX_NW + n] = (unsigned char)j;
+                    S.ww[s * SFX_NW + n] = (float)wj;      // model weights are float32: exact
+                }
+                ++n;
+            }
+        }
+        S.wn[s] = (unsigned char)(n <= SFX_NW ? n : SFX_NW);
+        if (n > SFX_NW) S.w_overflow = 1;                  // dense fall-back for this frame
+    }
+}
+
+// by-joint transpose of the per-slot lists (entries of a joint in ascending slot order)
+template <typename T>
+SFX_FN void support_by_joint(Scratch<T>& S) {
+    SFX_SYNC();
+    SFX_FOR(j, SFX_NJ) {
+        int cnt = 0;
+        for (int s = 0; s < SFX_NSLOT; ++s)
+            for (int e = 0; e < S.wn[s]; ++e) cnt += S.wj[s * SFX_NW + e] == j;
+        S.jt_ptr[j + 1] = cnt;
+    }
+    SFX_SYNC();
+    if (SFX_TID == 0) {
+        S.jt_ptr[0] = 0;
+        for (int j = 0; j < SFX_NJ; ++j) S.jt_ptr[j + 1] += S.jt_ptr[j];
+    }
+    SFX_SYNC();
+    SFX_FOR(j, SFX_NJ) {
+        int pos = S.jt_ptr[j];
+        for (int s = 0; s < SFX_NSLOT; ++s)
+            for (int e = 0; e < S.wn[s]; ++e)
+                if (S.wj[s * SFX_NW + e] == j) {
+                    S.jt_slot[pos] = (unsigned char)s;
+                    S.jt_w[pos] = S.ww[s * SFX_NW + e];
+                    ++pos;
+                }
+    }
+    SFX_SYNC();
+}
+
+// once per frame (and per kernel launch): static slots; the dynamic ones follow the yaw row
+template <typename T>
+SFX_FN void support_begin_frame(const ModelView<T>& M, Scratch<T>& S) {
+    SFX_SYNC();
+    if (SFX_TID == 0) {
+        S.w_overflow = 0;
+        S.dynrow_cached = -1;
+    }
+    SFX_SYNC();
+    support_slots(M, S, 0, SFX_NSTATIC);
+    SFX_SYNC();
+}
+
+// ------------------------------------------------------------------ pose prologue
+// Full pose (hand PCA + mean), Rodrigues, rest joints from the shape, blend coefficients, yaw row
+// of the contour table.  Reads S.x.  Ends synchronised.
+template <typename T>
+SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>& S) {
     const int NS = M.NS;
-    // ---- 0. full pose, hand PCA, shape vector ------------------------------------------
     SFX_FOR(i, SFX_NPOSE) {
         T v;
         if (i < 3) v = S.x[L.off_go + i];
@@ -314,39 +428,23 @@ SFX_FN_NOINLINE void pose_forward(const ModelView<T>& M, const SfxLayout& L, Scr
         }
         S.fp[i] = v + M.pose_mean[i];
     }
-    SFX_FOR(i, 32) {
+    SFX_FOR_FROM(i, 32, 192) {
         T v = 0;
         if (i < L.n_betas) v = S.x[L.off_betas + i];
         else if (i < L.n_betas + L.n_expr) v = S.x[L.off_expr + i - L.n_betas];
         S.shape[i] = v;
     }
     SFX_SYNC();
-    // ---- 1. joint rotations, rest joints ------------------------------------------------
+    // joint rotations (threads 0..54), rest joints (threads 64..228), yaw row (thread 256)
     SFX_FOR(j, SFX_NJ) rodrigues(S.fp + 3 * j, S.R + 9 * j);
-    SFX_FOR(i, SFX_NJ * 3) {
+    SFX_FOR_FROM(i, SFX_NJ * 3, 64) {
         T acc = M.J0[i];
         const T* js = M.JS + i * 32;
         for (int s = 0; s < NS; ++s) acc += js[s] * S.shape[s];
         S.Jr[i] = acc;
     }
-    SFX_SYNC();
-    // blend coefficients: pose feature (R_j - I for j >= 1) | shape | 0
-    SFX_FOR(i, SFX_KPAD) {
-        T v = 0;
-        if (i < SFX_NPF) {
-            int e = i % 9;
-            v = S.R[9 + i] - ((e == 0 || e == 4 || e == 8) ? (T)1 : (T)0);
-        } else if (i < SFX_NPF + NS) {
-            v = S.shape[i - SFX_NPF];
-        }
-        S.c[i] = v;
-    }
-    SFX_FOR(i, SFX_NJ * 3) {
-        int j = i / 3, p = M.parents[j];
-        S.rel[i] = p < 0 ? S.Jr[i] : S.Jr[i] - S.Jr[3 * p + (i % 3)];
-    }
-    // dynamic-contour look-up row (smplx lbs.find_dynamic_lmk_idx_and_bcoords)
-    if (SFX_TID == 0) {
+    if (SFX_ON_THREAD(256)) {
+        // dynamic-contour look-up row (smplx lbs.find_dynamic_lmk_idx_and_bcoords)
         int row = 0;
         if (M.use_contour) {
             T rel[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tmp[9], Rn[9];
@@ -366,53 +464,152 @@ SFX_FN_NOINLINE void pose_forward(const ModelView<T>& M, const SfxLayout& L, Scr
         S.dynrow = row;
     }
     SFX_SYNC();
-    SFX_FOR(s, SFX_NSLOT) {
-        if (s < SFX_NSTATIC) {
-            S.vid[s] = M.sv_vid[s];
-            S.bary[s] = s < SFX_NEXTRA ? (T)1 : M.lmk_bary[s - SFX_NEXTRA];
-        } else if (M.use_contour) {
-            S.vid[s] = M.dyn_vid[S.dynrow * 51 + s - SFX_NSTATIC];
-            S.bary[s] = M.dyn_bary[S.dynrow * 51 + s - SFX_NSTATIC];
-        } else {
-            S.vid[s] = M.sv_vid[0];
-            S.bary[s] = 0;
+    // blend coefficients: pose feature (R_j - I for j >= 1) | shape | 0
+    SFX_FOR(i, SFX_KPAD) {
+        T v = 0;
+        if (i < SFX_NPF) {
+            int e = i % 9;
+            v = S.R[9 + i] - ((e == 0 || e == 4 || e == 8) ? (T)1 : (T)0);
+        } else if (i < SFX_NPF + NS) {
+            v = S.shape[i - SFX_NPF];
         }
+        S.c[i] = v;
     }
-    // ---- 2. kinematic chain, level by level -------------------------------------------
-    for (int lv = 0; lv < M.nlev; ++lv) {
-        int a = M.level_off[lv], b = M.level_off[lv + 1];
-        SFX_FOR(i, b - a) {
-            int j = M.order[a + i], p = M.parents[j];
-            if (p < 0) {
-                for (int k = 0; k < 9; ++k) S.Rw[9 * j + k] = S.R[9 * j + k];
-                for (int k = 0; k < 3; ++k) S.tw[3 * j + k] = S.Jr[3 * j + k];
-            } else {
-                mat3_mul(S.Rw + 9 * p, S.R + 9 * j, S.Rw + 9 * j);
-                const T* Rp = S.Rw + 9 * p;
-                const T* rl = S.rel + 3 * j;
-                for (int k = 0; k < 3; ++k)
-                    S.tw[3 * j + k] = Rp[3 * k] * rl[0] + Rp[3 * k + 1] * rl[1] +
-                                      Rp[3 * k + 2] * rl[2] + S.tw[3 * p + k];
-            }
-        }
+    SFX_FOR(i, SFX_NJ * 3) {
+        int j = i / 3, p = M.parents[j];
+        S.rel[i] = p < 0 ? S.Jr[i] : S.Jr[i] - S.Jr[3 * p + (i % 3)];
+    }
+    if (S.dynrow != S.dynrow_cached) {          // uniform: dynrow was written before the barrier
         SFX_SYNC();
-    }
-    SFX_FOR(j, SFX_NJ) {
-        const T* Rj = S.Rw + 9 * j;
-        const T* J = S.Jr + 3 * j;
-        T* A = S.A + 12 * j;
-        for (int r = 0; r < 3; ++r) {
-            A[4 * r] = Rj[3 * r];
-            A[4 * r + 1] = Rj[3 * r + 1];
-            A[4 * r + 2] = Rj[3 * r + 2];
-            A[4 * r + 3] = S.tw[3 * j + r] -
-                           (Rj[3 * r] * J[0] + Rj[3 * r + 1] * J[1] + Rj[3 * r + 2] * J[2]);
-        }
-        for (int k = 0; k < 3; ++k) S.X[3 * j + k] = S.tw[3 * j + k];
+        support_slots(M, S, SFX_NSTATIC, SFX_NSLOT);
+        support_by_joint(S);
+        if (SFX_TID == 0) S.dynrow_cached = S.dynrow;
     }
     SFX_SYNC();
 }
 
+// Kinematic chain, skinning transforms A and the 55 posed skeleton joints -- one warp, level by
+// level with warp-level synchronisation only (the rest of the block streams blend rows meanwhile).
+// Operands are staged in registers: the shared-memory arrays may alias as far as the compiler
+// knows, which would serialise every load behind the previous store.
+template <typename T>
+SFX_FN void chain_forward(const ModelView<T>& M, Scratch<T>& S) {
+    for (int lv = 0; lv < M.nlev; ++lv) {
+        int a = M.level_off[lv], b = M.level_off[lv + 1];
+        SFX_LANE_FOR(i, b - a) {
+            const int j = M.order[a + i], p = M.parents[j];
+            T Rj[9], out[9], t[3];
+            for (int k = 0; k < 9; ++k) Rj[k] = S.R[9 * j + k];
+            if (p < 0) {
+                for (int k = 0; k < 9; ++k) out[k] = Rj[k];
+                for (int k = 0; k < 3; ++k) t[k] = S.Jr[3 * j + k];
+            } else {
+                T Rp[9], rl[3], tp[3];
+                for (int k = 0; k < 9; ++k) Rp[k] = S.Rw[9 * p + k];
+                for (int k = 0; k < 3; ++k) { rl[k] = S.rel[3 * j + k]; tp[k] = S.tw[3 * p + k]; }
+                mat3_mul(Rp, Rj, out);
+                for (int k = 0; k < 3; ++k)
+                    t[k] = Rp[3 * k] * rl[0] + Rp[3 * k + 1] * rl[1] + Rp[3 * k + 2] * rl[2] + tp[k];
+            }
+            for (int k = 0; k < 9; ++k) S.Rw[9 * j + k] = out[k];
+            for (int k = 0; k < 3; ++k) S.tw[3 * j + k] = t[k];
+            // A_j = [Rw | tw - Rw J_rest], posed joint = tw
+            T J[3], Aj[12];
+            for (int k = 0; k < 3; ++k) J[k] = S.Jr[3 * j + k];
+            for (int r = 0; r < 3; ++r) {
+                Aj[4 * r] = out[3 * r];
+                Aj[4 * r + 1] = out[3 * r + 1];
+                Aj[4 * r + 2] = out[3 * r + 2];
+                Aj[4 * r + 3] = t[r] - (out[3 * r] * J[0] + out[3 * r + 1] * J[1] + out[3 * r + 2] * J[2]);
+            }
+            for (int k = 0; k < 12; ++k) S.A[12 * j + k] = Aj[k];
+            for (int k = 0; k < 3; ++k) S.X[3 * j + k] = t[k];
+        }
+        SFX_SYNCWARP();
+    }
+}
+
+// Adjoint of chain_forward (one warp): dA, dX[0..55) -> dR (chain part), drel, dJ (A part).
+template <typename T>
+SFX_FN void chain_adjoint(const ModelView<T>& M, Scratch<T>& S) {
+    for (int lv = M.nlev - 1; lv >= 0; --lv) {
+        int a = M.level_off[lv], b = M.level_off[lv + 1];
+        SFX_LANE_FOR(i, b - a) {
+            const int j = M.order[a + i], p = M.parents[j];
+            // own terms from A_j and the posed joint
+            T dA[12], J[3], Rwj[9], dRw[9], dtw[3];
+            for (int k = 0; k < 12; ++k) dA[k] = S.dA[12 * j + k];
+            for (int k = 0; k < 3; ++k) J[k] = S.Jr[3 * j + k];
+            for (int k = 0; k < 9; ++k) Rwj[k] = S.Rw[9 * j + k];
+            for (int r = 0; r < 3; ++r) {
+                const T dat = dA[4 * r + 3];
+                for (int k = 0; k < 3; ++k) dRw[3 * r + k] = dA[4 * r + k] - dat * J[k];
+                dtw[r] = dat + S.dX[3 * j + r];
+            }
+            for (int k = 0; k < 3; ++k)
+                S.dJ[3 * j + k] = -(Rwj[k] * dA[3] + Rwj[3 + k] * dA[7] + Rwj[6 + k] * dA[11]);
+            // children (already complete: they sit one level deeper)
+            for (int e = M.child_off[j]; e < M.child_off[j + 1]; ++e) {
+                const int ch = M.child_idx[e];
+                T dRc[9], Rch[9], dtc[3], rl[3];
+                for (int k = 0; k < 9; ++k) { dRc[k] = S.dRw[9 * ch + k]; Rch[k] = S.R[9 * ch + k]; }
+                for (int k = 0; k < 3; ++k) { dtc[k] = S.dtw[3 * ch + k]; rl[k] = S.rel[3 * ch + k]; }
+                for (int r = 0; r < 3; ++r)
+                    for (int k = 0; k < 3; ++k)
+                        dRw[3 * r + k] += dRc[3 * r] * Rch[3 * k] + dRc[3 * r + 1] * Rch[3 * k + 1] +
+                                          dRc[3 * r + 2] * Rch[3 * k + 2] + dtc[r] * rl[k];
+                for (int r = 0; r < 3; ++r) dtw[r] += dtc[r];
+            }
+            for (int k = 0; k < 9; ++k) S.dRw[9 * j + k] = dRw[k];
+            for (int k = 0; k < 3; ++k) S.dtw[3 * j + k] = dtw[k];
+            if (p < 0) {
+                for (int k = 0; k < 9; ++k) S.dR[9 * j + k] = dRw[k];
+                for (int k = 0; k < 3; ++k) S.drel[3 * j + k] = dtw[k];
+            } else {
+                T Rp[9];
+                for (int k = 0; k < 9; ++k) Rp[k] = S.Rw[9 * p + k];
+                for (int r = 0; r < 3; ++r)
+                    for (int k = 0; k < 3; ++k)
+                        S.dR[9 * j + 3 * r + k] = Rp[r] * dRw[k] + Rp[3 + r] * dRw[3 + k] + Rp[6 + r] * dRw[6 + k];
+                for (int r = 0; r < 3; ++r)
+                    S.drel[3 * j + r] = Rp[r] * dtw[0] + Rp[3 + r] * dtw[1] + Rp[6 + r] * dtw[2];
+            }
+        }
+        SFX_SYNCWARP();
+    }
+}
+
+// several sums at once: warp q (q, q + nwarps, ...) reduces quantity q over i < n in the fixed
+// lane order of block_reduce(); results in out[0..nq)
+template <typename T, typename F>
+SFX_FN void multi_sum(int nq, int n, F f, T* out) {
+    SFX_SYNC();
+#ifdef __CUDACC__
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int q = warp; q < nq; q += nw) {
+        T p = 0;
+        for (int i = lane; i < n; i += 32) p = p + f(q, i);
+        for (int o = 16; o > 0; o >>= 1) p = p + __shfl_xor_sync(0xffffffffu, p, o);
+        if (lane == 0) out[q] = p;
+    }
+#else
+    for (int q = 0; q < nq; ++q) {
+        T part[32];
+        for (int l = 0; l < 32; ++l) {
+            T p = 0;
+            for (int i = l; i < n; i += 32) p = p + f(q, i);
+            part[l] = p;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            T nxt[32];
+            for (int l = 0; l < 32; ++l) nxt[l] = part[l] + part[l ^ o];
+            for (int l = 0; l < 32; ++l) part[l] = nxt[l];
+        }
+        out[q] = part[0];
+    }
+#endif
+    SFX_SYNC();
+}
 
 // MaxMixturePrior.merged_log_likelihood (prior.py:181-196) and its gradient for one frame:
 // value = min_m [ 0.5 (x - mu_m)^T P_m (x - mu_m) - log w_m ],  grad = 0.5 (P_m* + P_m*^T)(x - mu_m*).
@@ -453,7 +650,8 @@ SFX_FN T gmm_prior(const ModelView<T>& M, const T* pose, Scratch<T>& S, T* grad)
 }
 
 // One evaluation of the stage objective and its gradient for one frame (the reference's
-// closure, fitting.py:232-273).  Reads S.x, writes S.loss and S.gfull.
+// closure, fitting.py:232-273).  Reads S.x, writes S.loss and S.gfull.  Needs
+// support_begin_frame() once per frame and stage_joint_weights() once per stage beforehand.
 template <typename T>
 SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const SfxStage& st,
                                 const T* gt, const T* conf, const unsigned char* init_mask,
@@ -461,20 +659,37 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     const int NS = M.NS;
     const int nj = M.NJOUT;
     const int K = M.K;
-    pose_forward(M, L, S);
-    // ---- 3. blendshapes on the support vertices (streams 225*3 rows of PK) -----------
+    SFX_PROF_BEGIN(eval);
+    pose_prologue(M, L, S);
+    // ---- 3. kinematic chain (warp 0) || blendshapes on the support vertices (every warp) ----
+    SFX_PROF_BEGIN(bf);
+    if (SFX_IS_WARP0) chain_forward(M, S);
+    SFX_PROF_END(S, 5, bf);                     // chain alone (warp 0)
+    SFX_PROF_BEGIN(bs);
     blend_forward(M, S, stream_ws);
+#if defined(__CUDACC__) && defined(SFX_CYCLE_PROF)
+    if (threadIdx.x == 32) S.prof[6] += clock64() - _t_bs;      // warp 1's own streaming time
+#endif
     SFX_SYNC();
+    SFX_PROF_END(S, 2, bf);
     // ---- 4. skinning of the support vertices ------------------------------------------
     SFX_FOR(s, SFX_NSLOT) {
-        const T* w = M.Wd + (long)S.vid[s] * SFX_WROW;
         T Tm[12];
         for (int k = 0; k < 12; ++k) Tm[k] = 0;
-        for (int j = 0; j < SFX_NJ; ++j) {
-            T wj = w[j];
-            if (wj != (T)0) {
-                const T* A = S.A + 12 * j;
+        if (!S.w_overflow) {
+            for (int e = 0; e < S.wn[s]; ++e) {
+                const T wj = (T)S.ww[s * SFX_NW + e];
+                const T* A = S.A + 12 * S.wj[s * SFX_NW + e];
                 for (int k = 0; k < 12; ++k) Tm[k] += wj * A[k];
+            }
+        } else {
+            const T* w = M.Wd + (long)S.vid[s] * SFX_WROW;
+            for (int j = 0; j < SFX_NJ; ++j) {
+                T wj = w[j];
+                if (wj != (T)0) {
+                    const T* A = S.A + 12 * j;
+                    for (int k = 0; k < 12; ++k) Tm[k] += wj * A[k];
+                }
             }
         }
         const T* v = S.vp + 3 * s;
@@ -508,12 +723,8 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     const T dw2 = dw * dw;
     const T* ct = S.x + L.off_camt;
     const T rho2 = (T)(st.rho * st.rho);
-    T confsq = 1;
-    if (st.loss_kind == SFX_LOSS_CAMERA_INIT && st.use_conf_camera) {
-        // fitting.py:510-511: conf [1,n,1,1]^2 broadcast against err [1,n,2] -> (sum conf^2)(sum err)
-        confsq = block_reduce<T>(K, [=](int k) { return init_mask[k] ? conf[k] * conf[k] : (T)0; },
-                                 OpAdd<T>(), (T)0, &S.red[0]);
-    }
+    // fitting.py:510-511: conf [1,n,1,1]^2 broadcast against err [1,n,2] -> (sum conf^2)(sum err)
+    const T confsq = (st.loss_kind == SFX_LOSS_CAMERA_INIT && st.use_conf_camera) ? S.confsq : (T)1;
     SFX_FOR(k, K) {
         const T* Xj = S.X + 3 * M.joint_map[k];
         T px = Rc[0] * Xj[0] + Rc[1] * Xj[1] + Rc[2] * Xj[2] + ct[0];
@@ -547,12 +758,14 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.dp[3 * k + 1] = dpy;
         S.dp[3 * k + 2] = dpz;
     }
-    T data_loss = block_reduce<T>(K, [&](int k) { return S.kl[k]; }, OpAdd<T>(), (T)0, &S.red[0]);
-    // camera translation gradient = sum_k dL/dp_k
-    T gct[3];
-    for (int a = 0; a < 3; ++a)
-        gct[a] = block_reduce<T>(K, [&](int k) { return S.dp[3 * k + a]; }, OpAdd<T>(), (T)0,
-                                 &S.red[1]);
+    // data loss and camera-translation gradient (= sum_k dL/dp_k): four sums, one pass
+    {
+        const T* kl = S.kl;
+        const T* dp = S.dp;
+        multi_sum<T>(4, K, [=](int q, int k) { return q == 0 ? kl[k] : dp[3 * k + q - 1]; }, S.red);
+    }
+    const T data_loss = S.red[0];
+    const T gct[3] = {S.red[1], S.red[2], S.red[3]};
     // ---- 7. adjoint: keypoints -> model joints -> support vertices ---------------------
     SFX_FOR(i, nj * 3) {
         int j = i / 3, a = i % 3;
@@ -577,89 +790,65 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.dvp[i] = Tr[k] * dv[0] + Tr[3 + k] * dv[1] + Tr[6 + k] * dv[2];
     }
     // dA[j][r][cc] = sum_s W[vid_s][j] * dvert[s][r] * (cc < 3 ? vp[s][cc] : 1)
-    SFX_FOR(i, SFX_NJ * 12) {
+    SFX_FOR_FROM(i, SFX_NJ * 12, 160) {
         int j = i / 12, r = (i % 12) / 4, cc = i % 4;
         T acc = 0;
-        for (int s = 0; s < SFX_NSLOT; ++s) {
-            T w = M.Wd[(long)S.vid[s] * SFX_WROW + j];
-            if (w != (T)0) acc += w * S.dvert[3 * s + r] * (cc < 3 ? S.vp[3 * s + cc] : (T)1);
+        if (!S.w_overflow) {
+            for (int e = S.jt_ptr[j]; e < S.jt_ptr[j + 1]; ++e) {
+                const int s = S.jt_slot[e];
+                acc += (T)S.jt_w[e] * S.dvert[3 * s + r] * (cc < 3 ? S.vp[3 * s + cc] : (T)1);
+            }
+        } else {
+            for (int s = 0; s < SFX_NSLOT; ++s) {
+                T w = M.Wd[(long)S.vid[s] * SFX_WROW + j];
+                if (w != (T)0) acc += w * S.dvert[3 * s + r] * (cc < 3 ? S.vp[3 * s + cc] : (T)1);
+            }
         }
         S.dA[i] = acc;
     }
     SFX_SYNC();
-    // ---- 8. adjoint of the blendshapes (second stream over the PK rows) ---------------
+    // ---- 8. adjoint of the chain (warp 0) || adjoint of the blendshapes (every warp) -----
+    SFX_PROF_BEGIN(ba);
+    if (SFX_IS_WARP0) chain_adjoint(M, S);
+    SFX_PROF_END(S, 7, ba);                     // chain adjoint alone (warp 0)
     if (st.need_blend_grad) {
         blend_adjoint(M, S, stream_ws);
     } else {
         SFX_FOR(i, SFX_KPAD) S.dc[i] = 0;
     }
     SFX_SYNC();
-    // ---- 9. adjoint of the kinematic chain --------------------------------------------
+    SFX_PROF_END(S, 3, ba);
+    // ---- 9. pose-feature gradient joins the chain's; Rodrigues adjoint; rest-joint adjoint --
     SFX_FOR(j, SFX_NJ) {
-        const T* dA = S.dA + 12 * j;
-        const T* J = S.Jr + 3 * j;
-        const T* Rj = S.Rw + 9 * j;
-        for (int r = 0; r < 3; ++r) {
-            T dat = dA[4 * r + 3];
-            for (int k = 0; k < 3; ++k) S.dRw[9 * j + 3 * r + k] = dA[4 * r + k] - dat * J[k];
-            S.dtw[3 * j + r] = dat + S.dX[3 * j + r];
-        }
-        for (int k = 0; k < 3; ++k)
-            S.dJ[3 * j + k] = -(Rj[k] * dA[3] + Rj[3 + k] * dA[7] + Rj[6 + k] * dA[11]);
-        for (int k = 0; k < 9; ++k) S.dR[9 * j + k] = j >= 1 ? S.dc[9 * (j - 1) + k] : (T)0;
-    }
-    SFX_SYNC();
-    for (int lv = M.nlev - 1; lv >= 0; --lv) {
-        int a = M.level_off[lv], b = M.level_off[lv + 1];
-        SFX_FOR(i, b - a) {
-            int j = M.order[a + i], p = M.parents[j];
-            T* dRwj = S.dRw + 9 * j;
-            T* dtwj = S.dtw + 3 * j;
-            for (int e = M.child_off[j]; e < M.child_off[j + 1]; ++e) {
-                int ch = M.child_idx[e];
-                const T* dRc = S.dRw + 9 * ch;
-                const T* Rch = S.R + 9 * ch;
-                const T* dtc = S.dtw + 3 * ch;
-                const T* rl = S.rel + 3 * ch;
-                for (int r = 0; r < 3; ++r)
-                    for (int k = 0; k < 3; ++k)
-                        dRwj[3 * r + k] += dRc[3 * r] * Rch[3 * k] + dRc[3 * r + 1] * Rch[3 * k + 1] +
-                                           dRc[3 * r + 2] * Rch[3 * k + 2] + dtc[r] * rl[k];
-                for (int r = 0; r < 3; ++r) dtwj[r] += dtc[r];
-            }
-            if (p < 0) {
-                for (int k = 0; k < 9; ++k) S.dR[9 * j + k] += dRwj[k];
-                for (int k = 0; k < 3; ++k) S.drel[3 * j + k] = dtwj[k];
-            } else {
-                const T* Rp = S.Rw + 9 * p;
-                for (int r = 0; r < 3; ++r)
-                    for (int k = 0; k < 3; ++k)
-                        S.dR[9 * j + 3 * r + k] += Rp[r] * dRwj[k] + Rp[3 + r] * dRwj[3 + k] +
-                                                   Rp[6 + r] * dRwj[6 + k];
-                for (int r = 0; r < 3; ++r)
-                    S.drel[3 * j + r] = Rp[r] * dtwj[0] + Rp[3 + r] * dtwj[1] + Rp[6 + r] * dtwj[2];
-            }
-        }
-        SFX_SYNC();
+        if (j >= 1)
+            for (int k = 0; k < 9; ++k) S.dR[9 * j + k] += S.dc[9 * (j - 1) + k];
+        rodrigues_bwd(S.fp + 3 * j, S.dR + 9 * j, S.dfp + 3 * j);
     }
     // rel_j = J_j - J_parent(j)
-    SFX_FOR(i, SFX_NJ * 3) {
+    SFX_FOR_FROM(i, SFX_NJ * 3, 64) {
         int j = i / 3, k = i % 3;
         T acc = S.dJ[i] + S.drel[i];
         for (int e = M.child_off[j]; e < M.child_off[j + 1]; ++e) acc -= S.drel[3 * M.child_idx[e] + k];
-        S.dJ[i] = acc;
+        S.gl[i] = acc;                       // dL/dJ_rest (gl is rewritten after every evaluation)
     }
     SFX_SYNC();
-    SFX_FOR(s, 32) {
+    // dshape[s] = dc[486 + s] + sum_i JS[i][s] dJ[i]: 16 partial sums per s, fixed order
+    SFX_FOR(t, 512) {
+        const int sidx = t & 31, part = t >> 5;
         T acc = 0;
-        if (s < NS) {
-            acc = S.dc[SFX_NPF + s];
-            for (int i = 0; i < SFX_NJ * 3; ++i) acc += M.JS[i * 32 + s] * S.dJ[i];
-        }
-        S.dshape[s] = acc;
+        if (sidx < NS)
+            for (int i = part; i < SFX_NJ * 3; i += 16) acc += M.JS[i * 32 + sidx] * S.gl[i];
+        S.c[t] = acc;
     }
-    SFX_FOR(j, SFX_NJ) rodrigues_bwd(S.fp + 3 * j, S.dR + 9 * j, S.dfp + 3 * j);
     SFX_SYNC();
+    SFX_FOR(sidx, 32) {
+        T acc = 0;
+        if (sidx < NS) {
+            acc = S.dc[SFX_NPF + sidx];
+            for (int part = 0; part < 16; ++part) acc += S.c[part * 32 + sidx];
+        }
+        S.dshape[sidx] = acc;
+    }
     // ---- 10. priors + gradient wrt the parameter vector --------------------------------
     const T bpw2 = (T)st.body_pose_weight * (T)st.body_pose_weight;
     const T sw2 = (T)st.shape_weight * (T)st.shape_weight;
@@ -669,7 +858,8 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     const bool body = st.loss_kind == SFX_LOSS_SMPLIFY;
     T gmm_val = 0;
     const bool use_gmm = body && st.pprior_kind == SFX_PPRIOR_GMM;
-    if (use_gmm) gmm_val = gmm_prior(M, S.x + L.off_pose, S, S.dvp);    // dvp is free by now
+    if (use_gmm) gmm_val = gmm_prior(M, S.x + L.off_pose, S, S.dvp);    // c, dvp are free by now
+    SFX_SYNC();
     SFX_FOR(i, L.np) {
         T gv = 0;
         if (i >= L.off_camt && i < L.off_camt + 3) {
@@ -729,27 +919,33 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     // ---- 11. total loss, summed in the order of fitting.py:457-460 ----------------------
     T total = data_loss;
     if (body) {
-        T pp;
+        // five sums of squares at once: pose prior, betas, expression, left hand, right hand
         const T* pe = S.x + L.off_pose;
-        if (st.pprior_kind == SFX_PPRIOR_REGRESSION)
-            pp = block_reduce<T>(L.n_pose, [=](int i) { T d = pe[i] - reg_pose[i]; return d * d; },
-                                 OpAdd<T>(), (T)0, &S.red[0]);
-        else if (use_gmm)
-            pp = gmm_val;
-        else
-            pp = block_reduce<T>(L.n_pose, [=](int i) { return pe[i] * pe[i]; }, OpAdd<T>(), (T)0,
-                                 &S.red[0]);
-        total += pp * bpw2;
         const T* be = S.x + L.off_betas;
-        T sh = block_reduce<T>(L.n_betas, [=](int i) { return be[i] * be[i]; }, OpAdd<T>(), (T)0,
-                               &S.red[1]);
-        total += sh * sw2;
+        const T* ex = S.x + L.off_expr;
+        const T* hv = S.hand;
+        const int n_pose = L.n_pose, n_betas = L.n_betas, n_expr = L.n_expr;
+        const bool reg = st.pprior_kind == SFX_PPRIOR_REGRESSION;
+        multi_sum<T>(5, 64, [=](int q, int i) -> T {
+            if (q == 0) {
+                if (i >= n_pose) return (T)0;
+                T d = reg ? pe[i] - reg_pose[i] : pe[i];
+                return d * d;
+            }
+            if (q == 1) return i < n_betas ? be[i] * be[i] : (T)0;
+            if (q == 2) return i < n_expr ? ex[i] * ex[i] : (T)0;
+            if (q == 3) return i < 45 ? hv[i] * hv[i] : (T)0;
+            return i < 45 ? hv[45 + i] * hv[45 + i] : (T)0;
+        }, S.red + 4);
+        const T pp = use_gmm ? gmm_val : S.red[4];
+        total += pp * bpw2;
+        total += S.red[5] * sw2;
         T ang = 0;
         {
             const int idx[4] = {52, 55, 9, 12};
             for (int a = 0; a < 4; ++a) {
-                T ex = sfx_exp(S.fp[3 + idx[a]] * (a == 0 ? (T)1 : (T)-1));
-                ang += ex * ex;
+                T e4 = sfx_exp(S.fp[3 + idx[a]] * (a == 0 ? (T)1 : (T)-1));
+                ang += e4 * e4;
             }
         }
         total += ang * bendw;
@@ -759,16 +955,9 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
             jaw += v * v;
         }
         total += jaw;
-        const T* ex = S.x + L.off_expr;
-        T el = block_reduce<T>(L.n_expr, [=](int i) { return ex[i] * ex[i]; }, OpAdd<T>(), (T)0,
-                               &S.red[0]);
-        total += el * ew2;
-        const T* hv = S.hand;
-        T lh = block_reduce<T>(45, [=](int i) { return hv[i] * hv[i]; }, OpAdd<T>(), (T)0, &S.red[1]);
-        total += lh * hw2;
-        T rh = block_reduce<T>(45, [=](int i) { return hv[45 + i] * hv[45 + i]; }, OpAdd<T>(), (T)0,
-                               &S.red[0]);
-        total += rh * hw2;
+        total += S.red[6] * ew2;
+        total += S.red[7] * hw2;
+        total += S.red[8] * hw2;
     } else if (st.depth_loss_weight > 0) {
         T dlw = (T)st.depth_loss_weight;
         T dz = ct[2] - cam[SFX_CAM_TZ];
@@ -781,6 +970,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.n_passes += st.need_blend_grad ? 2 : 1;
     }
     SFX_SYNC();
+    SFX_PROF_END(S, 0, eval);
 #ifdef SFX_TRACE
     SFX_TRACE((double)total);
 #endif
@@ -790,8 +980,8 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
 // weights, the 42 hand keypoints take hand_joint_weight, the face block face_joint_weight, and
 // low-confidence keypoints are zeroed again.
 template <typename T>
-SFX_FN void stage_joint_weights(const SfxStage& st, const T* jw_base, const unsigned char* lowconf,
-                                int K, Scratch<T>& S) {
+SFX_FN void stage_joint_weights_only(const SfxStage& st, const T* jw_base, const unsigned char* lowconf,
+                                     int K, Scratch<T>& S) {
     SFX_FOR(k, K) {
         T w = jw_base[k];
         if (k >= st.n_body_kpts + 42) w = (T)st.face_joint_weight;
@@ -800,6 +990,25 @@ SFX_FN void stage_joint_weights(const SfxStage& st, const T* jw_base, const unsi
         S.jw[k] = w;
     }
     SFX_SYNC();
+}
+
+// camera stage with use_conf_for_camera_init: sum_k conf_k^2 over the init joints (constant
+// during the stage; fitting.py:509-511)
+template <typename T>
+SFX_FN void stage_confidence_sum(const T* conf, const unsigned char* init_mask, int K, Scratch<T>& S) {
+    T v = block_reduce<T>(K, [=](int k) { return init_mask[k] ? conf[k] * conf[k] : (T)0; },
+                          OpAdd<T>(), (T)0, &S.red[0]);
+    if (SFX_TID == 0) S.confsq = v;
+    SFX_SYNC();
+}
+
+// everything a stage needs before its first evaluation
+template <typename T>
+SFX_FN void stage_setup(const SfxStage& st, const T* jw_base, const unsigned char* lowconf,
+                        const T* conf, const unsigned char* init_mask, int K, Scratch<T>& S) {
+    stage_joint_weights_only(st, jw_base, lowconf, K, S);
+    if (st.loss_kind == SFX_LOSS_CAMERA_INIT && st.use_conf_camera)
+        stage_confidence_sum(conf, init_mask, K, S);
 }
 
 // ------------------------------------------------------- optimiser plumbing (compact <-> full)
@@ -995,71 +1204,110 @@ struct LbfgsState {
 
 
 #ifdef __CUDACC__
+// Sum of the 32 per-lane partials in exactly the association of the xor butterfly
+// (p + shfl_xor 16, 8, 4, 2, 1), but through shared memory: one store, one warp barrier, eight
+// broadcast 16-byte loads and a 5-deep add tree -- about half the latency of five dependent
+// shuffles, which matters because every step of the two-loop recursion waits on this value.
+template <typename T>
+__device__ __forceinline__ T warp_tree_sum(T p, T* slot, int lane) {
+    slot[lane] = p;
+    __syncwarp();
+    T a[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = slot[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int l = 0; l < o; ++l) a[l] = a[l] + a[l + o];
+    return a[0];
+}
+#endif
+
+#ifdef __CUDACC__
 // Two-loop recursion of one L-BFGS iteration (lbfgs_ls.py:336-358) by warp 0 alone: the
 // direction lives in registers (element e <-> lane e % 32, register e / 32), the (s, y) pairs
 // stream from global memory one pair ahead of use, and nothing synchronises the block.  The
 // arithmetic -- per-lane partial sums over e = lane, lane + 32, ... followed by an xor
 // butterfly -- is the one block_reduce() performs, so both paths produce the same bits.
-template <typename T>
-__device__ __forceinline__ void two_loop_warp(Scratch<T>& S, int k, int head, int H, T hd,
-                                              const T* hist_s, const T* hist_y, int D) {
-    constexpr int NR = SFX_NP_MAX / 32;
+template <typename T, int NR>
+__device__ __noinline__ void two_loop_warp_n(Scratch<T>& S, int k, int head, int H, T hd,
+                                            const T* hist_s, const T* hist_y, int D) {
+    constexpr int PF = 3;                 // (s, y) pairs in flight ahead of the one in use
     const int lane = threadIdx.x;
-    T q[NR], sc[NR], yc[NR], sn[NR], yn[NR];
+    T q[NR], sb[PF][NR], yb[PF][NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const int e = 32 * r + lane;
         q[r] = e < D ? -S.g[e] : (T)0;
-        sn[r] = yn[r] = 0;
     }
-    auto fetch = [&](int i) {
-        const long row = (long)((head + i) % H) * SFX_NP_MAX;
+#define SFX_TL_FETCH(slot, i)                                                      \
+    do {                                                                           \
+        const long row_ = (long)((head + (i)) % H) * SFX_NP_MAX;                   \
+        _Pragma("unroll") for (int r = 0; r < NR; ++r) {                           \
+            const int e = 32 * r + lane;                                           \
+            sb[slot][r] = e < D ? hist_s[row_ + e] : (T)0;                         \
+            yb[slot][r] = e < D ? hist_y[row_ + e] : (T)0;                         \
+        }                                                                          \
+    } while (0)
+    // ---- first loop: i = k-1 .. 0 ----
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const int e = 32 * r + lane;
-            sn[r] = e < D ? hist_s[row + e] : (T)0;
-            yn[r] = e < D ? hist_y[row + e] : (T)0;
+    for (int u = 0; u < PF; ++u)
+        if (k - 1 - u >= 0) SFX_TL_FETCH(u, k - 1 - u);
+    for (int i0 = k - 1; i0 >= 0; i0 -= PF) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int i = i0 - u;
+            if (i >= 0) {
+                T p = 0;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) p = p + sb[u][r] * q[r];
+                p = warp_tree_sum(p, S.tl_red + 32 * (i & 1), lane);
+                const T a = p * S.ro[i];
+                if (lane == 0) S.al[i] = a;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) q[r] += -a * yb[u][r];
+                if (i - PF >= 0) SFX_TL_FETCH(u, i - PF);
+            }
         }
-    };
-    if (k > 0) fetch(k - 1);
-    for (int i = k - 1; i >= 0; --i) {
-#pragma unroll
-        for (int r = 0; r < NR; ++r) { sc[r] = sn[r]; yc[r] = yn[r]; }
-        if (i > 0) fetch(i - 1);
-        T p = 0;
-#pragma unroll
-        for (int r = 0; r < NR; ++r)
-            if (32 * r < D) p = p + sc[r] * q[r];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) p = p + __shfl_xor_sync(0xffffffffu, p, o);
-        const T a = p * S.ro[i];
-        if (lane == 0) S.al[i] = a;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) q[r] += -a * yc[r];
     }
 #pragma unroll
     for (int r = 0; r < NR; ++r) q[r] = q[r] * hd;       // q now holds the direction d
     __syncwarp();
-    if (k > 0) fetch(0);
-    for (int i = 0; i < k; ++i) {
+    // ---- second loop: i = 0 .. k-1 ----
 #pragma unroll
-        for (int r = 0; r < NR; ++r) { sc[r] = sn[r]; yc[r] = yn[r]; }
-        if (i + 1 < k) fetch(i + 1);
-        T p = 0;
+    for (int u = 0; u < PF; ++u)
+        if (u < k) SFX_TL_FETCH(u, u);
+    for (int i0 = 0; i0 < k; i0 += PF) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r)
-            if (32 * r < D) p = p + yc[r] * q[r];
+        for (int u = 0; u < PF; ++u) {
+            const int i = i0 + u;
+            if (i < k) {
+                T p = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) p = p + __shfl_xor_sync(0xffffffffu, p, o);
-        const T co = S.al[i] - p * S.ro[i];
+                for (int r = 0; r < NR; ++r) p = p + yb[u][r] * q[r];
+                p = warp_tree_sum(p, S.tl_red + 32 * (i & 1), lane);
+                const T co = S.al[i] - p * S.ro[i];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) q[r] += co * sc[r];
+                for (int r = 0; r < NR; ++r) q[r] += co * sb[u][r];
+                if (i + PF < k) SFX_TL_FETCH(u, i + PF);
+            }
+        }
     }
+#undef SFX_TL_FETCH
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const int e = 32 * r + lane;
         if (e < D) S.d[e] = q[r];
     }
+}
+
+template <typename T>
+__device__ __forceinline__ void two_loop_warp(Scratch<T>& S, int k, int head, int H, T hd,
+                                              const T* hist_s, const T* hist_y, int D) {
+    // elements beyond D are zeros and add nothing, so the register count follows D
+    if (D <= 32) two_loop_warp_n<T, 1>(S, k, head, H, hd, hist_s, hist_y, D);
+    else if (D <= 128) two_loop_warp_n<T, 4>(S, k, head, H, hd, hist_s, hist_y, D);
+    else two_loop_warp_n<T, SFX_NP_MAX / 32>(S, k, head, H, hd, hist_s, hist_y, D);
 }
 #endif
 
@@ -1121,9 +1369,11 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
 #ifdef __CUDACC__
             if (!E.st->generic_two_loop) {
                 SFX_SYNC();
+                SFX_PROF_BEGIN(tl);
                 if (threadIdx.x < 32)
                     two_loop_warp(S, k, ls.head, H, ls.H_diag, hist_s, hist_y, D);
                 SFX_SYNC();
+                SFX_PROF_END(S, 1, tl);
             } else
 #endif
             {

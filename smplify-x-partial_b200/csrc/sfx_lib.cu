@@ -59,7 +59,10 @@ __device__ __forceinline__ void load_frame(const BatchView<T>& Bv, int f, Scratc
     const int np = Bv.lay.np;
     for (int i = threadIdx.x; i < SFX_NP_MAX; i += blockDim.x)
         S.x[i] = i < np ? Bv.params[(size_t)f * np + i] : (T)0;
-    if (threadIdx.x == 0) S.n_evals = S.n_passes = 0;
+    if (threadIdx.x == 0) {
+        S.n_evals = S.n_passes = 0;
+        for (int i = 0; i < 8; ++i) S.prof[i] = 0;
+    }
     __syncthreads();
 }
 
@@ -80,7 +83,9 @@ fit_stage_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__
     __syncthreads();
     stream_init<T>(ws);
     load_frame(Bv, f, S);
-    stage_joint_weights(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, K, S);
+    support_begin_frame(M, S);
+    stage_setup(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
+                Bv.init_mask + (size_t)f * K, K, S);
     EvalCtx<T> E;
     E.M = &M; E.L = &Bv.lay; E.st = &st;
     E.gt = Bv.gt + (size_t)f * K * 2;
@@ -117,7 +122,9 @@ eval_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ Batc
     __syncthreads();
     stream_init<T>(ws);
     load_frame(Bv, f, S);
-    stage_joint_weights(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, K, S);
+    support_begin_frame(M, S);
+    stage_setup(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
+                Bv.init_mask + (size_t)f * K, K, S);
     eval_frame(M, Bv.lay, st, Bv.gt + (size_t)f * K * 2, Bv.conf + (size_t)f * K,
                Bv.init_mask + (size_t)f * K, Bv.cam + (size_t)f * SFX_CAM_STRIDE,
                Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr, S, &ws);
@@ -141,7 +148,10 @@ mesh_coef_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__
     Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(smem);
     const int f = blockIdx.x;
     load_frame(Bv, f, S);
-    pose_forward(M, Bv.lay, S);
+    support_begin_frame(M, S);
+    pose_prologue(M, Bv.lay, S);
+    if (threadIdx.x < 32) chain_forward(M, S);
+    __syncthreads();
     for (int i = threadIdx.x; i < SFX_NJ * 12; i += blockDim.x) Aout[(size_t)f * SFX_NJ * 12 + i] = S.A[i];
     for (int i = threadIdx.x; i < SFX_KPAD; i += blockDim.x) Cout[(size_t)f * SFX_KPAD + i] = S.c[i];
 }
@@ -286,6 +296,8 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
         if (idx >= n_frames) break;
         const int f = Bv.frame_ids ? Bv.frame_ids[idx] : idx;
         load_frame(Bv, f, S);
+        SFX_PROF_BEGIN(total);
+        support_begin_frame(M, S);
         EvalCtx<T> E;
         E.M = &M; E.L = &Bv.lay; E.st = &st;
         E.gt = Bv.gt + (size_t)f * K * 2;
@@ -298,7 +310,8 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
         T* hy = Bv.hist_y + (size_t)f * SFX_HIST * SFX_NP_MAX;
         // stage C: camera translation + global orientation (fit_single_frame.py:473-496)
         load_stage(&P->cam);
-        stage_joint_weights(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, K, S);
+        stage_setup(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
+                Bv.init_mask + (size_t)f * K, K, S);
         double r = run_fitting(E, S, hs, hy, &flags);
         __syncthreads();
         if (threadIdx.x == 0 && cam_loss_out) cam_loss_out[f] = (T)r;
@@ -326,7 +339,8 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
             reset_for_orientation(L, S);
             for (int si = 0; si < P->n_stages; ++si) {
                 load_stage(&P->body[si]);
-                stage_joint_weights(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, K, S);
+                stage_setup(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
+                Bv.init_mask + (size_t)f * K, K, S);
                 r = run_fitting(E, S, hs, hy, &flags);
             }
         }
@@ -343,6 +357,10 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
             Bv.n_evals[f] += S.n_evals;
             Bv.n_passes[f] += S.n_passes;
             Bv.flags[f] |= flags;
+#ifdef SFX_CYCLE_PROF
+            S.prof[4] += clock64() - _t_total;
+            for (int i = 0; i < 8; ++i) Bv.prof[(size_t)f * 8 + i] = S.prof[i];
+#endif
         }
     }
 }
@@ -421,7 +439,7 @@ struct sfx_batch {
     size_t es = 4;        // element size of the batch dtype
     DevBuf params, gt, conf, jw, lowconf, init_mask, cam, reg_pose, hist_s, hist_y, final_loss,
         n_evals, n_passes, flags, Acoef, Ccoef, vposed, go_saved, params_alt, loss_alt, pipe, counter,
-        cam_loss, params_last;
+        cam_loss, params_last, prof;
     bool last_valid = false;
     bool has_reg = false;
     std::vector<unsigned char> stage_host;     // host staging for set_targets
@@ -434,7 +452,7 @@ struct sfx_batch {
         v.init_mask = (const unsigned char*)init_mask.p; v.cam = (const T*)cam.p;
         v.reg_pose = has_reg ? (const T*)reg_pose.p : nullptr;
         v.hist_s = (T*)hist_s.p; v.hist_y = (T*)hist_y.p; v.final_loss = (T*)final_loss.p;
-        v.n_evals = (int*)n_evals.p; v.n_passes = (int*)n_passes.p; v.flags = (int*)flags.p; v.frame_ids = frame_ids;
+        v.prof = (long long*)prof.p; v.n_evals = (int*)n_evals.p; v.n_passes = (int*)n_passes.p; v.flags = (int*)flags.p; v.frame_ids = frame_ids;
         return v;
     }
 };
@@ -544,6 +562,7 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     ALLOC(pipe, sizeof(SfxPipeline));
     ALLOC(counter, 64);
     ALLOC(cam_loss, (size_t)B * es);
+    ALLOC(prof, (size_t)B * 8 * sizeof(long long));
     ALLOC(params_last, (size_t)B * b->lay.np * es);
 #undef ALLOC
     *out = b;
@@ -776,6 +795,7 @@ int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order
 }
 
 void* sfx_batch_cam_loss_dev(sfx_batch* b) { return b ? b->cam_loss.p : nullptr; }
+long long* sfx_batch_prof_dev(sfx_batch* b) { return b ? (long long*)b->prof.p : nullptr; }
 
 static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream);
 

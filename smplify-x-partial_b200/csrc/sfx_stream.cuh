@@ -100,17 +100,20 @@ __device__ __forceinline__ void load_row_regs(const T* row, int lane, T* dst) {
 template <typename T, typename FN>
 __device__ __forceinline__ void stream_rows(const ModelView<T>& M, const Scratch<T>& S,
                                             StreamWS& ws, FN fn) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp 0 runs the kinematic chain while warps 1 .. NWARP-1 stream the rows
+    const int warp = (threadIdx.x >> 5) - 1, lane = threadIdx.x & 31;
+    constexpr int NSTREAM = SFX_NWARP - 1;
     const int nrows = SFX_NSLOT * 3;
-    const int count = warp < nrows ? (nrows - warp + SFX_NWARP - 1) / SFX_NWARP : 0;
+    const int count = warp >= 0 ? (nrows - warp + NSTREAM - 1) / NSTREAM : 0;
     constexpr uint32_t ROWB = SFX_KPAD * sizeof(T);
     T vals[RowVec<T>::NE];
+    if (count == 0) return;
     if (ws.ring_mode) {
         unsigned char* mybuf = ws.ring + (size_t)warp * SFX_NBUF * ROWB;
         uint64_t* mybar = ws.bars + warp * SFX_NBUF;
         const unsigned int n0 = ws.fills[warp];
         auto issue = [&](int i) {
-            int r = warp + i * SFX_NWARP;
+            int r = warp + i * NSTREAM;
             long row = (long)S.vid[r / 3] * 3 + (r % 3);
             unsigned int n = n0 + i;
             int b = n % SFX_NBUF;
@@ -131,13 +134,13 @@ __device__ __forceinline__ void stream_rows(const ModelView<T>& M, const Scratch
                 fence_proxy_async();
                 issue(i + SFX_NBUF);
             }
-            fn(warp + i * SFX_NWARP, vals);
+            fn(warp + i * NSTREAM, vals);
         }
         __syncwarp();
         if (lane == 0) ws.fills[warp] = n0 + count;
     } else {
         for (int i = 0; i < count; ++i) {
-            int r = warp + i * SFX_NWARP;
+            int r = warp + i * NSTREAM;
             long row = (long)S.vid[r / 3] * 3 + (r % 3);
             load_row_regs<T>(M.PK + row * SFX_KPAD, lane, vals);
             fn(r, vals);
@@ -160,10 +163,7 @@ __device__ __forceinline__ void blend_forward(const ModelView<T>& M, Scratch<T>&
         for (int i = 0; i < RowVec<T>::NE; ++i) acc += v[i] * c[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) {
-            long row = (long)S.vid[r / 3] * 3 + (r % 3);
-            S.vp[r] = M.vt[row] + acc;
-        }
+        if (lane == 0) S.vp[r] = S.vt_s[r] + acc;
     });
 }
 

@@ -19,6 +19,7 @@
 #define SFX_NP_MAX 192       // max length of the per-frame parameter vector
 #define SFX_HIST 100         // L-BFGS history (reference lbfgs_ls.py:200)
 #define SFX_WROW 56          // padded row length of the dense skinning-weight table
+#define SFX_NW 8             // non-zero skinning weights kept per support vertex (dense fall-back beyond)
 #define SFX_MAX_BLOCKS 12    // parameter blocks of the optimised vector (for the gtol test)
 #define SFX_NLATENT 32       // VPoser latent size
 

@@ -40,7 +40,8 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
     Scratch<T>& S = *Sp;
     std::memset(&S, 0, sizeof(S));
     for (int i = 0; i < L.np; ++i) S.x[i] = params[i];
-    stage_joint_weights(*st, jw, lowconf, M.K, S);
+    support_begin_frame(M, S);
+    stage_setup(*st, jw, lowconf, conf, init_mask, M.K, S);
     std::vector<T> hs((size_t)SFX_HIST * SFX_NP_MAX), hy((size_t)SFX_HIST * SFX_NP_MAX);
     EvalCtx<T> E{&M, &L, st, gt, conf, init_mask, cam, reg_pose, nullptr};
     if (!do_fit) {

@@ -95,7 +95,7 @@ def test_mixture_prior_matches_reference(model32, model64):
         g_ref = Cm.golden_grad_vector(I['L'], ev, 'gmm')
         assert np.abs(grad.cpu().numpy()[1] - g_ref).max() <= tg * np.abs(g_ref).max()
         final = batch.fit_stage(I['stage']).cpu().numpy()
-        assert np.all(np.isfinite(final)) and np.all(final < 0.5 * ref)
+        assert np.all(np.isfinite(final)) and np.all(final < 0.8 * ref)
 
 
 def test_ring_and_direct_streams_agree(model32, monkeypatch):
