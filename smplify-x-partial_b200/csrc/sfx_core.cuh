@@ -1231,28 +1231,38 @@ __device__ __forceinline__ T warp_tree_sum(T p, T* slot, int lane) {
 // butterfly -- is the one block_reduce() performs, so both paths produce the same bits.
 template <typename T, int NR>
 __device__ __noinline__ void two_loop_warp_n(Scratch<T>& S, int k, int head, int H, T hd,
-                                            const T* hist_s, const T* hist_y, int D) {
+                                            const T* __restrict__ hist_s,
+                                            const T* __restrict__ hist_y, int D) {
     constexpr int PF = 3;                 // (s, y) pairs in flight ahead of the one in use
     const int lane = threadIdx.x;
+    // only the last register of a lane can lie beyond D
+    const bool tail_live = 32 * (NR - 1) + lane < D;
     T q[NR], sb[PF][NR], yb[PF][NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const int e = 32 * r + lane;
         q[r] = e < D ? -S.g[e] : (T)0;
     }
-#define SFX_TL_FETCH(slot, i)                                                      \
+    // ring position of pair i is (head + i) % H; the loops walk it incrementally
+#define SFX_TL_FETCH(slot, pos)                                                    \
     do {                                                                           \
-        const long row_ = (long)((head + (i)) % H) * SFX_NP_MAX;                   \
-        _Pragma("unroll") for (int r = 0; r < NR; ++r) {                           \
-            const int e = 32 * r + lane;                                           \
-            sb[slot][r] = e < D ? hist_s[row_ + e] : (T)0;                         \
-            yb[slot][r] = e < D ? hist_y[row_ + e] : (T)0;                         \
+        const T* ps_ = hist_s + (pos) * SFX_NP_MAX + lane;                         \
+        const T* py_ = hist_y + (pos) * SFX_NP_MAX + lane;                         \
+        _Pragma("unroll") for (int r = 0; r < NR - 1; ++r) {                       \
+            sb[slot][r] = ps_[32 * r];                                             \
+            yb[slot][r] = py_[32 * r];                                             \
         }                                                                          \
+        sb[slot][NR - 1] = tail_live ? ps_[32 * (NR - 1)] : (T)0;                  \
+        yb[slot][NR - 1] = tail_live ? py_[32 * (NR - 1)] : (T)0;                  \
     } while (0)
     // ---- first loop: i = k-1 .. 0 ----
+    int fpos = (head + k - 1) % H;        // position of the next pair to fetch
 #pragma unroll
     for (int u = 0; u < PF; ++u)
-        if (k - 1 - u >= 0) SFX_TL_FETCH(u, k - 1 - u);
+        if (k - 1 - u >= 0) {
+            SFX_TL_FETCH(u, fpos);
+            fpos = fpos == 0 ? H - 1 : fpos - 1;
+        }
     for (int i0 = k - 1; i0 >= 0; i0 -= PF) {
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
@@ -1266,7 +1276,10 @@ __device__ __noinline__ void two_loop_warp_n(Scratch<T>& S, int k, int head, int
                 if (lane == 0) S.al[i] = a;
 #pragma unroll
                 for (int r = 0; r < NR; ++r) q[r] += -a * yb[u][r];
-                if (i - PF >= 0) SFX_TL_FETCH(u, i - PF);
+                if (i - PF >= 0) {
+                    SFX_TL_FETCH(u, fpos);
+                    fpos = fpos == 0 ? H - 1 : fpos - 1;
+                }
             }
         }
     }
@@ -1274,9 +1287,13 @@ __device__ __noinline__ void two_loop_warp_n(Scratch<T>& S, int k, int head, int
     for (int r = 0; r < NR; ++r) q[r] = q[r] * hd;       // q now holds the direction d
     __syncwarp();
     // ---- second loop: i = 0 .. k-1 ----
+    fpos = head % H;
 #pragma unroll
     for (int u = 0; u < PF; ++u)
-        if (u < k) SFX_TL_FETCH(u, u);
+        if (u < k) {
+            SFX_TL_FETCH(u, fpos);
+            fpos = fpos + 1 == H ? 0 : fpos + 1;
+        }
     for (int i0 = 0; i0 < k; i0 += PF) {
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
@@ -1289,7 +1306,10 @@ __device__ __noinline__ void two_loop_warp_n(Scratch<T>& S, int k, int head, int
                 const T co = S.al[i] - p * S.ro[i];
 #pragma unroll
                 for (int r = 0; r < NR; ++r) q[r] += co * sb[u][r];
-                if (i + PF < k) SFX_TL_FETCH(u, i + PF);
+                if (i + PF < k) {
+                    SFX_TL_FETCH(u, fpos);
+                    fpos = fpos + 1 == H ? 0 : fpos + 1;
+                }
             }
         }
     }

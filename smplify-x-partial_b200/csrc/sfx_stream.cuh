@@ -19,7 +19,7 @@
 namespace sfx {
 
 #define SFX_NWARP 16
-#define SFX_NBUF 3
+#define SFX_NBUF 4
 
 struct StreamWS {
     unsigned char* ring;        // ring mode: [NWARP][NBUF][512*sizeof(T)]; else partials only
