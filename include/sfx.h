@@ -66,6 +66,13 @@ typedef struct {
 /* smplx.create(...).to(device) -- copies and re-lays the constants on the current device. */
 int sfx_model_create(const sfx_model_desc* desc, sfx_model** out);
 void sfx_model_destroy(sfx_model* m);
+/* VPoser v1 decoder weights (human_body_prior cvpr19 `bodyprior_dec_fc1/fc2/out`, loaded by the
+ * reference at fit_single_frame.py:241-243): fc1 [512,32] + [512], fc2 [512,512] + [512], out
+ * [126,512] + [126], torch nn.Linear layout, model dtype, host pointers.  Needed before
+ * sfx_batch_create(..., use_vposer = 1): the pose block of such a batch is the 32-D latent and
+ * every evaluation decodes it (fitting.py:236). */
+int sfx_model_set_vposer(sfx_model* m, const void* fc1_w, const void* fc1_b, const void* fc2_w,
+                         const void* fc2_b, const void* out_w, const void* out_b);
 /* MaxMixturePrior on the body pose (reference prior.py:100-231, created at main.py:133-136):
  * means [M,D], precisions [M,D,D], log(nll_weights) [M] as the reference's buffers hold them, in
  * the model dtype (host pointers).  Call before any batch of this model is evaluated. */

@@ -244,6 +244,7 @@ def load_library(path=None):
     lib = C.CDLL(p)
     vp, i32 = C.c_void_p, C.c_int32
     lib.sfx_model_create.argtypes = [C.POINTER(SfxModelDesc), C.POINTER(vp)]
+    lib.sfx_model_set_vposer.argtypes = [vp] * 7
     lib.sfx_model_set_gmm.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.sfx_model_destroy.argtypes = [vp]
     lib.sfx_model_destroy.restype = None

@@ -86,6 +86,14 @@ struct ModelView {
     const T* gmm_means;     // [M][D]
     const T* gmm_prec;      // [M][D][D]
     const T* gmm_logw;      // [M]   log(nll_weights)
+    // VPoser v1 decoder (human_body_prior vposer_smpl.py); vp_ready = 0 when not set
+    int vp_ready;
+    const T* vp_w1;         // [512][32]   bodyprior_dec_fc1.weight
+    const T* vp_b1;         // [512]
+    const T* vp_w2;         // [512][512]  bodyprior_dec_fc2.weight
+    const T* vp_b2;         // [512]
+    const T* vp_w3;         // [128][512]  bodyprior_dec_out.weight (126 rows + 2 zero rows)
+    const T* vp_b3;         // [128]
     int parents[SFX_NJ];
     int order[SFX_NJ];      // joints sorted by depth
     int level_off[16];
@@ -149,6 +157,10 @@ struct Scratch {
     unsigned char wj[SFX_NSLOT * SFX_NW], jt_slot[SFX_NSLOT * SFX_NW], wn[SFX_NSLOT];
     int jt_ptr[SFX_NJ + 1];
     int w_overflow, dynrow_cached;
+    T bp[64];                 // VPoser: decoded body pose (63) and its gradient
+    T dbp[64];
+    T o6[128], do6[128];      // VPoser: 6-D rotation outputs and their gradient
+    unsigned char vm1[512], vm2[512]; // VPoser: leaky-ReLU masks of the two hidden layers
     T tl_red[64];             // two-loop recursion: per-lane partial sums (double buffered)
     long long prof[8];        // cycle counters: 0 eval, 1 two-loop, 2 blend fwd, 3 blend adj, 4 total
     T gq[16];                 // mixture prior: per-component negative log-likelihood
@@ -292,7 +304,25 @@ template <typename T>
 __device__ __forceinline__ void blend_forward(const ModelView<T>& M, Scratch<T>& S, void* wsp);
 template <typename T>
 __device__ __forceinline__ void blend_adjoint(const ModelView<T>& M, Scratch<T>& S, void* wsp);
+template <typename T>
+__device__ __forceinline__ void rows_dot(const T* W, const T* bias, int nrows, const T* x, T* y, void* wsp);
+template <typename T>
+__device__ __forceinline__ void rows_accum(const T* W, int nrows, const T* g, T* out, void* wsp);
 #else
+template <typename T>
+static void rows_dot(const T* W, const T* bias, int nrows, const T* x, T* y, void*) {
+    for (int r = 0; r < nrows; ++r) {
+        T acc = 0;
+        for (int k = 0; k < SFX_KPAD; ++k) acc += W[(long)r * SFX_KPAD + k] * x[k];
+        y[r] = bias[r] + acc;
+    }
+}
+template <typename T>
+static void rows_accum(const T* W, int nrows, const T* g, T* out, void*) {
+    for (int k = 0; k < SFX_KPAD; ++k) out[k] = 0;
+    for (int r = 0; r < nrows; ++r)
+        for (int k = 0; k < SFX_KPAD; ++k) out[k] += W[(long)r * SFX_KPAD + k] * g[r];
+}
 template <typename T>
 static void blend_forward(const ModelView<T>& M, Scratch<T>& S, void*) {
     for (int r = 0; r < SFX_NSLOT * 3; ++r) {
@@ -404,16 +434,215 @@ SFX_FN void support_begin_frame(const ModelView<T>& M, Scratch<T>& S) {
     SFX_SYNC();
 }
 
+
+// ------------------------------------------------------------------ VPoser v1 decoder
+// z [32] -> FC 512 -> leaky-ReLU(0.2) -> FC 512 -> leaky-ReLU(0.2) -> FC 126 -> per joint: 6-D
+// continuous rotation -> Gram-Schmidt -> rotation matrix -> quaternion (torchgeometry's branchy
+// conversion) -> axis-angle.  Third-party algorithm (human_body_prior, torchgeometry), restated
+// from the published code; reference call site: fitting.py:236.
+SFX_FN float sfx_max(float a, float b) { return a > b ? a : b; }
+SFX_FN double sfx_max(double a, double b) { return a > b ? a : b; }
+
+// one joint: o[6] -> aa[3]; keeps nothing (the adjoint recomputes the forward values)
+template <typename T>
+struct Rot6 {
+    T b1[3], b2[3], b3[3], n1, n2, dt, u[3];
+    T rt[9];            // transposed rotation matrix (torchgeometry works on R^T)
+    int kase;
+    T t, qraw[4], q[4], ss, sn, k, tt;
+};
+
+template <typename T>
+SFX_FN void rot6_forward(const T* o, Rot6<T>& F, T* aa) {
+    const T eps = (T)1e-12;
+    T a1[3] = {o[0], o[2], o[4]}, a2[3] = {o[1], o[3], o[5]};
+    F.n1 = sfx_max(sfx_sqrt(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]), eps);
+    for (int k = 0; k < 3; ++k) F.b1[k] = a1[k] / F.n1;
+    F.dt = F.b1[0] * a2[0] + F.b1[1] * a2[1] + F.b1[2] * a2[2];
+    for (int k = 0; k < 3; ++k) F.u[k] = a2[k] - F.dt * F.b1[k];
+    F.n2 = sfx_max(sfx_sqrt(F.u[0] * F.u[0] + F.u[1] * F.u[1] + F.u[2] * F.u[2]), eps);
+    for (int k = 0; k < 3; ++k) F.b2[k] = F.u[k] / F.n2;
+    F.b3[0] = F.b1[1] * F.b2[2] - F.b1[2] * F.b2[1];
+    F.b3[1] = F.b1[2] * F.b2[0] - F.b1[0] * F.b2[2];
+    F.b3[2] = F.b1[0] * F.b2[1] - F.b1[1] * F.b2[0];
+    // R[r][c] = (b1 b2 b3)[c][r];  rt = R^T: rt[i][j] = R[j][i] -> rt row i is b_i
+    for (int k = 0; k < 3; ++k) { F.rt[k] = F.b1[k]; F.rt[3 + k] = F.b2[k]; F.rt[6 + k] = F.b3[k]; }
+    const T* m = F.rt;
+    const bool d2 = m[8] < (T)1e-6, d0d1 = m[0] > m[4], d0nd1 = m[0] < -m[4];
+    if (d2 && d0d1) {
+        F.kase = 0; F.t = (T)1 + m[0] - m[4] - m[8];
+        F.qraw[0] = m[5] - m[7]; F.qraw[1] = F.t; F.qraw[2] = m[1] + m[3]; F.qraw[3] = m[6] + m[2];
+    } else if (d2) {
+        F.kase = 1; F.t = (T)1 - m[0] + m[4] - m[8];
+        F.qraw[0] = m[6] - m[2]; F.qraw[1] = m[1] + m[3]; F.qraw[2] = F.t; F.qraw[3] = m[5] + m[7];
+    } else if (d0nd1) {
+        F.kase = 2; F.t = (T)1 - m[0] - m[4] + m[8];
+        F.qraw[0] = m[1] - m[3]; F.qraw[1] = m[6] + m[2]; F.qraw[2] = m[5] + m[7]; F.qraw[3] = F.t;
+    } else {
+        F.kase = 3; F.t = (T)1 + m[0] + m[4] + m[8];
+        F.qraw[0] = F.t; F.qraw[1] = m[5] - m[7]; F.qraw[2] = m[6] - m[2]; F.qraw[3] = m[1] - m[3];
+    }
+    const T rs = sfx_sqrt(F.t);
+    for (int i = 0; i < 4; ++i) F.q[i] = F.qraw[i] / rs * (T)0.5;
+    F.ss = F.q[1] * F.q[1] + F.q[2] * F.q[2] + F.q[3] * F.q[3];
+    F.sn = sfx_sqrt(F.ss);
+    const T c = F.q[0];
+    F.tt = (T)2 * (c < (T)0 ? sfx_atan2(-F.sn, -c) : sfx_atan2(F.sn, c));
+    F.k = F.ss > (T)0 ? F.tt / F.sn : (T)2;
+    for (int i = 0; i < 3; ++i) aa[i] = F.q[1 + i] * F.k;
+}
+
+template <typename T>
+SFX_FN void rot6_backward(const Rot6<T>& F, const T* g, T* dO) {
+    // angle-axis <- quaternion
+    T dq[4] = {0, g[0] * F.k, g[1] * F.k, g[2] * F.k};
+    if (F.ss > (T)0) {
+        const T dk = g[0] * F.q[1] + g[1] * F.q[2] + g[2] * F.q[3];
+        const T dtt = dk / F.sn;
+        T ds = -dk * F.tt / (F.sn * F.sn);
+        const T c = F.q[0], den = F.sn * F.sn + c * c;
+        ds += dtt * (T)2 * c / den;
+        dq[0] = dtt * (T)2 * (-F.sn) / den;
+        const T dss = ds / ((T)2 * F.sn);
+        for (int i = 1; i < 4; ++i) dq[i] += (T)2 * F.q[i] * dss;
+    }
+    // q = 0.5 qraw / sqrt(t)
+    const T rs = sfx_sqrt(F.t);
+    T dqr[4], dt = 0;
+    for (int i = 0; i < 4; ++i) {
+        dqr[i] = dq[i] * (T)0.5 / rs;
+        dt += -dq[i] * (T)0.25 * F.qraw[i] / (F.t * rs);
+    }
+    T dm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (F.kase == 0) {
+        dt += dqr[1];
+        dm[5] += dqr[0]; dm[7] -= dqr[0]; dm[1] += dqr[2]; dm[3] += dqr[2]; dm[6] += dqr[3]; dm[2] += dqr[3];
+        dm[0] += dt; dm[4] -= dt; dm[8] -= dt;
+    } else if (F.kase == 1) {
+        dt += dqr[2];
+        dm[6] += dqr[0]; dm[2] -= dqr[0]; dm[1] += dqr[1]; dm[3] += dqr[1]; dm[5] += dqr[3]; dm[7] += dqr[3];
+        dm[0] -= dt; dm[4] += dt; dm[8] -= dt;
+    } else if (F.kase == 2) {
+        dt += dqr[3];
+        dm[1] += dqr[0]; dm[3] -= dqr[0]; dm[6] += dqr[1]; dm[2] += dqr[1]; dm[5] += dqr[2]; dm[7] += dqr[2];
+        dm[0] -= dt; dm[4] -= dt; dm[8] += dt;
+    } else {
+        dt += dqr[0];
+        dm[5] += dqr[1]; dm[7] -= dqr[1]; dm[6] += dqr[2]; dm[2] -= dqr[2]; dm[1] += dqr[3]; dm[3] -= dqr[3];
+        dm[0] += dt; dm[4] += dt; dm[8] += dt;
+    }
+    // rt rows are b1, b2, b3
+    T db1[3] = {dm[0], dm[1], dm[2]}, db2[3] = {dm[3], dm[4], dm[5]}, db3[3] = {dm[6], dm[7], dm[8]};
+    // b3 = b1 x b2
+    db1[0] += F.b2[1] * db3[2] - F.b2[2] * db3[1];
+    db1[1] += F.b2[2] * db3[0] - F.b2[0] * db3[2];
+    db1[2] += F.b2[0] * db3[1] - F.b2[1] * db3[0];
+    db2[0] += db3[1] * F.b1[2] - db3[2] * F.b1[1];
+    db2[1] += db3[2] * F.b1[0] - db3[0] * F.b1[2];
+    db2[2] += db3[0] * F.b1[1] - db3[1] * F.b1[0];
+    // b2 = u / |u|
+    const T pb2 = F.b2[0] * db2[0] + F.b2[1] * db2[1] + F.b2[2] * db2[2];
+    T du[3], da2[3], da1[3];
+    for (int k = 0; k < 3; ++k) du[k] = (db2[k] - F.b2[k] * pb2) / F.n2;
+    // u = a2 - dt b1 ; dt = b1 . a2
+    const T ddt = -(du[0] * F.b1[0] + du[1] * F.b1[1] + du[2] * F.b1[2]);
+    T a2[3];
+    for (int k = 0; k < 3; ++k) a2[k] = F.u[k] + F.dt * F.b1[k];
+    for (int k = 0; k < 3; ++k) {
+        da2[k] = du[k] + ddt * F.b1[k];
+        db1[k] += -F.dt * du[k] + ddt * a2[k];
+    }
+    // b1 = a1 / |a1|
+    const T pb1 = F.b1[0] * db1[0] + F.b1[1] * db1[1] + F.b1[2] * db1[2];
+    for (int k = 0; k < 3; ++k) da1[k] = (db1[k] - F.b1[k] * pb1) / F.n1;
+    dO[0] = da1[0]; dO[2] = da1[1]; dO[4] = da1[2];
+    dO[1] = da2[0]; dO[3] = da2[1]; dO[5] = da2[2];
+}
+
+// z = S.x[off_pose ..] -> S.bp[63].  h1 lives in S.dc, h2 in S.dvp (both free before the blend
+// passes); only the leaky-ReLU masks and the 6-D outputs are kept for the adjoint.
+template <typename T>
+SFX_FN void vposer_decode(const ModelView<T>& M, const T* z, Scratch<T>& S, void* wsp) {
+    SFX_SYNC();
+    SFX_FOR(i, 512) {
+        const T* w = M.vp_w1 + i * SFX_NLATENT;
+        T acc = 0;
+        for (int k = 0; k < SFX_NLATENT; ++k) acc += w[k] * z[k];
+        acc += M.vp_b1[i];
+        S.vm1[i] = acc > (T)0;
+        S.dc[i] = acc > (T)0 ? acc : (T)0.2 * acc;
+    }
+    SFX_SYNC();
+    rows_dot(M.vp_w2, M.vp_b2, 512, S.dc, S.dvp, wsp);
+    SFX_SYNC();
+    SFX_FOR(i, 512) {
+        const T v = S.dvp[i];
+        S.vm2[i] = v > (T)0;
+        S.dvp[i] = v > (T)0 ? v : (T)0.2 * v;
+    }
+    SFX_SYNC();
+    rows_dot(M.vp_w3, M.vp_b3, 128, S.dvp, S.o6, wsp);
+    SFX_SYNC();
+    SFX_FOR(j, 21) {
+        Rot6<T> F;
+        rot6_forward(S.o6 + 6 * j, F, S.bp + 3 * j);
+    }
+    SFX_SYNC();
+}
+
+// S.dbp[63] (gradient wrt the decoded pose) -> dz[32] (written to out).  Uses S.c / S.dc as
+// 512-wide temporaries (free at this point of the evaluation).
+template <typename T>
+SFX_FN void vposer_adjoint(const ModelView<T>& M, Scratch<T>& S, T* out, void* wsp) {
+    SFX_SYNC();
+    SFX_FOR(j, 128 / 6 + 1) {
+        if (j < 21) {
+            Rot6<T> F;
+            T aa[3];
+            rot6_forward(S.o6 + 6 * j, F, aa);
+            rot6_backward(F, S.dbp + 3 * j, S.do6 + 6 * j);
+        } else {
+            S.do6[126] = 0;
+            S.do6[127] = 0;
+        }
+    }
+    SFX_SYNC();
+    rows_accum(M.vp_w3, 128, S.do6, S.c, wsp);                 // dL/dh2
+    SFX_SYNC();
+    SFX_FOR(i, 512) S.c[i] = S.vm2[i] ? S.c[i] : (T)0.2 * S.c[i];
+    SFX_SYNC();
+    rows_accum(M.vp_w2, 512, S.c, S.dc, wsp);                  // dL/dh1
+    SFX_SYNC();
+    SFX_FOR(i, 512) S.dc[i] = S.vm1[i] ? S.dc[i] : (T)0.2 * S.dc[i];
+    SFX_SYNC();
+    // dz[k] = sum_i W1[i][k] g1[i]: 16 partial sums per k in a fixed order
+    SFX_FOR(t, 512) {
+        const int k = t & 31, part = t >> 5;
+        T acc = 0;
+        for (int i = part; i < 512; i += 16) acc += M.vp_w1[i * SFX_NLATENT + k] * S.dc[i];
+        S.c[t] = acc;
+    }
+    SFX_SYNC();
+    SFX_FOR(k, SFX_NLATENT) {
+        T acc = 0;
+        for (int part = 0; part < 16; ++part) acc += S.c[part * 32 + k];
+        out[k] = acc;
+    }
+    SFX_SYNC();
+}
+
 // ------------------------------------------------------------------ pose prologue
 // Full pose (hand PCA + mean), Rodrigues, rest joints from the shape, blend coefficients, yaw row
 // of the contour table.  Reads S.x.  Ends synchronised.
 template <typename T>
-SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>& S) {
+SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>& S,
+                          bool use_vposer = false, void* wsp = nullptr) {
     const int NS = M.NS;
+    if (use_vposer) vposer_decode(M, S.x + L.off_pose, S, wsp);     // body pose = decode(z)
     SFX_FOR(i, SFX_NPOSE) {
         T v;
         if (i < 3) v = S.x[L.off_go + i];
-        else if (i < 66) v = S.x[L.off_pose + i - 3];      // VPoser decode replaces this block
+        else if (i < 66) v = use_vposer ? S.bp[i - 3] : S.x[L.off_pose + i - 3];
         else if (i < 69) v = S.x[L.off_jaw + i - 66];
         else if (i < 72) v = S.x[L.off_leye + i - 69];
         else if (i < 75) v = S.x[L.off_reye + i - 72];
@@ -660,7 +889,8 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     const int nj = M.NJOUT;
     const int K = M.K;
     SFX_PROF_BEGIN(eval);
-    pose_prologue(M, L, S);
+    const bool vposer = st.use_vposer != 0;
+    pose_prologue(M, L, S, vposer, stream_ws);
     // ---- 3. kinematic chain (warp 0) || blendshapes on the support vertices (every warp) ----
     SFX_PROF_BEGIN(bf);
     if (SFX_IS_WARP0) chain_forward(M, S);
@@ -859,6 +1089,21 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     T gmm_val = 0;
     const bool use_gmm = body && st.pprior_kind == SFX_PPRIOR_GMM;
     if (use_gmm) gmm_val = gmm_prior(M, S.x + L.off_pose, S, S.dvp);    // c, dvp are free by now
+    const bool latent_reg = vposer && reg_pose != nullptr && st.stage_index + 1 == st.num_stages;
+    if (vposer) {
+        // gradient wrt the decoded body pose: data term (dfp) + bending prior, then the decoder
+        SFX_SYNC();
+        SFX_FOR(e, 63) {
+            T gv = S.dfp[3 + e];
+            if (body && (e == 52 || e == 55 || e == 9 || e == 12)) {
+                T sg = e == 52 ? (T)1 : (T)-1;
+                T ex = sfx_exp(S.fp[3 + e] * sg);
+                gv += bendw * (T)2 * ex * ex * sg;
+            }
+            S.dbp[e] = gv;
+        }
+        vposer_adjoint(M, S, S.gl, stream_ws);
+    }
     SFX_SYNC();
     SFX_FOR(i, L.np) {
         T gv = 0;
@@ -870,6 +1115,11 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
             }
         } else if (i >= L.off_go && i < L.off_go + 3) {
             gv = S.dfp[i - L.off_go];
+        } else if (vposer && i >= L.off_pose && i < L.off_pose + L.n_pose) {
+            // latent pose: decoder adjoint (S.gl) + latent prior (fitting.py:389-395)
+            int e = i - L.off_pose;
+            gv = S.gl[e];
+            if (body) gv += (T)2 * bpw2 * (latent_reg ? S.x[i] - reg_pose[e] : S.x[i]);
         } else if (i >= L.off_pose && i < L.off_pose + L.n_pose) {
             int e = i - L.off_pose;
             gv = S.dfp[3 + e];
@@ -925,7 +1175,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         const T* ex = S.x + L.off_expr;
         const T* hv = S.hand;
         const int n_pose = L.n_pose, n_betas = L.n_betas, n_expr = L.n_expr;
-        const bool reg = st.pprior_kind == SFX_PPRIOR_REGRESSION;
+        const bool reg = vposer ? latent_reg : st.pprior_kind == SFX_PPRIOR_REGRESSION;
         multi_sum<T>(5, 64, [=](int q, int i) -> T {
             if (q == 0) {
                 if (i >= n_pose) return (T)0;

@@ -141,15 +141,18 @@ eval_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ Batc
 // Pose prologue only: skinning transforms A [B][55*12] and blend coefficients c [B][512] for the
 // full-mesh path.
 template <typename T>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(SFX_THREADS, 1)
 mesh_coef_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ BatchView<T> Bv,
-                 T* Aout, T* Cout) {
+                 int use_vposer, T* Aout, T* Cout) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(smem);
+    __shared__ StreamWS ws;
+    if (threadIdx.x == 0) ws = carve_stream<T>(smem + scratch_bytes<T>(), 0);    // plain loads
+    __syncthreads();
     const int f = blockIdx.x;
     load_frame(Bv, f, S);
     support_begin_frame(M, S);
-    pose_prologue(M, Bv.lay, S);
+    pose_prologue(M, Bv.lay, S, use_vposer != 0, &ws);
     if (threadIdx.x < 32) chain_forward(M, S);
     __syncthreads();
     for (int i = threadIdx.x; i < SFX_NJ * 12; i += blockDim.x) Aout[(size_t)f * SFX_NJ * 12 + i] = S.A[i];
@@ -393,7 +396,8 @@ struct sfx_model {
     ModelView<float> vf;
     ModelView<double> vd;
     DevBuf PK, vt, J0, JS, Wd, hand_l, hand_r, pose_mean, sv_vid, lmk_bary, dyn_vid, dyn_bary,
-        joint_map, inv_ptr, inv_idx, faces, gmm_means, gmm_prec, gmm_logw;
+        joint_map, inv_ptr, inv_idx, faces, gmm_means, gmm_prec, gmm_logw, vp_w1, vp_b1, vp_w2,
+        vp_b2, vp_w3, vp_b3;
     int device = 0;
     int num_sms = 0;
     MeshPlan mesh;        // TMA descriptor of the blend matrix for the tensor-core mesh kernel
@@ -468,6 +472,24 @@ static int ring_mode_for(const sfx_model* m) {
     return m->use_double ? 0 : 1;
 }
 
+template <typename T>
+static int upload_vposer(sfx_model* m, ModelView<T>& v, const T* w1, const T* b1, const T* w2,
+                         const T* b2, const T* w3, const T* b3) {
+    std::vector<T> w3p((size_t)128 * SFX_KPAD, (T)0), b3p(128, (T)0);
+    for (size_t i = 0; i < (size_t)126 * SFX_KPAD; ++i) w3p[i] = w3[i];
+    for (int i = 0; i < 126; ++i) b3p[i] = b3[i];
+    std::vector<T> vw1(w1, w1 + 512 * SFX_NLATENT), vb1(b1, b1 + 512), vw2(w2, w2 + (size_t)512 * 512),
+        vb2(b2, b2 + 512);
+    CUDA_TRY(m->vp_w1.upload(vw1)); CUDA_TRY(m->vp_b1.upload(vb1));
+    CUDA_TRY(m->vp_w2.upload(vw2)); CUDA_TRY(m->vp_b2.upload(vb2));
+    CUDA_TRY(m->vp_w3.upload(w3p)); CUDA_TRY(m->vp_b3.upload(b3p));
+    v.vp_w1 = (const T*)m->vp_w1.p; v.vp_b1 = (const T*)m->vp_b1.p; v.vp_w2 = (const T*)m->vp_w2.p;
+    v.vp_b2 = (const T*)m->vp_b2.p; v.vp_w3 = (const T*)m->vp_w3.p; v.vp_b3 = (const T*)m->vp_b3.p;
+    v.vp_ready = 1;
+    return SFX_OK;
+}
+
+
 // ------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -498,6 +520,19 @@ int sfx_model_create(const sfx_model_desc* desc, sfx_model** out) {
 
 void sfx_model_destroy(sfx_model* m) { delete m; }
 
+int sfx_model_set_vposer(sfx_model* m, const void* fc1_w, const void* fc1_b, const void* fc2_w,
+                         const void* fc2_b, const void* out_w, const void* out_b) {
+    if (!m || !fc1_w || !fc1_b || !fc2_w || !fc2_b || !out_w || !out_b)
+        return fail(SFX_ERR_ARG, "null argument");
+    if (m->use_double)
+        return upload_vposer<double>(m, m->vd, (const double*)fc1_w, (const double*)fc1_b,
+                                     (const double*)fc2_w, (const double*)fc2_b,
+                                     (const double*)out_w, (const double*)out_b);
+    return upload_vposer<float>(m, m->vf, (const float*)fc1_w, (const float*)fc1_b,
+                                (const float*)fc2_w, (const float*)fc2_b, (const float*)out_w,
+                                (const float*)out_b);
+}
+
 int sfx_model_set_gmm(sfx_model* m, int32_t num_gaussians, int32_t dim, const void* means,
                       const void* precisions, const void* log_nll_weights) {
     if (!m || !means || !precisions || !log_nll_weights) return fail(SFX_ERR_ARG, "null argument");
@@ -524,7 +559,8 @@ int sfx_model_set_gmm(sfx_model* m, int32_t num_gaussians, int32_t dim, const vo
 
 int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batch** out) {
     if (!m || !out || B < 1) return fail(SFX_ERR_ARG, "bad argument");
-    if (use_vposer) return fail(SFX_ERR_UNSUPPORTED, "VPoser latent pose is not built yet");
+    if (use_vposer && !(m->use_double ? m->vd.vp_ready : m->vf.vp_ready))
+        return fail(SFX_ERR_ARG, "use_vposer: call sfx_model_set_vposer first");
     sfx_batch* b = new sfx_batch();
     b->m = m; b->B = B; b->use_vposer = use_vposer;
     b->lay = make_layout(m->NB, m->NE, m->NH, use_vposer);
@@ -674,8 +710,16 @@ static int check_stage(const sfx_batch* b, const SfxStage* st) {
         if (gd != b->lay.n_pose || b->use_vposer)
             return fail(SFX_ERR_ARG, "stage: mixture prior dimension does not match the body pose");
     }
-    if (st->pprior_kind == SFX_PPRIOR_LATENT || st->use_vposer)
-        return fail(SFX_ERR_UNSUPPORTED, "VPoser latent pose is not built yet");
+    if ((st->use_vposer != 0) != (b->use_vposer != 0))
+        return fail(SFX_ERR_ARG, "stage: use_vposer does not match the batch (sfx_batch_create)");
+    if (st->use_vposer) {
+        const int ready = b->m->use_double ? b->m->vd.vp_ready : b->m->vf.vp_ready;
+        if (!ready) return fail(SFX_ERR_ARG, "stage: use_vposer but sfx_model_set_vposer was not called");
+        if (st->loss_kind == SFX_LOSS_SMPLIFY && st->pprior_kind != SFX_PPRIOR_LATENT)
+            return fail(SFX_ERR_ARG, "stage: use_vposer needs the latent pose prior (fitting.py:389-395)");
+    } else if (st->pprior_kind == SFX_PPRIOR_LATENT) {
+        return fail(SFX_ERR_ARG, "stage: latent pose prior without use_vposer");
+    }
     if (st->opt_kind != SFX_OPT_LBFGSLS && st->opt_kind != SFX_OPT_ADAM)
         return fail(SFX_ERR_UNSUPPORTED, "optimiser kind not supported on the device");
     return SFX_OK;
@@ -820,9 +864,9 @@ static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev,
     cudaStream_t s = (cudaStream_t)stream;
     const sfx_model* m = b->m;
     if (m->use_double) {
-        size_t smem = scratch_bytes<double>();
+        size_t smem = fit_smem<double>(0);
         CUDA_TRY(cudaFuncSetAttribute(mesh_coef_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mesh_coef_kernel<double><<<b->B, 256, smem, s>>>(m->vd, b->view<double>(nullptr),
+        mesh_coef_kernel<double><<<b->B, SFX_THREADS, smem, s>>>(m->vd, b->view<double>(nullptr), b->use_vposer,
                                                          (double*)b->Acoef.p, (double*)b->Ccoef.p);
         CUDA_TRY(cudaGetLastError());
         std::string e = mesh_forward_simt<double>(m->vd, b->B, (const double*)b->Acoef.p,
@@ -830,9 +874,9 @@ static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev,
                                                   (double*)vertices_dev, s);
         if (!e.empty()) return fail(SFX_ERR_CUDA, e);
     } else {
-        size_t smem = scratch_bytes<float>();
+        size_t smem = fit_smem<float>(0);
         CUDA_TRY(cudaFuncSetAttribute(mesh_coef_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mesh_coef_kernel<float><<<b->B, 256, smem, s>>>(m->vf, b->view<float>(nullptr),
+        mesh_coef_kernel<float><<<b->B, SFX_THREADS, smem, s>>>(m->vf, b->view<float>(nullptr), b->use_vposer,
                                                        (float*)b->Acoef.p, (float*)b->Ccoef.p);
         CUDA_TRY(cudaGetLastError());
         // blend contraction: tcgen05 / TMA kernel (SFX_MESH_SIMT=1 selects the fp32 SIMT kernel,
@@ -860,6 +904,7 @@ static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev,
         st.rho = 100;
         st.n_active = 3; st.n_blocks = 1; st.block_start[0] = 0; st.block_len[0] = 3;
         st.block_off[0] = b->lay.off_go; st.history = SFX_HIST; st.opt_kind = SFX_OPT_LBFGSLS;
+        st.use_vposer = b->use_vposer;
         int rc = sfx_eval(b, &st, nullptr, nullptr, joints_dev, stream);
         if (rc) return rc;
     }

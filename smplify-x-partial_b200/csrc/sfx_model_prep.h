@@ -22,6 +22,7 @@ struct HostModel {
     void fill_scalars(ModelView<T>& m) const {
         m.V = V; m.NS = NS; m.NB = NB; m.NE = NE; m.NH = NH; m.K = K; m.NJOUT = NJOUT;
         m.use_contour = use_contour; m.n_neck = n_neck; m.nlev = nlev;
+        m.vp_ready = 0; m.vp_w1 = m.vp_b1 = m.vp_w2 = m.vp_b2 = m.vp_w3 = m.vp_b3 = nullptr;
         m.gmm_M = 0; m.gmm_D = 0; m.gmm_means = nullptr; m.gmm_prec = nullptr; m.gmm_logw = nullptr;
         for (int i = 0; i < SFX_NJ; ++i) { m.parents[i] = parents[i]; m.order[i] = order[i]; }
         for (int i = 0; i < 16; ++i) m.level_off[i] = level_off[i];

@@ -97,13 +97,11 @@ __device__ __forceinline__ void load_row_regs(const T* row, int lane, T* dst) {
 
 // Generic driver: FN(row_index_r, const T* row_values_in_regs[16]) is called by every lane of the
 // warp that owns support row r, rows taken in the fixed order r = warp, warp + NWARP, ...
-template <typename T, typename FN>
-__device__ __forceinline__ void stream_rows(const ModelView<T>& M, const Scratch<T>& S,
-                                            StreamWS& ws, FN fn) {
+template <typename T, typename RP, typename FN>
+__device__ __forceinline__ void stream_rows(int nrows, RP rowptr, StreamWS& ws, FN fn) {
     // warp 0 runs the kinematic chain while warps 1 .. NWARP-1 stream the rows
     const int warp = (threadIdx.x >> 5) - 1, lane = threadIdx.x & 31;
     constexpr int NSTREAM = SFX_NWARP - 1;
-    const int nrows = SFX_NSLOT * 3;
     const int count = warp >= 0 ? (nrows - warp + NSTREAM - 1) / NSTREAM : 0;
     constexpr uint32_t ROWB = SFX_KPAD * sizeof(T);
     T vals[RowVec<T>::NE];
@@ -114,11 +112,10 @@ __device__ __forceinline__ void stream_rows(const ModelView<T>& M, const Scratch
         const unsigned int n0 = ws.fills[warp];
         auto issue = [&](int i) {
             int r = warp + i * NSTREAM;
-            long row = (long)S.vid[r / 3] * 3 + (r % 3);
             unsigned int n = n0 + i;
             int b = n % SFX_NBUF;
             mbar_expect_tx(mybar + b, ROWB);
-            bulk_g2s(mybuf + (size_t)b * ROWB, M.PK + row * SFX_KPAD, ROWB, mybar + b);
+            bulk_g2s(mybuf + (size_t)b * ROWB, rowptr(r), ROWB, mybar + b);
         };
         if (lane == 0) {
             fence_proxy_async();
@@ -141,8 +138,7 @@ __device__ __forceinline__ void stream_rows(const ModelView<T>& M, const Scratch
     } else {
         for (int i = 0; i < count; ++i) {
             int r = warp + i * NSTREAM;
-            long row = (long)S.vid[r / 3] * 3 + (r % 3);
-            load_row_regs<T>(M.PK + row * SFX_KPAD, lane, vals);
+            load_row_regs<T>(rowptr(r), lane, vals);
             fn(r, vals);
         }
     }
@@ -157,7 +153,10 @@ __device__ __forceinline__ void blend_forward(const ModelView<T>& M, Scratch<T>&
     for (int i = 0; i < RowVec<T>::NV; ++i)
 #pragma unroll
         for (int e = 0; e < RowVec<T>::VEC; ++e) c[i * RowVec<T>::VEC + e] = S.c[SFX_ELEM(i, lane, e)];
-    stream_rows<T>(M, S, ws, [&](int r, const T* v) {
+    const T* PK = M.PK;
+    const int* vid = S.vid;
+    auto rowptr = [=](int r) { return PK + ((long)vid[r / 3] * 3 + (r % 3)) * SFX_KPAD; };
+    stream_rows<T>(SFX_NSLOT * 3, rowptr, ws, [&](int r, const T* v) {
         T acc = 0;
 #pragma unroll
         for (int i = 0; i < RowVec<T>::NE; ++i) acc += v[i] * c[i];
@@ -174,7 +173,10 @@ __device__ __forceinline__ void blend_adjoint(const ModelView<T>& M, Scratch<T>&
     T acc[RowVec<T>::NE];
 #pragma unroll
     for (int i = 0; i < RowVec<T>::NE; ++i) acc[i] = 0;
-    stream_rows<T>(M, S, ws, [&](int r, const T* v) {
+    const T* PK = M.PK;
+    const int* vid = S.vid;
+    auto rowptr = [=](int r) { return PK + ((long)vid[r / 3] * 3 + (r % 3)) * SFX_KPAD; };
+    stream_rows<T>(SFX_NSLOT * 3, rowptr, ws, [&](int r, const T* v) {
         const T w = S.dvp[r];
 #pragma unroll
         for (int i = 0; i < RowVec<T>::NE; ++i) acc[i] += v[i] * w;
@@ -196,6 +198,61 @@ __device__ __forceinline__ void blend_adjoint(const ModelView<T>& M, Scratch<T>&
     }
     __syncthreads();
     if (ws.ring_mode) fence_proxy_async();   // generic writes to the ring precede later bulk copies
+}
+
+
+// ---- dense 512-wide rows (VPoser decoder layers): y = bias + W x  and  out = W^T g -----------
+template <typename T>
+__device__ __forceinline__ void rows_dot(const T* W, const T* bias, int nrows, const T* x, T* y,
+                                         void* wsp) {
+    StreamWS& ws = *reinterpret_cast<StreamWS*>(wsp);
+    const int lane = threadIdx.x & 31;
+    T c[RowVec<T>::NE];
+#pragma unroll
+    for (int i = 0; i < RowVec<T>::NV; ++i)
+#pragma unroll
+        for (int e = 0; e < RowVec<T>::VEC; ++e) c[i * RowVec<T>::VEC + e] = x[SFX_ELEM(i, lane, e)];
+    auto rowptr = [=](int r) { return W + (long)r * SFX_KPAD; };
+    stream_rows<T>(nrows, rowptr, ws, [&](int r, const T* v) {
+        T acc = 0;
+#pragma unroll
+        for (int i = 0; i < RowVec<T>::NE; ++i) acc += v[i] * c[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) y[r] = bias[r] + acc;
+    });
+    __syncthreads();
+}
+
+template <typename T>
+__device__ __forceinline__ void rows_accum(const T* W, int nrows, const T* g, T* out, void* wsp) {
+    StreamWS& ws = *reinterpret_cast<StreamWS*>(wsp);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T acc[RowVec<T>::NE];
+#pragma unroll
+    for (int i = 0; i < RowVec<T>::NE; ++i) acc[i] = 0;
+    auto rowptr = [=](int r) { return W + (long)r * SFX_KPAD; };
+    stream_rows<T>(nrows, rowptr, ws, [&](int r, const T* v) {
+        const T w = g[r];
+#pragma unroll
+        for (int i = 0; i < RowVec<T>::NE; ++i) acc[i] += v[i] * w;
+    });
+    __syncthreads();
+    T* part = reinterpret_cast<T*>(ws.ring);
+#pragma unroll
+    for (int i = 0; i < RowVec<T>::NV; ++i)
+#pragma unroll
+        for (int e = 0; e < RowVec<T>::VEC; ++e)
+            part[warp * SFX_KPAD + SFX_ELEM(i, lane, e)] = acc[i * RowVec<T>::VEC + e];
+    __syncthreads();
+    for (int k = threadIdx.x; k < SFX_KPAD; k += blockDim.x) {
+        T s = 0;
+#pragma unroll
+        for (int w = 0; w < SFX_NWARP; ++w) s += part[w * SFX_KPAD + k];
+        out[k] = s;
+    }
+    __syncthreads();
+    if (ws.ring_mode) fence_proxy_async();
 }
 
 template <typename T>

@@ -47,6 +47,23 @@ class Model(object):
         self.n_betas = int(desc.num_betas)
         self.n_expr = int(desc.num_expr)
 
+    def set_vposer(self, weights):
+        """Installs the VPoser decoder: dict with dec_fc1_w/b, dec_fc2_w/b, dec_out_w/b (numpy,
+        torch Linear layout) -- see ``vposer.load_vposer_weights``."""
+        if getattr(self, '_vposer_id', None) == id(weights):
+            return
+        arrs = [np.ascontiguousarray(np.asarray(weights[k]), dtype=self.np_dtype) for k in
+                ('dec_fc1_w', 'dec_fc1_b', 'dec_fc2_w', 'dec_fc2_b', 'dec_out_w', 'dec_out_b')]
+        shapes = [(512, 32), (512,), (512, 512), (512,), (126, 512), (126,)]
+        for a, sh in zip(arrs, shapes):
+            if a.shape != sh:
+                raise ValueError('VPoser decoder weight has shape {}, expected {}'.format(a.shape, sh))
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            N.check(self.lib, self.lib.sfx_model_set_vposer(
+                self.h, *[C.c_void_p(a.ctypes.data) for a in arrs]))
+        self._vposer_id = id(weights)
+
     def set_gmm(self, prior):
         """Installs a ``prior.MaxMixturePrior`` (or anything with ``means`` [M,D], ``precisions``
         [M,D,D], ``nll_weights`` [1,M] tensors) as the body-pose mixture prior of this model."""

@@ -228,7 +228,7 @@ class FitPlan(object):
     the second (flipped) orientation.  Pure numpy; built without touching the device."""
 
     def __init__(self, L, K, keypoints, H, W, cfg, expose=None, pixie=None, body_mean_pose=None,
-                 np_dtype=np.float32, body_pose_prior=None):
+                 np_dtype=np.float32, body_pose_prior=None, vposer=None):
         B = keypoints.shape[0]
         self.B, self.K, self.L, self.cfg = B, K, L, cfg
         npd = self.np_dtype = np_dtype
@@ -247,17 +247,31 @@ class FitPlan(object):
         # --- initial parameters (fit_single_frame.py:209-274) ---
         x = np.zeros((B, L.np), dtype=np.float64)
         self.reg = None
+        use_vposer = bool(cfg.get('use_vposer', False))
+        self.vposer = vposer
+        if use_vposer and (vposer is None or L.n_pose != 32):
+            raise ValueError('use_vposer needs vposer= (vposer.VPoser) and a batch created with '
+                             'use_vposer=True')
+        if not use_vposer and L.n_pose != 63:
+            raise ValueError('the batch was created with use_vposer=True but the config says False')
         if cfg.get('regression_prior'):
-            if cfg.get('use_vposer', False):
-                raise NotImplementedError('VPoser encode of the regression prior')
             self.reg = np.zeros((B, L.n_pose), dtype=np.float64)
+            poses = np.zeros((B, 63), dtype=npd)
             for b in range(B):
                 pose, go = regression_pose(cfg, None if expose is None else expose[b],
                                            None if pixie is None else pixie[b], dtype=npd)
-                self.reg[b] = pose
-                x[b, L.off_pose:L.off_pose + L.n_pose] = pose
+                poses[b] = pose
                 x[b, L.off_go:L.off_go + 3] = go
-        elif not cfg.get('use_vposer', False):
+            if use_vposer:
+                # pose_embedding = vposer.encode(prior).sample()  (fit_single_frame.py:245):
+                # stochastic in the reference too; seed torch for reproducible runs
+                import torch
+                with torch.no_grad():
+                    z = vposer.encode(torch.as_tensor(poses, dtype=vposer.dec_fc1_w.dtype)).sample()
+                poses = z.cpu().numpy()
+            self.reg[:] = poses
+            x[:, L.off_pose:L.off_pose + L.n_pose] = poses
+        elif not use_vposer:
             # body_mean_pose = body_pose_prior.get_mean() (fit_single_frame.py:250-252)
             if body_mean_pose is None and hasattr(body_pose_prior, 'get_mean'):
                 body_mean_pose = body_pose_prior.get_mean().detach().cpu().numpy()
@@ -294,6 +308,8 @@ class FitPlan(object):
 def upload(batch, plan):
     """Host -> device copies of one batch (async on the current stream); returns the byte count."""
     import torch
+    if plan.vposer is not None and plan.cfg.get('use_vposer', False):
+        batch.model.set_vposer(plan.vposer.weights)
     if getattr(plan.body_pose_prior, 'kind', '') == 'gmm':
         batch.model.set_gmm(plan.body_pose_prior)
     n = batch.set_targets(plan.keypoints, plan.jw, plan.lowconf, plan.init_mask, plan.cam, plan.reg)
@@ -396,11 +412,20 @@ def download(batch, plan, cam_loss, verts, joints):
         off, n = blocks['pose_embedding']
         r['body_pose'] = params[b, off:off + n].reshape(1, n).copy()
         out.results.append(r)
+    if plan.vposer is not None and plan.cfg.get('use_vposer', False):
+        # result['body_pose'] = vposer.decode(pose_embedding, 'aa') (fit_single_frame.py:653-657)
+        import torch
+        off, n = blocks['pose_embedding']
+        with torch.no_grad():
+            z = torch.as_tensor(params[:, off:off + n], dtype=plan.vposer.dec_fc1_w.dtype)
+            bp = plan.vposer.decode(z, output_type='aa').reshape(B, -1).cpu().numpy().astype(npd)
+        for b in range(B):
+            out.results[b]['body_pose'] = bp[b:b + 1].copy()
     return out
 
 
 def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_verts=True,
-               body_mean_pose=None, body_pose_prior=None):
+               body_mean_pose=None, body_pose_prior=None, vposer=None):
     """Fits every frame of ``batch`` (an ``engine.FrameBatch``).
 
     keypoints [B,K,3] (x, y, confidence) in the reference's row order; ``H``, ``W`` scalars or
@@ -408,7 +433,7 @@ def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_vert
     reference's YAML files); ``expose`` / ``pixie`` lists of per-frame regression results.
     """
     plan = FitPlan(batch.L, batch.model.K, np.asarray(keypoints), H, W, cfg, expose, pixie,
-                   body_mean_pose, batch.model.np_dtype, body_pose_prior)
+                   body_mean_pose, batch.model.np_dtype, body_pose_prior, vposer)
     h2d = upload(batch, plan)
     cam_loss, verts, joints, launches = run(batch, plan, return_verts)
     out = download(batch, plan, cam_loss, verts, joints)

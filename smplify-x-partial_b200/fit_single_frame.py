@@ -54,8 +54,13 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
     dev = body_model.engine_model.device
     H, W = int(np.asarray(img).shape[0]), int(np.asarray(img).shape[1])
     use_vposer = kwargs.get('use_vposer', True)
+    vposer = kwargs.pop('vposer', None)
+    if use_vposer and vposer is None:
+        from .vposer import load_vposer
+        vposer, _ = load_vposer(os.path.expandvars(vposer_ckpt), vp_model='snapshot', dtype=dtype)
     if use_vposer:
-        raise NotImplementedError('use_vposer: VPoser decode is not built yet (SURVEY.md a15)')
+        vposer = vposer.to(device=dev)
+        vposer.eval()
     if visualize:
         raise NotImplementedError('visualisation is out of scope (SURVEY.md #16)')
     if pare_results is not None and regression_prior == 'PARE':
@@ -87,8 +92,14 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
         po, go = zip(*[FF.regression_pose(cfg, expose[b], pixie[b]) for b in range(B)])
         pose0 = torch.tensor(np.stack(po), dtype=dtype, device=dev)
         go0 = torch.tensor(np.stack(go), dtype=dtype, device=dev)
-    else:
+    elif not use_vposer:
         pose0 = body_pose_prior.get_mean().detach().to(device=dev, dtype=dtype).expand(B, -1).clone()
+    if use_vposer:
+        if regression_prior:
+            with torch.no_grad():
+                pose0 = vposer.encode(pose0).sample()
+        else:
+            pose0 = torch.zeros([B, 32], dtype=dtype, device=dev)
     pose_embedding = pose0.clone().requires_grad_(True)
     if go0 is not None:
         body_model.reset_params(global_orient=go0, body_pose=pose_embedding)
@@ -117,7 +128,8 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
                 camera.center[b] = torch.tensor([W, H], dtype=dtype, device=dev) * 0.5
         if FF.camera_prior(cfg, focal_length, expose[0], pixie[0]) is None:
             init_t = fitting.guess_init(body_model, gt_joints, kwargs.get('body_tri_idxs'),
-                                        use_vposer=False, pose_embedding=pose_embedding,
+                                        use_vposer=use_vposer, vposer=vposer,
+                                        pose_embedding=pose_embedding,
                                         model_type=kwargs.get('model_type', 'smpl'),
                                         focal_length=focal_length, dtype=dtype)
             camera.translation[:] = init_t.view_as(camera.translation)
@@ -129,7 +141,7 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
         use_conf=kwargs.get('use_conf_for_camera_init')).to(device=dev)
     loss = fitting.create_loss(
         loss_type, joint_weights=jw, rho=rho, use_joints_conf=use_joints_conf, use_face=use_face,
-        use_hands=use_hands, vposer=None, pose_embedding=pose_embedding,
+        use_hands=use_hands, vposer=vposer, pose_embedding=pose_embedding,
         body_pose_prior=body_pose_prior, shape_prior=shape_prior, angle_prior=angle_prior,
         expr_prior=expr_prior, left_hand_prior=left_hand_prior, right_hand_prior=right_hand_prior,
         jaw_prior=jaw_prior, interpenetration=interpenetration, dtype=dtype,
@@ -148,8 +160,8 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
         closure = monitor.create_fitting_closure(
             cam_opt, body_model, camera, gt_joints, camera_loss, create_graph=cam_graph, use_vposer=False, vposer=None, pose_embedding=pose_embedding,
             return_full_pose=False, return_verts=False)
-        monitor.run_fitting(cam_opt, closure, cam_params, body_model, stage=0, use_vposer=False,
-                            pose_embedding=pose_embedding, vposer=None)
+        monitor.run_fitting(cam_opt, closure, cam_params, body_model, stage=0,
+                            use_vposer=use_vposer, pose_embedding=pose_embedding, vposer=vposer)
         camera.translation.requires_grad = False
 
         # --- orientations (:461-463, :527-538) ---
@@ -187,18 +199,24 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
                 closure = monitor.create_fitting_closure(
                     body_opt, body_model, camera=camera, gt_joints=gt_joints,
                     joints_conf=joints_conf, joint_weights=jw, loss=loss, create_graph=body_graph,
-                    use_vposer=False, vposer=None, pose_embedding=pose_embedding,
+                    use_vposer=use_vposer, vposer=vposer, pose_embedding=pose_embedding,
                     return_verts=True, return_full_pose=True)
                 final_loss_val = monitor.run_fitting(
                     body_opt, closure, final_params, body_model, opt_idx,
-                    pose_embedding=pose_embedding, vposer=None, use_vposer=False)
-            body_model_output = body_model(return_verts=True, body_pose=pose_embedding)
+                    pose_embedding=pose_embedding, vposer=vposer, use_vposer=use_vposer)
+
+            def decoded():
+                if use_vposer:
+                    with torch.no_grad():
+                        return vposer.decode(pose_embedding, output_type='aa').view(B, -1)
+                return pose_embedding
+            body_model_output = body_model(return_verts=True, body_pose=decoded())
             result = {'camera_' + str(k): v.detach().cpu().numpy()
                       for k, v in camera.named_parameters()}
             result['camera_center'] = camera.center.detach().cpu().numpy()
             result['H'], result['W'], result['focal_length'] = H, W, focal_length
             result.update({k: v.detach().cpu().numpy() for k, v in body_model.named_parameters()})
-            result['body_pose'] = pose_embedding.detach().cpu().numpy()
+            result['body_pose'] = decoded().detach().cpu().numpy()
             results.append({'loss': final_loss_val, 'result': result})
 
     def pick(b):

@@ -31,8 +31,10 @@ def guess_init(model, joints_2d, edge_idxs, focal_length=5000, pose_embedding=No
                use_vposer=True, dtype=torch.float32, model_type='smpl', **kwargs):
     """Initial camera translation by similar triangles (fitting.py:36-110)."""
     if use_vposer:
-        raise NotImplementedError('VPoser decode is not built yet')
-    body_pose = pose_embedding
+        body_pose = vposer.decode(pose_embedding, output_type='aa').view(
+            pose_embedding.shape[0], -1)
+    else:
+        body_pose = pose_embedding
     output = model(body_pose=body_pose, return_verts=False, return_full_pose=False)
     joints_3d = output.joints
     d3, d2 = [], []
@@ -192,6 +194,11 @@ class _FitBundle(object):
         self.body_model, self.camera, self.loss = body_model, camera, loss
         self.gt_joints, self.joints_conf, self.joint_weights = gt_joints, joints_conf, joint_weights
         self.use_vposer, self.pose_embedding = bool(use_vposer), pose_embedding
+        if self.use_vposer:
+            vp = getattr(loss, 'vposer', None) or _FitBundle._last_vposer
+            if vp is None:
+                raise ValueError('use_vposer needs the vposer module (create_loss(vposer=...))')
+            body_model.engine_model.set_vposer(vp.weights)
         self.batch = body_model.frame_batch(self.use_vposer)
 
     @staticmethod
@@ -204,6 +211,7 @@ class _FitBundle(object):
                           pose_embedding)
 
     _last_model = None
+    _last_vposer = None
 
     def push(self):
         bm, cam, loss, batch = self.body_model, self.camera, self.loss, self.batch
@@ -321,6 +329,8 @@ class FittingMonitor(object):
         on the device; with ``backward`` the analytic gradient is written into ``.grad`` of the
         body-model parameters, the pose embedding and the camera translation
         (fitting.py:232-273).  Returns the summed loss."""
+        if vposer is not None:
+            _FitBundle._last_vposer = vposer
         bundle = _FitBundle(body_model, camera, gt_joints, joints_conf, joint_weights, loss,
                             use_vposer, pose_embedding)
         _FitBundle._last_model = body_model

@@ -53,8 +53,6 @@ def main(**args):
     if args.get('use_gender_classifier'):
         raise NotImplementedError('gender classifier (TF1 Homogenus) is out of scope; pass '
                                   '--use_gender_classifier False --gender <g>')
-    if args.get('use_vposer'):
-        raise NotImplementedError('use_vposer: VPoser decode is not built yet')
     float_dtype = args.get('float_dtype', 'float32')
     if float_dtype not in ('float32', 'float64'):
         raise ValueError('Unknown float type {}, exiting!'.format(float_dtype))
@@ -78,6 +76,11 @@ def main(**args):
     if args.get('body_prior_type') == 'gmm':
         from .prior import create_prior
         body_pose_prior = create_prior(prior_type='gmm', dtype=dtype, **args)
+    vposer = None
+    if args.get('use_vposer'):
+        from .vposer import load_vposer
+        vposer, _ = load_vposer(os.path.expandvars(args.get('vposer_ckpt')), dtype=dtype)
+        model.set_vposer(vposer.weights)
     items = [d for d in dataset if d]
     mine = sharding.shard_range(len(items), rank, world)
     items = items[mine.start:mine.stop]
@@ -89,11 +92,11 @@ def main(**args):
         H = [d['img'].shape[0] for d in chunk]
         W = [d['img'].shape[1] for d in chunk]
         reg = [_load_regression(args, d['fn']) for d in chunk]
-        batch = engine.FrameBatch(model, B)
+        batch = engine.FrameBatch(model, B, use_vposer=bool(args.get('use_vposer')))
         out = FF.fit_frames(batch, kp, H, W, args, expose=[r[1] for r in reg],
                             pixie=[r[0] for r in reg],
                             return_verts=bool(args.get('save_vertices')),
-                            body_pose_prior=body_pose_prior)
+                            body_pose_prior=body_pose_prior, vposer=vposer)
         for b, d in enumerate(chunk):
             folder = os.path.join(result_folder, d['fn'])
             os.makedirs(folder, exist_ok=True)

@@ -64,8 +64,11 @@ def cam_row(focal, center, data_weight, tz_est=0.0, R=None, dtype=np.float64):
 
 def eval_case_inputs(ev, case):
     """Engine-side inputs for one case of tests/golden/ref_eval_*.npz."""
-    L = layout()
+    vposer = case.startswith('vposer')
+    L = layout(use_vposer=vposer)
     named = {k[6:]: ev[k] for k in ev if k.startswith('param/')}
+    if vposer:
+        named['pose_embedding'] = ev['vposer/latent']
     x = pack_params(L, named, cam_t=ev['cam_t'])
     kp = ev['keypoints']
     H = int(ev['HW'][0])
@@ -76,11 +79,13 @@ def eval_case_inputs(ev, case):
     init_mask = np.zeros(K, np.uint8)
     init_mask[ev['init_idxs']] = 1
     cam = cam_row(float(ev['focal']), ev['center'], 1000.0 / H, tz_est=3.5)
-    if case in ('l2', 'reg', 'gmm'):
+    if case in ('l2', 'reg', 'gmm', 'vposer', 'vposer_reg'):
         st = N.make_stage(
             L, N.BODY_STAGE_BLOCKS, loss_kind=N.LOSS_SMPLIFY,
-            pprior_kind={'reg': N.PPRIOR_REGRESSION, 'l2': N.PPRIOR_L2, 'gmm': N.PPRIOR_GMM}[case],
-            stage_index=1, num_stages=3, body_pose_weight=w['body_pose_weight'],
+            pprior_kind={'reg': N.PPRIOR_REGRESSION, 'l2': N.PPRIOR_L2, 'gmm': N.PPRIOR_GMM,
+                         'vposer': N.PPRIOR_LATENT, 'vposer_reg': N.PPRIOR_LATENT}[case],
+            use_vposer=vposer, stage_index=2 if case == 'vposer_reg' else 1, num_stages=3,
+            body_pose_weight=w['body_pose_weight'],
             shape_weight=w['shape_weight'], bending_prior_weight=w['bending_prior_weight'],
             hand_prior_weight=w['hand_prior_weight'], expr_prior_weight=w['expr_prior_weight'],
             jaw_prior_weight=w['jaw_prior_weight'], hand_joint_weight=0.1,
@@ -92,9 +97,16 @@ def eval_case_inputs(ev, case):
     jw_base = np.ones(K)
     jw_base[[1, 9, 12]] = 0
     jw_base[lowconf.astype(bool)] = 0
+    reg_pose = ev['reg_pose'][0]
+    if vposer:
+        reg_pose = ev['vposer/latent_reg'][0] if case == 'vposer_reg' else None
     return dict(L=L, x=x, gt=kp[:, :2].copy(), conf=kp[:, 2].copy(), jw=jw_base,
-                lowconf=lowconf, init_mask=init_mask, cam=cam, reg_pose=ev['reg_pose'][0],
+                lowconf=lowconf, init_mask=init_mask, cam=cam, reg_pose=reg_pose,
                 stage=st, named=named)
+
+
+def vposer_weights():
+    return synthetic.make_vposer_like(seed=2)
 
 
 def golden_grad_vector(L, ev, case):

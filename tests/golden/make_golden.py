@@ -53,6 +53,17 @@ def cfg_combined():
     return cfg
 
 
+def cfg_smplifyx():
+    """cfg_files/fit_smplx_smplifyx.yaml (5 stages, VPoser latent pose, no regression prior)
+    with the switches of BASELINE config 3."""
+    from smplifyx_b200.cmd_parser import parse_config
+    cfg = parse_config(['-c', os.path.join(REF, 'cfg_files', 'fit_smplx_smplifyx.yaml')])
+    cfg.pop('config')
+    cfg.update(interpenetration=False, visualize=False, interactive=False, use_cuda=False,
+               use_gender_classifier=False, gender='neutral', use_vposer=True)
+    return cfg
+
+
 def demo_inputs():
     import cv2
     import joblib
@@ -135,9 +146,18 @@ def ref_fit(frame='02_cropped', inputs=None, cfg=None, tag='ref_fit_02', save=Tr
     dtype = torch.float32
     torch.manual_seed(0)
     torch.set_num_threads(1)          # bit-stable reductions
-    body_model, pri, jw, _ = build_reference_objects(cfg, dtype)
+    use_vposer = bool(cfg.get('use_vposer'))
+    body_model, pri, jw, _ = build_reference_objects(cfg, dtype, use_vposer=use_vposer)
+    if use_vposer:
+        # the reference calls load_vposer(vposer_ckpt) (fit_single_frame.py:241); hand it the
+        # restated VPoser v1 with the seeded synthetic weights
+        from oracle import vposer_shim
+        vp = vposer_shim.from_weights(synthetic.make_vposer_like(seed=2), dtype=dtype)
+        ref.fit_single_frame.load_vposer = lambda *a, **k: (vp, None)
     H, W = [int(v) for v in inputs[frame + '/HW']]
-    focal = (W ** 2 + H ** 2) ** 0.5
+    focal = cfg.get('focal_length')                      # main.py:212-214
+    if focal is None:
+        focal = (W ** 2 + H ** 2) ** 0.5
     args = dict(cfg)
     camera = ref.camera.create_camera(focal_length_x=focal, focal_length_y=focal, dtype=dtype,
                                       **args)
@@ -251,6 +271,34 @@ def ref_eval(inputs, dtype=torch.float64, tag='f64'):
             if name != 'body_pose':
                 out[case + '/grad/' + name] = p.grad.numpy().copy()
         out[case + '/grad/pose_embedding'] = emb.grad.numpy().copy()
+        out[case + '/grad/camera_translation'] = camera.translation.grad.numpy().copy()
+    # VPoser latent pose (fitting.py:235-236, :389-395): reference loss + restated VPoser v1
+    from oracle import vposer_shim
+    vposer = vposer_shim.from_weights(synthetic.make_vposer_like(seed=2), dtype=dtype)
+    z = torch.tensor(rng.normal(size=(1, 32)) * 0.7, dtype=dtype, requires_grad=True)
+    z_reg = torch.tensor(rng.normal(size=(1, 32)) * 0.7, dtype=dtype)
+    out['vposer/latent'] = z.detach().numpy().copy()
+    out['vposer/latent_reg'] = z_reg.numpy().copy()
+    for case, regression, stage in (('vposer', None, 1), ('vposer_reg', z_reg, 2)):
+        loss = ref.fitting.create_loss(
+            loss_type='smplify', rho=100, use_joints_conf=True, use_face=True, use_hands=True,
+            vposer=vposer, interpenetration=False, dtype=dtype, regression_pose=regression,
+            num_stages=3, **pri)
+        loss.reset_loss_weights({k: v for k, v in weights.items()})
+        for p in list(body_model.parameters()) + [z, camera.translation]:
+            p.grad = None
+        bp = vposer.decode(z, output_type='aa').view(1, -1)
+        o = body_model(return_verts=True, body_pose=bp, return_full_pose=True)
+        val = loss(o, camera=camera, gt_joints=gt, body_model_faces=None, joints_conf=conf,
+                   joint_weights=jw, pose_embedding=z, use_vposer=True, stage=stage)
+        val.backward()
+        out[case + '/loss'] = val.detach().numpy()
+        out[case + '/body_pose'] = bp.detach().numpy()
+        out[case + '/joints'] = o.joints.detach().numpy()[0]
+        for name, p in body_model.named_parameters():
+            if name != 'body_pose':
+                out[case + '/grad/' + name] = p.grad.numpy().copy()
+        out[case + '/grad/pose_embedding'] = z.grad.numpy().copy()
         out[case + '/grad/camera_translation'] = camera.translation.grad.numpy().copy()
     # camera-init loss, both confidence modes
     init_idxs = [i for i in cfg['init_joints_idxs'] if i not in low]
@@ -401,3 +449,4 @@ if __name__ == '__main__':
     ref_eval(inp, torch.float32, 'f32')
     ref_stage(inp, torch.float64, 'f64')
     ref_fit('02_cropped', inp)
+    ref_fit('18_cropped', inp, cfg=cfg_smplifyx(), tag='ref_fit_18_vposer')

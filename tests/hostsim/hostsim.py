@@ -45,6 +45,13 @@ class HostSim(object):
         self.L = N.SfxLayout()
         self.lib.hs_layout(self.h, int(use_vposer), C.byref(self.L))
 
+    def set_vposer(self, w):
+        a = [np.ascontiguousarray(w[k], dtype=self.dt) for k in
+             ('dec_fc1_w', 'dec_fc1_b', 'dec_fc2_w', 'dec_fc2_b', 'dec_out_w', 'dec_out_b')]
+        self._vp_keep = a
+        self.lib.hs_set_vposer.argtypes = [C.c_void_p] * 7
+        self.lib.hs_set_vposer(self.h, *[x.ctypes.data_as(C.c_void_p) for x in a])
+
     def set_gmm(self, means, precisions, log_nll_weights):
         a = [np.ascontiguousarray(x, dtype=self.dt) for x in (means, precisions, log_nll_weights)]
         self.lib.hs_set_gmm.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3

@@ -20,6 +20,7 @@ struct SimModel {
     HostModel<T> h;
     int gmm_M = 0, gmm_D = 0;
     std::vector<T> gmm_means, gmm_prec, gmm_logw;
+    std::vector<T> vw1, vb1, vw2, vb2, vw3, vb3;
 };
 struct SimHandle {
     int use_double;
@@ -34,6 +35,10 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
                 T* grad_out, T* joints_out, int* n_evals, int* flags) {
     ModelView<T> M = sm.h.host_view();
     M.gmm_M = sm.gmm_M; M.gmm_D = sm.gmm_D;
+    if (!sm.vw1.empty()) {
+        M.vp_ready = 1; M.vp_w1 = sm.vw1.data(); M.vp_b1 = sm.vb1.data(); M.vp_w2 = sm.vw2.data();
+        M.vp_b2 = sm.vb2.data(); M.vp_w3 = sm.vw3.data(); M.vp_b3 = sm.vb3.data();
+    }
     M.gmm_means = sm.gmm_means.data(); M.gmm_prec = sm.gmm_prec.data(); M.gmm_logw = sm.gmm_logw.data();
     SfxLayout L = make_layout(sm.h.NB, sm.h.NE, sm.h.NH, use_vposer);
     std::unique_ptr<Scratch<T>> Sp(new Scratch<T>());
@@ -66,7 +71,26 @@ static void set_gmm(SimModel<T>& sm, int M, int D, const T* means, const T* prec
     sm.gmm_prec.assign(prec, prec + (size_t)M * D * D);
     sm.gmm_logw.assign(logw, logw + M);
 }
+template <typename T>
+static void set_vposer(SimModel<T>& sm, const T* w1, const T* b1, const T* w2, const T* b2,
+                       const T* w3, const T* b3) {
+    sm.vw1.assign(w1, w1 + 512 * 32); sm.vb1.assign(b1, b1 + 512);
+    sm.vw2.assign(w2, w2 + 512 * 512); sm.vb2.assign(b2, b2 + 512);
+    sm.vw3.assign((size_t)128 * 512, (T)0); sm.vb3.assign(128, (T)0);
+    for (size_t i = 0; i < (size_t)126 * 512; ++i) sm.vw3[i] = w3[i];
+    for (int i = 0; i < 126; ++i) sm.vb3[i] = b3[i];
+}
 extern "C" {
+void hs_set_vposer(void* p, const void* w1, const void* b1, const void* w2, const void* b2,
+                   const void* w3, const void* b3) {
+    SimHandle* h = (SimHandle*)p;
+    if (h->use_double)
+        set_vposer<double>(h->d, (const double*)w1, (const double*)b1, (const double*)w2,
+                           (const double*)b2, (const double*)w3, (const double*)b3);
+    else
+        set_vposer<float>(h->f, (const float*)w1, (const float*)b1, (const float*)w2,
+                          (const float*)b2, (const float*)w3, (const float*)b3);
+}
 int hs_trace(double* out, int cap) {
     int n = (int)g_trace.size();
     for (int i = 0; i < n && i < cap; ++i) out[i] = g_trace[i];

@@ -93,3 +93,33 @@ def test_pipeline_launch_equals_staged_launches():
     assert np.array_equal(a.n_evals, b.n_evals)
     assert np.array_equal(a.vertices, b.vertices)
     assert a.n_evals[0] > 1.5 * a.n_evals[1]          # frame 0 really ran two orientations
+
+
+def test_vposer_five_stage_fit_against_reference():
+    """BASELINE config 3 flow on a demo frame: fit_smplx_smplifyx schedule (5 stages, VPoser
+    latent pose, guess_init camera, focal 5000) against the reference's fit_single_frame driving
+    the restated VPoser (tests/golden/ref_fit_18_vposer.npz)."""
+    from smplifyx_b200 import engine, fit_frames as FF, vposer as V
+    inp = Cm.golden('demo_inputs.npz')
+    ref = Cm.golden('ref_fit_18_vposer.npz')
+    cfg = json.loads(str(ref['cfg_json']))
+    cfg['body_tri_idxs'] = [tuple(p) for p in cfg['body_tri_idxs']]
+    model = engine.Model(Cm.model_data(), Cm.joint_map(), dtype=torch.float32, **Cm.MODEL_KW)
+    vp = V.VPoser(Cm.vposer_weights())
+    model.set_vposer(vp.weights)
+    kp, H, W, expose, pixie = _frame_inputs(inp, '18_cropped')
+    batch = engine.FrameBatch(model, 2, use_vposer=True)
+    out = FF.fit_frames(batch, np.stack([kp, kp]), H, W, cfg, vposer=vp)
+    assert out.flags.max() == 0
+    assert np.array_equal(out.params[0], out.params[1])
+    r = out.results[0]
+    assert r['body_pose'].shape == (1, 63) and r['focal_length'] == 5000.0
+    # the camera stage is well conditioned: guess_init depth + stage C
+    assert np.allclose(r['camera_translation'], ref['result/camera_translation'], atol=0.15)
+    err = np.abs(out.vertices[0] - ref['vertices'])
+    n_ref = int(ref['n_forward_calls']) - 6
+    print('vposer fit: vertex error max %.4g mean %.4g; evals %d (reference %d)' %
+          (err.max(), err.mean(), out.n_evals[0], n_ref))
+    # chaotic 5-stage trajectory (DESIGN.md "Parity"): same basin, centimetre-level agreement
+    assert err.mean() < 3e-2 and err.max() < 0.25
+    assert 0.4 * n_ref < out.n_evals[0] < 2.5 * n_ref

@@ -98,6 +98,35 @@ def test_mixture_prior_matches_reference(model32, model64):
         assert np.all(np.isfinite(final)) and np.all(final < 0.8 * ref)
 
 
+@pytest.mark.parametrize('case', ['vposer', 'vposer_reg'])
+def test_vposer_latent_pose_matches_reference(case):
+    """VPoser decoder + adjoint inside the evaluation kernel (fitting.py:235-236, :389-395)."""
+    for dt, evn, tl, tg in ((torch.float64, 'ref_eval_f64.npz', 1e-10, 1e-8),
+                            (torch.float32, 'ref_eval_f32.npz', 1e-5, 1e-3)):
+        ev = Cm.golden(evn)
+        model = _engine().Model(Cm.model_data(), Cm.joint_map(), dtype=dt, **Cm.MODEL_KW)
+        model.set_vposer(Cm.vposer_weights())
+        I = Cm.eval_case_inputs(ev, case)
+        batch = _engine().FrameBatch(model, 3, use_vposer=True)
+        assert batch.L.n_pose == 32
+        B = 3
+        rep = lambda a: None if a is None else np.repeat(np.asarray(a)[None], B, axis=0)
+        kp = np.concatenate([I['gt'], I['conf'][:, None]], axis=1)
+        batch.set_targets(rep(kp), rep(I['jw']), rep(I['lowconf']), rep(I['init_mask']),
+                          rep(I['cam']), rep(I['reg_pose']))
+        batch.set_params(rep(I['x']))
+        loss, grad, joints = batch.eval(I['stage'], want_joints=True)
+        ref = float(ev[case + '/loss'])
+        assert np.allclose(loss.cpu().numpy(), ref, rtol=tl, atol=0)
+        g_ref = Cm.golden_grad_vector(I['L'], ev, case)
+        assert np.abs(grad.cpu().numpy()[2] - g_ref).max() <= tg * np.abs(g_ref).max()
+        assert np.abs(joints.cpu().numpy()[0] - ev[case + '/joints']).max() < (1e-11 if dt == torch.float64 else 3e-5)
+        final = batch.fit_stage(I['stage']).cpu().numpy()
+        assert np.all(np.isfinite(final)) and np.all(final < 0.8 * ref)
+        verts, _ = batch.forward_mesh()
+        assert bool(torch.isfinite(verts).all())
+
+
 def test_ring_and_direct_streams_agree(model32, monkeypatch):
     """The TMA ring and the plain-load path of the blend passes give the same bits."""
     ev = Cm.golden('ref_eval_f32.npz')

@@ -67,6 +67,25 @@ def test_mixture_prior_f64(hs64):
     assert abs(ref - float(ev['l2/loss'])) > 1e3
 
 
+@pytest.mark.parametrize('case', ['vposer', 'vposer_reg'])
+def test_vposer_latent_pose_f64(case):
+    """Latent pose through the VPoser decoder (fitting.py:235-236) + latent prior (:389-395):
+    loss and gradient wrt the 32-D embedding and every other parameter against the reference
+    loss stack driving the restated VPoser v1 (oracle/vposer_shim.py)."""
+    ev = Cm.golden('ref_eval_f64.npz')
+    I = Cm.eval_case_inputs(ev, case)
+    hs = HostSim(Cm.model_data(), Cm.joint_map(), use_double=True, use_vposer=True, **Cm.MODEL_KW)
+    hs.set_vposer(Cm.vposer_weights())
+    r = hs.eval(I['stage'], I['x'], I['gt'], I['conf'], I['jw'], I['cam'], I['lowconf'],
+                I['init_mask'], I['reg_pose'])
+    ref = float(ev[case + '/loss'])
+    assert abs(r['loss'] - ref) <= 1e-12 * abs(ref)
+    g_ref = Cm.golden_grad_vector(I['L'], ev, case)
+    assert I['L'].n_pose == 32
+    assert np.abs(r['grad'] - g_ref).max() <= 1e-10 * np.abs(g_ref).max()
+    assert np.abs(r['joints'] - ev[case + '/joints']).max() < 1e-13
+
+
 def test_gradient_against_finite_differences(hs64):
     ev = Cm.golden('ref_eval_f64.npz')
     I = Cm.eval_case_inputs(ev, 'reg')
