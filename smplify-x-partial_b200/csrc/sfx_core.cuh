@@ -308,6 +308,11 @@ template <typename T>
 __device__ __forceinline__ void rows_dot(const T* W, const T* bias, int nrows, const T* x, T* y, void* wsp);
 template <typename T>
 __device__ __forceinline__ void rows_accum(const T* W, int nrows, const T* g, T* out, void* wsp);
+template <typename T>
+struct Scratch;
+template <typename T>
+__device__ __forceinline__ bool two_loop_staged(Scratch<T>& S, int k, int head, int H, T hd,
+                                                const T* hist_s, const T* hist_y, int D, void* wsp);
 #else
 template <typename T>
 static void rows_dot(const T* W, const T* bias, int nrows, const T* x, T* y, void*) {
@@ -1630,6 +1635,10 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
                     ys_row[i] = S.q[i];
                     ss_row[i] = S.x0[i];
                 }
+#ifdef __CUDACC__
+                // the rows are read back by TMA bulk copies (async proxy) in two_loop_staged
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+#endif
                 if (SFX_TID == 0) S.ro[ls.num_old - 1] = (T)1 / ys;
                 T yy = block_dot(S.q, S.q, D, &S.red[2]);
                 ls.H_diag = ys / yy;
@@ -1640,8 +1649,10 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
             if (!E.st->generic_two_loop) {
                 SFX_SYNC();
                 SFX_PROF_BEGIN(tl);
-                if (threadIdx.x < 32)
-                    two_loop_warp(S, k, ls.head, H, ls.H_diag, hist_s, hist_y, D);
+                if (threadIdx.x < 32) {
+                    if (!two_loop_staged(S, k, ls.head, H, ls.H_diag, hist_s, hist_y, D, E.stream_ws))
+                        two_loop_warp(S, k, ls.head, H, ls.H_diag, hist_s, hist_y, D);
+                }
                 SFX_SYNC();
                 SFX_PROF_END(S, 1, tl);
             } else

@@ -45,6 +45,9 @@ __device__ __forceinline__ StreamWS carve_stream(unsigned char* base, int ring_m
     ws.ring = base;
     ws.bars = reinterpret_cast<uint64_t*>(base + ring);
     ws.fills = reinterpret_cast<unsigned int*>(base + ring + SFX_NWARP * SFX_NBUF * sizeof(uint64_t));
+    ws.tl_bars = reinterpret_cast<uint64_t*>(base + ring + SFX_NWARP * SFX_NBUF * sizeof(uint64_t) +
+                                             SFX_NWARP * sizeof(unsigned int));
+    ws.tl_calls = reinterpret_cast<unsigned int*>(ws.tl_bars + SFX_TL_GROUPS);
     ws.ring_mode = ring_mode;
     return ws;
 }

@@ -25,8 +25,11 @@ struct StreamWS {
     unsigned char* ring;        // ring mode: [NWARP][NBUF][512*sizeof(T)]; else partials only
     uint64_t* bars;             // [NWARP][NBUF]
     unsigned int* fills;        // [NWARP] number of buffers filled so far (phase tracking)
+    uint64_t* tl_bars;          // [SFX_TL_GROUPS] two-loop history staging (see two_loop_staged)
+    unsigned int* tl_calls;     // [1] staged two-loop calls so far (phase tracking)
     int ring_mode;
 };
+#define SFX_TL_GROUPS 8
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -70,6 +73,8 @@ __device__ __forceinline__ void stream_init(StreamWS& ws) {
     if (ws.ring_mode) {
         if (threadIdx.x < SFX_NWARP * SFX_NBUF) mbar_init(ws.bars + threadIdx.x, 1);
         if (threadIdx.x < SFX_NWARP) ws.fills[threadIdx.x] = 0;
+        if (threadIdx.x < SFX_TL_GROUPS) mbar_init(ws.tl_bars + threadIdx.x, 1);
+        if (threadIdx.x == 0) ws.tl_calls[0] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -255,11 +260,127 @@ __device__ __forceinline__ void rows_accum(const T* W, int nrows, const T* g, T*
     if (ws.ring_mode) fence_proxy_async();
 }
 
+
+// ---- L-BFGS two-loop recursion with the history staged in shared memory --------------------
+// The (s, y) pairs live in global memory (154 KB per frame); reading them pair by pair puts an
+// L2 round trip on the critical path of every step of the recursion.  Here lane 0 issues one TMA
+// bulk copy per history row at the start -- all 2k of them in flight at once, into the blend
+// ring that is idle at this point -- grouped on 8 mbarriers in consumption order; the first loop
+// starts as soon as the newest group has landed and the second loop re-reads the same shared
+// memory, so the history crosses the L2->SM path once per iteration instead of twice.
+// Arithmetic and summation order are those of two_loop_warp_n / block_reduce (bit-identical).
+template <typename T, int NR>
+__device__ __noinline__ void two_loop_staged_n(Scratch<T>& S, int k, int head, int H, T hd,
+                                               const T* __restrict__ hist_s,
+                                               const T* __restrict__ hist_y, int D, StreamWS& ws) {
+    const int lane = threadIdx.x;
+    const uint32_t RB = (uint32_t)((D * sizeof(T) + 15) & ~(size_t)15);
+    const int per = (k + SFX_TL_GROUPS - 1) / SFX_TL_GROUPS;
+    const unsigned int parity = ws.tl_calls[0] & 1;
+    unsigned char* base = ws.ring;
+    if (lane == 0) {
+        fence_proxy_async();
+        int pos = (head + k - 1) % H;
+        for (int g = 0; g < SFX_TL_GROUPS; ++g) {
+            const int first = g * per;
+            const int n = first < k ? (k - first < per ? k - first : per) : 0;
+            mbar_expect_tx(ws.tl_bars + g, (uint32_t)n * 2 * RB);
+            for (int j = 0; j < n; ++j) {
+                unsigned char* dst = base + (size_t)(first + j) * 2 * RB;
+                bulk_g2s(dst, hist_s + (long)pos * SFX_NP_MAX, RB, ws.tl_bars + g);
+                bulk_g2s(dst + RB, hist_y + (long)pos * SFX_NP_MAX, RB, ws.tl_bars + g);
+                pos = pos == 0 ? H - 1 : pos - 1;
+            }
+        }
+    }
+    __syncwarp();
+    const bool tail_live = 32 * (NR - 1) + lane < D;
+    T q[NR], sc[NR], yc[NR], sn[NR], yn[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int e = 32 * r + lane;
+        q[r] = e < D ? -S.g[e] : (T)0;
+    }
+#define SFX_TL_LOAD(dsts, dsty, idx)                                                \
+    do {                                                                            \
+        const T* ps_ = reinterpret_cast<const T*>(base + (size_t)(idx) * 2 * RB) + lane;      \
+        const T* py_ = reinterpret_cast<const T*>(base + (size_t)(idx) * 2 * RB + RB) + lane; \
+        _Pragma("unroll") for (int r = 0; r < NR - 1; ++r) {                        \
+            dsts[r] = ps_[32 * r];                                                  \
+            dsty[r] = py_[32 * r];                                                  \
+        }                                                                           \
+        dsts[NR - 1] = tail_live ? ps_[32 * (NR - 1)] : (T)0;                       \
+        dsty[NR - 1] = tail_live ? py_[32 * (NR - 1)] : (T)0;                       \
+    } while (0)
+    // ---- first loop: consumption index idx = 0 .. k-1  <->  pair i = k-1-idx ----
+    mbar_wait(ws.tl_bars, parity);
+    SFX_TL_LOAD(sn, yn, 0);
+    for (int idx = 0; idx < k; ++idx) {
+        const int i = k - 1 - idx;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { sc[r] = sn[r]; yc[r] = yn[r]; }
+        if (idx + 1 < k) {
+            if ((idx + 1) % per == 0) mbar_wait(ws.tl_bars + (idx + 1) / per, parity);
+            SFX_TL_LOAD(sn, yn, idx + 1);
+        }
+        T p = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) p = p + sc[r] * q[r];
+        p = warp_tree_sum(p, S.tl_red + 32 * (i & 1), lane);
+        const T a = p * S.ro[i];
+        if (lane == 0) S.al[i] = a;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) q[r] += -a * yc[r];
+    }
+    // groups that hold no pair still complete their phase: wait so every barrier is observed
+    for (int g = (k + per - 1) / per; g < SFX_TL_GROUPS; ++g) mbar_wait(ws.tl_bars + g, parity);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) q[r] = q[r] * hd;       // q now holds the direction d
+    __syncwarp();
+    // ---- second loop: pair i = 0 .. k-1  <->  idx = k-1-i (already in shared memory) ----
+    SFX_TL_LOAD(sn, yn, k - 1);
+    for (int i = 0; i < k; ++i) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { sc[r] = sn[r]; yc[r] = yn[r]; }
+        if (i + 1 < k) SFX_TL_LOAD(sn, yn, k - 2 - i);
+        T p = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) p = p + yc[r] * q[r];
+        p = warp_tree_sum(p, S.tl_red + 32 * (i & 1), lane);
+        const T co = S.al[i] - p * S.ro[i];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) q[r] += co * sc[r];
+    }
+#undef SFX_TL_LOAD
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int e = 32 * r + lane;
+        if (e < D) S.d[e] = q[r];
+    }
+    __syncwarp();
+    if (lane == 0) ws.tl_calls[0] += 1;
+}
+
+// returns false when the staged path does not apply (plain-load mode, or history too large for
+// the ring: float64, more than 128 active parameters with a long history)
+template <typename T>
+__device__ __forceinline__ bool two_loop_staged(Scratch<T>& S, int k, int head, int H, T hd,
+                                                const T* hist_s, const T* hist_y, int D, void* wsp) {
+    StreamWS& ws = *reinterpret_cast<StreamWS*>(wsp);
+    const size_t RB = (D * sizeof(T) + 15) & ~(size_t)15;
+    const size_t ring_bytes = (size_t)SFX_NWARP * SFX_NBUF * SFX_KPAD * sizeof(T);
+    if (!ws.ring_mode || k < 1 || (size_t)k * 2 * RB > ring_bytes || D > 128) return false;
+    if (D <= 32) two_loop_staged_n<T, 1>(S, k, head, H, hd, hist_s, hist_y, D, ws);
+    else two_loop_staged_n<T, 4>(S, k, head, H, hd, hist_s, hist_y, D, ws);
+    return true;
+}
+
 template <typename T>
 __host__ __device__ inline size_t stream_smem_bytes(int ring_mode) {
     size_t ring = ring_mode ? (size_t)SFX_NWARP * SFX_NBUF * SFX_KPAD * sizeof(T)
                             : (size_t)SFX_NWARP * SFX_KPAD * sizeof(T);
-    return ring + SFX_NWARP * SFX_NBUF * sizeof(uint64_t) + SFX_NWARP * sizeof(unsigned int) + 64;
+    return ring + SFX_NWARP * SFX_NBUF * sizeof(uint64_t) + SFX_NWARP * sizeof(unsigned int) +
+           SFX_TL_GROUPS * sizeof(uint64_t) + 16 + 64;
 }
 
 }  // namespace sfx
