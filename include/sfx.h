@@ -79,11 +79,25 @@ int sfx_model_set_vposer(sfx_model* m, const void* fc1_w, const void* fc1_b, con
 int sfx_model_set_gmm(sfx_model* m, int32_t num_gaussians, int32_t dim, const void* means,
                       const void* precisions, const void* log_nll_weights);
 
+/* Interpenetration term (reference fitting.py:437-455): the face segmentation the reference
+ * loads from part_segm_fn at fit_single_frame.py:317-328 (`segm` [F] = body part of every face,
+ * `parents` [F] = kinematic parent of that part; parts 0..63) and its ign_part_pairs option
+ * ([n,2] part ids) -- the inputs of mesh_intersection.FilterFaces.  Stands in for the
+ * construction of BVH / FilterFaces / DistanceFieldPenetrationLoss at fit_single_frame.py:300-328.
+ * The device path needs the segmentation (it is its broad phase); point2plane = False and
+ * penalize_outside = True, the values of every shipped configuration, are what is built. */
+int sfx_model_set_collision(sfx_model* m, const int32_t* faces_segm, const int32_t* faces_parents,
+                            const int32_t* ign_part_pairs, int32_t n_ign_pairs);
+
 /* Per-batch workspace: parameters, targets, L-BFGS history for B independent frames.
  * use_vposer selects a 32-D latent pose block instead of the 63-D axis-angle one. */
 int sfx_batch_create(const sfx_model* m, int32_t num_frames, int32_t use_vposer, sfx_batch** out);
 void sfx_batch_destroy(sfx_batch* b);
 int sfx_batch_layout(const sfx_batch* b, SfxLayout* out);
+/* Allocates the full-mesh workspace of the interpenetration term (about 1.7 MB per frame in
+ * float32).  Needed before a stage with coll_loss_weight > 0 (SfxStage) is evaluated or fitted;
+ * df_cone_height travels as SfxStage.coll_sigma. */
+int sfx_batch_enable_collisions(sfx_batch* b);
 
 /* Targets of every frame (host pointers; copied with cudaMemcpyAsync on `stream`):
  *   keypoints [B,K,3] (x, y, conf)        fit_single_frame.py:276-284

@@ -14,6 +14,7 @@ SFX_MAX_BLOCKS = 12
 SFX_NP_MAX = 192
 SFX_KMAX = 160
 SFX_CAM_STRIDE = 16
+SFX_FLAG_NAN, SFX_FLAG_INF, SFX_FLAG_COLL_OVERFLOW = 1, 2, 4
 SFX_CAM_FX, SFX_CAM_FY, SFX_CAM_CX, SFX_CAM_CY, SFX_CAM_R, SFX_CAM_DW, SFX_CAM_TZ = 0, 1, 2, 3, 4, 13, 14
 
 LOSS_SMPLIFY, LOSS_CAMERA_INIT = 0, 1
@@ -52,6 +53,7 @@ class SfxStage(C.Structure):
         ('block_start', C.c_int * SFX_MAX_BLOCKS), ('block_len', C.c_int * SFX_MAX_BLOCKS),
         ('block_off', C.c_int * SFX_MAX_BLOCKS), ('need_blend_grad', C.c_int),
         ('generic_two_loop', C.c_int),
+        ('coll_loss_weight', C.c_double), ('coll_sigma', C.c_double),
     ]
 
 
@@ -187,7 +189,8 @@ def make_stage(L, blocks, loss_kind=LOSS_SMPLIFY, opt_kind=OPT_LBFGSLS, pprior_k
                expr_prior_weight=0.0, jaw_prior_weight=(0.0, 0.0, 0.0), hand_joint_weight=0.0,
                face_joint_weight=0.0, depth_loss_weight=0.0, maxiters=30, ftol=1e-9, gtol=1e-9,
                lr=1.0, max_iter=None, max_eval=None, history=100, tol_grad=1e-5,
-               tol_change=1e-9, adam_beta1=0.9, adam_beta2=0.999, adam_eps=1e-8):
+               tol_change=1e-9, adam_beta1=0.9, adam_beta2=0.999, adam_eps=1e-8,
+               coll_loss_weight=0.0, coll_sigma=0.5):
     """Builds an SfxStage.  ``max_iter`` defaults to ``maxiters`` and ``max_eval`` to
     ``max_iter * 5 // 4`` exactly like create_optimizer('lbfgsls') (optim_factory.py:51-53,
     lbfgs_ls.py:202-203)."""
@@ -213,6 +216,7 @@ def make_stage(L, blocks, loss_kind=LOSS_SMPLIFY, opt_kind=OPT_LBFGSLS, pprior_k
     st.history = history
     st.tol_grad, st.tol_change = tol_grad, tol_change
     st.adam_beta1, st.adam_beta2, st.adam_eps = adam_beta1, adam_beta2, adam_eps
+    st.coll_loss_weight, st.coll_sigma = float(coll_loss_weight), float(coll_sigma)
     pb = param_blocks(L)
     pos = 0
     if len(blocks) > SFX_MAX_BLOCKS:
@@ -246,6 +250,8 @@ def load_library(path=None):
     lib.sfx_model_create.argtypes = [C.POINTER(SfxModelDesc), C.POINTER(vp)]
     lib.sfx_model_set_vposer.argtypes = [vp] * 7
     lib.sfx_model_set_gmm.argtypes = [vp, i32, i32, vp, vp, vp]
+    lib.sfx_model_set_collision.argtypes = [vp, vp, vp, vp, i32]
+    lib.sfx_batch_enable_collisions.argtypes = [vp]
     lib.sfx_model_destroy.argtypes = [vp]
     lib.sfx_model_destroy.restype = None
     lib.sfx_batch_create.argtypes = [vp, i32, i32, C.POINTER(vp)]

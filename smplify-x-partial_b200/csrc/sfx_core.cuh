@@ -94,6 +94,15 @@ struct ModelView {
     const T* vp_b2;         // [512]
     const T* vp_w3;         // [128][512]  bodyprior_dec_out.weight (126 rows + 2 zero rows)
     const T* vp_b3;         // [128]
+    // interpenetration term (sfx_collide.cuh); coll_ready = 0 until sfx_model_set_collision
+    int coll_ready, F, n_parts;
+    const int* faces;                      // [F][3]
+    const int* part_ptr;                   // [n_parts + 1]  faces grouped by body part (CSR)
+    const int* part_faces;                 // [F]            face ids, ascending within a part
+    const unsigned char* face_part;        // [F]            part of every face
+    const unsigned long long* part_allow;  // [SFX_NPART_MAX] bit q of word p: FilterFaces keeps (p, q)
+    const int* vf_ptr;                     // [V + 1]        vertex -> incident faces (CSR)
+    const int* vf_idx;                     // [3F]           face * 4 + corner
     int parents[SFX_NJ];
     int order[SFX_NJ];      // joints sorted by depth
     int level_off[16];
@@ -122,6 +131,12 @@ struct BatchView {
     int* flags;          // [B]
     const int* frame_ids;   // optional indirection (nullptr: block b -> frame b)
     long long* prof;        // [B][8] cycle counters (builds with -DSFX_CYCLE_PROF only)
+    // interpenetration term: global workspace, one slot per block (nullptr until
+    // sfx_batch_enable_collisions).  Values: vp[3V] | vert[3V] | dvert[3V] | dtri[9F] | box[6F];
+    // indices: tv[V] | face[F]
+    T* coll_vals;
+    unsigned short* coll_idx;
+    long coll_vals_stride, coll_idx_stride;
 };
 
 // per-frame working set (shared memory on the device)
@@ -164,6 +179,10 @@ struct Scratch {
     T tl_red[64];             // two-loop recursion: per-lane partial sums (double buffered)
     long long prof[8];        // cycle counters: 0 eval, 1 two-loop, 2 blend fwd, 3 blend adj, 4 total
     T gq[16];                 // mixture prior: per-component negative log-likelihood
+    // interpenetration term: ordered-compaction state, touched-vertex count
+    int cscan[2][32];
+    int cscan_total, cscan_calls, coll_overflow, n_touch;
+    T coll_loss;
     T loss;
     int dynrow;
     int n_evals;
@@ -309,6 +328,11 @@ __device__ __forceinline__ void rows_dot(const T* W, const T* bias, int nrows, c
 template <typename T>
 __device__ __forceinline__ void rows_accum(const T* W, int nrows, const T* g, T* out, void* wsp);
 template <typename T>
+__device__ __forceinline__ void blend_forward_full(const ModelView<T>& M, Scratch<T>& S, void* wsp, T* vp_g);
+template <typename T>
+__device__ __forceinline__ void blend_adjoint_ext(const ModelView<T>& M, Scratch<T>& S, void* wsp,
+                                                  const unsigned short* tv, const T* dvp_g);
+template <typename T>
 struct Scratch;
 template <typename T>
 __device__ __forceinline__ bool two_loop_staged(Scratch<T>& S, int k, int head, int H, T hd,
@@ -347,6 +371,29 @@ static void blend_adjoint(const ModelView<T>& M, Scratch<T>& S, void*) {
         T w = S.dvp[r];
         for (int k = 0; k < SFX_KPAD; ++k) S.dc[k] += p[k] * w;
     }
+}
+// every row of the blend matrix: vp_g[r] = vt[r] + PK[r] . c   (interpenetration term)
+template <typename T>
+static void blend_forward_full(const ModelView<T>& M, Scratch<T>& S, void*, T* vp_g) {
+    for (long r = 0; r < 3L * M.V; ++r) {
+        const T* p = M.PK + r * SFX_KPAD;
+        T acc = 0;
+        for (int k = 0; k < SFX_KPAD; ++k) acc += p[k] * S.c[k];
+        vp_g[r] = M.vt[r] + acc;
+    }
+}
+// support rows followed by the rows of the touched vertices tv (weights dvpc[3 t + k])
+template <typename T>
+static void blend_adjoint_ext(const ModelView<T>& M, Scratch<T>& S, void* w, const unsigned short* tv,
+                              const T* dvpc) {
+    blend_adjoint(M, S, w);
+    for (int t = 0; t < S.n_touch; ++t)
+        for (int c = 0; c < 3; ++c) {
+            const long row = 3L * tv[t] + c;
+            const T* p = M.PK + row * SFX_KPAD;
+            const T wgt = dvpc[3 * t + c];
+            for (int k = 0; k < SFX_KPAD; ++k) S.dc[k] += p[k] * wgt;
+        }
 }
 #endif
 
@@ -883,30 +930,49 @@ SFX_FN T gmm_prior(const ModelView<T>& M, const T* pose, Scratch<T>& S, T* grad)
     return val;
 }
 
+}  // namespace sfx
+#include "sfx_collide.cuh"
+namespace sfx {
+
 // One evaluation of the stage objective and its gradient for one frame (the reference's
 // closure, fitting.py:232-273).  Reads S.x, writes S.loss and S.gfull.  Needs
 // support_begin_frame() once per frame and stage_joint_weights() once per stage beforehand.
 template <typename T>
 SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const SfxStage& st,
                                 const T* gt, const T* conf, const unsigned char* init_mask,
-                                const T* cam, const T* reg_pose, Scratch<T>& S, void* stream_ws) {
+                                const T* cam, const T* reg_pose, Scratch<T>& S, void* stream_ws,
+                                const CollWS<T>* CW = nullptr) {
     const int NS = M.NS;
     const int nj = M.NJOUT;
     const int K = M.K;
     SFX_PROF_BEGIN(eval);
     const bool vposer = st.use_vposer != 0;
+    // interpenetration term: active in body stages with a positive weight (fitting.py:439)
+    const bool coll = CW != nullptr && M.coll_ready && st.loss_kind == SFX_LOSS_SMPLIFY &&
+                      st.coll_loss_weight > 0;
     pose_prologue(M, L, S, vposer, stream_ws);
     // ---- 3. kinematic chain (warp 0) || blendshapes on the support vertices (every warp) ----
     SFX_PROF_BEGIN(bf);
     if (SFX_IS_WARP0) chain_forward(M, S);
     SFX_PROF_END(S, 5, bf);                     // chain alone (warp 0)
     SFX_PROF_BEGIN(bs);
-    blend_forward(M, S, stream_ws);
+    if (coll) {
+        // the whole mesh is needed: stream every row once, the support rows are a subset
+        blend_forward_full(M, S, stream_ws, CW->vp_g);
+        SFX_SYNC();
+        SFX_FOR(r, SFX_NSLOT * 3) S.vp[r] = CW->vp_g[3L * S.vid[r / 3] + (r % 3)];
+    } else {
+        blend_forward(M, S, stream_ws);
+    }
 #if defined(__CUDACC__) && defined(SFX_CYCLE_PROF)
     if (threadIdx.x == 32) S.prof[6] += clock64() - _t_bs;      // warp 1's own streaming time
 #endif
     SFX_SYNC();
     SFX_PROF_END(S, 2, bf);
+    if (coll) {
+        coll_skin_mesh(M, S, *CW);
+        coll_search_and_penalty(M, S, *CW, (T)st.coll_sigma, (T)st.coll_loss_weight);
+    }
     // ---- 4. skinning of the support vertices ------------------------------------------
     SFX_FOR(s, SFX_NSLOT) {
         T Tm[12];
@@ -1042,12 +1108,14 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.dA[i] = acc;
     }
     SFX_SYNC();
+    if (coll && S.n_touch > 0) coll_skin_adjoint(M, S, *CW);
     // ---- 8. adjoint of the chain (warp 0) || adjoint of the blendshapes (every warp) -----
     SFX_PROF_BEGIN(ba);
     if (SFX_IS_WARP0) chain_adjoint(M, S);
     SFX_PROF_END(S, 7, ba);                     // chain adjoint alone (warp 0)
     if (st.need_blend_grad) {
-        blend_adjoint(M, S, stream_ws);
+        if (coll && S.n_touch > 0) blend_adjoint_ext(M, S, stream_ws, CW->tv_g, CW->vert_g);
+        else blend_adjoint(M, S, stream_ws);
     } else {
         SFX_FOR(i, SFX_KPAD) S.dc[i] = 0;
     }
@@ -1204,6 +1272,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
             }
         }
         total += ang * bendw;
+        if (coll) total += (T)st.coll_loss_weight * S.coll_loss;      // pen_loss (fitting.py:453-458)
         T jaw = 0;
         for (int e = 0; e < 3; ++e) {
             T v = S.x[L.off_jaw + e] * (T)st.jaw_prior_weight[e];
@@ -1223,6 +1292,8 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.loss = total;
         S.n_evals += 1;
         S.n_passes += st.need_blend_grad ? 2 : 1;
+        // rows beyond the 675 support rows, in units of one support pass
+        if (coll) S.n_passes += (3 * M.V + 3 * S.n_touch) / (3 * SFX_NSLOT);
     }
     SFX_SYNC();
     SFX_PROF_END(S, 0, eval);
@@ -1289,6 +1360,7 @@ struct EvalCtx {
     const T* cam;
     const T* reg_pose;
     void* stream_ws;
+    const CollWS<T>* coll;      // workspace of the interpenetration term, or nullptr
 };
 
 // closure(): evaluate at S.xa, leave loss in S.loss and the compact gradient in S.gl
@@ -1297,7 +1369,7 @@ template <typename T>
 SFX_FN double closure(const EvalCtx<T>& E, Scratch<T>& S) {
     const int D = E.st->n_active;
     scatter_active(S, D);
-    eval_frame(*E.M, *E.L, *E.st, E.gt, E.conf, E.init_mask, E.cam, E.reg_pose, S, E.stream_ws);
+    eval_frame(*E.M, *E.L, *E.st, E.gt, E.conf, E.init_mask, E.cam, E.reg_pose, S, E.stream_ws, E.coll);
     gather_grad(S, D, S.gl);
     return (double)S.loss;
 }

@@ -64,9 +64,24 @@ __device__ __forceinline__ void load_frame(const BatchView<T>& Bv, int f, Scratc
         S.x[i] = i < np ? Bv.params[(size_t)f * np + i] : (T)0;
     if (threadIdx.x == 0) {
         S.n_evals = S.n_passes = 0;
+        S.n_touch = 0;
+        S.coll_overflow = 0;
         for (int i = 0; i < 8; ++i) S.prof[i] = 0;
     }
     __syncthreads();
+}
+
+// workspace of the interpenetration term for this block: global slot blockIdx.x + the blend
+// ring as shared work area (idle while the search runs)
+template <typename T>
+__device__ __forceinline__ bool block_coll_ws(const ModelView<T>& M, const BatchView<T>& Bv,
+                                              const StreamWS& ws, CollWS<T>& W) {
+    if (!M.coll_ready || !Bv.coll_vals) return false;
+    const int ring_bytes = (int)((ws.ring_mode ? (size_t)SFX_NWARP * SFX_NBUF : (size_t)SFX_NWARP) *
+                                 SFX_KPAD * sizeof(T));
+    W = coll_block_ws<T>(M.V, M.F, Bv.coll_vals + (size_t)blockIdx.x * Bv.coll_vals_stride,
+                         Bv.coll_idx + (size_t)blockIdx.x * Bv.coll_idx_stride, ws.ring, ring_bytes);
+    return true;
 }
 
 template <typename T>
@@ -97,9 +112,12 @@ fit_stage_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__
     E.cam = Bv.cam + (size_t)f * SFX_CAM_STRIDE;
     E.reg_pose = Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr;
     E.stream_ws = &ws;
+    CollWS<T> CW;
+    E.coll = block_coll_ws(M, Bv, ws, CW) ? &CW : nullptr;
     double r = run_fitting(E, S, Bv.hist_s + (size_t)f * SFX_HIST * SFX_NP_MAX,
                            Bv.hist_y + (size_t)f * SFX_HIST * SFX_NP_MAX, &flags);
     __syncthreads();
+    if (threadIdx.x == 0 && S.coll_overflow) flags |= SFX_FLAG_COLL_OVERFLOW;
     const int np = Bv.lay.np;
     for (int i = threadIdx.x; i < np; i += blockDim.x) Bv.params[(size_t)f * np + i] = S.x[i];
     if (threadIdx.x == 0) {
@@ -128,9 +146,13 @@ eval_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ Batc
     support_begin_frame(M, S);
     stage_setup(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
                 Bv.init_mask + (size_t)f * K, K, S);
+    CollWS<T> CW;
+    const bool has_coll = block_coll_ws(M, Bv, ws, CW);
     eval_frame(M, Bv.lay, st, Bv.gt + (size_t)f * K * 2, Bv.conf + (size_t)f * K,
                Bv.init_mask + (size_t)f * K, Bv.cam + (size_t)f * SFX_CAM_STRIDE,
-               Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr, S, &ws);
+               Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr, S, &ws,
+               has_coll ? &CW : nullptr);
+    if (threadIdx.x == 0 && S.coll_overflow) Bv.flags[f] |= SFX_FLAG_COLL_OVERFLOW;
     const int np = Bv.lay.np;
     if (loss_out && threadIdx.x == 0) loss_out[f] = S.loss;
     if (grad_out)
@@ -312,6 +334,8 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
         E.cam = Bv.cam + (size_t)f * SFX_CAM_STRIDE;
         E.reg_pose = Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr;
         E.stream_ws = &ws;
+        CollWS<T> CW;
+        E.coll = block_coll_ws(M, Bv, ws, CW) ? &CW : nullptr;
         T* hs = Bv.hist_s + (size_t)f * SFX_HIST * SFX_NP_MAX;
         T* hy = Bv.hist_y + (size_t)f * SFX_HIST * SFX_NP_MAX;
         // stage C: camera translation + global orientation (fit_single_frame.py:473-496)
@@ -362,7 +386,7 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
             Bv.final_loss[f] = (T)(restore ? loss0 : r);
             Bv.n_evals[f] += S.n_evals;
             Bv.n_passes[f] += S.n_passes;
-            Bv.flags[f] |= flags;
+            Bv.flags[f] |= flags | (S.coll_overflow ? SFX_FLAG_COLL_OVERFLOW : 0);
 #ifdef SFX_CYCLE_PROF
             S.prof[4] += clock64() - _t_total;
             for (int i = 0; i < 8; ++i) Bv.prof[(size_t)f * 8 + i] = S.prof[i];
@@ -400,7 +424,8 @@ struct sfx_model {
     ModelView<double> vd;
     DevBuf PK, vt, J0, JS, Wd, hand_l, hand_r, pose_mean, sv_vid, lmk_bary, dyn_vid, dyn_bary,
         joint_map, inv_ptr, inv_idx, faces, gmm_means, gmm_prec, gmm_logw, vp_w1, vp_b1, vp_w2,
-        vp_b2, vp_w3, vp_b3;
+        vp_b2, vp_w3, vp_b3, part_ptr, part_faces, face_part, part_allow, vf_ptr, vf_idx;
+    std::vector<int> faces_host;
     int device = 0;
     int num_sms = 0;
     MeshPlan mesh;        // TMA descriptor of the blend matrix for the tensor-core mesh kernel
@@ -429,6 +454,7 @@ static int upload_model(const sfx_model_desc& d, sfx_model* m, ModelView<T>& vie
     CUDA_TRY(m->inv_ptr.upload(h.inv_ptr));
     CUDA_TRY(m->inv_idx.upload(h.inv_idx));
     CUDA_TRY(m->faces.upload(h.faces));
+    m->faces_host = h.faces;
     view.PK = (const T*)m->PK.p; view.vt = (const T*)m->vt.p; view.J0 = (const T*)m->J0.p;
     view.JS = (const T*)m->JS.p; view.Wd = (const T*)m->Wd.p;
     view.hand_l = (const T*)m->hand_l.p; view.hand_r = (const T*)m->hand_r.p;
@@ -446,7 +472,7 @@ struct sfx_batch {
     size_t es = 4;        // element size of the batch dtype
     DevBuf params, gt, conf, jw, lowconf, init_mask, cam, reg_pose, hist_s, hist_y, final_loss,
         n_evals, n_passes, flags, Acoef, Ccoef, vposed, go_saved, params_alt, loss_alt, pipe, counter,
-        cam_loss, params_last, prof;
+        cam_loss, params_last, prof, coll_vals, coll_idx;
     bool last_valid = false;
     bool has_reg = false;
     std::vector<unsigned char> stage_host;     // host staging for set_targets
@@ -459,6 +485,9 @@ struct sfx_batch {
         v.init_mask = (const unsigned char*)init_mask.p; v.cam = (const T*)cam.p;
         v.reg_pose = has_reg ? (const T*)reg_pose.p : nullptr;
         v.hist_s = (T*)hist_s.p; v.hist_y = (T*)hist_y.p; v.final_loss = (T*)final_loss.p;
+        v.coll_vals = (T*)coll_vals.p; v.coll_idx = (unsigned short*)coll_idx.p;
+        v.coll_vals_stride = coll_vals_per_block(m->V, m->F);
+        v.coll_idx_stride = coll_idx_per_block(m->V, m->F);
         v.prof = (long long*)prof.p; v.n_evals = (int*)n_evals.p; v.n_passes = (int*)n_passes.p; v.flags = (int*)flags.p; v.frame_ids = frame_ids;
         return v;
     }
@@ -557,6 +586,42 @@ int sfx_model_set_gmm(sfx_model* m, int32_t num_gaussians, int32_t dim, const vo
         m->vf.gmm_means = (const float*)m->gmm_means.p; m->vf.gmm_prec = (const float*)m->gmm_prec.p;
         m->vf.gmm_logw = (const float*)m->gmm_logw.p;
     }
+    return SFX_OK;
+}
+
+int sfx_model_set_collision(sfx_model* m, const int32_t* faces_segm, const int32_t* faces_parents,
+                            const int32_t* ign_part_pairs, int32_t n_ign_pairs) {
+    if (!m || !faces_segm || !faces_parents || (n_ign_pairs > 0 && !ign_part_pairs) || n_ign_pairs < 0)
+        return fail(SFX_ERR_ARG, "bad argument");
+    HostCollision c;
+    std::string e = prepare_collision(m->V, m->F, m->faces_host.data(), faces_segm, faces_parents,
+                                      ign_part_pairs, n_ign_pairs, c);
+    if (!e.empty()) return fail(SFX_ERR_ARG, e);
+    CUDA_TRY(m->part_ptr.upload(c.part_ptr));
+    CUDA_TRY(m->part_faces.upload(c.part_faces));
+    CUDA_TRY(m->face_part.upload(c.face_part));
+    CUDA_TRY(m->part_allow.upload(c.part_allow));
+    CUDA_TRY(m->vf_ptr.upload(c.vf_ptr));
+    CUDA_TRY(m->vf_idx.upload(c.vf_idx));
+    auto fill = [&](auto& v) {
+        v.coll_ready = 1; v.F = m->F; v.n_parts = c.n_parts; v.faces = (const int*)m->faces.p;
+        v.part_ptr = (const int*)m->part_ptr.p; v.part_faces = (const int*)m->part_faces.p;
+        v.face_part = (const unsigned char*)m->face_part.p;
+        v.part_allow = (const unsigned long long*)m->part_allow.p;
+        v.vf_ptr = (const int*)m->vf_ptr.p; v.vf_idx = (const int*)m->vf_idx.p;
+    };
+    if (m->use_double) fill(m->vd); else fill(m->vf);
+    return SFX_OK;
+}
+
+int sfx_batch_enable_collisions(sfx_batch* b) {
+    if (!b) return fail(SFX_ERR_ARG, "null argument");
+    const int ready = b->m->use_double ? b->m->vd.coll_ready : b->m->vf.coll_ready;
+    if (!ready) return fail(SFX_ERR_ARG, "interpenetration: call sfx_model_set_collision first");
+    if (b->coll_vals.p) return SFX_OK;
+    // one slot per block; no launch uses more blocks than frames
+    CUDA_TRY(b->coll_vals.alloc((size_t)b->B * coll_vals_per_block(b->m->V, b->m->F) * b->es));
+    CUDA_TRY(b->coll_idx.alloc((size_t)b->B * coll_idx_per_block(b->m->V, b->m->F) * sizeof(unsigned short)));
     return SFX_OK;
 }
 
@@ -725,6 +790,12 @@ static int check_stage(const sfx_batch* b, const SfxStage* st) {
     }
     if (st->opt_kind != SFX_OPT_LBFGSLS && st->opt_kind != SFX_OPT_ADAM)
         return fail(SFX_ERR_UNSUPPORTED, "optimiser kind not supported on the device");
+    if (st->loss_kind == SFX_LOSS_SMPLIFY && st->coll_loss_weight > 0) {
+        if (!b->coll_vals.p)
+            return fail(SFX_ERR_ARG, "stage: coll_loss_weight > 0 needs sfx_model_set_collision and "
+                                     "sfx_batch_enable_collisions");
+        if (!(st->coll_sigma > 0)) return fail(SFX_ERR_ARG, "stage: coll_sigma (df_cone_height) must be positive");
+    }
     return SFX_OK;
 }
 

@@ -24,6 +24,9 @@ struct HostModel {
         m.use_contour = use_contour; m.n_neck = n_neck; m.nlev = nlev;
         m.vp_ready = 0; m.vp_w1 = m.vp_b1 = m.vp_w2 = m.vp_b2 = m.vp_w3 = m.vp_b3 = nullptr;
         m.gmm_M = 0; m.gmm_D = 0; m.gmm_means = nullptr; m.gmm_prec = nullptr; m.gmm_logw = nullptr;
+        m.coll_ready = 0; m.F = F; m.n_parts = 0; m.faces = nullptr; m.part_ptr = nullptr;
+        m.part_faces = nullptr; m.face_part = nullptr; m.part_allow = nullptr; m.vf_ptr = nullptr;
+        m.vf_idx = nullptr;
         for (int i = 0; i < SFX_NJ; ++i) { m.parents[i] = parents[i]; m.order[i] = order[i]; }
         for (int i = 0; i < 16; ++i) m.level_off[i] = level_off[i];
         for (int i = 0; i <= SFX_NJ; ++i) m.child_off[i] = child_off[i];
@@ -189,6 +192,66 @@ std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
     h.inv_idx.resize(h.K);
     std::vector<int> fillp(h.inv_ptr.begin(), h.inv_ptr.end() - 1);
     for (int k = 0; k < h.K; ++k) h.inv_idx[fillp[h.joint_map[k]]++] = k;
+    return "";
+}
+
+// Tables of the interpenetration term (sfx_collide.cuh) from the face segmentation the reference
+// reads at fit_single_frame.py:317-328 (smplx_parts_segm.pkl: 'segm' = body part of every face,
+// 'parents' = kinematic parent of that part) and its ign_part_pairs option.
+struct HostCollision {
+    int n_parts = 0;
+    std::vector<int> part_ptr, part_faces, vf_ptr, vf_idx;
+    std::vector<unsigned char> face_part;
+    std::vector<unsigned long long> part_allow;
+};
+
+inline std::string prepare_collision(int V, int F, const int* faces, const int32_t* segm,
+                                     const int32_t* parents, const int32_t* ign_pairs, int n_ign,
+                                     HostCollision& c) {
+    if (!faces || !segm || !parents || F < 1) return "collision tables: missing array";
+    if (F > 65535) return "collision tables: more than 65535 faces";
+    int np = 0;
+    for (int f = 0; f < F; ++f) {
+        if (segm[f] < 0 || segm[f] >= SFX_NPART_MAX) return "faces_segm entry out of range (0..63)";
+        if (parents[f] >= SFX_NPART_MAX) return "faces_parents entry out of range";
+        np = std::max(np, segm[f] + 1);
+    }
+    c.n_parts = np;
+    std::vector<int> parent_of(np, -1);
+    for (int f = 0; f < F; ++f) parent_of[segm[f]] = parents[f];
+    // FilterFaces: same part, parent / child parts and ignored pairs never collide
+    c.part_allow.assign(SFX_NPART_MAX, 0ull);
+    for (int p = 0; p < np; ++p)
+        for (int q = 0; q < np; ++q)
+            if (p != q && parent_of[p] != q && parent_of[q] != p) c.part_allow[p] |= 1ull << q;
+    for (int i = 0; i < n_ign; ++i) {
+        const int a = ign_pairs[2 * i], b = ign_pairs[2 * i + 1];
+        if (a < 0 || b < 0) return "ign_part_pairs entry out of range";
+        if (a >= np || b >= np) continue;
+        c.part_allow[a] &= ~(1ull << b);
+        c.part_allow[b] &= ~(1ull << a);
+    }
+    c.face_part.resize(F);
+    c.part_ptr.assign(np + 1, 0);
+    for (int f = 0; f < F; ++f) {
+        c.face_part[f] = (unsigned char)segm[f];
+        c.part_ptr[segm[f] + 1]++;
+    }
+    for (int p = 0; p < np; ++p) c.part_ptr[p + 1] += c.part_ptr[p];
+    c.part_faces.resize(F);
+    {
+        std::vector<int> pos(c.part_ptr.begin(), c.part_ptr.end() - 1);
+        for (int f = 0; f < F; ++f) c.part_faces[pos[segm[f]]++] = f;
+    }
+    c.vf_ptr.assign(V + 1, 0);
+    for (long i = 0; i < 3L * F; ++i) c.vf_ptr[faces[i] + 1]++;
+    for (int v = 0; v < V; ++v) c.vf_ptr[v + 1] += c.vf_ptr[v];
+    c.vf_idx.resize((size_t)3 * F);
+    {
+        std::vector<int> pos(c.vf_ptr.begin(), c.vf_ptr.end() - 1);
+        for (int f = 0; f < F; ++f)
+            for (int k = 0; k < 3; ++k) c.vf_idx[pos[faces[3 * f + k]]++] = f * 4 + k;
+    }
     return "";
 }
 

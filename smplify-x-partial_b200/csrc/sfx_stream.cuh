@@ -100,10 +100,18 @@ __device__ __forceinline__ void load_row_regs(const T* row, int lane, T* dst) {
     }
 }
 
-// Generic driver: FN(row_index_r, const T* row_values_in_regs[16]) is called by every lane of the
-// warp that owns support row r, rows taken in the fixed order r = warp, warp + NWARP, ...
-template <typename T, typename RP, typename FN>
-__device__ __forceinline__ void stream_rows(int nrows, RP rowptr, StreamWS& ws, FN fn) {
+// Generic driver: FN(row_index_r, const T* row_values_in_regs[16], aux) is called by every lane
+// of the warp that owns support row r, rows taken in the fixed order r = warp, warp + NWARP, ...
+// AUX(r) is a per-row scalar (e.g. the adjoint weight of the row) that may live in global
+// memory: lane l fetches the value of the warp's row i0 + l once per 32 rows and the warp reads
+// it back by shuffle, so its latency is paid once per 32 rows instead of on every row.
+struct NoAux {
+    __device__ __forceinline__ float operator()(int) const { return 0.f; }
+};
+
+template <typename T, typename RP, typename FN, typename AUX>
+__device__ __forceinline__ void stream_rows_aux(int nrows, RP rowptr, StreamWS& ws, FN fn, AUX auxf,
+                                                bool use_aux) {
     // warp 0 runs the kinematic chain while warps 1 .. NWARP-1 stream the rows
     const int warp = (threadIdx.x >> 5) - 1, lane = threadIdx.x & 31;
     constexpr int NSTREAM = SFX_NWARP - 1;
@@ -111,6 +119,12 @@ __device__ __forceinline__ void stream_rows(int nrows, RP rowptr, StreamWS& ws, 
     constexpr uint32_t ROWB = SFX_KPAD * sizeof(T);
     T vals[RowVec<T>::NE];
     if (count == 0) return;
+    T auxv = 0;
+    auto aux_at = [&](int i) -> T {
+        if (!use_aux) return (T)0;
+        if ((i & 31) == 0) auxv = i + lane < count ? (T)auxf(warp + (i + lane) * NSTREAM) : (T)0;
+        return __shfl_sync(0xffffffffu, auxv, i & 31);
+    };
     if (ws.ring_mode) {
         unsigned char* mybuf = ws.ring + (size_t)warp * SFX_NBUF * ROWB;
         uint64_t* mybar = ws.bars + warp * SFX_NBUF;
@@ -127,6 +141,7 @@ __device__ __forceinline__ void stream_rows(int nrows, RP rowptr, StreamWS& ws, 
             for (int i = 0; i < SFX_NBUF && i < count; ++i) issue(i);
         }
         for (int i = 0; i < count; ++i) {
+            const T aux = aux_at(i);
             unsigned int n = n0 + i;
             int b = n % SFX_NBUF;
             mbar_wait(mybar + b, (n / SFX_NBUF) & 1);
@@ -136,17 +151,23 @@ __device__ __forceinline__ void stream_rows(int nrows, RP rowptr, StreamWS& ws, 
                 fence_proxy_async();
                 issue(i + SFX_NBUF);
             }
-            fn(warp + i * NSTREAM, vals);
+            fn(warp + i * NSTREAM, vals, aux);
         }
         __syncwarp();
         if (lane == 0) ws.fills[warp] = n0 + count;
     } else {
         for (int i = 0; i < count; ++i) {
+            const T aux = aux_at(i);
             int r = warp + i * NSTREAM;
             load_row_regs<T>(rowptr(r), lane, vals);
-            fn(r, vals);
+            fn(r, vals, aux);
         }
     }
+}
+
+template <typename T, typename RP, typename FN>
+__device__ __forceinline__ void stream_rows(int nrows, RP rowptr, StreamWS& ws, FN fn) {
+    stream_rows_aux<T>(nrows, rowptr, ws, [&](int r, const T* v, T) { fn(r, v); }, NoAux(), false);
 }
 
 template <typename T>
@@ -203,6 +224,72 @@ __device__ __forceinline__ void blend_adjoint(const ModelView<T>& M, Scratch<T>&
     }
     __syncthreads();
     if (ws.ring_mode) fence_proxy_async();   // generic writes to the ring precede later bulk copies
+}
+
+
+// every row of the blend matrix (interpenetration term): vp_g[r] = vt[r] + PK[r] . c
+template <typename T>
+__device__ __forceinline__ void blend_forward_full(const ModelView<T>& M, Scratch<T>& S, void* wsp,
+                                                   T* vp_g) {
+    StreamWS& ws = *reinterpret_cast<StreamWS*>(wsp);
+    const int lane = threadIdx.x & 31;
+    T c[RowVec<T>::NE];
+#pragma unroll
+    for (int i = 0; i < RowVec<T>::NV; ++i)
+#pragma unroll
+        for (int e = 0; e < RowVec<T>::VEC; ++e) c[i * RowVec<T>::VEC + e] = S.c[SFX_ELEM(i, lane, e)];
+    const T* PK = M.PK;
+    const T* vt = M.vt;
+    auto rowptr = [=](int r) { return PK + (long)r * SFX_KPAD; };
+    stream_rows_aux<T>(3 * M.V, rowptr, ws, [&](int r, const T* v, T base) {
+        T acc = 0;
+#pragma unroll
+        for (int i = 0; i < RowVec<T>::NE; ++i) acc += v[i] * c[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) vp_g[r] = base + acc;
+    }, [=](int r) { return vt[r]; }, true);
+}
+
+// support rows followed by the three rows of every touched vertex tv[t]; the adjoint weights of
+// those rows are dvpc[3 t + k] (compact order)
+template <typename T>
+__device__ __forceinline__ void blend_adjoint_ext(const ModelView<T>& M, Scratch<T>& S, void* wsp,
+                                                  const unsigned short* tv, const T* dvpc) {
+    StreamWS& ws = *reinterpret_cast<StreamWS*>(wsp);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T acc[RowVec<T>::NE];
+#pragma unroll
+    for (int i = 0; i < RowVec<T>::NE; ++i) acc[i] = 0;
+    const T* PK = M.PK;
+    const int* vid = S.vid;
+    const T* dvp = S.dvp;
+    constexpr int NS3 = SFX_NSLOT * 3;
+    auto rowptr = [=](int r) {
+        const long row = r < NS3 ? (long)vid[r / 3] * 3 + (r % 3)
+                                 : (long)tv[(r - NS3) / 3] * 3 + ((r - NS3) % 3);
+        return PK + row * SFX_KPAD;
+    };
+    stream_rows_aux<T>(NS3 + 3 * S.n_touch, rowptr, ws, [&](int r, const T* v, T w) {
+#pragma unroll
+        for (int i = 0; i < RowVec<T>::NE; ++i) acc[i] += v[i] * w;
+    }, [=](int r) { return r < NS3 ? dvp[r] : dvpc[r - NS3]; }, true);
+    __syncthreads();
+    T* part = reinterpret_cast<T*>(ws.ring);
+#pragma unroll
+    for (int i = 0; i < RowVec<T>::NV; ++i)
+#pragma unroll
+        for (int e = 0; e < RowVec<T>::VEC; ++e)
+            part[warp * SFX_KPAD + SFX_ELEM(i, lane, e)] = acc[i * RowVec<T>::VEC + e];
+    __syncthreads();
+    for (int k = threadIdx.x; k < SFX_KPAD; k += blockDim.x) {
+        T s = 0;
+#pragma unroll
+        for (int w = 0; w < SFX_NWARP; ++w) s += part[w * SFX_KPAD + k];
+        S.dc[k] = s;
+    }
+    __syncthreads();
+    if (ws.ring_mode) fence_proxy_async();
 }
 
 

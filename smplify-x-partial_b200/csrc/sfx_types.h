@@ -22,6 +22,7 @@
 #define SFX_NW 8             // non-zero skinning weights kept per support vertex (dense fall-back beyond)
 #define SFX_MAX_BLOCKS 12    // parameter blocks of the optimised vector (for the gtol test)
 #define SFX_NLATENT 32       // VPoser latent size
+#define SFX_NPART_MAX 64     // body parts of the face segmentation (smplx_parts_segm.pkl: 55)
 
 // loss kinds (reference fitting.py:278-284)
 #define SFX_LOSS_SMPLIFY 0
@@ -75,6 +76,9 @@ struct SfxStage {
     int block_off[SFX_MAX_BLOCKS];             // into the full parameter vector
     int need_blend_grad;                       // 0 when only global_orient / camera are optimised
     int generic_two_loop;                      // debug: block-wide two-loop recursion (A/B test)
+    // --- interpenetration term (fitting.py:437-455; third-party mesh_intersection) ---
+    double coll_loss_weight;                   // enters unsquared (fitting.py:453-455); 0 = term off
+    double coll_sigma;                         // df_cone_height (fit_single_frame.py:310)
 };
 
 // The whole per-frame flow of fit_single_frame.py:447-668 as one launch: camera stage, then the
@@ -101,3 +105,4 @@ struct SfxPipeline {
 // per-frame status flags written by the fit kernel
 #define SFX_FLAG_NAN 1
 #define SFX_FLAG_INF 2
+#define SFX_FLAG_COLL_OVERFLOW 4     // candidate or touched-vertex list of the interpenetration term was truncated

@@ -80,6 +80,29 @@ class Model(object):
             N.check(self.lib, self.lib.sfx_model_set_gmm(self.h, M, D, p(means), p(prec), p(logw)))
         self._gmm_id = id(prior)
 
+    def set_collision(self, faces_segm, faces_parents, ign_part_pairs=None):
+        """Installs the face segmentation of the interpenetration term: ``segm`` / ``parents``
+        of ``part_segm_fn`` (reference fit_single_frame.py:317-328) and ``ign_part_pairs``
+        (strings "a,b" as in the yaml files, or pairs of ints)."""
+        key = (id(faces_segm), id(faces_parents), tuple(map(str, ign_part_pairs or ())))
+        if getattr(self, '_coll_key', None) == key:
+            return
+        segm = np.ascontiguousarray(np.asarray(faces_segm), dtype=np.int32).reshape(-1)
+        par = np.ascontiguousarray(np.asarray(faces_parents), dtype=np.int32).reshape(-1)
+        if segm.shape[0] != self.faces.shape[0] or par.shape[0] != segm.shape[0]:
+            raise ValueError('part segmentation has {} faces, the model {}'.format(
+                segm.shape[0], self.faces.shape[0]))
+        ign = [[int(x) for x in (p.split(',') if isinstance(p, str) else p)]
+               for p in (ign_part_pairs or [])]
+        ign = np.ascontiguousarray(np.asarray(ign, dtype=np.int32).reshape(-1, 2))
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            N.check(self.lib, self.lib.sfx_model_set_collision(
+                self.h, C.c_void_p(segm.ctypes.data), C.c_void_p(par.ctypes.data),
+                C.c_void_p(ign.ctypes.data) if ign.shape[0] else None, int(ign.shape[0])))
+        self._coll_key = key
+        self.has_collision = True
+
     def close(self):
         if getattr(self, 'h', None):
             self.lib.sfx_model_destroy(self.h)
@@ -108,6 +131,12 @@ class FrameBatch(object):
         self.L = N.SfxLayout()
         N.check(self.lib, self.lib.sfx_batch_layout(self.h, C.byref(self.L)))
         self.blocks = N.param_blocks(self.L)
+
+    def enable_collisions(self):
+        """Allocates the full-mesh workspace of the interpenetration term (needs
+        ``Model.set_collision``)."""
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_batch_enable_collisions(self.h))
 
     def close(self):
         if getattr(self, 'h', None):

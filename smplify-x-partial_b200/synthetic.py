@@ -441,6 +441,39 @@ def cached_smplx_like(seed=0):
     return _CACHE[seed]
 
 
+def parts_segm_like(model_data):
+    """Face segmentation with the keys of ``smplx_parts_segm.pkl`` (reference
+    fit_single_frame.py:317-328) for a model of this module: the real file describes the
+    licensed mesh topology, not the tube-man's.  ``segm[f]`` = bone owning the face (majority of
+    its corners' dominant skinning joint), ``parents[f]`` = kinematic parent of that bone."""
+    W = np.asarray(model_data['weights'])
+    faces = np.asarray(model_data['f']).astype(np.int64)
+    parents = np.asarray(model_data['kintree_table'])[0].astype(np.int64).copy()
+    parents[0] = -1
+    dom = W.argmax(1)[faces]
+    segm = np.where(dom[:, 1] == dom[:, 2], dom[:, 1], dom[:, 0]).astype(np.int64)
+    par = parents[segm]
+    # the tube caps contain a few faces with a repeated corner (zero area, no circumcircle):
+    # they get a part of their own that sibling_part_pairs() excludes from every pairing
+    degen = ((faces[:, 0] == faces[:, 1]) | (faces[:, 1] == faces[:, 2]) |
+             (faces[:, 0] == faces[:, 2]))
+    segm[degen] = NUM_JOINTS
+    par[degen] = -1
+    return {'segm': segm, 'parents': par}
+
+
+def sibling_part_pairs(model_data):
+    """``ign_part_pairs`` entries for every pair of bones with the same parent: the tubes of
+    sibling bones overlap at the shared joint by construction (the licensed mesh is one
+    watertight surface and has no such overlaps)."""
+    parents = np.asarray(model_data['kintree_table'])[0].astype(np.int64).copy()
+    parents[0] = -1
+    n = parents.shape[0]
+    pairs = ['{},{}'.format(a, b) for a in range(n) for b in range(a + 1, n)
+             if parents[a] == parents[b]]
+    return pairs + ['{},{}'.format(a, n) for a in range(n)]       # zero-area faces: never paired
+
+
 def make_vposer_like(seed=2, latent=32, hidden=512, dtype=np.float32):
     """Weights with the VPoser v1 layer shapes, seeded.
 

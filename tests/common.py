@@ -128,3 +128,41 @@ def gmm_arrays(dtype):
     pr = gmm_prior(dtype)
     return (pr.means.numpy(), pr.precisions.numpy(),
             torch.log(pr.nll_weights).reshape(-1).numpy())
+
+
+COLL_IGN = ["9,16", "9,17", "6,16", "6,17", "1,2", "12,22"]      # the shipped yaml files
+
+
+def coll_segmentation():
+    """(segm, parents, ign_part_pairs) of the synthetic model -- as tests/golden/make_golden.py
+    builds them for the reference-side FilterFaces."""
+    md = model_data()
+    seg = synthetic.parts_segm_like(md)
+    return seg['segm'], seg['parents'], COLL_IGN + synthetic.sibling_part_pairs(md)
+
+
+def coll_case_inputs(ev, case):
+    """Engine-side inputs for tests/golden/ref_eval_coll_*.npz (case 'coll' or 'nocoll')."""
+    L = layout()
+    named = {k[6:]: ev[k] for k in ev if k.startswith('param/')}
+    x = pack_params(L, named, cam_t=ev['cam_t'])
+    kp = ev['keypoints']
+    H = int(ev['HW'][0])
+    w = json.loads(str(ev['weights_json']))
+    K = kp.shape[0]
+    lowconf = np.zeros(K, np.uint8)
+    lowconf[:25] = kp[:25, 2] < 0.2
+    cam = cam_row(float(ev['focal']), ev['center'], 1000.0 / H, tz_est=3.5)
+    jw_base = np.ones(K)
+    jw_base[[1, 9, 12]] = 0
+    jw_base[lowconf.astype(bool)] = 0
+    st = N.make_stage(
+        L, N.BODY_STAGE_BLOCKS, loss_kind=N.LOSS_SMPLIFY, pprior_kind=N.PPRIOR_L2, stage_index=1,
+        num_stages=3, body_pose_weight=w['body_pose_weight'], shape_weight=w['shape_weight'],
+        bending_prior_weight=w['bending_prior_weight'], hand_prior_weight=w['hand_prior_weight'],
+        expr_prior_weight=w['expr_prior_weight'], jaw_prior_weight=w['jaw_prior_weight'],
+        hand_joint_weight=0.1, face_joint_weight=2.0,
+        coll_loss_weight=w['coll_loss_weight'] if case == 'coll' else 0.0,
+        coll_sigma=float(ev['sigma']))
+    return dict(L=L, x=x, gt=kp[:, :2].copy(), conf=kp[:, 2].copy(), jw=jw_base, lowconf=lowconf,
+                init_mask=np.zeros(K, np.uint8), cam=cam, reg_pose=None, stage=st)

@@ -322,6 +322,101 @@ def ref_eval(inputs, dtype=torch.float64, tag='f64'):
     return out
 
 
+COLL_IGN = ["9,16", "9,17", "6,16", "6,17", "1,2", "12,22"]      # the shipped yaml files
+
+
+def coll_modules(md, max_collisions=128, sigma=1e-4):
+    """The three objects fit_single_frame.py:305-328 builds, from the restated package."""
+    from oracle import isect_port as IP
+    seg = synthetic.parts_segm_like(md)
+    ign = COLL_IGN + synthetic.sibling_part_pairs(md)
+    return (IP.BVH(max_collisions=max_collisions),
+            IP.DistanceFieldPenetrationLoss(sigma=sigma, point2plane=False, vectorized=True,
+                                            penalize_outside=True),
+            IP.FilterFaces(faces_segm=seg['segm'], faces_parents=seg['parents'],
+                           ign_part_pairs=ign))
+
+
+def ref_eval_coll(inputs, dtype=torch.float64, tag='f64'):
+    """One closure evaluation of the reference's SMPLifyLoss WITH the interpenetration term
+    (fitting.py:437-455) driving the restated mesh_intersection package (oracle/isect_port.py),
+    at a pose whose arms cut into the torso."""
+    ref = ref_bridge.load()
+    cfg = cfg_combined()
+    frame = '18_cropped'
+    body_model, pri, jw, _ = build_reference_objects(cfg, dtype)
+    md = synthetic.cached_smplx_like(0)
+    rng = np.random.default_rng(11)
+    P = _rand_params(rng, scale=0.5)
+    pe = P['pose_embedding']
+    pe[0, 15 * 3 + 2] += -1.3          # shoulders down, elbows bent across the chest
+    pe[0, 16 * 3 + 2] += 1.3
+    pe[0, 17 * 3 + 1] += -1.6
+    pe[0, 18 * 3 + 1] += 1.6
+    H, W = [int(v) for v in inputs[frame + '/HW']]
+    focal = (W ** 2 + H ** 2) ** 0.5
+    camera = ref.camera.create_camera(focal_length_x=focal, focal_length_y=focal, dtype=dtype)
+    with torch.no_grad():
+        camera.translation[:] = torch.tensor([[0.05, 0.25, 3.2]], dtype=dtype)
+        camera.center[:] = torch.tensor([[W * 0.5 + 3, H * 0.5 - 5]], dtype=dtype)
+    camera.rotation.requires_grad = False
+    camera.translation.requires_grad = True
+    kp = torch.tensor(inputs[frame + '/keypoints'][None], dtype=dtype)
+    gt, conf = kp[:, :, :2], kp[:, :, 2]
+    body_model.reset_params(**{k: v for k, v in P.items() if k != 'pose_embedding'})
+    emb = torch.tensor(pe, dtype=dtype, requires_grad=True)
+    jw = jw.clone()
+    jw[:, 25:67] = 0.1
+    jw[:, 67:] = 2.0
+    low = [i for i in range(25) if float(conf[0, i]) < 0.2]
+    jw[:, low] = 0
+    out = {'jw': jw.numpy(), 'keypoints': kp.numpy()[0],
+           'cam_t': camera.translation.detach().numpy().copy(),
+           'center': camera.center.numpy().copy(), 'focal': np.array(focal),
+           'HW': np.array([H, W]), 'reg_pose': np.zeros((1, 63))}
+    for k, v in P.items():
+        out['param/' + k] = np.asarray(v)
+    weights = dict(data_weight=1000.0 / H, body_pose_weight=300.0, shape_weight=50.0,
+                   bending_prior_weight=3.17 * 300.0, hand_prior_weight=4.78,
+                   expr_prior_weight=5.0, jaw_prior_weight=[100.0, 1000.0, 1000.0],
+                   coll_loss_weight=0.1)
+    out['weights_json'] = np.array(json.dumps(weights))
+    out['sigma'] = np.array(1e-4)
+    search_tree, pen_distance, filter_faces = coll_modules(md, sigma=1e-4)
+    faces = body_model.faces_tensor.view(-1)
+    for case, w_coll in (('coll', 0.1), ('nocoll', 0.0)):
+        loss = ref.fitting.create_loss(
+            loss_type='smplify', rho=100, use_joints_conf=True, use_face=True, use_hands=True,
+            vposer=None, interpenetration=True, search_tree=search_tree,
+            pen_distance=pen_distance, tri_filtering_module=filter_faces, dtype=dtype,
+            regression_pose=None, num_stages=3, **pri)
+        ww = dict(weights)
+        ww['coll_loss_weight'] = w_coll
+        loss.reset_loss_weights(ww)
+        for p in list(body_model.parameters()) + [emb, camera.translation]:
+            p.grad = None
+        o = body_model(return_verts=True, body_pose=emb, return_full_pose=True)
+        val = loss(o, camera=camera, gt_joints=gt, body_model_faces=faces, joints_conf=conf,
+                   joint_weights=jw, pose_embedding=emb, use_vposer=False, stage=1)
+        val.backward()
+        out[case + '/loss'] = val.detach().numpy()
+        for name, p in body_model.named_parameters():
+            if name != 'body_pose':
+                out[case + '/grad/' + name] = p.grad.numpy().copy()
+        out[case + '/grad/pose_embedding'] = emb.grad.numpy().copy()
+        out[case + '/grad/camera_translation'] = camera.translation.grad.numpy().copy()
+        if case == 'coll':
+            tri = o.vertices[:, faces].view(1, -1, 3, 3)
+            ci = filter_faces(search_tree(tri))
+            pairs = ci[0][ci[0, :, 0] >= 0].numpy()
+            out['coll/pairs'] = pairs.astype(np.int32)
+            out['coll/vertices'] = o.vertices.detach().numpy()[0]
+    np.savez_compressed(os.path.join(HERE, 'ref_eval_coll_{}.npz'.format(tag)), **out)
+    print('ref_eval_coll', tag, float(out['coll/loss']), float(out['nocoll/loss']),
+          'pairs', len(out['coll/pairs']))
+    return out
+
+
 def ref_stage(inputs, dtype=torch.float64, tag='f64', perturb=None, save=True):
     """Reference run_fitting + reference LBFGS on one body stage from the ref_eval start.
     ``perturb=(eps, seed)`` multiplies the start by 1 + eps * N(0,1) (envelope runs)."""
@@ -445,8 +540,14 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'envelope':
         ref_envelope(inp)
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'coll':
+        ref_eval_coll(inp, torch.float64, 'f64')
+        ref_eval_coll(inp, torch.float32, 'f32')
+        raise SystemExit(0)
     ref_eval(inp, torch.float64, 'f64')
     ref_eval(inp, torch.float32, 'f32')
     ref_stage(inp, torch.float64, 'f64')
+    ref_eval_coll(inp, torch.float64, 'f64')
+    ref_eval_coll(inp, torch.float32, 'f32')
     ref_fit('02_cropped', inp)
     ref_fit('18_cropped', inp, cfg=cfg_smplifyx(), tag='ref_fit_18_vposer')

@@ -17,7 +17,7 @@ _CORE = os.path.join(_HERE, '..', '..', 'smplify-x-partial_b200', 'csrc')
 
 def build(force=False):
     deps = [_SRC] + [os.path.join(_CORE, f) for f in
-                     ('sfx_core.cuh', 'sfx_types.h', 'sfx_model_prep.h')]
+                     ('sfx_core.cuh', 'sfx_collide.cuh', 'sfx_types.h', 'sfx_model_prep.h')]
     if (not force and os.path.isfile(_SO) and
             all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps)):
         return _SO
@@ -57,6 +57,25 @@ class HostSim(object):
         self.lib.hs_set_gmm.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3
         self.lib.hs_set_gmm(self.h, a[0].shape[0], a[0].shape[1],
                             *[x.ctypes.data_as(C.c_void_p) for x in a])
+
+    def set_collision(self, faces_segm, faces_parents, ign_part_pairs=(), work_bytes=None):
+        segm = np.ascontiguousarray(faces_segm, dtype=np.int32)
+        par = np.ascontiguousarray(faces_parents, dtype=np.int32)
+        ign = np.ascontiguousarray(np.asarray(ign_part_pairs, dtype=np.int32).reshape(-1, 2))
+        if work_bytes is None:          # what the device has: the idle blend ring
+            work_bytes = 131072 if self.dt == np.float32 else 65536
+        err = C.create_string_buffer(256)
+        self.lib.hs_set_collision.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_char_p, C.c_int]
+        rc = self.lib.hs_set_collision(self.h, segm.ctypes.data_as(C.c_void_p),
+                                       par.ctypes.data_as(C.c_void_p),
+                                       ign.ctypes.data_as(C.c_void_p), ign.shape[0],
+                                       int(work_bytes), err, 256)
+        if rc:
+            raise RuntimeError(err.value.decode())
+
+    def last_touched(self):
+        self.lib.hs_last_touch.argtypes = [C.c_void_p]
+        return self.lib.hs_last_touch(self.h)
 
     def __del__(self):
         try:

@@ -21,6 +21,10 @@ struct SimModel {
     int gmm_M = 0, gmm_D = 0;
     std::vector<T> gmm_means, gmm_prec, gmm_logw;
     std::vector<T> vw1, vb1, vw2, vb2, vw3, vb3;
+    HostCollision coll;
+    bool has_coll = false;
+    int coll_work_bytes = 131072;
+    int last_touch = 0, last_overflow = 0;
 };
 struct SimHandle {
     int use_double;
@@ -48,9 +52,28 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
     support_begin_frame(M, S);
     stage_setup(*st, jw, lowconf, conf, init_mask, M.K, S);
     std::vector<T> hs((size_t)SFX_HIST * SFX_NP_MAX), hy((size_t)SFX_HIST * SFX_NP_MAX);
-    EvalCtx<T> E{&M, &L, st, gt, conf, init_mask, cam, reg_pose, nullptr};
+    CollWS<T> W;
+    std::vector<T> vp_g, vert_g, dvert_g, dtri_g, big_box;
+    std::vector<unsigned short> big_face, tv_g;
+    std::vector<unsigned char> work;
+    const CollWS<T>* Wp = nullptr;
+    if (sm.has_coll) {
+        M.coll_ready = 1; M.n_parts = sm.coll.n_parts; M.faces = sm.h.faces.data();
+        M.part_ptr = sm.coll.part_ptr.data(); M.part_faces = sm.coll.part_faces.data();
+        M.face_part = sm.coll.face_part.data(); M.part_allow = sm.coll.part_allow.data();
+        M.vf_ptr = sm.coll.vf_ptr.data(); M.vf_idx = sm.coll.vf_idx.data();
+        vp_g.assign((size_t)3 * M.V, 0); vert_g.assign((size_t)3 * M.V, 0);
+        dvert_g.assign((size_t)3 * M.V, 0); dtri_g.assign((size_t)9 * M.F, 0);
+        work.assign(sm.coll_work_bytes, 0);
+        big_box.assign((size_t)6 * M.F, 0); big_face.assign(M.F, 0); tv_g.assign(M.V, 0);
+        W.big_box = big_box.data(); W.big_face = big_face.data(); W.tv_g = tv_g.data();
+        W.vp_g = vp_g.data(); W.vert_g = vert_g.data(); W.dvert_g = dvert_g.data();
+        W.dtri_g = dtri_g.data(); W.work = work.data(); W.work_bytes = sm.coll_work_bytes;
+        Wp = &W;
+    }
+    EvalCtx<T> E{&M, &L, st, gt, conf, init_mask, cam, reg_pose, nullptr, Wp};
     if (!do_fit) {
-        eval_frame(M, L, *st, gt, conf, init_mask, cam, reg_pose, S, nullptr);
+        eval_frame(M, L, *st, gt, conf, init_mask, cam, reg_pose, S, nullptr, Wp);
         *loss_out = S.loss;
         for (int i = 0; i < L.np; ++i) grad_out[i] = S.gfull[i];
     } else {
@@ -62,6 +85,9 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
         for (int k = 0; k < M.K; ++k)
             for (int a = 0; a < 3; ++a) joints_out[3 * k + a] = S.X[3 * M.joint_map[k] + a];
     *n_evals = S.n_evals;
+    sm.last_touch = S.n_touch;
+    sm.last_overflow = S.coll_overflow;
+    if (S.coll_overflow) *flags |= SFX_FLAG_COLL_OVERFLOW;
 }
 
 template <typename T>
@@ -91,6 +117,28 @@ void hs_set_vposer(void* p, const void* w1, const void* b1, const void* w2, cons
         set_vposer<float>(h->f, (const float*)w1, (const float*)b1, (const float*)w2,
                           (const float*)b2, (const float*)w3, (const float*)b3);
 }
+// face segmentation + ignored part pairs of the interpenetration term; work_bytes = size of the
+// candidate area (the device uses the idle blend ring: 128 KB in float, 64 KB in double)
+int hs_set_collision(void* p, const int32_t* segm, const int32_t* parents, const int32_t* ign,
+                     int n_ign, int work_bytes, char* err, int errlen) {
+    SimHandle* h = (SimHandle*)p;
+    std::string e;
+    if (h->use_double) {
+        e = prepare_collision(h->d.h.V, h->d.h.F, h->d.h.faces.data(), segm, parents, ign, n_ign, h->d.coll);
+        h->d.has_coll = e.empty(); h->d.coll_work_bytes = work_bytes;
+    } else {
+        e = prepare_collision(h->f.h.V, h->f.h.F, h->f.h.faces.data(), segm, parents, ign, n_ign, h->f.coll);
+        h->f.has_coll = e.empty(); h->f.coll_work_bytes = work_bytes;
+    }
+    if (!e.empty()) { std::strncpy(err, e.c_str(), errlen - 1); return -1; }
+    return 0;
+}
+// unit access to the narrow phase and the pair penalty (double)
+int hs_triangles_intersect(const double* t1, const double* t2) { return triangles_intersect(t1, t2) ? 1 : 0; }
+void hs_pair_terms(const double* ti, const double* tj, double sigma, double* loss, double* gi) {
+    pair_terms(ti, tj, sigma, loss, gi);
+}
+int hs_last_touch(void* p) { SimHandle* h = (SimHandle*)p; return h->use_double ? h->d.last_touch : h->f.last_touch; }
 int hs_trace(double* out, int cap) {
     int n = (int)g_trace.size();
     for (int i = 0; i < n && i < cap; ++i) out[i] = g_trace[i];
