@@ -40,8 +40,24 @@ ROW_BYTES = 512 * 4
 
 
 # ------------------------------------------------------------------------------ workload
-def bench_cfg():
-    """fit_smplx_combined_coco25.yaml (reference cfg_files/) with BASELINE config-2 switches."""
+COLL_POSE_CORRECTIVE_SCALE = 0.1      # config 4: see synthetic.cached_smplx_like
+
+
+def bench_cfg(interpenetration=False):
+    """fit_smplx_combined_coco25.yaml (reference cfg_files/) with BASELINE config-2 switches;
+    ``interpenetration`` turns the yaml's own interpenetration settings back on (config 4)."""
+    cfg = _bench_cfg()
+    if interpenetration:
+        from smplifyx_b200 import synthetic
+        md = synthetic.cached_smplx_like(0, COLL_POSE_CORRECTIVE_SCALE)
+        cfg.update(interpenetration=True, coll_loss_weights=[0.0, 0.1, 1.0], df_cone_height=1e-4,
+                   max_collisions=128, penalize_outside=True, point2plane=False,
+                   ign_part_pairs=["9,16", "9,17", "6,16", "6,17", "1,2", "12,22"] +
+                   synthetic.sibling_part_pairs(md))
+    return cfg
+
+
+def _bench_cfg():
     return dict(
         format='coco25', joints_to_ign=[1, 9, 12], gender='neutral', model_type='smplx',
         float_dtype='float32', use_joints_conf=True, use_pca=True, use_hands=True, use_face=True,
@@ -76,8 +92,13 @@ def _rodrigues_batch(r):
     return np.eye(3) + s * K + (1 - c) * (K @ K)
 
 
-def ground_truth(B, seed):
-    """Seeded ground-truth parameters of B frames."""
+def ground_truth(B, seed, shape_scale=1.0):
+    """Seeded ground-truth parameters of B frames.
+
+    ``shape_scale`` < 1 (config 4): the synthetic model's shape directions are per-vertex noise,
+    so at unit betas the tube mesh self-intersects in ~10^4 triangle pairs wherever two tubes
+    meet -- two orders of magnitude beyond a real body.  Scaling the ground-truth shape keeps the
+    interpenetration term's load at what the pose causes (arms against the torso)."""
     from smplifyx_b200 import utils as U
     rng = np.random.default_rng(seed)
     gt = dict(
@@ -91,6 +112,8 @@ def ground_truth(B, seed):
     for b in range(B):
         go[b] = U.inv_rodrigues(U.rodrigues(rng.normal(size=3) * 0.3).dot(Rx))
     gt['global_orient'] = go
+    gt['betas'] *= shape_scale
+    gt['expression'] *= shape_scale
     t = np.stack([rng.normal(size=B) * 0.1, rng.normal(size=B) * 0.1,
                   rng.uniform(2.5, 6.0, size=B)], axis=1)
     gt['transl'] = t
@@ -257,11 +280,13 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(B, n_gpus):
+def workload_config(B, n_gpus, interpenetration=False):
     return {'workload': 'batch={} synthetic frames per GPU, 135 keypoints (127 model joints + 17 '
                         'face-contour), neutral SMPL-X-shaped synthetic model, GMoF + L2 priors, '
                         '3-stage fit_smplx_combined_coco25 schedule, lbfgsls, combined regression '
-                        '+ camera prior, interpenetration off'.format(B),
+                        '+ camera prior, interpenetration {}'.format(
+                            B, 'ON (coll_loss_weights 0 / 0.1 / 1.0, df_cone_height 1e-4, part '
+                            'filter; BASELINE config 4)' if interpenetration else 'off'),
             'frames_per_gpu': B, 'global_frames': B * n_gpus,
             'parallelism': 'frames sharded, dp{}'.format(n_gpus),
             'l2': 'flushed between timed steps (256 MiB write)'}
@@ -280,16 +305,19 @@ def run_b200(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    cfg = bench_cfg()
+    cfg = bench_cfg(args.interpenetration)
+    md = synthetic.cached_smplx_like(
+        0, COLL_POSE_CORRECTIVE_SCALE if args.interpenetration else 1.0)
+    part_segm = synthetic.parts_segm_like(md) if args.interpenetration else None
     B = args.frames
     jm = U.smpl_to_annotation('smplx', use_hands=True, use_face=True, use_face_contour=True,
                               format='coco25')
-    model = engine.Model(synthetic.cached_smplx_like(0), jm, dtype=torch.float32, **MODEL_KW)
+    model = engine.Model(md, jm, dtype=torch.float32, **MODEL_KW)
     batch = engine.FrameBatch(model, B)
     L = batch.L
 
     # ---- synthetic inputs: GT parameters -> model joints (engine forward) -> noisy keypoints
-    gt, rng = ground_truth(B, args.seed + 1000 * rank)
+    gt, rng = ground_truth(B, args.seed + 1000 * rank, 0.2 if args.interpenetration else 1.0)
     cam_st = N.make_stage(L, N.CAMERA_STAGE_BLOCKS, loss_kind=N.LOSS_CAMERA_INIT)
     K = model.K
     zero_cam = np.zeros((B, N.SFX_CAM_STRIDE))
@@ -303,7 +331,8 @@ def run_b200(args):
     _, _, j3 = batch.eval(cam_st, want_joints=True)
     kp, expose, pixie = observations(gt, j3.cpu().numpy().astype(np.float64), rng)
 
-    plan = FF.FitPlan(L, K, kp, H_IMG, W_IMG, cfg, expose, pixie, None, np.float32)
+    plan = FF.FitPlan(L, K, kp, H_IMG, W_IMG, cfg, expose, pixie, None, np.float32,
+                      part_segm=part_segm)
     FF.upload(batch, plan)
     x0_dev = batch.params_tensor().clone()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -349,12 +378,14 @@ def run_b200(args):
               for _ in range(args.steps)]
     out = None
     for _ in range(min(args.warmup, 2)):
-        out = FF.fit_frames(batch, kp, H_IMG, W_IMG, cfg, expose, pixie, return_verts=True)
+        out = FF.fit_frames(batch, kp, H_IMG, W_IMG, cfg, expose, pixie, return_verts=True,
+                            part_segm=part_segm)
     barrier()
     for i in range(args.steps):
         flush.fill_(i & 0xff)
         e2e_ev[i][0].record()
-        out = FF.fit_frames(batch, kp, H_IMG, W_IMG, cfg, expose, pixie, return_verts=True)
+        out = FF.fit_frames(batch, kp, H_IMG, W_IMG, cfg, expose, pixie, return_verts=True,
+                            part_segm=part_segm)
         if world > 1:
             dist.all_gather_into_tensor(gathered, batch.params_tensor())
         e2e_ev[i][1].record()
@@ -407,7 +438,7 @@ def run_b200(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(B, world),
+        'config': workload_config(B, world, args.interpenetration),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(out.h2d_bytes),
                 'd2h_bytes_per_step': int(out.d2h_bytes), 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
@@ -416,7 +447,7 @@ def run_b200(args):
                 'frames_with_nan_or_inf': int((out.flags != 0).sum()),
                 'frames_second_orientation': int(len(plan.flip_ids))},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.interpenetration:
         sample = list(range(min(args.cpu_frames, B)))
         threads = os.cpu_count() or 1
         secs, evals = time_oracle_frames(cfg, kp, expose, pixie, sample, threads)
@@ -443,6 +474,10 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-frames', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--interpenetration', action='store_true',
+                    help='BASELINE config 4: the same workload with the interpenetration term on '
+                         '(not the default bench line; the CPU baseline is skipped because the '
+                         'restated third-party search takes seconds per evaluation in numpy)')
     ap.add_argument('--traffic', type=float, default=None,
                     help='dram bytes per launch from an ncu capture (profiles/), recorded as-is')
     args = ap.parse_args()

@@ -98,6 +98,9 @@ int sfx_batch_layout(const sfx_batch* b, SfxLayout* out);
  * float32).  Needed before a stage with coll_loss_weight > 0 (SfxStage) is evaluated or fitted;
  * df_cone_height travels as SfxStage.coll_sigma. */
 int sfx_batch_enable_collisions(sfx_batch* b);
+/* Diagnostics of the term ([B][2] int32, device; NULL before sfx_batch_enable_collisions): the
+ * largest number of candidate faces and of touched vertices any evaluation of the frame saw. */
+int32_t* sfx_batch_coll_stat_dev(sfx_batch* b);
 
 /* Targets of every frame (host pointers; copied with cudaMemcpyAsync on `stream`):
  *   keypoints [B,K,3] (x, y, conf)        fit_single_frame.py:276-284
@@ -160,9 +163,9 @@ void* sfx_batch_final_loss_dev(sfx_batch* b);
 int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order_dev,
                      const uint8_t* flip_dev, void* stream);
 void* sfx_batch_cam_loss_dev(sfx_batch* b);
-/* [B][8] int64 cycle counters per frame (all zero unless the library was built with
+/* [B][16] int64 cycle counters per frame (all zero unless the library was built with
  * -DSFX_CYCLE_PROF): 0 evaluations, 1 two-loop recursion, 2 blend forward, 3 blend adjoint,
- * 4 whole frame. */
+ * 4 whole frame, 8..12 phases of the interpenetration term. */
 long long* sfx_batch_prof_dev(sfx_batch* b);
 /* body_model(return_verts=True) at the LAST fitted orientation of every frame -- the mesh the
  * reference writes to vertices.ply (fit_single_frame.py:611, :671-676). */

@@ -5,11 +5,13 @@ from smplifyx_b200 import _native as N
 N.LIB_PATH = os.path.join(os.path.dirname(N.LIB_PATH), 'libsfx_prof.so')
 import bench
 from smplifyx_b200 import engine, fit_frames as FF, synthetic, utils as U
-cfg = bench.bench_cfg(); B=128
+COLL = '--interpenetration' in sys.argv
+cfg = bench.bench_cfg(COLL); B = 128
 jm = U.smpl_to_annotation('smplx', True, True, True, 'coco25')
-model = engine.Model(synthetic.cached_smplx_like(0), jm, dtype=torch.float32, **bench.MODEL_KW)
+md = synthetic.cached_smplx_like(0, bench.COLL_POSE_CORRECTIVE_SCALE if COLL else 1.0)
+model = engine.Model(md, jm, dtype=torch.float32, **bench.MODEL_KW)
 batch = engine.FrameBatch(model, B); L = batch.L
-gt, rng = bench.ground_truth(B, 0)
+gt, rng = bench.ground_truth(B, 0, 0.2 if COLL else 1.0)
 cam_st = N.make_stage(L, N.CAMERA_STAGE_BLOCKS, loss_kind=N.LOSS_CAMERA_INIT)
 zc = np.zeros((B, 16)); zc[:,0:2]=1; zc[:,4:13]=np.eye(3).reshape(-1)
 xg = bench.gt_param_matrix(L, gt); xg[:, L.off_camt+2]=1
@@ -17,7 +19,8 @@ batch.set_targets(np.zeros((B,135,3)), np.zeros((B,135)), np.zeros((B,135),np.ui
 batch.set_params(xg)
 _,_,j3 = batch.eval(cam_st, want_joints=True)
 kp, ex, px = bench.observations(gt, j3.cpu().numpy().astype(np.float64), rng)
-plan = FF.FitPlan(L, 135, kp, 600, 800, cfg, ex, px, None, np.float32)
+part_segm = synthetic.parts_segm_like(md) if COLL else None
+plan = FF.FitPlan(L, 135, kp, 600, 800, cfg, ex, px, None, np.float32, part_segm=part_segm)
 FF.upload(batch, plan)
 x0 = batch.params_tensor().clone()
 for it in range(2):
@@ -25,11 +28,17 @@ for it in range(2):
     FF.run(batch, plan, True); torch.cuda.synchronize()
 lib = batch.lib; lib.sfx_batch_prof_dev.restype = C.c_void_p; lib.sfx_batch_prof_dev.argtypes=[C.c_void_p]
 ptr = lib.sfx_batch_prof_dev(batch.h)
-prof = engine._wrap(ptr, (B*16,), torch.int32, model.device, batch).cpu().numpy().view(np.int64).reshape(B,8)
+prof = engine._wrap(ptr, (B*32,), torch.int32, model.device, batch).cpu().numpy().view(np.int64).reshape(B,16)
 ev = batch.evals().cpu().numpy()
 tot = prof[:,4].astype(float)
 i = np.argmax(tot)
 print('slowest frame', i, 'evals', ev[i], 'cycles total %.3g (%.1f ms @1.965GHz)' % (tot[i], tot[i]/1.965e6))
-for name, k in (('eval',0),('two_loop',1),('blend_fwd',2),('blend_adj',3),('chain_fwd_w0',5),('stream_fwd_w1',6),('chain_adj_w0',7)):
+for name, k in (('eval',0),('two_loop',1),('blend_fwd',2),('blend_adj',3),('chain_fwd_w0',5),('stream_fwd_w1',6),('chain_adj_w0',7),
+                ('coll_skin',8),('coll_boxes_cand',9),('coll_narrow',10),('coll_vgather',11),('coll_skin_adj',12),('coll_walk_t0',13),('coll_pairs_t0',14)):
     print('%-10s slowest: %5.1f%%   all frames: %5.1f%%   per eval (slowest) %.1f us' % (name, 100*prof[i,k]/tot[i], 100*prof[:,k].sum()/tot.sum(), prof[i,k]/ev[i]/1965.))
 print('mean frame total ms', tot.mean()/1.965e6, 'median evals', np.median(ev))
+
+cs = batch.coll_stats()
+if cs is not None:
+    cs = cs.cpu().numpy()
+    print('candidates per frame (max over evals): median %d max %d; touched vertices: median %d max %d' % (np.median(cs[:,0]), cs[:,0].max(), np.median(cs[:,1]), cs[:,1].max()))

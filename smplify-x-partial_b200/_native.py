@@ -252,6 +252,8 @@ def load_library(path=None):
     lib.sfx_model_set_gmm.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.sfx_model_set_collision.argtypes = [vp, vp, vp, vp, i32]
     lib.sfx_batch_enable_collisions.argtypes = [vp]
+    lib.sfx_batch_coll_stat_dev.argtypes = [vp]
+    lib.sfx_batch_coll_stat_dev.restype = vp
     lib.sfx_model_destroy.argtypes = [vp]
     lib.sfx_model_destroy.restype = None
     lib.sfx_batch_create.argtypes = [vp, i32, i32, C.POINTER(vp)]

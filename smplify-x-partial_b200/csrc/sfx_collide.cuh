@@ -33,11 +33,18 @@ struct CollWS {
     T* dvert_g;            // [3V]  dL/dvertex of touched vertices
     T* dtri_g;             // [F][9] dL/d(own corners) of faces that collided
     unsigned short* tv_g;  // [V]   touched vertices of the current evaluation, ascending
-    T* big_box;            // [F][6] candidate boxes / faces when they outgrow the shared area
-    unsigned short* big_face;   // [F]
+    T* fbox;               // [F][6] axis-aligned box of every face
+    unsigned char* sort_g; // [SFX_COLL_ENTRY * SFX_COLL_SORT_G] sweep arrays when they outgrow the shared area
+    unsigned short* hits_g;     // [threads][hits_cap] per-thread lists: (count, partner faces...) per candidate
+    int hits_cap;
     unsigned char* work;   // shared-memory work area (the idle blend ring on the device)
     int work_bytes;
 };
+#define SFX_COLL_SORT_G 32768      // capacity of the global sweep arrays (power of two >= F)
+#define SFX_COLL_LARGE 256         // capacity of the list of long candidates
+#define SFX_COLL_LARGE_GOAL 192    // the short / long threshold aims at no more long candidates than this
+#define SFX_COLL_ENTRY 12          // bytes per candidate: packed part + quantised box 8, key 2, face 2
+#define SFX_COLL_HITS 2048         // per-thread region of the potential-hit list (16-bit entries)
 
 template <typename T>
 SFX_FN CollWS<T> coll_block_ws(int V, int F, T* vals, unsigned short* idx, unsigned char* work,
@@ -47,15 +54,17 @@ SFX_FN CollWS<T> coll_block_ws(int V, int F, T* vals, unsigned short* idx, unsig
     W.vert_g = vals + 3L * V;
     W.dvert_g = vals + 6L * V;
     W.dtri_g = vals + 9L * V;
-    W.big_box = vals + 9L * V + 9L * F;
+    W.fbox = vals + 9L * V + 9L * F;
     W.tv_g = idx;
-    W.big_face = idx + V;
+    W.sort_g = reinterpret_cast<unsigned char*>(idx + (V + 7) / 8 * 8);
+    W.hits_g = idx + (V + 7) / 8 * 8 + (long)SFX_COLL_ENTRY * SFX_COLL_SORT_G / 2;
+    W.hits_cap = SFX_COLL_HITS;
     W.work = work;
     W.work_bytes = work_bytes;
     return W;
 }
 inline long coll_vals_per_block(int V, int F) { return (9L * V + 15L * F + 3) / 4 * 4; }
-inline long coll_idx_per_block(int V, int F) { return ((long)V + F + 7) / 8 * 8; }
+inline long coll_idx_per_block(int V, int F) { return ((long)V + 7) / 8 * 8 + (long)SFX_COLL_ENTRY * SFX_COLL_SORT_G / 2 + 512L * SFX_COLL_HITS; }
 
 template <typename T>
 SFX_FN void v3sub(const T* a, const T* b, T* c) { c[0] = a[0] - b[0]; c[1] = a[1] - b[1]; c[2] = a[2] - b[2]; }
@@ -312,16 +321,37 @@ SFX_FN bool boxes_overlap(const T* a, const T* b) {
 // layout of the shared work area
 template <typename T>
 struct CollArea {
-    int cap;                     // candidate capacity
-    T* box;                      // [cap][6]
-    unsigned short* face;        // [cap]
+    int cap;                     // candidate capacity (a power of two)
+    int cap_lean;                // ... when the packed entries move out to global memory
+    unsigned char* sort_base;    // start of the sweep arrays inside the work area
+    unsigned short* skey;        // [cap] box minimum along the sweep axis on a 65536-level grid, ascending after the sort
+    unsigned short* sface;       // [cap] face of the candidate
+    unsigned long long* pk;      // [cap] packed: bytes 0-2 box minimum on a 256-level grid over the body's box
+                                 // (rounded outwards), byte 3 part | 0x80 when long along the sweep axis,
+                                 // bytes 4-6 box maximum, byte 7 unused
+    int* hist;                   // [256] candidates by quantised extent along the sweep axis
+    unsigned short* large;       // [SFX_COLL_LARGE] sorted positions of the long candidates
     unsigned int* hit;           // [(F + 31) / 32] faces that collided
     unsigned int* vtouch;        // [(V + 31) / 32] vertices of such faces
     T* part_loss;                // [SFX_NT] per-thread partial sums
     T* pbox;                     // [SFX_NPART_MAX][6]
+    T* cbox;                     // [SFX_NCLUSTER_MAX][6] boxes of the face clusters
     unsigned long long* pmask;   // [SFX_NPART_MAX] admissible partner parts whose boxes overlap
-    int* cptr;                   // [SFX_NPART_MAX + 1] candidates by part (CSR)
 };
+
+// sweep arrays of `cap` candidates at p; the packed entries either in front of them or at q
+template <typename T>
+SFX_FN void coll_sort_arrays(CollArea<T>& A, unsigned char* p, int cap, unsigned char* q = nullptr) {
+    A.cap = cap;
+    if (q) {
+        A.pk = reinterpret_cast<unsigned long long*>(q);
+    } else {
+        A.pk = reinterpret_cast<unsigned long long*>(p);
+        p += 8L * cap;
+    }
+    A.skey = reinterpret_cast<unsigned short*>(p);
+    A.sface = reinterpret_cast<unsigned short*>(p + 2L * cap);
+}
 
 template <typename T>
 SFX_FN CollArea<T> coll_area(const ModelView<T>& M, const CollWS<T>& W, int nthreads) {
@@ -329,39 +359,113 @@ SFX_FN CollArea<T> coll_area(const ModelView<T>& M, const CollWS<T>& W, int nthr
     unsigned char* p = W.work;
     A.pmask = reinterpret_cast<unsigned long long*>(p); p += SFX_NPART_MAX * 8;
     A.pbox = reinterpret_cast<T*>(p); p += SFX_NPART_MAX * 6 * sizeof(T);
+    A.cbox = reinterpret_cast<T*>(p); p += (size_t)M.n_clusters * 6 * sizeof(T);
     A.part_loss = reinterpret_cast<T*>(p); p += (size_t)nthreads * sizeof(T);
-    A.cptr = reinterpret_cast<int*>(p); p += (SFX_NPART_MAX + 4) * 4;
     A.hit = reinterpret_cast<unsigned int*>(p); p += ((M.F + 31) / 32 + 1) / 2 * 8;
     A.vtouch = reinterpret_cast<unsigned int*>(p); p += ((M.V + 31) / 32 + 1) / 2 * 8;
+    A.large = reinterpret_cast<unsigned short*>(p); p += SFX_COLL_LARGE * 2;
+    A.hist = reinterpret_cast<int*>(p); p += 256 * 4;
     const long left = (long)W.work_bytes - (long)(p - W.work);
-    int cap = left > 0 ? (int)(left / (long)(6 * sizeof(T) + 2)) : 0;
-    cap = cap / 32 * 32;
-    if (cap > 65535) cap = 65535 / 32 * 32;
-    A.cap = cap;
-    A.box = reinterpret_cast<T*>(p); p += (size_t)cap * 6 * sizeof(T);
-    A.face = reinterpret_cast<unsigned short*>(p);
+    int cap = 0;
+    for (int c = 64; (long)SFX_COLL_ENTRY * c <= left && c <= SFX_COLL_SORT_G; c <<= 1) cap = c;
+    coll_sort_arrays(A, p, cap);
+    A.sort_base = p;
+    A.cap_lean = 0;
+    for (int c = 64; 4L * c <= left && c <= SFX_COLL_SORT_G; c <<= 1) A.cap_lean = c;
     return A;
 }
 
-// Full-mesh skinning: vert_g = T(v) . [vp_g; 1], T(v) = sum_j W[v][j] A_j
+// Full-mesh skinning through the per-vertex weight lists: vert_g = T(v) . [vp_g; 1]
 template <typename T>
 SFX_FN void coll_skin_mesh(const ModelView<T>& M, Scratch<T>& S, const CollWS<T>& W) {
     SFX_FOR(v, M.V) {
-        const T* w = M.Wd + (long)v * SFX_WROW;
         T Tm[12];
         for (int k = 0; k < 12; ++k) Tm[k] = 0;
-        for (int j = 0; j < SFX_NJ; ++j) {
-            const T wj = w[j];
-            if (wj != (T)0) {
-                const T* A = S.A + 12 * j;
-                for (int k = 0; k < 12; ++k) Tm[k] += wj * A[k];
-            }
+        for (int e = M.sk_ptr[v]; e < M.sk_ptr[v + 1]; ++e) {
+            const T wj = M.sk_w[e];
+            const T* A = S.A + 12 * M.sk_j[e];
+            for (int k = 0; k < 12; ++k) Tm[k] += wj * A[k];
         }
         const T x = W.vp_g[3 * v], y = W.vp_g[3 * v + 1], z = W.vp_g[3 * v + 2];
         for (int r = 0; r < 3; ++r)
             W.vert_g[3 * v + r] = Tm[4 * r] * x + Tm[4 * r + 1] * y + Tm[4 * r + 2] * z + Tm[4 * r + 3];
     }
     SFX_SYNC();
+}
+
+// packed entry helpers
+SFX_FN unsigned int pk_lo(unsigned long long e) { return (unsigned int)e; }
+SFX_FN unsigned int pk_hi(unsigned long long e) { return (unsigned int)(e >> 32); }
+// do the quantised boxes of two entries overlap?  (bytes 0-2 of lo = minimum, of hi = maximum)
+SFX_FN bool pk_overlap(unsigned long long a, unsigned long long b) {
+    const unsigned int alo = pk_lo(a) & 0xffffffu, ahi = pk_hi(a) & 0xffffffu;
+    const unsigned int blo = pk_lo(b) & 0xffffffu, bhi = pk_hi(b) & 0xffffffu;
+#ifdef __CUDACC__
+    // per-byte unsigned compares: all of alo <= bhi and blo <= ahi
+    return (__vcmpleu4(alo, bhi) & __vcmpleu4(blo, ahi) & 0xffffffu) == 0xffffffu;
+#else
+    for (int k = 0; k < 3; ++k) {
+        const unsigned int s = 8 * k;
+        if (((alo >> s) & 255u) > ((bhi >> s) & 255u) || ((blo >> s) & 255u) > ((ahi >> s) & 255u)) return false;
+    }
+    return true;
+#endif
+}
+
+// Partners of the candidate at sorted position pos: visit(face) for every other candidate whose
+// part is admissible and whose box overlaps, each exactly once.  A short candidate meets other
+// short ones inside a window of the sorted order (backwards no further than the longest short
+// extent E, forwards up to its own maximum; both ends by binary search) and the long ones
+// through their list; a long candidate scans everything.
+template <typename T, typename VISIT>
+SFX_FN void coll_partners(const CollWS<T>& W, const CollArea<T>& A, int pos, int ncand, int nlarge,
+                          int axis, int E16, VISIT visit) {
+    const unsigned long long me = A.pk[pos];
+    const unsigned long long allow = A.pmask[(pk_lo(me) >> 24) & 0x7f];
+    const bool me_long = (pk_lo(me) >> 31) & 1u;
+    int lo = 0, hi = ncand;
+    if (!me_long) {
+        // 8-bit level q covers 257 of the 16-bit key levels; the box maximum is rounded up
+        const int kmin = (int)A.skey[pos] - E16;
+        const int kmax = (int)(((pk_hi(me) >> (8 * axis)) & 255u) + 1u) * 257;
+        int a = 0, b = pos;                  // first index with key >= kmin
+        while (a < b) { const int m = (a + b) >> 1; if ((int)A.skey[m] < kmin) a = m + 1; else b = m; }
+        lo = a;
+        a = pos + 1; b = ncand;              // first index with key > kmax
+        while (a < b) { const int m = (a + b) >> 1; if ((int)A.skey[m] <= kmax) a = m + 1; else b = m; }
+        hi = a;
+    }
+    const int nsteps = (hi - lo) + (me_long ? 0 : nlarge);
+    for (int s = 0; s < nsteps; ++s) {
+        const int b = s < hi - lo ? lo + s : (int)A.large[s - (hi - lo)];
+        if (b == pos) continue;
+        const unsigned long long e = A.pk[b];
+        if (s < hi - lo && !me_long && ((pk_lo(e) >> 31) & 1u)) continue;   // long ones: via the list
+        if (!((allow >> ((pk_lo(e) >> 24) & 0x7f)) & 1ull)) continue;
+        // the quantised boxes are rounded outwards: a superset of the exact box overlaps; the
+        // separating-axis test sorts out the rest (triangles with disjoint boxes never pass it)
+        if (!pk_overlap(me, e)) continue;
+        visit((int)A.sface[b]);
+    }
+}
+
+// separating-axis test + penalty of one listed partner
+template <typename T>
+SFX_FN void coll_pair(const ModelView<T>& M, const T* vert, int fi, const T* ti, int fj, T sigma,
+                      bool* hit, T* loss_i, T* gi) {
+    T tj[9];
+    int idj[3];
+    face_corners(M, vert, fj, tj, idj);
+    // the package compares corner coordinates (shareVertex); so do we
+    bool share = false;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+            share = share || (ti[3 * a] == tj[3 * b] && ti[3 * a + 1] == tj[3 * b + 1] &&
+                              ti[3 * a + 2] == tj[3 * b + 2]);
+    if (!share && (fi < fj ? triangles_intersect(ti, tj) : triangles_intersect(tj, ti))) {
+        *hit = true;
+        pair_terms(ti, tj, sigma, loss_i, gi);
+    }
 }
 
 // Search + penalty + per-vertex gradients.  On return: S.coll_loss (unweighted sum over the
@@ -374,20 +478,33 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
     CollArea<T> A = coll_area(M, W, SFX_NT);
     const T* vert = W.vert_g;
     SFX_SYNC();
-    // ---- per-part boxes: one warp per part, lanes stride over its faces ----
+    SFX_PROF_BEGIN(cb);
+    // ---- boxes of all faces, then of the parts (one warp per part) ----
+    SFX_FOR(f, F) {
+        T tri[9], box[6];
+        int ids[3];
+        face_corners(M, vert, f, tri, ids);
+        tri_box(tri, box);
+        for (int d = 0; d < 6; ++d) W.fbox[(long)f * 6 + d] = box[d];
+    }
+    SFX_FOR(i, (F + 31) / 32) A.hit[i] = 0;
+    SFX_FOR(i, (V + 31) / 32) A.vtouch[i] = 0;
+    if (SFX_TID == 0) {
+        S.cscan_total = 0;
+        S.cscan_calls = 0;
+    }
+    SFX_SYNC();
+    // boxes of the face clusters (one warp per cluster, two faces per lane), then of the parts
 #ifdef __CUDACC__
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-        for (int p = warp; p < NP; p += nw) {
+        for (int c = warp; c < M.n_clusters; c += nw) {
             T lo[3] = {(T)INFINITY, (T)INFINITY, (T)INFINITY}, hi[3] = {-(T)INFINITY, -(T)INFINITY, -(T)INFINITY};
-            for (int k = M.part_ptr[p] + lane; k < M.part_ptr[p + 1]; k += 32) {
-                const int f = M.part_faces[k];
-                for (int c = 0; c < 3; ++c) {
-                    const T* q = vert + 3 * M.faces[3 * f + c];
-                    for (int d = 0; d < 3; ++d) {
-                        lo[d] = q[d] < lo[d] ? q[d] : lo[d];
-                        hi[d] = q[d] > hi[d] ? q[d] : hi[d];
-                    }
+            for (int k = M.cl_ptr[c] + lane; k < M.cl_ptr[c + 1]; k += 32) {
+                const T* q = W.fbox + (long)M.part_faces[k] * 6;
+                for (int d = 0; d < 3; ++d) {
+                    lo[d] = q[d] < lo[d] ? q[d] : lo[d];
+                    hi[d] = q[3 + d] > hi[d] ? q[3 + d] : hi[d];
                 }
             }
             for (int o = 16; o > 0; o >>= 1)
@@ -397,30 +514,31 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
                     hi[d] = h2 > hi[d] ? h2 : hi[d];
                 }
             if (lane == 0)
-                for (int d = 0; d < 3; ++d) { A.pbox[6 * p + d] = lo[d]; A.pbox[6 * p + 3 + d] = hi[d]; }
+                for (int d = 0; d < 3; ++d) { A.cbox[6 * c + d] = lo[d]; A.cbox[6 * c + 3 + d] = hi[d]; }
         }
     }
 #else
-    for (int p = 0; p < NP; ++p) {
+    for (int c = 0; c < M.n_clusters; ++c) {
         T lo[3] = {(T)INFINITY, (T)INFINITY, (T)INFINITY}, hi[3] = {-(T)INFINITY, -(T)INFINITY, -(T)INFINITY};
-        for (int k = M.part_ptr[p]; k < M.part_ptr[p + 1]; ++k) {
-            const int f = M.part_faces[k];
-            for (int c = 0; c < 3; ++c) {
-                const T* q = vert + 3 * M.faces[3 * f + c];
-                for (int d = 0; d < 3; ++d) {
-                    lo[d] = q[d] < lo[d] ? q[d] : lo[d];
-                    hi[d] = q[d] > hi[d] ? q[d] : hi[d];
-                }
+        for (int k = M.cl_ptr[c]; k < M.cl_ptr[c + 1]; ++k) {
+            const T* q = W.fbox + (long)M.part_faces[k] * 6;
+            for (int d = 0; d < 3; ++d) {
+                lo[d] = q[d] < lo[d] ? q[d] : lo[d];
+                hi[d] = q[3 + d] > hi[d] ? q[3 + d] : hi[d];
             }
         }
-        for (int d = 0; d < 3; ++d) { A.pbox[6 * p + d] = lo[d]; A.pbox[6 * p + 3 + d] = hi[d]; }
+        for (int d = 0; d < 3; ++d) { A.cbox[6 * c + d] = lo[d]; A.cbox[6 * c + 3 + d] = hi[d]; }
     }
 #endif
-    SFX_FOR(i, (F + 31) / 32) A.hit[i] = 0;
-    SFX_FOR(i, (V + 31) / 32) A.vtouch[i] = 0;
-    if (SFX_TID == 0) {
-        S.cscan_total = 0;
-        S.cscan_calls = 0;
+    SFX_SYNC();
+    SFX_FOR(p, NP) {
+        T lo[3] = {(T)INFINITY, (T)INFINITY, (T)INFINITY}, hi[3] = {-(T)INFINITY, -(T)INFINITY, -(T)INFINITY};
+        for (int c = M.part_cl_ptr[p]; c < M.part_cl_ptr[p + 1]; ++c)
+            for (int d = 0; d < 3; ++d) {
+                lo[d] = A.cbox[6 * c + d] < lo[d] ? A.cbox[6 * c + d] : lo[d];
+                hi[d] = A.cbox[6 * c + 3 + d] > hi[d] ? A.cbox[6 * c + 3 + d] : hi[d];
+            }
+        for (int d = 0; d < 3; ++d) { A.pbox[6 * p + d] = lo[d]; A.pbox[6 * p + 3 + d] = hi[d]; }
     }
     SFX_SYNC();
     SFX_FOR(p, NP) {
@@ -434,38 +552,70 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
         A.pmask[p] = m;
     }
     SFX_SYNC();
-    // ---- candidate faces, compacted in part order ----
-    // First into the shared area; if they do not fit, once more into the block's global arrays.
+    // sweep axis: the longest side of the body's box
+    int axis = 0;
+    {
+        T best = -1;
+        for (int d = 0; d < 3; ++d) {
+            T lo = (T)INFINITY, hi = -(T)INFINITY;
+            for (int p = 0; p < NP; ++p)
+                if (M.part_ptr[p] != M.part_ptr[p + 1]) {
+                    lo = A.pbox[6 * p + d] < lo ? A.pbox[6 * p + d] : lo;
+                    hi = A.pbox[6 * p + 3 + d] > hi ? A.pbox[6 * p + 3 + d] : hi;
+                }
+            if (hi - lo > best) { best = hi - lo; axis = d; }
+        }
+    }
+    // the body's box: origin and scale of the 256-level (boxes) and 65536-level (sweep key) grids
+    T blo[3], bsc[3];
+    for (int d = 0; d < 3; ++d) {
+        T lo = (T)INFINITY, hi = -(T)INFINITY;
+        for (int p = 0; p < NP; ++p)
+            if (M.part_ptr[p] != M.part_ptr[p + 1]) {
+                lo = A.pbox[6 * p + d] < lo ? A.pbox[6 * p + d] : lo;
+                hi = A.pbox[6 * p + 3 + d] > hi ? A.pbox[6 * p + 3 + d] : hi;
+            }
+        blo[d] = lo;
+        bsc[d] = hi > lo ? (T)255 / (hi - lo) : (T)0;
+    }
+    // ---- candidate faces: their box reaches into the box of an admissible partner part ----
+    // Compacted in part order into the sweep arrays: first the shared ones; if they do not fit,
+    // once more into the block's global arrays.
     for (int attempt = 0; attempt < 2; ++attempt) {
         for (int k0 = 0; k0 < F; k0 += SFX_NT) {
             const int k = k0 + SFX_TID;
             bool cand = false;
-            int f = 0;
-            T box[6];
+            int f = 0, part = 0;
+            int key = 0;
             if (k < F) {
                 f = M.part_faces[k];
-                const unsigned long long m = A.pmask[M.face_part[f]];
+                part = M.face_part[f];
+                const unsigned long long m = A.pmask[part];
                 if (m) {
-                    T tri[9];
-                    int ids[3];
-                    face_corners(M, vert, f, tri, ids);
-                    tri_box(tri, box);
+                    T box[6];
+                    for (int d = 0; d < 6; ++d) box[d] = W.fbox[(long)f * 6 + d];
+                    // ... the box of one of the partner part's clusters, to be precise
                     for (int q = 0; q < NP && !cand; ++q)
-                        if (((m >> q) & 1ull) && boxes_overlap(box, A.pbox + 6 * q)) cand = true;
+                        if (((m >> q) & 1ull) && boxes_overlap(box, A.pbox + 6 * q))
+                            for (int c = M.part_cl_ptr[q]; c < M.part_cl_ptr[q + 1] && !cand; ++c)
+                                cand = boxes_overlap(box, A.cbox + 6 * c);
+                    key = (int)floorf((float)((box[axis] - blo[axis]) * bsc[axis]) * 257.f);
+                    key = key < 0 ? 0 : (key > 65535 ? 65535 : key);
                 }
             }
             const int slot = ordered_slot(cand, S);
             if (cand && slot < A.cap) {
-                for (int d = 0; d < 6; ++d) A.box[6 * slot + d] = box[d];
-                A.face[slot] = (unsigned short)f;
+                A.skey[slot] = (unsigned short)key;
+                A.sface[slot] = (unsigned short)f;
             }
         }
         SFX_SYNC();
         if (S.cscan_total <= A.cap) break;           // uniform: written before the barrier
-        if (attempt == 0 && W.big_box != nullptr) {
-            A.box = W.big_box;
-            A.face = W.big_face;
-            A.cap = F;
+        if (attempt == 0 && W.sort_g != nullptr && A.cap < SFX_COLL_SORT_G) {
+            // second tier: keys / faces / parts stay in shared memory, the quantised boxes move
+            // to the block's global arrays; third tier: everything in global memory
+            if (S.cscan_total <= A.cap_lean) coll_sort_arrays(A, A.sort_base, A.cap_lean, W.sort_g);
+            else coll_sort_arrays(A, W.sort_g, SFX_COLL_SORT_G);
             SFX_SYNC();
             if (SFX_TID == 0) {
                 S.cscan_total = 0;
@@ -477,74 +627,161 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
             break;
         }
     }
-    SFX_SYNC();
     const int ncand = S.cscan_total < A.cap ? S.cscan_total : A.cap;
-    // candidates by part: the list is sorted by part, mark where each part starts
-    SFX_FOR(p, NP + 1) A.cptr[p] = ncand;
-    SFX_SYNC();
-    SFX_FOR(c, ncand) {
-        const int p = M.face_part[A.face[c]];
-        const int pp = c > 0 ? (int)M.face_part[A.face[c - 1]] : -1;
-        if (p != pp) A.cptr[p] = c;
+    if (SFX_TID == 0 && ncand > S.coll_max_cand) S.coll_max_cand = ncand;
+    // ---- sort by (key, face): bitonic network over the next power of two ----
+    int n2 = 1;
+    while (n2 < ncand) n2 <<= 1;
+    SFX_FOR(i, n2 - ncand) {
+        A.skey[ncand + i] = 0xffff;
+        A.sface[ncand + i] = 0xffff;
     }
     SFX_SYNC();
-    if (SFX_TID == 0)                          // parts without candidates start where the next one does
-        for (int p = NP - 1; p >= 0; --p)
-            if (A.cptr[p] > A.cptr[p + 1]) A.cptr[p] = A.cptr[p + 1];
-    SFX_SYNC();
-    // ---- narrow phase + penalty: each thread gathers for the candidates it owns ----
-    T my_loss = 0;
-    SFX_FOR(c, ncand) {
-        const int fi = A.face[c];
-        const unsigned long long m = A.pmask[M.face_part[fi]];
-        T bi[6], ti[9], gi[9];
-        int idi[3];
-        for (int d = 0; d < 6; ++d) bi[d] = A.box[6 * c + d];
-        bool loaded = false, hit = false;
-        T loss_i = 0;
-        for (int q = 0; q < NP; ++q) {
-            if (!((m >> q) & 1ull)) continue;
-            for (int c2 = A.cptr[q]; c2 < A.cptr[q + 1]; ++c2) {
-                if (!boxes_overlap(bi, A.box + 6 * c2)) continue;
-                if (!loaded) {
-                    face_corners(M, vert, fi, ti, idi);
-                    for (int d = 0; d < 9; ++d) gi[d] = 0;
-                    loaded = true;
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            SFX_FOR(t, n2) {
+                const int u = t ^ j;
+                if (u > t) {
+                    const unsigned short kt = A.skey[t], ku = A.skey[u];
+                    const unsigned short ft = A.sface[t], fu = A.sface[u];
+                    const bool greater = (((unsigned)kt << 16) | ft) > (((unsigned)ku << 16) | fu);
+                    if (greater == ((t & k) == 0)) {
+                        A.skey[t] = ku; A.skey[u] = kt;
+                        A.sface[t] = fu; A.sface[u] = ft;
+                    }
                 }
-                T tj[9];
-                int idj[3];
-                face_corners(M, vert, (int)A.face[c2], tj, idj);
-                // the package compares corner coordinates (shareVertex); so do we
-                bool share = false;
-                for (int a = 0; a < 3; ++a)
-                    for (int b = 0; b < 3; ++b)
-                        share = share || (ti[3 * a] == tj[3 * b] && ti[3 * a + 1] == tj[3 * b + 1] &&
-                                          ti[3 * a + 2] == tj[3 * b + 2]);
-                if (share) continue;
-                const bool lower_first = fi < (int)A.face[c2];
-                if (!(lower_first ? triangles_intersect(ti, tj) : triangles_intersect(tj, ti))) continue;
-                hit = true;
-                pair_terms(ti, tj, sigma, &loss_i, gi);
+            }
+            SFX_SYNC();
+        }
+    // ---- quantised boxes (256 levels over the body's box, rounded outwards) ----
+    SFX_FOR(i, 256) A.hist[i] = 0;
+    SFX_SYNC();
+    SFX_FOR(c, ncand) {
+        const T* fb = W.fbox + (long)A.sface[c] * 6;
+        int q[6];
+        for (int d = 0; d < 3; ++d) {
+            const float lo = (float)((fb[d] - blo[d]) * bsc[d]) - 1e-3f;
+            const float hi = (float)((fb[3 + d] - blo[d]) * bsc[d]) + 1e-3f;
+            int a = (int)floorf(lo), b = (int)ceilf(hi);
+            a = a < 0 ? 0 : (a > 255 ? 255 : a);
+            b = b < 0 ? 0 : (b > 255 ? 255 : b);
+            q[d] = a;
+            q[3 + d] = b;
+        }
+        A.pk[c] = (unsigned long long)((unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16) |
+                                       ((unsigned)M.face_part[A.sface[c]] << 24)) |
+                  ((unsigned long long)((unsigned)q[3] | ((unsigned)q[4] << 8) | ((unsigned)q[5] << 16)) << 32);
+#ifdef __CUDACC__
+        atomicAdd(&A.hist[q[3 + axis] - q[axis]], 1);     // integer counts: order does not matter
+#else
+        A.hist[q[3 + axis] - q[axis]] += 1;
+#endif
+    }
+    SFX_SYNC();
+    // ---- short / long candidates: the smallest extent threshold that leaves at most
+    // SFX_COLL_LARGE_GOAL long ones (long ones scan everything, short ones a window) ----
+    int Eq = 255;
+    {
+        int above = 0;
+        while (Eq > 0 && above + A.hist[Eq] <= SFX_COLL_LARGE_GOAL) {
+            above += A.hist[Eq];
+            Eq -= 1;
+        }
+    }
+    const int E16 = Eq * 257 + 2;            // the same bound on the 65536-level key grid
+    if (SFX_TID == 0) {
+        S.cscan_total = 0;
+        S.cscan_calls = 0;
+    }
+    SFX_SYNC();
+    for (int c0 = 0; c0 < ncand; c0 += SFX_NT) {
+        const int c = c0 + SFX_TID;
+        bool big = false;
+        if (c < ncand) {
+            const unsigned long long e = A.pk[c];
+            big = (int)((pk_hi(e) >> (8 * axis)) & 255u) - (int)((pk_lo(e) >> (8 * axis)) & 255u) > Eq;
+            if (big) A.pk[c] = e | (0x80ull << 24);
+        }
+        const int slot = ordered_slot(big, S);
+        if (big && slot < SFX_COLL_LARGE) A.large[slot] = (unsigned short)c;
+    }
+    SFX_SYNC();
+    const int nlarge = S.cscan_total;       // <= SFX_COLL_LARGE_GOAL by construction
+    // ---- walk + narrow phase, per thread and in chunks ----
+    // Walk: the thread lists, for the candidates it owns (sorted positions tid, tid + NT, ...),
+    // the partners whose part is admissible and whose box overlaps.  A short candidate meets
+    // other short ones inside a window of the sorted order (backwards no further than the
+    // longest short extent E, forwards up to its own maximum; both ends by binary search) and
+    // the long ones through their list; a long candidate scans everything: every ordered pair is
+    // visited exactly once.  The list lives in the thread's own region, (count, faces...) per
+    // candidate; a candidate is only started while half the region is free, and when the region
+    // cannot take the next one the thread works it off before it walks on.
+    // Narrow phase: straight through the list -- separating-axis test, penalty of the own cone
+    // and gradient w.r.t. the own corners, accumulated in registers per candidate (a gather: no
+    // atomics on values, a fixed summation order).
+    const int HC = W.hits_cap;
+    unsigned short* myhits = W.hits_g + (long)SFX_TID * HC;
+    T my_loss = 0;
+    SFX_PROF_END(S, 9, cb);
+    for (int pos0 = SFX_TID; pos0 < ncand;) {
+        int w = 0, pos1 = pos0;
+        SFX_PROF_BEGIN(cw);
+        for (; pos1 < ncand && w + HC / 2 <= HC; pos1 += SFX_NT) {
+            const int head = w++;
+            int cnt = 0;
+            bool full = false;
+            coll_partners(W, A, pos1, ncand, nlarge, axis, E16, [&](int fj) {
+                if (w < HC) { myhits[w++] = (unsigned short)fj; cnt += 1; }
+                else full = true;
+            });
+            // a candidate with more box partners than the region holds is walked again in the
+            // narrow phase, partner by partner
+            if (full) { w = head + 1; cnt = 0xffff; }
+            myhits[head] = (unsigned short)cnt;
+        }
+        SFX_PROF_END(S, 13, cw);
+        SFX_PROF_BEGIN(ch);
+        int r = 0;
+        for (int pos = pos0; pos < pos1; pos += SFX_NT) {
+            const int cnt = myhits[r++];
+            if (cnt == 0) continue;
+            const int fi = A.sface[pos];
+            T ti[9], gi[9], loss_i = 0;
+            int idi[3];
+            face_corners(M, vert, fi, ti, idi);
+            for (int d = 0; d < 9; ++d) gi[d] = 0;
+            bool hit = false;
+            if (cnt == 0xffff) {
+                coll_partners(W, A, pos, ncand, nlarge, axis, E16, [&](int fj) {
+                    coll_pair(M, vert, fi, ti, fj, sigma, &hit, &loss_i, gi);
+                });
+            } else {
+                for (int h = 0; h < cnt; ++h) coll_pair(M, vert, fi, ti, (int)myhits[r++], sigma, &hit, &loss_i, gi);
+            }
+            if (hit) {
+                my_loss += loss_i;
+                for (int d = 0; d < 9; ++d) W.dtri_g[(long)fi * 9 + d] = gi[d];
+#ifdef __CUDACC__
+                atomicOr(&A.hit[fi >> 5], 1u << (fi & 31));
+                for (int a = 0; a < 3; ++a) atomicOr(&A.vtouch[idi[a] >> 5], 1u << (idi[a] & 31));
+#else
+                A.hit[fi >> 5] |= 1u << (fi & 31);
+                for (int a = 0; a < 3; ++a) A.vtouch[idi[a] >> 5] |= 1u << (idi[a] & 31);
+#endif
             }
         }
-        if (hit) {
-            my_loss += loss_i;
-            for (int d = 0; d < 9; ++d) W.dtri_g[(long)fi * 9 + d] = gi[d];
-#ifdef __CUDACC__
-            atomicOr(&A.hit[fi >> 5], 1u << (fi & 31));
-            for (int a = 0; a < 3; ++a) atomicOr(&A.vtouch[idi[a] >> 5], 1u << (idi[a] & 31));
-#else
-            A.hit[fi >> 5] |= 1u << (fi & 31);
-            for (int a = 0; a < 3; ++a) A.vtouch[idi[a] >> 5] |= 1u << (idi[a] & 31);
-#endif
-        }
+        SFX_PROF_END(S, 14, ch);
+        pos0 = pos1;
     }
+    SFX_PROF_BEGIN(cn);
     A.part_loss[SFX_TID] = my_loss;
     {
         const T* pl = A.part_loss;
         const T tot = block_reduce<T>(SFX_NT, [=](int i) { return pl[i]; }, OpAdd<T>(), (T)0, &S.red[9]);
         if (SFX_TID == 0) S.coll_loss = tot;
     }
+    SFX_PROF_END(S, 10, cn);
+    SFX_PROF_BEGIN(cg);
     // ---- per-vertex gradients through the static vertex -> face table; touched list ----
     if (SFX_TID == 0) {
         S.cscan_total = 0;
@@ -568,7 +805,11 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
         if (touched) W.tv_g[slot] = (unsigned short)v;
     }
     SFX_SYNC();
-    if (SFX_TID == 0) S.n_touch = S.cscan_total;
+    if (SFX_TID == 0) {
+        S.n_touch = S.cscan_total;
+        if (S.cscan_total > S.coll_max_touch) S.coll_max_touch = S.cscan_total;
+    }
+    SFX_PROF_END(S, 11, cg);
 #ifdef __CUDACC__
     // the work area goes back to the blend ring, which TMA (async proxy) writes next
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -587,23 +828,21 @@ SFX_FN void coll_skin_adjoint(const ModelView<T>& M, Scratch<T>& S, const CollWS
         T acc = 0;
         for (int t = 0; t < nt; ++t) {
             const int v = W.tv_g[t];
-            const T w = M.Wd[(long)v * SFX_WROW + j];
-            if (w != (T)0) acc += w * W.dvert_g[3 * v + r] * (cc < 3 ? W.vp_g[3 * v + cc] : (T)1);
+            for (int e = M.sk_ptr[v]; e < M.sk_ptr[v + 1]; ++e)
+                if (M.sk_j[e] == j)
+                    acc += M.sk_w[e] * W.dvert_g[3 * v + r] * (cc < 3 ? W.vp_g[3 * v + cc] : (T)1);
         }
         S.dA[i] += acc;
     }
     SFX_SYNC();
     SFX_FOR(t, nt) {
         const int v = W.tv_g[t];
-        const T* w = M.Wd + (long)v * SFX_WROW;
         T R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < SFX_NJ; ++j) {
-            const T wj = w[j];
-            if (wj != (T)0) {
-                const T* A = S.A + 12 * j;
-                for (int r = 0; r < 3; ++r)
-                    for (int k = 0; k < 3; ++k) R[3 * r + k] += wj * A[4 * r + k];
-            }
+        for (int e = M.sk_ptr[v]; e < M.sk_ptr[v + 1]; ++e) {
+            const T wj = M.sk_w[e];
+            const T* A = S.A + 12 * M.sk_j[e];
+            for (int r = 0; r < 3; ++r)
+                for (int k = 0; k < 3; ++k) R[3 * r + k] += wj * A[4 * r + k];
         }
         const T d0 = W.dvert_g[3 * v], d1 = W.dvert_g[3 * v + 1], d2 = W.dvert_g[3 * v + 2];
         for (int k = 0; k < 3; ++k) W.vert_g[3 * t + k] = R[k] * d0 + R[3 + k] * d1 + R[6 + k] * d2;

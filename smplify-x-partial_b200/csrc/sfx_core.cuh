@@ -71,6 +71,9 @@ struct ModelView {
     const T* J0;         // [165]           J_regressor . v_template
     const T* JS;         // [165][32]       J_regressor . shapedirs
     const T* Wd;         // [V][SFX_WROW]   dense skinning weights
+    const int* sk_ptr;            // [V + 1]  the same weights as per-vertex lists (CSR)
+    const unsigned char* sk_j;    // [nnz]    joint
+    const T* sk_w;                // [nnz]    weight
     const T* hand_l;     // [NH][45]
     const T* hand_r;     // [NH][45]
     const T* pose_mean;  // [165]
@@ -98,7 +101,10 @@ struct ModelView {
     int coll_ready, F, n_parts;
     const int* faces;                      // [F][3]
     const int* part_ptr;                   // [n_parts + 1]  faces grouped by body part (CSR)
-    const int* part_faces;                 // [F]            face ids, ascending within a part
+    const int* part_faces;                 // [F]            face ids, along the part's long axis
+    int n_clusters;
+    const int* cl_ptr;                     // [n_clusters + 1] runs of <= 64 consecutive part_faces entries
+    const int* part_cl_ptr;                // [n_parts + 1]  clusters of every part
     const unsigned char* face_part;        // [F]            part of every face
     const unsigned long long* part_allow;  // [SFX_NPART_MAX] bit q of word p: FilterFaces keeps (p, q)
     const int* vf_ptr;                     // [V + 1]        vertex -> incident faces (CSR)
@@ -130,12 +136,13 @@ struct BatchView {
     int* n_passes;       // [B]  blend-matrix passes streamed (1 per forward, 1 per adjoint)
     int* flags;          // [B]
     const int* frame_ids;   // optional indirection (nullptr: block b -> frame b)
-    long long* prof;        // [B][8] cycle counters (builds with -DSFX_CYCLE_PROF only)
+    long long* prof;        // [B][16] cycle counters (builds with -DSFX_CYCLE_PROF only)
     // interpenetration term: global workspace, one slot per block (nullptr until
     // sfx_batch_enable_collisions).  Values: vp[3V] | vert[3V] | dvert[3V] | dtri[9F] | box[6F];
     // indices: tv[V] | face[F]
     T* coll_vals;
     unsigned short* coll_idx;
+    int* coll_stat;         // [B][2] largest candidate / touched-vertex count of a frame's evaluations
     long coll_vals_stride, coll_idx_stride;
 };
 
@@ -177,11 +184,13 @@ struct Scratch {
     T o6[128], do6[128];      // VPoser: 6-D rotation outputs and their gradient
     unsigned char vm1[512], vm2[512]; // VPoser: leaky-ReLU masks of the two hidden layers
     T tl_red[64];             // two-loop recursion: per-lane partial sums (double buffered)
-    long long prof[8];        // cycle counters: 0 eval, 1 two-loop, 2 blend fwd, 3 blend adj, 4 total
+    long long prof[16];       // cycle counters: 0 eval, 1 two-loop, 2 blend fwd, 3 blend adj, 4 total,
+                              // 8 mesh skinning, 9 part boxes + candidates, 10 narrow phase + penalty,
+                              // 11 per-vertex gather, 12 skinning adjoint of touched vertices
     T gq[16];                 // mixture prior: per-component negative log-likelihood
     // interpenetration term: ordered-compaction state, touched-vertex count
     int cscan[2][32];
-    int cscan_total, cscan_calls, coll_overflow, n_touch;
+    int cscan_total, cscan_calls, coll_overflow, n_touch, coll_max_cand, coll_max_touch;
     T coll_loss;
     T loss;
     int dynrow;
@@ -970,7 +979,9 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     SFX_SYNC();
     SFX_PROF_END(S, 2, bf);
     if (coll) {
+        SFX_PROF_BEGIN(cs);
         coll_skin_mesh(M, S, *CW);
+        SFX_PROF_END(S, 8, cs);
         coll_search_and_penalty(M, S, *CW, (T)st.coll_sigma, (T)st.coll_loss_weight);
     }
     // ---- 4. skinning of the support vertices ------------------------------------------
@@ -1108,7 +1119,11 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.dA[i] = acc;
     }
     SFX_SYNC();
-    if (coll && S.n_touch > 0) coll_skin_adjoint(M, S, *CW);
+    if (coll && S.n_touch > 0) {
+        SFX_PROF_BEGIN(ca);
+        coll_skin_adjoint(M, S, *CW);
+        SFX_PROF_END(S, 12, ca);
+    }
     // ---- 8. adjoint of the chain (warp 0) || adjoint of the blendshapes (every warp) -----
     SFX_PROF_BEGIN(ba);
     if (SFX_IS_WARP0) chain_adjoint(M, S);

@@ -66,7 +66,8 @@ __device__ __forceinline__ void load_frame(const BatchView<T>& Bv, int f, Scratc
         S.n_evals = S.n_passes = 0;
         S.n_touch = 0;
         S.coll_overflow = 0;
-        for (int i = 0; i < 8; ++i) S.prof[i] = 0;
+        S.coll_max_cand = S.coll_max_touch = 0;
+        for (int i = 0; i < 16; ++i) S.prof[i] = 0;
     }
     __syncthreads();
 }
@@ -118,6 +119,10 @@ fit_stage_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__
                            Bv.hist_y + (size_t)f * SFX_HIST * SFX_NP_MAX, &flags);
     __syncthreads();
     if (threadIdx.x == 0 && S.coll_overflow) flags |= SFX_FLAG_COLL_OVERFLOW;
+    if (threadIdx.x == 0 && Bv.coll_stat) {
+        Bv.coll_stat[2 * f] = max(Bv.coll_stat[2 * f], S.coll_max_cand);
+        Bv.coll_stat[2 * f + 1] = max(Bv.coll_stat[2 * f + 1], S.coll_max_touch);
+    }
     const int np = Bv.lay.np;
     for (int i = threadIdx.x; i < np; i += blockDim.x) Bv.params[(size_t)f * np + i] = S.x[i];
     if (threadIdx.x == 0) {
@@ -153,6 +158,10 @@ eval_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ Batc
                Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr, S, &ws,
                has_coll ? &CW : nullptr);
     if (threadIdx.x == 0 && S.coll_overflow) Bv.flags[f] |= SFX_FLAG_COLL_OVERFLOW;
+    if (threadIdx.x == 0 && Bv.coll_stat) {
+        Bv.coll_stat[2 * f] = max(Bv.coll_stat[2 * f], S.coll_max_cand);
+        Bv.coll_stat[2 * f + 1] = max(Bv.coll_stat[2 * f + 1], S.coll_max_touch);
+    }
     const int np = Bv.lay.np;
     if (loss_out && threadIdx.x == 0) loss_out[f] = S.loss;
     if (grad_out)
@@ -387,9 +396,13 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
             Bv.n_evals[f] += S.n_evals;
             Bv.n_passes[f] += S.n_passes;
             Bv.flags[f] |= flags | (S.coll_overflow ? SFX_FLAG_COLL_OVERFLOW : 0);
+            if (Bv.coll_stat) {
+                Bv.coll_stat[2 * f] = max(Bv.coll_stat[2 * f], S.coll_max_cand);
+                Bv.coll_stat[2 * f + 1] = max(Bv.coll_stat[2 * f + 1], S.coll_max_touch);
+            }
 #ifdef SFX_CYCLE_PROF
             S.prof[4] += clock64() - _t_total;
-            for (int i = 0; i < 8; ++i) Bv.prof[(size_t)f * 8 + i] = S.prof[i];
+            for (int i = 0; i < 16; ++i) Bv.prof[(size_t)f * 16 + i] = S.prof[i];
 #endif
         }
     }
@@ -424,8 +437,10 @@ struct sfx_model {
     ModelView<double> vd;
     DevBuf PK, vt, J0, JS, Wd, hand_l, hand_r, pose_mean, sv_vid, lmk_bary, dyn_vid, dyn_bary,
         joint_map, inv_ptr, inv_idx, faces, gmm_means, gmm_prec, gmm_logw, vp_w1, vp_b1, vp_w2,
-        vp_b2, vp_w3, vp_b3, part_ptr, part_faces, face_part, part_allow, vf_ptr, vf_idx;
+        vp_b2, vp_w3, vp_b3, part_ptr, part_faces, face_part, part_allow, vf_ptr, vf_idx, sk_ptr,
+        sk_j, sk_w, cl_ptr, part_cl_ptr;
     std::vector<int> faces_host;
+    std::vector<double> vt_host;
     int device = 0;
     int num_sms = 0;
     MeshPlan mesh;        // TMA descriptor of the blend matrix for the tensor-core mesh kernel
@@ -454,7 +469,13 @@ static int upload_model(const sfx_model_desc& d, sfx_model* m, ModelView<T>& vie
     CUDA_TRY(m->inv_ptr.upload(h.inv_ptr));
     CUDA_TRY(m->inv_idx.upload(h.inv_idx));
     CUDA_TRY(m->faces.upload(h.faces));
+    CUDA_TRY(m->sk_ptr.upload(h.sk_ptr));
+    CUDA_TRY(m->sk_j.upload(h.sk_j));
+    CUDA_TRY(m->sk_w.upload(h.sk_w));
+    view.sk_ptr = (const int*)m->sk_ptr.p; view.sk_j = (const unsigned char*)m->sk_j.p;
+    view.sk_w = (const T*)m->sk_w.p;
     m->faces_host = h.faces;
+    m->vt_host.assign(h.vt.begin(), h.vt.end());
     view.PK = (const T*)m->PK.p; view.vt = (const T*)m->vt.p; view.J0 = (const T*)m->J0.p;
     view.JS = (const T*)m->JS.p; view.Wd = (const T*)m->Wd.p;
     view.hand_l = (const T*)m->hand_l.p; view.hand_r = (const T*)m->hand_r.p;
@@ -472,7 +493,7 @@ struct sfx_batch {
     size_t es = 4;        // element size of the batch dtype
     DevBuf params, gt, conf, jw, lowconf, init_mask, cam, reg_pose, hist_s, hist_y, final_loss,
         n_evals, n_passes, flags, Acoef, Ccoef, vposed, go_saved, params_alt, loss_alt, pipe, counter,
-        cam_loss, params_last, prof, coll_vals, coll_idx;
+        cam_loss, params_last, prof, coll_vals, coll_idx, coll_stat;
     bool last_valid = false;
     bool has_reg = false;
     std::vector<unsigned char> stage_host;     // host staging for set_targets
@@ -486,6 +507,7 @@ struct sfx_batch {
         v.reg_pose = has_reg ? (const T*)reg_pose.p : nullptr;
         v.hist_s = (T*)hist_s.p; v.hist_y = (T*)hist_y.p; v.final_loss = (T*)final_loss.p;
         v.coll_vals = (T*)coll_vals.p; v.coll_idx = (unsigned short*)coll_idx.p;
+        v.coll_stat = (int*)coll_stat.p;
         v.coll_vals_stride = coll_vals_per_block(m->V, m->F);
         v.coll_idx_stride = coll_idx_per_block(m->V, m->F);
         v.prof = (long long*)prof.p; v.n_evals = (int*)n_evals.p; v.n_passes = (int*)n_passes.p; v.flags = (int*)flags.p; v.frame_ids = frame_ids;
@@ -594,8 +616,8 @@ int sfx_model_set_collision(sfx_model* m, const int32_t* faces_segm, const int32
     if (!m || !faces_segm || !faces_parents || (n_ign_pairs > 0 && !ign_part_pairs) || n_ign_pairs < 0)
         return fail(SFX_ERR_ARG, "bad argument");
     HostCollision c;
-    std::string e = prepare_collision(m->V, m->F, m->faces_host.data(), faces_segm, faces_parents,
-                                      ign_part_pairs, n_ign_pairs, c);
+    std::string e = prepare_collision(m->V, m->F, m->faces_host.data(), m->vt_host.data(), faces_segm,
+                                      faces_parents, ign_part_pairs, n_ign_pairs, c);
     if (!e.empty()) return fail(SFX_ERR_ARG, e);
     CUDA_TRY(m->part_ptr.upload(c.part_ptr));
     CUDA_TRY(m->part_faces.upload(c.part_faces));
@@ -603,7 +625,11 @@ int sfx_model_set_collision(sfx_model* m, const int32_t* faces_segm, const int32
     CUDA_TRY(m->part_allow.upload(c.part_allow));
     CUDA_TRY(m->vf_ptr.upload(c.vf_ptr));
     CUDA_TRY(m->vf_idx.upload(c.vf_idx));
+    CUDA_TRY(m->cl_ptr.upload(c.cl_ptr));
+    CUDA_TRY(m->part_cl_ptr.upload(c.part_cl_ptr));
     auto fill = [&](auto& v) {
+        v.n_clusters = c.n_clusters; v.cl_ptr = (const int*)m->cl_ptr.p;
+        v.part_cl_ptr = (const int*)m->part_cl_ptr.p;
         v.coll_ready = 1; v.F = m->F; v.n_parts = c.n_parts; v.faces = (const int*)m->faces.p;
         v.part_ptr = (const int*)m->part_ptr.p; v.part_faces = (const int*)m->part_faces.p;
         v.face_part = (const unsigned char*)m->face_part.p;
@@ -622,8 +648,12 @@ int sfx_batch_enable_collisions(sfx_batch* b) {
     // one slot per block; no launch uses more blocks than frames
     CUDA_TRY(b->coll_vals.alloc((size_t)b->B * coll_vals_per_block(b->m->V, b->m->F) * b->es));
     CUDA_TRY(b->coll_idx.alloc((size_t)b->B * coll_idx_per_block(b->m->V, b->m->F) * sizeof(unsigned short)));
+    CUDA_TRY(b->coll_stat.alloc((size_t)b->B * 2 * sizeof(int)));
+    CUDA_TRY(cudaMemset(b->coll_stat.p, 0, b->coll_stat.bytes));
     return SFX_OK;
 }
+
+int32_t* sfx_batch_coll_stat_dev(sfx_batch* b) { return b ? (int32_t*)b->coll_stat.p : nullptr; }
 
 int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batch** out) {
     if (!m || !out || B < 1) return fail(SFX_ERR_ARG, "bad argument");
@@ -666,7 +696,7 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     ALLOC(pipe, sizeof(SfxPipeline));
     ALLOC(counter, 64);
     ALLOC(cam_loss, (size_t)B * es);
-    ALLOC(prof, (size_t)B * 8 * sizeof(long long));
+    ALLOC(prof, (size_t)B * 16 * sizeof(long long));
     ALLOC(params_last, (size_t)B * b->lay.np * es);
 #undef ALLOC
     *out = b;
@@ -752,6 +782,7 @@ int sfx_batch_reset_counters(sfx_batch* b, void* stream) {
     CUDA_TRY(cudaMemsetAsync(b->n_evals.p, 0, (size_t)b->B * sizeof(int), (cudaStream_t)stream));
     CUDA_TRY(cudaMemsetAsync(b->n_passes.p, 0, (size_t)b->B * sizeof(int), (cudaStream_t)stream));
     CUDA_TRY(cudaMemsetAsync(b->flags.p, 0, (size_t)b->B * sizeof(int), (cudaStream_t)stream));
+    if (b->coll_stat.p) CUDA_TRY(cudaMemsetAsync(b->coll_stat.p, 0, b->coll_stat.bytes, (cudaStream_t)stream));
     return SFX_OK;
 }
 

@@ -14,7 +14,9 @@ template <typename T>
 struct HostModel {
     int V = 0, F = 0, NS = 0, NB = 0, NE = 0, NH = 0, K = 0, NJOUT = 0, use_contour = 0;
     std::vector<T> PK, vt, J0, JS, Wd, hand_l, hand_r, pose_mean, lmk_bary, dyn_bary;
-    std::vector<int> sv_vid, dyn_vid, joint_map, inv_ptr, inv_idx, faces;
+    std::vector<int> sv_vid, dyn_vid, joint_map, inv_ptr, inv_idx, faces, sk_ptr;
+    std::vector<unsigned char> sk_j;
+    std::vector<T> sk_w;
     int parents[SFX_NJ], order[SFX_NJ], level_off[16], nlev = 0;
     int child_off[SFX_NJ + 1], child_idx[SFX_NJ], neck[8], n_neck = 0;
 
@@ -25,7 +27,8 @@ struct HostModel {
         m.vp_ready = 0; m.vp_w1 = m.vp_b1 = m.vp_w2 = m.vp_b2 = m.vp_w3 = m.vp_b3 = nullptr;
         m.gmm_M = 0; m.gmm_D = 0; m.gmm_means = nullptr; m.gmm_prec = nullptr; m.gmm_logw = nullptr;
         m.coll_ready = 0; m.F = F; m.n_parts = 0; m.faces = nullptr; m.part_ptr = nullptr;
-        m.part_faces = nullptr; m.face_part = nullptr; m.part_allow = nullptr; m.vf_ptr = nullptr;
+        m.part_faces = nullptr; m.n_clusters = 0; m.cl_ptr = nullptr; m.part_cl_ptr = nullptr;
+        m.face_part = nullptr; m.part_allow = nullptr; m.vf_ptr = nullptr;
         m.vf_idx = nullptr;
         for (int i = 0; i < SFX_NJ; ++i) { m.parents[i] = parents[i]; m.order[i] = order[i]; }
         for (int i = 0; i < 16; ++i) m.level_off[i] = level_off[i];
@@ -41,6 +44,7 @@ struct HostModel {
         m.sv_vid = sv_vid.data(); m.lmk_bary = lmk_bary.data(); m.dyn_vid = dyn_vid.data();
         m.dyn_bary = dyn_bary.data(); m.joint_map = joint_map.data();
         m.inv_ptr = inv_ptr.data(); m.inv_idx = inv_idx.data();
+        m.sk_ptr = sk_ptr.data(); m.sk_j = sk_j.data(); m.sk_w = sk_w.data();
         return m;
     }
 };
@@ -132,6 +136,17 @@ std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
     h.Wd.assign((size_t)V * SFX_WROW, (T)0);
     for (long v = 0; v < V; ++v)
         for (int j = 0; j < SFX_NJ; ++j) h.Wd[v * SFX_WROW + j] = (T)d.lbs_weights[v * SFX_NJ + j];
+    h.sk_ptr.assign(V + 1, 0);
+    h.sk_j.clear();
+    h.sk_w.clear();
+    for (long v = 0; v < V; ++v) {
+        for (int j = 0; j < SFX_NJ; ++j)
+            if (d.lbs_weights[v * SFX_NJ + j] != 0.f) {
+                h.sk_j.push_back((unsigned char)j);
+                h.sk_w.push_back((T)d.lbs_weights[v * SFX_NJ + j]);
+            }
+        h.sk_ptr[v + 1] = (int)h.sk_j.size();
+    }
     // --- hands ---
     h.hand_l.resize((size_t)h.NH * 45);
     h.hand_r.resize((size_t)h.NH * 45);
@@ -199,13 +214,17 @@ std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
 // reads at fit_single_frame.py:317-328 (smplx_parts_segm.pkl: 'segm' = body part of every face,
 // 'parents' = kinematic parent of that part) and its ign_part_pairs option.
 struct HostCollision {
-    int n_parts = 0;
-    std::vector<int> part_ptr, part_faces, vf_ptr, vf_idx;
+    int n_parts = 0, n_clusters = 0;
+    std::vector<int> part_ptr, part_faces, vf_ptr, vf_idx, cl_ptr, part_cl_ptr;
     std::vector<unsigned char> face_part;
     std::vector<unsigned long long> part_allow;
 };
 
-inline std::string prepare_collision(int V, int F, const int* faces, const int32_t* segm,
+#define SFX_CLUSTER_FACES 64      // faces per cluster of the broad phase
+#define SFX_NCLUSTER_MAX 512
+
+template <typename TV>
+inline std::string prepare_collision(int V, int F, const int* faces, const TV* vt, const int32_t* segm,
                                      const int32_t* parents, const int32_t* ign_pairs, int n_ign,
                                      HostCollision& c) {
     if (!faces || !segm || !parents || F < 1) return "collision tables: missing array";
@@ -243,6 +262,42 @@ inline std::string prepare_collision(int V, int F, const int* faces, const int32
         std::vector<int> pos(c.part_ptr.begin(), c.part_ptr.end() - 1);
         for (int f = 0; f < F; ++f) c.part_faces[pos[segm[f]]++] = f;
     }
+    // Clusters: inside a part the faces are ordered along the longest side of the part's
+    // template box and cut into runs of SFX_CLUSTER_FACES -- a static two-level hierarchy whose
+    // boxes are refitted at every evaluation (the broad phase of sfx_collide.cuh).
+    c.cl_ptr.clear();
+    c.part_cl_ptr.assign(np + 1, 0);
+    for (int p = 0; p < np; ++p) {
+        const int a = c.part_ptr[p], b = c.part_ptr[p + 1];
+        if (b > a) {
+            double lo[3] = {1e30, 1e30, 1e30}, hi[3] = {-1e30, -1e30, -1e30};
+            std::vector<std::pair<double, int>> key(b - a);
+            std::vector<double> cen((size_t)(b - a) * 3);
+            for (int k = a; k < b; ++k) {
+                const int f = c.part_faces[k];
+                for (int d = 0; d < 3; ++d) {
+                    double s = 0;
+                    for (int e = 0; e < 3; ++e) s += (double)vt[3L * faces[3 * f + e] + d];
+                    cen[(size_t)(k - a) * 3 + d] = s / 3;
+                    lo[d] = std::min(lo[d], s / 3);
+                    hi[d] = std::max(hi[d], s / 3);
+                }
+            }
+            int ax = 0;
+            for (int d = 1; d < 3; ++d)
+                if (hi[d] - lo[d] > hi[ax] - lo[ax]) ax = d;
+            for (int k = a; k < b; ++k) key[k - a] = {cen[(size_t)(k - a) * 3 + ax], c.part_faces[k]};
+            std::sort(key.begin(), key.end());
+            for (int k = a; k < b; ++k) c.part_faces[k] = key[k - a].second;
+            for (int k = a; k < b; k += SFX_CLUSTER_FACES) c.cl_ptr.push_back(k);
+        }
+        c.part_cl_ptr[p + 1] = (int)c.cl_ptr.size();
+    }
+    c.n_clusters = (int)c.cl_ptr.size();
+    c.cl_ptr.push_back(F);
+    if (c.n_clusters > SFX_NCLUSTER_MAX) return "collision tables: too many face clusters";
+    // cluster boundaries must not cross parts: the sentinel of a part's last cluster is the
+    // next part's first face, which is what cl_ptr holds by construction
     c.vf_ptr.assign(V + 1, 0);
     for (long i = 0; i < 3L * F; ++i) c.vf_ptr[faces[i] + 1]++;
     for (int v = 0; v < V; ++v) c.vf_ptr[v + 1] += c.vf_ptr[v];

@@ -283,6 +283,14 @@ class FrameBatch(object):
         ptr = self.lib.sfx_batch_flags_dev(self.h)
         return _wrap(ptr, (self.B,), torch.int32, self.model.device, self)
 
+    def coll_stats(self):
+        """[B, 2] int32: largest candidate-face / touched-vertex count of each frame's
+        evaluations of the interpenetration term (None when the term is not enabled)."""
+        ptr = self.lib.sfx_batch_coll_stat_dev(self.h)
+        if not ptr:
+            return None
+        return _wrap(ptr, (self.B, 2), torch.int32, self.model.device, self)
+
     def reset_counters(self):
         with torch.cuda.device(self.model.device):
             N.check(self.lib, self.lib.sfx_batch_reset_counters(self.h, _stream()))

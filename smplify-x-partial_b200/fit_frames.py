@@ -105,6 +105,7 @@ def make_stages(cfg, L):
     weights = stage_weights(cfg)
     pk = body_pose_prior_kind(cfg)
     stages = []
+    coll_on = bool(cfg.get('interpenetration', False))      # fitting.py:439
     for i, w in enumerate(weights):
         stages.append(N.make_stage(
             L, N.BODY_STAGE_BLOCKS, loss_kind=N.LOSS_SMPLIFY, pprior_kind=pk, stage_index=i,
@@ -114,7 +115,9 @@ def make_stages(cfg, L):
             bending_prior_weight=3.17 * w['body_pose_weight'],
             hand_prior_weight=w['hand_prior_weight'], expr_prior_weight=w['expr_prior_weight'],
             jaw_prior_weight=w['jaw_prior_weight'], hand_joint_weight=w['hand_weight'],
-            face_joint_weight=w['face_weight'], **okw))
+            face_joint_weight=w['face_weight'],
+            coll_loss_weight=w['coll_loss_weight'] if coll_on else 0.0,
+            coll_sigma=cfg.get('df_cone_height', 0.5), **okw))
     return cam, stages
 
 
@@ -228,7 +231,7 @@ class FitPlan(object):
     the second (flipped) orientation.  Pure numpy; built without touching the device."""
 
     def __init__(self, L, K, keypoints, H, W, cfg, expose=None, pixie=None, body_mean_pose=None,
-                 np_dtype=np.float32, body_pose_prior=None, vposer=None):
+                 np_dtype=np.float32, body_pose_prior=None, vposer=None, part_segm=None):
         B = keypoints.shape[0]
         self.B, self.K, self.L, self.cfg = B, K, L, cfg
         npd = self.np_dtype = np_dtype
@@ -238,9 +241,23 @@ class FitPlan(object):
         fl = cfg.get('focal_length')
         self.focal = focal = (np.sqrt(W ** 2 + H ** 2) if fl is None
                               else np.broadcast_to(float(fl), (B,)))
+        # interpenetration term (fit_single_frame.py:296-328)
+        self.collision = None
         if cfg.get('interpenetration', False) and any(
                 w['coll_loss_weight'] > 0 for w in stage_weights(cfg)):
-            raise NotImplementedError('interpenetration term: not built yet (SURVEY.md 8a, a16)')
+            from . import mesh_intersection as MI
+            _, _, ff = MI.create_term(
+                True, max_collisions=cfg.get('max_collisions', 8),
+                df_cone_height=cfg.get('df_cone_height', 0.5),
+                point2plane=cfg.get('point2plane', False),
+                penalize_outside=cfg.get('penalize_outside', True),
+                part_segm_fn=cfg.get('part_segm_fn', ''),
+                ign_part_pairs=cfg.get('ign_part_pairs'), part_segm=part_segm)
+            if ff is None:
+                raise NotImplementedError(
+                    'interpenetration on the device needs the face segmentation: pass '
+                    'part_segm_fn (reference README.md:55) or part_segm=')
+            self.collision = ff
         self.cam_stage, self.stages = make_stages(cfg, L)
         self.jw, self.lowconf, self.init_mask = keypoint_masks(
             keypoints, cfg, base_joint_weights(cfg, K))
@@ -312,6 +329,10 @@ def upload(batch, plan):
         batch.model.set_vposer(plan.vposer.weights)
     if getattr(plan.body_pose_prior, 'kind', '') == 'gmm':
         batch.model.set_gmm(plan.body_pose_prior)
+    if plan.collision is not None:
+        ff = plan.collision
+        batch.model.set_collision(ff.faces_segm, ff.faces_parents, ff.ign_part_pairs)
+        batch.enable_collisions()
     n = batch.set_targets(plan.keypoints, plan.jw, plan.lowconf, plan.init_mask, plan.cam, plan.reg)
     n += batch.set_params(plan.x0)
     if plan.need_guess:
@@ -425,7 +446,7 @@ def download(batch, plan, cam_loss, verts, joints):
 
 
 def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_verts=True,
-               body_mean_pose=None, body_pose_prior=None, vposer=None):
+               body_mean_pose=None, body_pose_prior=None, vposer=None, part_segm=None):
     """Fits every frame of ``batch`` (an ``engine.FrameBatch``).
 
     keypoints [B,K,3] (x, y, confidence) in the reference's row order; ``H``, ``W`` scalars or
@@ -433,7 +454,7 @@ def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_vert
     reference's YAML files); ``expose`` / ``pixie`` lists of per-frame regression results.
     """
     plan = FitPlan(batch.L, batch.model.K, np.asarray(keypoints), H, W, cfg, expose, pixie,
-                   body_mean_pose, batch.model.np_dtype, body_pose_prior, vposer)
+                   body_mean_pose, batch.model.np_dtype, body_pose_prior, vposer, part_segm)
     h2d = upload(batch, plan)
     cam_loss, verts, joints, launches = run(batch, plan, return_verts)
     out = download(batch, plan, cam_loss, verts, joints)

@@ -75,8 +75,12 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
                regression_prior=regression_prior, init_joints_idxs=list(init_joints_idxs),
                confidence_threshold=kwargs.get('confidence_threshold', 0))
     weights = FF.stage_weights(cfg)                      # validation + defaults (:136-207)
-    if interpenetration and any(w['coll_loss_weight'] > 0 for w in weights):
-        raise NotImplementedError('interpenetration term is not built yet (SURVEY.md a16)')
+    # search tree, penetration penalty and face filter (:296-328)
+    from . import mesh_intersection as MI
+    search_tree, pen_distance, filter_faces = MI.create_term(
+        interpenetration, max_collisions=max_collisions, df_cone_height=df_cone_height,
+        point2plane=point2plane, penalize_outside=penalize_outside, part_segm_fn=part_segm_fn,
+        ign_part_pairs=ign_part_pairs, part_segm=kwargs.get('part_segm'))
     from . import utils as U
     nb = U.NUM_BODY_KEYPOINTS[format]
 
@@ -144,7 +148,8 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
         use_hands=use_hands, vposer=vposer, pose_embedding=pose_embedding,
         body_pose_prior=body_pose_prior, shape_prior=shape_prior, angle_prior=angle_prior,
         expr_prior=expr_prior, left_hand_prior=left_hand_prior, right_hand_prior=right_hand_prior,
-        jaw_prior=jaw_prior, interpenetration=interpenetration, dtype=dtype,
+        jaw_prior=jaw_prior, interpenetration=interpenetration, search_tree=search_tree,
+        pen_distance=pen_distance, tri_filtering_module=filter_faces, dtype=dtype,
         regression_pose=pose_embedding.clone().detach() if regression_prior else None,
         num_stages=len(weights)).to(device=dev)
 

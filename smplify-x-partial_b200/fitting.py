@@ -93,6 +93,8 @@ class SMPLifyLoss(_WeightedLoss):
         self.left_hand_prior, self.right_hand_prior = left_hand_prior, right_hand_prior
         self.expr_prior, self.jaw_prior = expr_prior, jaw_prior
         self.interpenetration = interpenetration
+        self.search_tree, self.pen_distance = search_tree, pen_distance
+        self.tri_filtering_module = tri_filtering_module
         self.vposer = vposer
         self.regression_pose = regression_pose
         self.num_stages = num_stages
@@ -111,8 +113,16 @@ class SMPLifyLoss(_WeightedLoss):
 
     def stage_kwargs(self, use_vposer, stage):
         """Weights + pose-prior branch of forward() (fitting.py:389-401) as SfxStage fields."""
+        coll_w, coll_sigma = 0.0, 0.5
         if self.interpenetration and _as_float(getattr(self, 'coll_loss_weight', 0.0)) > 0:
-            raise NotImplementedError('interpenetration term is not built yet')
+            # fitting.py:439-455; the device search needs the face segmentation (it is its
+            # broad phase), i.e. the reference's --part_segm_fn option
+            if self.pen_distance is None or self.tri_filtering_module is None:
+                raise NotImplementedError(
+                    'interpenetration on the device needs pen_distance and tri_filtering_module '
+                    '(mesh_intersection.create_term with part_segm_fn, reference README.md:55)')
+            coll_w = _as_float(self.coll_loss_weight)
+            coll_sigma = float(self.pen_distance.sigma)
         if use_vposer:
             pk = N.PPRIOR_LATENT
         elif self.regression_pose is not None:
@@ -136,7 +146,7 @@ class SMPLifyLoss(_WeightedLoss):
             bending_prior_weight=_as_float(self.bending_prior_weight),
             hand_prior_weight=_as_float(getattr(self, 'hand_prior_weight', None), 0.0),
             expr_prior_weight=_as_float(getattr(self, 'expr_prior_weight', None), 0.0),
-            jaw_prior_weight=jaw)
+            jaw_prior_weight=jaw, coll_loss_weight=coll_w, coll_sigma=coll_sigma)
 
     def forward(self, body_model_output, camera, gt_joints, joints_conf, body_model_faces=None,
                 joint_weights=None, use_vposer=False, pose_embedding=None, stage=0, **kwargs):
@@ -245,6 +255,10 @@ class _FitBundle(object):
             reg = loss.regression_pose.to(device=dev, dtype=dt).reshape(B, -1).contiguous()
         if getattr(getattr(loss, 'body_pose_prior', None), 'kind', '') == 'gmm':
             bm.engine_model.set_gmm(loss.body_pose_prior)
+        ff = getattr(loss, 'tri_filtering_module', None)
+        if getattr(loss, 'interpenetration', False) and ff is not None:
+            bm.engine_model.set_collision(ff.faces_segm, ff.faces_parents, ff.ign_part_pairs)
+            batch.enable_collisions()
         self._keep = (gt, conf, jw, lowconf, init_mask, camrow, reg)
         batch.set_targets_dev(gt, conf, jw, lowconf, init_mask, camrow, reg)
 

@@ -434,11 +434,24 @@ def make_smplx_like(seed=0, dtype=np.float32, full_shape_space=True):
 _CACHE = {}
 
 
-def cached_smplx_like(seed=0):
-    """Process-local cache (generation takes a few seconds)."""
-    if seed not in _CACHE:
-        _CACHE[seed] = make_smplx_like(seed=seed, full_shape_space=False)
-    return _CACHE[seed]
+def cached_smplx_like(seed=0, pose_corrective_scale=1.0):
+    """Process-local cache (generation takes a few seconds).
+
+    ``pose_corrective_scale`` rescales ``posedirs``.  The pose correctives of this module are
+    white noise per vertex (up to ~2 cm at a strongly bent joint, the size of a triangle): fine
+    for the keypoint terms, but it turns the surface around bent joints into a soup of crossing
+    triangles, tens of thousands of pairs, which no real body mesh shows.  The interpenetration
+    workload (BASELINE config 4) therefore uses 0.1 (millimetre-level correctives)."""
+    key = (seed, float(pose_corrective_scale))
+    if key not in _CACHE:
+        if (seed, 1.0) not in _CACHE:
+            _CACHE[(seed, 1.0)] = make_smplx_like(seed=seed, full_shape_space=False)
+        if key not in _CACHE:
+            m = dict(_CACHE[(seed, 1.0)])
+            m['posedirs'] = (m['posedirs'] * np.float32(pose_corrective_scale)).astype(
+                m['posedirs'].dtype)
+            _CACHE[key] = m
+    return _CACHE[key]
 
 
 def parts_segm_like(model_data):

@@ -10,6 +10,7 @@
 static std::vector<double> g_trace;
 #define SFX_TRACE(v) g_trace.push_back(v)
 static std::vector<double> g_steps;
+static int g_hits_cap = 0;      // 0: the device's region size
 #define SFX_TRACE_STEP(t) g_steps.push_back(t)
 #include "../../smplify-x-partial_b200/csrc/sfx_model_prep.h"
 
@@ -54,19 +55,24 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
     std::vector<T> hs((size_t)SFX_HIST * SFX_NP_MAX), hy((size_t)SFX_HIST * SFX_NP_MAX);
     CollWS<T> W;
     std::vector<T> vp_g, vert_g, dvert_g, dtri_g, big_box;
-    std::vector<unsigned short> big_face, tv_g;
-    std::vector<unsigned char> work;
+    std::vector<unsigned short> tv_g, hits_g;
+    std::vector<unsigned char> work, sort_g;
     const CollWS<T>* Wp = nullptr;
     if (sm.has_coll) {
         M.coll_ready = 1; M.n_parts = sm.coll.n_parts; M.faces = sm.h.faces.data();
         M.part_ptr = sm.coll.part_ptr.data(); M.part_faces = sm.coll.part_faces.data();
         M.face_part = sm.coll.face_part.data(); M.part_allow = sm.coll.part_allow.data();
         M.vf_ptr = sm.coll.vf_ptr.data(); M.vf_idx = sm.coll.vf_idx.data();
+        M.n_clusters = sm.coll.n_clusters; M.cl_ptr = sm.coll.cl_ptr.data();
+        M.part_cl_ptr = sm.coll.part_cl_ptr.data();
         vp_g.assign((size_t)3 * M.V, 0); vert_g.assign((size_t)3 * M.V, 0);
         dvert_g.assign((size_t)3 * M.V, 0); dtri_g.assign((size_t)9 * M.F, 0);
         work.assign(sm.coll_work_bytes, 0);
-        big_box.assign((size_t)6 * M.F, 0); big_face.assign(M.F, 0); tv_g.assign(M.V, 0);
-        W.big_box = big_box.data(); W.big_face = big_face.data(); W.tv_g = tv_g.data();
+        big_box.assign((size_t)6 * M.F, 0); sort_g.assign((size_t)SFX_COLL_ENTRY * SFX_COLL_SORT_G, 0); tv_g.assign(M.V, 0);
+        W.fbox = big_box.data(); W.sort_g = sort_g.data(); W.tv_g = tv_g.data();
+        W.hits_cap = g_hits_cap > 0 ? g_hits_cap : SFX_COLL_HITS;
+        hits_g.assign((size_t)W.hits_cap, 0);         // one thread on the host: many chunks
+        W.hits_g = hits_g.data();
         W.vp_g = vp_g.data(); W.vert_g = vert_g.data(); W.dvert_g = dvert_g.data();
         W.dtri_g = dtri_g.data(); W.work = work.data(); W.work_bytes = sm.coll_work_bytes;
         Wp = &W;
@@ -124,10 +130,10 @@ int hs_set_collision(void* p, const int32_t* segm, const int32_t* parents, const
     SimHandle* h = (SimHandle*)p;
     std::string e;
     if (h->use_double) {
-        e = prepare_collision(h->d.h.V, h->d.h.F, h->d.h.faces.data(), segm, parents, ign, n_ign, h->d.coll);
+        e = prepare_collision(h->d.h.V, h->d.h.F, h->d.h.faces.data(), h->d.h.vt.data(), segm, parents, ign, n_ign, h->d.coll);
         h->d.has_coll = e.empty(); h->d.coll_work_bytes = work_bytes;
     } else {
-        e = prepare_collision(h->f.h.V, h->f.h.F, h->f.h.faces.data(), segm, parents, ign, n_ign, h->f.coll);
+        e = prepare_collision(h->f.h.V, h->f.h.F, h->f.h.faces.data(), h->f.h.vt.data(), segm, parents, ign, n_ign, h->f.coll);
         h->f.has_coll = e.empty(); h->f.coll_work_bytes = work_bytes;
     }
     if (!e.empty()) { std::strncpy(err, e.c_str(), errlen - 1); return -1; }
@@ -138,6 +144,7 @@ int hs_triangles_intersect(const double* t1, const double* t2) { return triangle
 void hs_pair_terms(const double* ti, const double* tj, double sigma, double* loss, double* gi) {
     pair_terms(ti, tj, sigma, loss, gi);
 }
+void hs_set_hits_cap(int n) { g_hits_cap = n; }
 int hs_last_touch(void* p) { SimHandle* h = (SimHandle*)p; return h->use_double ? h->d.last_touch : h->f.last_touch; }
 int hs_trace(double* out, int cap) {
     int n = (int)g_trace.size();

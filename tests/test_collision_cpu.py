@@ -179,7 +179,7 @@ def test_candidate_overflow_falls_back_to_the_global_area():
     ev = Cm.golden('ref_eval_coll_f64.npz')
     I = Cm.coll_case_inputs(ev, 'coll')
     out = []
-    for wb in (1 << 20, 20000):
+    for wb in (1 << 20, 48000):
         hs = HostSim(Cm.model_data(), Cm.joint_map(), use_double=True, **Cm.MODEL_KW)
         segm, par, ign = Cm.coll_segmentation()
         hs.set_collision(segm, par, [[int(x) for x in p.split(',')] for p in ign], work_bytes=wb)
@@ -188,6 +188,24 @@ def test_candidate_overflow_falls_back_to_the_global_area():
         assert r['flags'] == 0
         out.append(r)
     assert out[0]['loss'] == out[1]['loss'] and np.array_equal(out[0]['grad'], out[1]['grad'])
+
+
+def test_tiny_hit_regions_take_the_inline_path():
+    """With a hit region of 16 entries most candidates overflow it and are walked again partner
+    by partner in the narrow phase: same result, no overflow flag."""
+    ev = Cm.golden('ref_eval_coll_f64.npz')
+    I = Cm.coll_case_inputs(ev, 'coll')
+    hs = _hs('f64')
+    run = lambda: hs.eval(I['stage'], I['x'], I['gt'], I['conf'], I['jw'], I['cam'], I['lowconf'],
+                          I['init_mask'], None)
+    a = run()
+    hs.lib.hs_set_hits_cap(16)
+    try:
+        b = run()
+    finally:
+        hs.lib.hs_set_hits_cap(0)
+    assert a['flags'] == 0 and b['flags'] == 0
+    assert a['loss'] == b['loss'] and np.array_equal(a['grad'], b['grad'])
 
 
 def test_gradient_of_the_term_against_finite_differences():

@@ -93,3 +93,47 @@ def test_short_fit_with_interpenetration_reduces_penalty():
     assert int(batch.flags().cpu().numpy().max()) == 0
     x = batch.get_params()
     assert np.array_equal(x[0], x[1]) and np.array_equal(x[0], x[2])
+
+
+def test_fit_frames_with_interpenetration_pipeline_equals_staged():
+    """The whole multi-stage flow with the term on (coll_loss_weights 0 / 0.1 / 1.0 as in the
+    shipped yaml) through the batched driver: one persistent launch == one launch per stage,
+    bit for bit; no flags; the term lowers the penalty left at the end of the fit."""
+    import json
+    from smplifyx_b200 import engine, fit_frames as FF, synthetic
+    inp = Cm.golden('demo_inputs.npz')
+    ref = Cm.golden('ref_fit_02.npz')
+    cfg = json.loads(str(ref['cfg_json']))
+    md = Cm.model_data()
+    segm, par, ign = Cm.coll_segmentation()
+    cfg.update(interpenetration=True, coll_loss_weights=[0.0, 0.1, 1.0], df_cone_height=1e-4,
+               max_collisions=128, penalize_outside=True, point2plane=False, ign_part_pairs=ign,
+               maxiters=8)
+    part_segm = {'segm': segm, 'parents': par}
+    model = engine.Model(md, Cm.joint_map(), dtype=torch.float32, **Cm.MODEL_KW)
+    frames = ['02_cropped', '18_cropped']
+    data = []
+    for fr in frames:
+        expose = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr + '/expose/')}
+        pixie = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr + '/pixie/')}
+        H, W = [int(v) for v in inp[fr + '/HW']]
+        data.append((inp[fr + '/keypoints'], H, W, expose, pixie))
+    kp = np.stack([d[0] for d in data])
+    res = []
+    for runner in (FF.run, FF.run_staged):
+        batch = engine.FrameBatch(model, 2)
+        plan = FF.FitPlan(batch.L, model.K, kp, [d[1] for d in data], [d[2] for d in data], cfg,
+                          [d[3] for d in data], [d[4] for d in data], None, np.float32,
+                          part_segm=part_segm)
+        assert plan.stages[2].coll_loss_weight == 1.0 and plan.stages[0].coll_loss_weight == 0.0
+        FF.upload(batch, plan)
+        cam_loss, verts, joints, _ = runner(batch, plan, True)
+        res.append(FF.download(batch, plan, cam_loss, verts, joints))
+    a, b = res
+    assert a.flags.max() == 0 and np.all(np.isfinite(a.params))
+    assert np.array_equal(a.params, b.params) and np.array_equal(a.loss, b.loss)
+    assert np.array_equal(a.n_evals, b.n_evals) and np.array_equal(a.vertices, b.vertices)
+    # without part_segm the device path refuses instead of silently dropping the term
+    with pytest.raises(NotImplementedError, match='segmentation'):
+        FF.FitPlan(batch.L, model.K, kp, 600, 800, cfg, [d[3] for d in data],
+                   [d[4] for d in data], None, np.float32)
