@@ -53,7 +53,7 @@ def bench_cfg(interpenetration=False):
         cfg.update(interpenetration=True, coll_loss_weights=[0.0, 0.1, 1.0], df_cone_height=1e-4,
                    max_collisions=128, penalize_outside=True, point2plane=False,
                    ign_part_pairs=["9,16", "9,17", "6,16", "6,17", "1,2", "12,22"] +
-                   synthetic.sibling_part_pairs(md))
+                   synthetic.sibling_part_pairs(md) + synthetic.REST_POSE_TOUCHING_PART_PAIRS)
     return cfg
 
 

@@ -412,14 +412,15 @@ SFX_FN bool pk_overlap(unsigned long long a, unsigned long long b) {
 #endif
 }
 
-// Partners of the candidate at sorted position pos: visit(face) for every other candidate whose
-// part is admissible and whose box overlaps, each exactly once.  A short candidate meets other
-// short ones inside a window of the sorted order (backwards no further than the longest short
-// extent E, forwards up to its own maximum; both ends by binary search) and the long ones
-// through their list; a long candidate scans everything.
+// Partners of the candidate at sorted position pos, enumerated by one warp: every lane calls
+// visit(face, ok) once per step of the walk, ok marking a candidate whose part is admissible and
+// whose (quantised) box overlaps; each partner shows up exactly once, in sorted order.  A short
+// candidate meets other short ones inside a window of the sorted order (backwards no further than
+// the longest short extent, forwards up to its own maximum; both ends by binary search) and the
+// long ones through their list; a long candidate scans everything.
 template <typename T, typename VISIT>
-SFX_FN void coll_partners(const CollWS<T>& W, const CollArea<T>& A, int pos, int ncand, int nlarge,
-                          int axis, int E16, VISIT visit) {
+SFX_FN void coll_partners(const CollArea<T>& A, int pos, int ncand, int nlarge, int axis, int E16,
+                          int lane, int LW, VISIT visit) {
     const unsigned long long me = A.pk[pos];
     const unsigned long long allow = A.pmask[(pk_lo(me) >> 24) & 0x7f];
     const bool me_long = (pk_lo(me) >> 31) & 1u;
@@ -435,17 +436,22 @@ SFX_FN void coll_partners(const CollWS<T>& W, const CollArea<T>& A, int pos, int
         while (a < b) { const int m = (a + b) >> 1; if ((int)A.skey[m] <= kmax) a = m + 1; else b = m; }
         hi = a;
     }
-    const int nsteps = (hi - lo) + (me_long ? 0 : nlarge);
-    for (int s = 0; s < nsteps; ++s) {
-        const int b = s < hi - lo ? lo + s : (int)A.large[s - (hi - lo)];
-        if (b == pos) continue;
-        const unsigned long long e = A.pk[b];
-        if (s < hi - lo && !me_long && ((pk_lo(e) >> 31) & 1u)) continue;   // long ones: via the list
-        if (!((allow >> ((pk_lo(e) >> 24) & 0x7f)) & 1ull)) continue;
-        // the quantised boxes are rounded outwards: a superset of the exact box overlaps; the
-        // separating-axis test sorts out the rest (triangles with disjoint boxes never pass it)
-        if (!pk_overlap(me, e)) continue;
-        visit((int)A.sface[b]);
+    const int nwin = hi - lo;
+    const int nsteps = nwin + (me_long ? 0 : nlarge);
+    for (int s0 = 0; s0 < nsteps; s0 += LW) {
+        const int s = s0 + lane;
+        bool ok = s < nsteps;
+        int fj = 0;
+        if (ok) {
+            const int b = s < nwin ? lo + s : (int)A.large[s - nwin];
+            const unsigned long long e = A.pk[b];
+            // long ones come through the list; the quantised boxes are rounded outwards: a
+            // superset of the exact box overlaps, the separating-axis test sorts out the rest
+            ok = b != pos && !(s < nwin && !me_long && ((pk_lo(e) >> 31) & 1u)) &&
+                 ((allow >> ((pk_lo(e) >> 24) & 0x7f)) & 1ull) && pk_overlap(me, e);
+            fj = A.sface[b];
+        }
+        visit(fj, ok);
     }
 }
 
@@ -707,60 +713,78 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
     }
     SFX_SYNC();
     const int nlarge = S.cscan_total;       // <= SFX_COLL_LARGE_GOAL by construction
-    // ---- walk + narrow phase, per thread and in chunks ----
-    // Walk: the thread lists, for the candidates it owns (sorted positions tid, tid + NT, ...),
-    // the partners whose part is admissible and whose box overlaps.  A short candidate meets
-    // other short ones inside a window of the sorted order (backwards no further than the
-    // longest short extent E, forwards up to its own maximum; both ends by binary search) and
-    // the long ones through their list; a long candidate scans everything: every ordered pair is
-    // visited exactly once.  The list lives in the thread's own region, (count, faces...) per
-    // candidate; a candidate is only started while half the region is free, and when the region
-    // cannot take the next one the thread works it off before it walks on.
-    // Narrow phase: straight through the list -- separating-axis test, penalty of the own cone
-    // and gradient w.r.t. the own corners, accumulated in registers per candidate (a gather: no
-    // atomics on values, a fixed summation order).
-    const int HC = W.hits_cap;
-    unsigned short* myhits = W.hits_g + (long)SFX_TID * HC;
+    // ---- walk + narrow phase, a warp per candidate, in chunks ----
+    // Walk: the warp lists the box-overlapping, admissible partners of the candidates it owns
+    // (sorted positions warp, warp + 16, ...) in its own region, (count, faces...) per candidate;
+    // a candidate is only started while half the region is free, and when the region cannot take
+    // the next one the warp works the list off before it walks on.
+    // Narrow phase: separating-axis test, penalty of the own cone and gradient w.r.t. the own
+    // corners (a gather: no atomics on values, a fixed summation order).
+#ifdef __CUDACC__
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NWP = blockDim.x >> 5, LW = 32;
+#else
+    const int lane = 0, warp = 0, NWP = 1, LW = 1;
+#endif
+    const int HCW = W.hits_cap * LW;                 // the warp's region: its lanes' regions together
+    unsigned short* myhits = W.hits_g + (long)warp * HCW;
     T my_loss = 0;
     SFX_PROF_END(S, 9, cb);
-    for (int pos0 = SFX_TID; pos0 < ncand;) {
+    for (int pos0 = warp; pos0 < ncand;) {
+        // ---- walk: a warp per candidate, lanes side by side through the window ----
         int w = 0, pos1 = pos0;
         SFX_PROF_BEGIN(cw);
-        for (; pos1 < ncand && w + HC / 2 <= HC; pos1 += SFX_NT) {
+        for (; pos1 < ncand && w + HCW / 2 <= HCW; pos1 += NWP) {
             const int head = w++;
             int cnt = 0;
-            bool full = false;
-            coll_partners(W, A, pos1, ncand, nlarge, axis, E16, [&](int fj) {
-                if (w < HC) { myhits[w++] = (unsigned short)fj; cnt += 1; }
-                else full = true;
+            coll_partners(A, pos1, ncand, nlarge, axis, E16, lane, LW, [&](int fj, bool ok) {
+#ifdef __CUDACC__
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                const int slot = w + __popc(m & ((1u << lane) - 1u)), n = __popc(m);
+#else
+                const int slot = w, n = ok ? 1 : 0;
+#endif
+                if (ok && slot < HCW) myhits[slot] = (unsigned short)fj;
+                w += n;
+                cnt += n;
             });
-            // a candidate with more box partners than the region holds is walked again in the
-            // narrow phase, partner by partner
-            if (full) { w = head + 1; cnt = 0xffff; }
-            myhits[head] = (unsigned short)cnt;
+            // a candidate with more box partners than the region holds (or than a 16-bit count)
+            // is walked again in the narrow phase, partner by partner
+            if (w > HCW || cnt >= 0xffff) { w = head + 1; cnt = 0xffff; }
+            if (lane == 0) myhits[head] = (unsigned short)cnt;
         }
+        SFX_SYNCWARP();
         SFX_PROF_END(S, 13, cw);
         SFX_PROF_BEGIN(ch);
+        // ---- narrow phase: the lanes share a candidate's partners; per-lane partial sums,
+        // combined in a fixed order ----
         int r = 0;
-        for (int pos = pos0; pos < pos1; pos += SFX_NT) {
+        for (int pos = pos0; pos < pos1; pos += NWP) {
             const int cnt = myhits[r++];
             if (cnt == 0) continue;
             const int fi = A.sface[pos];
-            T ti[9], gi[9], loss_i = 0;
+            T ti[9], acc[10];
             int idi[3];
             face_corners(M, vert, fi, ti, idi);
-            for (int d = 0; d < 9; ++d) gi[d] = 0;
+            for (int d = 0; d < 10; ++d) acc[d] = 0;
             bool hit = false;
             if (cnt == 0xffff) {
-                coll_partners(W, A, pos, ncand, nlarge, axis, E16, [&](int fj) {
-                    coll_pair(M, vert, fi, ti, fj, sigma, &hit, &loss_i, gi);
+                coll_partners(A, pos, ncand, nlarge, axis, E16, lane, LW, [&](int fj, bool ok) {
+                    if (ok) coll_pair(M, vert, fi, ti, fj, sigma, &hit, acc + 9, acc);
                 });
             } else {
-                for (int h = 0; h < cnt; ++h) coll_pair(M, vert, fi, ti, (int)myhits[r++], sigma, &hit, &loss_i, gi);
+                for (int h = lane; h < cnt; h += LW)
+                    coll_pair(M, vert, fi, ti, (int)myhits[r + h], sigma, &hit, acc + 9, acc);
+                r += cnt;
             }
-            if (hit) {
-                my_loss += loss_i;
-                for (int d = 0; d < 9; ++d) W.dtri_g[(long)fi * 9 + d] = gi[d];
+#ifdef __CUDACC__
+            hit = __any_sync(0xffffffffu, hit);
+            if (hit)
+                for (int o = 16; o > 0; o >>= 1)
+                    for (int d = 0; d < 10; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
+#endif
+            if (hit && lane == 0) {
+                my_loss += acc[9];
+                for (int d = 0; d < 9; ++d) W.dtri_g[(long)fi * 9 + d] = acc[d];
 #ifdef __CUDACC__
                 atomicOr(&A.hit[fi >> 5], 1u << (fi & 31));
                 for (int a = 0; a < 3; ++a) atomicOr(&A.vtouch[idi[a] >> 5], 1u << (idi[a] & 31));
@@ -770,6 +794,7 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
 #endif
             }
         }
+        SFX_SYNCWARP();
         SFX_PROF_END(S, 14, ch);
         pos0 = pos1;
     }
@@ -820,8 +845,9 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
 // Adjoint of the skinning of the touched vertices: S.dA += ..., vert_g[3 t ..] <- dL/dv_posed of
 // touched vertex t (compact order; the posed vertices are no longer needed at this point).
 template <typename T>
-SFX_FN void coll_skin_adjoint(const ModelView<T>& M, Scratch<T>& S, const CollWS<T>& W) {
+SFX_FN_NOINLINE void coll_skin_adjoint(const ModelView<T>& M, Scratch<T>& S, const CollWS<T>& W) {
     const int nt = S.n_touch;
+    SFX_PROF_BEGIN(ca);
     SFX_SYNC();
     SFX_FOR(i, SFX_NJ * 12) {
         const int j = i / 12, r = (i % 12) / 4, cc = i % 4;
@@ -848,6 +874,7 @@ SFX_FN void coll_skin_adjoint(const ModelView<T>& M, Scratch<T>& S, const CollWS
         for (int k = 0; k < 3; ++k) W.vert_g[3 * t + k] = R[k] * d0 + R[3 + k] * d1 + R[6 + k] * d2;
     }
     SFX_SYNC();
+    SFX_PROF_END(S, 12, ca);
 }
 
 }  // namespace sfx

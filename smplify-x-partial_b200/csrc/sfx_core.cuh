@@ -943,6 +943,28 @@ SFX_FN T gmm_prior(const ModelView<T>& M, const T* pose, Scratch<T>& S, T* grad)
 #include "sfx_collide.cuh"
 namespace sfx {
 
+// Out-of-line entry points of the interpenetration term, so that the evaluation without the
+// term keeps its register allocation.
+template <typename T>
+SFX_FN_NOINLINE void coll_blend_forward(const ModelView<T>& M, Scratch<T>& S, const CollWS<T>& W, void* ws) {
+    // the whole mesh is needed: stream every row once, the support rows are a subset
+    blend_forward_full(M, S, ws, W.vp_g);
+    SFX_SYNC();
+    SFX_FOR(r, SFX_NSLOT * 3) S.vp[r] = W.vp_g[3L * S.vid[r / 3] + (r % 3)];
+}
+template <typename T>
+SFX_FN_NOINLINE void coll_mesh_and_penalty(const ModelView<T>& M, Scratch<T>& S, const CollWS<T>& W,
+                                           T sigma, T weight) {
+    SFX_PROF_BEGIN(cs);
+    coll_skin_mesh(M, S, W);
+    SFX_PROF_END(S, 8, cs);
+    coll_search_and_penalty(M, S, W, sigma, weight);
+}
+template <typename T>
+SFX_FN_NOINLINE void coll_blend_adjoint(const ModelView<T>& M, Scratch<T>& S, const CollWS<T>& W, void* ws) {
+    blend_adjoint_ext(M, S, ws, W.tv_g, W.vert_g);
+}
+
 // One evaluation of the stage objective and its gradient for one frame (the reference's
 // closure, fitting.py:232-273).  Reads S.x, writes S.loss and S.gfull.  Needs
 // support_begin_frame() once per frame and stage_joint_weights() once per stage beforehand.
@@ -965,25 +987,14 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     if (SFX_IS_WARP0) chain_forward(M, S);
     SFX_PROF_END(S, 5, bf);                     // chain alone (warp 0)
     SFX_PROF_BEGIN(bs);
-    if (coll) {
-        // the whole mesh is needed: stream every row once, the support rows are a subset
-        blend_forward_full(M, S, stream_ws, CW->vp_g);
-        SFX_SYNC();
-        SFX_FOR(r, SFX_NSLOT * 3) S.vp[r] = CW->vp_g[3L * S.vid[r / 3] + (r % 3)];
-    } else {
-        blend_forward(M, S, stream_ws);
-    }
+    if (coll) coll_blend_forward(M, S, *CW, stream_ws);
+    else blend_forward(M, S, stream_ws);
 #if defined(__CUDACC__) && defined(SFX_CYCLE_PROF)
     if (threadIdx.x == 32) S.prof[6] += clock64() - _t_bs;      // warp 1's own streaming time
 #endif
     SFX_SYNC();
     SFX_PROF_END(S, 2, bf);
-    if (coll) {
-        SFX_PROF_BEGIN(cs);
-        coll_skin_mesh(M, S, *CW);
-        SFX_PROF_END(S, 8, cs);
-        coll_search_and_penalty(M, S, *CW, (T)st.coll_sigma, (T)st.coll_loss_weight);
-    }
+    if (coll) coll_mesh_and_penalty(M, S, *CW, (T)st.coll_sigma, (T)st.coll_loss_weight);
     // ---- 4. skinning of the support vertices ------------------------------------------
     SFX_FOR(s, SFX_NSLOT) {
         T Tm[12];
@@ -1119,17 +1130,14 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.dA[i] = acc;
     }
     SFX_SYNC();
-    if (coll && S.n_touch > 0) {
-        SFX_PROF_BEGIN(ca);
-        coll_skin_adjoint(M, S, *CW);
-        SFX_PROF_END(S, 12, ca);
-    }
+    const bool coll_adj = coll && S.n_touch > 0;
+    if (coll_adj) coll_skin_adjoint(M, S, *CW);
     // ---- 8. adjoint of the chain (warp 0) || adjoint of the blendshapes (every warp) -----
     SFX_PROF_BEGIN(ba);
     if (SFX_IS_WARP0) chain_adjoint(M, S);
     SFX_PROF_END(S, 7, ba);                     // chain adjoint alone (warp 0)
     if (st.need_blend_grad) {
-        if (coll && S.n_touch > 0) blend_adjoint_ext(M, S, stream_ws, CW->tv_g, CW->vert_g);
+        if (coll_adj) coll_blend_adjoint(M, S, *CW, stream_ws);
         else blend_adjoint(M, S, stream_ws);
     } else {
         SFX_FOR(i, SFX_KPAD) S.dc[i] = 0;

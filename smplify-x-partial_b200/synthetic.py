@@ -487,6 +487,15 @@ def sibling_part_pairs(model_data):
     return pairs + ['{},{}'.format(a, n) for a in range(n)]       # zero-area faces: never paired
 
 
+# Part pairs whose tubes already cross in the rest pose of make_smplx_like (found with the
+# restated search of oracle/isect_port.py on the template; sibling pairs excluded).  The reference
+# lists such pairs of ITS mesh in ign_part_pairs ("Upper arms and Spine 2", "Neck and jaw" in the
+# yaml files); for the tube-man the list is longer.
+REST_POSE_TOUCHING_PART_PAIRS = [
+    '1,5', '4,10', '5,11', '9,16', '9,17', '12,16', '12,17', '12,22', '13,17', '25,29', '28,35',
+    '32,34', '40,44', '43,50', '47,49']
+
+
 def make_vposer_like(seed=2, latent=32, hidden=512, dtype=np.float32):
     """Weights with the VPoser v1 layer shapes, seeded.
 
