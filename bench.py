@@ -37,6 +37,10 @@ METRIC = 'frames/sec (full multi-stage fit, 127 body kpts)'
 UNIT = 'frames/s'
 SUPPORT_ROWS = 225 * 3
 ROW_BYTES = 512 * 4
+# dram__bytes_read.sum + dram__bytes_write.sum of one fit_pipeline_kernel<float> launch of the
+# default workload (128 frames), from the `ncu --set full` capture summarised in
+# profiles/r01f_ncu_raw_pipeline_kernel.csv (6.93 MB read + 6.66 MB written)
+NCU_TRAFFIC_BYTES_DEFAULT_WORKLOAD = 13591552.0
 
 
 # ------------------------------------------------------------------------------ workload
@@ -431,6 +435,14 @@ def run_b200(args):
                         'by the L2->SM path and by per-frame serial latency, not by HBM'}
     if args.traffic is not None:
         roofline['traffic'] = args.traffic
+    elif B == 128 and not args.interpenetration:
+        roofline['traffic'] = NCU_TRAFFIC_BYTES_DEFAULT_WORKLOAD
+        roofline['traffic_source'] = 'profiles/r01f_ncu_raw_pipeline_kernel.csv'
+    coll_stats = batch.coll_stats()
+    if coll_stats is not None:
+        cs = coll_stats.cpu().numpy()
+        roofline['collision_candidates_per_frame_median_max'] = [int(np.median(cs[:, 0])), int(cs[:, 0].max())]
+        roofline['collision_touched_vertices_median_max'] = [int(np.median(cs[:, 1])), int(cs[:, 1].max())]
 
     value = world * B * args.steps / (total_ms * 1e-3)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)

@@ -174,6 +174,29 @@ def regression_pose(cfg, expose=None, pixie=None, dtype=np.float32):
     return full.reshape(-1).astype(dtype), gp.reshape(-1).astype(dtype)
 
 
+def regression_pose_batch(cfg, expose, pixie, B, dtype=np.float32):
+    """``regression_pose`` for B frames at once (the Euler conversion is elementwise, so the
+    result is bit-identical to B separate calls): -> (pose [B,63], global_orient [B,3])."""
+    kind = cfg.get('regression_prior')
+    pix = exp = gp = None
+    stack = lambda rows, key: np.stack([np.asarray(r[key], dtype=dtype) for r in rows])
+    if kind in ('PIXIE', 'combined'):
+        pix = U.euler_xyz_from_matrix(stack(pixie, 'body_pose'))                 # [B,21,3]
+        gp = U.euler_xyz_from_matrix(stack(pixie, 'global_pose'))[:, 0]
+    if kind in ('ExPose', 'combined'):
+        exp = U.euler_xyz_from_matrix(stack(expose, 'body_pose'))
+        gp = U.euler_xyz_from_matrix(stack(expose, 'global_orient'))[:, 0]
+    if kind == 'PIXIE':
+        full = pix
+    elif kind == 'ExPose':
+        full = exp
+    elif kind == 'combined':
+        full = np.concatenate([exp[:, :19], pix[:, 19:]], axis=1)
+    else:
+        raise ValueError('unknown regression prior {}'.format(kind))
+    return full.reshape(B, -1).astype(dtype), gp.reshape(B, -1).astype(dtype)
+
+
 def camera_prior(cfg, focal, expose=None, pixie=None):
     """-> (translation [3], centre [2]) or None when guess_init applies
     (fit_single_frame.py:359-411)."""
@@ -273,12 +296,8 @@ class FitPlan(object):
             raise ValueError('the batch was created with use_vposer=True but the config says False')
         if cfg.get('regression_prior'):
             self.reg = np.zeros((B, L.n_pose), dtype=np.float64)
-            poses = np.zeros((B, 63), dtype=npd)
-            for b in range(B):
-                pose, go = regression_pose(cfg, None if expose is None else expose[b],
-                                           None if pixie is None else pixie[b], dtype=npd)
-                poses[b] = pose
-                x[b, L.off_go:L.off_go + 3] = go
+            poses, gos = regression_pose_batch(cfg, expose, pixie, B, dtype=npd)
+            x[:, L.off_go:L.off_go + 3] = gos
             if use_vposer:
                 # pose_embedding = vposer.encode(prior).sample()  (fit_single_frame.py:245):
                 # stochastic in the reference too; seed torch for reproducible runs

@@ -88,6 +88,16 @@ def test_regression_pose_and_camera_prior():
         assert np.allclose(pose, torch.cat(want).reshape(-1).numpy(), atol=2e-6)
         src = pixie['global_pose'] if kind == 'PIXIE' else expose['global_orient']
         assert np.allclose(go, FP.euler_xyz_from_matrix(torch.tensor(src[0])).numpy()[0], atol=2e-6)
+    # the batched planner gives exactly what per-frame calls give
+    fr2 = '02_cropped'
+    expose2 = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr2 + '/expose/')}
+    pixie2 = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr2 + '/pixie/')}
+    for kind in ('ExPose', 'PIXIE', 'combined'):
+        cfg = dict(regression_prior=kind)
+        pb, gb = FF.regression_pose_batch(cfg, [expose, expose2, expose], [pixie, pixie2, pixie], 3)
+        for b, (e_, p_) in enumerate([(expose, pixie), (expose2, pixie2), (expose, pixie)]):
+            pose, go = FF.regression_pose(cfg, e_, p_)
+            assert np.array_equal(pb[b], pose) and np.array_equal(gb[b], go)
     t, c = FF.camera_prior(dict(regression_prior='combined', use_camera_prior=True), 1000.0,
                            expose, pixie)
     assert np.allclose(t[:2], expose['transl'][:2]) and t[2] == pytest.approx(expose['transl'][2] / 5.0)
