@@ -47,10 +47,24 @@ NCU_TRAFFIC_BYTES_DEFAULT_WORKLOAD = 13591552.0
 COLL_POSE_CORRECTIVE_SCALE = 0.1      # config 4: see synthetic.cached_smplx_like
 
 
-def bench_cfg(interpenetration=False):
+def bench_cfg(interpenetration=False, vposer=False):
     """fit_smplx_combined_coco25.yaml (reference cfg_files/) with BASELINE config-2 switches;
-    ``interpenetration`` turns the yaml's own interpenetration settings back on (config 4)."""
+    ``interpenetration`` turns the yaml's own interpenetration settings back on (config 4);
+    ``vposer`` selects the 5-stage fit_smplx_smplifyx.yaml schedule with the VPoser latent pose,
+    zero-latent start, guess_init camera and focal length 5000 (config 3)."""
     cfg = _bench_cfg()
+    if vposer:
+        cfg.update(
+            use_vposer=True, regression_prior=None, use_camera_prior=False,
+            use_conf_for_camera_init=False, init_joints_idxs=[9, 12, 2, 5], focal_length=5000.0,
+            body_pose_prior_weights=[404.0, 404.0, 57.4, 4.78, 4.78],
+            coll_loss_weights=[0.0, 0.0, 0.0, 0.0, 0.0],
+            shape_weights=[100.0, 50.0, 10.0, 5.0, 5.0], expr_weights=[100.0, 50.0, 10.0, 5.0, 5.0],
+            hand_pose_prior_weights=[404.0, 404.0, 57.4, 4.78, 4.78],
+            jaw_pose_prior_weights=['4.04e03,4.04e04,4.04e04', '4.04e03,4.04e04,4.04e04',
+                                    '574,5740,5740', '47.8,478,478', '47.8,478,478'],
+            hand_joints_weights=[0.0, 0.0, 0.0, 0.1, 2.0],
+            face_joints_weights=[0.0, 0.0, 0.0, 0.0, 2.0])
     if interpenetration:
         from smplifyx_b200 import synthetic
         md = synthetic.cached_smplx_like(0, COLL_POSE_CORRECTIVE_SCALE)
@@ -124,11 +138,16 @@ def ground_truth(B, seed, shape_scale=1.0):
     return gt, rng
 
 
-def observations(gt, joints3d, rng):
-    """Noisy 2-D keypoints + synthetic regression results from GT joints [B,K,3]."""
+def observations(gt, joints3d, rng, focal_length=None):
+    """Noisy 2-D keypoints + synthetic regression results from GT joints [B,K,3].  With an
+    explicit ``focal_length`` (config 3: 5000) the ground-truth depth is scaled along so the
+    person keeps its size in the 800 x 600 image."""
     from smplifyx_b200 import utils as U
     B, K, _ = joints3d.shape
     focal = float(np.sqrt(H_IMG ** 2 + W_IMG ** 2))
+    if focal_length is not None:
+        gt['transl'][:, 2] *= float(focal_length) / focal
+        focal = float(focal_length)
     c = np.array([W_IMG * 0.5, H_IMG * 0.5])
     p = joints3d + gt['transl'][:, None]
     uv = focal * p[:, :, :2] / p[:, :, 2:3] + c
@@ -284,7 +303,15 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(B, n_gpus, interpenetration=False):
+def workload_config(B, n_gpus, interpenetration=False, vposer=False):
+    if vposer:
+        return {'workload': 'batch={} synthetic frames per GPU, 135 keypoints, neutral SMPL-X-shaped '
+                            'synthetic model, VPoser latent pose prior (synthetic VPoser v1 weights), '
+                            '5-stage fit_smplx_smplifyx schedule, lbfgsls, guess_init camera, focal '
+                            '5000, interpenetration off (BASELINE config 3)'.format(B),
+                'frames_per_gpu': B, 'global_frames': B * n_gpus,
+                'parallelism': 'frames sharded, dp{}'.format(n_gpus),
+                'l2': 'flushed between timed steps (256 MiB write)'}
     return {'workload': 'batch={} synthetic frames per GPU, 135 keypoints (127 model joints + 17 '
                         'face-contour), neutral SMPL-X-shaped synthetic model, GMoF + L2 priors, '
                         '3-stage fit_smplx_combined_coco25 schedule, lbfgsls, combined regression '
@@ -309,7 +336,7 @@ def run_b200(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    cfg = bench_cfg(args.interpenetration)
+    cfg = bench_cfg(args.interpenetration, args.vposer)
     md = synthetic.cached_smplx_like(
         0, COLL_POSE_CORRECTIVE_SCALE if args.interpenetration else 1.0)
     part_segm = synthetic.parts_segm_like(md) if args.interpenetration else None
@@ -317,26 +344,38 @@ def run_b200(args):
     jm = U.smpl_to_annotation('smplx', use_hands=True, use_face=True, use_face_contour=True,
                               format='coco25')
     model = engine.Model(md, jm, dtype=torch.float32, **MODEL_KW)
-    batch = engine.FrameBatch(model, B)
+    vp = None
+    if args.vposer:
+        from smplifyx_b200 import vposer as V
+        vp = V.VPoser(synthetic.make_vposer_like(seed=2))
+        model.set_vposer(vp.weights)
+    batch = engine.FrameBatch(model, B, use_vposer=args.vposer)
     L = batch.L
 
     # ---- synthetic inputs: GT parameters -> model joints (engine forward) -> noisy keypoints
     gt, rng = ground_truth(B, args.seed + 1000 * rank, 0.2 if args.interpenetration else 1.0)
-    cam_st = N.make_stage(L, N.CAMERA_STAGE_BLOCKS, loss_kind=N.LOSS_CAMERA_INIT)
     K = model.K
+    gbatch = engine.FrameBatch(model, B) if args.vposer else batch     # axis-angle pose block
+    Lg = gbatch.L
+    cam_st = N.make_stage(Lg, N.CAMERA_STAGE_BLOCKS, loss_kind=N.LOSS_CAMERA_INIT)
     zero_cam = np.zeros((B, N.SFX_CAM_STRIDE))
     zero_cam[:, 0:2] = 1.0
     zero_cam[:, 4:13] = np.eye(3).reshape(-1)
-    xg = gt_param_matrix(L, gt)
-    xg[:, L.off_camt + 2] = 1.0
-    batch.set_targets(np.zeros((B, K, 3)), np.zeros((B, K)), np.zeros((B, K), np.uint8),
-                      np.zeros((B, K), np.uint8), zero_cam, None)
-    batch.set_params(xg)
-    _, _, j3 = batch.eval(cam_st, want_joints=True)
-    kp, expose, pixie = observations(gt, j3.cpu().numpy().astype(np.float64), rng)
+    xg = gt_param_matrix(Lg, gt)
+    xg[:, Lg.off_camt + 2] = 1.0
+    gbatch.set_targets(np.zeros((B, K, 3)), np.zeros((B, K)), np.zeros((B, K), np.uint8),
+                       np.zeros((B, K), np.uint8), zero_cam, None)
+    gbatch.set_params(xg)
+    _, _, j3 = gbatch.eval(cam_st, want_joints=True)
+    if args.vposer:
+        gbatch.close()
+    kp, expose, pixie = observations(gt, j3.cpu().numpy().astype(np.float64), rng,
+                                     cfg.get('focal_length'))
 
+    if args.vposer:
+        expose = pixie = None
     plan = FF.FitPlan(L, K, kp, H_IMG, W_IMG, cfg, expose, pixie, None, np.float32,
-                      part_segm=part_segm)
+                      part_segm=part_segm, vposer=vp)
     FF.upload(batch, plan)
     x0_dev = batch.params_tensor().clone()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -383,13 +422,13 @@ def run_b200(args):
     out = None
     for _ in range(min(args.warmup, 2)):
         out = FF.fit_frames(batch, kp, H_IMG, W_IMG, cfg, expose, pixie, return_verts=True,
-                            part_segm=part_segm)
+                            part_segm=part_segm, vposer=vp)
     barrier()
     for i in range(args.steps):
         flush.fill_(i & 0xff)
         e2e_ev[i][0].record()
         out = FF.fit_frames(batch, kp, H_IMG, W_IMG, cfg, expose, pixie, return_verts=True,
-                            part_segm=part_segm)
+                            part_segm=part_segm, vposer=vp)
         if world > 1:
             dist.all_gather_into_tensor(gathered, batch.params_tensor())
         e2e_ev[i][1].record()
@@ -435,7 +474,7 @@ def run_b200(args):
                         'by the L2->SM path and by per-frame serial latency, not by HBM'}
     if args.traffic is not None:
         roofline['traffic'] = args.traffic
-    elif B == 128 and not args.interpenetration:
+    elif B == 128 and not args.interpenetration and not args.vposer:
         roofline['traffic'] = NCU_TRAFFIC_BYTES_DEFAULT_WORKLOAD
         roofline['traffic_source'] = 'profiles/r01f_ncu_raw_pipeline_kernel.csv'
     coll_stats = batch.coll_stats()
@@ -450,7 +489,7 @@ def run_b200(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(B, world, args.interpenetration),
+        'config': workload_config(B, world, args.interpenetration, args.vposer),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(out.h2d_bytes),
                 'd2h_bytes_per_step': int(out.d2h_bytes), 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
@@ -459,7 +498,8 @@ def run_b200(args):
                 'frames_with_nan_or_inf': int((out.flags != 0).sum()),
                 'frames_second_orientation': int(len(plan.flip_ids))},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.interpenetration:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.interpenetration \
+            and not args.vposer:
         sample = list(range(min(args.cpu_frames, B)))
         threads = os.cpu_count() or 1
         secs, evals = time_oracle_frames(cfg, kp, expose, pixie, sample, threads)
@@ -490,6 +530,9 @@ def main():
                     help='BASELINE config 4: the same workload with the interpenetration term on '
                          '(not the default bench line; the CPU baseline is skipped because the '
                          'restated third-party search takes seconds per evaluation in numpy)')
+    ap.add_argument('--vposer', action='store_true',
+                    help='BASELINE config 3: 5-stage schedule with the VPoser latent pose prior '
+                         '(not the default bench line)')
     ap.add_argument('--traffic', type=float, default=None,
                     help='dram bytes per launch from an ncu capture (profiles/), recorded as-is')
     args = ap.parse_args()

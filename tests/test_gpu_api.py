@@ -157,3 +157,107 @@ def test_fit_single_frame_mirror_against_reference(tmp_path):
     err = np.abs(verts - ref['vertices'])
     assert err.max() <= float(env['fit/vertex_pairwise_max'])
     assert err.mean() <= float(env['fit/vertex_pairwise_mean'])
+
+
+def test_closure_with_interpenetration_objects():
+    """fitting.create_loss(search_tree=, pen_distance=, tri_filtering_module=) the way the
+    reference builds it (fit_single_frame.py:300-328, :413-428): the closure's loss and .grad
+    equal the reference loss driving the restated mesh_intersection package (float64)."""
+    from smplifyx_b200 import fitting, camera as C, mesh_intersection as MI
+    from smplifyx_b200.optimizers import optim_factory
+    dtype = torch.float64
+    ev = Cm.golden('ref_eval_coll_f64.npz')
+    bm, pri = _objects(dtype)
+    dev = bm.engine_model.device
+    cam = C.create_camera(focal_length_x=float(ev['focal']), focal_length_y=float(ev['focal']),
+                          dtype=dtype).to(dev)
+    with torch.no_grad():
+        cam.translation[:] = torch.tensor(ev['cam_t'], dtype=dtype)
+        cam.center[:] = torch.tensor(ev['center'], dtype=dtype)
+    named = {k[6:]: ev[k] for k in ev if k.startswith('param/')}
+    emb = torch.tensor(named.pop('pose_embedding'), dtype=dtype, device=dev, requires_grad=True)
+    bm.reset_params(**named)
+    kp = torch.tensor(ev['keypoints'][None], dtype=dtype, device=dev)
+    gt, conf = kp[:, :, :2], kp[:, :, 2]
+    jw = torch.tensor(ev['jw'], dtype=dtype, device=dev)
+    w = json.loads(str(ev['weights_json']))
+    segm, par, ign = Cm.coll_segmentation()
+    search_tree = MI.BVH(max_collisions=128)
+    pen_distance = MI.DistanceFieldPenetrationLoss(sigma=float(ev['sigma']), point2plane=False,
+                                                   vectorized=True, penalize_outside=True)
+    filter_faces = MI.FilterFaces(faces_segm=segm, faces_parents=par, ign_part_pairs=ign)
+    loss = fitting.create_loss('smplify', rho=100, use_joints_conf=True, use_face=True,
+                               use_hands=True, interpenetration=True, search_tree=search_tree,
+                               pen_distance=pen_distance, tri_filtering_module=filter_faces,
+                               dtype=dtype, regression_pose=None, num_stages=3, **pri).to(dev)
+    loss.reset_loss_weights(w)
+    params = [p for p in bm.parameters() if p.requires_grad] + [emb]
+    with fitting.FittingMonitor(maxiters=30, ftol=1e-9, gtol=1e-9) as monitor:
+        opt, cg = optim_factory.create_optimizer(params, optim_type='lbfgsls', lr=1.0, maxiters=30)
+        closure = monitor.create_fitting_closure(
+            opt, bm, camera=cam, gt_joints=gt, joints_conf=conf, joint_weights=jw, loss=loss,
+            create_graph=cg, use_vposer=False, vposer=None, pose_embedding=emb,
+            return_verts=True, return_full_pose=True)
+        val = closure(stage=1, backward=True)
+        assert float(val) == pytest.approx(float(ev['coll/loss']), rel=1e-11)
+        g_pen = ev['coll/grad/pose_embedding'] - ev['nocoll/grad/pose_embedding']
+        got = emb.grad.cpu().numpy() - ev['nocoll/grad/pose_embedding']
+        assert np.abs(got - g_pen).max() <= 1e-8 * np.abs(g_pen).max()
+        # weight 0 switches the term off (fitting.py:439)
+        loss.reset_loss_weights(dict(w, coll_loss_weight=0.0))
+        assert float(closure(stage=1, backward=False)) == pytest.approx(float(ev['nocoll/loss']), rel=1e-11)
+    # without the face filter the device path refuses instead of dropping the term
+    bad = fitting.create_loss('smplify', interpenetration=True, search_tree=search_tree,
+                              pen_distance=pen_distance, tri_filtering_module=None, dtype=dtype,
+                              num_stages=3, **pri).to(dev)
+    bad.reset_loss_weights(w)
+    with pytest.raises(NotImplementedError):
+        bad.stage_kwargs(False, 1)
+    with pytest.raises(NotImplementedError):
+        MI.DistanceFieldPenetrationLoss(sigma=1e-4, point2plane=True)
+
+
+def test_fit_single_frame_mirror_with_part_segm_fn(tmp_path):
+    """The reference call with interpenetration=True and --part_segm_fn (README.md:55): the
+    pickle is read, the term runs in the last two stages, the result keys are the reference's."""
+    from smplifyx_b200 import camera as C, fit_single_frame as FSF, synthetic
+    inp = Cm.golden('demo_inputs.npz')
+    ref = Cm.golden('ref_fit_02.npz')
+    cfg = json.loads(str(ref['cfg_json']))
+    cfg['body_tri_idxs'] = [tuple(p) for p in cfg['body_tri_idxs']]
+    segm, par, ign = Cm.coll_segmentation()
+    seg_fn = str(tmp_path / 'parts_segm.pkl')
+    with open(seg_fn, 'wb') as f:
+        pickle.dump({'segm': segm, 'parents': par}, f, protocol=2)
+    cfg.update(interpenetration=True, coll_loss_weights=[0.0, 0.1, 1.0], df_cone_height=1e-4,
+               max_collisions=128, penalize_outside=True, point2plane=False, ign_part_pairs=ign,
+               part_segm_fn=seg_fn, maxiters=6)
+    fr = '02_cropped'
+    expose = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr + '/expose/')}
+    pixie = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr + '/pixie/')}
+    H, W = [int(v) for v in inp[fr + '/HW']]
+    dtype = torch.float32
+    bm, pri = _objects(dtype)
+    focal = (W ** 2 + H ** 2) ** 0.5
+    cam = C.create_camera(focal_length_x=focal, focal_length_y=focal, dtype=dtype).to(
+        bm.engine_model.device)
+    cam.rotation.requires_grad = False
+    jw = torch.ones([1, 135], dtype=dtype)
+    jw[:, cfg['joints_to_ign']] = 0
+    args = dict(cfg)
+    for k in ('dtype', 'output_folder', 'result_folder', 'focal_length'):
+        args.pop(k, None)
+    res_fn = str(tmp_path / '000.pkl')
+    FSF.fit_single_frame(np.zeros((H, W, 3), np.float32), inp[fr + '/keypoints'][None],
+                         body_model=bm, camera=cam, joint_weights=jw, dtype=dtype,
+                         result_folder=str(tmp_path), result_fn=res_fn, img_name=fr,
+                         pixie_results=pixie, expose_results=expose, focal_length=focal,
+                         **pri, **args)
+    with open(res_fn, 'rb') as f:
+        result = pickle.load(f)
+    assert set(result.keys()) == {k[7:] for k in ref if k.startswith('result/')}
+    assert all(np.all(np.isfinite(v)) for v in result.values() if isinstance(v, np.ndarray))
+    batch = bm.frame_batch(False)
+    cs = batch.coll_stats().cpu().numpy()
+    assert cs[0, 0] > 0                     # the search ran and saw candidates
+    assert int(batch.flags().cpu().numpy().max()) == 0
