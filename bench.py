@@ -452,7 +452,7 @@ def run_b200(args):
     kern_ms = a.elapsed_time(b_)
     passes = batch.passes().cpu().numpy().astype(np.int64)
     evals = batch.evals().cpu().numpy().astype(np.int64)
-    alg_bytes = float(passes.sum()) * SUPPORT_ROWS * ROW_BYTES
+    alg_bytes = float(passes.sum()) * ROW_BYTES        # rows of the blend matrix streamed x 2 KiB
     evals_per_frame = float(evals.mean())
     peaks = {}
     try:
@@ -468,10 +468,11 @@ def run_b200(args):
                 'launches': 1, 'kernel_ms_per_step': kern_ms,
                 'algorithmic_bytes_per_step': alg_bytes,
                 'evals_max_frame': int(evals.max()), 'evals_min_frame': int(evals.min()),
-                'note': 'algorithmic bytes = blend passes (1 per forward, 1 per adjoint of every '
-                        'closure evaluation) x 675 support rows x 2 KiB; the rows are shared by '
-                        'all frames and served from L2 after first touch, so the kernel is bound '
-                        'by the L2->SM path and by per-frame serial latency, not by HBM'}
+                'note': 'algorithmic bytes = rows of the blend matrix streamed (forward + adjoint '
+                        'pass of every closure evaluation, only the support rows a live keypoint '
+                        'depends on: at most 675) x 2 KiB; the rows are shared by all frames and '
+                        'served from L2 after first touch, so the kernel is bound by the L2->SM '
+                        'path and by per-frame serial latency, not by HBM'}
     if args.traffic is not None:
         roofline['traffic'] = args.traffic
     elif B == 128 and not args.interpenetration and not args.vposer:

@@ -178,7 +178,7 @@ int sfx_forward_mesh(sfx_batch* b, void* vertices_dev, void* joints_dev, void* s
 /* Diagnostics: closure evaluations and status flags per frame ([B] int32, device). */
 int32_t* sfx_batch_evals_dev(sfx_batch* b);
 int32_t* sfx_batch_flags_dev(sfx_batch* b);
-/* passes over the support rows of the blend matrix per frame (1 per forward, 1 per adjoint). */
+/* rows of the blend matrix (2 KiB each in float32) streamed per frame, forward + adjoint passes. */
 int32_t* sfx_batch_passes_dev(sfx_batch* b);
 int sfx_batch_reset_counters(sfx_batch* b, void* stream);
 

@@ -133,7 +133,7 @@ struct BatchView {
     T* hist_y;           // [B][HIST][SFX_NP_MAX]
     T* final_loss;       // [B]
     int* n_evals;        // [B]  (accumulated)
-    int* n_passes;       // [B]  blend-matrix passes streamed (1 per forward, 1 per adjoint)
+    int* n_passes;       // [B]  rows of the blend matrix streamed (forward + adjoint passes)
     int* flags;          // [B]
     const int* frame_ids;   // optional indirection (nullptr: block b -> frame b)
     long long* prof;        // [B][16] cycle counters (builds with -DSFX_CYCLE_PROF only)
@@ -189,6 +189,11 @@ struct Scratch {
                               // 11 per-vertex gather, 12 skinning adjoint of touched vertices
     T gq[16];                 // mixture prior: per-component negative log-likelihood
     // interpenetration term: ordered-compaction state, touched-vertex count
+    unsigned short rows[SFX_NSLOT * 3];   // support rows the stage needs (slots with a live keypoint),
+                                          // grouped by the streaming warp that owns them (row % 15)
+    unsigned short wptr[SFX_NSTREAM + 1]; // start of every warp's group in rows[]
+    unsigned char slot_live[SFX_NSLOT];
+    int n_rows;
     int cscan[2][32];
     int cscan_total, cscan_calls, coll_overflow, n_touch, coll_max_cand, coll_max_touch;
     T coll_loss;
@@ -363,7 +368,8 @@ static void rows_accum(const T* W, int nrows, const T* g, T* out, void*) {
 }
 template <typename T>
 static void blend_forward(const ModelView<T>& M, Scratch<T>& S, void*) {
-    for (int r = 0; r < SFX_NSLOT * 3; ++r) {
+    for (int i = 0; i < S.n_rows; ++i) {
+        const int r = S.rows[i];
         long row = (long)S.vid[r / 3] * 3 + (r % 3);
         const T* p = M.PK + row * SFX_KPAD;
         T acc = 0;
@@ -374,7 +380,8 @@ static void blend_forward(const ModelView<T>& M, Scratch<T>& S, void*) {
 template <typename T>
 static void blend_adjoint(const ModelView<T>& M, Scratch<T>& S, void*) {
     for (int k = 0; k < SFX_KPAD; ++k) S.dc[k] = 0;
-    for (int r = 0; r < SFX_NSLOT * 3; ++r) {
+    for (int i = 0; i < S.n_rows; ++i) {
+        const int r = S.rows[i];
         long row = (long)S.vid[r / 3] * 3 + (r % 3);
         const T* p = M.PK + row * SFX_KPAD;
         T w = S.dvp[r];
@@ -987,6 +994,10 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     if (SFX_IS_WARP0) chain_forward(M, S);
     SFX_PROF_END(S, 5, bf);                     // chain alone (warp 0)
     SFX_PROF_BEGIN(bs);
+    // rows no live keypoint depends on are not streamed: their slots stay at the template
+    // position (finite; every term they enter carries a zero weight)
+    SFX_FOR(r, SFX_NSLOT * 3)
+        if (!S.slot_live[r / 3]) S.vp[r] = S.vt_s[r];
     if (coll) coll_blend_forward(M, S, *CW, stream_ws);
     else blend_forward(M, S, stream_ws);
 #if defined(__CUDACC__) && defined(SFX_CYCLE_PROF)
@@ -1314,9 +1325,9 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     if (SFX_TID == 0) {
         S.loss = total;
         S.n_evals += 1;
-        S.n_passes += st.need_blend_grad ? 2 : 1;
-        // rows beyond the 675 support rows, in units of one support pass
-        if (coll) S.n_passes += (3 * M.V + 3 * S.n_touch) / (3 * SFX_NSLOT);
+        // rows of the blend matrix streamed by this evaluation (forward + adjoint)
+        S.n_passes += (coll ? 3 * M.V : S.n_rows) +
+                      (st.need_blend_grad ? S.n_rows + (coll ? 3 * S.n_touch : 0) : 0);
     }
     SFX_SYNC();
     SFX_PROF_END(S, 0, eval);
@@ -1351,13 +1362,51 @@ SFX_FN void stage_confidence_sum(const T* conf, const unsigned char* init_mask, 
     SFX_SYNC();
 }
 
+// Support rows the stage has to stream: the three rows of every slot whose model joint feeds at
+// least one keypoint with a non-zero weight (hand / face weights are zero in the early stages,
+// undetected keypoints have zero confidence, the camera stage looks at a dozen body joints).
+// Exact: the skipped rows only ever enter terms multiplied by a zero weight.
+template <typename T>
+SFX_FN void stage_live_rows(const ModelView<T>& M, const SfxStage& st, const T* conf,
+                            const unsigned char* init_mask, Scratch<T>& S, bool all_rows) {
+    SFX_SYNC();
+    SFX_FOR(s, SFX_NSLOT) {
+        const int j = s < SFX_NEXTRA ? SFX_NJ + s : SFX_NJ + SFX_NEXTRA + (s - SFX_NEXTRA) / 3;
+        bool live = all_rows;
+        if (!live && j < M.NJOUT)
+            for (int e = M.inv_ptr[j]; e < M.inv_ptr[j + 1]; ++e) {
+                const int k = M.inv_idx[e];
+                if (st.loss_kind == SFX_LOSS_CAMERA_INIT) live = live || init_mask[k] != 0;
+                else live = live || (st.use_joints_conf ? S.jw[k] * conf[k] : S.jw[k]) != (T)0;
+            }
+        S.slot_live[s] = live ? 1 : 0;
+    }
+    SFX_SYNC();
+    // Row r stays with streaming warp r % 15 and the warps keep ascending order, exactly as when
+    // all 675 rows are streamed: the skipped rows would have added exact zeros to the adjoint's
+    // per-warp partial sums, so the result is bit-identical to streaming everything.
+    if (SFX_TID == 0) {
+        int n = 0;
+        for (int w = 0; w < SFX_NSTREAM; ++w) {
+            S.wptr[w] = (unsigned short)n;
+            for (int r = w; r < SFX_NSLOT * 3; r += SFX_NSTREAM)
+                if (S.slot_live[r / 3]) S.rows[n++] = (unsigned short)r;
+        }
+        S.wptr[SFX_NSTREAM] = (unsigned short)n;
+        S.n_rows = n;
+    }
+    SFX_SYNC();
+}
+
 // everything a stage needs before its first evaluation
 template <typename T>
-SFX_FN void stage_setup(const SfxStage& st, const T* jw_base, const unsigned char* lowconf,
-                        const T* conf, const unsigned char* init_mask, int K, Scratch<T>& S) {
+SFX_FN void stage_setup(const ModelView<T>& M, const SfxStage& st, const T* jw_base,
+                        const unsigned char* lowconf, const T* conf, const unsigned char* init_mask,
+                        int K, Scratch<T>& S, bool all_rows = false) {
     stage_joint_weights_only(st, jw_base, lowconf, K, S);
     if (st.loss_kind == SFX_LOSS_CAMERA_INIT && st.use_conf_camera)
         stage_confidence_sum(conf, init_mask, K, S);
+    stage_live_rows(M, st, conf, init_mask, S, all_rows);
 }
 
 // ------------------------------------------------------- optimiser plumbing (compact <-> full)

@@ -48,7 +48,8 @@ __device__ __forceinline__ StreamWS carve_stream(unsigned char* base, int ring_m
     ws.tl_bars = reinterpret_cast<uint64_t*>(base + ring + SFX_NWARP * SFX_NBUF * sizeof(uint64_t) +
                                              SFX_NWARP * sizeof(unsigned int));
     ws.tl_calls = reinterpret_cast<unsigned int*>(ws.tl_bars + SFX_TL_GROUPS);
-    ws.ring_mode = ring_mode;
+    ws.ring_mode = ring_mode & 1;
+    ws.tl_generic = (ring_mode >> 1) & 1;
     return ws;
 }
 
@@ -103,7 +104,7 @@ fit_stage_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__
     stream_init<T>(ws);
     load_frame(Bv, f, S);
     support_begin_frame(M, S);
-    stage_setup(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
+    stage_setup(M, st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
                 Bv.init_mask + (size_t)f * K, K, S);
     EvalCtx<T> E;
     E.M = &M; E.L = &Bv.lay; E.st = &st;
@@ -149,8 +150,9 @@ eval_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ Batc
     stream_init<T>(ws);
     load_frame(Bv, f, S);
     support_begin_frame(M, S);
-    stage_setup(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
-                Bv.init_mask + (size_t)f * K, K, S);
+    // the mapped joints of EVERY keypoint are an output: no row may be skipped then
+    stage_setup(M, st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
+                Bv.init_mask + (size_t)f * K, K, S, joints_out != nullptr);
     CollWS<T> CW;
     const bool has_coll = block_coll_ws(M, Bv, ws, CW);
     eval_frame(M, Bv.lay, st, Bv.gt + (size_t)f * K * 2, Bv.conf + (size_t)f * K,
@@ -349,7 +351,7 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
         T* hy = Bv.hist_y + (size_t)f * SFX_HIST * SFX_NP_MAX;
         // stage C: camera translation + global orientation (fit_single_frame.py:473-496)
         load_stage(&P->cam);
-        stage_setup(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
+        stage_setup(M, st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
                 Bv.init_mask + (size_t)f * K, K, S);
         double r = run_fitting(E, S, hs, hy, &flags);
         __syncthreads();
@@ -378,7 +380,7 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
             reset_for_orientation(L, S);
             for (int si = 0; si < P->n_stages; ++si) {
                 load_stage(&P->body[si]);
-                stage_setup(st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
+                stage_setup(M, st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
                 Bv.init_mask + (size_t)f * K, K, S);
                 r = run_fitting(E, S, hs, hy, &flags);
             }
@@ -520,10 +522,14 @@ static size_t fit_smem(int ring_mode) {
     return scratch_bytes<T>() + stream_smem_bytes<T>(ring_mode);
 }
 
+// bit 0: TMA ring (float32) vs plain loads; bit 1: SFX_TWO_LOOP_GENERIC=1 selects the
+// generic-pointer staged two-loop recursion (A/B check of the shared-address version)
 static int ring_mode_for(const sfx_model* m) {
     const char* e = getenv("SFX_STREAM_DIRECT");
     if (e && e[0] == '1') return 0;
-    return m->use_double ? 0 : 1;
+    if (m->use_double) return 0;
+    const char* g = getenv("SFX_TWO_LOOP_GENERIC");
+    return 1 | ((g && g[0] == '1') ? 2 : 0);
 }
 
 template <typename T>

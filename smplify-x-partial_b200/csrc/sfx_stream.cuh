@@ -28,6 +28,7 @@ struct StreamWS {
     uint64_t* tl_bars;          // [SFX_TL_GROUPS] two-loop history staging (see two_loop_staged)
     unsigned int* tl_calls;     // [1] staged two-loop calls so far (phase tracking)
     int ring_mode;
+    int tl_generic;             // debug: the generic-pointer staged recursion (A/B test)
 };
 #define SFX_TL_GROUPS 8
 
@@ -109,20 +110,41 @@ struct NoAux {
     __device__ __forceinline__ float operator()(int) const { return 0.f; }
 };
 
-template <typename T, typename RP, typename FN, typename AUX>
-__device__ __forceinline__ void stream_rows_aux(int nrows, RP rowptr, StreamWS& ws, FN fn, AUX auxf,
+// The rows of a pass are numbered 0 .. n-1; streaming warp w (0 .. 14) owns `count` of them, its
+// i-th one being row index(w, i).  Strided ownership (w, w + 15, ...) is the default.
+struct StridedRows {
+    int nrows;
+    __device__ __forceinline__ int count(int w) const { return (nrows - w + SFX_NSTREAM - 1) / SFX_NSTREAM; }
+    __device__ __forceinline__ int index(int w, int i) const { return w + i * SFX_NSTREAM; }
+};
+// Live support rows grouped by warp (Scratch::rows / wptr), optionally followed by `extra`
+// further rows numbered from `base` on and owned in strided fashion.
+struct GroupedRows {
+    const unsigned short* wptr;
+    int base, extra;
+    __device__ __forceinline__ int count(int w) const {
+        return (int)wptr[w + 1] - (int)wptr[w] + (extra - w + SFX_NSTREAM - 1) / SFX_NSTREAM;
+    }
+    __device__ __forceinline__ int index(int w, int i) const {
+        const int own = (int)wptr[w + 1] - (int)wptr[w];
+        return i < own ? (int)wptr[w] + i : base + w + (i - own) * SFX_NSTREAM;
+    }
+};
+
+template <typename T, typename OWN, typename RP, typename FN, typename AUX>
+__device__ __forceinline__ void stream_rows_own(OWN own, RP rowptr, StreamWS& ws, FN fn, AUX auxf,
                                                 bool use_aux) {
+    static_assert(SFX_NSTREAM == SFX_NWARP - 1, "one warp runs the kinematic chain");
     // warp 0 runs the kinematic chain while warps 1 .. NWARP-1 stream the rows
     const int warp = (threadIdx.x >> 5) - 1, lane = threadIdx.x & 31;
-    constexpr int NSTREAM = SFX_NWARP - 1;
-    const int count = warp >= 0 ? (nrows - warp + NSTREAM - 1) / NSTREAM : 0;
+    const int count = warp >= 0 ? own.count(warp) : 0;
     constexpr uint32_t ROWB = SFX_KPAD * sizeof(T);
     T vals[RowVec<T>::NE];
     if (count == 0) return;
     T auxv = 0;
     auto aux_at = [&](int i) -> T {
         if (!use_aux) return (T)0;
-        if ((i & 31) == 0) auxv = i + lane < count ? (T)auxf(warp + (i + lane) * NSTREAM) : (T)0;
+        if ((i & 31) == 0) auxv = i + lane < count ? (T)auxf(own.index(warp, i + lane)) : (T)0;
         return __shfl_sync(0xffffffffu, auxv, i & 31);
     };
     if (ws.ring_mode) {
@@ -130,7 +152,7 @@ __device__ __forceinline__ void stream_rows_aux(int nrows, RP rowptr, StreamWS& 
         uint64_t* mybar = ws.bars + warp * SFX_NBUF;
         const unsigned int n0 = ws.fills[warp];
         auto issue = [&](int i) {
-            int r = warp + i * NSTREAM;
+            int r = own.index(warp, i);
             unsigned int n = n0 + i;
             int b = n % SFX_NBUF;
             mbar_expect_tx(mybar + b, ROWB);
@@ -151,18 +173,24 @@ __device__ __forceinline__ void stream_rows_aux(int nrows, RP rowptr, StreamWS& 
                 fence_proxy_async();
                 issue(i + SFX_NBUF);
             }
-            fn(warp + i * NSTREAM, vals, aux);
+            fn(own.index(warp, i), vals, aux);
         }
         __syncwarp();
         if (lane == 0) ws.fills[warp] = n0 + count;
     } else {
         for (int i = 0; i < count; ++i) {
             const T aux = aux_at(i);
-            int r = warp + i * NSTREAM;
+            int r = own.index(warp, i);
             load_row_regs<T>(rowptr(r), lane, vals);
             fn(r, vals, aux);
         }
     }
+}
+
+template <typename T, typename RP, typename FN, typename AUX>
+__device__ __forceinline__ void stream_rows_aux(int nrows, RP rowptr, StreamWS& ws, FN fn, AUX auxf,
+                                                bool use_aux) {
+    stream_rows_own<T>(StridedRows{nrows}, rowptr, ws, fn, auxf, use_aux);
 }
 
 template <typename T, typename RP, typename FN>
@@ -181,15 +209,20 @@ __device__ __forceinline__ void blend_forward(const ModelView<T>& M, Scratch<T>&
         for (int e = 0; e < RowVec<T>::VEC; ++e) c[i * RowVec<T>::VEC + e] = S.c[SFX_ELEM(i, lane, e)];
     const T* PK = M.PK;
     const int* vid = S.vid;
-    auto rowptr = [=](int r) { return PK + ((long)vid[r / 3] * 3 + (r % 3)) * SFX_KPAD; };
-    stream_rows<T>(SFX_NSLOT * 3, rowptr, ws, [&](int r, const T* v) {
+    const unsigned short* rows = S.rows;          // the stage's live support rows
+    auto rowptr = [=](int i) {
+        const int r = rows[i];
+        return PK + ((long)vid[r / 3] * 3 + (r % 3)) * SFX_KPAD;
+    };
+    stream_rows_own<T>(GroupedRows{S.wptr, 0, 0}, rowptr, ws, [&](int i, const T* v, T) {
         T acc = 0;
 #pragma unroll
-        for (int i = 0; i < RowVec<T>::NE; ++i) acc += v[i] * c[i];
+        for (int k = 0; k < RowVec<T>::NE; ++k) acc += v[k] * c[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const int r = rows[i];
         if (lane == 0) S.vp[r] = S.vt_s[r] + acc;
-    });
+    }, NoAux(), false);
 }
 
 template <typename T>
@@ -201,12 +234,16 @@ __device__ __forceinline__ void blend_adjoint(const ModelView<T>& M, Scratch<T>&
     for (int i = 0; i < RowVec<T>::NE; ++i) acc[i] = 0;
     const T* PK = M.PK;
     const int* vid = S.vid;
-    auto rowptr = [=](int r) { return PK + ((long)vid[r / 3] * 3 + (r % 3)) * SFX_KPAD; };
-    stream_rows<T>(SFX_NSLOT * 3, rowptr, ws, [&](int r, const T* v) {
-        const T w = S.dvp[r];
+    const unsigned short* rows = S.rows;
+    auto rowptr = [=](int i) {
+        const int r = rows[i];
+        return PK + ((long)vid[r / 3] * 3 + (r % 3)) * SFX_KPAD;
+    };
+    stream_rows_own<T>(GroupedRows{S.wptr, 0, 0}, rowptr, ws, [&](int i, const T* v, T) {
+        const T w = S.dvp[rows[i]];
 #pragma unroll
-        for (int i = 0; i < RowVec<T>::NE; ++i) acc[i] += v[i] * w;
-    });
+        for (int k = 0; k < RowVec<T>::NE; ++k) acc[k] += v[k] * w;
+    }, NoAux(), false);
     // cross-warp reduction in a fixed order; the partial sums reuse the ring storage
     __syncthreads();
     T* part = reinterpret_cast<T*>(ws.ring);
@@ -264,16 +301,22 @@ __device__ __forceinline__ void blend_adjoint_ext(const ModelView<T>& M, Scratch
     const T* PK = M.PK;
     const int* vid = S.vid;
     const T* dvp = S.dvp;
-    constexpr int NS3 = SFX_NSLOT * 3;
-    auto rowptr = [=](int r) {
-        const long row = r < NS3 ? (long)vid[r / 3] * 3 + (r % 3)
-                                 : (long)tv[(r - NS3) / 3] * 3 + ((r - NS3) % 3);
+    const unsigned short* rows = S.rows;
+    const int NS3 = S.n_rows;                     // live support rows first, then the touched vertices'
+    auto rowptr = [=](int i) {
+        long row;
+        if (i < NS3) {
+            const int r = rows[i];
+            row = (long)vid[r / 3] * 3 + (r % 3);
+        } else {
+            row = (long)tv[(i - NS3) / 3] * 3 + ((i - NS3) % 3);
+        }
         return PK + row * SFX_KPAD;
     };
-    stream_rows_aux<T>(NS3 + 3 * S.n_touch, rowptr, ws, [&](int r, const T* v, T w) {
+    stream_rows_own<T>(GroupedRows{S.wptr, NS3, 3 * S.n_touch}, rowptr, ws, [&](int i, const T* v, T w) {
 #pragma unroll
-        for (int i = 0; i < RowVec<T>::NE; ++i) acc[i] += v[i] * w;
-    }, [=](int r) { return r < NS3 ? dvp[r] : dvpc[r - NS3]; }, true);
+        for (int k = 0; k < RowVec<T>::NE; ++k) acc[k] += v[k] * w;
+    }, [=](int i) { return i < NS3 ? dvp[rows[i]] : dvpc[i - NS3]; }, true);
     __syncthreads();
     T* part = reinterpret_cast<T*>(ws.ring);
 #pragma unroll
@@ -448,6 +491,150 @@ __device__ __noinline__ void two_loop_staged_n(Scratch<T>& S, int k, int head, i
     if (lane == 0) ws.tl_calls[0] += 1;
 }
 
+// ---- the same recursion, float32 only, written against shared-state-space addresses ---------
+// Every step of the recursion is one dependent chain (dot product -> warp sum -> scalar ->
+// axpy), executed by a single warp while the other fifteen wait: its length is what the longest
+// frames of a batch pay per L-BFGS iteration.  This version computes the shared-memory addresses
+// once (the generic-pointer version re-derives the shared window with S2R on every access),
+// counts the staging groups down instead of dividing, and fetches the per-pair scalars ahead of
+// the chain.  Arithmetic and summation order are unchanged (bit-identical, tested).
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ float warp_tree_sum_sa(float p, uint32_t slot, int lane) {
+    sts_f32(slot + 4u * lane, p);
+    __syncwarp();
+    float a[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(a[4 * i]), "=f"(a[4 * i + 1]), "=f"(a[4 * i + 2]), "=f"(a[4 * i + 3])
+                     : "r"(slot + 16u * i)
+                     : "memory");
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int l = 0; l < o; ++l) a[l] = a[l] + a[l + o];
+    return a[0];
+}
+
+template <int NR>
+__device__ __noinline__ void two_loop_staged_f32(Scratch<float>& S, int k, int head, int H, float hd,
+                                                 const float* __restrict__ hist_s,
+                                                 const float* __restrict__ hist_y, int D, StreamWS& ws) {
+    const int lane = threadIdx.x;
+    const uint32_t RB = (uint32_t)((D * sizeof(float) + 15) & ~(size_t)15);
+    const int per = (k + SFX_TL_GROUPS - 1) / SFX_TL_GROUPS;
+    const unsigned int parity = ws.tl_calls[0] & 1;
+    unsigned char* base = ws.ring;
+    if (lane == 0) {
+        fence_proxy_async();
+        int pos = (head + k - 1) % H;
+        for (int g = 0; g < SFX_TL_GROUPS; ++g) {
+            const int first = g * per;
+            const int n = first < k ? (k - first < per ? k - first : per) : 0;
+            mbar_expect_tx(ws.tl_bars + g, (uint32_t)n * 2 * RB);
+            for (int j = 0; j < n; ++j) {
+                unsigned char* dst = base + (size_t)(first + j) * 2 * RB;
+                bulk_g2s(dst, hist_s + (long)pos * SFX_NP_MAX, RB, ws.tl_bars + g);
+                bulk_g2s(dst + RB, hist_y + (long)pos * SFX_NP_MAX, RB, ws.tl_bars + g);
+                pos = pos == 0 ? H - 1 : pos - 1;
+            }
+        }
+    }
+    __syncwarp();
+    const bool tail_live = 32 * (NR - 1) + lane < D;
+    const uint32_t a_base = smem_u32(base) + 4u * lane;      // this lane's column of the staged pairs
+    const uint32_t a_red = smem_u32(S.tl_red), a_ro = smem_u32(S.ro), a_al = smem_u32(S.al);
+    float q[NR], sc[NR], yc[NR], sn[NR], yn[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int e = 32 * r + lane;
+        q[r] = e < D ? -S.g[e] : 0.f;
+    }
+#define SFX_TL_LOAD(dsts, dsty, idx)                                                   \
+    do {                                                                               \
+        const uint32_t as_ = a_base + (uint32_t)(idx) * 2u * RB, ay_ = as_ + RB;       \
+        _Pragma("unroll") for (int r = 0; r < NR - 1; ++r) {                           \
+            dsts[r] = lds_f32(as_ + 128u * r);                                         \
+            dsty[r] = lds_f32(ay_ + 128u * r);                                         \
+        }                                                                              \
+        dsts[NR - 1] = tail_live ? lds_f32(as_ + 128u * (NR - 1)) : 0.f;               \
+        dsty[NR - 1] = tail_live ? lds_f32(ay_ + 128u * (NR - 1)) : 0.f;               \
+    } while (0)
+    // ---- first loop: consumption index idx = 0 .. k-1  <->  pair i = k-1-idx ----
+    mbar_wait(ws.tl_bars, parity);
+    SFX_TL_LOAD(sn, yn, 0);
+    int next_group_at = per, group = 1;
+    for (int idx = 0; idx < k; ++idx) {
+        const int i = k - 1 - idx;
+        const float ro_i = lds_f32(a_ro + 4u * i);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { sc[r] = sn[r]; yc[r] = yn[r]; }
+        if (idx + 1 < k) {
+            if (idx + 1 == next_group_at) {
+                mbar_wait(ws.tl_bars + group, parity);
+                group += 1;
+                next_group_at += per;
+            }
+            SFX_TL_LOAD(sn, yn, idx + 1);
+        }
+        float p = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) p = p + sc[r] * q[r];
+        p = warp_tree_sum_sa(p, a_red + 128u * (i & 1), lane);
+        const float a = p * ro_i;
+        if (lane == 0) sts_f32(a_al + 4u * i, a);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) q[r] += -a * yc[r];
+    }
+    // groups that hold no pair still complete their phase: wait so every barrier is observed
+    for (int g = (k + per - 1) / per; g < SFX_TL_GROUPS; ++g) mbar_wait(ws.tl_bars + g, parity);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) q[r] = q[r] * hd;       // q now holds the direction d
+    __syncwarp();
+    // ---- second loop: pair i = 0 .. k-1  <->  idx = k-1-i (already in shared memory) ----
+    SFX_TL_LOAD(sn, yn, k - 1);
+    for (int i = 0; i < k; ++i) {
+        const float ro_i = lds_f32(a_ro + 4u * i), al_i = lds_f32(a_al + 4u * i);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { sc[r] = sn[r]; yc[r] = yn[r]; }
+        if (i + 1 < k) SFX_TL_LOAD(sn, yn, k - 2 - i);
+        float p = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) p = p + yc[r] * q[r];
+        p = warp_tree_sum_sa(p, a_red + 128u * (i & 1), lane);
+        const float co = al_i - p * ro_i;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) q[r] += co * sc[r];
+    }
+#undef SFX_TL_LOAD
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int e = 32 * r + lane;
+        if (e < D) S.d[e] = q[r];
+    }
+    __syncwarp();
+    if (lane == 0) ws.tl_calls[0] += 1;
+}
+
+template <typename T, int NR>
+__device__ __forceinline__ void two_loop_staged_pick(Scratch<T>& S, int k, int head, int H, T hd,
+                                                     const T* hist_s, const T* hist_y, int D, StreamWS& ws) {
+    if constexpr (sizeof(T) == 4) {
+        if (!ws.tl_generic) {
+            two_loop_staged_f32<NR>(S, k, head, H, hd, hist_s, hist_y, D, ws);
+            return;
+        }
+    }
+    two_loop_staged_n<T, NR>(S, k, head, H, hd, hist_s, hist_y, D, ws);
+}
+
 // returns false when the staged path does not apply (plain-load mode, or history too large for
 // the ring: float64, more than 128 active parameters with a long history)
 template <typename T>
@@ -457,8 +644,8 @@ __device__ __forceinline__ bool two_loop_staged(Scratch<T>& S, int k, int head, 
     const size_t RB = (D * sizeof(T) + 15) & ~(size_t)15;
     const size_t ring_bytes = (size_t)SFX_NWARP * SFX_NBUF * SFX_KPAD * sizeof(T);
     if (!ws.ring_mode || k < 1 || (size_t)k * 2 * RB > ring_bytes || D > 128) return false;
-    if (D <= 32) two_loop_staged_n<T, 1>(S, k, head, H, hd, hist_s, hist_y, D, ws);
-    else two_loop_staged_n<T, 4>(S, k, head, H, hd, hist_s, hist_y, D, ws);
+    if (D <= 32) two_loop_staged_pick<T, 1>(S, k, head, H, hd, hist_s, hist_y, D, ws);
+    else two_loop_staged_pick<T, 4>(S, k, head, H, hd, hist_s, hist_y, D, ws);
     return true;
 }
 

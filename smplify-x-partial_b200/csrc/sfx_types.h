@@ -22,6 +22,7 @@
 #define SFX_NW 8             // non-zero skinning weights kept per support vertex (dense fall-back beyond)
 #define SFX_MAX_BLOCKS 12    // parameter blocks of the optimised vector (for the gtol test)
 #define SFX_NLATENT 32       // VPoser latent size
+#define SFX_NSTREAM 15       // warps of a block that stream blend rows (warp 0 runs the kinematic chain)
 #define SFX_NPART_MAX 64     // body parts of the face segmentation (smplx_parts_segm.pkl: 55)
 
 // loss kinds (reference fitting.py:278-284)

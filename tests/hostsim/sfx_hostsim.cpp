@@ -11,6 +11,8 @@ static std::vector<double> g_trace;
 #define SFX_TRACE(v) g_trace.push_back(v)
 static std::vector<double> g_steps;
 static int g_hits_cap = 0;      // 0: the device's region size
+static int g_all_rows = 1;      // 1: a single evaluation streams every support row (it returns all joints,
+                                // like the device's eval with a joints output); 0: only the live rows
 #define SFX_TRACE_STEP(t) g_steps.push_back(t)
 #include "../../smplify-x-partial_b200/csrc/sfx_model_prep.h"
 
@@ -51,7 +53,7 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
     std::memset(&S, 0, sizeof(S));
     for (int i = 0; i < L.np; ++i) S.x[i] = params[i];
     support_begin_frame(M, S);
-    stage_setup(*st, jw, lowconf, conf, init_mask, M.K, S);
+    stage_setup(M, *st, jw, lowconf, conf, init_mask, M.K, S, joints_out != nullptr && !do_fit && g_all_rows);
     std::vector<T> hs((size_t)SFX_HIST * SFX_NP_MAX), hy((size_t)SFX_HIST * SFX_NP_MAX);
     CollWS<T> W;
     std::vector<T> vp_g, vert_g, dvert_g, dtri_g, big_box;
@@ -145,6 +147,7 @@ void hs_pair_terms(const double* ti, const double* tj, double sigma, double* los
     pair_terms(ti, tj, sigma, loss, gi);
 }
 void hs_set_hits_cap(int n) { g_hits_cap = n; }
+void hs_set_all_rows(int on) { g_all_rows = on; }
 int hs_last_touch(void* p) { SimHandle* h = (SimHandle*)p; return h->use_double ? h->d.last_touch : h->f.last_touch; }
 int hs_trace(double* out, int cap) {
     int n = (int)g_trace.size();

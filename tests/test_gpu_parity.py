@@ -139,6 +139,29 @@ def test_ring_and_direct_streams_agree(model32, monkeypatch):
     assert torch.equal(l0, l1) and torch.equal(g0, g1)
 
 
+def test_two_loop_variants_agree(model32, monkeypatch):
+    """Shared-address, generic-pointer (both TMA-staged) and block-wide two-loop recursion: a
+    whole stage ends with the same bits and the same evaluation count."""
+    ev = Cm.golden('ref_eval_f32.npz')
+    I = Cm.eval_case_inputs(ev, 'reg')
+    out = []
+    for env, generic in ((None, 0), ('SFX_TWO_LOOP_GENERIC', 0), (None, 1)):
+        if env:
+            monkeypatch.setenv(env, '1')
+        batch = _engine().FrameBatch(model32, 2)
+        _load(batch, I, 2)
+        I['stage'].generic_two_loop = generic
+        final = batch.fit_stage(I['stage'])
+        out.append((batch.get_params(), final.cpu().numpy(), batch.evals().cpu().numpy()))
+        if env:
+            monkeypatch.delenv(env)
+    I['stage'].generic_two_loop = 0
+    for o in out[1:]:
+        assert np.array_equal(out[0][0], o[0]) and np.array_equal(out[0][1], o[1])
+        assert np.array_equal(out[0][2], o[2])
+    assert out[0][2].min() > 60
+
+
 def test_tensor_core_mesh_against_simt(model32, monkeypatch):
     """tcgen05 / TMA blend kernel (tf32 inputs, fp32 accumulation) against the fp32 SIMT kernel
     on 130 frames (two frame tiles, ragged) with distinct parameters: the tf32 rounding of the

@@ -86,6 +86,36 @@ def test_vposer_latent_pose_f64(case):
     assert np.abs(r['joints'] - ev[case + '/joints']).max() < 1e-13
 
 
+@pytest.mark.parametrize('case', ['l2', 'reg', 'cam', 'camconf'])
+def test_skipping_dead_support_rows_is_exact(hs64, case):
+    """A stage streams only the support rows a keypoint with a non-zero weight depends on
+    (zero hand / face weights, undetected keypoints, the camera stage's dozen joints): loss and
+    gradient equal those of the evaluation that streams all 675 rows."""
+    ev = Cm.golden('ref_eval_f64.npz')
+    I = Cm.eval_case_inputs(ev, case)
+    I['stage'].face_joint_weight = 0.0          # as in the first annealing stages
+    conf = I['conf'].copy()
+    conf[30:40] = 0.0                            # a few undetected hand keypoints
+    run = lambda: hs64.eval(I['stage'], I['x'], I['gt'], conf, I['jw'], I['cam'], I['lowconf'],
+                            I['init_mask'], I['reg_pose'])
+    full = run()
+    hs64.lib.hs_set_all_rows(0)
+    try:
+        lean = run()
+    finally:
+        hs64.lib.hs_set_all_rows(1)
+    assert lean['loss'] == pytest.approx(full['loss'], rel=1e-15)
+    assert np.abs(lean['grad'] - full['grad']).max() <= 1e-13 * np.abs(full['grad']).max()
+    # joints of live keypoints are untouched; the face block is what was skipped
+    eff = I['jw'].copy()                          # per-stage weights (fit_single_frame.py:569-574)
+    eff[25:67] = I['stage'].hand_joint_weight
+    eff[67:] = I['stage'].face_joint_weight
+    eff[I['lowconf'].astype(bool)] = 0
+    live = (eff * conf != 0) if case in ('l2', 'reg') else I['init_mask'].astype(bool)
+    assert np.array_equal(lean['joints'][live], full['joints'][live])
+    assert not np.array_equal(lean['joints'], full['joints'])
+
+
 def test_gradient_against_finite_differences(hs64):
     ev = Cm.golden('ref_eval_f64.npz')
     I = Cm.eval_case_inputs(ev, 'reg')
