@@ -182,6 +182,19 @@ int32_t* sfx_batch_flags_dev(sfx_batch* b);
 int32_t* sfx_batch_passes_dev(sfx_batch* b);
 int sfx_batch_reset_counters(sfx_batch* b, void* stream);
 
+/* Evaluation metrics (reference utils.py:540-771, eval.py:14-44 compute_v2v): per-point error
+ * sqrt(sum((aligned est - gt)^2)) between B fitted and ground-truth point sets [B,N,3] (device,
+ * float32 or float64 per use_double) after an alignment:
+ *   mode 0 none; 1 Procrustes / similarity transform (ProcrustesAlignment.__call__);
+ *   2 pelvis: both sets minus the mean of their points hip0, hip1 (PelvisAlignment);
+ *   3 scale + translation only (ScaleAlignment).
+ * idx_dev (int32 [n]) selects a subset of the N points (eval.py `vids`) or is NULL with n == N;
+ * hip0 / hip1 index the selected points.  err_dev [B,n]; transform_dev NULL or [B,13]: scale,
+ * R[9] row major, t[3] applied to est. */
+int sfx_aligned_errors(const void* est_dev, const void* gt_dev, const int32_t* idx_dev, int32_t B,
+                       int32_t N, int32_t n, int32_t mode, int32_t hip0, int32_t hip1,
+                       int32_t use_double, void* err_dev, void* transform_dev, void* stream);
+
 const char* sfx_last_error(void);
 int sfx_version(void);
 

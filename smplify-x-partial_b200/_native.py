@@ -18,6 +18,7 @@ SFX_FLAG_NAN, SFX_FLAG_INF, SFX_FLAG_COLL_OVERFLOW = 1, 2, 4
 SFX_CAM_FX, SFX_CAM_FY, SFX_CAM_CX, SFX_CAM_CY, SFX_CAM_R, SFX_CAM_DW, SFX_CAM_TZ = 0, 1, 2, 3, 4, 13, 14
 
 LOSS_SMPLIFY, LOSS_CAMERA_INIT = 0, 1
+ALIGN_NONE, ALIGN_PROCRUSTES, ALIGN_PELVIS, ALIGN_SCALE = 0, 1, 2, 3
 OPT_LBFGSLS, OPT_ADAM = 0, 1
 PPRIOR_L2, PPRIOR_REGRESSION, PPRIOR_GMM, PPRIOR_LATENT = 0, 1, 2, 3
 
@@ -284,6 +285,7 @@ def load_library(path=None):
     lib.sfx_batch_passes_dev.argtypes = [vp]
     lib.sfx_batch_passes_dev.restype = vp
     lib.sfx_batch_reset_counters.argtypes = [vp, vp]
+    lib.sfx_aligned_errors.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.sfx_last_error.restype = C.c_char_p
     lib.sfx_version.restype = C.c_int
     if path is None:

@@ -19,6 +19,7 @@
 #include "sfx_stream.cuh"
 #include "sfx_mesh.cuh"
 #include "sfx_mesh_tc.cuh"
+#include "sfx_metrics.cuh"
 
 using namespace sfx;
 
@@ -554,6 +555,26 @@ static int upload_vposer(sfx_model* m, ModelView<T>& v, const T* w1, const T* b1
 extern "C" {
 
 const char* sfx_last_error(void) { return g_err.c_str(); }
+
+int sfx_aligned_errors(const void* est_dev, const void* gt_dev, const int32_t* idx_dev, int32_t B,
+                       int32_t N, int32_t n, int32_t mode, int32_t hip0, int32_t hip1,
+                       int32_t use_double, void* err_dev, void* transform_dev, void* stream) {
+    if (!est_dev || !gt_dev || !err_dev || B < 0 || N < 1 || n < 1 || (!idx_dev && n != N))
+        return fail(SFX_ERR_ARG, "bad argument");
+    if (mode < SFX_ALIGN_NONE || mode > SFX_ALIGN_SCALE) return fail(SFX_ERR_ARG, "unknown alignment");
+    if (mode == SFX_ALIGN_PELVIS && (hip0 < 0 || hip1 < 0 || hip0 >= n || hip1 >= n))
+        return fail(SFX_ERR_ARG, "pelvis alignment: hip index out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SFX_ERR_CUDA, "no CUDA device visible: libsfx has no CPU path");
+    std::string e = use_double
+        ? aligned_errors<double>((const double*)est_dev, (const double*)gt_dev, idx_dev, B, N, n, mode,
+                                 hip0, hip1, (double*)err_dev, (double*)transform_dev, (cudaStream_t)stream)
+        : aligned_errors<float>((const float*)est_dev, (const float*)gt_dev, idx_dev, B, N, n, mode,
+                                hip0, hip1, (float*)err_dev, (float*)transform_dev, (cudaStream_t)stream);
+    if (!e.empty()) return fail(SFX_ERR_CUDA, e);
+    return SFX_OK;
+}
 int sfx_version(void) { return 100; }
 
 int sfx_model_create(const sfx_model_desc* desc, sfx_model** out) {

@@ -417,6 +417,38 @@ def ref_eval_coll(inputs, dtype=torch.float64, tag='f64'):
     return out
 
 
+def ref_metrics():
+    """The reference's alignment classes (utils.py:540-801) and eval.py's compute_v2v loop on
+    seeded point sets: a rotated / scaled / noisy copy of a mesh-sized cloud, a reflected one
+    (exercises the det(R) = +1 fix) and a vertex subset."""
+    ref = ref_bridge.load()
+    U = ref.utils
+    rng = np.random.default_rng(21)
+    B, Np = 4, 600
+    gt = rng.normal(size=(B, Np, 3)) * np.array([0.3, 0.8, 0.2])
+    est = np.zeros_like(gt)
+    for b in range(B):
+        q, r = np.linalg.qr(rng.normal(size=(3, 3)))
+        q = q * np.sign(np.diag(r))
+        if (np.linalg.det(q) < 0) != (b == 1):   # frame 1 is a reflection: Z must flip the last axis
+            q[:, 0] *= -1
+        est[b] = (gt[b] @ q.T) * rng.uniform(0.5, 2.0) + rng.normal(size=3) + \
+            rng.normal(size=(Np, 3)) * 0.01
+    vids = np.sort(rng.choice(Np, size=200, replace=False))
+    out = {'est': est, 'gt': gt, 'vids': vids.astype(np.int64)}
+    pa, pe, sa = U.ProcrustesAlignmentMPJPE(), U.PelvisAlignmentMPJPE(), U.ScaleAlignment()
+    out['procrustes'] = np.stack([pa(est[b], gt[b])['point'] for b in range(B)])
+    out['procrustes_aligned'] = np.stack([U.ProcrustesAlignment()(est[b], gt[b]) for b in range(B)])
+    out['pelvis'] = np.stack([pe(est[b], gt[b])['point'] for b in range(B)])
+    out['scale_aligned'] = np.stack([sa(est[b], gt[b]) for b in range(B)])
+    out['none'] = np.stack([U.mpjpe(est[b], gt[b]) for b in range(B)])
+    out['procrustes_vids'] = np.stack([pa(est[b][vids], gt[b][vids])['point'] for b in range(B)])
+    out['pelvis_vids'] = np.stack([pe(est[b][vids], gt[b][vids])['point'] for b in range(B)])
+    np.savez_compressed(os.path.join(HERE, 'ref_metrics.npz'), **out)
+    print('ref_metrics: PA error mean', out['procrustes'].mean(), 'pelvis', out['pelvis'].mean())
+    return out
+
+
 def ref_stage(inputs, dtype=torch.float64, tag='f64', perturb=None, save=True):
     """Reference run_fitting + reference LBFGS on one body stage from the ref_eval start.
     ``perturb=(eps, seed)`` multiplies the start by 1 + eps * N(0,1) (envelope runs)."""
@@ -540,6 +572,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'envelope':
         ref_envelope(inp)
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'metrics':
+        ref_metrics()
+        raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'coll':
         ref_eval_coll(inp, torch.float64, 'f64')
         ref_eval_coll(inp, torch.float32, 'f32')
@@ -549,5 +584,6 @@ if __name__ == '__main__':
     ref_stage(inp, torch.float64, 'f64')
     ref_eval_coll(inp, torch.float64, 'f64')
     ref_eval_coll(inp, torch.float32, 'f32')
+    ref_metrics()
     ref_fit('02_cropped', inp)
     ref_fit('18_cropped', inp, cfg=cfg_smplifyx(), tag='ref_fit_18_vposer')
