@@ -177,7 +177,8 @@ struct Scratch {
     T vt_s[SFX_NSLOT * 3];    // template position of the support rows
     float ww[SFX_NSLOT * SFX_NW], jt_w[SFX_NSLOT * SFX_NW];    // skinning weights by slot / by joint
     unsigned char wj[SFX_NSLOT * SFX_NW], jt_slot[SFX_NSLOT * SFX_NW], wn[SFX_NSLOT];
-    int jt_ptr[SFX_NJ + 1];
+    int jt_ptr[SFX_NJ + 1];   // by-joint table of the static slots ...
+    int jtd_ptr[SFX_NJ + 1];  // ... and of the dynamic contour slots (entries from NSTATIC * NW on)
     int w_overflow, dynrow_cached;
     T bp[64];                 // VPoser: decoded body pose (63) and its gradient
     T dbp[64];
@@ -443,42 +444,40 @@ SFX_FN void support_slots(const ModelView<T>& M, Scratch<T>& S, int s_begin, int
         S.vid[s] = vid;
         S.bary[s] = b;
         for (int k = 0; k < 3; ++k) S.vt_s[3 * s + k] = M.vt[3L * vid + k];
-        const T* w = M.Wd + (long)vid * SFX_WROW;
-        int n = 0;
-        for (int j = 0; j < SFX_NJ; ++j) {
-            const T wj = w[j];
-            if (wj != (T)0) {
-                if (n < SFX_NW) {
-                    S.wj[s * SFX_NW + n] = (unsigned char)j;
-                    S.ww[s * SFX_NW + n] = (float)wj;      // model weights are float32: exact
-                }
-                ++n;
-            }
+        // the vertex's non-zero skinning weights, joints ascending (per-vertex lists of the model)
+        const int e0 = M.sk_ptr[vid], n = M.sk_ptr[vid + 1] - e0;
+        for (int e = 0; e < n && e < SFX_NW; ++e) {
+            S.wj[s * SFX_NW + e] = M.sk_j[e0 + e];
+            S.ww[s * SFX_NW + e] = (float)M.sk_w[e0 + e];  // model weights are float32: exact
         }
         S.wn[s] = (unsigned char)(n <= SFX_NW ? n : SFX_NW);
         if (n > SFX_NW) S.w_overflow = 1;                  // dense fall-back for this frame
     }
 }
 
-// by-joint transpose of the per-slot lists (entries of a joint in ascending slot order)
+// By-joint transpose of the per-slot lists of slots [s_begin, s_end) (entries of a joint in
+// ascending slot order), written from `base` on in jt_slot / jt_w with offsets ptr[0 .. NJ].
+// Two such tables exist: the static slots (built once per frame) and the dynamic contour slots
+// (rebuilt whenever the head's yaw crosses into another row of the look-up table -- every few
+// evaluations during a line search, which is why it is kept small).
 template <typename T>
-SFX_FN void support_by_joint(Scratch<T>& S) {
+SFX_FN void support_by_joint(Scratch<T>& S, int s_begin, int s_end, int* ptr, int base) {
     SFX_SYNC();
     SFX_FOR(j, SFX_NJ) {
         int cnt = 0;
-        for (int s = 0; s < SFX_NSLOT; ++s)
+        for (int s = s_begin; s < s_end; ++s)
             for (int e = 0; e < S.wn[s]; ++e) cnt += S.wj[s * SFX_NW + e] == j;
-        S.jt_ptr[j + 1] = cnt;
+        ptr[j + 1] = cnt;
     }
     SFX_SYNC();
     if (SFX_TID == 0) {
-        S.jt_ptr[0] = 0;
-        for (int j = 0; j < SFX_NJ; ++j) S.jt_ptr[j + 1] += S.jt_ptr[j];
+        ptr[0] = base;
+        for (int j = 0; j < SFX_NJ; ++j) ptr[j + 1] += ptr[j];
     }
     SFX_SYNC();
     SFX_FOR(j, SFX_NJ) {
-        int pos = S.jt_ptr[j];
-        for (int s = 0; s < SFX_NSLOT; ++s)
+        int pos = ptr[j];
+        for (int s = s_begin; s < s_end; ++s)
             for (int e = 0; e < S.wn[s]; ++e)
                 if (S.wj[s * SFX_NW + e] == j) {
                     S.jt_slot[pos] = (unsigned char)s;
@@ -499,7 +498,7 @@ SFX_FN void support_begin_frame(const ModelView<T>& M, Scratch<T>& S) {
     }
     SFX_SYNC();
     support_slots(M, S, 0, SFX_NSTATIC);
-    SFX_SYNC();
+    support_by_joint(S, 0, SFX_NSTATIC, S.jt_ptr, 0);
 }
 
 
@@ -779,7 +778,7 @@ SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>&
     if (S.dynrow != S.dynrow_cached) {          // uniform: dynrow was written before the barrier
         SFX_SYNC();
         support_slots(M, S, SFX_NSTATIC, SFX_NSLOT);
-        support_by_joint(S);
+        support_by_joint(S, SFX_NSTATIC, SFX_NSLOT, S.jtd_ptr, SFX_NSTATIC * SFX_NW);
         if (SFX_TID == 0) S.dynrow_cached = S.dynrow;
     }
     SFX_SYNC();
@@ -1128,7 +1127,12 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         int j = i / 12, r = (i % 12) / 4, cc = i % 4;
         T acc = 0;
         if (!S.w_overflow) {
+            // static slots, then the dynamic ones: ascending slot order
             for (int e = S.jt_ptr[j]; e < S.jt_ptr[j + 1]; ++e) {
+                const int s = S.jt_slot[e];
+                acc += (T)S.jt_w[e] * S.dvert[3 * s + r] * (cc < 3 ? S.vp[3 * s + cc] : (T)1);
+            }
+            for (int e = S.jtd_ptr[j]; e < S.jtd_ptr[j + 1]; ++e) {
                 const int s = S.jt_slot[e];
                 acc += (T)S.jt_w[e] * S.dvert[3 * s + r] * (cc < 3 ? S.vp[3 * s + cc] : (T)1);
             }
