@@ -987,7 +987,9 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     // interpenetration term: active in body stages with a positive weight (fitting.py:439)
     const bool coll = CW != nullptr && M.coll_ready && st.loss_kind == SFX_LOSS_SMPLIFY &&
                       st.coll_loss_weight > 0;
+    SFX_PROF_BEGIN(pp);
     pose_prologue(M, L, S, vposer, stream_ws);
+    if (!coll) SFX_PROF_END(S, 8, pp);
     // ---- 3. kinematic chain (warp 0) || blendshapes on the support vertices (every warp) ----
     SFX_PROF_BEGIN(bf);
     if (SFX_IS_WARP0) chain_forward(M, S);
@@ -1005,6 +1007,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     SFX_SYNC();
     SFX_PROF_END(S, 2, bf);
     if (coll) coll_mesh_and_penalty(M, S, *CW, (T)st.coll_sigma, (T)st.coll_loss_weight);
+    SFX_PROF_BEGIN(mid);
     // ---- 4. skinning of the support vertices ------------------------------------------
     SFX_FOR(s, SFX_NSLOT) {
         T Tm[12];
@@ -1147,6 +1150,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     SFX_SYNC();
     const bool coll_adj = coll && S.n_touch > 0;
     if (coll_adj) coll_skin_adjoint(M, S, *CW);
+    if (!coll) SFX_PROF_END(S, 9, mid);
     // ---- 8. adjoint of the chain (warp 0) || adjoint of the blendshapes (every warp) -----
     SFX_PROF_BEGIN(ba);
     if (SFX_IS_WARP0) chain_adjoint(M, S);
@@ -1159,6 +1163,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     }
     SFX_SYNC();
     SFX_PROF_END(S, 3, ba);
+    SFX_PROF_BEGIN(tail);
     // ---- 9. pose-feature gradient joins the chain's; Rodrigues adjoint; rest-joint adjoint --
     SFX_FOR(j, SFX_NJ) {
         if (j >= 1)
@@ -1334,6 +1339,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
                       (st.need_blend_grad ? S.n_rows + (coll ? 3 * S.n_touch : 0) : 0);
     }
     SFX_SYNC();
+    if (!coll) SFX_PROF_END(S, 10, tail);
     SFX_PROF_END(S, 0, eval);
 #ifdef SFX_TRACE
     SFX_TRACE((double)total);

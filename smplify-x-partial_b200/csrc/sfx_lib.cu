@@ -51,6 +51,7 @@ __device__ __forceinline__ StreamWS carve_stream(unsigned char* base, int ring_m
     ws.tl_calls = reinterpret_cast<unsigned int*>(ws.tl_bars + SFX_TL_GROUPS);
     ws.ring_mode = ring_mode & 1;
     ws.tl_generic = (ring_mode >> 1) & 1;
+    ws.stream_regs = (ring_mode >> 2) & 1;
     return ws;
 }
 
@@ -530,7 +531,8 @@ static int ring_mode_for(const sfx_model* m) {
     if (e && e[0] == '1') return 0;
     if (m->use_double) return 0;
     const char* g = getenv("SFX_TWO_LOOP_GENERIC");
-    return 1 | ((g && g[0] == '1') ? 2 : 0);
+    const char* r = getenv("SFX_STREAM_REGS");
+    return 1 | ((g && g[0] == '1') ? 2 : 0) | ((r && r[0] == '1') ? 4 : 0);
 }
 
 template <typename T>

@@ -29,6 +29,7 @@ struct StreamWS {
     unsigned int* tl_calls;     // [1] staged two-loop calls so far (phase tracking)
     int ring_mode;
     int tl_generic;             // debug: the generic-pointer staged recursion (A/B test)
+    int stream_regs;            // rows travel global -> registers, several in flight per warp (no ring)
 };
 #define SFX_TL_GROUPS 8
 
@@ -147,6 +148,28 @@ __device__ __forceinline__ void stream_rows_own(OWN own, RP rowptr, StreamWS& ws
         if ((i & 31) == 0) auxv = i + lane < count ? (T)auxf(own.index(warp, i + lane)) : (T)0;
         return __shfl_sync(0xffffffffu, auxv, i & 31);
     };
+    if (ws.stream_regs) {
+        // software pipeline in registers: PF rows of the warp in flight as plain 16-byte loads
+        constexpr int PF = 3;
+        T buf[PF][RowVec<T>::NE];
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+            if (u < count) load_row_regs<T>(rowptr(own.index(warp, u)), lane, buf[u]);
+        for (int i0 = 0; i0 < count; i0 += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int i = i0 + u;
+                if (i < count) {
+                    const T aux = aux_at(i);
+#pragma unroll
+                    for (int e = 0; e < RowVec<T>::NE; ++e) vals[e] = buf[u][e];
+                    if (i + PF < count) load_row_regs<T>(rowptr(own.index(warp, i + PF)), lane, buf[u]);
+                    fn(own.index(warp, i), vals, aux);
+                }
+            }
+        }
+        return;
+    }
     if (ws.ring_mode) {
         unsigned char* mybuf = ws.ring + (size_t)warp * SFX_NBUF * ROWB;
         uint64_t* mybar = ws.bars + warp * SFX_NBUF;
