@@ -52,6 +52,7 @@ __device__ __forceinline__ StreamWS carve_stream(unsigned char* base, int ring_m
     ws.ring_mode = ring_mode & 1;
     ws.tl_generic = (ring_mode >> 1) & 1;
     ws.stream_regs = (ring_mode >> 2) & 1;
+    ws.tl_shfl = (ring_mode >> 3) & 1;
     return ws;
 }
 
@@ -532,7 +533,8 @@ static int ring_mode_for(const sfx_model* m) {
     if (m->use_double) return 0;
     const char* g = getenv("SFX_TWO_LOOP_GENERIC");
     const char* r = getenv("SFX_STREAM_REGS");
-    return 1 | ((g && g[0] == '1') ? 2 : 0) | ((r && r[0] == '1') ? 4 : 0);
+    const char* h = getenv("SFX_TWO_LOOP_SHFL");
+    return 1 | ((g && g[0] == '1') ? 2 : 0) | ((r && r[0] == '1') ? 4 : 0) | ((h && h[0] == '1') ? 8 : 0);
 }
 
 template <typename T>

@@ -30,6 +30,7 @@ struct StreamWS {
     int ring_mode;
     int tl_generic;             // debug: the generic-pointer staged recursion (A/B test)
     int stream_regs;            // rows travel global -> registers, several in flight per warp (no ring)
+    int tl_shfl;                // A/B: shuffle butterfly instead of the shared-memory tree in the two-loop
 };
 #define SFX_TL_GROUPS 8
 
@@ -529,7 +530,14 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
+template <bool SHFL>
 __device__ __forceinline__ float warp_tree_sum_sa(float p, uint32_t slot, int lane) {
+    if (SHFL) {
+        // the same association through five shuffles
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p = p + __shfl_xor_sync(0xffffffffu, p, o);
+        return p;
+    }
     sts_f32(slot + 4u * lane, p);
     __syncwarp();
     float a[32];
@@ -546,7 +554,7 @@ __device__ __forceinline__ float warp_tree_sum_sa(float p, uint32_t slot, int la
     return a[0];
 }
 
-template <int NR>
+template <int NR, bool SHFL>
 __device__ __noinline__ void two_loop_staged_f32(Scratch<float>& S, int k, int head, int H, float hd,
                                                  const float* __restrict__ hist_s,
                                                  const float* __restrict__ hist_y, int D, StreamWS& ws) {
@@ -610,7 +618,7 @@ __device__ __noinline__ void two_loop_staged_f32(Scratch<float>& S, int k, int h
         float p = 0;
 #pragma unroll
         for (int r = 0; r < NR; ++r) p = p + sc[r] * q[r];
-        p = warp_tree_sum_sa(p, a_red + 128u * (i & 1), lane);
+        p = warp_tree_sum_sa<SHFL>(p, a_red + 128u * (i & 1), lane);
         const float a = p * ro_i;
         if (lane == 0) sts_f32(a_al + 4u * i, a);
 #pragma unroll
@@ -631,7 +639,7 @@ __device__ __noinline__ void two_loop_staged_f32(Scratch<float>& S, int k, int h
         float p = 0;
 #pragma unroll
         for (int r = 0; r < NR; ++r) p = p + yc[r] * q[r];
-        p = warp_tree_sum_sa(p, a_red + 128u * (i & 1), lane);
+        p = warp_tree_sum_sa<SHFL>(p, a_red + 128u * (i & 1), lane);
         const float co = al_i - p * ro_i;
 #pragma unroll
         for (int r = 0; r < NR; ++r) q[r] += co * sc[r];
@@ -651,7 +659,8 @@ __device__ __forceinline__ void two_loop_staged_pick(Scratch<T>& S, int k, int h
                                                      const T* hist_s, const T* hist_y, int D, StreamWS& ws) {
     if constexpr (sizeof(T) == 4) {
         if (!ws.tl_generic) {
-            two_loop_staged_f32<NR>(S, k, head, H, hd, hist_s, hist_y, D, ws);
+            if (ws.tl_shfl) two_loop_staged_f32<NR, true>(S, k, head, H, hd, hist_s, hist_y, D, ws);
+            else two_loop_staged_f32<NR, false>(S, k, head, H, hd, hist_s, hist_y, D, ws);
             return;
         }
     }
