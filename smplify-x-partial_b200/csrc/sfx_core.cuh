@@ -190,6 +190,9 @@ struct Scratch {
                               // 11 per-vertex gather, 12 skinning adjoint of touched vertices
     T gq[16];                 // mixture prior: per-component negative log-likelihood
     // interpenetration term: ordered-compaction state, touched-vertex count
+    float hand_c[2 * 12 * 45];    // hand PCA components of both hands (when there are <= 12 of them);
+    float pose_mean_c[SFX_NPOSE]; // the model stores them as float32, so a float copy is exact
+    int hand_cached;
     unsigned short rows[SFX_NSLOT * 3];   // support rows the stage needs (slots with a live keypoint),
                                           // grouped by the streaming warp that owns them (row % 15)
     unsigned short wptr[SFX_NSTREAM + 1]; // start of every warp's group in rows[]
@@ -497,6 +500,12 @@ SFX_FN void support_begin_frame(const ModelView<T>& M, Scratch<T>& S) {
         S.dynrow_cached = -1;
     }
     SFX_SYNC();
+    // small model constants every evaluation reads: keep them next to the data
+    if (SFX_TID == 0) S.hand_cached = M.NH <= 12;
+    if (M.NH <= 12)
+        SFX_FOR(i, 2 * M.NH * 45)
+            S.hand_c[i] = (float)(i < M.NH * 45 ? M.hand_l[i] : M.hand_r[i - M.NH * 45]);
+    SFX_FOR(i, SFX_NPOSE) S.pose_mean_c[i] = (float)M.pose_mean[i];
     support_slots(M, S, 0, SFX_NSTATIC);
     support_by_joint(S, 0, SFX_NSTATIC, S.jt_ptr, 0);
 }
@@ -715,14 +724,19 @@ SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>&
         else if (i < 75) v = S.x[L.off_reye + i - 72];
         else {
             int h = (i - 75) / 45, e = (i - 75) % 45;
-            const T* C = h ? M.hand_r : M.hand_l;
             const T* pc = S.x + (h ? L.off_rh : L.off_lh);
             T acc = 0;
-            for (int k = 0; k < L.n_hand; ++k) acc += pc[k] * C[k * 45 + e];
+            if (S.hand_cached) {
+                const float* C = S.hand_c + h * L.n_hand * 45;
+                for (int k = 0; k < L.n_hand; ++k) acc += pc[k] * (T)C[k * 45 + e];
+            } else {
+                const T* C = h ? M.hand_r : M.hand_l;
+                for (int k = 0; k < L.n_hand; ++k) acc += pc[k] * C[k * 45 + e];
+            }
             S.hand[h * 45 + e] = acc;
             v = acc;
         }
-        S.fp[i] = v + M.pose_mean[i];
+        S.fp[i] = v + (T)S.pose_mean_c[i];
     }
     SFX_FOR_FROM(i, 32, 192) {
         T v = 0;
@@ -1094,11 +1108,32 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.dp[3 * k + 1] = dpy;
         S.dp[3 * k + 2] = dpz;
     }
-    // data loss and camera-translation gradient (= sum_k dL/dp_k): four sums, one pass
+    // data loss and camera-translation gradient (= sum_k dL/dp_k) and, in body stages, the five
+    // sums of squares of the priors (pose, betas, expression, left hand, right hand; they only
+    // need the parameters): nine sums, one pass, one pair of barriers
+    const bool body = st.loss_kind == SFX_LOSS_SMPLIFY;
+    const bool latent_reg = vposer && reg_pose != nullptr && st.stage_index + 1 == st.num_stages;
     {
         const T* kl = S.kl;
         const T* dp = S.dp;
-        multi_sum<T>(4, K, [=](int q, int k) { return q == 0 ? kl[k] : dp[3 * k + q - 1]; }, S.red);
+        const T* pe = S.x + L.off_pose;
+        const T* be = S.x + L.off_betas;
+        const T* ex = S.x + L.off_expr;
+        const T* hv = S.hand;
+        const int n_pose = L.n_pose, n_betas = L.n_betas, n_expr = L.n_expr;
+        const bool reg = vposer ? latent_reg : st.pprior_kind == SFX_PPRIOR_REGRESSION;
+        multi_sum<T>(body ? 9 : 4, K > 64 ? K : 64, [=](int q, int i) -> T {
+            if (q < 4) return i < K ? (q == 0 ? kl[i] : dp[3 * i + q - 1]) : (T)0;
+            if (q == 4) {
+                if (i >= n_pose) return (T)0;
+                T d = reg ? pe[i] - reg_pose[i] : pe[i];
+                return d * d;
+            }
+            if (q == 5) return i < n_betas ? be[i] * be[i] : (T)0;
+            if (q == 6) return i < n_expr ? ex[i] * ex[i] : (T)0;
+            if (q == 7) return i < 45 ? hv[i] * hv[i] : (T)0;
+            return i < 45 ? hv[45 + i] * hv[45 + i] : (T)0;
+        }, S.red);
     }
     const T data_loss = S.red[0];
     const T gct[3] = {S.red[1], S.red[2], S.red[3]};
@@ -1201,11 +1236,9 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     const T hw2 = (T)st.hand_prior_weight * (T)st.hand_prior_weight;
     const T ew2 = (T)st.expr_prior_weight * (T)st.expr_prior_weight;
     const T bendw = (T)st.bending_prior_weight;
-    const bool body = st.loss_kind == SFX_LOSS_SMPLIFY;
     T gmm_val = 0;
     const bool use_gmm = body && st.pprior_kind == SFX_PPRIOR_GMM;
     if (use_gmm) gmm_val = gmm_prior(M, S.x + L.off_pose, S, S.dvp);    // c, dvp are free by now
-    const bool latent_reg = vposer && reg_pose != nullptr && st.stage_index + 1 == st.num_stages;
     if (vposer) {
         // gradient wrt the decoded body pose: data term (dfp) + bending prior, then the decoder
         SFX_SYNC();
@@ -1272,12 +1305,18 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
             if (body) gv += (T)2 * ew2 * S.x[i];
         } else if (i >= L.off_lh && i < L.off_lh + 2 * L.n_hand) {
             int h = (i - L.off_lh) / L.n_hand, k = (i - L.off_lh) % L.n_hand;
-            const T* C = (h ? M.hand_r : M.hand_l) + k * 45;
             const T* dh = S.dfp + 75 + 45 * h;
             const T* hv = S.hand + 45 * h;
             T acc = 0;
-            for (int e = 0; e < 45; ++e)
-                acc += C[e] * (dh[e] + (body ? (T)2 * hw2 * hv[e] : (T)0));
+            if (S.hand_cached) {
+                const float* C = S.hand_c + (h * L.n_hand + k) * 45;
+                for (int e = 0; e < 45; ++e)
+                    acc += (T)C[e] * (dh[e] + (body ? (T)2 * hw2 * hv[e] : (T)0));
+            } else {
+                const T* C = (h ? M.hand_r : M.hand_l) + k * 45;
+                for (int e = 0; e < 45; ++e)
+                    acc += C[e] * (dh[e] + (body ? (T)2 * hw2 * hv[e] : (T)0));
+            }
             gv = acc;
         }
         S.gfull[i] = gv;
@@ -1285,24 +1324,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     // ---- 11. total loss, summed in the order of fitting.py:457-460 ----------------------
     T total = data_loss;
     if (body) {
-        // five sums of squares at once: pose prior, betas, expression, left hand, right hand
-        const T* pe = S.x + L.off_pose;
-        const T* be = S.x + L.off_betas;
-        const T* ex = S.x + L.off_expr;
-        const T* hv = S.hand;
-        const int n_pose = L.n_pose, n_betas = L.n_betas, n_expr = L.n_expr;
-        const bool reg = vposer ? latent_reg : st.pprior_kind == SFX_PPRIOR_REGRESSION;
-        multi_sum<T>(5, 64, [=](int q, int i) -> T {
-            if (q == 0) {
-                if (i >= n_pose) return (T)0;
-                T d = reg ? pe[i] - reg_pose[i] : pe[i];
-                return d * d;
-            }
-            if (q == 1) return i < n_betas ? be[i] * be[i] : (T)0;
-            if (q == 2) return i < n_expr ? ex[i] * ex[i] : (T)0;
-            if (q == 3) return i < 45 ? hv[i] * hv[i] : (T)0;
-            return i < 45 ? hv[45 + i] * hv[45 + i] : (T)0;
-        }, S.red + 4);
+        // S.red[4..8]: the prior sums of squares taken together with the data term above
         const T pp = use_gmm ? gmm_val : S.red[4];
         total += pp * bpw2;
         total += S.red[5] * sw2;
