@@ -137,6 +137,19 @@ def test_ring_and_direct_streams_agree(model32, monkeypatch):
     monkeypatch.setenv('SFX_STREAM_DIRECT', '1')
     l1, g1, _ = batch.eval(I['stage'])
     assert torch.equal(l0, l1) and torch.equal(g0, g1)
+    # the register-pipelined variant (no ring) and the shuffle-sum two-loop are A/B switches of
+    # the same arithmetic
+    monkeypatch.delenv('SFX_STREAM_DIRECT')
+    monkeypatch.setenv('SFX_STREAM_REGS', '1')
+    l2, g2, _ = batch.eval(I['stage'])
+    assert torch.equal(l0, l2) and torch.equal(g0, g2)
+    monkeypatch.delenv('SFX_STREAM_REGS')
+    ref = batch.fit_stage(I['stage']).clone()
+    x_ref = batch.get_params()
+    monkeypatch.setenv('SFX_TWO_LOOP_SHFL', '1')
+    _load(batch, I, 2)
+    again = batch.fit_stage(I['stage'])
+    assert torch.equal(ref, again) and np.array_equal(x_ref, batch.get_params())
 
 
 def test_two_loop_variants_agree(model32, monkeypatch):
