@@ -98,8 +98,9 @@ int sfx_batch_layout(const sfx_batch* b, SfxLayout* out);
  * float32).  Needed before a stage with coll_loss_weight > 0 (SfxStage) is evaluated or fitted;
  * df_cone_height travels as SfxStage.coll_sigma. */
 int sfx_batch_enable_collisions(sfx_batch* b);
-/* Diagnostics of the term ([B][2] int32, device; NULL before sfx_batch_enable_collisions): the
- * largest number of candidate faces and of touched vertices any evaluation of the frame saw. */
+/* Diagnostics of the term ([B][4] int32, device; NULL before sfx_batch_enable_collisions), per
+ * frame the largest value any of its evaluations saw: candidate faces, touched vertices, and for
+ * warp 0 (which owns 1/16 of the candidates) sweep iterations and listed partner faces. */
 int32_t* sfx_batch_coll_stat_dev(sfx_batch* b);
 
 /* Targets of every frame (host pointers; copied with cudaMemcpyAsync on `stream`):

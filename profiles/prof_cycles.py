@@ -42,3 +42,4 @@ cs = batch.coll_stats()
 if cs is not None:
     cs = cs.cpu().numpy()
     print('candidates per frame (max over evals): median %d max %d; touched vertices: median %d max %d' % (np.median(cs[:,0]), cs[:,0].max(), np.median(cs[:,1]), cs[:,1].max()))
+    print('warp 0 (1/16 of the candidates): sweep iterations median %d max %d; listed partners median %d max %d; slowest frame: cand %d iters %d hits %d' % (np.median(cs[:,2]), cs[:,2].max(), np.median(cs[:,3]), cs[:,3].max(), cs[i,0], cs[i,2], cs[i,3]))

@@ -34,6 +34,7 @@ struct CollWS {
     T* dtri_g;             // [F][9] dL/d(own corners) of faces that collided
     unsigned short* tv_g;  // [V]   touched vertices of the current evaluation, ascending
     T* fbox;               // [F][6] axis-aligned box of every face
+    T* ftri;               // [F][9] its three corners, contiguous (one 36-byte read per partner)
     unsigned char* sort_g; // [SFX_COLL_ENTRY * SFX_COLL_SORT_G] sweep arrays when they outgrow the shared area
     unsigned short* hits_g;     // [threads][hits_cap] per-thread lists: (count, partner faces...) per candidate
     int hits_cap;
@@ -41,8 +42,7 @@ struct CollWS {
     int work_bytes;
 };
 #define SFX_COLL_SORT_G 32768      // capacity of the global sweep arrays (power of two >= F)
-#define SFX_COLL_LARGE 256         // capacity of the list of long candidates
-#define SFX_COLL_LARGE_GOAL 192    // the short / long threshold aims at no more long candidates than this
+#define SFX_COLL_CLASSES 4         // extent classes of the sweep (quantised extent <= 4, 16, 64, any)
 #define SFX_COLL_ENTRY 12          // bytes per candidate: packed part + quantised box 8, key 2, face 2
 #define SFX_COLL_HITS 2048         // per-thread region of the potential-hit list (16-bit entries)
 
@@ -55,6 +55,7 @@ SFX_FN CollWS<T> coll_block_ws(int V, int F, T* vals, unsigned short* idx, unsig
     W.dvert_g = vals + 6L * V;
     W.dtri_g = vals + 9L * V;
     W.fbox = vals + 9L * V + 9L * F;
+    W.ftri = vals + 9L * V + 15L * F;
     W.tv_g = idx;
     W.sort_g = reinterpret_cast<unsigned char*>(idx + (V + 7) / 8 * 8);
     W.hits_g = idx + (V + 7) / 8 * 8 + (long)SFX_COLL_ENTRY * SFX_COLL_SORT_G / 2;
@@ -63,7 +64,7 @@ SFX_FN CollWS<T> coll_block_ws(int V, int F, T* vals, unsigned short* idx, unsig
     W.work_bytes = work_bytes;
     return W;
 }
-inline long coll_vals_per_block(int V, int F) { return (9L * V + 15L * F + 3) / 4 * 4; }
+inline long coll_vals_per_block(int V, int F) { return (9L * V + 24L * F + 3) / 4 * 4; }
 inline long coll_idx_per_block(int V, int F) { return ((long)V + 7) / 8 * 8 + (long)SFX_COLL_ENTRY * SFX_COLL_SORT_G / 2 + 512L * SFX_COLL_HITS; }
 
 template <typename T>
@@ -324,13 +325,13 @@ struct CollArea {
     int cap;                     // candidate capacity (a power of two)
     int cap_lean;                // ... when the packed entries move out to global memory
     unsigned char* sort_base;    // start of the sweep arrays inside the work area
-    unsigned short* skey;        // [cap] box minimum along the sweep axis on a 65536-level grid, ascending after the sort
+    unsigned short* skey;        // [cap] extent class << 14 | box minimum along the sweep axis on a 16384-level
+                                 // grid: after the sort one ascending run per class
     unsigned short* sface;       // [cap] face of the candidate
     unsigned long long* pk;      // [cap] packed: bytes 0-2 box minimum on a 256-level grid over the body's box
-                                 // (rounded outwards), byte 3 part | 0x80 when long along the sweep axis,
+                                 // (rounded outwards), byte 3 part,
                                  // bytes 4-6 box maximum, byte 7 unused
-    int* hist;                   // [256] candidates by quantised extent along the sweep axis
-    unsigned short* large;       // [SFX_COLL_LARGE] sorted positions of the long candidates
+    int* cseg;                   // [SFX_COLL_CLASSES + 1] segments of the sorted order, one per extent class
     unsigned int* hit;           // [(F + 31) / 32] faces that collided
     unsigned int* vtouch;        // [(V + 31) / 32] vertices of such faces
     T* part_loss;                // [SFX_NT] per-thread partial sums
@@ -363,8 +364,7 @@ SFX_FN CollArea<T> coll_area(const ModelView<T>& M, const CollWS<T>& W, int nthr
     A.part_loss = reinterpret_cast<T*>(p); p += (size_t)nthreads * sizeof(T);
     A.hit = reinterpret_cast<unsigned int*>(p); p += ((M.F + 31) / 32 + 1) / 2 * 8;
     A.vtouch = reinterpret_cast<unsigned int*>(p); p += ((M.V + 31) / 32 + 1) / 2 * 8;
-    A.large = reinterpret_cast<unsigned short*>(p); p += SFX_COLL_LARGE * 2;
-    A.hist = reinterpret_cast<int*>(p); p += 256 * 4;
+    A.cseg = reinterpret_cast<int*>(p); p += 8 * 4;
     const long left = (long)W.work_bytes - (long)(p - W.work);
     int cap = 0;
     for (int c = 64; (long)SFX_COLL_ENTRY * c <= left && c <= SFX_COLL_SORT_G; c <<= 1) cap = c;
@@ -412,56 +412,78 @@ SFX_FN bool pk_overlap(unsigned long long a, unsigned long long b) {
 #endif
 }
 
+// First index in [lo, hi) of the ascending 14-bit keys that is >= target (hi if none), found by
+// the whole warp: 32 evenly spaced probes per round instead of one, three rounds for 8192 keys.
+SFX_FN int warp_lower_bound(const unsigned short* skey, int lo, int hi, int target, int lane, int LW) {
+#ifdef __CUDACC__
+    while (lo < hi) {
+        const int step = (hi - lo + LW - 1) / LW;
+        const int p = lo + lane * step;
+        const bool below = p < hi && (int)(skey[p] & 0x3fffu) < target;
+        const int c = __popc(__ballot_sync(0xffffffffu, below));      // sorted: a prefix of the probes
+        if (c == 0) return lo;
+        const int pc = lo + c * step;
+        lo = lo + (c - 1) * step + 1;
+        hi = pc < hi ? pc : hi;
+    }
+    return lo;
+#else
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if ((int)(skey[m] & 0x3fffu) < target) lo = m + 1; else hi = m;
+    }
+    return lo;
+#endif
+}
+
+// quantised extent along the sweep axis -> class; a class's bound is the largest extent in it
+SFX_FN int coll_class(int ext) { return ext <= 4 ? 0 : (ext <= 16 ? 1 : (ext <= 64 ? 2 : 3)); }
+SFX_FN int coll_class_bound(int c) { return c == 0 ? 4 : (c == 1 ? 16 : (c == 2 ? 64 : 255)); }
+
 // Partners of the candidate at sorted position pos, enumerated by one warp: every lane calls
 // visit(face, ok) once per step of the walk, ok marking a candidate whose part is admissible and
-// whose (quantised) box overlaps; each partner shows up exactly once, in sorted order.  A short
-// candidate meets other short ones inside a window of the sorted order (backwards no further than
-// the longest short extent, forwards up to its own maximum; both ends by binary search) and the
-// long ones through their list; a long candidate scans everything.
+// whose (quantised) box overlaps; each partner shows up exactly once, in sorted order.
+// The candidates are sorted by (extent class, box minimum along the sweep axis): four ascending
+// runs.  In the run of class c a partner can only overlap if its key lies between the
+// candidate's own key minus the class's extent bound and the candidate's maximum -- two binary
+// searches, then a window whose length follows the partners' size instead of the largest
+// triangle of the mesh.
 template <typename T, typename VISIT>
-SFX_FN void coll_partners(const CollArea<T>& A, int pos, int ncand, int nlarge, int axis, int E16,
-                          int lane, int LW, VISIT visit) {
+SFX_FN void coll_partners(const CollArea<T>& A, int pos, int axis, int lane, int LW, VISIT visit) {
     const unsigned long long me = A.pk[pos];
     const unsigned long long allow = A.pmask[(pk_lo(me) >> 24) & 0x7f];
-    const bool me_long = (pk_lo(me) >> 31) & 1u;
-    int lo = 0, hi = ncand;
-    if (!me_long) {
-        // 8-bit level q covers 257 of the 16-bit key levels; the box maximum is rounded up
-        const int kmin = (int)A.skey[pos] - E16;
-        const int kmax = (int)(((pk_hi(me) >> (8 * axis)) & 255u) + 1u) * 257;
-        int a = 0, b = pos;                  // first index with key >= kmin
-        while (a < b) { const int m = (a + b) >> 1; if ((int)A.skey[m] < kmin) a = m + 1; else b = m; }
-        lo = a;
-        a = pos + 1; b = ncand;              // first index with key > kmax
-        while (a < b) { const int m = (a + b) >> 1; if ((int)A.skey[m] <= kmax) a = m + 1; else b = m; }
-        hi = a;
-    }
-    const int nwin = hi - lo;
-    const int nsteps = nwin + (me_long ? 0 : nlarge);
-    for (int s0 = 0; s0 < nsteps; s0 += LW) {
-        const int s = s0 + lane;
-        bool ok = s < nsteps;
-        int fj = 0;
-        if (ok) {
-            const int b = s < nwin ? lo + s : (int)A.large[s - nwin];
-            const unsigned long long e = A.pk[b];
-            // long ones come through the list; the quantised boxes are rounded outwards: a
-            // superset of the exact box overlaps, the separating-axis test sorts out the rest
-            ok = b != pos && !(s < nwin && !me_long && ((pk_lo(e) >> 31) & 1u)) &&
-                 ((allow >> ((pk_lo(e) >> 24) & 0x7f)) & 1ull) && pk_overlap(me, e);
-            fj = A.sface[b];
+    // one 8-bit level of the box grid spans 64.25 levels of the 14-bit key grid; boxes are
+    // rounded outwards, so these bounds are conservative
+    const int key = (int)(A.skey[pos] & 0x3fffu);
+    const int kmax = (int)(((pk_hi(me) >> (8 * axis)) & 255u) + 1u) * 65;
+    for (int c = 0; c < SFX_COLL_CLASSES; ++c) {
+        const int s0 = A.cseg[c], s1 = A.cseg[c + 1];
+        if (s0 == s1) continue;
+        const int kmin = key - (coll_class_bound(c) * 65 + 2);
+        const int lo = warp_lower_bound(A.skey, s0, s1, kmin, lane, LW);       // first key >= kmin
+        const int hi = warp_lower_bound(A.skey, lo, s1, kmax + 1, lane, LW);   // first key > kmax
+        // Box test first (two byte-SIMD compares); the part filter and the face id only for the
+        // few that pass.  The quantised boxes are rounded outwards: a superset of the exact box
+        // overlaps, the separating-axis test sorts out the rest.
+        for (int t0 = lo; t0 < hi; t0 += LW) {
+            const int p = t0 + lane;
+            bool ok = false;
+            int fj = 0;
+            if (p < hi) {
+                const unsigned long long e = A.pk[p];
+                if (pk_overlap(me, e) && p != pos) {
+                    ok = (allow >> ((pk_lo(e) >> 24) & 0x7fu)) & 1ull;
+                    fj = A.sface[p];
+                }
+            }
+            visit(fj, ok);
         }
-        visit(fj, ok);
     }
 }
 
 // separating-axis test + penalty of one listed partner
 template <typename T>
-SFX_FN void coll_pair(const ModelView<T>& M, const T* vert, int fi, const T* ti, int fj, T sigma,
-                      bool* hit, T* loss_i, T* gi) {
-    T tj[9];
-    int idj[3];
-    face_corners(M, vert, fj, tj, idj);
+SFX_FN void coll_pair_loaded(int fi, const T* ti, int fj, const T* tj, T sigma, bool* hit, T* loss_i, T* gi) {
     // the package compares corner coordinates (shareVertex); so do we
     bool share = false;
     for (int a = 0; a < 3; ++a)
@@ -472,6 +494,12 @@ SFX_FN void coll_pair(const ModelView<T>& M, const T* vert, int fi, const T* ti,
         *hit = true;
         pair_terms(ti, tj, sigma, loss_i, gi);
     }
+}
+template <typename T>
+SFX_FN void coll_pair(const T* ftri, int fi, const T* ti, int fj, T sigma, bool* hit, T* loss_i, T* gi) {
+    T tj[9];
+    for (int d = 0; d < 9; ++d) tj[d] = ftri[(long)fj * 9 + d];
+    coll_pair_loaded(fi, ti, fj, tj, sigma, hit, loss_i, gi);
 }
 
 // Search + penalty + per-vertex gradients.  On return: S.coll_loss (unweighted sum over the
@@ -492,6 +520,7 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
         face_corners(M, vert, f, tri, ids);
         tri_box(tri, box);
         for (int d = 0; d < 6; ++d) W.fbox[(long)f * 6 + d] = box[d];
+        for (int d = 0; d < 9; ++d) W.ftri[(long)f * 9 + d] = tri[d];
     }
     SFX_FOR(i, (F + 31) / 32) A.hit[i] = 0;
     SFX_FOR(i, (V + 31) / 32) A.vtouch[i] = 0;
@@ -605,8 +634,16 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
                         if (((m >> q) & 1ull) && boxes_overlap(box, A.pbox + 6 * q))
                             for (int c = M.part_cl_ptr[q]; c < M.part_cl_ptr[q + 1] && !cand; ++c)
                                 cand = boxes_overlap(box, A.cbox + 6 * c);
-                    key = (int)floorf((float)((box[axis] - blo[axis]) * bsc[axis]) * 257.f);
-                    key = key < 0 ? 0 : (key > 65535 ? 65535 : key);
+                    // 14-bit key of the box minimum and the extent class, both on grids derived
+                    // from the same 256-level box grid as the packed entries below
+                    const float qlo = (float)((box[axis] - blo[axis]) * bsc[axis]);
+                    const float qhi = (float)((box[3 + axis] - blo[axis]) * bsc[axis]);
+                    int k14 = (int)floorf(qlo * 64.25f);
+                    k14 = k14 < 0 ? 0 : (k14 > 16383 ? 16383 : k14);
+                    int e0 = (int)floorf(qlo - 1e-3f), e1 = (int)ceilf(qhi + 1e-3f);
+                    e0 = e0 < 0 ? 0 : (e0 > 255 ? 255 : e0);
+                    e1 = e1 < 0 ? 0 : (e1 > 255 ? 255 : e1);
+                    key = (coll_class(e1 - e0) << 14) | k14;
                 }
             }
             const int slot = ordered_slot(cand, S);
@@ -660,8 +697,6 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
             SFX_SYNC();
         }
     // ---- quantised boxes (256 levels over the body's box, rounded outwards) ----
-    SFX_FOR(i, 256) A.hist[i] = 0;
-    SFX_SYNC();
     SFX_FOR(c, ncand) {
         const T* fb = W.fbox + (long)A.sface[c] * 6;
         int q[6];
@@ -677,42 +712,14 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
         A.pk[c] = (unsigned long long)((unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16) |
                                        ((unsigned)M.face_part[A.sface[c]] << 24)) |
                   ((unsigned long long)((unsigned)q[3] | ((unsigned)q[4] << 8) | ((unsigned)q[5] << 16)) << 32);
-#ifdef __CUDACC__
-        atomicAdd(&A.hist[q[3 + axis] - q[axis]], 1);     // integer counts: order does not matter
-#else
-        A.hist[q[3 + axis] - q[axis]] += 1;
-#endif
+    }
+    // where each extent class starts in the sorted order
+    SFX_FOR(c, SFX_COLL_CLASSES + 1) {
+        int a = 0, b = ncand;
+        while (a < b) { const int m = (a + b) >> 1; if ((int)(A.skey[m] >> 14) < c) a = m + 1; else b = m; }
+        A.cseg[c] = a;
     }
     SFX_SYNC();
-    // ---- short / long candidates: the smallest extent threshold that leaves at most
-    // SFX_COLL_LARGE_GOAL long ones (long ones scan everything, short ones a window) ----
-    int Eq = 255;
-    {
-        int above = 0;
-        while (Eq > 0 && above + A.hist[Eq] <= SFX_COLL_LARGE_GOAL) {
-            above += A.hist[Eq];
-            Eq -= 1;
-        }
-    }
-    const int E16 = Eq * 257 + 2;            // the same bound on the 65536-level key grid
-    if (SFX_TID == 0) {
-        S.cscan_total = 0;
-        S.cscan_calls = 0;
-    }
-    SFX_SYNC();
-    for (int c0 = 0; c0 < ncand; c0 += SFX_NT) {
-        const int c = c0 + SFX_TID;
-        bool big = false;
-        if (c < ncand) {
-            const unsigned long long e = A.pk[c];
-            big = (int)((pk_hi(e) >> (8 * axis)) & 255u) - (int)((pk_lo(e) >> (8 * axis)) & 255u) > Eq;
-            if (big) A.pk[c] = e | (0x80ull << 24);
-        }
-        const int slot = ordered_slot(big, S);
-        if (big && slot < SFX_COLL_LARGE) A.large[slot] = (unsigned short)c;
-    }
-    SFX_SYNC();
-    const int nlarge = S.cscan_total;       // <= SFX_COLL_LARGE_GOAL by construction
     // ---- walk + narrow phase, a warp per candidate, in chunks ----
     // Walk: the warp lists the box-overlapping, admissible partners of the candidates it owns
     // (sorted positions warp, warp + 16, ...) in its own region, (count, faces...) per candidate;
@@ -728,6 +735,7 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
     const int HCW = W.hits_cap * LW;                 // the warp's region: its lanes' regions together
     unsigned short* myhits = W.hits_g + (long)warp * HCW;
     T my_loss = 0;
+    int walk_iters = 0, walk_hits = 0;      // diagnostics (warp 0): window steps / 32, listed partners
     SFX_PROF_END(S, 9, cb);
     for (int pos0 = warp; pos0 < ncand;) {
         // ---- walk: a warp per candidate, lanes side by side through the window ----
@@ -736,19 +744,21 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
         for (; pos1 < ncand && w + HCW / 2 <= HCW; pos1 += NWP) {
             const int head = w++;
             int cnt = 0;
-            coll_partners(A, pos1, ncand, nlarge, axis, E16, lane, LW, [&](int fj, bool ok) {
+            coll_partners(A, pos1, axis, lane, LW, [&](int fj, bool ok) {
 #ifdef __CUDACC__
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
                 const int slot = w + __popc(m & ((1u << lane) - 1u)), n = __popc(m);
 #else
                 const int slot = w, n = ok ? 1 : 0;
 #endif
+                walk_iters += 1;
                 if (ok && slot < HCW) myhits[slot] = (unsigned short)fj;
                 w += n;
                 cnt += n;
             });
             // a candidate with more box partners than the region holds (or than a 16-bit count)
             // is walked again in the narrow phase, partner by partner
+            walk_hits += cnt;
             if (w > HCW || cnt >= 0xffff) { w = head + 1; cnt = 0xffff; }
             if (lane == 0) myhits[head] = (unsigned short)cnt;
         }
@@ -768,12 +778,27 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
             for (int d = 0; d < 10; ++d) acc[d] = 0;
             bool hit = false;
             if (cnt == 0xffff) {
-                coll_partners(A, pos, ncand, nlarge, axis, E16, lane, LW, [&](int fj, bool ok) {
-                    if (ok) coll_pair(M, vert, fi, ti, fj, sigma, &hit, acc + 9, acc);
+                coll_partners(A, pos, axis, lane, LW, [&](int fj, bool ok) {
+                    if (ok) coll_pair(W.ftri, fi, ti, fj, sigma, &hit, acc + 9, acc);
                 });
             } else {
-                for (int h = lane; h < cnt; h += LW)
-                    coll_pair(M, vert, fi, ti, (int)myhits[r + h], sigma, &hit, acc + 9, acc);
+                // the partner's corners of the next round travel while this round's test runs
+                T tn[9];
+                int fn = 0;
+                if (lane < cnt) {
+                    fn = myhits[r + lane];
+                    for (int d = 0; d < 9; ++d) tn[d] = W.ftri[(long)fn * 9 + d];
+                }
+                for (int h = lane; h < cnt; h += LW) {
+                    T tj[9];
+                    const int fj = fn;
+                    for (int d = 0; d < 9; ++d) tj[d] = tn[d];
+                    if (h + LW < cnt) {
+                        fn = myhits[r + h + LW];
+                        for (int d = 0; d < 9; ++d) tn[d] = W.ftri[(long)fn * 9 + d];
+                    }
+                    coll_pair_loaded(fi, ti, fj, tj, sigma, &hit, acc + 9, acc);
+                }
                 r += cnt;
             }
 #ifdef __CUDACC__
@@ -797,6 +822,10 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
         SFX_SYNCWARP();
         SFX_PROF_END(S, 14, ch);
         pos0 = pos1;
+    }
+    if (SFX_TID == 0) {
+        if (walk_iters > S.coll_max_iters) S.coll_max_iters = walk_iters;
+        if (walk_hits > S.coll_max_hits) S.coll_max_hits = walk_hits;
     }
     SFX_PROF_BEGIN(cn);
     A.part_loss[SFX_TID] = my_loss;

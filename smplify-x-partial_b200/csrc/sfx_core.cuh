@@ -138,11 +138,12 @@ struct BatchView {
     const int* frame_ids;   // optional indirection (nullptr: block b -> frame b)
     long long* prof;        // [B][16] cycle counters (builds with -DSFX_CYCLE_PROF only)
     // interpenetration term: global workspace, one slot per block (nullptr until
-    // sfx_batch_enable_collisions).  Values: vp[3V] | vert[3V] | dvert[3V] | dtri[9F] | box[6F];
+    // sfx_batch_enable_collisions).  Values: vp[3V] | vert[3V] | dvert[3V] | dtri[9F] | box[6F] | tri[9F];
     // indices: tv[V] | face[F]
     T* coll_vals;
     unsigned short* coll_idx;
-    int* coll_stat;         // [B][2] largest candidate / touched-vertex count of a frame's evaluations
+    int* coll_stat;         // [B][4] per frame, largest over its evaluations: candidates, touched vertices,
+                            // sweep iterations and listed partners of warp 0 (1/16 of the candidates)
     long coll_vals_stride, coll_idx_stride;
 };
 
@@ -199,7 +200,7 @@ struct Scratch {
     unsigned char slot_live[SFX_NSLOT];
     int n_rows;
     int cscan[2][32];
-    int cscan_total, cscan_calls, coll_overflow, n_touch, coll_max_cand, coll_max_touch;
+    int cscan_total, cscan_calls, coll_overflow, n_touch, coll_max_cand, coll_max_touch, coll_max_iters, coll_max_hits;
     T coll_loss;
     T loss;
     int dynrow;

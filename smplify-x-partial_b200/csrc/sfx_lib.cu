@@ -70,7 +70,7 @@ __device__ __forceinline__ void load_frame(const BatchView<T>& Bv, int f, Scratc
         S.n_evals = S.n_passes = 0;
         S.n_touch = 0;
         S.coll_overflow = 0;
-        S.coll_max_cand = S.coll_max_touch = 0;
+        S.coll_max_cand = S.coll_max_touch = S.coll_max_iters = S.coll_max_hits = 0;
         for (int i = 0; i < 16; ++i) S.prof[i] = 0;
     }
     __syncthreads();
@@ -124,8 +124,10 @@ fit_stage_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__
     __syncthreads();
     if (threadIdx.x == 0 && S.coll_overflow) flags |= SFX_FLAG_COLL_OVERFLOW;
     if (threadIdx.x == 0 && Bv.coll_stat) {
-        Bv.coll_stat[2 * f] = max(Bv.coll_stat[2 * f], S.coll_max_cand);
-        Bv.coll_stat[2 * f + 1] = max(Bv.coll_stat[2 * f + 1], S.coll_max_touch);
+        Bv.coll_stat[4 * f] = max(Bv.coll_stat[4 * f], S.coll_max_cand);
+        Bv.coll_stat[4 * f + 1] = max(Bv.coll_stat[4 * f + 1], S.coll_max_touch);
+        Bv.coll_stat[4 * f + 2] = max(Bv.coll_stat[4 * f + 2], S.coll_max_iters);
+        Bv.coll_stat[4 * f + 3] = max(Bv.coll_stat[4 * f + 3], S.coll_max_hits);
     }
     const int np = Bv.lay.np;
     for (int i = threadIdx.x; i < np; i += blockDim.x) Bv.params[(size_t)f * np + i] = S.x[i];
@@ -164,8 +166,10 @@ eval_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ Batc
                has_coll ? &CW : nullptr);
     if (threadIdx.x == 0 && S.coll_overflow) Bv.flags[f] |= SFX_FLAG_COLL_OVERFLOW;
     if (threadIdx.x == 0 && Bv.coll_stat) {
-        Bv.coll_stat[2 * f] = max(Bv.coll_stat[2 * f], S.coll_max_cand);
-        Bv.coll_stat[2 * f + 1] = max(Bv.coll_stat[2 * f + 1], S.coll_max_touch);
+        Bv.coll_stat[4 * f] = max(Bv.coll_stat[4 * f], S.coll_max_cand);
+        Bv.coll_stat[4 * f + 1] = max(Bv.coll_stat[4 * f + 1], S.coll_max_touch);
+        Bv.coll_stat[4 * f + 2] = max(Bv.coll_stat[4 * f + 2], S.coll_max_iters);
+        Bv.coll_stat[4 * f + 3] = max(Bv.coll_stat[4 * f + 3], S.coll_max_hits);
     }
     const int np = Bv.lay.np;
     if (loss_out && threadIdx.x == 0) loss_out[f] = S.loss;
@@ -402,8 +406,10 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
             Bv.n_passes[f] += S.n_passes;
             Bv.flags[f] |= flags | (S.coll_overflow ? SFX_FLAG_COLL_OVERFLOW : 0);
             if (Bv.coll_stat) {
-                Bv.coll_stat[2 * f] = max(Bv.coll_stat[2 * f], S.coll_max_cand);
-                Bv.coll_stat[2 * f + 1] = max(Bv.coll_stat[2 * f + 1], S.coll_max_touch);
+                Bv.coll_stat[4 * f] = max(Bv.coll_stat[4 * f], S.coll_max_cand);
+                Bv.coll_stat[4 * f + 1] = max(Bv.coll_stat[4 * f + 1], S.coll_max_touch);
+                Bv.coll_stat[4 * f + 2] = max(Bv.coll_stat[4 * f + 2], S.coll_max_iters);
+                Bv.coll_stat[4 * f + 3] = max(Bv.coll_stat[4 * f + 3], S.coll_max_hits);
             }
 #ifdef SFX_CYCLE_PROF
             S.prof[4] += clock64() - _t_total;
@@ -679,7 +685,7 @@ int sfx_batch_enable_collisions(sfx_batch* b) {
     // one slot per block; no launch uses more blocks than frames
     CUDA_TRY(b->coll_vals.alloc((size_t)b->B * coll_vals_per_block(b->m->V, b->m->F) * b->es));
     CUDA_TRY(b->coll_idx.alloc((size_t)b->B * coll_idx_per_block(b->m->V, b->m->F) * sizeof(unsigned short)));
-    CUDA_TRY(b->coll_stat.alloc((size_t)b->B * 2 * sizeof(int)));
+    CUDA_TRY(b->coll_stat.alloc((size_t)b->B * 4 * sizeof(int)));
     CUDA_TRY(cudaMemset(b->coll_stat.p, 0, b->coll_stat.bytes));
     return SFX_OK;
 }

@@ -284,12 +284,13 @@ class FrameBatch(object):
         return _wrap(ptr, (self.B,), torch.int32, self.model.device, self)
 
     def coll_stats(self):
-        """[B, 2] int32: largest candidate-face / touched-vertex count of each frame's
-        evaluations of the interpenetration term (None when the term is not enabled)."""
+        """[B, 4] int32 per frame, largest over its evaluations of the interpenetration term:
+        candidate faces, touched vertices, sweep iterations and listed partners of warp 0 (None
+        when the term is not enabled)."""
         ptr = self.lib.sfx_batch_coll_stat_dev(self.h)
         if not ptr:
             return None
-        return _wrap(ptr, (self.B, 2), torch.int32, self.model.device, self)
+        return _wrap(ptr, (self.B, 4), torch.int32, self.model.device, self)
 
     def reset_counters(self):
         with torch.cuda.device(self.model.device):
