@@ -39,8 +39,8 @@ SUPPORT_ROWS = 225 * 3
 ROW_BYTES = 512 * 4
 # dram__bytes_read.sum + dram__bytes_write.sum of one fit_pipeline_kernel<float> launch of the
 # default workload (128 frames), from the `ncu --set full` capture summarised in
-# profiles/r01k_ncu_raw_pipeline_kernel.csv (6.82 MB read + 5.13 MB written)
-NCU_TRAFFIC_BYTES_DEFAULT_WORKLOAD = 11955712.0
+# profiles/r01p_ncu_raw_pipeline_kernel.csv (7.22 MB read + 5.38 MB written)
+NCU_TRAFFIC_BYTES_DEFAULT_WORKLOAD = 12591616.0
 
 
 # ------------------------------------------------------------------------------ workload
@@ -477,7 +477,7 @@ def run_b200(args):
         roofline['traffic'] = args.traffic
     elif B == 128 and not args.interpenetration and not args.vposer:
         roofline['traffic'] = NCU_TRAFFIC_BYTES_DEFAULT_WORKLOAD
-        roofline['traffic_source'] = 'profiles/r01k_ncu_raw_pipeline_kernel.csv'
+        roofline['traffic_source'] = 'profiles/r01p_ncu_raw_pipeline_kernel.csv'
     coll_stats = batch.coll_stats()
     if coll_stats is not None:
         cs = coll_stats.cpu().numpy()

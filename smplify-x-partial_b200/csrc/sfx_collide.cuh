@@ -10,16 +10,20 @@
 // B200 design.  One block owns one frame, so the search is built for 512 threads and the
 // shared memory of one SM instead of a device-wide LBVH:
 //   * the part filter comes FIRST: only faces of parts (p, q) that FilterFaces would keep can
-//     form a pair, so the broad phase works on per-part boxes (55 boxes, one warp per part) and
-//     on the "candidate" faces whose box reaches into the box of an admissible partner part;
-//   * candidates are compacted in a fixed order (faces are pre-sorted by part on the host) into
-//     the shared-memory area that holds the blend-row ring during the streaming passes, boxes
-//     and all, so the O(candidates x partner candidates) box tests never leave the SM;
-//   * each thread GATHERS: it owns a candidate face, walks its partners in list order, runs
-//     the separating-axis test and accumulates the penalty of its own cone plus the gradient
-//     w.r.t. its own three vertices in registers -- no atomics on values, so the result is
-//     bit-reproducible run to run; the per-vertex sums walk the static vertex->face table in
-//     order for the same reason.
+//     form a pair, so the broad phase works on a static two-level hierarchy (faces grouped by
+//     part and, inside a part, cut into clusters of 64 along the part's long axis) whose boxes
+//     are refitted per evaluation; a face is a "candidate" iff its box reaches a cluster box of
+//     an admissible partner part;
+//   * candidates are compacted in a fixed order and sorted by (extent class, box minimum along
+//     the body's longest axis) in the shared-memory area that holds the blend-row ring during the
+//     streaming passes, each with a packed 8-byte entry (part + box on a 256-level grid); a warp
+//     per candidate walks the windows of the four class runs that can overlap it and lists the
+//     box-overlapping, admissible partners;
+//   * the narrow phase GATHERS: the warp owning a candidate runs the separating-axis test against
+//     its listed partners and accumulates the penalty of the candidate's own cone plus the
+//     gradient w.r.t. its own three corners -- no atomics on values, fixed summation order, so
+//     the result is bit-reproducible run to run; the per-vertex sums walk the static
+//     vertex->face table in order for the same reason.
 // The same source compiles for the single-threaded host simulation (tests only).
 #pragma once
 
@@ -36,7 +40,7 @@ struct CollWS {
     T* fbox;               // [F][6] axis-aligned box of every face
     T* ftri;               // [F][9] its three corners, contiguous (one 36-byte read per partner)
     unsigned char* sort_g; // [SFX_COLL_ENTRY * SFX_COLL_SORT_G] sweep arrays when they outgrow the shared area
-    unsigned short* hits_g;     // [threads][hits_cap] per-thread lists: (count, partner faces...) per candidate
+    unsigned short* hits_g;     // [warps][32 * hits_cap] per-warp lists: (count, partner faces...) per candidate
     int hits_cap;
     unsigned char* work;   // shared-memory work area (the idle blend ring on the device)
     int work_bytes;
@@ -44,7 +48,7 @@ struct CollWS {
 #define SFX_COLL_SORT_G 32768      // capacity of the global sweep arrays (power of two >= F)
 #define SFX_COLL_CLASSES 4         // extent classes of the sweep (quantised extent <= 4, 16, 64, any)
 #define SFX_COLL_ENTRY 12          // bytes per candidate: packed part + quantised box 8, key 2, face 2
-#define SFX_COLL_HITS 2048         // per-thread region of the potential-hit list (16-bit entries)
+#define SFX_COLL_HITS 2048         // potential-hit list: 16-bit entries per lane (a warp's region is 32 x this)
 
 template <typename T>
 SFX_FN CollWS<T> coll_block_ws(int V, int F, T* vals, unsigned short* idx, unsigned char* work,

@@ -56,7 +56,7 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
     stage_setup(M, *st, jw, lowconf, conf, init_mask, M.K, S, joints_out != nullptr && !do_fit && g_all_rows);
     std::vector<T> hs((size_t)SFX_HIST * SFX_NP_MAX), hy((size_t)SFX_HIST * SFX_NP_MAX);
     CollWS<T> W;
-    std::vector<T> vp_g, vert_g, dvert_g, dtri_g, big_box, ftri;
+    std::vector<T> vp_g, vert_g, dvert_g, dtri_g, fbox_buf, ftri;
     std::vector<unsigned short> tv_g, hits_g;
     std::vector<unsigned char> work, sort_g;
     const CollWS<T>* Wp = nullptr;
@@ -70,9 +70,9 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
         vp_g.assign((size_t)3 * M.V, 0); vert_g.assign((size_t)3 * M.V, 0);
         dvert_g.assign((size_t)3 * M.V, 0); dtri_g.assign((size_t)9 * M.F, 0);
         work.assign(sm.coll_work_bytes, 0);
-        big_box.assign((size_t)6 * M.F, 0); sort_g.assign((size_t)SFX_COLL_ENTRY * SFX_COLL_SORT_G, 0); tv_g.assign(M.V, 0);
+        fbox_buf.assign((size_t)6 * M.F, 0); sort_g.assign((size_t)SFX_COLL_ENTRY * SFX_COLL_SORT_G, 0); tv_g.assign(M.V, 0);
         ftri.assign((size_t)9 * M.F, 0);
-        W.fbox = big_box.data(); W.ftri = ftri.data(); W.sort_g = sort_g.data(); W.tv_g = tv_g.data();
+        W.fbox = fbox_buf.data(); W.ftri = ftri.data(); W.sort_g = sort_g.data(); W.tv_g = tv_g.data();
         W.hits_cap = g_hits_cap > 0 ? g_hits_cap : SFX_COLL_HITS;
         hits_g.assign((size_t)W.hits_cap, 0);         // one thread on the host: many chunks
         W.hits_g = hits_g.data();
