@@ -417,6 +417,82 @@ def ref_eval_coll(inputs, dtype=torch.float64, tag='f64'):
     return out
 
 
+def ref_blending():
+    """The reference's keypoints_blending.blending() (keypoints_blending.py:276-381), unmodified,
+    on seeded detections and seeded statistics.  Its non-arithmetic imports (mmcv, mmpose, PIL,
+    matplotlib) are stubbed and its hard-coded '/content/heuristics/' paths are redirected to a
+    temporary folder by giving the module its own ``open``."""
+    import builtins
+    import importlib
+    import types
+    ref_bridge.load()
+    for name in ('mmcv', 'mmcv.visualization', 'mmcv.visualization.image', 'mmcv.image', 'mmpose',
+                 'mmpose.core', 'PIL', 'matplotlib', 'matplotlib.pyplot'):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__getattr__ = lambda attr: (lambda *a, **k: None)
+            sys.modules[name] = m
+    sys.path.insert(0, os.path.join(REF, 'smplifyx'))
+    KB = importlib.import_module('keypoints_blending')
+    from smplifyx_b200 import keypoints_blending as PB
+    rng = np.random.default_rng(33)
+    tmp = tempfile.mkdtemp()
+    heur = os.path.join(tmp, 'heuristics')
+    for d in ('images', 'op', 'mm', 'out', 'heuristics'):
+        os.makedirs(os.path.join(tmp, d))
+    keys = [p[0] for p in PB.blended_pairs()]
+    stats = {'openpose_means': {k: float(rng.uniform(0.4, 0.8)) for k in keys},
+             'openpose_stds': {k: float(rng.uniform(0.1, 0.3)) for k in keys},
+             'mmpose_means': {k: float(rng.uniform(0.5, 0.9)) for k in keys},
+             'mmpose_stds': {k: float(rng.uniform(0.05, 0.2)) for k in keys}}
+    for k, v in stats.items():
+        with open(os.path.join(heur, k + '.json'), 'w') as f:
+            json.dump(v, f)
+
+    def redirected_open(fn, *a, **kw):
+        if isinstance(fn, str) and fn.startswith('/content/heuristics/'):
+            fn = os.path.join(heur, os.path.basename(fn))
+        return builtins.open(fn, *a, **kw)
+    KB.open = redirected_open
+    out = {'stats_json': np.array(json.dumps(stats))}
+    ops, mms, res = [], [], []
+    for n in range(6):
+        # the reference writes only the last image's file: one image per call
+        for d in ('images', 'op', 'mm'):
+            for fn in os.listdir(os.path.join(tmp, d)):
+                os.remove(os.path.join(tmp, d, fn))
+        name = 'img%02d' % n
+        open(os.path.join(tmp, 'images', name + '.jpg'), 'w').close()
+        op = np.concatenate([rng.uniform(0, 800, size=(137, 2)),
+                             rng.uniform(-0.1, 1.2, size=(137, 1))], axis=1).astype(np.float32)
+        mm = np.concatenate([rng.uniform(0, 800, size=(138, 2)),
+                             rng.uniform(0.0, 1.1, size=(138, 1))], axis=1).astype(np.float32)
+        op[rng.uniform(size=137) < 0.1] = 0            # undetected keypoints
+        for arr, body, fn in ((op, 25, os.path.join(tmp, 'op', name + '_keypoints.json')),
+                              (mm, 26, os.path.join(tmp, 'mm', name + '_mmpose.json'))):
+            person = {'pose_keypoints_2d': arr[:body].reshape(-1).tolist(),
+                      'hand_left_keypoints_2d': arr[body:body + 21].reshape(-1).tolist(),
+                      'hand_right_keypoints_2d': arr[body + 21:body + 42].reshape(-1).tolist(),
+                      'face_keypoints_2d': arr[body + 42:].reshape(-1).tolist()}     # 70 points
+            with open(fn, 'w') as f:
+                json.dump({'people': [person]}, f)
+        KB.blending(os.path.join(tmp, 'images'), os.path.join(tmp, 'op'), os.path.join(tmp, 'mm'),
+                    os.path.join(tmp, 'out'))
+        with open(os.path.join(tmp, 'out', name + '_blended.json')) as f:
+            person = json.load(f)['people'][0]
+        res.append(np.concatenate([np.array(person[k]).reshape(-1, 3) for k in
+                                   ('pose_keypoints_2d', 'hand_left_keypoints_2d',
+                                    'hand_right_keypoints_2d', 'face_keypoints_2d')]))
+        ops.append(op[:135])
+        mms.append(mm[:136])
+    out['openpose'] = np.stack(ops)
+    out['mmpose'] = np.stack(mms)
+    out['blended'] = np.stack(res)
+    np.savez_compressed(os.path.join(HERE, 'ref_blending.npz'), **out)
+    print('ref_blending: rows taken from MMPose', int((out['blended'][:, :67, :2] != out['openpose'][:, :67, :2]).any(-1).sum()), 'of', 6 * 67)
+    return out
+
+
 def ref_metrics():
     """The reference's alignment classes (utils.py:540-801) and eval.py's compute_v2v loop on
     seeded point sets: a rotated / scaled / noisy copy of a mesh-sized cloud, a reflected one
@@ -572,6 +648,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'envelope':
         ref_envelope(inp)
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'blending':
+        ref_blending()
+        raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'metrics':
         ref_metrics()
         raise SystemExit(0)
@@ -585,5 +664,6 @@ if __name__ == '__main__':
     ref_eval_coll(inp, torch.float64, 'f64')
     ref_eval_coll(inp, torch.float32, 'f32')
     ref_metrics()
+    ref_blending()
     ref_fit('02_cropped', inp)
     ref_fit('18_cropped', inp, cfg=cfg_smplifyx(), tag='ref_fit_18_vposer')
