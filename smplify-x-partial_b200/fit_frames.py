@@ -150,13 +150,19 @@ def keypoint_masks(keypoints, cfg, base_jw):
     return jw, lowconf.astype(np.uint8), init.astype(np.uint8)
 
 
-def regression_pose(cfg, expose=None, pixie=None, dtype=np.float32):
+def regression_pose(cfg, expose=None, pixie=None, dtype=np.float32, pare=None):
     """Regression prior -> (pose [63], global_orient [3]) as xyz-Euler angles used *as if*
     they were axis-angle, exactly like the reference (fit_single_frame.py:209-235)."""
     kind = cfg.get('regression_prior')
     if not kind:
         return None, None
     pix = exp = gp = None
+    if kind == 'PARE':
+        # pred_pose [1, 24, 3, 3]: joint 0 is the global orientation, 1..21 the body
+        pp = np.asarray(pare['pred_pose'], dtype=dtype)
+        full = U.euler_xyz_from_matrix(pp[0, 1:22])
+        gp = U.euler_xyz_from_matrix(pp[0, :1])[0]
+        return full.reshape(-1).astype(dtype), gp.reshape(-1).astype(dtype)
     if kind in ('PIXIE', 'combined'):
         pix = U.euler_xyz_from_matrix(np.asarray(pixie['body_pose'], dtype=dtype))
         gp = U.euler_xyz_from_matrix(np.asarray(pixie['global_pose'], dtype=dtype))[0]
@@ -174,12 +180,17 @@ def regression_pose(cfg, expose=None, pixie=None, dtype=np.float32):
     return full.reshape(-1).astype(dtype), gp.reshape(-1).astype(dtype)
 
 
-def regression_pose_batch(cfg, expose, pixie, B, dtype=np.float32):
+def regression_pose_batch(cfg, expose, pixie, B, dtype=np.float32, pare=None):
     """``regression_pose`` for B frames at once (the Euler conversion is elementwise, so the
     result is bit-identical to B separate calls): -> (pose [B,63], global_orient [B,3])."""
     kind = cfg.get('regression_prior')
     pix = exp = gp = None
     stack = lambda rows, key: np.stack([np.asarray(r[key], dtype=dtype) for r in rows])
+    if kind == 'PARE':
+        pp = stack(pare, 'pred_pose')[:, 0]                                      # [B,24,3,3]
+        full = U.euler_xyz_from_matrix(pp[:, 1:22])
+        gp = U.euler_xyz_from_matrix(pp[:, :1])[:, 0]
+        return full.reshape(B, -1).astype(dtype), gp.reshape(B, -1).astype(dtype)
     if kind in ('PIXIE', 'combined'):
         pix = U.euler_xyz_from_matrix(stack(pixie, 'body_pose'))                 # [B,21,3]
         gp = U.euler_xyz_from_matrix(stack(pixie, 'global_pose'))[:, 0]
@@ -197,12 +208,20 @@ def regression_pose_batch(cfg, expose, pixie, B, dtype=np.float32):
     return full.reshape(B, -1).astype(dtype), gp.reshape(B, -1).astype(dtype)
 
 
-def camera_prior(cfg, focal, expose=None, pixie=None):
+def camera_prior(cfg, focal, expose=None, pixie=None, pare=None):
     """-> (translation [3], centre [2]) or None when guess_init applies
     (fit_single_frame.py:359-411)."""
     kind = cfg.get('regression_prior')
     if not cfg.get('use_camera_prior') or not kind:
         return None
+    if kind == 'PARE':
+        # bounding box (cx, cy, b, _) of the 224-pixel crop and its weak-perspective camera
+        RES = 224
+        cx, cy, b, _ = [float(v) for v in np.asarray(pare['bboxes'])[0]]
+        cam = np.asarray(pare['pred_cam'])[0]
+        r = b / RES
+        return (np.array([cam[1], cam[2], (2 * focal) / (r * RES * cam[0])], dtype=np.float64),
+                np.array([cx, cy], dtype=np.float64))
     if kind in ('ExPose', 'combined'):
         t = np.array(expose['transl'], dtype=np.float64).copy()
         t[-1] /= (5000 / focal)
@@ -254,7 +273,8 @@ class FitPlan(object):
     the second (flipped) orientation.  Pure numpy; built without touching the device."""
 
     def __init__(self, L, K, keypoints, H, W, cfg, expose=None, pixie=None, body_mean_pose=None,
-                 np_dtype=np.float32, body_pose_prior=None, vposer=None, part_segm=None):
+                 np_dtype=np.float32, body_pose_prior=None, vposer=None, part_segm=None,
+                 pare=None):
         B = keypoints.shape[0]
         self.B, self.K, self.L, self.cfg = B, K, L, cfg
         npd = self.np_dtype = np_dtype
@@ -296,7 +316,7 @@ class FitPlan(object):
             raise ValueError('the batch was created with use_vposer=True but the config says False')
         if cfg.get('regression_prior'):
             self.reg = np.zeros((B, L.n_pose), dtype=np.float64)
-            poses, gos = regression_pose_batch(cfg, expose, pixie, B, dtype=npd)
+            poses, gos = regression_pose_batch(cfg, expose, pixie, B, dtype=npd, pare=pare)
             x[:, L.off_go:L.off_go + 3] = gos
             if use_vposer:
                 # pose_embedding = vposer.encode(prior).sample()  (fit_single_frame.py:245):
@@ -325,7 +345,8 @@ class FitPlan(object):
         self.need_guess = []
         for b in range(B):
             pr = camera_prior(cfg, focal[b], None if expose is None else expose[b],
-                              None if pixie is None else pixie[b])
+                              None if pixie is None else pixie[b],
+                              None if pare is None else pare[b])
             if pr is None:
                 self.need_guess.append(b)
                 cam[b, 2:4] = (W[b] * 0.5, H[b] * 0.5)
@@ -465,7 +486,7 @@ def download(batch, plan, cam_loss, verts, joints):
 
 
 def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_verts=True,
-               body_mean_pose=None, body_pose_prior=None, vposer=None, part_segm=None):
+               body_mean_pose=None, body_pose_prior=None, vposer=None, part_segm=None, pare=None):
     """Fits every frame of ``batch`` (an ``engine.FrameBatch``).
 
     keypoints [B,K,3] (x, y, confidence) in the reference's row order; ``H``, ``W`` scalars or
@@ -473,7 +494,7 @@ def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_vert
     reference's YAML files); ``expose`` / ``pixie`` lists of per-frame regression results.
     """
     plan = FitPlan(batch.L, batch.model.K, np.asarray(keypoints), H, W, cfg, expose, pixie,
-                   body_mean_pose, batch.model.np_dtype, body_pose_prior, vposer, part_segm)
+                   body_mean_pose, batch.model.np_dtype, body_pose_prior, vposer, part_segm, pare)
     h2d = upload(batch, plan)
     cam_loss, verts, joints, launches = run(batch, plan, return_verts)
     out = download(batch, plan, cam_loss, verts, joints)

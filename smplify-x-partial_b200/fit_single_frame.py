@@ -63,8 +63,6 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
         vposer.eval()
     if visualize:
         raise NotImplementedError('visualisation is out of scope (SURVEY.md #16)')
-    if pare_results is not None and regression_prior == 'PARE':
-        raise NotImplementedError('PARE regression prior')
     cfg = dict(kwargs)
     cfg.update(data_weights=data_weights, body_pose_prior_weights=body_pose_prior_weights,
                hand_pose_prior_weights=hand_pose_prior_weights,
@@ -88,12 +86,13 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
     K = kp.shape[1]
     expose = expose_results if isinstance(expose_results, (list, tuple)) else [expose_results] * B
     pixie = pixie_results if isinstance(pixie_results, (list, tuple)) else [pixie_results] * B
+    pare = pare_results if isinstance(pare_results, (list, tuple)) else [pare_results] * B
 
     # --- regression prior -> initial pose (:209-274) ---
     pose0 = torch.zeros([B, 63], dtype=dtype, device=dev)
     go0 = None
     if regression_prior:
-        po, go = zip(*[FF.regression_pose(cfg, expose[b], pixie[b]) for b in range(B)])
+        po, go = zip(*[FF.regression_pose(cfg, expose[b], pixie[b], pare=pare[b]) for b in range(B)])
         pose0 = torch.tensor(np.stack(po), dtype=dtype, device=dev)
         go0 = torch.tensor(np.stack(go), dtype=dtype, device=dev)
     elif not use_vposer:
@@ -124,13 +123,13 @@ def fit_single_frame(img, keypoints, body_model, camera, joint_weights, body_pos
     # --- camera initialisation (:359-411) ---
     with torch.no_grad():
         for b in range(B):
-            pr = FF.camera_prior(cfg, focal_length, expose[b], pixie[b])
+            pr = FF.camera_prior(cfg, focal_length, expose[b], pixie[b], pare[b])
             if pr is not None:
                 camera.translation[b] = torch.tensor(pr[0], dtype=dtype, device=dev)
                 camera.center[b] = torch.tensor(pr[1], dtype=dtype, device=dev)
             else:
                 camera.center[b] = torch.tensor([W, H], dtype=dtype, device=dev) * 0.5
-        if FF.camera_prior(cfg, focal_length, expose[0], pixie[0]) is None:
+        if FF.camera_prior(cfg, focal_length, expose[0], pixie[0], pare[0]) is None:
             init_t = fitting.guess_init(body_model, gt_joints, kwargs.get('body_tri_idxs'),
                                         use_vposer=use_vposer, vposer=vposer,
                                         pose_embedding=pose_embedding,

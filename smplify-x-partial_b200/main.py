@@ -29,7 +29,7 @@ from .fit_single_frame import write_ply_vertices
 
 def _load_regression(args, img_name):
     import joblib
-    pixie = expose = None
+    pixie = expose = pare = None
     if args.get('regression_prior'):
         d = args.get('pixie_results_directory')
         if d:
@@ -38,9 +38,10 @@ def _load_regression(args, img_name):
         if d:
             expose = dict(np.load(os.path.join(d, img_name + '.jpg', img_name + '.jpg_params.npz'),
                                   allow_pickle=True))
-        if args.get('pare_results_directory'):
-            raise NotImplementedError('PARE regression prior')
-    return pixie, expose
+        d = args.get('pare_results_directory')
+        if d:
+            pare = joblib.load(os.path.join(d, img_name + '.pkl'))          # main.py:292-293
+    return pixie, expose, pare
 
 
 def main(**args):
@@ -94,7 +95,7 @@ def main(**args):
         reg = [_load_regression(args, d['fn']) for d in chunk]
         batch = engine.FrameBatch(model, B, use_vposer=bool(args.get('use_vposer')))
         out = FF.fit_frames(batch, kp, H, W, args, expose=[r[1] for r in reg],
-                            pixie=[r[0] for r in reg],
+                            pixie=[r[0] for r in reg], pare=[r[2] for r in reg],
                             return_verts=bool(args.get('save_vertices')),
                             body_pose_prior=body_pose_prior, vposer=vposer)
         for b, d in enumerate(chunk):

@@ -110,6 +110,50 @@ def test_regression_pose_and_camera_prior():
     assert FF.camera_prior(dict(regression_prior=None, use_camera_prior=True), 1000.0) is None
 
 
+def test_pare_regression_and_camera_prior():
+    """regression_prior 'PARE' (fit_single_frame.py:220-231, :360-369): body pose from
+    pred_pose[:, 1:22], orientation from pred_pose[:, :1], camera from the 224-pixel crop."""
+    from oracle import fit_port as FP
+    rng = np.random.default_rng(5)
+
+    def rotmats(n):
+        q, r = np.linalg.qr(rng.normal(size=(n, 3, 3)))
+        q = q * np.sign(np.diagonal(r, axis1=1, axis2=2))[:, None, :]
+        q[np.linalg.det(q) < 0, :, 0] *= -1
+        return q.astype(np.float32)
+    pares = [dict(pred_pose=rotmats(24)[None], bboxes=np.array([[410.0, 305.0, 380.0, 380.0]]),
+                  pred_cam=np.array([[0.9, 0.02, -0.05]], dtype=np.float32)) for _ in range(3)]
+    cfg = dict(regression_prior='PARE', use_camera_prior=True)
+    for p in pares:
+        pose, go = FF.regression_pose(cfg, None, None, pare=p)
+        want = torch.cat([FP.euler_xyz_from_matrix(torch.tensor(m)) for m in p['pred_pose'][0, 1:22]])
+        assert pose.shape == (63,) and np.allclose(pose, want.reshape(-1).numpy(), atol=2e-6)
+        assert np.allclose(go, FP.euler_xyz_from_matrix(torch.tensor(p['pred_pose'][0, :1])).numpy()[0],
+                           atol=2e-6)
+        t, c = FF.camera_prior(cfg, 1000.0, pare=p)
+        assert np.allclose(c, [410.0, 305.0])
+        assert np.allclose(t, [0.02, -0.05, 2 * 1000.0 / (380.0 * 0.9)], rtol=1e-6)
+    pb, gb = FF.regression_pose_batch(cfg, None, None, 3, pare=pares)
+    for b, p in enumerate(pares):
+        pose, go = FF.regression_pose(cfg, None, None, pare=p)
+        assert np.array_equal(pb[b], pose) and np.array_equal(gb[b], go)
+    # and through the plan: initial pose, orientation, camera row
+    L = Cm.layout()
+    kp = np.zeros((3, 135, 3))
+    kp[:, :, :2] = rng.uniform(100, 500, size=(3, 135, 2))
+    kp[:, :, 2] = 0.9
+    plan_cfg = dict(cfg, format='coco25', use_hands=True, use_face=True, joints_to_ign=[1, 9, 12],
+                    body_pose_prior_weights=[1.0], shape_weights=[1.0], expr_weights=[1.0],
+                    hand_pose_prior_weights=[1.0], hand_joints_weights=[1.0],
+                    face_joints_weights=[1.0], coll_loss_weights=[0.0],
+                    jaw_pose_prior_weights=['1,1,1'])
+    plan = FF.FitPlan(L, 135, kp, 600, 800, plan_cfg, None, None, None, np.float32, pare=pares)
+    assert np.allclose(plan.x0[:, L.off_pose:L.off_pose + 63], pb)
+    assert np.allclose(plan.x0[:, L.off_go:L.off_go + 3], gb)
+    assert np.allclose(plan.cam[:, 2:4], [410.0, 305.0]) and not plan.need_guess
+    assert np.allclose(plan.x0[:, L.off_camt + 2], 2 * 1000.0 / (380.0 * 0.9), rtol=1e-6)
+
+
 def test_flipped_orientation_matches_cv2():
     cv2 = pytest.importorskip('cv2')
     rng = np.random.default_rng(5)
