@@ -1,3 +1,14 @@
+"""Cycle-counter profile of the per-frame pipeline kernel (clock64 around the phases of an
+evaluation, per frame; thread 0's view).  Needs the profiling build of the library next to the
+product one:
+
+    cd smplify-x-partial_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 \
+        -std=c++17 --extended-lambda -Xcompiler -fPIC -shared -DSFX_CYCLE_PROF \
+        -o libsfx_prof.so sfx_lib.cu
+
+    python profiles/prof_cycles.py [--interpenetration]        # on a B200 (gpurun)
+
+Numbers taken with this build are diagnostics, never bench values."""
 import sys, os, ctypes as C
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
