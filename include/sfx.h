@@ -94,7 +94,7 @@ int sfx_model_set_collision(sfx_model* m, const int32_t* faces_segm, const int32
 int sfx_batch_create(const sfx_model* m, int32_t num_frames, int32_t use_vposer, sfx_batch** out);
 void sfx_batch_destroy(sfx_batch* b);
 int sfx_batch_layout(const sfx_batch* b, SfxLayout* out);
-/* Allocates the full-mesh workspace of the interpenetration term (about 1.7 MB per frame in
+/* Allocates the full-mesh workspace of the interpenetration term (about 4.9 MB per frame in
  * float32).  Needed before a stage with coll_loss_weight > 0 (SfxStage) is evaluated or fitted;
  * df_cone_height travels as SfxStage.coll_sigma. */
 int sfx_batch_enable_collisions(sfx_batch* b);
