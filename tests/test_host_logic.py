@@ -154,6 +154,34 @@ def test_pare_regression_and_camera_prior():
     assert np.allclose(plan.x0[:, L.off_camt + 2], 2 * 1000.0 / (380.0 * 0.9), rtol=1e-6)
 
 
+def test_plan_carries_the_interpenetration_settings():
+    """The shipped profile's interpenetration keys reach the stages (coll weights per stage,
+    df_cone_height) and the face filter; without a segmentation the plan refuses."""
+    from smplifyx_b200.cmd_parser import parse_config
+    cfg = parse_config(['-c', os.path.join(Cm.ROOT, 'cfg_files', 'fit_smplx_combined_coco25.yaml')])
+    cfg.pop('config')
+    cfg.update(regression_prior=None, use_camera_prior=False)
+    L = Cm.layout()
+    kp = np.zeros((2, 135, 3))
+    kp[:, :, :2] = 300.0
+    kp[:, :, 2] = 0.9
+    with pytest.raises(NotImplementedError, match='part_segm_fn'):
+        FF.FitPlan(L, 135, kp, 600, 800, cfg, None, None, None, np.float32)
+    segm, par, ign = Cm.coll_segmentation()
+    plan = FF.FitPlan(L, 135, kp, 600, 800, cfg, None, None, None, np.float32,
+                      part_segm={'segm': segm, 'parents': par})
+    assert [st.coll_loss_weight for st in plan.stages] == [0.0, 0.1, 1.0]
+    assert all(st.coll_sigma == 1e-4 for st in plan.stages) and plan.cam_stage.coll_loss_weight == 0
+    assert plan.collision.ign_part_pairs == cfg['ign_part_pairs']
+    assert plan.collision.faces_segm.dtype == np.int32 and len(plan.collision.faces_segm) == 20908
+    off = dict(cfg, interpenetration=False)
+    plan = FF.FitPlan(L, 135, kp, 600, 800, off, None, None, None, np.float32)
+    assert plan.collision is None and all(st.coll_loss_weight == 0 for st in plan.stages)
+    with pytest.raises(NotImplementedError):
+        FF.FitPlan(L, 135, kp, 600, 800, dict(cfg, point2plane=True), None, None, None, np.float32,
+                   part_segm={'segm': segm, 'parents': par})
+
+
 def test_flipped_orientation_matches_cv2():
     cv2 = pytest.importorskip('cv2')
     rng = np.random.default_rng(5)
