@@ -45,6 +45,10 @@ NCU_TRAFFIC_BYTES_DEFAULT_WORKLOAD = 12591616.0
 
 # ------------------------------------------------------------------------------ workload
 COLL_POSE_CORRECTIVE_SCALE = 0.1      # config 4: see synthetic.cached_smplx_like
+# How the engine computes the L-BFGS direction (_native.TWO_LOOP_MODES): 'gram' runs the
+# reference's two-loop recursion on the inner products of the history (same mathematics,
+# different rounding, ~2.4x shorter); 'exact' reproduces the reference's operation order.
+TWO_LOOP = os.environ.get('SFX_TWO_LOOP', 'gram')
 
 
 def bench_cfg(interpenetration=False, vposer=False):
@@ -91,7 +95,7 @@ def _bench_cfg():
         body_tri_idxs=[(5, 12), (2, 9)], use_vposer=False, num_betas=10,
         num_expression_coeffs=10, regression_prior='combined', use_camera_prior=True,
         use_conf_for_camera_init=True, confidence_threshold=0.2, depth_loss_weight=1e2,
-        side_view_thsh=25.0, focal_length=None)
+        side_view_thsh=25.0, focal_length=None, two_loop=TWO_LOOP)
 
 
 MODEL_KW = dict(num_betas=10, num_expression_coeffs=10, use_pca=True, num_pca_comps=12,
@@ -311,7 +315,9 @@ def workload_config(B, n_gpus, interpenetration=False, vposer=False):
                             '5000, interpenetration off (BASELINE config 3)'.format(B),
                 'frames_per_gpu': B, 'global_frames': B * n_gpus,
                 'parallelism': 'frames sharded, dp{}'.format(n_gpus),
-                'l2': 'flushed between timed steps (256 MiB write)'}
+                'l2': 'flushed between timed steps (256 MiB write)',
+                'two_loop': TWO_LOOP + ' (engine option for the L-BFGS direction; the reference '
+                            'arm always runs the reference recursion)'}
     return {'workload': 'batch={} synthetic frames per GPU, 135 keypoints (127 model joints + 17 '
                         'face-contour), neutral SMPL-X-shaped synthetic model, GMoF + L2 priors, '
                         '3-stage fit_smplx_combined_coco25 schedule, lbfgsls, combined regression '
@@ -320,7 +326,9 @@ def workload_config(B, n_gpus, interpenetration=False, vposer=False):
                             'filter; BASELINE config 4)' if interpenetration else 'off'),
             'frames_per_gpu': B, 'global_frames': B * n_gpus,
             'parallelism': 'frames sharded, dp{}'.format(n_gpus),
-            'l2': 'flushed between timed steps (256 MiB write)'}
+            'l2': 'flushed between timed steps (256 MiB write)',
+            'two_loop': TWO_LOOP + ' (engine option for the L-BFGS direction; the reference arm '
+                        'always runs the reference recursion)'}
 
 
 # ------------------------------------------------------------------------------ B200 arm
@@ -534,9 +542,15 @@ def main():
     ap.add_argument('--vposer', action='store_true',
                     help='BASELINE config 3: 5-stage schedule with the VPoser latent pose prior '
                          '(not the default bench line)')
+    ap.add_argument('--two-loop', default=None, choices=['exact', 'gram'],
+                    help="L-BFGS direction: 'gram' (default; coefficient-space recursion) or "
+                         "'exact' (the reference's operation order)")
     ap.add_argument('--traffic', type=float, default=None,
                     help='dram bytes per launch from an ncu capture (profiles/), recorded as-is')
     args = ap.parse_args()
+    if args.two_loop:
+        global TWO_LOOP
+        TWO_LOOP = args.two_loop
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -45,7 +45,7 @@ tot = prof[:,4].astype(float)
 i = np.argmax(tot)
 print('slowest frame', i, 'evals', ev[i], 'cycles total %.3g (%.1f ms @1.965GHz)' % (tot[i], tot[i]/1.965e6))
 for name, k in (('eval',0),('two_loop',1),('blend_fwd',2),('blend_adj',3),('chain_fwd_w0',5),('stream_fwd_w1',6),('chain_adj_w0',7),
-                ('coll_skin|prologue',8),('coll_boxes|skin+proj+adj',9),('coll_narrow|eval_tail',10),('coll_vgather',11),('coll_skin_adj',12),('coll_walk_t0',13),('coll_pairs_t0',14)):
+                ('coll_skin|prologue',8),('coll_boxes|skin+proj+adj',9),('coll_narrow|eval_tail',10),('coll_vgather|gram_dots',11),('coll_skin_adj|gram_chain',12),('coll_walk_t0|gram_combine',13),('coll_pairs_t0',14)):
     print('%-10s slowest: %5.1f%%   all frames: %5.1f%%   per eval (slowest) %.1f us' % (name, 100*prof[i,k]/tot[i], 100*prof[:,k].sum()/tot.sum(), prof[i,k]/ev[i]/1965.))
 print('mean frame total ms', tot.mean()/1.965e6, 'median evals', np.median(ev))
 

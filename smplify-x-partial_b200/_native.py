@@ -183,6 +183,23 @@ BODY_STAGE_BLOCKS = ['betas', 'global_orient', 'left_hand_pose', 'right_hand_pos
 CAMERA_STAGE_BLOCKS = ['camera_translation', 'global_orient']
 
 
+# L-BFGS direction (lbfgs_ls.py:336-358): 'exact' = the reference's recursion and operation order,
+# one warp (default); 'block' = the same by the whole block (debug A/B); 'gram' = the same
+# recursion run on the inner products of the history (csrc/sfx_core.cuh gram_two_loop): equal
+# in exact arithmetic, different rounding, several times shorter dependent chain.
+TWO_LOOP_MODES = {'exact': 0, 'block': 1, 'gram': 2}
+
+
+def two_loop_mode(name=None):
+    if name is None:
+        name = os.environ.get('SFX_TWO_LOOP', 'exact')
+    if isinstance(name, int):
+        return name
+    if name not in TWO_LOOP_MODES:
+        raise ValueError('two_loop must be one of {}'.format(sorted(TWO_LOOP_MODES)))
+    return TWO_LOOP_MODES[name]
+
+
 def make_stage(L, blocks, loss_kind=LOSS_SMPLIFY, opt_kind=OPT_LBFGSLS, pprior_kind=PPRIOR_L2,
                stage_index=0, num_stages=1, use_joints_conf=True, use_conf_camera=False,
                use_vposer=False, n_body_kpts=25, rho=100.0, body_pose_weight=0.0,
@@ -191,11 +208,13 @@ def make_stage(L, blocks, loss_kind=LOSS_SMPLIFY, opt_kind=OPT_LBFGSLS, pprior_k
                face_joint_weight=0.0, depth_loss_weight=0.0, maxiters=30, ftol=1e-9, gtol=1e-9,
                lr=1.0, max_iter=None, max_eval=None, history=100, tol_grad=1e-5,
                tol_change=1e-9, adam_beta1=0.9, adam_beta2=0.999, adam_eps=1e-8,
-               coll_loss_weight=0.0, coll_sigma=0.5):
+               coll_loss_weight=0.0, coll_sigma=0.5, two_loop=None):
     """Builds an SfxStage.  ``max_iter`` defaults to ``maxiters`` and ``max_eval`` to
     ``max_iter * 5 // 4`` exactly like create_optimizer('lbfgsls') (optim_factory.py:51-53,
-    lbfgs_ls.py:202-203)."""
+    lbfgs_ls.py:202-203).  ``two_loop`` selects how the L-BFGS direction is computed (see
+    ``TWO_LOOP_MODES``; default: the environment variable ``SFX_TWO_LOOP``, else 'exact')."""
     st = SfxStage()
+    st.generic_two_loop = two_loop_mode(two_loop)
     st.loss_kind, st.opt_kind, st.pprior_kind = loss_kind, opt_kind, pprior_kind
     st.stage_index, st.num_stages = stage_index, num_stages
     st.use_joints_conf = int(bool(use_joints_conf))

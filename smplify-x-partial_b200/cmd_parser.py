@@ -67,6 +67,8 @@ _FLAGS = [
     ('use_camera_prior', _b, False, None), ('use_conf_for_camera_init', _b, False, None),
     ('use_gender_classifier', _b, False, None), ('save_vertices', _b, False, None),
     ('confidence_threshold', float, 0, None),
+    # engine option (not in the reference): how the L-BFGS direction is computed, _native.TWO_LOOP_MODES
+    ('two_loop', str, None, None),
 ]
 
 

@@ -131,6 +131,7 @@ struct BatchView {
     const T* reg_pose;   // [B][n_pose] or nullptr
     T* hist_s;           // [B][HIST][SFX_NP_MAX]
     T* hist_y;           // [B][HIST][SFX_NP_MAX]
+    T* gram;             // [B][2][HIST][HIST]  inner products of the history (Gram two-loop)
     T* final_loss;       // [B]
     int* n_evals;        // [B]  (accumulated)
     int* n_passes;       // [B]  rows of the blend matrix streamed (forward + adjoint passes)
@@ -172,6 +173,7 @@ struct Scratch {
     T g_prev[SFX_NP_MAX], bg0[SFX_NP_MAX], bg1[SFX_NP_MAX], q[SFX_NP_MAX], gl[SFX_NP_MAX];
     T m1[SFX_NP_MAX], m2[SFX_NP_MAX];   // Adam moments
     T al[SFX_HIST], ro[SFX_HIST];
+    T sg[SFX_HIST], yg[SFX_HIST], cf[SFX_HIST];   // Gram two-loop: s_i.g, y_i.g, second-loop coefficients
     int act[SFX_NP_MAX];      // compact index -> full parameter index
     T red[12];
     T confsq;                 // camera stage: sum of squared confidences of the init joints
@@ -356,6 +358,14 @@ struct Scratch;
 template <typename T>
 __device__ __forceinline__ bool two_loop_staged(Scratch<T>& S, int k, int head, int H, T hd,
                                                 const T* hist_s, const T* hist_y, int D, void* wsp);
+// shared work area that is idle between evaluations (the blend ring), and its release
+template <typename T>
+__device__ __forceinline__ unsigned char* idle_area(void* wsp, size_t* bytes);
+__device__ __forceinline__ void idle_area_release(void* wsp);
+// float32 Gram chain over a [SFX_GRAM_ROWS][SFX_GRAM_LDF] zero-padded block in shared memory
+#define SFX_GRAM_ROWS 128
+#define SFX_GRAM_LDF 129
+__device__ __forceinline__ void gram_chain_f32(Scratch<float>& S, int k, float hd, const float* G, int lane);
 #else
 template <typename T>
 static void rows_dot(const T* W, const T* bias, int nrows, const T* x, T* y, void*) {
@@ -1466,6 +1476,7 @@ struct EvalCtx {
     const T* reg_pose;
     void* stream_ws;
     const CollWS<T>* coll;      // workspace of the interpenetration term, or nullptr
+    T* gram;                    // [2][SFX_HIST][SFX_HIST] s_i.y_j and y_i.y_j by history slot (Gram two-loop), or nullptr
 };
 
 // closure(): evaluate at S.xa, leave loss in S.loss and the compact gradient in S.gl
@@ -1763,6 +1774,369 @@ __device__ __forceinline__ void two_loop_warp(Scratch<T>& S, int k, int head, in
 }
 #endif
 
+// ---- two-loop recursion in coefficient space ("Gram" two-loop, SfxStage::generic_two_loop == 2) ----
+// The recursion of lbfgs_ls.py:336-358 only ever combines the vectors g, s_i, y_i, so it can be
+// run on their inner products: with SY[i][j] = s_i.y_j, YY[i][j] = y_i.y_j (kept per frame and
+// extended by one row / column whenever a pair enters the history), sg[i] = s_i.g and
+// yg[i] = y_i.g, the 2k dependent steps become scalar recurrences
+//     first loop   j = k-1..0 :  al_j = ro_j b_j ;  b_i -= al_j SY[i][j] (i < j) ;  e_i -= al_j YY[i][j]
+//     second loop  j = 0..k-1 :  c_j = al_j - ro_j f_j ;  f_i += c_j SY[j][i] (i > j),  f = H_diag e
+// (b_i = s_i.q, e_i = y_i.q, f_i = y_i.r of the textbook recursion) and the direction is one
+// combination  d = -H_diag g + sum_j (-H_diag al_j) y_j + c_j s_j.  A step of the chain is a
+// register broadcast and one multiply-add (~35 cycles) instead of a 32-lane floating-point sum
+// over the parameter vector (~250); the inner products and the final combination are spread
+// over all warps.  Same mathematics as the reference's recursion, different rounding: it is an
+// explicit option (the default recursion reproduces the reference's operation order).
+#ifdef __CUDACC__
+#define SFX_GRAM_NL 32
+#define SFX_GRAM_NRK ((SFX_HIST + 31) / 32)
+#define SFX_GRAM_NRD (SFX_NP_MAX / 32)
+#else
+#define SFX_GRAM_NL 1
+#define SFX_GRAM_NRK SFX_HIST
+#define SFX_GRAM_NRD SFX_NP_MAX
+#endif
+
+template <typename T>
+SFX_FN T gram_warp_sum(T p) {
+#ifdef __CUDACC__
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+#endif
+    return p;
+}
+// value `idx` of a lane-distributed array (element i lives in lane i % NL, register i / NL)
+template <typename T>
+SFX_FN T gram_pick(const T* regs, int idx) {
+#ifdef __CUDACC__
+    static_assert(SFX_GRAM_NRK <= 4, "history longer than 128 pairs");
+    const int r = idx >> 5;
+    T v = regs[0];
+#pragma unroll
+    for (int q = 1; q < SFX_GRAM_NRK; ++q) v = r == q ? regs[q] : v;
+    return __shfl_sync(0xffffffffu, v, idx & 31);
+#else
+    return regs[idx];
+#endif
+}
+
+// Packed view of the two Gram matrices in recursion order (pair 0 = oldest): element (i, j) is
+// s_i.y_j above the diagonal and y_i.y_j on / below it -- all the recursion reads.
+template <typename T>
+struct GramStaged {            // k x k copy in shared memory, odd row stride (conflict-free by row and by column)
+    const T* G;
+    int ld;
+    SFX_MFN T operator()(int i, int j) const { return G[i * ld + j]; }
+};
+template <typename T>
+struct GramInPlace {           // the per-frame global arrays, indexed by history slot
+    const T* GSY;
+    const T* GYY;
+    int head, H;
+    SFX_MFN T operator()(int i, int j) const {
+        const int pi = (head + i) % H, pj = (head + j) % H;
+        return i < j ? GSY[pi * SFX_HIST + pj] : GYY[pi * SFX_HIST + pj];
+    }
+};
+
+// the two scalar recurrences, run by one warp with the state in registers; the loop bodies are
+// branch-free (clamped loads + selects) so that the warp never diverges inside the chain
+template <typename T, typename ACC>
+SFX_FN void gram_chain(Scratch<T>& S, int k, T hd, ACC G, int lane) {
+    T b[SFX_GRAM_NRK], e[SFX_GRAM_NRK];
+    int ic[SFX_GRAM_NRK];
+#pragma unroll
+    for (int r = 0; r < SFX_GRAM_NRK; ++r) {
+        const int i = lane + SFX_GRAM_NL * r;
+        ic[r] = i < k ? i : k - 1;                       // clamped: always a valid element
+        b[r] = i < k ? -S.sg[i] : (T)0;
+        e[r] = i < k ? -S.yg[i] : (T)0;
+    }
+    const T* ro = S.ro;
+    T* al = S.al;
+    T* cf = S.cf;
+    for (int j = k - 1; j >= 0; --j) {
+        // column j (s_i.y_j for i < j, y_i.y_j for i >= j) and row j (y_j.y_i for i < j): no
+        // dependence on the chain, so the loads overlap the broadcast below
+        T colv[SFX_GRAM_NRK], rowv[SFX_GRAM_NRK];
+#pragma unroll
+        for (int r = 0; r < SFX_GRAM_NRK; ++r) {
+            colv[r] = G(ic[r], j);
+            rowv[r] = G(j, ic[r]);
+        }
+        const T a = gram_pick(b, j) * ro[j];
+        if (lane == 0) al[j] = a;
+#pragma unroll
+        for (int r = 0; r < SFX_GRAM_NRK; ++r) {
+            const int i = lane + SFX_GRAM_NL * r;
+            const bool lo = i < j, in = i < k;
+            const T cb = lo ? colv[r] : (T)0;
+            const T ce = lo ? rowv[r] : (in ? colv[r] : (T)0);
+            b[r] -= a * cb;
+            e[r] -= a * ce;
+        }
+    }
+    SFX_SYNCWARP();
+#pragma unroll
+    for (int r = 0; r < SFX_GRAM_NRK; ++r) e[r] = e[r] * hd;      // f_i = y_i . (H_diag q)
+    for (int j = 0; j < k; ++j) {
+        T rowv[SFX_GRAM_NRK];
+#pragma unroll
+        for (int r = 0; r < SFX_GRAM_NRK; ++r) rowv[r] = G(j, ic[r]);
+        const T c = al[j] - gram_pick(e, j) * ro[j];
+        if (lane == 0) cf[j] = c;
+#pragma unroll
+        for (int r = 0; r < SFX_GRAM_NRK; ++r) {
+            const int i = lane + SFX_GRAM_NL * r;
+            const T cv = (i > j && i < k) ? rowv[r] : (T)0;
+            e[r] += c * cv;
+        }
+    }
+}
+
+// Inner products of every pair with the gradient and, when a pair was just stored, with that pair
+// (S.x0 = s_new, S.q = y_new: lbfgs_step).  Warp w takes pairs w, w + nw, ...; P pairs (2 P NR
+// loads per lane) are in flight at once because every row costs an L2 round trip.
+template <typename T, int NR, int P>
+SFX_FN void gram_dots(Scratch<T>& S, int k, int head, int H, const T* hist_s, const T* hist_y, int D,
+                      bool has_new, T* GSY, T* GYY, T* sG, int lds, int warp, int nw, int lane) {
+    constexpr int LD = SFX_HIST;
+    const int pn = (head + k - 1) % H;
+    const int n = k - 1;                              // recursion index of the new pair
+    T gv[NR], sn[NR], yn[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int el = lane + SFX_GRAM_NL * r;
+        gv[r] = el < D ? S.g[el] : (T)0;
+        sn[r] = (has_new && el < D) ? S.x0[el] : (T)0;
+        yn[r] = (has_new && el < D) ? S.q[el] : (T)0;
+    }
+    for (int i0 = warp; i0 < k; i0 += P * nw) {
+        T sv[P][NR], yv[P][NR];
+        int pi[P];
+#pragma unroll
+        for (int h = 0; h < P; ++h) {
+            const int i = i0 + h * nw;
+            pi[h] = (head + (i < k ? i : i0)) % H;    // past the end: repeat a valid pair (unused)
+            const T* srow = hist_s + (long)pi[h] * SFX_NP_MAX;
+            const T* yrow = hist_y + (long)pi[h] * SFX_NP_MAX;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int el = lane + SFX_GRAM_NL * r;
+                sv[h][r] = el < D ? srow[el] : (T)0;
+                yv[h][r] = el < D ? yrow[el] : (T)0;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < P; ++h) {
+            T q[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) q[u] = 0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                q[0] += sv[h][r] * gv[r];
+                q[1] += yv[h][r] * gv[r];
+                q[2] += sv[h][r] * yn[r];
+                q[3] += sn[r] * yv[h][r];
+                q[4] += yv[h][r] * yn[r];
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u) q[u] = gram_warp_sum(q[u]);
+            const int i = i0 + h * nw;
+            if (lane == 0 && i < k) {
+                S.sg[i] = q[0];
+                S.yg[i] = q[1];
+                if (has_new) {
+                    GSY[pi[h] * LD + pn] = q[2];
+                    GSY[pn * LD + pi[h]] = q[3];
+                    GYY[pi[h] * LD + pn] = q[4];
+                    GYY[pn * LD + pi[h]] = q[4];
+                    if (sG) {
+                        if (i < n) sG[i * lds + n] = q[2];      // s_i . y_new
+                        sG[n * lds + i] = q[4];                 // y_new . y_i  (i <= n)
+                    }
+                }
+            }
+        }
+    }
+}
+
+// d = -H_diag g + sum_j (-H_diag al_j) y_j + c_j s_j : pairs spread over the warps (P in flight),
+// per-warp partial vectors in `part`
+template <typename T, int NR, int P>
+SFX_FN void gram_combine(Scratch<T>& S, int k, int head, int H, T hd, const T* hist_s, const T* hist_y,
+                         int D, T* part, int warp, int nw, int lane) {
+    T acc[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) acc[r] = 0;
+    for (int j0 = warp; j0 < k; j0 += P * nw) {
+        T sv[P][NR], yv[P][NR], cy[P], cs[P];
+#pragma unroll
+        for (int h = 0; h < P; ++h) {
+            const int j = j0 + h * nw;
+            const bool live = j < k;
+            const int pj = (head + (live ? j : j0)) % H;
+            cy[h] = live ? -hd * S.al[j] : (T)0;
+            cs[h] = live ? S.cf[j] : (T)0;
+            const T* srow = hist_s + (long)pj * SFX_NP_MAX;
+            const T* yrow = hist_y + (long)pj * SFX_NP_MAX;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int el = lane + SFX_GRAM_NL * r;
+                sv[h][r] = el < D ? srow[el] : (T)0;
+                yv[h][r] = el < D ? yrow[el] : (T)0;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < P; ++h)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] += cy[h] * yv[h][r] + cs[h] * sv[h][r];
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int el = lane + SFX_GRAM_NL * r;
+        if (el < D) part[warp * SFX_NP_MAX + el] = acc[r];
+    }
+}
+
+template <typename T>
+SFX_FN_NOINLINE void gram_two_loop(const EvalCtx<T>& E, Scratch<T>& S, int k, int head, int H, T hd,
+                          const T* hist_s, const T* hist_y, int D, bool has_new) {
+    constexpr int LD = SFX_HIST;
+    T* GSY = E.gram;
+    T* GYY = E.gram + (size_t)LD * LD;
+#ifdef __CUDACC__
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
+#else
+    const int warp = 0, nw = 1, lane = 0;
+#endif
+    SFX_SYNC();
+    SFX_PROF_BEGIN(gd);
+    // ---- the live k x k blocks, packed, into the idle blend ring when they fit (otherwise --
+    //      float64 with a long history -- they are read in place).  The row / column of a pair
+    //      stored in this iteration is written by gram_dots, straight from its inner products. ----
+    T* part = S.q;                     // per-warp partial directions (host: one "warp")
+    T* sG = nullptr;
+    int lds = 0;
+    bool fast = false;
+#ifdef __CUDACC__
+    {
+        size_t area_bytes;
+        unsigned char* area = idle_area<T>(E.stream_ws, &area_bytes);
+        part = reinterpret_cast<T*>(area);
+        const size_t part_bytes = (size_t)nw * SFX_NP_MAX * sizeof(T);
+        const int ko = has_new ? k - 1 : k;              // pairs whose products are already stored
+        if constexpr (sizeof(T) == 4)
+            fast = part_bytes + (size_t)SFX_GRAM_ROWS * SFX_GRAM_LDF * sizeof(T) <= area_bytes;
+        if (fast) {
+            // float32 with the ring: fixed-stride [128][129] block, zero outside the live part,
+            // for gram_chain_f32.  A warp copies four rows at a time (16 loads in flight per lane).
+            static_assert(SFX_GRAM_ROWS == 128, "four 32-column registers per row");
+            sG = reinterpret_cast<T*>(area + part_bytes);
+            lds = SFX_GRAM_LDF;
+            int pj[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int j = lane + 32 * r;
+                pj[r] = head + (j < ko ? j : 0);
+                if (pj[r] >= H) pj[r] -= H;
+            }
+            for (int i0 = warp; i0 < SFX_GRAM_ROWS; i0 += 4 * nw) {
+                T v[4][4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const int i = i0 + h * nw;
+                    int pi = head + (i < ko ? i : 0);
+                    if (pi >= H) pi -= H;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int j = lane + 32 * r;
+                        v[h][r] = (i < ko && j < ko) ? (i < j ? GSY[pi * LD + pj[r]] : GYY[pi * LD + pj[r]])
+                                                     : (T)0;
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const int i = i0 + h * nw;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int j = lane + 32 * r;
+                        const bool new_pair = has_new && (i == ko || j == ko) && i < k && j < k;
+                        if (i < SFX_GRAM_ROWS && !new_pair) sG[i * SFX_GRAM_LDF + j] = v[h][r];
+                    }
+                }
+            }
+        } else {
+            // tight k x k block (odd row stride) for the generic chain
+            lds = k | 1;
+            if (part_bytes + (size_t)k * lds * sizeof(T) <= area_bytes) {
+                sG = reinterpret_cast<T*>(area + part_bytes);
+                const int n = ko * ko;
+                constexpr int U = 4;                     // loads in flight per thread
+                for (int idx0 = SFX_TID; idx0 < n; idx0 += U * SFX_NT) {
+                    T v[U];
+                    int dst[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int idx = idx0 + u * SFX_NT;
+                        const int i = idx / ko, j = idx - i * ko;
+                        int pi = head + i, pj = head + j;
+                        if (pi >= H) pi -= H;
+                        if (pj >= H) pj -= H;
+                        dst[u] = i * lds + j;
+                        v[u] = idx < n ? (i < j ? GSY[pi * LD + pj] : GYY[pi * LD + pj]) : (T)0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (idx0 + u * SFX_NT < n) sG[dst[u]] = v[u];
+                }
+            }
+        }
+    }
+    if (D <= 128) gram_dots<T, 4, 4>(S, k, head, H, hist_s, hist_y, D, has_new, GSY, GYY, sG, lds, warp, nw, lane);
+    else gram_dots<T, SFX_GRAM_NRD, 2>(S, k, head, H, hist_s, hist_y, D, has_new, GSY, GYY, sG, lds, warp, nw, lane);
+#else
+    gram_dots<T, SFX_GRAM_NRD, 2>(S, k, head, H, hist_s, hist_y, D, has_new, GSY, GYY, sG, lds, warp, nw, lane);
+#endif
+    SFX_SYNC();
+    SFX_PROF_END(S, 11, gd);
+    SFX_PROF_BEGIN(gc);
+    if (SFX_IS_WARP0) {
+        bool done = false;
+#ifdef __CUDACC__
+        if constexpr (sizeof(T) == 4) {
+            if (fast) {
+                gram_chain_f32(S, k, hd, sG, lane);
+                done = true;
+            }
+        }
+#endif
+        if (!done) {
+            if (sG) gram_chain(S, k, hd, GramStaged<T>{sG, lds}, lane);
+            else gram_chain(S, k, hd, GramInPlace<T>{GSY, GYY, head, H}, lane);
+        }
+    }
+    SFX_SYNC();
+    SFX_PROF_END(S, 12, gc);
+    SFX_PROF_BEGIN(gm);
+#ifdef __CUDACC__
+    if (D <= 128) gram_combine<T, 4, 4>(S, k, head, H, hd, hist_s, hist_y, D, part, warp, nw, lane);
+    else gram_combine<T, SFX_GRAM_NRD, 2>(S, k, head, H, hd, hist_s, hist_y, D, part, warp, nw, lane);
+#else
+    gram_combine<T, SFX_GRAM_NRD, 2>(S, k, head, H, hd, hist_s, hist_y, D, part, warp, nw, lane);
+#endif
+    SFX_SYNC();
+    SFX_FOR(el, D) {
+        T v = -hd * S.g[el];
+        for (int w = 0; w < nw; ++w) v += part[w * SFX_NP_MAX + el];
+        S.d[el] = v;
+    }
+    SFX_SYNC();
+    SFX_PROF_END(S, 13, gm);
+#ifdef __CUDACC__
+    idle_area_release(E.stream_ws);
+#endif
+}
+
 // One LBFGS.step (lbfgs_ls.py:256-445).  Returns the loss at entry ("orig_loss").
 template <typename T>
 SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, T* hist_s, T* hist_y) {
@@ -1792,7 +2166,9 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
                 S.x0[i] = S.d[i] * tt;
             }
             T ys = block_dot(S.q, S.x0, D, &S.red[2]);
+            bool has_new = false;
             if (ys > (T)1e-10) {
+                has_new = true;
                 int slot;
                 if (ls.num_old == H) {
                     slot = ls.head;
@@ -1822,6 +2198,11 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
             }
             // two-loop recursion
             const int k = ls.num_old;
+            if (E.st->generic_two_loop == 2 && E.gram != nullptr) {
+                SFX_PROF_BEGIN(tlg);
+                gram_two_loop(E, S, k, ls.head, H, ls.H_diag, hist_s, hist_y, D, has_new);
+                SFX_PROF_END(S, 1, tlg);
+            } else
 #ifdef __CUDACC__
             if (!E.st->generic_two_loop) {
                 SFX_SYNC();

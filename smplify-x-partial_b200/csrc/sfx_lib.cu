@@ -117,6 +117,7 @@ fit_stage_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__
     E.cam = Bv.cam + (size_t)f * SFX_CAM_STRIDE;
     E.reg_pose = Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr;
     E.stream_ws = &ws;
+    E.gram = Bv.gram ? Bv.gram + (size_t)f * 2 * SFX_HIST * SFX_HIST : nullptr;
     CollWS<T> CW;
     E.coll = block_coll_ws(M, Bv, ws, CW) ? &CW : nullptr;
     double r = run_fitting(E, S, Bv.hist_s + (size_t)f * SFX_HIST * SFX_NP_MAX,
@@ -352,6 +353,7 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
         E.cam = Bv.cam + (size_t)f * SFX_CAM_STRIDE;
         E.reg_pose = Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr;
         E.stream_ws = &ws;
+        E.gram = Bv.gram ? Bv.gram + (size_t)f * 2 * SFX_HIST * SFX_HIST : nullptr;
         CollWS<T> CW;
         E.coll = block_coll_ws(M, Bv, ws, CW) ? &CW : nullptr;
         T* hs = Bv.hist_s + (size_t)f * SFX_HIST * SFX_NP_MAX;
@@ -502,7 +504,7 @@ struct sfx_batch {
     int B = 0, use_vposer = 0;
     SfxLayout lay;
     size_t es = 4;        // element size of the batch dtype
-    DevBuf params, gt, conf, jw, lowconf, init_mask, cam, reg_pose, hist_s, hist_y, final_loss,
+    DevBuf params, gt, conf, jw, lowconf, init_mask, cam, reg_pose, hist_s, hist_y, gram, final_loss,
         n_evals, n_passes, flags, Acoef, Ccoef, vposed, go_saved, params_alt, loss_alt, pipe, counter,
         cam_loss, params_last, prof, coll_vals, coll_idx, coll_stat;
     bool last_valid = false;
@@ -516,7 +518,7 @@ struct sfx_batch {
         v.jw_base = (const T*)jw.p; v.lowconf = (const unsigned char*)lowconf.p;
         v.init_mask = (const unsigned char*)init_mask.p; v.cam = (const T*)cam.p;
         v.reg_pose = has_reg ? (const T*)reg_pose.p : nullptr;
-        v.hist_s = (T*)hist_s.p; v.hist_y = (T*)hist_y.p; v.final_loss = (T*)final_loss.p;
+        v.hist_s = (T*)hist_s.p; v.hist_y = (T*)hist_y.p; v.gram = (T*)gram.p; v.final_loss = (T*)final_loss.p;
         v.coll_vals = (T*)coll_vals.p; v.coll_idx = (unsigned short*)coll_idx.p;
         v.coll_stat = (int*)coll_stat.p;
         v.coll_vals_stride = coll_vals_per_block(m->V, m->F);
@@ -720,6 +722,7 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     ALLOC(reg_pose, (size_t)B * b->lay.n_pose * es);
     ALLOC(hist_s, (size_t)B * SFX_HIST * SFX_NP_MAX * es);
     ALLOC(hist_y, (size_t)B * SFX_HIST * SFX_NP_MAX * es);
+    ALLOC(gram, (size_t)B * 2 * SFX_HIST * SFX_HIST * es);
     ALLOC(final_loss, (size_t)B * es);
     ALLOC(n_evals, (size_t)B * sizeof(int));
     ALLOC(n_passes, (size_t)B * sizeof(int));

@@ -681,6 +681,92 @@ __device__ __forceinline__ bool two_loop_staged(Scratch<T>& S, int k, int head, 
     return true;
 }
 
+// ---- scalar recurrences of the Gram two-loop (sfx_core.cuh gram_chain), float32, written against
+// shared-state-space addresses.  G is the packed [SFX_GRAM_ROWS][SFX_GRAM_LDF] block (zero outside
+// the live k x k part), so a column is one walking address + immediates, the history is cut
+// into four 32-pair segments whose owner register is known at compile time (no selects on the
+// dependent chain), and a step is ~30 instructions: broadcast, multiply, multiply-adds.
+// Same operations in the same order as gram_chain<float>: bit-identical to it.
+__device__ __forceinline__ void gram_chain_f32(Scratch<float>& S, int k, float hd, const float* G, int lane) {
+    static_assert(SFX_HIST <= 128, "four 32-pair segments");
+    constexpr uint32_t LDB = 4u * SFX_GRAM_LDF;          // bytes per row
+    const uint32_t gA = smem_u32(G);
+    const uint32_t a_ro = smem_u32(S.ro), a_al = smem_u32(S.al), a_cf = smem_u32(S.cf);
+    float b[4], e[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = lane + 32 * r;
+        b[r] = i < k ? -S.sg[i] : 0.f;
+        e[r] = i < k ? -S.yg[i] : 0.f;
+    }
+#pragma unroll
+    for (int jr = 3; jr >= 0; --jr) {
+        const int jlo = 32 * jr, jhi = k - 1 < jlo + 31 ? k - 1 : jlo + 31;
+        uint32_t colA = gA + LDB * lane + 4u * jhi;      // element (lane, j); register r: + 32 rows
+        uint32_t rowA = gA + LDB * jhi + 4u * lane;      // element (j, lane); register r: + 32 columns
+        for (int j = jhi; j >= jlo; --j) {
+            float colv[4], rowv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) colv[r] = lds_f32(colA + 32u * LDB * r);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) rowv[r] = r <= jr ? lds_f32(rowA + 128u * r) : 0.f;
+            const float ro_j = lds_f32(a_ro + 4u * j);
+            const float a = __shfl_sync(0xffffffffu, b[jr], j & 31) * ro_j;
+            if (lane == 0) sts_f32(a_al + 4u * j, a);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (r < jr) {
+                    b[r] -= a * colv[r];
+                    e[r] -= a * rowv[r];
+                } else if (r == jr) {
+                    const bool lo = lane < (j & 31);
+                    b[r] -= a * (lo ? colv[r] : 0.f);
+                    e[r] -= a * (lo ? rowv[r] : colv[r]);
+                } else {
+                    e[r] -= a * colv[r];
+                }
+            }
+            colA -= 4u;
+            rowA -= LDB;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) e[r] = e[r] * hd;
+#pragma unroll
+    for (int jr = 0; jr < 4; ++jr) {
+        const int jlo = 32 * jr, jhi = k - 1 < jlo + 31 ? k - 1 : jlo + 31;
+        uint32_t rowA = gA + LDB * jlo + 4u * lane;
+        for (int j = jlo; j <= jhi; ++j) {
+            float rowv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) rowv[r] = r >= jr ? lds_f32(rowA + 128u * r) : 0.f;
+            const float ro_j = lds_f32(a_ro + 4u * j), al_j = lds_f32(a_al + 4u * j);
+            const float c = al_j - __shfl_sync(0xffffffffu, e[jr], j & 31) * ro_j;
+            if (lane == 0) sts_f32(a_cf + 4u * j, c);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (r > jr) e[r] += c * rowv[r];
+                else if (r == jr) e[r] += c * (lane > (j & 31) ? rowv[r] : 0.f);
+            }
+            rowA += LDB;
+        }
+    }
+    __syncwarp();
+}
+
+template <typename T>
+__device__ __forceinline__ unsigned char* idle_area(void* wsp, size_t* bytes) {
+    StreamWS& ws = *reinterpret_cast<StreamWS*>(wsp);
+    *bytes = ws.ring_mode ? (size_t)SFX_NWARP * SFX_NBUF * SFX_KPAD * sizeof(T)
+                          : (size_t)SFX_NWARP * SFX_KPAD * sizeof(T);
+    return ws.ring;
+}
+// the ring is written by TMA (async proxy) next: order the generic-proxy accesses before it
+__device__ __forceinline__ void idle_area_release(void* wsp) {
+    if (reinterpret_cast<StreamWS*>(wsp)->ring_mode) fence_proxy_async();
+}
+
 template <typename T>
 __host__ __device__ inline size_t stream_smem_bytes(int ring_mode) {
     size_t ring = ring_mode ? (size_t)SFX_NWARP * SFX_NBUF * SFX_KPAD * sizeof(T)

@@ -76,7 +76,10 @@ struct SfxStage {
     int block_len[SFX_MAX_BLOCKS];
     int block_off[SFX_MAX_BLOCKS];             // into the full parameter vector
     int need_blend_grad;                       // 0 when only global_orient / camera are optimised
-    int generic_two_loop;                      // debug: block-wide two-loop recursion (A/B test)
+    int generic_two_loop;                      // L-BFGS direction: 0 the reference's recursion, one warp (default);
+                                               // 1 the same by the whole block (A/B test); 2 the same recursion on
+                                               // the inner products of the history (gram_two_loop: same mathematics,
+                                               // different rounding, shorter dependent chain)
     // --- interpenetration term (fitting.py:437-455; third-party mesh_intersection) ---
     double coll_loss_weight;                   // enters unsquared (fitting.py:453-455); 0 = term off
     double coll_sigma;                         // df_cone_height (fit_single_frame.py:310)

@@ -76,7 +76,8 @@ def _opt_kw(cfg):
         raise ValueError('Optimizer {} not supported on the device (lbfgsls, adam)'.format(kind))
     return dict(opt_kind=_OPT_KIND[kind], lr=cfg.get('lr', 1.0), maxiters=cfg.get('maxiters', 30),
                 ftol=cfg.get('ftol', 1e-9), gtol=cfg.get('gtol', 1e-9),
-                adam_beta1=cfg.get('beta1', 0.9), adam_beta2=cfg.get('beta2', 0.999))
+                adam_beta1=cfg.get('beta1', 0.9), adam_beta2=cfg.get('beta2', 0.999),
+                two_loop=cfg.get('two_loop'))
 
 
 def body_pose_prior_kind(cfg):

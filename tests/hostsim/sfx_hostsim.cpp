@@ -80,7 +80,8 @@ static void run(SimModel<T>& sm, const SfxStage* st, int use_vposer, int do_fit,
         W.dtri_g = dtri_g.data(); W.work = work.data(); W.work_bytes = sm.coll_work_bytes;
         Wp = &W;
     }
-    EvalCtx<T> E{&M, &L, st, gt, conf, init_mask, cam, reg_pose, nullptr, Wp};
+    std::vector<T> gram((size_t)2 * SFX_HIST * SFX_HIST);
+    EvalCtx<T> E{&M, &L, st, gt, conf, init_mask, cam, reg_pose, nullptr, Wp, gram.data()};
     if (!do_fit) {
         eval_frame(M, L, *st, gt, conf, init_mask, cam, reg_pose, S, nullptr, Wp);
         *loss_out = S.loss;

@@ -20,12 +20,17 @@ def _frame_inputs(inp, frame):
     return inp[frame + '/keypoints'], H, W, expose, pixie
 
 
-def test_demo_frames_against_reference_fit():
+@pytest.mark.parametrize('two_loop', ['exact', 'gram'])
+def test_demo_frames_against_reference_fit(two_loop):
+    """``two_loop``: the reference's recursion in its own operation order, and the same recursion
+    on the inner products of the history (what bench.py runs by default) -- both are held to
+    the reference's own run-to-run envelope."""
     from smplifyx_b200 import engine, fit_frames as FF
     inp = Cm.golden('demo_inputs.npz')
     ref = Cm.golden('ref_fit_02.npz')
     env = Cm.golden('ref_envelope.npz')
     cfg = json.loads(str(ref['cfg_json']))
+    cfg['two_loop'] = two_loop
     model = engine.Model(Cm.model_data(), Cm.joint_map(), dtype=torch.float32, **Cm.MODEL_KW)
     frames = ['02_cropped', '18_cropped', '02_cropped']
     data = [_frame_inputs(inp, f) for f in frames]

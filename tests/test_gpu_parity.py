@@ -16,6 +16,7 @@ import pytest
 import torch
 
 from tests import common as Cm
+from smplifyx_b200 import _native as N
 
 pytestmark = pytest.mark.gpu
 
@@ -324,3 +325,73 @@ def test_adam_stage(model64):
     FP.run_fitting(opt, closure, [(0, 3), (3, 6)], lambda: last['g'], maxiters=30)
     assert np.abs(got[act] - x.detach().numpy()).max() < 1e-9
     assert np.abs(got[act] - I['x'][act]).max() > 1e-2          # it moved
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', ['l2', 'camconf'])
+def test_gram_two_loop_f64_matches_exact_recursion(model64, case):
+    """Coefficient-space two-loop on the device (registers + broadcast chain, Gram blocks staged
+    in shared memory or read in place) against the default recursion, float64: same minimum,
+    same number of evaluations up to the chaotic tail."""
+    import copy
+    ev = Cm.golden('ref_eval_f64.npz')
+    I = Cm.eval_case_inputs(ev, case)
+    outs = []
+    for mode in ('exact', 'gram'):
+        st = copy.copy(I['stage'])
+        st.generic_two_loop = N.two_loop_mode(mode)
+        batch = _engine().FrameBatch(model64, 2)
+        _load(batch, I, 2)
+        final = batch.fit_stage(st).cpu().numpy()
+        outs.append((final, batch.get_params(), batch.evals().cpu().numpy()))
+    assert np.abs(outs[0][0] - outs[1][0]).max() <= 1e-8 * np.abs(outs[0][0]).max()
+    assert np.abs(outs[0][2] - outs[1][2]).max() <= 10
+    assert np.array_equal(outs[1][1][0], outs[1][1][1])      # frames independent of position
+
+
+@pytest.mark.gpu
+def test_gram_two_loop_f32_short_history_follows_exact(model32):
+    """float32, staged path: with a handful of iterations the two recursions still agree to
+    round-off in the parameters they reach (before chaos amplifies the difference)."""
+    import copy
+    ev = Cm.golden('ref_eval_f32.npz')
+    I = Cm.eval_case_inputs(ev, 'camconf')
+    outs = []
+    for mode in ('exact', 'gram'):
+        st = copy.copy(I['stage'])
+        st.generic_two_loop = N.two_loop_mode(mode)
+        st.maxiters = 1
+        st.max_iter = 6
+        st.max_eval = 8
+        batch = _engine().FrameBatch(model32, 2)
+        _load(batch, I, 2)
+        final = batch.fit_stage(st).cpu().numpy()
+        outs.append((final, batch.get_params(), batch.evals().cpu().numpy()))
+    assert np.abs(outs[0][0] - outs[1][0]).max() <= 1e-4 * np.abs(outs[0][0]).max()
+    assert np.abs(outs[0][1] - outs[1][1]).max() <= 1e-3 * max(1.0, np.abs(outs[0][1]).max())
+
+
+@pytest.mark.gpu
+def test_gram_two_loop_f32_staging_variants_bit_identical(model32, monkeypatch):
+    """float32: the zero-padded fixed-stride block + shared-address chain (TMA-ring build of the
+    launch) and the tight block / in-place reads + generic chain (plain-load build) perform the
+    same operations in the same order: a whole stage ends with the same bits."""
+    import copy
+    ev = Cm.golden('ref_eval_f32.npz')
+    I = Cm.eval_case_inputs(ev, 'reg')
+    st = copy.copy(I['stage'])
+    st.generic_two_loop = N.two_loop_mode('gram')
+    outs = []
+    for direct in (False, True):
+        if direct:
+            monkeypatch.setenv('SFX_STREAM_DIRECT', '1')
+        batch = _engine().FrameBatch(model32, 2)
+        _load(batch, I, 2)
+        final = batch.fit_stage(st).cpu().numpy()
+        outs.append((final, batch.get_params(), batch.evals().cpu().numpy()))
+        if direct:
+            monkeypatch.delenv('SFX_STREAM_DIRECT')
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+    assert outs[0][2].min() > 60

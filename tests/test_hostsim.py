@@ -172,3 +172,27 @@ def test_adam_matches_torch(hs64):
     FP.run_fitting(FP.AdamPort(x, lr=1e-2), closure, [(0, 3), (3, 6)], lambda: last['g'],
                    maxiters=30)
     assert np.abs(r['params'][act] - x.numpy()).max() < 1e-12
+
+
+@pytest.mark.parametrize('case', ['l2', 'camconf'])
+def test_gram_two_loop_is_the_same_recursion(hs64, case):
+    """The coefficient-space ("Gram") two-loop (sfx_core.cuh gram_two_loop) is the recursion of
+    lbfgs_ls.py:336-358 in exact arithmetic: in float64 a stage follows the default recursion
+    loss for loss until round-off (chaos) separates them, and ends at the same minimum."""
+    import copy
+    ev = Cm.golden('ref_eval_f64.npz')
+    I = Cm.eval_case_inputs(ev, case)
+    runs = []
+    for mode in ('exact', 'gram'):
+        st = copy.copy(I['stage'])
+        st.generic_two_loop = N.two_loop_mode(mode)
+        hs64.trace()
+        r = hs64.fit(st, I['x'], I['gt'], I['conf'], I['jw'], I['cam'], I['lowconf'],
+                     I['init_mask'], I['reg_pose'])
+        runs.append((r, hs64.trace().copy()))
+    (r0, t0), (r1, t1) = runs
+    n = min(len(t0), len(t1), 30)
+    assert n >= 30
+    assert np.abs(t0[:n] - t1[:n]).max() <= 1e-9 * np.abs(t0[:n]).max()
+    assert abs(r0['loss'] - r1['loss']) <= 1e-8 * abs(r0['loss'])
+    assert abs(r0['n_evals'] - r1['n_evals']) <= 10
