@@ -40,8 +40,10 @@ SUPPORT_ROWS = 225 * 3
 ROW_BYTES = 512 * 4
 # dram__bytes_read.sum + dram__bytes_write.sum of one fit_pipeline_kernel<float> launch of the
 # default workload (128 frames), from the `ncu --set full` capture summarised in
-# profiles/r01p_ncu_raw_pipeline_kernel.csv (7.22 MB read + 5.38 MB written)
-NCU_TRAFFIC_BYTES_DEFAULT_WORKLOAD = 12591616.0
+# profiles/r01v_ncu_raw_pipeline_kernel.csv (Gram two-loop: 10.88 MB read + 13.70 MB written; the
+# per-frame Gram blocks add 80 KB per frame) and profiles/r01p_... (exact recursion: 7.22 + 5.38 MB)
+NCU_TRAFFIC_BYTES = {'gram': (24584448.0, 'profiles/r01v_ncu_raw_pipeline_kernel.csv'),
+                     'exact': (12591616.0, 'profiles/r01p_ncu_raw_pipeline_kernel.csv')}
 
 
 # ------------------------------------------------------------------------------ workload
@@ -545,8 +547,7 @@ def run_b200(args):
     if args.traffic is not None:
         roofline['traffic'] = args.traffic
     elif B == 128 and not args.interpenetration and not args.vposer:
-        roofline['traffic'] = NCU_TRAFFIC_BYTES_DEFAULT_WORKLOAD
-        roofline['traffic_source'] = 'profiles/r01p_ncu_raw_pipeline_kernel.csv'
+        roofline['traffic'], roofline['traffic_source'] = NCU_TRAFFIC_BYTES[TWO_LOOP]
     coll_stats = batch.coll_stats()
     if coll_stats is not None:
         cs = coll_stats.cpu().numpy()
