@@ -573,15 +573,25 @@ def run_b200(args):
             and not args.vposer:
         procs = os.cpu_count() or 1
         sample = list(range(min(args.cpu_frames or procs, B)))
-        pool = OraclePool(cfg, kp, expose, pixie, min(procs, len(sample)))
-        wall, res = pool.round(sample)
-        pool.close()
-        line['cpu_baseline'] = {
-            'value': len(sample) / wall, 'unit': UNIT, 'cores': pool.procs, 'kind': 'port',
-            'sample': 'frames 0..{} of the same batch fitted by the oracle port of the reference, '
-                      'one single-threaded process per host core ({} processes, one frame each); '
-                      '{:.1f} s wall, mean {:.0f} evals/frame'.format(
-                          len(sample) - 1, pool.procs, wall, float(np.mean([e for _, e in res])))}
+        try:
+            pool = OraclePool(cfg, kp, expose, pixie, min(procs, len(sample)))
+            wall, res = pool.round(sample)
+            pool.close()
+            line['cpu_baseline'] = {
+                'value': len(sample) / wall, 'unit': UNIT, 'cores': pool.procs, 'kind': 'port',
+                'sample': 'frames 0..{} of the same batch fitted by the oracle port of the '
+                          'reference, one single-threaded process per host core ({} processes, one '
+                          'frame each); {:.1f} s wall, mean {:.0f} evals/frame'.format(
+                              len(sample) - 1, pool.procs, wall,
+                              float(np.mean([e for _, e in res])))}
+        except Exception as exc:     # no worker processes on this host: one process, all threads
+            secs, evals = time_oracle_frames(cfg, kp, expose, pixie, sample[:2], procs)
+            line['cpu_baseline'] = {
+                'value': len(secs) / float(np.sum(secs)), 'unit': UNIT, 'cores': procs,
+                'kind': 'port',
+                'sample': 'frames 0..{} fitted sequentially by the oracle port ({} torch threads; '
+                          'worker processes unavailable: {}); {:.1f} s'.format(
+                              len(secs) - 1, procs, type(exc).__name__, float(np.sum(secs)))}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
