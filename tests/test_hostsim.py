@@ -196,3 +196,24 @@ def test_gram_two_loop_is_the_same_recursion(hs64, case):
     assert np.abs(t0[:n] - t1[:n]).max() <= 1e-9 * np.abs(t0[:n]).max()
     assert abs(r0['loss'] - r1['loss']) <= 1e-8 * abs(r0['loss'])
     assert abs(r0['n_evals'] - r1['n_evals']) <= 10
+
+
+def test_gram_two_loop_short_history_wraps(hs64):
+    """history = 6: the ring of (s, y) pairs wraps after a few iterations, so the per-slot Gram
+    blocks are overwritten in place (pop oldest / store newest) many times over a stage."""
+    import copy
+    ev = Cm.golden('ref_eval_f64.npz')
+    I = Cm.eval_case_inputs(ev, 'l2')
+    runs = []
+    for mode in ('exact', 'gram'):
+        st = copy.copy(I['stage'])
+        st.history = 6
+        st.generic_two_loop = N.two_loop_mode(mode)
+        hs64.trace()
+        r = hs64.fit(st, I['x'], I['gt'], I['conf'], I['jw'], I['cam'], I['lowconf'],
+                     I['init_mask'], I['reg_pose'])
+        runs.append((r, hs64.trace().copy()))
+    (r0, t0), (r1, t1) = runs
+    n = min(len(t0), len(t1), 40)
+    assert n >= 40                      # well past the first wrap
+    assert np.abs(t0[:n] - t1[:n]).max() <= 1e-9 * np.abs(t0[:n]).max()
