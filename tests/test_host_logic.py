@@ -260,3 +260,25 @@ def test_shard_ranges_partition_the_frames():
                 seen += list(rg)
                 assert abs(len(rg) - n / world) < 1
             assert seen == list(range(n))
+
+
+def test_two_loop_option_reaches_the_stages(monkeypatch):
+    """The engine-only key ``two_loop`` (yaml / CLI / SFX_TWO_LOOP) selects SfxStage's
+    L-BFGS-direction mode for the camera stage and every annealing stage; unknown names raise."""
+    from smplifyx_b200 import _native as N
+    from smplifyx_b200.cmd_parser import parse_config
+    cfg_file = os.path.join(Cm.ROOT, 'cfg_files', 'fit_smplx_combined_coco25.yaml')
+    cfg = parse_config(['-c', cfg_file])
+    assert cfg['two_loop'] is None
+    L = Cm.layout()
+    monkeypatch.delenv('SFX_TWO_LOOP', raising=False)
+    cam, stages = FF.make_stages(dict(cfg, interpenetration=False), L)
+    assert cam.generic_two_loop == 0 and all(st.generic_two_loop == 0 for st in stages)
+    cfg = parse_config(['-c', cfg_file, '--two_loop', 'gram'])
+    cam, stages = FF.make_stages(dict(cfg, interpenetration=False), L)
+    assert cam.generic_two_loop == 2 and all(st.generic_two_loop == 2 for st in stages)
+    monkeypatch.setenv('SFX_TWO_LOOP', 'gram')
+    assert N.make_stage(L, N.BODY_STAGE_BLOCKS).generic_two_loop == 2
+    assert N.make_stage(L, N.BODY_STAGE_BLOCKS, two_loop='exact').generic_two_loop == 0
+    with pytest.raises(ValueError):
+        N.make_stage(L, N.BODY_STAGE_BLOCKS, two_loop='fast')
