@@ -89,7 +89,8 @@ int sfx_model_set_gmm(sfx_model* m, int32_t num_gaussians, int32_t dim, const vo
 int sfx_model_set_collision(sfx_model* m, const int32_t* faces_segm, const int32_t* faces_parents,
                             const int32_t* ign_part_pairs, int32_t n_ign_pairs);
 
-/* Per-batch workspace: parameters, targets, L-BFGS history for B independent frames.
+/* Per-batch workspace: parameters, targets, L-BFGS history (154 KB per frame in float32) and its
+ * inner products (80 KB per frame; SfxStage.generic_two_loop = 2) for B independent frames.
  * use_vposer selects a 32-D latent pose block instead of the 63-D axis-angle one. */
 int sfx_batch_create(const sfx_model* m, int32_t num_frames, int32_t use_vposer, sfx_batch** out);
 void sfx_batch_destroy(sfx_batch* b);
