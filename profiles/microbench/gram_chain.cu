@@ -16,9 +16,9 @@ __global__ void chain_kernel(int k, float hd, int which, long long* out, float* 
     for (int idx = threadIdx.x; idx < SFX_GRAM_ROWS * SFX_GRAM_LDF; idx += blockDim.x) {
         const int i = idx / SFX_GRAM_LDF, j = idx % SFX_GRAM_LDF;
         unsigned h = (unsigned)(i * 131 + j * 71 + 7) * 2654435761u;
-        G[idx] = (i < k && j < k) ? ((h >> 8) % 2001 - 1000) * 1e-4f + (i == j ? 1.f : 0.f) : 0.f;
+        G[idx] = (i < k && j < k) ? ((int)((h >> 8) % 2001) - 1000) * 2e-6f + (i == j ? 1.f : 0.f) : 0.f;
     }
-    for (int i = threadIdx.x; i < k; i += blockDim.x) { S.sg[i] = 0.01f * (i % 13) - 0.05f; S.yg[i] = 0.02f * (i % 7) - 0.06f; S.ro[i] = 0.5f + 0.001f * i; }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) { S.sg[i] = 0.01f * (i % 13) - 0.05f; S.yg[i] = 0.02f * (i % 7) - 0.06f; S.ro[i] = 0.9f + 0.001f * i; }
     __syncthreads();
     long long t0 = clock64();
     if (threadIdx.x < 32) {
