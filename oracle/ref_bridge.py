@@ -123,3 +123,25 @@ def load():
                 sys.modules[k] = saved[k]
     _loaded = ns
     return ns
+
+
+def load_cmd_parser():
+    """The reference's unmodified ``cmd_parser`` module (smplifyx/cmd_parser.py) running on the
+    restated ``configargparse`` (oracle/configargparse_shim.py)."""
+    import importlib.util
+    from oracle import configargparse_shim
+    if not available():
+        raise RuntimeError('reference tree not present at ' + REF_ROOT)
+    saved = sys.modules.get('configargparse')
+    sys.modules['configargparse'] = configargparse_shim
+    try:
+        spec = importlib.util.spec_from_file_location('_sfxref_cmd_parser',
+                                                      os.path.join(REF_PKG, 'cmd_parser.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is not None:
+            sys.modules['configargparse'] = saved
+        else:
+            sys.modules.pop('configargparse', None)
+    return mod
