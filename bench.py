@@ -629,9 +629,13 @@ def main():
     ap.add_argument('--traffic', type=float, default=None,
                     help='dram bytes per launch from an ncu capture (profiles/), recorded as-is')
     args = ap.parse_args()
+    global TWO_LOOP
     if args.two_loop:
-        global TWO_LOOP
         TWO_LOOP = args.two_loop
+    elif args.interpenetration and 'SFX_TWO_LOOP' not in os.environ:
+        # config 4 was measured (profiles/r01o_*) with the exact recursion; its time is the
+        # collision search, not the two-loop
+        TWO_LOOP = 'exact'
     if args.impl == 'reference':
         run_reference(args)
     else:
