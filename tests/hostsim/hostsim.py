@@ -25,6 +25,24 @@ def build(force=False):
     return _SO
 
 
+def lbfgs_direction(mode, s, y, g, h_diag, use_double):
+    """L-BFGS direction from k pairs ``s, y [k, D]`` (oldest first) and the gradient ``g [D]``:
+    ``mode`` 'exact' = the reference's recursion as lbfgs_step runs it, 'gram' = gram_two_loop
+    with its Gram blocks built pair by pair (host build of csrc/sfx_core.cuh)."""
+    lib = C.CDLL(build())
+    dt = np.float64 if use_double else np.float32
+    s = np.ascontiguousarray(s, dtype=dt)
+    y = np.ascontiguousarray(y, dtype=dt)
+    g = np.ascontiguousarray(g, dtype=dt)
+    k, D = s.shape
+    out = np.zeros(D, dtype=dt)
+    lib.hs_lbfgs_direction.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_double, C.c_void_p]
+    lib.hs_lbfgs_direction(int(use_double), N.two_loop_mode(mode), k, D, s.ctypes.data,
+                           y.ctypes.data, g.ctypes.data, float(h_diag), out.ctypes.data)
+    return out
+
+
 class HostSim(object):
     def __init__(self, model_data, joint_map, use_double=True, use_vposer=False, **model_kw):
         self.lib = C.CDLL(build())

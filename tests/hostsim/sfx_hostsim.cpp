@@ -116,7 +116,67 @@ static void set_vposer(SimModel<T>& sm, const T* w1, const T* b1, const T* w2, c
     for (size_t i = 0; i < (size_t)126 * 512; ++i) sm.vw3[i] = w3[i];
     for (int i = 0; i < 126; ++i) sm.vb3[i] = b3[i];
 }
+// Unit access to the L-BFGS direction (lbfgs_ls.py:336-358): k pairs (s, y) [k][D], oldest first,
+// gradient g, initial scaling hd.  mode 0: the reference's recursion, statement for statement
+// the block-wide path of lbfgs_step; mode 2: gram_two_loop, its Gram blocks built pair by pair
+// exactly as lbfgs_step builds them (one call per stored pair).
+template <typename T>
+static void lbfgs_direction(int mode, int k, int D, const T* s, const T* y, const T* g, T hd, T* d_out) {
+    std::unique_ptr<Scratch<T>> Sp(new Scratch<T>());
+    Scratch<T>& S = *Sp;
+    std::memset(&S, 0, sizeof(S));
+    const int H = SFX_HIST;
+    std::vector<T> hs((size_t)SFX_HIST * SFX_NP_MAX), hy((size_t)SFX_HIST * SFX_NP_MAX);
+    std::vector<T> gram((size_t)2 * SFX_HIST * SFX_HIST);
+    for (int i = 0; i < k; ++i) {
+        for (int e = 0; e < D; ++e) {
+            hs[(size_t)i * SFX_NP_MAX + e] = s[(size_t)i * D + e];
+            hy[(size_t)i * SFX_NP_MAX + e] = y[(size_t)i * D + e];
+        }
+        T ys = block_dot(&hy[(size_t)i * SFX_NP_MAX], &hs[(size_t)i * SFX_NP_MAX], D, &S.red[2]);
+        S.ro[i] = (T)1 / ys;
+    }
+    for (int e = 0; e < D; ++e) S.g[e] = g[e];
+    if (mode == 0) {
+        for (int e = 0; e < D; ++e) S.q[e] = -S.g[e];
+        for (int i = k - 1; i >= 0; --i) {
+            const T* srow = &hs[(size_t)i * SFX_NP_MAX];
+            const T* yrow = &hy[(size_t)i * SFX_NP_MAX];
+            T a = block_dot(srow, S.q, D, &S.red[2]) * S.ro[i];
+            S.al[i] = a;
+            for (int e = 0; e < D; ++e) S.q[e] += -a * yrow[e];
+        }
+        for (int e = 0; e < D; ++e) S.d[e] = S.q[e] * hd;
+        for (int i = 0; i < k; ++i) {
+            const T* srow = &hs[(size_t)i * SFX_NP_MAX];
+            const T* yrow = &hy[(size_t)i * SFX_NP_MAX];
+            T be = block_dot(yrow, S.d, D, &S.red[2]) * S.ro[i];
+            T co = S.al[i] - be;
+            for (int e = 0; e < D; ++e) S.d[e] += co * srow[e];
+        }
+    } else {
+        EvalCtx<T> E{};
+        E.gram = gram.data();
+        for (int i = 0; i < k; ++i) {
+            for (int e = 0; e < D; ++e) {
+                S.x0[e] = hs[(size_t)i * SFX_NP_MAX + e];
+                S.q[e] = hy[(size_t)i * SFX_NP_MAX + e];
+            }
+            gram_two_loop(E, S, i + 1, 0, H, hd, hs.data(), hy.data(), D, true);
+        }
+        if (k == 0) gram_two_loop(E, S, 0, 0, H, hd, hs.data(), hy.data(), D, false);
+    }
+    for (int e = 0; e < D; ++e) d_out[e] = S.d[e];
+}
+
 extern "C" {
+void hs_lbfgs_direction(int use_double, int mode, int k, int D, const void* s, const void* y,
+                        const void* g, double hd, void* d_out) {
+    if (use_double)
+        lbfgs_direction<double>(mode, k, D, (const double*)s, (const double*)y, (const double*)g, hd, (double*)d_out);
+    else
+        lbfgs_direction<float>(mode, k, D, (const float*)s, (const float*)y, (const float*)g, (float)hd, (float*)d_out);
+}
 void hs_set_vposer(void* p, const void* w1, const void* b1, const void* w2, const void* b2,
                    const void* w3, const void* b3) {
     SimHandle* h = (SimHandle*)p;

@@ -217,3 +217,28 @@ def test_gram_two_loop_short_history_wraps(hs64):
     n = min(len(t0), len(t1), 40)
     assert n >= 40                      # well past the first wrap
     assert np.abs(t0[:n] - t1[:n]).max() <= 1e-9 * np.abs(t0[:n]).max()
+
+
+@pytest.mark.parametrize('k,cond', [(0, 1e2), (1, 1e2), (5, 1e5), (30, 1e2), (100, 1e5)])
+def test_gram_direction_accuracy(k, cond):
+    """One L-BFGS direction from a given history (quadratic model with condition number
+    ``cond``, steps shrinking towards the newest pair): the Gram two-loop equals the reference's
+    recursion to round-off in float64, and in float32 its distance from the float64 direction
+    is of the order of the exact recursion's own float32 error."""
+    from tests.hostsim import hostsim as HS
+    rng = np.random.default_rng(k)
+    D = 119
+    Q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    A = (Q * np.geomspace(1, cond, D)) @ Q.T
+    S = rng.standard_normal((k, D)) * np.geomspace(1, 1e-3, max(k, 1))[::-1][:k, None]
+    Y = S @ A
+    Y = Y + 1e-3 * rng.standard_normal((k, D)) * np.linalg.norm(Y, axis=1, keepdims=True) / np.sqrt(D)
+    g = rng.standard_normal(D) * 1e-2
+    hd = (S[-1] @ Y[-1]) / (Y[-1] @ Y[-1]) if k else 1.0
+    ref = HS.lbfgs_direction('exact', S, Y, g, hd, True)
+    nrm = np.linalg.norm(ref)
+    assert np.linalg.norm(HS.lbfgs_direction('gram', S, Y, g, hd, True) - ref) <= 1e-12 * nrm
+    e32 = np.linalg.norm(HS.lbfgs_direction('exact', S, Y, g, hd, False) - ref) / nrm
+    g32 = np.linalg.norm(HS.lbfgs_direction('gram', S, Y, g, hd, False) - ref) / nrm
+    assert e32 < 2e-6 and g32 < 2e-6
+    assert g32 <= 5 * e32 + 2e-7
