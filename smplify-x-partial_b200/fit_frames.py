@@ -277,6 +277,8 @@ class FitPlan(object):
                  np_dtype=np.float32, body_pose_prior=None, vposer=None, part_segm=None,
                  pare=None):
         B = keypoints.shape[0]
+        if B < 1:
+            raise ValueError('a fit needs at least one frame (sfx_batch_create rejects empty batches)')
         self.B, self.K, self.L, self.cfg = B, K, L, cfg
         npd = self.np_dtype = np_dtype
         self.keypoints = keypoints = np.asarray(keypoints, dtype=np.float64).reshape(B, K, 3)

@@ -282,3 +282,17 @@ def test_two_loop_option_reaches_the_stages(monkeypatch):
     assert N.make_stage(L, N.BODY_STAGE_BLOCKS, two_loop='exact').generic_two_loop == 0
     with pytest.raises(ValueError):
         N.make_stage(L, N.BODY_STAGE_BLOCKS, two_loop='fast')
+
+
+def test_degenerate_inputs_at_plan_level():
+    """Empty batches are refused with a clear message; frames without a single detected
+    keypoint still plan (no init joints, both orientations because the shoulders coincide,
+    finite start) -- the reference would run them too (fit_single_frame.py:285-294, :477-480)."""
+    import bench
+    cfg = dict(bench.bench_cfg(), regression_prior=None, use_camera_prior=False)
+    L = Cm.layout()
+    with pytest.raises(ValueError, match='at least one frame'):
+        FF.FitPlan(L, 135, np.zeros((0, 135, 3)), 600, 800, cfg, None, None, None, np.float32)
+    plan = FF.FitPlan(L, 135, np.zeros((2, 135, 3)), 600, 800, cfg, None, None, None, np.float32)
+    assert list(plan.flip_ids) == [0, 1]
+    assert np.isfinite(plan.x0).all()
