@@ -4,9 +4,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--frames B] [--impl b200|reference]
 
 A "step" is one complete fit (camera stage + every annealing stage + final full-mesh forward)
-of one batch of B synthetic frames (BASELINE.json configs[1]: 128 frames, neutral SMPL-X-shaped
-model, GMoF data term + L2 priors, 3-stage schedule of cfg_files/fit_smplx_combined_coco25.yaml
-with a synthetic "combined" regression prior and camera prior, lbfgsls, no interpenetration).
+of one batch of B synthetic frames.  Default workload = BASELINE.json configs[1] as SURVEY.md
+section 8d specifies it: 128 frames, neutral SMPL-X-shaped model, GMoF data term + L2 priors,
+3-stage weight schedule of cfg_files/fit_smplx_combined_coco25.yaml, lbfgsls, NO regression
+prior: the fit starts from the prior's mean pose (fit_single_frame.py:250-252) and the camera from
+guess_init (:404-411); no interpenetration.  ``--regression-prior`` adds the synthetic "combined"
+regression + camera prior (the per-frame setup of config 5; round 1's default line),
+``--vposer`` is config 3, ``--interpenetration`` config 4.
 
 * ``value``   frames/s with the inputs already resident in HBM (device-timed, CUDA events);
 * ``e2e``     frames/s through the public call ``fit_frames`` with host buffers: planning,
@@ -14,7 +18,11 @@ with a synthetic "combined" regression prior and camera prior, lbfgsls, no inter
               and meshes, all inside the timed region;
 * ``roofline`` for the dominant kernel ``fit_pipeline_kernel`` (DESIGN.md "Measurement");
 * ``cpu_baseline`` the oracle port of the reference (oracle/fit_port.py) on a bounded sample
-              of the same frames on this host's cores (rank 0, N = 1 only).
+              of the same frames on this host's cores (rank 0, N = 1 only);
+* ``parity``  the engine's fitted frames against the CPU leg's fits of the SAME frames (final
+              loss, vertices, reprojected keypoints, evaluation counts);
+* ``value_exact`` the same device-timed figure with the reference's own two-loop operation
+              order (``value`` runs the Gram formulation of the same recursion).
 
 ``--impl reference`` times the reference's CPU path (the oracle port; a step fits one frame per
 host core, one single-threaded process per core -- the reference itself is batch-size-1 and
@@ -42,8 +50,8 @@ ROW_BYTES = 512 * 4
 # default workload (128 frames), from the `ncu --set full` capture summarised in
 # profiles/r01v_ncu_raw_pipeline_kernel.csv (Gram two-loop: 10.88 MB read + 13.70 MB written; the
 # per-frame Gram blocks add 80 KB per frame) and profiles/r01p_... (exact recursion: 7.22 + 5.38 MB)
-NCU_TRAFFIC_BYTES = {'gram': (24584448.0, 'profiles/r01v_ncu_raw_pipeline_kernel.csv'),
-                     'exact': (12591616.0, 'profiles/r01p_ncu_raw_pipeline_kernel.csv')}
+NCU_TRAFFIC_BYTES = {'gram_reg': (24584448.0, 'profiles/r01v_ncu_raw_pipeline_kernel.csv'),
+                     'exact_reg': (12591616.0, 'profiles/r01p_ncu_raw_pipeline_kernel.csv')}
 
 
 # ------------------------------------------------------------------------------ workload
@@ -54,12 +62,20 @@ COLL_POSE_CORRECTIVE_SCALE = 0.1      # config 4: see synthetic.cached_smplx_lik
 TWO_LOOP = os.environ.get('SFX_TWO_LOOP', 'gram')
 
 
-def bench_cfg(interpenetration=False, vposer=False):
-    """fit_smplx_combined_coco25.yaml (reference cfg_files/) with BASELINE config-2 switches;
-    ``interpenetration`` turns the yaml's own interpenetration settings back on (config 4);
-    ``vposer`` selects the 5-stage fit_smplx_smplifyx.yaml schedule with the VPoser latent pose,
-    zero-latent start, guess_init camera and focal length 5000 (config 3)."""
+def bench_cfg(interpenetration=False, vposer=False, regression_prior=False, two_loop=None):
+    """fit_smplx_combined_coco25.yaml (reference cfg_files/) with BASELINE config-2 switches.
+
+    Default: no regression prior -- pose from the prior's mean
+    (fit_single_frame.py:250-252; the zero pose for the L2 prior, see oracle/fit_port.py), camera
+    depth from guess_init (:404-411).  ``regression_prior`` restores the yaml's "combined"
+    regression + camera prior (config 5's per-frame setup); ``interpenetration`` turns the
+    yaml's interpenetration settings back on (config 4, with the regression prior as the yaml
+    has it); ``vposer`` selects the 5-stage fit_smplx_smplifyx.yaml schedule with the VPoser
+    latent pose, zero-latent start, guess_init camera and focal length 5000 (config 3)."""
     cfg = _bench_cfg()
+    cfg['two_loop'] = two_loop or TWO_LOOP
+    if not (regression_prior or interpenetration):
+        cfg.update(regression_prior=None, use_camera_prior=False)
     if vposer:
         cfg.update(
             use_vposer=True, regression_prior=None, use_camera_prior=False,
@@ -239,17 +255,23 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------------------ reference arm
 def oracle_objects(cfg):
+    """-> (restated smplx body model, base joint weights, restated VPoser or None)."""
     import torch
     from oracle import smplx_shim
     from smplifyx_b200 import synthetic, utils as U
     jm = U.smpl_to_annotation('smplx', use_hands=True, use_face=True, use_face_contour=True,
                               format='coco25')
-    bm = smplx_shim.create(model_data=synthetic.cached_smplx_like(0),
+    scale = COLL_POSE_CORRECTIVE_SCALE if cfg.get('interpenetration') else 1.0
+    bm = smplx_shim.create(model_data=synthetic.cached_smplx_like(0, scale),
                            joint_mapper=U.JointMapper(jm.astype(np.int64)), dtype=torch.float32,
-                           **MODEL_KW)
+                           create_body_pose=not cfg.get('use_vposer', False), **MODEL_KW)
     jw = np.ones(len(jm))
     jw[cfg['joints_to_ign']] = 0
-    return bm, jw
+    vp = None
+    if cfg.get('use_vposer', False):
+        from oracle import vposer_shim
+        vp = vposer_shim.from_weights(synthetic.make_vposer_like(seed=2), dtype=torch.float32)
+    return bm, jw, vp
 
 
 def oracle_joints(bm, gt):
@@ -260,23 +282,35 @@ def oracle_joints(bm, gt):
     return out.joints.numpy().astype(np.float64)
 
 
-def time_oracle_frames(cfg, kp, expose, pixie, frames, threads):
-    """Fits ``frames`` sequentially with the oracle port; returns seconds per frame list."""
+def _fit_one(W, b, want_result):
+    import torch
+    from oracle import fit_port as FP
+    ex = None if W['expose'] is None else W['expose'][b]
+    px = None if W['pixie'] is None else W['pixie'][b]
+    t0 = time.perf_counter()
+    r = FP.fit_frame(W['bm'], W['kp'][b], H_IMG, W_IMG, W['cfg'], W['jw'], expose=ex, pixie=px,
+                     vposer=W['vp'], dtype=torch.float32, return_verts=True)
+    dt = time.perf_counter() - t0
+    out = {'secs': dt, 'evals': int(r['n_evals'])}
+    if want_result:
+        out.update(loss=float(r['loss']), vertices=np.asarray(r['vertices'], np.float32)[0],
+                   joints=np.asarray(r['joints'], np.float32)[0],
+                   cam_t=np.asarray(r['result']['camera_translation'], np.float32).reshape(3),
+                   center=np.asarray(r['result']['camera_center'], np.float32).reshape(2),
+                   n_orient=int(r['n_orient']))
+    return out
+
+
+def time_oracle_frames(cfg, kp, expose, pixie, frames, threads, want_result=False):
+    """Fits ``frames`` sequentially with the oracle port; returns one dict per frame."""
     import torch
     import warnings
-    from oracle import fit_port as FP
     torch.set_num_threads(threads)
-    bm, jw = oracle_objects(cfg)
-    secs, evals = [], []
+    bm, jw, vp = oracle_objects(cfg)
+    W = dict(cfg=cfg, kp=kp, expose=expose, pixie=pixie, bm=bm, jw=jw, vp=vp)
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        for b in frames:
-            t0 = time.perf_counter()
-            r = FP.fit_frame(bm, kp[b], H_IMG, W_IMG, cfg, jw, expose=expose[b], pixie=pixie[b],
-                             dtype=torch.float32, return_verts=True)
-            secs.append(time.perf_counter() - t0)
-            evals.append(r['n_evals'])
-    return secs, evals
+        return [_fit_one(W, b, want_result) for b in frames]
 
 
 # The reference fits one frame at a time (fit_single_frame.py:119 asserts batch_size == 1) and its
@@ -291,8 +325,8 @@ def _oracle_worker_init(cfg, kp, expose, pixie):
     import torch
     torch.set_num_threads(1)
     warnings.simplefilter('ignore')
-    bm, jw = oracle_objects(cfg)
-    _W.update(cfg=cfg, kp=kp, expose=expose, pixie=pixie, bm=bm, jw=jw)
+    bm, jw, vp = oracle_objects(cfg)
+    _W.update(cfg=cfg, kp=kp, expose=expose, pixie=pixie, bm=bm, jw=jw, vp=vp)
 
 
 def _oracle_worker_ready(_):
@@ -300,14 +334,9 @@ def _oracle_worker_ready(_):
     return os.getpid()
 
 
-def _oracle_worker_fit(b):
-    import torch
-    from oracle import fit_port as FP
-    t0 = time.perf_counter()
-    r = FP.fit_frame(_W['bm'], _W['kp'][b], H_IMG, W_IMG, _W['cfg'], _W['jw'],
-                     expose=_W['expose'][b], pixie=_W['pixie'][b], dtype=torch.float32,
-                     return_verts=True)
-    return time.perf_counter() - t0, r['n_evals']
+def _oracle_worker_fit(task):
+    b, want_result = task
+    return _fit_one(_W, b, want_result)
 
 
 class OraclePool(object):
@@ -322,10 +351,10 @@ class OraclePool(object):
                              initargs=(cfg, kp, expose, pixie))
         self.pool.map(_oracle_worker_ready, range(4 * procs), chunksize=1)
 
-    def round(self, frames):
-        """Fits ``frames`` (one task each) -> (wall seconds, [(seconds, evals) per frame])."""
+    def round(self, frames, want_result=False):
+        """Fits ``frames`` (one task each) -> (wall seconds, [dict per frame])."""
         t0 = time.perf_counter()
-        res = self.pool.map(_oracle_worker_fit, list(frames), chunksize=1)
+        res = self.pool.map(_oracle_worker_fit, [(b, want_result) for b in frames], chunksize=1)
         return time.perf_counter() - t0, res
 
     def close(self):
@@ -333,40 +362,87 @@ class OraclePool(object):
         self.pool.join()
 
 
+def oracle_coll_eval_seconds(cfg, kp, expose, pixie, n_evals=3):
+    """config 4's CPU leg: the interpenetration term's restated search is seconds per evaluation
+    in numpy, a full fit hours; so a bounded sample times single closure evaluations (forward,
+    loss with the term on, backward) of frame 0 and the caller scales by the evaluation counts.
+    -> (seconds per evaluation with the term on, seconds per evaluation with it off)."""
+    import torch
+    import warnings
+    from oracle import fit_port as FP
+    from smplifyx_b200 import synthetic
+    torch.set_num_threads(1)
+    bm, jw, vp = oracle_objects(cfg)
+    md = synthetic.cached_smplx_like(0, COLL_POSE_CORRECTIVE_SCALE)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return FP.time_coll_closure(bm, kp[0], H_IMG, W_IMG, cfg, jw, expose[0], pixie[0],
+                                    synthetic.parts_segm_like(md), n_evals=n_evals)
+
+
+def make_inputs_cpu(args, cfg):
+    """Reference arm: keypoints from the oracle's own forward pass."""
+    B = args.frames
+    gt, rng = ground_truth(B, args.seed, 0.2 if cfg.get('interpenetration') else 1.0)
+    bm, _, _ = oracle_objects(cfg)
+    kp, expose, pixie = observations(gt, oracle_joints(bm, gt), rng, cfg.get('focal_length'))
+    if not cfg.get('regression_prior'):
+        expose = pixie = None
+    return kp, expose, pixie
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cfg = bench_cfg()
+    cfg = bench_cfg(args.interpenetration, args.vposer, args.regression_prior)
     B = args.frames
-    gt, rng = ground_truth(B, args.seed)
-    bm, _ = oracle_objects(cfg)
-    kp, expose, pixie = observations(gt, oracle_joints(bm, gt), rng)
+    kp, expose, pixie = make_inputs_cpu(args, cfg)
     procs = os.cpu_count() or 1
     walls, evals = [], []
-    try:
-        pool = OraclePool(cfg, kp, expose, pixie, procs)
-        for step in range(args.warmup + args.steps):
-            frames = [(step * procs + i) % B for i in range(procs)]
-            wall, res = pool.round(frames)
-            if step >= args.warmup:
-                walls.append(wall)
-                evals += [e for _, e in res]
-        pool.close()
-        per_step, how = procs, 'one single-threaded process per host core, each fitting one frame'
-    except Exception as exc:         # no worker processes on this host: one process, all threads
-        frames = [i % B for i in range(args.warmup + args.steps)]
-        secs, ev = time_oracle_frames(cfg, kp, expose, pixie, frames, procs)
-        walls, evals = secs[args.warmup:], ev[args.warmup:]
-        per_step, how = 1, 'fitted sequentially with {} torch threads (worker processes ' \
-                           'unavailable: {})'.format(procs, type(exc).__name__)
-    total = float(np.sum(walls))
-    value = per_step * len(walls) / total
+    if args.interpenetration:
+        # bounded sample: single evaluations, scaled by the reference's own evaluation count of
+        # the same schedule without the term (the engine's count is not available to this arm)
+        t_on, t_off = oracle_coll_eval_seconds(cfg, kp, expose, pixie, n_evals=max(1, args.steps))
+        cfg0 = bench_cfg(False, False, True)
+        r = time_oracle_frames(cfg0, kp, expose, pixie, [0], 1)[0]
+        per_frame = r['evals'] * (t_off + 2.0 / 3.0 * (t_on - t_off))     # term on in 2 of 3 stages
+        value = procs / per_frame
+        total, nsteps = per_frame, 1
+        per_step, how = procs, ('extrapolated: {:.2f} s per evaluation with the interpenetration '
+                                'term on, {:.3f} s without, x {} evaluations of frame 0 (term on in 2 '
+                                'of 3 stages), one single-threaded process per host core assumed'
+                                .format(t_on, t_off, r['evals']))
+        evals = [r['evals']]
+        ms_per_step = 1e3 * per_frame
+    else:
+        try:
+            pool = OraclePool(cfg, kp, expose, pixie, procs)
+            for step in range(args.warmup + args.steps):
+                frames = [(step * procs + i) % B for i in range(procs)]
+                wall, res = pool.round(frames)
+                if step >= args.warmup:
+                    walls.append(wall)
+                    evals += [r['evals'] for r in res]
+            pool.close()
+            per_step, how = procs, 'one single-threaded process per host core, each fitting one frame'
+        except Exception as exc:         # no worker processes on this host: one process, all threads
+            frames = [i % B for i in range(args.warmup + args.steps)]
+            res = time_oracle_frames(cfg, kp, expose, pixie, frames, procs)
+            walls = [r['secs'] for r in res][args.warmup:]
+            evals = [r['evals'] for r in res][args.warmup:]
+            per_step, how = 1, 'fitted sequentially with {} torch threads (worker processes ' \
+                               'unavailable: {})'.format(procs, type(exc).__name__)
+        total = float(np.sum(walls))
+        value = per_step * len(walls) / total
+        ms_per_step = 1e3 * total / len(walls)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(walls),
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': workload_config(B, 1),
+        'data': 'synthetic',
+        'config': workload_config(B, args.gpus, args.interpenetration, args.vposer,
+                                  args.regression_prior),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port',
                          'sample': '{} frame(s) of the batch per step, {} (the reference asserts '
                                    'batch_size == 1); mean evals/frame {:.0f}'.format(
@@ -377,32 +453,81 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(B, n_gpus, interpenetration=False, vposer=False):
+def workload_config(B, n_gpus, interpenetration=False, vposer=False, regression_prior=False):
+    common = {'frames_per_gpu': B, 'global_frames': B * n_gpus,
+              'parallelism': 'frames sharded, dp{}'.format(n_gpus),
+              'l2': 'flushed between timed steps (256 MiB write)',
+              'two_loop': TWO_LOOP + ' (engine option for the L-BFGS direction, value_exact is '
+                          'the other one; the reference arm always runs the reference recursion)'}
     if vposer:
-        return {'workload': 'batch={} synthetic frames per GPU, 135 keypoints, neutral SMPL-X-shaped '
-                            'synthetic model, VPoser latent pose prior (synthetic VPoser v1 weights), '
-                            '5-stage fit_smplx_smplifyx schedule, lbfgsls, guess_init camera, focal '
-                            '5000, interpenetration off (BASELINE config 3)'.format(B),
-                'frames_per_gpu': B, 'global_frames': B * n_gpus,
-                'parallelism': 'frames sharded, dp{}'.format(n_gpus),
-                'l2': 'flushed between timed steps (256 MiB write)',
-                'two_loop': TWO_LOOP + ' (engine option for the L-BFGS direction; the reference '
-                            'arm always runs the reference recursion)'}
-    return {'workload': 'batch={} synthetic frames per GPU, 135 keypoints (127 model joints + 17 '
-                        'face-contour), neutral SMPL-X-shaped synthetic model, GMoF + L2 priors, '
-                        '3-stage fit_smplx_combined_coco25 schedule, lbfgsls, combined regression '
-                        '+ camera prior, interpenetration {}'.format(
-                            B, 'ON (coll_loss_weights 0 / 0.1 / 1.0, df_cone_height 1e-4, part '
-                            'filter; BASELINE config 4)' if interpenetration else 'off'),
-            'frames_per_gpu': B, 'global_frames': B * n_gpus,
-            'parallelism': 'frames sharded, dp{}'.format(n_gpus),
-            'l2': 'flushed between timed steps (256 MiB write)',
-            'two_loop': TWO_LOOP + ' (engine option for the L-BFGS direction; the reference arm '
-                        'always runs the reference recursion)'}
+        w = ('batch={} synthetic frames per GPU, 135 keypoints, neutral SMPL-X-shaped synthetic '
+             'model, VPoser latent pose prior (synthetic VPoser v1 weights), 5-stage '
+             'fit_smplx_smplifyx schedule, lbfgsls, guess_init camera, focal 5000, interpenetration '
+             'off (BASELINE config 3)'.format(B))
+    else:
+        init = ('combined regression + camera prior (config 5 per-frame setup)'
+                if (regression_prior or interpenetration) else
+                'no regression prior: zero (prior-mean) start pose, guess_init camera (BASELINE '
+                'config 2 as SURVEY 8d specifies it)')
+        w = ('batch={} synthetic frames per GPU, 135 keypoints (127 model joints + 17 face-contour), '
+             'neutral SMPL-X-shaped synthetic model, GMoF + L2 priors, 3-stage '
+             'fit_smplx_combined_coco25 schedule, lbfgsls, {}, interpenetration {}'.format(
+                 B, init, 'ON (coll_loss_weights 0 / 0.1 / 1.0, df_cone_height 1e-4, part filter; '
+                 'BASELINE config 4)' if interpenetration else 'off'))
+    common['workload'] = w
+    return common
+
+
+# ------------------------------------------------------------------------------ parity
+def project_np(joints, cam_t, center, focal):
+    p = joints + cam_t[None]
+    return focal * p[:, :2] / p[:, 2:3] + center[None]
+
+
+def parity_block(out, oracle_res, sample, kp, focal):
+    """Engine fit (``out``: fit_frames result) against the CPU leg's fit of the same frames."""
+    loss_rel, v_mean, v_max, px_mean, px_max, ev_e, ev_o = [], [], [], [], [], [], []
+    for b, r in zip(sample, oracle_res):
+        loss_rel.append(abs(float(out.loss[b]) - r['loss']) / max(abs(r['loss']), 1.0))
+        d = np.sqrt(((out.vertices[b].astype(np.float64) - r['vertices']) ** 2).sum(-1))
+        v_mean.append(float(d.mean()))
+        v_max.append(float(d.max()))
+        res = out.results[b]
+        pe = project_np(out.joints[b].astype(np.float64),
+                        res['camera_translation'].reshape(3).astype(np.float64),
+                        res['camera_center'].reshape(2).astype(np.float64), focal)
+        po = project_np(r['joints'].astype(np.float64), r['cam_t'].astype(np.float64),
+                        r['center'].astype(np.float64), focal)
+        live = kp[b, :, 2] > 0
+        dpx = np.sqrt(((pe - po) ** 2).sum(-1))[live]
+        px_mean.append(float(dpx.mean()))
+        px_max.append(float(dpx.max()))
+        ev_e.append(int(out.n_evals[b]))
+        ev_o.append(int(r['evals']))
+    return {'frames': len(sample),
+            'final_loss_rel_median': float(np.median(loss_rel)),
+            'final_loss_rel_max': float(np.max(loss_rel)),
+            'vertex_err_mean_m': float(np.mean(v_mean)), 'vertex_err_max_m': float(np.max(v_max)),
+            'vertex_err_mean_m_median_frame': float(np.median(v_mean)),
+            'reproj_px_mean': float(np.mean(px_mean)), 'reproj_px_max': float(np.max(px_max)),
+            'evals_engine': float(np.mean(ev_e)), 'evals_oracle': float(np.mean(ev_o)),
+            'note': 'engine (two_loop {}) vs the oracle port of the reference on the same frames '
+                    'of this batch; vertices in model space (last orientation, as vertices.ply), '
+                    'reprojection over the detected keypoints; float32 fits are chaotic -- the '
+                    'reference-vs-reference envelope on these frames is in '
+                    'tests/golden/bench_parity.npz (tests/test_gpu_bench_parity.py)'.format(TWO_LOOP)}
 
 
 # ------------------------------------------------------------------------------ B200 arm
+# floating-point operations of one closure evaluation besides the blend rows (pose prologue,
+# kinematic chain, skinning of <= 225 support vertices, projection, loss, their adjoints):
+# counted from the loops of csrc/sfx_core.cuh eval_frame -- see DESIGN.md section 4
+EVAL_FIXED_FLOPS = 2.3e5
+FP32_SIMT_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # FMA lanes x 2 x boost clock
+
+
 def run_b200(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from smplifyx_b200 import engine, fit_frames as FF, synthetic, utils as U, _native as N
@@ -414,7 +539,7 @@ def run_b200(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    cfg = bench_cfg(args.interpenetration, args.vposer)
+    cfg = bench_cfg(args.interpenetration, args.vposer, args.regression_prior)
     md = synthetic.cached_smplx_like(
         0, COLL_POSE_CORRECTIVE_SCALE if args.interpenetration else 1.0)
     part_segm = synthetic.parts_segm_like(md) if args.interpenetration else None
@@ -449,50 +574,69 @@ def run_b200(args):
         gbatch.close()
     kp, expose, pixie = observations(gt, j3.cpu().numpy().astype(np.float64), rng,
                                      cfg.get('focal_length'))
-
-    if args.vposer:
+    if not cfg.get('regression_prior'):
         expose = pixie = None
-    plan = FF.FitPlan(L, K, kp, H_IMG, W_IMG, cfg, expose, pixie, None, np.float32,
-                      part_segm=part_segm, vposer=vp)
-    FF.upload(batch, plan)
-    x0_dev = batch.params_tensor().clone()
+    focal = float(cfg.get('focal_length') or np.sqrt(H_IMG ** 2 + W_IMG ** 2))
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gathered = torch.empty((world * B, L.np), dtype=torch.float32, device=dev) if world > 1 else None
-
-    def resident_step():
-        batch.params_tensor().copy_(x0_dev)
-        _, verts, joints, launches = FF.run(batch, plan, return_verts=True)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, batch.params_tensor())
-        return launches
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        resident_step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    launches = 0
-    barrier()
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)
-        ev[i][0].record()
-        launches += resident_step()
-        ev[i][1].record()
-    barrier()
-    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
-    total_ms = float(step_ms.sum())
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    def reduce_max(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        return float(t.item())
+
+    # ---- device-timed steps, inputs resident: default two-loop mode first, then the other ----
+    other = {'gram': 'exact', 'exact': 'gram'}[TWO_LOOP]
+    modes = [TWO_LOOP] if (args.interpenetration or args.single_mode) else [TWO_LOOP, other]
+    sampler = ClockSampler(local)
+    timed, plans = {}, {}
+    launches = 0
+    for mi, mode in enumerate(modes):
+        mcfg = dict(cfg, two_loop=mode)
+        plan = FF.FitPlan(L, K, kp, H_IMG, W_IMG, mcfg, expose, pixie, None, np.float32,
+                          part_segm=part_segm, vposer=vp)
+        FF.upload(batch, plan)
+        plans[mode] = plan
+        x0_dev = batch.params_tensor().clone()
+
+        def resident_step():
+            batch.params_tensor().copy_(x0_dev)
+            _, verts, joints, n = FF.run(batch, plan, return_verts=True)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, batch.params_tensor())
+            return n
+
+        for _ in range(args.warmup):
+            resident_step()
+        barrier()
+        if rank == 0 and mi == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(args.steps)]
+        barrier()
+        for i in range(args.steps):
+            flush.fill_(i & 0xff)
+            ev[i][0].record()
+            n = resident_step()
+            ev[i][1].record()
+            if mi == 0:
+                launches += n
+        barrier()
+        timed[mode] = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+    total_ms_rank = timed[TWO_LOOP]
+    total_ms = reduce_max(total_ms_rank)
+    total_ms_other = reduce_max(timed[other]) if other in timed else None
+    plan = plans[TWO_LOOP]
+    FF.upload(batch, plan)
+    x0_dev = batch.params_tensor().clone()
 
     # ---- end to end through the public call with host buffers --------------------------------
     e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -512,11 +656,7 @@ def run_b200(args):
         e2e_ev[i][1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms = float(np.sum([a.elapsed_time(b) for a, b in e2e_ev]))
-    if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = reduce_max(float(np.sum([a.elapsed_time(b) for a, b in e2e_ev])))
 
     # ---- roofline accounting for the dominant kernel (one untimed replay with counters) ------
     batch.params_tensor().copy_(x0_dev)
@@ -530,7 +670,8 @@ def run_b200(args):
     kern_ms = a.elapsed_time(b_)
     passes = batch.passes().cpu().numpy().astype(np.int64)
     evals = batch.evals().cpu().numpy().astype(np.int64)
-    alg_bytes = float(passes.sum()) * ROW_BYTES        # rows of the blend matrix streamed x 2 KiB
+    row_bytes = float(passes.sum()) * ROW_BYTES        # rows of the blend matrix streamed x 2 KiB
+    flops = float(passes.sum()) * 2 * 512 + float(evals.sum()) * EVAL_FIXED_FLOPS
     evals_per_frame = float(evals.mean())
     peaks = {}
     try:
@@ -538,28 +679,61 @@ def run_b200(args):
             peaks = json.load(f)
     except Exception:
         pass
-    peak = float(peaks.get('hbm_gbs', 6650.0))
-    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'fit_pipeline_kernel<float>', 'achieved': achieved,
-                'peak': peak, 'peak_source': 'measured' if peaks else 'fallback',
-                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                'launches': 1, 'kernel_ms_per_step': kern_ms,
-                'algorithmic_bytes_per_step': alg_bytes,
-                'evals_max_frame': int(evals.max()), 'evals_min_frame': int(evals.min()),
-                'note': 'algorithmic bytes = rows of the blend matrix streamed (forward + adjoint '
-                        'pass of every closure evaluation, only the support rows a live keypoint '
-                        'depends on: at most 675) x 2 KiB; the rows are shared by all frames and '
-                        'served from L2 after first touch, so the kernel is bound by the L2->SM '
-                        'path and by per-frame serial latency, not by HBM'}
-    if args.traffic is not None:
-        roofline['traffic'] = args.traffic
-    elif B == 128 and not args.interpenetration and not args.vposer:
-        roofline['traffic'], roofline['traffic_source'] = NCU_TRAFFIC_BYTES[TWO_LOOP]
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    tf_peak = float(peaks.get('bf16_tflops_sustained', 1400.0))
+    l2_gbs = C.c_double(0.0)
+    N.check(batch.lib, batch.lib.sfx_diag_l2_read_gbs(48 << 20, 20, C.byref(l2_gbs)))
+    traffic = args.traffic
+    traffic_src = 'command line' if traffic is not None else None
+    if traffic is None and B == 128 and not (args.interpenetration or args.vposer):
+        key = TWO_LOOP + ('_reg' if args.regression_prior else '')
+        if key in NCU_TRAFFIC_BYTES:
+            traffic, traffic_src = NCU_TRAFFIC_BYTES[key]
+    sec = kern_ms * 1e-3
+    achieved_tf = flops / sec / 1e12
+    roofline = {
+        'bound': 'latency', 'kernel': 'fit_pipeline_kernel<float>',
+        'achieved': achieved_tf, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': achieved_tf / tf_peak,
+        'peak_source': ('MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else
+                        'fallback (B200_PROFILING.md)'),
+        'traffic': traffic, 'traffic_source': traffic_src,
+        'launches': 1, 'kernel_ms_per_step': kern_ms, 'executed_flops_per_step': flops,
+        'frac_of_fp32_simt_peak': achieved_tf / FP32_SIMT_PEAK_TFLOPS,
+        'hbm': None if traffic is None else {
+            'achieved': traffic / sec / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': traffic / sec / 1e9 / hbm_peak},
+        'l2_to_sm': {'achieved': row_bytes / sec / 1e9, 'peak': float(l2_gbs.value), 'unit': 'GB/s',
+                     'frac': row_bytes / sec / 1e9 / max(float(l2_gbs.value), 1e-9),
+                     'bytes_per_step': row_bytes,
+                     'peak_source': 'sfx_diag_l2_read_gbs, measured in this run (all SMs '
+                                    'sweeping a 48 MiB L2-resident buffer)'},
+        'evals_max_frame': int(evals.max()), 'evals_min_frame': int(evals.min()),
+        'sm_time_busy_frac': float(evals.sum()) / (float(evals.max()) * model_sms(batch)),
+        'note': 'per-frame serial latency bound (DESIGN.md section 4): executed flops = blend '
+                'rows streamed x 1024 + evaluations x {:.0f}; skipped full-mesh work is not '
+                'credited.  The blend rows are shared by all frames and served from L2: '
+                'l2_to_sm is that stream against the measured L2 read peak; hbm is the ncu '
+                'dram traffic of the launch.  sm_time_busy_frac = sum of evaluations / '
+                '(evaluations of the longest frame x SMs): the single-wave tail'.format(
+                    EVAL_FIXED_FLOPS)}
     coll_stats = batch.coll_stats()
     if coll_stats is not None:
         cs = coll_stats.cpu().numpy()
         roofline['collision_candidates_per_frame_median_max'] = [int(np.median(cs[:, 0])), int(cs[:, 0].max())]
         roofline['collision_touched_vertices_median_max'] = [int(np.median(cs[:, 1])), int(cs[:, 1].max())]
+
+    # ---- per-rank evidence of the straggler (N > 1: all ranks) -------------------------------
+    mine = torch.tensor([total_ms_rank / args.steps, kern_ms, float(evals.max()),
+                         float(evals.mean()), float(len(plan.flip_ids))],
+                        dtype=torch.float64, device=dev)
+    if world > 1:
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = [{'rank': i, 'ms_per_step': float(t[0]), 'kernel_ms': float(t[1]),
+                 'evals_max_frame': int(t[2]), 'evals_mean': float(t[3]),
+                 'frames_second_orientation': int(t[4])} for i, t in enumerate(allr)]
 
     value = world * B * args.steps / (total_ms * 1e-3)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
@@ -567,42 +741,65 @@ def run_b200(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(B, world, args.interpenetration, args.vposer),
+        'config': workload_config(B, world, args.interpenetration, args.vposer,
+                                  args.regression_prior),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(out.h2d_bytes),
                 'd2h_bytes_per_step': int(out.d2h_bytes), 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
-        'evals_per_frame': evals_per_frame,
+        'evals_per_frame': evals_per_frame, 'per_rank': per_rank,
         'fit': {'final_loss_median': float(np.median(out.loss)),
                 'frames_with_nan_or_inf': int((out.flags != 0).sum()),
                 'frames_second_orientation': int(len(plan.flip_ids))},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.interpenetration \
-            and not args.vposer:
+    if total_ms_other is not None:
+        line['value_' + other] = world * B * args.steps / (total_ms_other * 1e-3)
+        line['ms_per_step_' + other] = total_ms_other / args.steps
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         procs = os.cpu_count() or 1
-        sample = list(range(min(args.cpu_frames or procs, B)))
-        try:
-            pool = OraclePool(cfg, kp, expose, pixie, min(procs, len(sample)))
-            wall, res = pool.round(sample)
-            pool.close()
+        if args.interpenetration:
+            t_on, t_off = oracle_coll_eval_seconds(cfg, kp, expose, pixie, n_evals=3)
+            per_frame = evals_per_frame * (t_off + 2.0 / 3.0 * (t_on - t_off))
             line['cpu_baseline'] = {
-                'value': len(sample) / wall, 'unit': UNIT, 'cores': pool.procs, 'kind': 'port',
-                'sample': 'frames 0..{} of the same batch fitted by the oracle port of the '
-                          'reference, one single-threaded process per host core ({} processes, one '
-                          'frame each); {:.1f} s wall, mean {:.0f} evals/frame'.format(
-                              len(sample) - 1, pool.procs, wall,
-                              float(np.mean([e for _, e in res])))}
-        except Exception as exc:     # no worker processes on this host: one process, all threads
-            secs, evals = time_oracle_frames(cfg, kp, expose, pixie, sample[:2], procs)
-            line['cpu_baseline'] = {
-                'value': len(secs) / float(np.sum(secs)), 'unit': UNIT, 'cores': procs,
-                'kind': 'port',
-                'sample': 'frames 0..{} fitted sequentially by the oracle port ({} torch threads; '
-                          'worker processes unavailable: {}); {:.1f} s'.format(
-                              len(secs) - 1, procs, type(exc).__name__, float(np.sum(secs)))}
+                'value': procs / per_frame, 'unit': UNIT, 'cores': procs, 'kind': 'port',
+                'sample': 'extrapolated from 3 timed closure evaluations of frame 0 by the oracle '
+                          'port: {:.2f} s per evaluation with the interpenetration term on (restated '
+                          'mesh_intersection search in numpy), {:.3f} s without; x the engine\'s {:.0f} '
+                          'evaluations per frame (term on in 2 of 3 stages); {} single-threaded '
+                          'processes assumed.  A full CPU fit of one frame would take ~{:.0f} min'
+                          .format(t_on, t_off, evals_per_frame, procs, per_frame / 60.0)}
+        else:
+            sample = list(range(min(args.cpu_frames or procs, B)))
+            try:
+                pool = OraclePool(cfg, kp, expose, pixie, min(procs, len(sample)))
+                wall, res = pool.round(sample, want_result=True)
+                pool.close()
+                line['cpu_baseline'] = {
+                    'value': len(sample) / wall, 'unit': UNIT, 'cores': pool.procs, 'kind': 'port',
+                    'sample': 'frames 0..{} of the same batch fitted by the oracle port of the '
+                              'reference, one single-threaded process per host core ({} processes, '
+                              'one frame each); {:.1f} s wall, mean {:.0f} evals/frame'.format(
+                                  len(sample) - 1, pool.procs, wall,
+                                  float(np.mean([r['evals'] for r in res])))}
+            except Exception as exc:   # no worker processes on this host: one process, all threads
+                sample = sample[:2]
+                res = time_oracle_frames(cfg, kp, expose, pixie, sample, procs, want_result=True)
+                secs = [r['secs'] for r in res]
+                line['cpu_baseline'] = {
+                    'value': len(secs) / float(np.sum(secs)), 'unit': UNIT, 'cores': procs,
+                    'kind': 'port',
+                    'sample': 'frames 0..{} fitted sequentially by the oracle port ({} torch '
+                              'threads; worker processes unavailable: {}); {:.1f} s'.format(
+                                  len(secs) - 1, procs, type(exc).__name__, float(np.sum(secs)))}
+            line['parity'] = parity_block(out, res, sample, kp, focal)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def model_sms(batch):
+    import torch
+    return torch.cuda.get_device_properties(batch.model.device).multi_processor_count
 
 
 def main():
@@ -616,16 +813,21 @@ def main():
     ap.add_argument('--cpu-frames', type=int, default=0,
                     help='frames of the CPU baseline sample (default: one per host core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--regression-prior', action='store_true',
+                    help='config 5\'s per-frame setup on the config-2 batch: synthetic "combined" '
+                         'regression prior + camera prior (round 1\'s default line)')
     ap.add_argument('--interpenetration', action='store_true',
-                    help='BASELINE config 4: the same workload with the interpenetration term on '
-                         '(not the default bench line; the CPU baseline is skipped because the '
-                         'restated third-party search takes seconds per evaluation in numpy)')
+                    help='BASELINE config 4: the regression-prior workload with the '
+                         'interpenetration term on (not the default bench line; the CPU baseline '
+                         'is extrapolated from timed single evaluations)')
     ap.add_argument('--vposer', action='store_true',
                     help='BASELINE config 3: 5-stage schedule with the VPoser latent pose prior '
                          '(not the default bench line)')
     ap.add_argument('--two-loop', default=None, choices=['exact', 'gram'],
-                    help="L-BFGS direction: 'gram' (default; coefficient-space recursion) or "
-                         "'exact' (the reference's operation order)")
+                    help="L-BFGS direction of `value`: 'gram' (default; coefficient-space "
+                         "recursion) or 'exact' (the reference's operation order); the other "
+                         "one is reported as value_<mode>")
+    ap.add_argument('--single-mode', action='store_true', help='time only the default two-loop mode')
     ap.add_argument('--traffic', type=float, default=None,
                     help='dram bytes per launch from an ncu capture (profiles/), recorded as-is')
     args = ap.parse_args()

@@ -197,6 +197,12 @@ int sfx_aligned_errors(const void* est_dev, const void* gt_dev, const int32_t* i
                        int32_t N, int32_t n, int32_t mode, int32_t hip0, int32_t hip1,
                        int32_t use_double, void* err_dev, void* transform_dev, void* stream);
 
+/* Diagnostic, no counterpart in the reference: measured L2 -> SM read bandwidth (GB/s) of the
+ * current device -- every SM sweeping one L2-resident buffer of buffer_bytes, iters times.  The
+ * benchmark reports the fit kernel's blend-row traffic (rows shared by all frames, served from
+ * L2) against this figure.  Synchronous. */
+int sfx_diag_l2_read_gbs(int64_t buffer_bytes, int32_t iters, double* gbs_out);
+
 const char* sfx_last_error(void);
 int sfx_version(void);
 

@@ -441,6 +441,7 @@ class FrameProblem(object):
 
     def forward(self, params, emb, return_verts=False):
         kw = {k: v for k, v in params.items() if k != 'body_pose'}
+        return_verts = return_verts or getattr(self, 'coll', None) is not None
         return self.bm(body_pose=self.body_pose_from(emb), return_verts=return_verts,
                        return_full_pose=True, **kw)
 
@@ -550,6 +551,17 @@ class FrameProblem(object):
         expr = torch.sum(torch.sum(out.expression.pow(2))) * w['expr_prior_weight'] ** 2
         jaw = torch.sum(torch.sum(out.jaw_pose.mul(w['jaw_prior_weight']).pow(2)))
         pen = 0.0
+        coll = getattr(self, 'coll', None)
+        if coll is not None and float(w.get('coll_loss_weight', 0.0)) > 0:
+            # fitting.py:437-455: search (no gradient), part filter, conic penalty
+            search_tree, pen_distance, filter_faces, faces = coll
+            tri = torch.index_select(out.vertices, 1, faces).view(1, -1, 3, 3)
+            with torch.no_grad():
+                idxs = search_tree(tri)
+            if filter_faces is not None:
+                idxs = filter_faces(idxs)
+            if idxs.ge(0).sum().item() > 0:
+                pen = torch.sum(w['coll_loss_weight'] * pen_distance(tri, idxs))
         return (joint_loss + pprior + shape_loss + angle_loss + pen + jaw + expr + lh + rh)
 
 
@@ -656,8 +668,16 @@ def fit_frame(body_model, keypoints, H, W, cfg, joint_weights, expose=None, pixi
         else:
             prob.pose_embedding = torch.zeros([1, 32], dtype=dtype)
     else:
-        prob.pose_embedding = (full_prior.clone() if regression_prior
-                               else body_prior.get_mean().detach().clone().to(dtype))
+        # body_pose_prior.get_mean() (fit_single_frame.py:250-252).  Only MaxMixturePrior has one
+        # (prior.py:176-179): with body_prior_type 'l2' the reference raises AttributeError at this
+        # line, so an un-initialised L2 fit cannot run there at all.  The port (and the engine,
+        # fit_frames.FitPlan) start such a fit from the L2 prior's own mean, the zero pose.
+        if regression_prior:
+            prob.pose_embedding = full_prior.clone()
+        elif hasattr(body_prior, 'get_mean'):
+            prob.pose_embedding = body_prior.get_mean().detach().clone().to(dtype)
+        else:
+            prob.pose_embedding = torch.zeros([1, 63], dtype=dtype)
     if regression_prior:
         prob.reset_params(global_orient=global_pose, body_pose=prob.pose_embedding)
     else:
@@ -759,3 +779,65 @@ def fit_frame(body_model, keypoints, H, W, cfg, joint_weights, expose=None, pixi
                 vertices=None if out.vertices is None else out.vertices.numpy().copy(),
                 joints=out.joints.numpy().copy(), n_evals=prob.n_evals, evals_cam=evals_cam,
                 cam_loss=cam_loss, n_orient=len(orients))
+
+
+def time_coll_closure(body_model, keypoints, H, W, cfg, joint_weights, expose, pixie, part_segm,
+                      n_evals=3):
+    """Bounded CPU sample for the interpenetration workload (bench.py): seconds per closure
+    evaluation (forward + SMPLifyLoss + backward, fitting.py:232-273) of one frame at its
+    regression-prior start, second annealing stage, with the interpenetration term
+    (fitting.py:437-455 driving oracle/isect_port.py) on and off."""
+    import time
+    from oracle import isect_port as IP
+    dtype = torch.float32
+    focal = cfg.get('focal_length') or (W ** 2 + H ** 2) ** 0.5
+    prob = FrameProblem(body_model, keypoints, H, W, focal, joint_weights, dtype=dtype,
+                        rho=cfg.get('rho', 100), body_prior=l2_body_prior,
+                        confidence_threshold=cfg.get('confidence_threshold', 0))
+
+    def eul(mats):
+        return [euler_xyz_from_matrix(torch.tensor(np.asarray(m))) for m in mats]
+    full = torch.cat(eul(expose['body_pose'])[:19] + eul(pixie['body_pose'])[19:]).reshape(1, -1)
+    prob.pose_embedding = full.to(dtype)
+    prob.reset_params(global_orient=eul([expose['global_orient']])[0], body_pose=prob.pose_embedding)
+    tr = np.array(expose['transl'], dtype=np.float64).copy()
+    tr[-1] /= (5000 / focal)
+    prob.cam_t = torch.tensor(tr, dtype=dtype).reshape(1, 3)
+    prob.center = torch.tensor([[float(v) for v in expose['center']]], dtype=dtype)
+    si = 1
+    w = dict(body_pose_weight=cfg['body_pose_prior_weights'][si], shape_weight=cfg['shape_weights'][si],
+             expr_prior_weight=cfg['expr_weights'][si],
+             hand_prior_weight=cfg['hand_pose_prior_weights'][si],
+             jaw_prior_weight=[float(v) for v in cfg['jaw_pose_prior_weights'][si].split(',')],
+             data_weight=1000.0 / H)
+    w = {k: torch.tensor(v, dtype=dtype) for k, v in w.items()}
+    w['bending_prior_weight'] = 3.17 * w['body_pose_weight']
+    prob.jw[:, 25:67] = cfg['hand_joints_weights'][si]
+    prob.jw[:, 67:] = cfg['face_joints_weights'][si]
+    prob.jw[:, prob.low_conf] = 0
+    jw = prob.jw.clone()
+    names = [n for n in prob.P] + ['pose_embedding']
+    reg = prob.pose_embedding.clone()
+    out = []
+    for on in (True, False):
+        if on:
+            prob.coll = (IP.BVH(max_collisions=cfg.get('max_collisions', 128)),
+                         IP.DistanceFieldPenetrationLoss(
+                             sigma=cfg.get('df_cone_height', 1e-4), point2plane=False,
+                             vectorized=True, penalize_outside=True),
+                         IP.FilterFaces(faces_segm=part_segm['segm'],
+                                        faces_parents=part_segm['parents'],
+                                        ign_part_pairs=cfg.get('ign_part_pairs')),
+                         body_model.faces_tensor.view(-1))
+            w['coll_loss_weight'] = torch.tensor(cfg['coll_loss_weights'][si], dtype=dtype)
+        else:
+            prob.coll = None
+            w['coll_loss_weight'] = torch.tensor(0.0, dtype=dtype)
+        x, closure, _ = prob.make_closure(
+            names, lambda p, e, t: prob.smplify_loss(p, e, t, w, jw, si, 3, reg))
+        closure()                                    # warm-up
+        t0 = time.perf_counter()
+        for _ in range(n_evals if on else 10 * n_evals):
+            closure()
+        out.append((time.perf_counter() - t0) / (n_evals if on else 10 * n_evals))
+    return out[0], out[1]

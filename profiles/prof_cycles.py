@@ -17,7 +17,8 @@ N.LIB_PATH = os.path.join(os.path.dirname(N.LIB_PATH), 'libsfx_prof.so')
 import bench
 from smplifyx_b200 import engine, fit_frames as FF, synthetic, utils as U
 COLL = '--interpenetration' in sys.argv
-cfg = bench.bench_cfg(COLL); B = 128
+REG = '--regression-prior' in sys.argv
+cfg = bench.bench_cfg(COLL, False, REG); B = 128
 jm = U.smpl_to_annotation('smplx', True, True, True, 'coco25')
 md = synthetic.cached_smplx_like(0, bench.COLL_POSE_CORRECTIVE_SCALE if COLL else 1.0)
 model = engine.Model(md, jm, dtype=torch.float32, **bench.MODEL_KW)
@@ -30,6 +31,7 @@ batch.set_targets(np.zeros((B,135,3)), np.zeros((B,135)), np.zeros((B,135),np.ui
 batch.set_params(xg)
 _,_,j3 = batch.eval(cam_st, want_joints=True)
 kp, ex, px = bench.observations(gt, j3.cpu().numpy().astype(np.float64), rng)
+if not cfg.get('regression_prior'): ex = px = None
 part_segm = synthetic.parts_segm_like(md) if COLL else None
 plan = FF.FitPlan(L, 135, kp, 600, 800, cfg, ex, px, None, np.float32, part_segm=part_segm)
 FF.upload(batch, plan)
@@ -48,6 +50,8 @@ for name, k in (('eval',0),('two_loop',1),('blend_fwd',2),('blend_adj',3),('chai
                 ('coll_skin|prologue',8),('coll_boxes|skin+proj+adj',9),('coll_narrow|eval_tail',10),('coll_vgather|gram_dots',11),('coll_skin_adj|gram_chain',12),('coll_walk_t0|gram_combine',13),('coll_pairs_t0',14)):
     print('%-10s slowest: %5.1f%%   all frames: %5.1f%%   per eval (slowest) %.1f us' % (name, 100*prof[i,k]/tot[i], 100*prof[:,k].sum()/tot.sum(), prof[i,k]/ev[i]/1965.))
 print('mean frame total ms', tot.mean()/1.965e6, 'median evals', np.median(ev))
+print('evals sorted', np.sort(ev)[::-1][:24], 'flip frames', len(plan.flip_ids), 'their evals', ev[plan.flip_ids])
+print('frame ms sorted', np.round(np.sort(tot)[::-1][:24]/1.965e6, 1))
 
 cs = batch.coll_stats()
 if cs is not None:

@@ -421,6 +421,29 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
     }
 }
 
+// ---- diagnostics: L2 -> SM read bandwidth of this device ------------------------------------
+// Every block sweeps the same L2-resident buffer with 16-byte loads that bypass L1 (ld.global.cg);
+// bench.py reports the blend-row traffic of the fit kernel against this measured figure.
+__global__ void __launch_bounds__(512)
+l2_read_kernel(const uint4* __restrict__ buf, size_t n16, int iters, unsigned int* sink) {
+    unsigned int acc = 0;
+    const size_t start = ((size_t)blockIdx.x * 7919u * blockDim.x) % n16;     // blocks start apart
+    for (int it = 0; it < iters; ++it)
+        for (size_t i0 = threadIdx.x; i0 < n16; i0 += (size_t)blockDim.x * 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                size_t i = start + i0 + (size_t)u * blockDim.x;
+                if (i >= n16) i -= n16;
+                if (i >= n16) i -= n16;
+                v[u] = __ldcg(buf + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+        }
+    if (acc == 0x9e3779b9u) *sink = acc;         // keeps the loads alive
+}
+
 // ------------------------------------------------------------------------------ handles
 struct DevBuf {
     void* p = nullptr;
@@ -984,6 +1007,33 @@ int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order
 }
 
 void* sfx_batch_cam_loss_dev(sfx_batch* b) { return b ? b->cam_loss.p : nullptr; }
+int sfx_diag_l2_read_gbs(int64_t buffer_bytes, int32_t iters, double* gbs_out) {
+    if (!gbs_out || buffer_bytes < (1 << 20) || iters < 1) return fail(SFX_ERR_ARG, "bad argument");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DevBuf buf, sink;
+    CUDA_TRY(buf.alloc((size_t)buffer_bytes));
+    CUDA_TRY(sink.alloc(64));
+    CUDA_TRY(cudaMemset(buf.p, 1, (size_t)buffer_bytes));
+    const size_t n16 = (size_t)buffer_bytes / 16;
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    l2_read_kernel<<<sms, 512>>>((const uint4*)buf.p, n16, 1, (unsigned int*)sink.p);   // warm L2
+    CUDA_TRY(cudaEventRecord(a));
+    l2_read_kernel<<<sms, 512>>>((const uint4*)buf.p, n16, iters, (unsigned int*)sink.p);
+    CUDA_TRY(cudaEventRecord(b));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    CUDA_TRY(cudaGetLastError());
+    *gbs_out = (double)sms * (double)n16 * 16.0 * iters / (ms * 1e-3) / 1e9;
+    return SFX_OK;
+}
+
 long long* sfx_batch_prof_dev(sfx_batch* b) { return b ? (long long*)b->prof.p : nullptr; }
 
 static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev, void* stream);
