@@ -165,9 +165,10 @@ void* sfx_batch_final_loss_dev(sfx_batch* b);
 int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order_dev,
                      const uint8_t* flip_dev, void* stream);
 void* sfx_batch_cam_loss_dev(sfx_batch* b);
-/* [B][16] int64 cycle counters per frame (all zero unless the library was built with
+/* [B][64] int64 cycle counters per frame (all zero unless the library was built with
  * -DSFX_CYCLE_PROF): 0 evaluations, 1 two-loop recursion, 2 blend forward, 3 blend adjoint,
- * 4 whole frame, 8..12 phases of the interpenetration term. */
+ * 4 whole frame, 8..12 phases of the interpenetration term; 16..63 lap timers of the phases of an
+ * evaluation and of the line search (profiles/prof_cycles.py names them). */
 long long* sfx_batch_prof_dev(sfx_batch* b);
 /* body_model(return_verts=True) at the LAST fitted orientation of every frame -- the mesh the
  * reference writes to vertices.ply (fit_single_frame.py:611, :671-676). */

@@ -41,7 +41,8 @@ for it in range(2):
     FF.run(batch, plan, True); torch.cuda.synchronize()
 lib = batch.lib; lib.sfx_batch_prof_dev.restype = C.c_void_p; lib.sfx_batch_prof_dev.argtypes=[C.c_void_p]
 ptr = lib.sfx_batch_prof_dev(batch.h)
-prof = engine._wrap(ptr, (B*32,), torch.int32, model.device, batch).cpu().numpy().view(np.int64).reshape(B,16)
+prof = engine._wrap(ptr, (B*128,), torch.int32, model.device, batch).cpu().numpy().view(np.int64).reshape(B,64)
+laps = prof[:, 16:]
 ev = batch.evals().cpu().numpy()
 tot = prof[:,4].astype(float)
 i = np.argmax(tot)
@@ -52,6 +53,18 @@ for name, k in (('eval',0),('two_loop',1),('blend_fwd',2),('blend_adj',3),('chai
 print('mean frame total ms', tot.mean()/1.965e6, 'median evals', np.median(ev))
 print('evals sorted', np.sort(ev)[::-1][:24], 'flip frames', len(plan.flip_ids), 'their evals', ev[plan.flip_ids])
 print('frame ms sorted', np.round(np.sort(tot)[::-1][:24]/1.965e6, 1))
+
+LAPS = ['LS logic -> eval entry (scatter)', 'prologue: pose vector, hand PCA, shape', 'prologue: rodrigues, rest joints, yaw row',
+        'prologue: blend coefficients, rel (+contour tables)', 'blend forward || chain', 'skinning of support slots', 'extra joints + landmarks',
+        'projection + data term', 'nine sums (multi_sum)', 'dX (keypoints -> joints)', 'dvert', 'dvp + dA', 'blend adjoint || chain adjoint',
+        'rodrigues adjoint, rest-joint adjoint', 'shape gradient partials', 'priors, gradient vector, loss', '', '', '', '',
+        'line-search logic between probes', 'gather_grad after eval', 'probe: copy + g.d', 'end-of-iteration tests', 'history update (y, s, ys, yy)',
+        'two-loop recursion', 'step length, gtd, copies', 'line-search epilogue']
+print('lap timers, slowest frame (us per evaluation) | all frames (share of frame time)')
+for k, name in enumerate(LAPS):
+    if name:
+        print('  %2d %-52s %6.2f us   %5.1f%%' % (k, name, laps[i, k] / ev[i] / 1965., 100 * laps[:, k].sum() / tot.sum()))
+print('  laps total %.1f us per evaluation (frame total %.1f)' % (laps[i].sum() / ev[i] / 1965., tot[i] / ev[i] / 1965.))
 
 cs = batch.coll_stats()
 if cs is not None:

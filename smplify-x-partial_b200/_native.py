@@ -62,15 +62,21 @@ SFX_MAX_STAGES = 8
 
 
 class SfxPipeline(C.Structure):
-    _fields_ = [('n_stages', C.c_int), ('reserved', C.c_int), ('cam', SfxStage),
+    _fields_ = [('n_stages', C.c_int), ('n_wide', C.c_int), ('cam', SfxStage),
                 ('body', SfxStage * SFX_MAX_STAGES)]
 
 
-def make_pipeline(cam_stage, body_stages):
+WIDE_CLUSTER = 8      # CTAs per wide frame (csrc/sfx_stream.cuh SFX_WIDE_CLUSTER)
+
+
+def make_pipeline(cam_stage, body_stages, n_wide=0):
+    """``n_wide``: the first n_wide frames of the launch order each get a cluster of
+    ``WIDE_CLUSTER`` CTAs (SfxPipeline.n_wide)."""
     if not 1 <= len(body_stages) <= SFX_MAX_STAGES:
         raise ValueError('between 1 and {} annealing stages are supported'.format(SFX_MAX_STAGES))
     P = SfxPipeline()
     P.n_stages = len(body_stages)
+    P.n_wide = int(n_wide)
     P.cam = cam_stage
     for i, st in enumerate(body_stages):
         P.body[i] = st

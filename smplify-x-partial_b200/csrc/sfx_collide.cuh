@@ -512,6 +512,9 @@ SFX_FN void coll_pair(const T* ftri, int fi, const T* ti, int fj, T sigma, bool*
 template <typename T>
 SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& S, const CollWS<T>& W,
                                              T sigma, T weight) {
+    SFX_ASSUME_SHARED(M);
+    SFX_ASSUME_SHARED(S);
+    SFX_ASSUME_SHARED(W);
     const int F = M.F, V = M.V, NP = M.n_parts;
     CollArea<T> A = coll_area(M, W, SFX_NT);
     const T* vert = W.vert_g;
@@ -879,6 +882,9 @@ SFX_FN_NOINLINE void coll_search_and_penalty(const ModelView<T>& M, Scratch<T>& 
 // touched vertex t (compact order; the posed vertices are no longer needed at this point).
 template <typename T>
 SFX_FN_NOINLINE void coll_skin_adjoint(const ModelView<T>& M, Scratch<T>& S, const CollWS<T>& W) {
+    SFX_ASSUME_SHARED(M);
+    SFX_ASSUME_SHARED(S);
+    SFX_ASSUME_SHARED(W);
     const int nt = S.n_touch;
     SFX_PROF_BEGIN(ca);
     SFX_SYNC();

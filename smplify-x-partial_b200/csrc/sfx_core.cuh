@@ -39,9 +39,24 @@
 #if defined(__CUDACC__) && defined(SFX_CYCLE_PROF)
 #define SFX_PROF_BEGIN(name) long long _t_##name = clock64()
 #define SFX_PROF_END(S, slot, name) do { if (threadIdx.x == 0) (S).prof[slot] += clock64() - _t_##name; } while (0)
+// lap timer: the time since the previous lap goes to slot `i` (thread 0's view)
+#define SFX_LAP(S, i) do { if (threadIdx.x == 0) { long long _n = clock64(); (S).lap[i] += _n - (S).lap_t; (S).lap_t = _n; } } while (0)
+#define SFX_NLAP 48
 #else
 #define SFX_PROF_BEGIN(name) ((void)0)
 #define SFX_PROF_END(S, slot, name) ((void)0)
+#define SFX_LAP(S, i) ((void)0)
+#endif
+// Address-space hint: the per-frame working set, the staged model tables and the evaluation
+// context all live in shared memory, but the out-of-line functions below only see generic
+// references; without the hint every access is a generic LD/ST that re-derives the shared window
+// (measured on the two-loop recursion: 42 -> 25 us per evaluation from shared addressing alone).
+#ifdef __CUDACC__
+#define SFX_ASSUME_SHARED(ref) __builtin_assume(__isShared((const void*)&(ref)))
+#define SFX_ASSUME_SHARED_PTR(p) __builtin_assume(__isShared((const void*)(p)))
+#else
+#define SFX_ASSUME_SHARED(ref) ((void)0)
+#define SFX_ASSUME_SHARED_PTR(p) ((void)0)
 #endif
 #define SFX_FOR(i, n) for (int i = SFX_TID; i < (n); i += SFX_NT)
 // same, the iteration space starting at thread `first` (spreads independent loops of one phase
@@ -188,6 +203,9 @@ struct Scratch {
     T o6[128], do6[128];      // VPoser: 6-D rotation outputs and their gradient
     unsigned char vm1[512], vm2[512]; // VPoser: leaky-ReLU masks of the two hidden layers
     T tl_red[64];             // two-loop recursion: per-lane partial sums (double buffered)
+#if defined(__CUDACC__) && defined(SFX_CYCLE_PROF)
+    long long lap[SFX_NLAP], lap_t;    // fine-grained lap timers (profiling build only)
+#endif
     long long prof[16];       // cycle counters: 0 eval, 1 two-loop, 2 blend fwd, 3 blend adj, 4 total,
                               // 8 mesh skinning, 9 part boxes + candidates, 10 narrow phase + penalty,
                               // 11 per-vertex gather, 12 skinning adjoint of touched vertices
@@ -201,6 +219,7 @@ struct Scratch {
     unsigned short wptr[SFX_NSTREAM + 1]; // start of every warp's group in rows[]
     unsigned char slot_live[SFX_NSLOT];
     int n_rows;
+    int rows_dirty;           // wide frames: the helpers' resident copy of the live rows is stale
     int cscan[2][32];
     int cscan_total, cscan_calls, coll_overflow, n_touch, coll_max_cand, coll_max_touch, coll_max_iters, coll_max_hits;
     T coll_loss;
@@ -358,6 +377,19 @@ struct Scratch;
 template <typename T>
 __device__ __forceinline__ bool two_loop_staged(Scratch<T>& S, int k, int head, int H, T hd,
                                                 const T* hist_s, const T* hist_y, int D, void* wsp);
+// "wide" frames (a cluster of CTAs per frame, sfx_stream.cuh): the helpers keep the stage's live
+// rows resident in their shared memory and run both blend passes on them
+__device__ __forceinline__ bool wide_active(void* wsp);
+template <typename T>
+__device__ __forceinline__ void wide_begin(Scratch<T>& S, void* wsp, int cmd);
+template <typename T>
+__device__ __forceinline__ void wide_end_forward(Scratch<T>& S, void* wsp);
+template <typename T>
+__device__ __forceinline__ void wide_end_adjoint(Scratch<T>& S, void* wsp);
+#define SFX_WIDE_EXIT 0
+#define SFX_WIDE_LOAD 1
+#define SFX_WIDE_FWD 2
+#define SFX_WIDE_ADJ 3
 // shared work area that is idle between evaluations (the blend ring), and its release
 template <typename T>
 __device__ __forceinline__ unsigned char* idle_area(void* wsp, size_t* bytes);
@@ -756,6 +788,7 @@ SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>&
         S.shape[i] = v;
     }
     SFX_SYNC();
+    SFX_LAP(S, 1);
     // joint rotations (threads 0..54), rest joints (threads 64..228), yaw row (thread 256)
     SFX_FOR(j, SFX_NJ) rodrigues(S.fp + 3 * j, S.R + 9 * j);
     SFX_FOR_FROM(i, SFX_NJ * 3, 64) {
@@ -785,6 +818,7 @@ SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>&
         S.dynrow = row;
     }
     SFX_SYNC();
+    SFX_LAP(S, 2);
     // blend coefficients: pose feature (R_j - I for j >= 1) | shape | 0
     SFX_FOR(i, SFX_KPAD) {
         T v = 0;
@@ -804,9 +838,13 @@ SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>&
         SFX_SYNC();
         support_slots(M, S, SFX_NSTATIC, SFX_NSLOT);
         support_by_joint(S, SFX_NSTATIC, SFX_NSLOT, S.jtd_ptr, SFX_NSTATIC * SFX_NW);
-        if (SFX_TID == 0) S.dynrow_cached = S.dynrow;
+        if (SFX_TID == 0) {
+            S.dynrow_cached = S.dynrow;
+            S.rows_dirty = 1;
+        }
     }
     SFX_SYNC();
+    SFX_LAP(S, 3);
 }
 
 // Kinematic chain, skinning transforms A and the 55 posed skeleton joints -- one warp, level by
@@ -978,6 +1016,10 @@ namespace sfx {
 // term keeps its register allocation.
 template <typename T>
 SFX_FN_NOINLINE void coll_blend_forward(const ModelView<T>& M, Scratch<T>& S, const CollWS<T>& W, void* ws) {
+    SFX_ASSUME_SHARED(M);
+    SFX_ASSUME_SHARED(S);
+    SFX_ASSUME_SHARED(W);
+    SFX_ASSUME_SHARED_PTR(ws);
     // the whole mesh is needed: stream every row once, the support rows are a subset
     blend_forward_full(M, S, ws, W.vp_g);
     SFX_SYNC();
@@ -986,6 +1028,9 @@ SFX_FN_NOINLINE void coll_blend_forward(const ModelView<T>& M, Scratch<T>& S, co
 template <typename T>
 SFX_FN_NOINLINE void coll_mesh_and_penalty(const ModelView<T>& M, Scratch<T>& S, const CollWS<T>& W,
                                            T sigma, T weight) {
+    SFX_ASSUME_SHARED(M);
+    SFX_ASSUME_SHARED(S);
+    SFX_ASSUME_SHARED(W);
     SFX_PROF_BEGIN(cs);
     coll_skin_mesh(M, S, W);
     SFX_PROF_END(S, 8, cs);
@@ -993,6 +1038,10 @@ SFX_FN_NOINLINE void coll_mesh_and_penalty(const ModelView<T>& M, Scratch<T>& S,
 }
 template <typename T>
 SFX_FN_NOINLINE void coll_blend_adjoint(const ModelView<T>& M, Scratch<T>& S, const CollWS<T>& W, void* ws) {
+    SFX_ASSUME_SHARED(M);
+    SFX_ASSUME_SHARED(S);
+    SFX_ASSUME_SHARED(W);
+    SFX_ASSUME_SHARED_PTR(ws);
     blend_adjoint_ext(M, S, ws, W.tv_g, W.vert_g);
 }
 
@@ -1004,6 +1053,14 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
                                 const T* gt, const T* conf, const unsigned char* init_mask,
                                 const T* cam, const T* reg_pose, Scratch<T>& S, void* stream_ws,
                                 const CollWS<T>* CW = nullptr) {
+    SFX_ASSUME_SHARED(M);
+    SFX_ASSUME_SHARED(L);
+    SFX_ASSUME_SHARED(st);
+    SFX_ASSUME_SHARED(S);
+    SFX_ASSUME_SHARED_PTR(stream_ws);
+#ifdef __CUDACC__
+    __builtin_assume(CW == nullptr || __isShared((const void*)CW));
+#endif
     const int NS = M.NS;
     const int nj = M.NJOUT;
     const int K = M.K;
@@ -1013,10 +1070,17 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     const bool coll = CW != nullptr && M.coll_ready && st.loss_kind == SFX_LOSS_SMPLIFY &&
                       st.coll_loss_weight > 0;
     SFX_PROF_BEGIN(pp);
+    SFX_LAP(S, 0);
     pose_prologue(M, L, S, vposer, stream_ws);
     if (!coll) SFX_PROF_END(S, 8, pp);
     // ---- 3. kinematic chain (warp 0) || blendshapes on the support vertices (every warp) ----
     SFX_PROF_BEGIN(bf);
+#ifdef __CUDACC__
+    const bool wide = !coll && wide_active(stream_ws);
+    if (wide) wide_begin(S, stream_ws, SFX_WIDE_FWD);       // helpers start on their resident rows
+#else
+    const bool wide = false;
+#endif
     if (SFX_IS_WARP0) chain_forward(M, S);
     SFX_PROF_END(S, 5, bf);                     // chain alone (warp 0)
     SFX_PROF_BEGIN(bs);
@@ -1025,12 +1089,16 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     SFX_FOR(r, SFX_NSLOT * 3)
         if (!S.slot_live[r / 3]) S.vp[r] = S.vt_s[r];
     if (coll) coll_blend_forward(M, S, *CW, stream_ws);
+#ifdef __CUDACC__
+    else if (wide) wide_end_forward(S, stream_ws);
+#endif
     else blend_forward(M, S, stream_ws);
 #if defined(__CUDACC__) && defined(SFX_CYCLE_PROF)
     if (threadIdx.x == 32) S.prof[6] += clock64() - _t_bs;      // warp 1's own streaming time
 #endif
     SFX_SYNC();
     SFX_PROF_END(S, 2, bf);
+    SFX_LAP(S, 4);
     if (coll) coll_mesh_and_penalty(M, S, *CW, (T)st.coll_sigma, (T)st.coll_loss_weight);
     SFX_PROF_BEGIN(mid);
     // ---- 4. skinning of the support vertices ------------------------------------------
@@ -1063,6 +1131,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         }
     }
     SFX_SYNC();
+    SFX_LAP(S, 5);
     // ---- 5. extra joints and landmarks ------------------------------------------------
     SFX_FOR(i, (nj - SFX_NJ) * 3) {
         int j = SFX_NJ + i / 3, k = i % 3;
@@ -1077,6 +1146,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.X[3 * j + k] = v;
     }
     SFX_SYNC();
+    SFX_LAP(S, 6);
     // ---- 6. projection + data term per keypoint ---------------------------------------
     const T fx = cam[SFX_CAM_FX], fy = cam[SFX_CAM_FY], cx = cam[SFX_CAM_CX], cy = cam[SFX_CAM_CY];
     const T* Rc = cam + SFX_CAM_R;
@@ -1119,6 +1189,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.dp[3 * k + 1] = dpy;
         S.dp[3 * k + 2] = dpz;
     }
+    SFX_LAP(S, 7);
     // data loss and camera-translation gradient (= sum_k dL/dp_k) and, in body stages, the five
     // sums of squares of the priors (pose, betas, expression, left hand, right hand; they only
     // need the parameters): nine sums, one pass, one pair of barriers
@@ -1148,6 +1219,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     }
     const T data_loss = S.red[0];
     const T gct[3] = {S.red[1], S.red[2], S.red[3]};
+    SFX_LAP(S, 8);
     // ---- 7. adjoint: keypoints -> model joints -> support vertices ---------------------
     SFX_FOR(i, nj * 3) {
         int j = i / 3, a = i % 3;
@@ -1159,12 +1231,14 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.dX[i] = acc;
     }
     SFX_SYNC();
+    SFX_LAP(S, 9);
     SFX_FOR(i, SFX_NSLOT * 3) {
         int s = i / 3, k = i % 3;
         int j = s < SFX_NEXTRA ? SFX_NJ + s : SFX_NJ + SFX_NEXTRA + (s - SFX_NEXTRA) / 3;
         S.dvert[i] = j < nj ? S.bary[s] * S.dX[3 * j + k] : (T)0;
     }
     SFX_SYNC();
+    SFX_LAP(S, 10);
     SFX_FOR(i, SFX_NSLOT * 3) {
         int s = i / 3, k = i % 3;
         const T* Tr = S.Trot + 9 * s;
@@ -1194,21 +1268,30 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.dA[i] = acc;
     }
     SFX_SYNC();
+    SFX_LAP(S, 11);
     const bool coll_adj = coll && S.n_touch > 0;
     if (coll_adj) coll_skin_adjoint(M, S, *CW);
     if (!coll) SFX_PROF_END(S, 9, mid);
     // ---- 8. adjoint of the chain (warp 0) || adjoint of the blendshapes (every warp) -----
     SFX_PROF_BEGIN(ba);
+#ifdef __CUDACC__
+    const bool wide_adj = wide && !coll_adj && st.need_blend_grad;
+    if (wide_adj) wide_begin(S, stream_ws, SFX_WIDE_ADJ);
+#endif
     if (SFX_IS_WARP0) chain_adjoint(M, S);
     SFX_PROF_END(S, 7, ba);                     // chain adjoint alone (warp 0)
     if (st.need_blend_grad) {
         if (coll_adj) coll_blend_adjoint(M, S, *CW, stream_ws);
+#ifdef __CUDACC__
+        else if (wide_adj) wide_end_adjoint(S, stream_ws);
+#endif
         else blend_adjoint(M, S, stream_ws);
     } else {
         SFX_FOR(i, SFX_KPAD) S.dc[i] = 0;
     }
     SFX_SYNC();
     SFX_PROF_END(S, 3, ba);
+    SFX_LAP(S, 12);
     SFX_PROF_BEGIN(tail);
     // ---- 9. pose-feature gradient joins the chain's; Rodrigues adjoint; rest-joint adjoint --
     SFX_FOR(j, SFX_NJ) {
@@ -1224,6 +1307,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.gl[i] = acc;                       // dL/dJ_rest (gl is rewritten after every evaluation)
     }
     SFX_SYNC();
+    SFX_LAP(S, 13);
     // dshape[s] = dc[486 + s] + sum_i JS[i][s] dJ[i]: 16 partial sums per s, fixed order
     SFX_FOR(t, 512) {
         const int sidx = t & 31, part = t >> 5;
@@ -1233,6 +1317,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
         S.c[t] = acc;
     }
     SFX_SYNC();
+    SFX_LAP(S, 14);
     SFX_FOR(sidx, 32) {
         T acc = 0;
         if (sidx < NS) {
@@ -1372,6 +1457,7 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
                       (st.need_blend_grad ? S.n_rows + (coll ? 3 * S.n_touch : 0) : 0);
     }
     SFX_SYNC();
+    SFX_LAP(S, 15);
     if (!coll) SFX_PROF_END(S, 10, tail);
     SFX_PROF_END(S, 0, eval);
 #ifdef SFX_TRACE
@@ -1437,6 +1523,7 @@ SFX_FN void stage_live_rows(const ModelView<T>& M, const SfxStage& st, const T* 
         }
         S.wptr[SFX_NSTREAM] = (unsigned short)n;
         S.n_rows = n;
+        S.rows_dirty = 1;
     }
     SFX_SYNC();
 }
@@ -1520,11 +1607,14 @@ SFX_FN double probe(const EvalCtx<T>& E, Scratch<T>& S, double t, T* gdst, doubl
 #ifdef SFX_TRACE_STEP
     SFX_TRACE_STEP(t);
 #endif
+    SFX_LAP(S, 20);                       // line-search logic since the previous probe
     SFX_FOR(i, D) S.xa[i] = S.x0[i] + tt * S.d[i];
     SFX_SYNC();
     double f = closure(E, S);
+    SFX_LAP(S, 21);                       // gather_grad after the evaluation
     SFX_FOR(i, D) gdst[i] = S.gl[i];
     *gtd_out = (double)block_dot(S.gl, S.d, D, &S.red[2]);
+    SFX_LAP(S, 22);                       // copy + directional derivative
     return f;
 }
 
@@ -1676,6 +1766,7 @@ template <typename T, int NR>
 __device__ __noinline__ void two_loop_warp_n(Scratch<T>& S, int k, int head, int H, T hd,
                                             const T* __restrict__ hist_s,
                                             const T* __restrict__ hist_y, int D) {
+    SFX_ASSUME_SHARED(S);
     constexpr int PF = 3;                 // (s, y) pairs in flight ahead of the one in use
     const int lane = threadIdx.x;
     // only the last register of a lane can lie beyond D
@@ -2001,6 +2092,8 @@ SFX_FN void gram_combine(Scratch<T>& S, int k, int head, int H, T hd, const T* h
 template <typename T>
 SFX_FN_NOINLINE void gram_two_loop(const EvalCtx<T>& E, Scratch<T>& S, int k, int head, int H, T hd,
                           const T* hist_s, const T* hist_y, int D, bool has_new) {
+    SFX_ASSUME_SHARED(E);
+    SFX_ASSUME_SHARED(S);
     constexpr int LD = SFX_HIST;
     T* GSY = E.gram;
     T* GYY = E.gram + (size_t)LD * LD;
@@ -2160,6 +2253,7 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
             ls.H_diag = 1;
         } else {
             // y = g - prev_g ; s = d * t   (staged in q / x0 until accepted)
+            SFX_LAP(S, 23);               // end-of-iteration tests of the previous iteration
             const T tt = (T)ls.t;
             SFX_FOR(i, D) {
                 S.q[i] = S.g[i] - S.prev_g[i];
@@ -2197,6 +2291,7 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
                 ls.H_diag = ys / yy;
             }
             // two-loop recursion
+            SFX_LAP(S, 24);               // history update (y, s, ys, yy)
             const int k = ls.num_old;
             if (E.st->generic_two_loop == 2 && E.gram != nullptr) {
                 SFX_PROF_BEGIN(tlg);
@@ -2239,6 +2334,7 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
             SFX_SYNC();
             }
         }
+        SFX_LAP(S, 25);                   // two-loop recursion
         vcopy(S.prev_g, S.g, D);
         ls.prev_loss = loss;
         double t;
@@ -2255,8 +2351,10 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
             break;
         }
         vcopy(S.x0, S.xa, D);      // x_init
+        SFX_LAP(S, 26);                   // step length, gtd, copies before the line search
         int ls_evals = 0;
         loss = strong_wolfe(E, S, &t, loss, gtd, &ls_evals);
+        SFX_LAP(S, 27);                   // line-search epilogue (after the last probe)
         {
             const T tt = (T)t;
             SFX_FOR(i, D) S.xa[i] = S.x0[i] + tt * S.d[i];
@@ -2317,6 +2415,13 @@ SFX_FN double rel_change(double prev, double cur) {
 // the reference would return None).
 template <typename T>
 SFX_FN_NOINLINE double run_fitting(const EvalCtx<T>& E, Scratch<T>& S, T* hist_s, T* hist_y, int* flags) {
+    SFX_ASSUME_SHARED(E);
+    SFX_ASSUME_SHARED(S);
+    SFX_ASSUME_SHARED_PTR(E.st);
+    SFX_ASSUME_SHARED_PTR(E.M);
+    SFX_ASSUME_SHARED_PTR(E.L);
+    SFX_ASSUME_SHARED_PTR(E.stream_ws);
+    SFX_ASSUME_SHARED_PTR(flags);
     const SfxStage& st = *E.st;
     const int D = st.n_active;
     // compact index list

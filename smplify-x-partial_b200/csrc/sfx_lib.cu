@@ -53,7 +53,36 @@ __device__ __forceinline__ StreamWS carve_stream(unsigned char* base, int ring_m
     ws.tl_generic = (ring_mode >> 1) & 1;
     ws.stream_regs = (ring_mode >> 2) & 1;
     ws.tl_shfl = (ring_mode >> 3) & 1;
+    ws.wide = 0;
+    ws.wc = nullptr;
     return ws;
+}
+
+// Per-block copies, in shared memory, of everything the evaluation reads through references:
+// the model view (its kinematic tables are indexed per lane on the critical path of the chain),
+// the layout, the stage, the evaluation context and the workspace descriptors.  As kernel
+// parameters they are only reachable through generic loads from the parameter window once a
+// reference crosses into an out-of-line function.
+template <typename T>
+struct BlockCtx {
+    ModelView<T> M;
+    SfxLayout L;
+    SfxStage st;
+    EvalCtx<T> E;
+    CollWS<T> CW;
+    StreamWS ws;
+    int flags, s_idx;
+};
+
+template <typename T>
+__device__ __forceinline__ void stage_block_ctx(BlockCtx<T>& C, const ModelView<T>& M, const SfxLayout& L) {
+    const int* src = reinterpret_cast<const int*>(&M);
+    int* dst = reinterpret_cast<int*>(&C.M);
+    for (int i = threadIdx.x; i < (int)(sizeof(ModelView<T>) / 4); i += blockDim.x) dst[i] = src[i];
+    const int* ls = reinterpret_cast<const int*>(&L);
+    int* ld = reinterpret_cast<int*>(&C.L);
+    for (int i = threadIdx.x; i < (int)(sizeof(SfxLayout) / 4); i += blockDim.x) ld[i] = ls[i];
+    __syncthreads();
 }
 
 template <typename T>
@@ -72,6 +101,10 @@ __device__ __forceinline__ void load_frame(const BatchView<T>& Bv, int f, Scratc
         S.coll_overflow = 0;
         S.coll_max_cand = S.coll_max_touch = S.coll_max_iters = S.coll_max_hits = 0;
         for (int i = 0; i < 16; ++i) S.prof[i] = 0;
+#ifdef SFX_CYCLE_PROF
+        for (int i = 0; i < SFX_NLAP; ++i) S.lap[i] = 0;
+        S.lap_t = clock64();
+#endif
     }
     __syncthreads();
 }
@@ -91,39 +124,48 @@ __device__ __forceinline__ bool block_coll_ws(const ModelView<T>& M, const Batch
 
 template <typename T>
 __global__ void __launch_bounds__(SFX_THREADS, 1)
-fit_stage_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ BatchView<T> Bv,
-                 const __grid_constant__ SfxStage st, int ring_mode, T* final_loss_out) {
+fit_stage_kernel(const __grid_constant__ ModelView<T> Mp, const __grid_constant__ BatchView<T> Bv,
+                 const __grid_constant__ SfxStage stp, int ring_mode, T* final_loss_out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(smem);
-    __shared__ StreamWS ws;
-    __shared__ int flags;
+    __shared__ BlockCtx<T> C;
+    const ModelView<T>& M = C.M;
+    StreamWS& ws = C.ws;
     const int f = Bv.frame_ids ? Bv.frame_ids[blockIdx.x] : (int)blockIdx.x;
-    const int K = M.K;
     if (threadIdx.x == 0) {
         ws = carve_stream<T>(smem + scratch_bytes<T>(), ring_mode);
-        flags = 0;
+        C.flags = 0;
     }
-    __syncthreads();
+    {
+        const int* s32 = reinterpret_cast<const int*>(&stp);
+        int* d32 = reinterpret_cast<int*>(&C.st);
+        for (int i = threadIdx.x; i < (int)(sizeof(SfxStage) / 4); i += blockDim.x) d32[i] = s32[i];
+    }
+    stage_block_ctx(C, Mp, Bv.lay);
+    const SfxStage& st = C.st;
+    const int K = M.K;
     stream_init<T>(ws);
     load_frame(Bv, f, S);
     support_begin_frame(M, S);
     stage_setup(M, st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
                 Bv.init_mask + (size_t)f * K, K, S);
-    EvalCtx<T> E;
-    E.M = &M; E.L = &Bv.lay; E.st = &st;
-    E.gt = Bv.gt + (size_t)f * K * 2;
-    E.conf = Bv.conf + (size_t)f * K;
-    E.init_mask = Bv.init_mask + (size_t)f * K;
-    E.cam = Bv.cam + (size_t)f * SFX_CAM_STRIDE;
-    E.reg_pose = Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr;
-    E.stream_ws = &ws;
-    E.gram = Bv.gram ? Bv.gram + (size_t)f * 2 * SFX_HIST * SFX_HIST : nullptr;
-    CollWS<T> CW;
-    E.coll = block_coll_ws(M, Bv, ws, CW) ? &CW : nullptr;
-    double r = run_fitting(E, S, Bv.hist_s + (size_t)f * SFX_HIST * SFX_NP_MAX,
-                           Bv.hist_y + (size_t)f * SFX_HIST * SFX_NP_MAX, &flags);
+    if (threadIdx.x == 0) {
+        EvalCtx<T>& E = C.E;
+        E.M = &C.M; E.L = &C.L; E.st = &C.st;
+        E.gt = Bv.gt + (size_t)f * K * 2;
+        E.conf = Bv.conf + (size_t)f * K;
+        E.init_mask = Bv.init_mask + (size_t)f * K;
+        E.cam = Bv.cam + (size_t)f * SFX_CAM_STRIDE;
+        E.reg_pose = Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr;
+        E.stream_ws = &C.ws;
+        E.gram = Bv.gram ? Bv.gram + (size_t)f * 2 * SFX_HIST * SFX_HIST : nullptr;
+        E.coll = block_coll_ws(M, Bv, ws, C.CW) ? &C.CW : nullptr;
+    }
     __syncthreads();
-    if (threadIdx.x == 0 && S.coll_overflow) flags |= SFX_FLAG_COLL_OVERFLOW;
+    double r = run_fitting(C.E, S, Bv.hist_s + (size_t)f * SFX_HIST * SFX_NP_MAX,
+                           Bv.hist_y + (size_t)f * SFX_HIST * SFX_NP_MAX, &C.flags);
+    __syncthreads();
+    const int flags = C.flags | (S.coll_overflow ? SFX_FLAG_COLL_OVERFLOW : 0);
     if (threadIdx.x == 0 && Bv.coll_stat) {
         Bv.coll_stat[4 * f] = max(Bv.coll_stat[4 * f], S.coll_max_cand);
         Bv.coll_stat[4 * f + 1] = max(Bv.coll_stat[4 * f + 1], S.coll_max_touch);
@@ -143,28 +185,36 @@ fit_stage_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__
 
 template <typename T>
 __global__ void __launch_bounds__(SFX_THREADS, 1)
-eval_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ BatchView<T> Bv,
-            const __grid_constant__ SfxStage st, int ring_mode, T* loss_out, T* grad_out,
+eval_kernel(const __grid_constant__ ModelView<T> Mp, const __grid_constant__ BatchView<T> Bv,
+            const __grid_constant__ SfxStage stp, int ring_mode, T* loss_out, T* grad_out,
             T* joints_out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(smem);
-    __shared__ StreamWS ws;
+    __shared__ BlockCtx<T> C;
+    const ModelView<T>& M = C.M;
+    StreamWS& ws = C.ws;
     const int f = blockIdx.x;
-    const int K = M.K;
     if (threadIdx.x == 0) ws = carve_stream<T>(smem + scratch_bytes<T>(), ring_mode);
-    __syncthreads();
+    {
+        const int* s32 = reinterpret_cast<const int*>(&stp);
+        int* d32 = reinterpret_cast<int*>(&C.st);
+        for (int i = threadIdx.x; i < (int)(sizeof(SfxStage) / 4); i += blockDim.x) d32[i] = s32[i];
+    }
+    stage_block_ctx(C, Mp, Bv.lay);
+    const SfxStage& st = C.st;
+    const int K = M.K;
     stream_init<T>(ws);
     load_frame(Bv, f, S);
     support_begin_frame(M, S);
     // the mapped joints of EVERY keypoint are an output: no row may be skipped then
     stage_setup(M, st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
                 Bv.init_mask + (size_t)f * K, K, S, joints_out != nullptr);
-    CollWS<T> CW;
-    const bool has_coll = block_coll_ws(M, Bv, ws, CW);
-    eval_frame(M, Bv.lay, st, Bv.gt + (size_t)f * K * 2, Bv.conf + (size_t)f * K,
+    if (threadIdx.x == 0) C.s_idx = block_coll_ws(M, Bv, ws, C.CW) ? 1 : 0;
+    __syncthreads();
+    eval_frame(M, C.L, st, Bv.gt + (size_t)f * K * 2, Bv.conf + (size_t)f * K,
                Bv.init_mask + (size_t)f * K, Bv.cam + (size_t)f * SFX_CAM_STRIDE,
                Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr, S, &ws,
-               has_coll ? &CW : nullptr);
+               C.s_idx ? &C.CW : nullptr);
     if (threadIdx.x == 0 && S.coll_overflow) Bv.flags[f] |= SFX_FLAG_COLL_OVERFLOW;
     if (threadIdx.x == 0 && Bv.coll_stat) {
         Bv.coll_stat[4 * f] = max(Bv.coll_stat[4 * f], S.coll_max_cand);
@@ -186,17 +236,18 @@ eval_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ Batc
 // full-mesh path.
 template <typename T>
 __global__ void __launch_bounds__(SFX_THREADS, 1)
-mesh_coef_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ BatchView<T> Bv,
+mesh_coef_kernel(const __grid_constant__ ModelView<T> Mp, const __grid_constant__ BatchView<T> Bv,
                  int use_vposer, T* Aout, T* Cout) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(smem);
-    __shared__ StreamWS ws;
-    if (threadIdx.x == 0) ws = carve_stream<T>(smem + scratch_bytes<T>(), 0);    // plain loads
-    __syncthreads();
+    __shared__ BlockCtx<T> C;
+    const ModelView<T>& M = C.M;
+    if (threadIdx.x == 0) C.ws = carve_stream<T>(smem + scratch_bytes<T>(), 0);    // plain loads
+    stage_block_ctx(C, Mp, Bv.lay);
     const int f = blockIdx.x;
     load_frame(Bv, f, S);
     support_begin_frame(M, S);
-    pose_prologue(M, Bv.lay, S, use_vposer != 0, &ws);
+    pose_prologue(M, C.L, S, use_vposer != 0, &C.ws);
     if (threadIdx.x < 32) chain_forward(M, S);
     __syncthreads();
     for (int i = threadIdx.x; i < SFX_NJ * 12; i += blockDim.x) Aout[(size_t)f * SFX_NJ * 12 + i] = S.A[i];
@@ -310,59 +361,97 @@ __device__ void reset_for_orientation(const SfxLayout& L, Scratch<T>& S) {
 
 template <typename T>
 __global__ void __launch_bounds__(SFX_THREADS, 1)
-fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constant__ BatchView<T> Bv,
+fit_pipeline_kernel(const __grid_constant__ ModelView<T> Mp, const __grid_constant__ BatchView<T> Bv,
                     const SfxPipeline* __restrict__ P, const unsigned char* __restrict__ flip,
-                    int n_frames, int* counter, int ring_mode, T* cam_loss_out, T* params_last) {
+                    int n_frames, int* counter, int ring_mode, T* cam_loss_out, T* params_last,
+                    int wide_cl, int dyn_bytes) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(smem);
-    __shared__ StreamWS ws;
-    __shared__ SfxStage st;
-    __shared__ int flags, s_idx;
+    __shared__ BlockCtx<T> C;
     __shared__ T alt[SFX_NP_MAX];
-    const int K = M.K;
+    __shared__ WideCtl wctl;
+    const ModelView<T>& M = C.M;
+    StreamWS& ws = C.ws;
+    const SfxStage& st = C.st;
     const int np = Bv.lay.np;
-    const SfxLayout& L = Bv.lay;
+    const SfxLayout& L = C.L;
     if (threadIdx.x == 0) ws = carve_stream<T>(smem + scratch_bytes<T>(), ring_mode);
-    __syncthreads();
+    if constexpr (sizeof(T) == 4) {
+        // wide frames: this block belongs to a cluster of wide_cl CTAs (launched as such); rank 0
+        // leads, the others serve it until the leader has run out of frames
+        if (wide_cl > 1) {
+            // programmatic dependent launch: the one-block frames' kernel, queued behind this one
+            // in the same stream, may start as soon as every CTA of this grid is resident and got
+            // here -- so the clusters hold their GPC-aligned SMs before the other grid spreads out
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+            const int rank = (int)cluster_ctarank();
+            if (threadIdx.x == 0) {
+                mbar_init(&wctl.go_bar, 1);
+                mbar_init(&wctl.done_bar, wide_cl - 1);
+                mbar_init(&wctl.load_bar, 1);
+                wctl.cmd = 0;
+                wctl.n_rows = 0;
+                wctl.done_phase = 0;
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            cluster_sync_all();                  // every CTA's barriers exist before anyone signals
+            if (rank != 0) {
+                wide_helper_main(reinterpret_cast<const float*>(Mp.PK), smem, (size_t)dyn_bytes, &wctl, wide_cl);
+                cluster_sync_all();
+                return;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                ws.wide = wide_cl;
+                ws.wc = &wctl;
+            }
+        }
+    }
+    stage_block_ctx(C, Mp, Bv.lay);
+    const int K = M.K;
     stream_init<T>(ws);
     auto load_stage = [&](const SfxStage* src) {
         __syncthreads();
         const int* s32 = reinterpret_cast<const int*>(src);
-        int* d32 = reinterpret_cast<int*>(&st);
+        int* d32 = reinterpret_cast<int*>(&C.st);
         for (int i = threadIdx.x; i < (int)(sizeof(SfxStage) / 4); i += blockDim.x) d32[i] = s32[i];
         __syncthreads();
     };
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            s_idx = atomicAdd(counter, 1);
-            flags = 0;
+            C.s_idx = atomicAdd(counter, 1);
+            C.flags = 0;
         }
         __syncthreads();
-        const int idx = s_idx;
+        const int idx = C.s_idx;
         if (idx >= n_frames) break;
         const int f = Bv.frame_ids ? Bv.frame_ids[idx] : idx;
         load_frame(Bv, f, S);
         SFX_PROF_BEGIN(total);
         support_begin_frame(M, S);
-        EvalCtx<T> E;
-        E.M = &M; E.L = &Bv.lay; E.st = &st;
-        E.gt = Bv.gt + (size_t)f * K * 2;
-        E.conf = Bv.conf + (size_t)f * K;
-        E.init_mask = Bv.init_mask + (size_t)f * K;
-        E.cam = Bv.cam + (size_t)f * SFX_CAM_STRIDE;
-        E.reg_pose = Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr;
-        E.stream_ws = &ws;
-        E.gram = Bv.gram ? Bv.gram + (size_t)f * 2 * SFX_HIST * SFX_HIST : nullptr;
-        CollWS<T> CW;
-        E.coll = block_coll_ws(M, Bv, ws, CW) ? &CW : nullptr;
+        if (threadIdx.x == 0) {
+            EvalCtx<T>& E = C.E;
+            E.M = &C.M; E.L = &C.L; E.st = &C.st;
+            E.gt = Bv.gt + (size_t)f * K * 2;
+            E.conf = Bv.conf + (size_t)f * K;
+            E.init_mask = Bv.init_mask + (size_t)f * K;
+            E.cam = Bv.cam + (size_t)f * SFX_CAM_STRIDE;
+            E.reg_pose = Bv.reg_pose ? Bv.reg_pose + (size_t)f * Bv.lay.n_pose : nullptr;
+            E.stream_ws = &C.ws;
+            E.gram = Bv.gram ? Bv.gram + (size_t)f * 2 * SFX_HIST * SFX_HIST : nullptr;
+            E.coll = block_coll_ws(M, Bv, ws, C.CW) ? &C.CW : nullptr;
+        }
+        __syncthreads();
+        const EvalCtx<T>& E = C.E;
         T* hs = Bv.hist_s + (size_t)f * SFX_HIST * SFX_NP_MAX;
         T* hy = Bv.hist_y + (size_t)f * SFX_HIST * SFX_NP_MAX;
         // stage C: camera translation + global orientation (fit_single_frame.py:473-496)
         load_stage(&P->cam);
         stage_setup(M, st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
                 Bv.init_mask + (size_t)f * K, K, S);
-        double r = run_fitting(E, S, hs, hy, &flags);
+        double r = run_fitting(E, S, hs, hy, &C.flags);
         __syncthreads();
         if (threadIdx.x == 0 && cam_loss_out) cam_loss_out[f] = (T)r;
         T go0[3] = {S.x[L.off_go], S.x[L.off_go + 1], S.x[L.off_go + 2]};
@@ -391,7 +480,7 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
                 load_stage(&P->body[si]);
                 stage_setup(M, st, Bv.jw_base + (size_t)f * K, Bv.lowconf + (size_t)f * K, Bv.conf + (size_t)f * K,
                 Bv.init_mask + (size_t)f * K, K, S);
-                r = run_fitting(E, S, hs, hy, &flags);
+                r = run_fitting(E, S, hs, hy, &C.flags);
             }
         }
         __syncthreads();
@@ -406,7 +495,7 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
             Bv.final_loss[f] = (T)(restore ? loss0 : r);
             Bv.n_evals[f] += S.n_evals;
             Bv.n_passes[f] += S.n_passes;
-            Bv.flags[f] |= flags | (S.coll_overflow ? SFX_FLAG_COLL_OVERFLOW : 0);
+            Bv.flags[f] |= C.flags | (S.coll_overflow ? SFX_FLAG_COLL_OVERFLOW : 0);
             if (Bv.coll_stat) {
                 Bv.coll_stat[4 * f] = max(Bv.coll_stat[4 * f], S.coll_max_cand);
                 Bv.coll_stat[4 * f + 1] = max(Bv.coll_stat[4 * f + 1], S.coll_max_touch);
@@ -415,8 +504,16 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> M, const __grid_constan
             }
 #ifdef SFX_CYCLE_PROF
             S.prof[4] += clock64() - _t_total;
-            for (int i = 0; i < 16; ++i) Bv.prof[(size_t)f * 16 + i] = S.prof[i];
+            for (int i = 0; i < 16; ++i) Bv.prof[(size_t)f * 64 + i] = S.prof[i];
+            for (int i = 0; i < SFX_NLAP; ++i) Bv.prof[(size_t)f * 64 + 16 + i] = S.lap[i];
 #endif
+        }
+    }
+    if constexpr (sizeof(T) == 4) {
+        if (wide_cl > 1) {                       // leader: release the helpers, leave together
+            __syncthreads();
+            wide_post(ws, SFX_WIDE_EXIT, 0);
+            cluster_sync_all();
         }
     }
 }
@@ -532,6 +629,7 @@ struct sfx_batch {
         cam_loss, params_last, prof, coll_vals, coll_idx, coll_stat;
     bool last_valid = false;
     bool has_reg = false;
+
     std::vector<unsigned char> stage_host;     // host staging for set_targets
     template <typename T>
     BatchView<T> view(const int* frame_ids) const {
@@ -759,7 +857,7 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     ALLOC(pipe, sizeof(SfxPipeline));
     ALLOC(counter, 64);
     ALLOC(cam_loss, (size_t)B * es);
-    ALLOC(prof, (size_t)B * 16 * sizeof(long long));
+    ALLOC(prof, (size_t)B * 64 * sizeof(long long));
     ALLOC(params_last, (size_t)B * b->lay.np * es);
 #undef ALLOC
     *out = b;
@@ -985,21 +1083,71 @@ int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(b->pipe.p, pipe, sizeof(SfxPipeline), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemsetAsync(b->counter.p, 0, sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(b->counter.p, 0, 2 * sizeof(int), s));
     const int rm = ring_mode_for(b->m);
+    // wide frames (SfxPipeline::n_wide): float32 with the TMA ring, an explicit launch order, and
+    // only while the clusters fit next to the one-block frames (everything stays co-resident)
+    int n_wide = pipe->n_wide;
+    if (n_wide < 0 || n_wide > b->B) return fail(SFX_ERR_ARG, "pipeline: n_wide out of range");
+    if (b->m->use_double || !(rm & 1) || (rm & 4) || !order_dev || b->coll_vals.p) n_wide = 0;
+    while (n_wide > 0 && n_wide * SFX_WIDE_CLUSTER + (b->B - n_wide) > b->m->num_sms) --n_wide;
+    if (n_wide > 0) {
+        size_t smem = fit_smem<float>(rm);
+        CUDA_TRY(cudaFuncSetAttribute(fit_pipeline_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(n_wide * SFX_WIDE_CLUSTER));
+        cfg.blockDim = dim3(SFX_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = SFX_WIDE_CLUSTER;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, fit_pipeline_kernel<float>, b->m->vf, b->view<float>(order_dev),
+                                    (const SfxPipeline*)b->pipe.p, flip_dev, n_wide, (int*)b->counter.p + 1, rm,
+                                    (float*)b->cam_loss.p, (float*)b->params_last.p, (int)SFX_WIDE_CLUSTER,
+                                    (int)smem));
+        const int n_main = b->B - n_wide;
+        if (n_main > 0) {
+            // same stream, allowed to overlap the wide grid (which triggers at its very start):
+            // the frames of the two grids are independent, nothing here waits on the first grid
+            cudaLaunchConfig_t cm;
+            memset(&cm, 0, sizeof(cm));
+            cm.gridDim = dim3((unsigned)(n_main < b->m->num_sms ? n_main : b->m->num_sms));
+            cm.blockDim = dim3(SFX_THREADS);
+            cm.dynamicSmemBytes = smem;
+            cm.stream = s;
+            cudaLaunchAttribute am[1];
+            am[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            am[0].val.programmaticStreamSerializationAllowed = 1;
+            cm.attrs = am;
+            cm.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cm, fit_pipeline_kernel<float>, b->m->vf,
+                                        b->view<float>(order_dev + n_wide), (const SfxPipeline*)b->pipe.p,
+                                        flip_dev, n_main, (int*)b->counter.p, rm, (float*)b->cam_loss.p,
+                                        (float*)b->params_last.p, 1, (int)smem));
+        }
+        CUDA_TRY(cudaGetLastError());
+        b->last_valid = true;
+        return SFX_OK;
+    }
     const int grid = b->B < b->m->num_sms ? b->B : b->m->num_sms;
     if (b->m->use_double) {
         size_t smem = fit_smem<double>(rm);
         CUDA_TRY(cudaFuncSetAttribute(fit_pipeline_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fit_pipeline_kernel<double><<<grid, SFX_THREADS, smem, s>>>(
             b->m->vd, b->view<double>(order_dev), (const SfxPipeline*)b->pipe.p, flip_dev, b->B,
-            (int*)b->counter.p, rm, (double*)b->cam_loss.p, (double*)b->params_last.p);
+            (int*)b->counter.p, rm, (double*)b->cam_loss.p, (double*)b->params_last.p, 1, (int)smem);
     } else {
         size_t smem = fit_smem<float>(rm);
         CUDA_TRY(cudaFuncSetAttribute(fit_pipeline_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fit_pipeline_kernel<float><<<grid, SFX_THREADS, smem, s>>>(
             b->m->vf, b->view<float>(order_dev), (const SfxPipeline*)b->pipe.p, flip_dev, b->B,
-            (int*)b->counter.p, rm, (float*)b->cam_loss.p, (float*)b->params_last.p);
+            (int*)b->counter.p, rm, (float*)b->cam_loss.p, (float*)b->params_last.p, 1, (int)smem);
     }
     CUDA_TRY(cudaGetLastError());
     b->last_valid = true;

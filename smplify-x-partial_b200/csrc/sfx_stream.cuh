@@ -31,6 +31,8 @@ struct StreamWS {
     int tl_generic;             // debug: the generic-pointer staged recursion (A/B test)
     int stream_regs;            // rows travel global -> registers, several in flight per warp (no ring)
     int tl_shfl;                // A/B: shuffle butterfly instead of the shared-memory tree in the two-loop
+    int wide;                   // > 1: this block leads a cluster of `wide` CTAs (see "wide frames" below)
+    struct WideCtl* wc;
 };
 #define SFX_TL_GROUPS 8
 
@@ -174,6 +176,9 @@ __device__ __forceinline__ void stream_rows_own(OWN own, RP rowptr, StreamWS& ws
     if (ws.ring_mode) {
         unsigned char* mybuf = ws.ring + (size_t)warp * SFX_NBUF * ROWB;
         uint64_t* mybar = ws.bars + warp * SFX_NBUF;
+        SFX_ASSUME_SHARED_PTR(mybuf);
+        SFX_ASSUME_SHARED_PTR(mybar);
+        SFX_ASSUME_SHARED_PTR(ws.fills);
         const unsigned int n0 = ws.fills[warp];
         auto issue = [&](int i) {
             int r = own.index(warp, i);
@@ -271,6 +276,7 @@ __device__ __forceinline__ void blend_adjoint(const ModelView<T>& M, Scratch<T>&
     // cross-warp reduction in a fixed order; the partial sums reuse the ring storage
     __syncthreads();
     T* part = reinterpret_cast<T*>(ws.ring);
+    SFX_ASSUME_SHARED_PTR(part);
 #pragma unroll
     for (int i = 0; i < RowVec<T>::NV; ++i)
 #pragma unroll
@@ -343,6 +349,7 @@ __device__ __forceinline__ void blend_adjoint_ext(const ModelView<T>& M, Scratch
     }, [=](int i) { return i < NS3 ? dvp[rows[i]] : dvpc[i - NS3]; }, true);
     __syncthreads();
     T* part = reinterpret_cast<T*>(ws.ring);
+    SFX_ASSUME_SHARED_PTR(part);
 #pragma unroll
     for (int i = 0; i < RowVec<T>::NV; ++i)
 #pragma unroll
@@ -398,6 +405,7 @@ __device__ __forceinline__ void rows_accum(const T* W, int nrows, const T* g, T*
     });
     __syncthreads();
     T* part = reinterpret_cast<T*>(ws.ring);
+    SFX_ASSUME_SHARED_PTR(part);
 #pragma unroll
     for (int i = 0; i < RowVec<T>::NV; ++i)
 #pragma unroll
@@ -427,6 +435,8 @@ template <typename T, int NR>
 __device__ __noinline__ void two_loop_staged_n(Scratch<T>& S, int k, int head, int H, T hd,
                                                const T* __restrict__ hist_s,
                                                const T* __restrict__ hist_y, int D, StreamWS& ws) {
+    SFX_ASSUME_SHARED(S);
+    SFX_ASSUME_SHARED(ws);
     const int lane = threadIdx.x;
     const uint32_t RB = (uint32_t)((D * sizeof(T) + 15) & ~(size_t)15);
     const int per = (k + SFX_TL_GROUPS - 1) / SFX_TL_GROUPS;
@@ -558,6 +568,8 @@ template <int NR, bool SHFL>
 __device__ __noinline__ void two_loop_staged_f32(Scratch<float>& S, int k, int head, int H, float hd,
                                                  const float* __restrict__ hist_s,
                                                  const float* __restrict__ hist_y, int D, StreamWS& ws) {
+    SFX_ASSUME_SHARED(S);
+    SFX_ASSUME_SHARED(ws);
     const int lane = threadIdx.x;
     const uint32_t RB = (uint32_t)((D * sizeof(float) + 15) & ~(size_t)15);
     const int per = (k + SFX_TL_GROUPS - 1) / SFX_TL_GROUPS;
@@ -753,6 +765,261 @@ __device__ __forceinline__ void gram_chain_f32(Scratch<float>& S, int k, float h
         }
     }
     __syncwarp();
+}
+
+
+// ---- wide frames: one frame, a cluster of CTAs ------------------------------------------------
+// A batch smaller than the GPU leaves SMs idle while its longest frames -- those that fit two
+// orientations, known before the launch -- run on alone; most of their time is the two passes
+// over the live rows of the blend matrix in the last annealing stage (675 rows x 2 KiB, twice per
+// evaluation, through one SM's L2 port).  Such a frame is given a cluster of SFX_WIDE_CLUSTER
+// CTAs: rank 0 (the leader) runs the whole per-frame flow exactly as a single block does, ranks
+// 1.. (the helpers) keep the stage's live rows RESIDENT in their shared memory (7 x 110 rows
+// hold all 675) and do the two passes on them when the leader asks, over distributed shared memory:
+//
+//   LOAD   helper pulls its share of the leader's row list (S.rows / S.vid / S.vt_s) and copies
+//          those rows of PK from global memory into its shared memory (TMA bulk copies); once per
+//          stage and whenever the contour look-up row changes
+//   FWD    helper pulls c[512] from the leader, a warp per row: vp[r] = vt[r] + row . c, written
+//          straight into the leader's S.vp
+//   ADJ    helper pulls dvp of its rows, a thread per column: partial dc[k] = sum_rows row[k] dvp,
+//          written into the leader's ring; the leader adds the helpers' partials in rank order
+//
+// Commands travel as a word in the helper's shared memory + a remote mbarrier arrive
+// (release.cluster); completions as remote arrives on the leader's mbarrier.  The forward pass
+// gives bit-identical results to the single-block path (a row's dot product does not depend on
+// who computes it); the adjoint sums the rows in a different order (by helper, then row, instead
+// of by streaming warp), so a wide frame's rounding differs from the same frame run by one
+// block: an explicit option (SfxPipeline::n_wide), deterministic run to run.
+#define SFX_WIDE_CLUSTER 8
+#define SFX_WIDE_ROWS_MAX 110        // resident rows per helper (dynamic shared memory / 2 KiB)
+
+struct WideCtl {                     // static shared memory: same offset in every CTA of the cluster
+    uint64_t go_bar;                 // helper: the leader's commands arrive here
+    uint64_t done_bar;               // leader: one arrival per helper and command
+    uint64_t load_bar;               // helper: TMA completion of a LOAD
+    int cmd, n_rows;                 // written by the leader (remote stores)
+    unsigned int done_phase;         // leader: commands completed so far
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float ld_cluster_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_cluster_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned short ld_cluster_u16(uint32_t a) {
+    unsigned short v;
+    asm volatile("ld.shared::cluster.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_cluster_v4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t a, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_s32(uint32_t a, int v) {
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ bool wide_active(void* wsp) {
+    return reinterpret_cast<StreamWS*>(wsp)->wide > 1;
+}
+
+// leader: post `cmd` to every helper (threads 32 .. 32 + helpers - 1, one helper each).  The data
+// the command refers to was written before the caller's last block barrier.
+__device__ __forceinline__ void wide_post(StreamWS& ws, int cmd, int n_rows) {
+    const int h = (int)threadIdx.x - 32;
+    if (h >= 0 && h < ws.wide - 1) {
+        WideCtl* wc = ws.wc;
+        st_cluster_s32(mapa_u32(smem_u32(&wc->n_rows), h + 1), n_rows);
+        st_cluster_s32(mapa_u32(smem_u32(&wc->cmd), h + 1), cmd);
+        mbar_arrive_remote(mapa_u32(smem_u32(&wc->go_bar), h + 1));
+    }
+}
+// leader, every thread: wait for the helpers' completion of the outstanding command
+__device__ __forceinline__ void wide_wait(StreamWS& ws) {
+    SFX_ASSUME_SHARED_PTR(ws.wc);
+    const unsigned int p = ws.wc->done_phase;
+    mbar_wait_cluster(&ws.wc->done_bar, p & 1);
+}
+
+template <typename T>
+__device__ __forceinline__ void wide_begin(Scratch<T>& S, void* wsp, int cmd) {
+    StreamWS& ws = *reinterpret_cast<StreamWS*>(wsp);
+    // callers sit right behind a block barrier: S.c / S.dvp, S.rows_dirty and done_phase are settled
+    if (cmd == SFX_WIDE_FWD && S.rows_dirty) {
+        wide_post(ws, SFX_WIDE_LOAD, S.n_rows);
+        wide_wait(ws);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ws.wc->done_phase += 1;
+            S.rows_dirty = 0;
+        }
+        __syncthreads();
+    }
+    wide_post(ws, cmd, S.n_rows);
+}
+
+template <typename T>
+__device__ __forceinline__ void wide_end_forward(Scratch<T>& S, void* wsp) {
+    StreamWS& ws = *reinterpret_cast<StreamWS*>(wsp);
+    wide_wait(ws);                    // S.vp of every live row was written by the helpers
+    __syncthreads();
+    if (threadIdx.x == 0) ws.wc->done_phase += 1;
+}
+
+template <typename T>
+__device__ __forceinline__ void wide_end_adjoint(Scratch<T>& S, void* wsp) {
+    StreamWS& ws = *reinterpret_cast<StreamWS*>(wsp);
+    wide_wait(ws);
+    __syncthreads();
+    if (threadIdx.x == 0) ws.wc->done_phase += 1;
+    const T* part = reinterpret_cast<const T*>(ws.ring);
+    SFX_ASSUME_SHARED_PTR(part);
+    const int nh = ws.wide - 1;
+    for (int k = threadIdx.x; k < SFX_KPAD; k += blockDim.x) {
+        T s = 0;
+        for (int h = 0; h < nh; ++h) s += part[h * SFX_KPAD + k];
+        S.dc[k] = s;
+    }
+    __syncthreads();
+    if (ws.ring_mode) fence_proxy_async();   // generic reads of the ring precede later bulk copies
+}
+
+// helper CTA (cluster rank >= 1, float32): serves the leader until SFX_WIDE_EXIT.  `dyn` is the
+// block's dynamic shared memory (rows, then the per-row tables); the leader's Scratch sits at the
+// same offset of its own dynamic shared memory.
+__device__ __noinline__ void wide_helper_main(const float* __restrict__ PK, unsigned char* dyn,
+                                              size_t dyn_bytes, WideCtl* wc, int cl) {
+    SFX_ASSUME_SHARED_PTR(dyn);
+    SFX_ASSUME_SHARED_PTR(wc);
+    const int rank = (int)cluster_ctarank();
+    const int nh = cl - 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* rowbuf = reinterpret_cast<float*>(dyn);
+    unsigned char* tab = dyn + (size_t)SFX_WIDE_ROWS_MAX * SFX_KPAD * sizeof(float);
+    int* t_grow = reinterpret_cast<int*>(tab);                               // global row of PK
+    float* t_vt = reinterpret_cast<float*>(tab + 4 * SFX_WIDE_ROWS_MAX);     // template coordinate
+    float* t_dvp = reinterpret_cast<float*>(tab + 8 * SFX_WIDE_ROWS_MAX);    // adjoint weight (per pass)
+    unsigned short* t_r = reinterpret_cast<unsigned short*>(tab + 12 * SFX_WIDE_ROWS_MAX);  // slot row
+    float* t_c = rowbuf + (size_t)(SFX_WIDE_ROWS_MAX - 1) * SFX_KPAD;        // last row slot: copy of c
+    // the leader's Scratch<float>, seen through the cluster window
+    Scratch<float>* Sl = reinterpret_cast<Scratch<float>*>(dyn);
+    const uint32_t a_rows = mapa_u32(smem_u32(Sl->rows), 0), a_vid = mapa_u32(smem_u32(Sl->vid), 0);
+    const uint32_t a_vts = mapa_u32(smem_u32(Sl->vt_s), 0), a_c = mapa_u32(smem_u32(Sl->c), 0);
+    const uint32_t a_vp = mapa_u32(smem_u32(Sl->vp), 0), a_dvp = mapa_u32(smem_u32(Sl->dvp), 0);
+    // the leader's ring follows its Scratch (carve_stream): partial dc of helper `rank`
+    const uint32_t a_part = mapa_u32(smem_u32(dyn + ((sizeof(Scratch<float>) + 1023) / 1024 * 1024)), 0) +
+                            (uint32_t)(rank - 1) * SFX_KPAD * 4u;
+    const uint32_t a_done = mapa_u32(smem_u32(&wc->done_bar), 0);
+    unsigned int go_phase = 0, load_phase = 0;
+    int cnt = 0;
+    for (;;) {
+        mbar_wait_cluster(&wc->go_bar, go_phase & 1);
+        go_phase += 1;
+        const int cmd = *reinterpret_cast<volatile int*>(&wc->cmd);
+        if (cmd == SFX_WIDE_EXIT) break;
+        if (cmd == SFX_WIDE_LOAD) {
+            const int n = *reinterpret_cast<volatile int*>(&wc->n_rows);
+            const int per = (n + nh - 1) / nh;
+            const int lo = (rank - 1) * per;
+            cnt = n - lo < per ? n - lo : per;
+            if (cnt < 0) cnt = 0;
+            if (cnt > SFX_WIDE_ROWS_MAX - 1) cnt = SFX_WIDE_ROWS_MAX - 1;   // cannot happen: 675 / 7 = 97
+            __syncthreads();                       // the previous pass is done with the row buffer
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&wc->load_bar, (uint32_t)cnt * SFX_KPAD * 4u);
+            }
+            if (tid < cnt) {
+                const int r = (int)ld_cluster_u16(a_rows + 2u * (uint32_t)(lo + tid));
+                const int vid = ld_cluster_s32(a_vid + 4u * (uint32_t)(r / 3));
+                t_r[tid] = (unsigned short)r;
+                t_grow[tid] = vid * 3 + (r % 3);
+                t_vt[tid] = ld_cluster_f32(a_vts + 4u * (uint32_t)r);
+            }
+            __syncthreads();
+            if (tid < cnt)
+                bulk_g2s(rowbuf + (size_t)tid * SFX_KPAD, PK + (size_t)t_grow[tid] * SFX_KPAD,
+                         SFX_KPAD * 4u, &wc->load_bar);
+            mbar_wait(&wc->load_bar, load_phase & 1);   // (no rows: the expect_tx arrival completes it)
+            load_phase += 1;
+        } else if (cmd == SFX_WIDE_FWD) {
+            // one copy of c per helper over the cluster network (2 KiB), then this lane's 16
+            // coefficients in the element order of the streaming passes
+            t_c[tid] = ld_cluster_f32(a_c + 4u * (uint32_t)tid);
+            __syncthreads();
+            float c[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) c[4 * i + e] = t_c[(i * 32 + lane) * 4 + e];
+            for (int j = warp; j < cnt; j += SFX_NWARP) {
+                const float4* row = reinterpret_cast<const float4*>(rowbuf + (size_t)j * SFX_KPAD);
+                float acc = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = row[i * 32 + lane];
+                    acc += v.x * c[4 * i];
+                    acc += v.y * c[4 * i + 1];
+                    acc += v.z * c[4 * i + 2];
+                    acc += v.w * c[4 * i + 3];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) st_cluster_f32(a_vp + 4u * (uint32_t)t_r[j], t_vt[j] + acc);
+            }
+        } else if (cmd == SFX_WIDE_ADJ) {
+            if (tid < cnt) t_dvp[tid] = ld_cluster_f32(a_dvp + 4u * (uint32_t)t_r[tid]);
+            __syncthreads();
+            float acc = 0;
+            for (int j = 0; j < cnt; ++j) acc += rowbuf[(size_t)j * SFX_KPAD + tid] * t_dvp[j];
+            st_cluster_f32(a_part + 4u * (uint32_t)tid, acc);
+        }
+        __syncthreads();                           // every thread's remote stores are issued
+        if (tid == 0) mbar_arrive_remote(a_done);  // release.cluster: cumulative over the barrier
+    }
 }
 
 template <typename T>

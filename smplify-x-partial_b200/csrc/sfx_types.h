@@ -90,7 +90,10 @@ struct SfxStage {
 #define SFX_MAX_STAGES 8
 struct SfxPipeline {
     int n_stages;
-    int reserved;
+    int n_wide;               // "wide" frames: the first n_wide frames of the launch order are each run by a
+                              // cluster of 8 CTAs whose helpers keep the live blend rows resident in shared
+                              // memory (csrc/sfx_stream.cuh).  0 = every frame by one block (default).  Float32
+                              // only; the adjoint's summation order differs from the one-block path.
     SfxStage cam;
     SfxStage body[SFX_MAX_STAGES];
 };

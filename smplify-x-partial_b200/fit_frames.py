@@ -401,7 +401,15 @@ def upload(batch, plan):
         plan.flip_mask_dev = torch.as_tensor(mask, device=dev)
         plan.order_dev = torch.as_tensor(order, device=dev)
         n += plan.flip_ids.nbytes + mask.nbytes + order.nbytes
-    plan.pipeline = N.make_pipeline(plan.cam_stage, plan.stages)
+    # "wide" frames (csrc/sfx_stream.cuh): the frames that fit two orientations run twice as long as
+    # the rest of a batch; while the batch leaves SMs idle each of them gets a cluster of 8 CTAs
+    # (the library takes as many as fit next to the one-block frames).  cfg['wide_frames']: 'auto'
+    # (default) or 'off' (every frame by one block: the bit-reproducible reference path)
+    n_wide = 0
+    if plan.cfg.get('wide_frames', 'auto') != 'off' and plan.order_dev is not None \
+            and plan.collision is None and plan.np_dtype == np.float32:
+        n_wide = len(plan.flip_ids)
+    plan.pipeline = N.make_pipeline(plan.cam_stage, plan.stages, n_wide)
     batch.reset_counters()
     return n
 

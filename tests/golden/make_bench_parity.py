@@ -38,13 +38,23 @@ CASES = {
 }
 
 
-def one_ulp_apart(kp):
+def one_ulp_apart(kp, direction=np.inf):
     out = kp.copy()
-    out[:, :, :2] = np.nextafter(kp[:, :, :2], np.float32(np.inf))
+    out[:, :, :2] = np.nextafter(kp[:, :, :2], np.float32(direction))
     return out
 
 
+def variants(kp):
+    """The oracle's own runs of the same frames: the inputs themselves, one float32 ulp up, one
+    ulp down, and a relative 1e-6 apart."""
+    rel = kp.copy()
+    rel[:, :, :2] *= np.float32(1.0 + 1e-6)
+    return [('ref', kp), ('ref_ulp', one_ulp_apart(kp)), ('ref_ulp2', one_ulp_apart(kp, -np.inf)),
+            ('ref_ulp3', rel)]
+
+
 def main(only=None):
+    only = [o for o in (only or []) if o != 'redo']
     path = os.path.join(HERE, 'bench_parity.npz')
     out = dict(np.load(path, allow_pickle=False)) if os.path.isfile(path) else {}
     procs = os.cpu_count() or 1
@@ -56,8 +66,12 @@ def main(only=None):
         a.frames, a.seed = case['n'], case['seed']
         kp, expose, pixie = bench.make_inputs_cpu(a, cfg)
         frames = list(range(case['n']))
-        runs = []
-        for k in (kp, one_ulp_apart(kp)):
+        runs, tags = [], []
+        for tag, k in variants(kp):
+            tags.append(tag)
+            if '{}/{}/loss'.format(name, tag) in out and 'redo' not in sys.argv:
+                runs.append(None)
+                continue
             pool = bench.OraclePool(cfg, k, expose, pixie, min(procs, len(frames)))
             _, res = pool.round(frames, want_result=True)
             pool.close()
@@ -68,7 +82,9 @@ def main(only=None):
                 out[name + '/expose/' + key] = np.stack([np.asarray(e[key]) for e in expose])
             for key in ('body_pose', 'global_pose'):
                 out[name + '/pixie/' + key] = np.stack([np.asarray(p[key]) for p in pixie])
-        for tag, res in zip(('ref', 'ref_ulp'), runs):
+        for tag, res in zip(tags, runs):
+            if res is None:
+                continue
             out['{}/{}/loss'.format(name, tag)] = np.array([r['loss'] for r in res])
             out['{}/{}/vertices'.format(name, tag)] = np.stack(
                 [r['vertices'][::VSTRIDE] for r in res]).astype(np.float32)
@@ -77,7 +93,7 @@ def main(only=None):
             out['{}/{}/center'.format(name, tag)] = np.stack([r['center'] for r in res])
             out['{}/{}/evals'.format(name, tag)] = np.array([r['evals'] for r in res])
             out['{}/{}/n_orient'.format(name, tag)] = np.array([r['n_orient'] for r in res])
-        print(name, 'evals', out[name + '/ref/evals'], 'ulp', out[name + '/ref_ulp/evals'])
+        print(name, [int(out['{}/{}/evals'.format(name, t)].mean()) for t in tags])
         np.savez_compressed(path, **out)
 
 

@@ -140,10 +140,10 @@ class _Counter(object):
         bm.forward = fwd
 
 
-def ref_fit(frame='02_cropped', inputs=None, cfg=None, tag='ref_fit_02', save=True):
+def ref_fit(frame='02_cropped', inputs=None, cfg=None, tag='ref_fit_02', save=True,
+            dtype=torch.float32):
     ref = ref_bridge.load()
     cfg = cfg or cfg_combined()
-    dtype = torch.float32
     torch.manual_seed(0)
     torch.set_num_threads(1)          # bit-stable reductions
     use_vposer = bool(cfg.get('use_vposer'))
@@ -185,7 +185,7 @@ def ref_fit(frame='02_cropped', inputs=None, cfg=None, tag='ref_fit_02', save=Tr
         result = pickle.load(f)
     verts = np.load(os.path.join(tmp, 'vertices.ply.npy'))
     out = {'result/' + k: np.asarray(v) for k, v in result.items()}
-    out['vertices'] = verts.astype(np.float32)
+    out['vertices'] = verts.astype(np.float32 if dtype == torch.float32 else np.float64)
     out['n_forward_calls'] = np.array(counter.n)
     out['cfg_json'] = np.array(json.dumps({k: v for k, v in cfg.items()}))
     if save:
@@ -653,6 +653,11 @@ if __name__ == '__main__':
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'metrics':
         ref_metrics()
+        raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'fit64':
+        # float64 full fits of both demo frames: the well-conditioned end-to-end fixtures
+        ref_fit('02_cropped', inp, tag='ref_fit_02_f64', dtype=torch.float64)
+        ref_fit('18_cropped', inp, tag='ref_fit_18_f64', dtype=torch.float64)
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'coll':
         ref_eval_coll(inp, torch.float64, 'f64')

@@ -74,6 +74,7 @@ def test_pipeline_launch_equals_staged_launches():
     ref = Cm.golden('ref_fit_02.npz')
     cfg = json.loads(str(ref['cfg_json']))
     cfg['side_view_thsh'] = 1e6            # every frame fits both orientations
+    cfg['wide_frames'] = 'off'             # one block per frame: the bit-reproducible path
     model = engine.Model(Cm.model_data(), Cm.joint_map(), dtype=torch.float32, **Cm.MODEL_KW)
     frames = ['02_cropped', '18_cropped']
     data = [_frame_inputs(inp, f) for f in frames]
@@ -128,3 +129,73 @@ def test_vposer_five_stage_fit_against_reference():
     # chaotic 5-stage trajectory (DESIGN.md "Parity"): same basin, centimetre-level agreement
     assert err.mean() < 3e-2 and err.max() < 0.25
     assert 0.4 * n_ref < out.n_evals[0] < 2.5 * n_ref
+
+
+def _two_frame_plan(cfg, model, batch):
+    from smplifyx_b200 import fit_frames as FF
+    inp = Cm.golden('demo_inputs.npz')
+    data = [_frame_inputs(inp, f) for f in ('02_cropped', '18_cropped')]
+    kp = np.stack([d[0] for d in data])
+    cfg = dict(cfg)
+    cfg['side_view_thsh'] = float(np.hypot(*(kp[0, 2, :2] - kp[0, 5, :2]))) + 1.0
+    plan = FF.FitPlan(batch.L, model.K, kp, [d[1] for d in data], [d[2] for d in data], cfg,
+                      [d[3] for d in data], [d[4] for d in data], None, np.float32)
+    assert list(plan.flip_ids) == [0]
+    return plan
+
+
+def test_wide_frame_cluster_against_one_block():
+    """A frame run by a cluster of 8 CTAs (helpers keep the live blend rows resident in shared
+    memory, csrc/sfx_stream.cuh) against the same frame run by one block: the forward pass is
+    bit-identical, the adjoint sums the rows in another order, so after a handful of evaluations
+    (maxiters = 1: before the chaotic line search can amplify anything) the parameters agree to
+    float32 rounding; the wide path is deterministic run to run; the one-block frame of the same
+    launch is untouched bit for bit."""
+    from smplifyx_b200 import engine, fit_frames as FF
+    ref = Cm.golden('ref_fit_02.npz')
+    cfg = json.loads(str(ref['cfg_json']))
+    cfg['maxiters'] = 1
+    model = engine.Model(Cm.model_data(), Cm.joint_map(), dtype=torch.float32, **Cm.MODEL_KW)
+    res = {}
+    for mode in ('off', 'auto', 'auto2'):
+        batch = engine.FrameBatch(model, 2)
+        plan = _two_frame_plan(dict(cfg, wide_frames=mode[:4]), model, batch)
+        FF.upload(batch, plan)
+        assert plan.pipeline.n_wide == (0 if mode == 'off' else 1)
+        cam_loss, verts, joints, _ = FF.run(batch, plan, True)
+        res[mode] = FF.download(batch, plan, cam_loss, verts, joints)
+    off, wide, wide2 = res['off'], res['auto'], res['auto2']
+    assert wide.flags.max() == 0
+    assert np.array_equal(wide.params, wide2.params) and np.array_equal(wide.loss, wide2.loss)
+    assert np.array_equal(off.params[1], wide.params[1])          # the one-block frame
+    assert np.array_equal(off.n_evals, wide.n_evals)
+    d = np.abs(off.params[0] - wide.params[0]).max()
+    print('wide vs one block after %d evaluations: max parameter difference %.3g, loss %.9g vs %.9g'
+          % (off.n_evals[0], d, off.loss[0], wide.loss[0]))
+    assert d <= 2e-4 * max(1.0, np.abs(off.params[0]).max())
+    assert abs(off.loss[0] - wide.loss[0]) <= 1e-4 * abs(off.loss[0])
+
+
+def test_wide_frame_full_fit_stays_in_the_envelope():
+    """Full fit of the two-orientation demo frame by a cluster: inside the reference's own
+    run-to-run envelope, like the one-block path."""
+    from smplifyx_b200 import engine, fit_frames as FF
+    ref = Cm.golden('ref_fit_02.npz')
+    env = Cm.golden('ref_envelope.npz')
+    cfg = json.loads(str(ref['cfg_json']))
+    model = engine.Model(Cm.model_data(), Cm.joint_map(), dtype=torch.float32, **Cm.MODEL_KW)
+    out = {}
+    for mode in ('off', 'auto'):
+        batch = engine.FrameBatch(model, 2)
+        plan = _two_frame_plan(dict(cfg, wide_frames=mode), model, batch)
+        FF.upload(batch, plan)
+        cam_loss, verts, joints, _ = FF.run(batch, plan, True)
+        out[mode] = FF.download(batch, plan, cam_loss, verts, joints)
+    a, b = out['off'], out['auto']
+    assert b.flags.max() == 0
+    err = np.abs(a.vertices[0] - b.vertices[0])
+    print('wide vs one-block full fit: vertex max %.4g mean %.4g m, evals %d vs %d, loss %.6g vs %.6g'
+          % (err.max(), err.mean(), a.n_evals[0], b.n_evals[0], a.loss[0], b.loss[0]))
+    assert err.max() <= 2 * float(env['fit/vertex_pairwise_max'])
+    assert err.mean() <= 2 * float(env['fit/vertex_pairwise_mean'])
+    assert 0.6 * a.n_evals[0] <= b.n_evals[0] <= 1.6 * a.n_evals[0]
