@@ -364,11 +364,10 @@ __global__ void __launch_bounds__(SFX_THREADS, 1)
 fit_pipeline_kernel(const __grid_constant__ ModelView<T> Mp, const __grid_constant__ BatchView<T> Bv,
                     const SfxPipeline* __restrict__ P, const unsigned char* __restrict__ flip,
                     int n_frames, int* counter, int ring_mode, T* cam_loss_out, T* params_last,
-                    int wide_cl, int dyn_bytes) {
+                    int wide_cl, int dyn_bytes, T* alt_rows) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(smem);
     __shared__ BlockCtx<T> C;
-    __shared__ T alt[SFX_NP_MAX];
     __shared__ WideCtl wctl;
     const ModelView<T>& M = C.M;
     StreamWS& ws = C.ws;
@@ -429,6 +428,7 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> Mp, const __grid_consta
         if (idx >= n_frames) break;
         const int f = Bv.frame_ids ? Bv.frame_ids[idx] : idx;
         load_frame(Bv, f, S);
+        T* alt = alt_rows + (size_t)f * np;      // first orientation's result (global: one row per frame)
         SFX_PROF_BEGIN(total);
         support_begin_frame(M, S);
         if (threadIdx.x == 0) {
@@ -1110,7 +1110,7 @@ int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order
         CUDA_TRY(cudaLaunchKernelEx(&cfg, fit_pipeline_kernel<float>, b->m->vf, b->view<float>(order_dev),
                                     (const SfxPipeline*)b->pipe.p, flip_dev, n_wide, (int*)b->counter.p + 1, rm,
                                     (float*)b->cam_loss.p, (float*)b->params_last.p, (int)SFX_WIDE_CLUSTER,
-                                    (int)smem));
+                                    (int)smem, (float*)b->params_alt.p));
         const int n_main = b->B - n_wide;
         if (n_main > 0) {
             // same stream, allowed to overlap the wide grid (which triggers at its very start):
@@ -1129,7 +1129,7 @@ int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order
             CUDA_TRY(cudaLaunchKernelEx(&cm, fit_pipeline_kernel<float>, b->m->vf,
                                         b->view<float>(order_dev + n_wide), (const SfxPipeline*)b->pipe.p,
                                         flip_dev, n_main, (int*)b->counter.p, rm, (float*)b->cam_loss.p,
-                                        (float*)b->params_last.p, 1, (int)smem));
+                                        (float*)b->params_last.p, 1, (int)smem, (float*)b->params_alt.p));
         }
         CUDA_TRY(cudaGetLastError());
         b->last_valid = true;
@@ -1141,13 +1141,15 @@ int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order
         CUDA_TRY(cudaFuncSetAttribute(fit_pipeline_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fit_pipeline_kernel<double><<<grid, SFX_THREADS, smem, s>>>(
             b->m->vd, b->view<double>(order_dev), (const SfxPipeline*)b->pipe.p, flip_dev, b->B,
-            (int*)b->counter.p, rm, (double*)b->cam_loss.p, (double*)b->params_last.p, 1, (int)smem);
+            (int*)b->counter.p, rm, (double*)b->cam_loss.p, (double*)b->params_last.p, 1, (int)smem,
+            (double*)b->params_alt.p);
     } else {
         size_t smem = fit_smem<float>(rm);
         CUDA_TRY(cudaFuncSetAttribute(fit_pipeline_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fit_pipeline_kernel<float><<<grid, SFX_THREADS, smem, s>>>(
             b->m->vf, b->view<float>(order_dev), (const SfxPipeline*)b->pipe.p, flip_dev, b->B,
-            (int*)b->counter.p, rm, (float*)b->cam_loss.p, (float*)b->params_last.p, 1, (int)smem);
+            (int*)b->counter.p, rm, (float*)b->cam_loss.p, (float*)b->params_last.p, 1, (int)smem,
+            (float*)b->params_alt.p);
     }
     CUDA_TRY(cudaGetLastError());
     b->last_valid = true;

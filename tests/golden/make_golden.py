@@ -655,9 +655,24 @@ if __name__ == '__main__':
         ref_metrics()
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'fit64':
-        # float64 full fits of both demo frames: the well-conditioned end-to-end fixtures
-        ref_fit('02_cropped', inp, tag='ref_fit_02_f64', dtype=torch.float64)
-        ref_fit('18_cropped', inp, tag='ref_fit_18_f64', dtype=torch.float64)
+        # float64 full fits of both demo frames: the well-conditioned end-to-end fixtures.  No
+        # regression prior: the reference builds that prior with torch.tensor(<float32 array>)
+        # (fit_single_frame.py:211-235), so its pose embedding stays a float32 parameter even in a
+        # float64 run and is re-quantised by every optimiser update.  The un-initialised flow with
+        # the mixture prior (pose_embedding = body_pose_prior.get_mean(), :250-252; guess_init
+        # camera) is float64 throughout.
+        cfg = cfg_combined()
+        gdir = tempfile.mkdtemp()
+        with open(os.path.join(gdir, 'gmm_08.pkl'), 'wb') as f:
+            pickle.dump(synthetic.make_gmm_like(seed=1, num_gaussians=8, dim=63), f)
+        cfg.update(regression_prior=None, use_camera_prior=False, body_prior_type='gmm',
+                   prior_folder=gdir, num_gaussians=8, float_dtype='float64')
+        for fr, tag in (('02_cropped', 'ref_fit_02_f64'), ('18_cropped', 'ref_fit_18_f64')):
+            out = ref_fit(fr, inp, cfg=cfg, tag=tag, dtype=torch.float64, save=False)
+            c = json.loads(str(out['cfg_json']))
+            c.pop('prior_folder')
+            out['cfg_json'] = np.array(json.dumps(c))
+            np.savez_compressed(os.path.join(HERE, tag + '.npz'), **out)
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'coll':
         ref_eval_coll(inp, torch.float64, 'f64')

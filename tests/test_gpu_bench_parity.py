@@ -7,11 +7,8 @@ float32 fits are chaotic: the fixture also holds the oracle's OWN fit of the sam
 from keypoints one float32 ulp apart, and the thresholds below are set from that
 oracle-vs-oracle envelope (measured per workload), not from a guess:
 
-    workload   loss rel median / max     mean vertex distance median / max
-    cfg2       3.3e-2 / 0.27             10 mm / 50 mm
-    cfg2_reg   4.2e-3 / 0.20             2.1 mm / 32 mm
-    cfg3       4.6e-2 / 1.2              21 mm / 264 mm
-    cfg5       3.1e-3 / 0.54             1.8 mm / 12 mm
+    (three further oracle runs per workload: inputs one ulp up, one ulp down, 1e-6 apart; the
+    test prints the envelope next to the engine's distances)
 """
 import numpy as np
 import pytest
@@ -71,26 +68,33 @@ def test_bench_workload_against_oracle_fit(name, kw, two_loop):
     batch = engine.FrameBatch(model, n, use_vposer=bool(kw.get('vposer')))
     out = FF.fit_frames(batch, kp, H_IMG, W_IMG, cfg, expose, pixie, return_verts=True, vposer=vp)
     assert out.flags.max() == 0
-    ref, ulp = name + '/ref/', name + '/ref_ulp/'
+    ref = name + '/ref/'
+    others = [name + '/' + t + '/' for t in ('ref_ulp', 'ref_ulp2', 'ref_ulp3')]
     assert np.array_equal(out.n_orient, G[ref + 'n_orient'])       # same orientation decisions
     verts = out.vertices[:, ::VSTRIDE]
     rel, dv = _metrics(out.loss, verts, G[ref + 'loss'], G[ref + 'vertices'])
-    erel, edv = _metrics(G[ulp + 'loss'], G[ulp + 'vertices'], G[ref + 'loss'], G[ref + 'vertices'])
+    # envelope: the oracle's other runs (inputs one ulp up / down, 1e-6 apart) against its first
+    env = [_metrics(G[o + 'loss'], G[o + 'vertices'], G[ref + 'loss'], G[ref + 'vertices'])
+           for o in others]
+    erel_med = max(np.median(e[0]) for e in env)
+    erel_max = max(e[0].max() for e in env)
+    edv_med = max(np.median(e[1]) for e in env)
+    edv_max = max(e[1].max() for e in env)
+    ev = [G[ref + 'evals'].mean()] + [G[o + 'evals'].mean() for o in others]
     print('{} [{}]: loss rel median {:.3g} max {:.3g} (oracle envelope {:.3g} / {:.3g}); mean '
           'vertex distance median {:.4f} max {:.4f} m (envelope {:.4f} / {:.4f}); evals {:.0f} '
-          '(oracle {:.0f}, one ulp apart {:.0f})'.format(
-              name, two_loop, np.median(rel), rel.max(), np.median(erel), erel.max(),
-              np.median(dv), dv.max(), np.median(edv), edv.max(), out.n_evals.mean(),
-              G[ref + 'evals'].mean(), G[ulp + 'evals'].mean()))
+          '(oracle runs {})'.format(
+              name, two_loop, np.median(rel), rel.max(), erel_med, erel_max,
+              np.median(dv), dv.max(), edv_med, edv_max, out.n_evals.mean(),
+              ' '.join('%.0f' % v for v in ev)))
     # the engine sits inside the spread the reference shows against itself on these frames
-    assert np.median(rel) <= 2.0 * np.median(erel) + 2e-3
-    assert np.median(dv) <= 2.0 * np.median(edv) + 1e-3
-    assert rel.max() <= 2.0 * erel.max() + 0.05
-    assert dv.max() <= 2.0 * edv.max() + 0.01
+    # (medians over 8-16 chaotic fits: a factor 3 on the largest of the oracle's own three)
+    assert np.median(rel) <= 3.0 * erel_med + 2e-3
+    assert np.median(dv) <= 3.0 * edv_med + 1e-3
+    assert rel.max() <= 2.0 * erel_max + 0.05
+    assert dv.max() <= 2.0 * edv_max + 0.01
     # evaluation counts: same workload, same amount of work
-    lo = min(G[ref + 'evals'].mean(), G[ulp + 'evals'].mean())
-    hi = max(G[ref + 'evals'].mean(), G[ulp + 'evals'].mean())
-    assert 0.75 * lo <= out.n_evals.mean() <= 1.25 * hi
+    assert 0.75 * min(ev) <= out.n_evals.mean() <= 1.25 * max(ev)
     # reprojected keypoints are the well-conditioned quantity: medians within a pixel
     focal = float(cfg.get('focal_length') or np.sqrt(H_IMG ** 2 + W_IMG ** 2))
     cam_t = np.stack([r['camera_translation'].reshape(3) for r in out.results])
@@ -99,8 +103,10 @@ def test_bench_workload_against_oracle_fit(name, kw, two_loop):
     po = _project(G[ref + 'joints'], G[ref + 'cam_t'], G[ref + 'center'], focal)
     live = kp[:, :, 2] > 0
     dpx = np.sqrt(((pe - po) ** 2).sum(-1))
-    pu = _project(G[ulp + 'joints'], G[ulp + 'cam_t'], G[ulp + 'center'], focal)
-    epx = np.sqrt(((pu - po) ** 2).sum(-1))
+    epx = 0.0
+    for o in others:
+        pu = _project(G[o + 'joints'], G[o + 'cam_t'], G[o + 'center'], focal)
+        epx = max(epx, float(np.median(np.sqrt(((pu - po) ** 2).sum(-1))[live])))
     print('   reprojection distance to the oracle fit: median {:.3f} px (envelope {:.3f} px)'.format(
-        np.median(dpx[live]), np.median(epx[live])))
-    assert np.median(dpx[live]) <= 2.0 * np.median(epx[live]) + 0.5
+        np.median(dpx[live]), epx))
+    assert np.median(dpx[live]) <= 2.0 * epx + 0.5
