@@ -19,6 +19,7 @@
 #include "sfx_stream.cuh"
 #include "sfx_mesh.cuh"
 #include "sfx_mesh_tc.cuh"
+#include "sfx_mesh_fused.cuh"
 #include "sfx_metrics.cuh"
 
 using namespace sfx;
@@ -577,6 +578,8 @@ struct sfx_model {
     int device = 0;
     int num_sms = 0;
     MeshPlan mesh;        // TMA descriptor of the blend matrix for the tensor-core mesh kernel
+    FusedPlan fused;      // descriptors of the fused blend + skinning kernel (sfx_mesh_fused.cuh)
+    DevBuf whi, wlo;      // skinning weights [Vpad][64], tf32 hi / lo split
 };
 
 template <typename T>
@@ -625,7 +628,7 @@ struct sfx_batch {
     SfxLayout lay;
     size_t es = 4;        // element size of the batch dtype
     DevBuf params, gt, conf, jw, lowconf, init_mask, cam, reg_pose, hist_s, hist_y, gram, final_loss,
-        n_evals, n_passes, flags, Acoef, Ccoef, vposed, go_saved, params_alt, loss_alt, pipe, counter,
+        n_evals, n_passes, flags, Acoef, Ccoef, vposed, ahi, alo, go_saved, params_alt, loss_alt, pipe, counter,
         cam_loss, params_last, prof, coll_vals, coll_idx, coll_stat;
     bool last_valid = false;
     bool has_reg = false;
@@ -722,6 +725,20 @@ int sfx_model_create(const sfx_model_desc* desc, sfx_model** out) {
     int rc = m->use_double ? upload_model<double>(*desc, m, m->vd) : upload_model<float>(*desc, m, m->vf);
     if (rc == SFX_OK && !m->use_double) {
         std::string e = mesh_plan_create(m->mesh, (const float*)m->PK.p, m->V);
+        if (e.empty()) {
+            // skinning weights for the tensor-core kernel: 64 padded joints, split x = hi + lo
+            const int Vpad = (m->V + FU_TV - 1) / FU_TV * FU_TV;
+            std::vector<float> whi((size_t)Vpad * FU_WJ, 0.f), wlo((size_t)Vpad * FU_WJ, 0.f);
+            for (int v = 0; v < m->V; ++v)
+                for (int j = 0; j < SFX_NJ; ++j)
+                    tf32_split(desc->lbs_weights[(size_t)v * SFX_NJ + j], &whi[(size_t)v * FU_WJ + j],
+                               &wlo[(size_t)v * FU_WJ + j]);
+            cudaError_t ce = m->whi.upload(whi);
+            if (ce == cudaSuccess) ce = m->wlo.upload(wlo);
+            if (ce != cudaSuccess) e = std::string("upload skinning weights: ") + cudaGetErrorString(ce);
+            else e = fused_plan_create(m->fused, (const float*)m->PK.p, m->V, (const float*)m->whi.p,
+                                       (const float*)m->wlo.p, Vpad);
+        }
         if (!e.empty()) rc = fail(SFX_ERR_CUDA, e);
     }
     if (rc != SFX_OK) {
@@ -851,6 +868,8 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     ALLOC(Acoef, (size_t)B * SFX_NJ * 12 * es);
     ALLOC(Ccoef, (size_t)mesh_padded_frames(B) * SFX_KPAD * es);
     ALLOC(vposed, (size_t)mesh_padded_frames(B) * 3 * m->V * es);
+    ALLOC(ahi, (size_t)mesh_padded_frames(B) * 12 * FU_WJ * sizeof(float));
+    ALLOC(alo, (size_t)mesh_padded_frames(B) * 12 * FU_WJ * sizeof(float));
     ALLOC(go_saved, (size_t)B * 3 * es);
     ALLOC(params_alt, (size_t)B * b->lay.np * es);
     ALLOC(loss_alt, (size_t)B * es);
@@ -1227,11 +1246,17 @@ static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev,
         // blend contraction: tcgen05 / TMA kernel (SFX_MESH_SIMT=1 selects the fp32 SIMT kernel,
         // the accuracy reference of the tf32 path); skinning: SIMT epilogue kernel
         const char* simt = getenv("SFX_MESH_SIMT");
+        const char* unfused = getenv("SFX_MESH_UNFUSED");
         std::string e;
         if (simt && simt[0] == '1') {
             e = mesh_forward_simt<float>(m->vf, b->B, (const float*)b->Acoef.p,
                                          (const float*)b->Ccoef.p, (float*)b->vposed.p,
                                          (float*)vertices_dev, s);
+        } else if (!(unfused && unfused[0] == '1')) {
+            // one tensor-core kernel: blend (tf32) + skinning (3 x tf32) + transform epilogue
+            e = mesh_fused_tc(m->fused, b->B, (const float*)b->Ccoef.p, (const float*)b->Acoef.p,
+                              (float*)b->ahi.p, (float*)b->alo.p, (const float*)m->vt.p,
+                              (float*)vertices_dev, s);
         } else {
             e = mesh_blend_tc(m->mesh, b->B, (const float*)b->Ccoef.p, (const float*)m->vt.p,
                               (float*)b->vposed.p, s);

@@ -177,9 +177,11 @@ def test_two_loop_variants_agree(model32, monkeypatch):
 
 
 def test_tensor_core_mesh_against_simt(model32, monkeypatch):
-    """tcgen05 / TMA blend kernel (tf32 inputs, fp32 accumulation) against the fp32 SIMT kernel
-    on 130 frames (two frame tiles, ragged) with distinct parameters: the tf32 rounding of the
-    inputs bounds the vertex error by ~1e-4 m; structure errors would be centimetres."""
+    """Fused tcgen05 / TMA mesh kernel (blend in tf32, skinning in 3 x tf32, fp32 accumulation in
+    tensor memory; csrc/sfx_mesh_fused.cuh) and the round-1 pair (tcgen05 blend + SIMT skinning)
+    against the fp32 SIMT kernel on 130 frames (two frame tiles, ragged) with distinct
+    parameters: the tf32 rounding of the blend inputs bounds the vertex error by ~1e-4 m;
+    structure errors would be centimetres."""
     ev = Cm.golden('ref_eval_f32.npz')
     I = Cm.eval_case_inputs(ev, 'l2')
     B = 130
@@ -189,13 +191,19 @@ def test_tensor_core_mesh_against_simt(model32, monkeypatch):
     batch = _engine().FrameBatch(model32, B)
     _load(batch, I, B)
     batch.set_params(x)
-    v_tc, j_tc = batch.forward_mesh()
+    v_tc, j_tc = batch.forward_mesh()              # fused kernel: blend + skinning on tcgen05
+    monkeypatch.setenv('SFX_MESH_UNFUSED', '1')
+    v_un, _ = batch.forward_mesh()                 # tcgen05 blend kernel + SIMT skinning kernel
+    monkeypatch.delenv('SFX_MESH_UNFUSED')
     monkeypatch.setenv('SFX_MESH_SIMT', '1')
     v_simt, j_simt = batch.forward_mesh()
     err = (v_tc - v_simt).abs().max().item()
+    print('fused tensor-core mesh vs float32 SIMT: max %.3g m, mean %.3g m; unfused: max %.3g m'
+          % (err, (v_tc - v_simt).abs().mean().item(), (v_un - v_simt).abs().max().item()))
     assert torch.isfinite(v_tc).all()
     assert err < 2e-4, err
     assert (v_tc - v_simt).abs().mean().item() < 2e-5
+    assert (v_un - v_simt).abs().max().item() < 2e-4
     assert torch.equal(j_tc, j_simt)
     # frames are distinct: a tile / lane mix-up would not pass
     assert (v_simt[0] - v_simt[129]).abs().max().item() > 1e-2
