@@ -46,12 +46,13 @@ METRIC = 'frames/sec (full multi-stage fit, 127 body kpts)'
 UNIT = 'frames/s'
 SUPPORT_ROWS = 225 * 3
 ROW_BYTES = 512 * 4
-# dram__bytes_read.sum + dram__bytes_write.sum of one fit_pipeline_kernel<float> launch of the
-# default workload (128 frames), from the `ncu --set full` capture summarised in
-# profiles/r01v_ncu_raw_pipeline_kernel.csv (Gram two-loop: 10.88 MB read + 13.70 MB written; the
-# per-frame Gram blocks add 80 KB per frame) and profiles/r01p_... (exact recursion: 7.22 + 5.38 MB)
+# dram__bytes_read.sum + dram__bytes_write.sum of the fit_pipeline_kernel<float> launches of one
+# step (128 frames), from `ncu --set full` captures summarised under profiles/ (the per-frame Gram
+# blocks of the Gram two-loop add 80 KB per frame; `_reg` = the --regression-prior workload)
 NCU_TRAFFIC_BYTES = {'gram_reg': (24584448.0, 'profiles/r01v_ncu_raw_pipeline_kernel.csv'),
-                     'exact_reg': (12591616.0, 'profiles/r01p_ncu_raw_pipeline_kernel.csv')}
+                     'exact_reg': (12591616.0, 'profiles/r01p_ncu_raw_pipeline_kernel.csv'),
+                     # default workload, round 2: one-block grid 11.02 + 13.34 MB, wide grid 2.24 + 0.06 MB
+                     'gram': (26652928.0, 'profiles/r02l_ncu_raw_pipeline_kernel.csv')}
 
 
 # ------------------------------------------------------------------------------ workload

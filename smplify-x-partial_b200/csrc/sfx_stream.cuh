@@ -842,6 +842,10 @@ __device__ __forceinline__ void st_cluster_s32(uint32_t a, int v) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Polls without ordering semantics and orders once after the phase has completed: an acquire at
+// cluster scope invalidates the SM's L1 (CCTL.IVALL in SASS), which inside the polling loop cost the
+// leader its cached model tables on every poll (20 % of the wide grid's stall samples,
+// profiles/r02l_ncu_source_hotspots_pipeline_kernel.txt).
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     const uint32_t addr = smem_u32(bar);
@@ -849,13 +853,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
     } while (!done);
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n"
