@@ -198,6 +198,32 @@ int sfx_aligned_errors(const void* est_dev, const void* gt_dev, const int32_t* i
                        int32_t N, int32_t n, int32_t mode, int32_t hip0, int32_t hip1,
                        int32_t use_double, void* err_dev, void* transform_dev, void* stream);
 
+/* Keypoint ingestion on the device (all pointers device memory, float32 detections).
+ * sfx_pack_keypoints: read_keypoints of data_parser.py:57-104 without the JSON parsing -- the raw
+ * OpenPose blocks body [B,n_body,3], hands [B,21,3] each and face [B,n_face >= 68,3] become
+ * out [B,K,3], rows body | left hand | right hand | face[17:68] | face[0:17] (the last block only
+ * with use_face_contour), K = n_body + 42 + 51 (+ 17). */
+int sfx_pack_keypoints(const float* body_dev, const float* lhand_dev, const float* rhand_dev,
+                       const float* face_dev, int32_t B, int32_t n_body, int32_t n_face,
+                       int32_t use_face_contour, float* out_dev, void* stream);
+/* fit_single_frame.py:276-294 for B frames: keypoints [B,K,3] -> gt [B,K,2], conf [B,K] and
+ * joint weights [B,K] in the batch dtype (use_double), the low-confidence mask (conf <
+ * confidence_threshold on the first n_body rows, < 0 elsewhere) and the trimmed camera-init
+ * joints (listed, detected, not low-confidence): the arguments of sfx_batch_set_targets_dev.
+ * base_joint_weights [K] = dataset.get_joint_weights() (data_parser.py:159-171). */
+int sfx_keypoint_masks(const float* keypoints_dev, const float* base_joint_weights_dev,
+                       const int32_t* init_joints_idxs_dev, int32_t n_init, int32_t n_body,
+                       float confidence_threshold, int32_t B, int32_t K, int32_t use_double, void* gt_dev,
+                       void* conf_dev, void* joint_weights_dev, uint8_t* lowconf_dev, uint8_t* init_mask_dev,
+                       void* stream);
+/* keypoints_blending.py:337-369 for B frames: OpenPose [B,135,3] and MMPose [B,136,3] detections
+ * in raw order -> blended [B,135,3].  stats [4][n_pairs]: mmpose means, mmpose stds, openpose
+ * means, openpose stds of the n_pairs (<= 67) keypoints either detector can supply, whose rows
+ * are pair_mmpose / pair_openpose; face rows 67..134 come from OpenPose. */
+int sfx_blend_keypoints(const float* openpose_dev, const float* mmpose_dev, const float* stats_dev,
+                        const int32_t* pair_mmpose_dev, const int32_t* pair_openpose_dev, int32_t n_pairs,
+                        int32_t B, float* out_dev, void* stream);
+
 /* Diagnostic, no counterpart in the reference: measured L2 -> SM read bandwidth (GB/s) of the
  * current device -- every SM sweeping one L2-resident buffer of buffer_bytes, iters times.  The
  * benchmark reports the fit kernel's blend-row traffic (rows shared by all frames, served from

@@ -21,6 +21,7 @@
 #include "sfx_mesh_tc.cuh"
 #include "sfx_mesh_fused.cuh"
 #include "sfx_metrics.cuh"
+#include "sfx_ingest.cuh"
 
 using namespace sfx;
 
@@ -1176,6 +1177,54 @@ int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order
 }
 
 void* sfx_batch_cam_loss_dev(sfx_batch* b) { return b ? b->cam_loss.p : nullptr; }
+int sfx_pack_keypoints(const float* body_dev, const float* lhand_dev, const float* rhand_dev,
+                       const float* face_dev, int32_t B, int32_t n_body, int32_t n_face,
+                       int32_t use_face_contour, float* out_dev, void* stream) {
+    if (!body_dev || !lhand_dev || !rhand_dev || !face_dev || !out_dev || B < 1 || n_body < 1 || n_face < 68)
+        return fail(SFX_ERR_ARG, "bad argument");
+    const int K = n_body + 42 + 51 + (use_face_contour ? 17 : 0);
+    const int n = B * K;
+    pack_keypoints_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        body_dev, lhand_dev, rhand_dev, face_dev, B, n_body, n_face, use_face_contour, K, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return SFX_OK;
+}
+
+int sfx_keypoint_masks(const float* keypoints_dev, const float* base_joint_weights_dev,
+                       const int32_t* init_joints_idxs_dev, int32_t n_init, int32_t n_body,
+                       float confidence_threshold, int32_t B, int32_t K, int32_t use_double, void* gt_dev,
+                       void* conf_dev, void* joint_weights_dev, uint8_t* lowconf_dev, uint8_t* init_mask_dev,
+                       void* stream) {
+    if (!keypoints_dev || !base_joint_weights_dev || (n_init > 0 && !init_joints_idxs_dev) || !gt_dev ||
+        !conf_dev || !joint_weights_dev || !lowconf_dev || !init_mask_dev || B < 1 || K < 1 || n_init < 0)
+        return fail(SFX_ERR_ARG, "bad argument");
+    const int n = B * K;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (use_double)
+        keypoint_masks_kernel<double><<<(n + 255) / 256, 256, 0, s>>>(
+            keypoints_dev, base_joint_weights_dev, init_joints_idxs_dev, n_init, n_body, confidence_threshold,
+            B, K, (double*)gt_dev, (double*)conf_dev, (double*)joint_weights_dev, lowconf_dev, init_mask_dev);
+    else
+        keypoint_masks_kernel<float><<<(n + 255) / 256, 256, 0, s>>>(
+            keypoints_dev, base_joint_weights_dev, init_joints_idxs_dev, n_init, n_body, confidence_threshold,
+            B, K, (float*)gt_dev, (float*)conf_dev, (float*)joint_weights_dev, lowconf_dev, init_mask_dev);
+    CUDA_TRY(cudaGetLastError());
+    return SFX_OK;
+}
+
+int sfx_blend_keypoints(const float* openpose_dev, const float* mmpose_dev, const float* stats_dev,
+                        const int32_t* pair_mmpose_dev, const int32_t* pair_openpose_dev, int32_t n_pairs,
+                        int32_t B, float* out_dev, void* stream) {
+    if (!openpose_dev || !mmpose_dev || !stats_dev || !pair_mmpose_dev || !pair_openpose_dev || !out_dev ||
+        B < 1 || n_pairs < 1 || n_pairs > 67)
+        return fail(SFX_ERR_ARG, "bad argument");
+    const int n = B * (n_pairs + 68);
+    blend_keypoints_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        openpose_dev, mmpose_dev, stats_dev, pair_mmpose_dev, pair_openpose_dev, n_pairs, B, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return SFX_OK;
+}
+
 int sfx_diag_l2_read_gbs(int64_t buffer_bytes, int32_t iters, double* gbs_out) {
     if (!gbs_out || buffer_bytes < (1 << 20) || iters < 1) return fail(SFX_ERR_ARG, "bad argument");
     int dev = 0, sms = 0;

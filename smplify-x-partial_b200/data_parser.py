@@ -120,3 +120,26 @@ class KeypointDataset(object):
 
 def create_dataset(format='coco25', data_folder='data', **kwargs):
     return KeypointDataset(data_folder, fmt=format, **kwargs)
+
+
+# ------------------------------------------------------------------------------ device path
+def pack_keypoints_device(body, left_hand, right_hand, face, use_face_contour=True, device=None):
+    """``read_keypoints`` without the JSON parsing, on the device (libsfx ``sfx_pack_keypoints``):
+    raw OpenPose blocks of B frames -- body [B,n_body,3], hands [B,21,3], face [B,>=68,3]
+    (numpy or CUDA tensors, float32) -> CUDA tensor [B,K,3] in the reference's row order."""
+    import ctypes as C
+    from . import _native as N
+    lib = N.load_library()
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32) if not torch.is_tensor(a) else a,
+                                  dtype=torch.float32, device=dev).contiguous()
+    body, lh, rh, face = t(body), t(left_hand), t(right_hand), t(face)
+    B, nb, nf = body.shape[0], body.shape[1], face.shape[1]
+    K = nb + 42 + 51 + (17 if use_face_contour else 0)
+    out = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
+    p = lambda x: C.c_void_p(x.data_ptr())
+    with torch.cuda.device(dev):
+        N.check(lib, lib.sfx_pack_keypoints(p(body), p(lh), p(rh), p(face), B, nb, nf,
+                                            int(bool(use_face_contour)), p(out),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out

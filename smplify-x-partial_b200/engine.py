@@ -181,6 +181,45 @@ class FrameBatch(object):
                 self.h, _ptr(gt), _ptr(conf), _ptr(joint_weights), _ptr(lowconf), _ptr(init_mask),
                 _ptr(cam), _ptr(reg_pose)))
 
+    def set_targets_from_keypoints(self, keypoints, base_joint_weights, init_joints_idxs, n_body,
+                                   confidence_threshold, cam, reg_pose=None):
+        """Device ingestion (``sfx_keypoint_masks``, fit_single_frame.py:276-294): keypoints
+        [B,K,3] float32 (numpy, copied once, or a CUDA tensor) -> gt / conf / joint weights /
+        low-confidence mask / trimmed init joints computed on the device and installed as the
+        batch targets.  Returns the host->device byte count."""
+        B, K = self.B, self.model.K
+        dev, dt = self.model.device, self.model.dtype
+        nbytes = 0
+        if torch.is_tensor(keypoints) and keypoints.is_cuda:
+            kp = keypoints.to(torch.float32).contiguous()
+        else:
+            kp_h = self._host(keypoints, (B, K, 3), np.float32)
+            kp = torch.as_tensor(kp_h, device=dev)
+            nbytes += kp_h.nbytes
+        if tuple(kp.shape) != (B, K, 3):
+            raise ValueError('expected keypoints [{}, {}, 3]'.format(B, K))
+        bjw = torch.as_tensor(np.asarray(base_joint_weights, dtype=np.float32).reshape(K), device=dev)
+        idx = torch.as_tensor(np.asarray(init_joints_idxs, dtype=np.int32).reshape(-1), device=dev)
+        cm_h = self._host(cam, (B, N.SFX_CAM_STRIDE))
+        cm = torch.as_tensor(cm_h, device=dev)
+        rp = None
+        if reg_pose is not None:
+            rp_h = self._host(reg_pose, (B, self.L.n_pose))
+            rp = torch.as_tensor(rp_h, device=dev)
+            nbytes += rp_h.nbytes
+        nbytes += bjw.numel() * 4 + idx.numel() * 4 + cm_h.nbytes
+        gt, conf, jw = self._new(B, K, 2), self._new(B, K), self._new(B, K)
+        low = torch.empty((B, K), dtype=torch.uint8, device=dev)
+        init = torch.empty((B, K), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib, self.lib.sfx_keypoint_masks(
+                _ptr(kp), _ptr(bjw), _ptr(idx), int(idx.numel()), int(n_body),
+                float(confidence_threshold), B, K, int(dt == torch.float64), _ptr(gt), _ptr(conf),
+                _ptr(jw), _ptr(low), _ptr(init), _stream()))
+        self.set_targets_dev(gt, conf, jw, low, init, cm, rp)
+        self._keep_dev = (kp, gt, conf, jw, low, init, cm, rp)
+        return nbytes
+
     def set_params(self, params):
         x = self._host(params, (self.B, self.L.np))
         self._keep_x = x

@@ -365,6 +365,19 @@ class FitPlan(object):
         self.flip_ids = np.flatnonzero(sh < cfg.get('side_view_thsh', 25.)).astype(np.int32)
 
 
+def _set_targets(batch, plan):
+    """Targets of the batch: the host-built masks (default), or with cfg['device_ingest'] the
+    keypoints alone, split / thresholded / masked on the device (sfx_keypoint_masks) -- both give
+    the same bits (tests/test_gpu_ingest.py)."""
+    cfg = plan.cfg
+    if cfg.get('device_ingest', False):
+        nb = U.NUM_BODY_KEYPOINTS[cfg.get('format', 'coco25')]
+        return batch.set_targets_from_keypoints(
+            plan.keypoints, base_joint_weights(cfg, plan.K), cfg.get('init_joints_idxs', (9, 12, 2, 5)),
+            nb, cfg.get('confidence_threshold', 0), plan.cam, plan.reg)
+    return batch.set_targets(plan.keypoints, plan.jw, plan.lowconf, plan.init_mask, plan.cam, plan.reg)
+
+
 def upload(batch, plan):
     """Host -> device copies of one batch (async on the current stream); returns the byte count."""
     import torch
@@ -376,7 +389,7 @@ def upload(batch, plan):
         ff = plan.collision
         batch.model.set_collision(ff.faces_segm, ff.faces_parents, ff.ign_part_pairs)
         batch.enable_collisions()
-    n = batch.set_targets(plan.keypoints, plan.jw, plan.lowconf, plan.init_mask, plan.cam, plan.reg)
+    n = _set_targets(batch, plan)
     n += batch.set_params(plan.x0)
     if plan.need_guess:
         # guess_init needs the model joints at the initial parameters (fitting.py:36-110)
@@ -387,8 +400,7 @@ def upload(batch, plan):
         g = plan.need_guess
         plan.x0[g, L.off_camt:L.off_camt + 3] = t[g].astype(plan.np_dtype)
         plan.cam[:, N.SFX_CAM_TZ] = plan.x0[:, L.off_camt + 2]
-        n += batch.set_targets(plan.keypoints, plan.jw, plan.lowconf, plan.init_mask, plan.cam,
-                               plan.reg)
+        n += _set_targets(batch, plan)
         n += batch.set_params(plan.x0)
     plan.flip_dev = plan.flip_mask_dev = plan.order_dev = None
     if len(plan.flip_ids):

@@ -75,6 +75,35 @@ def blend_keypoints(openpose, mmpose, stats):
     return out
 
 
+def blend_keypoints_device(openpose, mmpose, stats, device=None):
+    """``blend_keypoints`` on the device (libsfx ``sfx_blend_keypoints``; float32 arithmetic
+    without fused multiply-adds, so the result equals the numpy version bit for bit):
+    openpose [B,135,3], mmpose [B,136,3] (numpy or CUDA tensors) -> CUDA tensor [B,135,3]."""
+    import ctypes as C
+    import torch
+    from . import _native as N
+    lib = N.load_library()
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32) if not torch.is_tensor(a) else a,
+                                  dtype=torch.float32, device=dev).contiguous()
+    op, mm = t(openpose), t(mmpose)
+    if op.shape[-2:] != (135, 3) or mm.shape[-2:] != (136, 3) or op.shape[0] != mm.shape[0]:
+        raise ValueError('expected openpose [B, 135, 3] and mmpose [B, 136, 3]')
+    pairs = blended_pairs()
+    st = np.stack([[stats[key][p[0]] for p in pairs] for key in
+                   ('mmpose_means', 'mmpose_stds', 'openpose_means', 'openpose_stds')]).astype(np.float32)
+    st_d = torch.as_tensor(st, device=dev).contiguous()
+    mi = torch.as_tensor(np.array([p[1] for p in pairs], dtype=np.int32), device=dev)
+    oi = torch.as_tensor(np.array([p[2] for p in pairs], dtype=np.int32), device=dev)
+    out = torch.zeros((op.shape[0], 135, 3), dtype=torch.float32, device=dev)
+    ptr = lambda x: C.c_void_p(x.data_ptr())
+    with torch.cuda.device(dev):
+        N.check(lib, lib.sfx_blend_keypoints(ptr(op), ptr(mm), ptr(st_d), ptr(mi), ptr(oi), len(pairs),
+                                             int(op.shape[0]), ptr(out),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out
+
+
 def read_raw_keypoints(keypoint_fn):
     """Person 0 of an OpenPose-style JSON in raw order: body | left hand | right hand | first 68
     face points (keypoints_blending.py:225-274 with its default ``orders``)."""
