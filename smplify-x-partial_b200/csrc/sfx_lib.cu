@@ -840,6 +840,13 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     sfx_batch* b = new sfx_batch();
     b->m = m; b->B = B; b->use_vposer = use_vposer;
     b->lay = make_layout(m->NB, m->NE, m->NH, use_vposer);
+    if (b->lay.np > SFX_NP_MAX) {
+        // e.g. use_pca = False (45 + 45 hand components) with 25+ shape / expression coefficients
+        const int np = b->lay.np;
+        delete b;
+        return fail(SFX_ERR_UNSUPPORTED, "parameter vector of " + std::to_string(np) + " entries exceeds SFX_NP_MAX (" +
+                    std::to_string(SFX_NP_MAX) + "): use fewer shape / expression coefficients or hand PCA");
+    }
     b->es = m->use_double ? 8 : 4;
     const size_t es = b->es, K = m->K;
 #define ALLOC(buf, n)                                                         \

@@ -101,6 +101,29 @@ class KeypointDataset(object):
             out['gender_gt'] = ggt
         return out
 
+    def read_meta(self, img_path):
+        """``read_item`` without the pixels: the fit only ever uses the image's height and width
+        (main.py:208-214), so the batched driver reads the header instead of decoding (and
+        keeping, 25 MB per 1080p frame) every image of the folder.  -> {} or dict(fn, img_path,
+        keypoints [P,K,3], H, W)."""
+        fn = os.path.splitext(os.path.basename(img_path))[0]
+        matches = glob.glob(os.path.join(self.keyp_folder, fn + '_*.json'))
+        if not matches:
+            return {}
+        people, gpd, ggt = read_keypoints(matches[0], use_hands=self.use_hands,
+                                          use_face=self.use_face,
+                                          use_face_contour=self.use_face_contour)
+        if len(people) < 1:
+            return {}
+        try:
+            from PIL import Image
+            with Image.open(img_path) as im:
+                W, H = im.size
+        except Exception:
+            import cv2
+            H, W = cv2.imread(img_path).shape[:2]
+        return {'fn': fn, 'img_path': img_path, 'keypoints': np.stack(people), 'H': int(H), 'W': int(W)}
+
     def __getitem__(self, idx):
         return self.read_item(self.img_paths[idx])
 

@@ -377,6 +377,7 @@ class FittingMonitor(object):
             bundle.push()
             st, blocks = bundle.make_stage(stage, optimizer, params, maxiters=self.maxiters,
                                            ftol=self.ftol, gtol=self.gtol)
+            bundle.batch.reset_counters()       # the status flags are sticky: report this stage only
             final = bundle.batch.fit_stage(st)
             bundle.pull(names=set(blocks))
             vals = final.detach().cpu().numpy().astype(np.float64)

@@ -6,8 +6,12 @@
 Same YAML keys / flags, same outputs (``<output>/results/<fn>/000.pkl``, ``vertices.ply``,
 ``conf.yaml``).  Unlike the reference, which fits image after image, the frames of the data
 folder are packed ``batch_size`` at a time and each batch is fitted in one persistent CUDA
-launch (``fit_frames.fit_frames``); with ``torchrun`` the batches are sharded over the ranks
-and the fitted parameters are all-gathered once at the end (``sharding``).
+launch (``fit_frames.fit_frames``); with ``torchrun`` the image list is sharded over the ranks
+(each rank reads only its own frames), and the fitted parameter rows are all-gathered once at the
+end (``sharding.gather_frames``): rank 0 writes ``<output>/fitted_params.npz`` (frame names,
+[n, np] parameter table, layout offsets) next to the per-frame pickles every rank writes.
+Limits kept from round 1: model_type 'smplx' and one gender per run (the reference builds three
+gendered models, main.py:109-127; its gender classifier is out of scope).
 """
 import os
 import pickle
@@ -21,6 +25,7 @@ import yaml
 from . import body_model as BM
 from . import fit_frames as FF
 from . import sharding
+from . import _native as N
 from . import utils as U
 from .cmd_parser import parse_config
 from .data_parser import create_dataset
@@ -82,30 +87,69 @@ def main(**args):
         from .vposer import load_vposer
         vposer, _ = load_vposer(os.path.expandvars(args.get('vposer_ckpt')), dtype=dtype)
         model.set_vposer(vposer.weights)
-    items = [d for d in dataset if d]
-    mine = sharding.shard_range(len(items), rank, world)
-    items = items[mine.start:mine.stop]
+    # The image paths are sharded first and read batch by batch: keypoints + image size only
+    # (the reference streams one decoded image at a time, main.py:207; nothing but H and W of the
+    # pixels is used by the fit).
+    paths = list(dataset.img_paths)
+    mine = sharding.shard_range(len(paths), rank, world)
+    paths = paths[mine.start:mine.stop]
     bs = max(1, int(args.get('batch_size', 1)))
-    for lo in range(0, len(items), bs):
-        chunk = items[lo:lo + bs]
+    args.setdefault('device_ingest', True)       # masks / thresholds on the device (sfx_keypoint_masks)
+    names, rows = [], []
+    L = None
+    for lo in range(0, len(paths), bs):
+        chunk = [d for d in (dataset.read_meta(p) for p in paths[lo:lo + bs]) if d]
+        if not chunk:
+            continue
         B = len(chunk)
         kp = np.stack([d['keypoints'][0] for d in chunk])          # person 0 only (main.py:242-246)
-        H = [d['img'].shape[0] for d in chunk]
-        W = [d['img'].shape[1] for d in chunk]
+        H = [d['H'] for d in chunk]
+        W = [d['W'] for d in chunk]
+        if args.get('focal_length') is None:
+            # the reference stores the first image's focal length back into its arguments
+            # (main.py:212-218): every later image of the folder re-uses it
+            args['focal_length'] = float((W[0] ** 2 + H[0] ** 2) ** 0.5)
         reg = [_load_regression(args, d['fn']) for d in chunk]
         batch = engine.FrameBatch(model, B, use_vposer=bool(args.get('use_vposer')))
+        L = batch.L
         out = FF.fit_frames(batch, kp, H, W, args, expose=[r[1] for r in reg],
                             pixie=[r[0] for r in reg], pare=[r[2] for r in reg],
                             return_verts=bool(args.get('save_vertices')),
                             body_pose_prior=body_pose_prior, vposer=vposer)
         for b, d in enumerate(chunk):
+            print('Processing: {}'.format(d['img_path']))
+            fl = int(out.flags[b])
+            if fl & N.SFX_FLAG_NAN:
+                print('NaN loss value, stopping!')                 # fitting.py:177-179
+            if fl & N.SFX_FLAG_INF:
+                print('Infinite loss value, stopping!')            # fitting.py:181-183
+            if fl & N.SFX_FLAG_COLL_OVERFLOW:
+                print('Warning: interpenetration candidate list truncated for {}'.format(d['fn']))
             folder = os.path.join(result_folder, d['fn'])
             os.makedirs(folder, exist_ok=True)
             with open(os.path.join(folder, '000.pkl'), 'wb') as f:
                 pickle.dump(out.results[b], f, protocol=2)
             if args.get('save_vertices'):
                 write_ply_vertices(os.path.join(folder, 'vertices.ply'), out.vertices[b])
+            names.append(d['fn'])
+            rows.append(out.params[b])
         batch.close()
+    # one all-gather of the fitted parameter rows: rank 0 writes the whole job's table
+    if world > 1:
+        dev = model.device
+        local = torch.as_tensor(np.stack(rows) if rows else np.zeros((0, L.np if L else 0)),
+                                dtype=dtype, device=dev)
+        allp = sharding.gather_frames(local)
+        all_names = [None] * world
+        torch.distributed.all_gather_object(all_names, names)
+        names = [n for part in all_names for n in part]
+        table = allp.cpu().numpy()
+    else:
+        table = np.stack(rows) if rows else np.zeros((0, 0))
+    if rank == 0 and len(names):
+        np.savez(os.path.join(output_folder, 'fitted_params.npz'), names=np.array(names),
+                 params=table, **({} if L is None else {
+                     'layout_' + k: np.array(getattr(L, k)) for k, _ in L._fields_}))
     sharding.finalize()
     if rank == 0:
         print('Processing the data took: {}'.format(

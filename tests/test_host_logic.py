@@ -296,3 +296,31 @@ def test_degenerate_inputs_at_plan_level():
     plan = FF.FitPlan(L, 135, np.zeros((2, 135, 3)), 600, 800, cfg, None, None, None, np.float32)
     assert list(plan.flip_ids) == [0, 1]
     assert np.isfinite(plan.x0).all()
+
+
+def test_dataset_read_meta_equals_read_item_without_pixels(tmp_path):
+    """The batched driver reads keypoints + image size only (``KeypointDataset.read_meta``): same
+    fields as ``read_item`` except the decoded pixels, whose shape it reports."""
+    import json
+    import cv2
+    from smplifyx_b200 import data_parser as DP
+    (tmp_path / 'images').mkdir()
+    (tmp_path / 'keypoints').mkdir()
+    rng = np.random.default_rng(0)
+    for name, (h, w) in (('a', (48, 64)), ('b', (30, 20))):
+        cv2.imwrite(str(tmp_path / 'images' / (name + '.png')), np.zeros((h, w, 3), np.uint8))
+        person = {'pose_keypoints_2d': rng.uniform(size=75).tolist(),
+                  'hand_left_keypoints_2d': rng.uniform(size=63).tolist(),
+                  'hand_right_keypoints_2d': rng.uniform(size=63).tolist(),
+                  'face_keypoints_2d': rng.uniform(size=210).tolist()}
+        with open(tmp_path / 'keypoints' / (name + '_keypoints.json'), 'w') as f:
+            json.dump({'people': [person]}, f)
+    cv2.imwrite(str(tmp_path / 'images' / 'c.png'), np.zeros((8, 8, 3), np.uint8))   # no keypoints
+    ds = DP.create_dataset(data_folder=str(tmp_path), use_hands=True, use_face=True,
+                           use_face_contour=True)
+    metas = [ds.read_meta(p) for p in ds.img_paths]
+    items = [ds.read_item(p) for p in ds.img_paths]
+    assert [bool(m) for m in metas] == [bool(i) for i in items] == [True, True, False]
+    for m, i in zip(metas[:2], items[:2]):
+        assert m['fn'] == i['fn'] and np.array_equal(m['keypoints'], i['keypoints'])
+        assert (m['H'], m['W']) == i['img'].shape[:2]
