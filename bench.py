@@ -443,7 +443,7 @@ def run_reference(args):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
         'config': workload_config(B, args.gpus, args.interpenetration, args.vposer,
-                                  args.regression_prior),
+                                  args.regression_prior, steps_in_flight(args)),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port',
                          'sample': '{} frame(s) of the batch per step, {} (the reference asserts '
                                    'batch_size == 1); mean evals/frame {:.0f}'.format(
@@ -454,8 +454,18 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(B, n_gpus, interpenetration=False, vposer=False, regression_prior=False):
+def steps_in_flight(args):
+    return 1 if args.interpenetration else max(1, int(getattr(args, 'depth', 2)))
+
+
+def workload_config(B, n_gpus, interpenetration=False, vposer=False, regression_prior=False, depth=2):
     common = {'frames_per_gpu': B, 'global_frames': B * n_gpus,
+              'steps_in_flight': '{} (engine arm: consecutive steps alternate between that many '
+                                 'FrameBatch objects on their own CUDA streams, so the straggler '
+                                 'frames of one step overlap the next step\'s frames; every step is a '
+                                 'complete fit of its own batch, value_one_step_at_a_time is the same '
+                                 'measurement with one step in flight; the reference arm fits one '
+                                 'frame per process)'.format(depth),
               'parallelism': 'frames sharded, dp{}'.format(n_gpus),
               'l2': 'flushed between timed steps (256 MiB write)',
               'two_loop': TWO_LOOP + ' (engine option for the L-BFGS direction, value_exact is '
@@ -594,70 +604,117 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- steps in flight -------------------------------------------------------------------------
+    # A step is one complete fit of one batch.  Consecutive steps alternate between `depth`
+    # independent FrameBatch objects, each on its own CUDA stream: the straggler frames of step i
+    # (a few SMs busy) overlap the first frames of step i + 1, the way a service that is fed batch
+    # after batch runs.  Every step still fits its own 128 frames from scratch and the timed region
+    # ends only when all of them are complete.  depth 1 = one batch at a time (also reported).
+    depth = steps_in_flight(args)                   # (config 4: one step, 0.6 GB of workspace per batch)
+    batches = [batch] + [engine.FrameBatch(model, B, use_vposer=args.vposer) for _ in range(depth - 1)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+    gathered_k = [torch.empty((world * B, L.np), dtype=torch.float32, device=dev) if world > 1 else None
+                  for _ in range(depth)]
+
+    def timed_steps(step_fn, d, steps):
+        """`steps` steps, step i on stream i % d; device time of the whole region (ms)."""
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record()
+        for st_ in streams[:d]:
+            st_.wait_event(start)
+        n = 0
+        for i in range(steps):
+            k = i % d
+            with torch.cuda.stream(streams[k]):
+                flush.fill_(i & 0xff)
+                n += step_fn(k)
+        for st_ in streams[:d]:
+            torch.cuda.current_stream().wait_stream(st_)
+        end.record()
+        barrier()
+        return start.elapsed_time(end), n
+
     # ---- device-timed steps, inputs resident: default two-loop mode first, then the other ----
     other = {'gram': 'exact', 'exact': 'gram'}[TWO_LOOP]
     modes = [TWO_LOOP] if (args.interpenetration or args.single_mode) else [TWO_LOOP, other]
     sampler = ClockSampler(local)
-    timed, plans = {}, {}
+    timed, timed_serial, plans = {}, {}, {}
     launches = 0
     for mi, mode in enumerate(modes):
         mcfg = dict(cfg, two_loop=mode)
-        plan = FF.FitPlan(L, K, kp, H_IMG, W_IMG, mcfg, expose, pixie, None, np.float32,
-                          part_segm=part_segm, vposer=vp)
-        FF.upload(batch, plan)
-        plans[mode] = plan
-        x0_dev = batch.params_tensor().clone()
+        mplans, x0s = [], []
+        for bk in batches:
+            pl = FF.FitPlan(L, K, kp, H_IMG, W_IMG, mcfg, expose, pixie, None, np.float32,
+                            part_segm=part_segm, vposer=vp)
+            FF.upload(bk, pl)
+            mplans.append(pl)
+            x0s.append(bk.params_tensor().clone())
+        plans[mode] = mplans[0]
 
-        def resident_step():
-            batch.params_tensor().copy_(x0_dev)
-            _, verts, joints, n = FF.run(batch, plan, return_verts=True)
+        def resident_step(k):
+            batches[k].params_tensor().copy_(x0s[k])
+            _, verts, joints, n = FF.run(batches[k], mplans[k], return_verts=True)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, batch.params_tensor())
+                dist.all_gather_into_tensor(gathered_k[k], batches[k].params_tensor())
             return n
 
-        for _ in range(args.warmup):
-            resident_step()
-        barrier()
+        timed_steps(resident_step, depth, args.warmup)
         if rank == 0 and mi == 0:
             sampler.start()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-              for _ in range(args.steps)]
-        barrier()
-        for i in range(args.steps):
-            flush.fill_(i & 0xff)
-            ev[i][0].record()
-            n = resident_step()
-            ev[i][1].record()
-            if mi == 0:
-                launches += n
-        barrier()
-        timed[mode] = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+        timed[mode], n = timed_steps(resident_step, depth, args.steps)
+        if mi == 0:
+            launches += n
+        if depth > 1:
+            timed_serial[mode], _ = timed_steps(resident_step, 1, args.steps)
+        else:
+            timed_serial[mode] = timed[mode]
     total_ms_rank = timed[TWO_LOOP]
     total_ms = reduce_max(total_ms_rank)
+    total_ms_serial = reduce_max(timed_serial[TWO_LOOP])
     total_ms_other = reduce_max(timed[other]) if other in timed else None
     plan = plans[TWO_LOOP]
     FF.upload(batch, plan)
     x0_dev = batch.params_tensor().clone()
 
     # ---- end to end through the public call with host buffers --------------------------------
-    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-              for _ in range(args.steps)]
-    out = None
-    for _ in range(min(args.warmup, 2)):
-        out = FF.fit_frames(batch, kp, H_IMG, W_IMG, cfg, expose, pixie, return_verts=True,
-                            part_segm=part_segm, vposer=vp)
-    barrier()
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)
-        e2e_ev[i][0].record()
-        out = FF.fit_frames(batch, kp, H_IMG, W_IMG, cfg, expose, pixie, return_verts=True,
-                            part_segm=part_segm, vposer=vp)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, batch.params_tensor())
-        e2e_ev[i][1].record()
-    barrier()
+    # FF.submit plans the batch on the host, queues H2D copies, the fit and the D2H copies of the
+    # results (pinned buffers) on the step's stream; FF.finish waits for that step and hands the
+    # results over.  With `depth` steps in flight the host reads step i - depth + 1 while step i runs.
+    def e2e_steps(d, steps):
+        import collections
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pending = collections.deque()
+        res = None
+        barrier()
+        start.record()
+        for st_ in streams[:d]:
+            st_.wait_event(start)
+        for i in range(steps):
+            k = i % d
+            if len(pending) == d:
+                res = FF.finish(pending.popleft())
+            with torch.cuda.stream(streams[k]):
+                flush.fill_(i & 0xff)
+                pf = FF.submit(batches[k], kp, H_IMG, W_IMG, cfg, expose, pixie, return_verts=True,
+                               part_segm=part_segm, vposer=vp)
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered_k[k], batches[k].params_tensor())
+            pending.append(pf)
+        while pending:
+            res = FF.finish(pending.popleft())
+        for st_ in streams[:d]:
+            torch.cuda.current_stream().wait_stream(st_)
+        end.record()
+        barrier()
+        return start.elapsed_time(end), res
+
+    e2e_steps(depth, min(args.warmup, 2 * depth))
+    e2e_ms_rank, out = e2e_steps(depth, args.steps)
+    e2e_serial_rank = e2e_steps(1, args.steps)[0] if depth > 1 else e2e_ms_rank
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms = reduce_max(float(np.sum([a.elapsed_time(b) for a, b in e2e_ev])))
+    e2e_ms = reduce_max(e2e_ms_rank)
+    e2e_serial_ms = reduce_max(e2e_serial_rank)
 
     # ---- roofline accounting for the dominant kernel (one untimed replay with counters) ------
     batch.params_tensor().copy_(x0_dev)
@@ -738,14 +795,19 @@ def run_b200(args):
 
     value = world * B * args.steps / (total_ms * 1e-3)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    roofline['sm_time_busy_frac_in_flight'] = min(1.0, roofline['sm_time_busy_frac'] * kern_ms /
+                                                 (total_ms / args.steps))
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(B, world, args.interpenetration, args.vposer,
-                                  args.regression_prior),
+                                  args.regression_prior, depth),
+        'value_one_step_at_a_time': world * B * args.steps / (total_ms_serial * 1e-3),
+        'ms_per_step_one_step_at_a_time': total_ms_serial / args.steps,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(out.h2d_bytes),
-                'd2h_bytes_per_step': int(out.d2h_bytes), 'ms_per_step': e2e_ms / args.steps},
+                'd2h_bytes_per_step': int(out.d2h_bytes), 'ms_per_step': e2e_ms / args.steps,
+                'value_one_step_at_a_time': world * B * args.steps / (e2e_serial_ms * 1e-3)},
         'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
         'evals_per_frame': evals_per_frame, 'per_rank': per_rank,
         'fit': {'final_loss_median': float(np.median(out.loss)),
@@ -829,6 +891,9 @@ def main():
                          "recursion) or 'exact' (the reference's operation order); the other "
                          "one is reported as value_<mode>")
     ap.add_argument('--single-mode', action='store_true', help='time only the default two-loop mode')
+    ap.add_argument('--depth', type=int, default=2,
+                    help='steps in flight (each on its own FrameBatch and CUDA stream); 1 = one batch '
+                         'at a time')
     ap.add_argument('--traffic', type=float, default=None,
                     help='dram bytes per launch from an ncu capture (profiles/), recorded as-is')
     args = ap.parse_args()

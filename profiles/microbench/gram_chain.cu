@@ -6,6 +6,8 @@
 //        -I smplify-x-partial_b200/csrc -o profiles/microbench/gram_chain.bin profiles/microbench/gram_chain.cu
 #include <cstdio>
 #include <cstring>
+__device__ long long g_probe;
+#define SFX_CHAIN_PROBE g_probe
 #include "sfx_core.cuh"
 #include "sfx_stream.cuh"
 using namespace sfx;
@@ -26,25 +28,26 @@ __global__ void chain_kernel(int k, float hd, int which, long long* out, float* 
         else gram_chain_f32(S, k, hd, G, (int)threadIdx.x);
     }
     __syncthreads();
-    if (threadIdx.x == 0) out[0] = clock64() - t0;
+    if (threadIdx.x == 0) { out[0] = clock64() - t0; out[1] = g_probe - t0; }
     for (int i = threadIdx.x; i < k; i += blockDim.x) { coef[i] = S.al[i]; coef[128 + i] = S.cf[i]; }
 }
 int main() {
     long long* out; float* coef;
-    cudaMalloc(&out, 8); cudaMalloc(&coef, 256 * 4);
+    cudaMalloc(&out, 16); cudaMalloc(&coef, 256 * 4);
     const int smem = 200 * 1024;
     cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     for (int k : {1, 31, 33, 64, 100}) {
-        long long h[2] = {0, 0};
+        long long h[2] = {0, 0}, h1[2] = {0, 0};
         float c[2][256];
         for (int which = 0; which < 2; ++which) {
             for (int it = 0; it < 3; ++it) {
                 cudaMemset(coef, 0, 256 * 4);
                 chain_kernel<<<1, 512, smem>>>(k, 0.7f, which, out, coef);
-                cudaMemcpy(&h[which], out, 8, cudaMemcpyDeviceToHost);
+                cudaMemcpy(&h[which], out, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&h1[which], out + 1, 8, cudaMemcpyDeviceToHost);
             }
             cudaMemcpy(c[which], coef, 256 * 4, cudaMemcpyDeviceToHost);
         }
+        printf("  f32 first loop %.1f cycles/step, second %.1f\n", (double)h1[1] / k, (double)(h[1] - h1[1]) / k);
         printf("k=%3d  generic %.1f cycles/step   f32 shared-address %.1f cycles/step   coefficients %s  (al[0]=%g cf[k-1]=%g) %s\n",
                k, (double)h[0] / (2 * k), (double)h[1] / (2 * k),
                memcmp(c[0], c[1], sizeof(c[0])) == 0 ? "bit-identical" : "DIFFER", c[1][0], c[1][128 + k - 1],

@@ -13,7 +13,7 @@ import sys, os, ctypes as C
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 from smplifyx_b200 import _native as N
-N.LIB_PATH = os.path.join(os.path.dirname(N.LIB_PATH), 'libsfx_prof.so')
+N.LIB_PATH = os.path.join(os.path.dirname(N.LIB_PATH), sys.argv[sys.argv.index('--lib') + 1] if '--lib' in sys.argv else 'libsfx_prof.so')
 import bench
 from smplifyx_b200 import engine, fit_frames as FF, synthetic, utils as U
 COLL = '--interpenetration' in sys.argv

@@ -39,6 +39,11 @@ static int fail(int code, const std::string& msg) {
 
 // ------------------------------------------------------------------------------ kernels
 #define SFX_THREADS 512
+// -DSFX_DEV_F32_ONLY: development builds that leave the float64 instantiations of the four large
+// kernels out (halves the compile time while iterating on the float32 path); never the product build
+#ifdef SFX_DEV_F32_ONLY
+#define SFX_NO_F64() return fail(SFX_ERR_UNSUPPORTED, "float64 kernels are left out of this development build")
+#endif
 
 template <typename T>
 __device__ __forceinline__ StreamWS carve_stream(unsigned char* base, int ring_mode) {
@@ -1025,11 +1030,15 @@ int sfx_eval(sfx_batch* b, const SfxStage* st, void* loss_dev, void* grad_dev, v
     cudaStream_t s = (cudaStream_t)stream;
     const int rm = ring_mode_for(b->m);
     if (b->m->use_double) {
+#ifdef SFX_DEV_F32_ONLY
+        SFX_NO_F64();
+#else
         size_t smem = fit_smem<double>(rm);
         CUDA_TRY(cudaFuncSetAttribute(eval_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         eval_kernel<double><<<b->B, SFX_THREADS, smem, s>>>(b->m->vd, b->view<double>(nullptr), *st, rm,
                                                             (double*)loss_dev, (double*)grad_dev,
                                                             (double*)joints_dev);
+#endif
     } else {
         size_t smem = fit_smem<float>(rm);
         CUDA_TRY(cudaFuncSetAttribute(eval_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1050,10 +1059,14 @@ int sfx_fit_stage(sfx_batch* b, const SfxStage* st, const int32_t* frame_ids_dev
     if (grid < 1) return SFX_OK;
     const int rm = ring_mode_for(b->m);
     if (b->m->use_double) {
+#ifdef SFX_DEV_F32_ONLY
+        SFX_NO_F64();
+#else
         size_t smem = fit_smem<double>(rm);
         CUDA_TRY(cudaFuncSetAttribute(fit_stage_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fit_stage_kernel<double><<<grid, SFX_THREADS, smem, s>>>(
             b->m->vd, b->view<double>(frame_ids_dev), *st, rm, (double*)final_loss_dev);
+#endif
     } else {
         size_t smem = fit_smem<float>(rm);
         CUDA_TRY(cudaFuncSetAttribute(fit_stage_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1164,12 +1177,16 @@ int sfx_fit_pipeline(sfx_batch* b, const SfxPipeline* pipe, const int32_t* order
     }
     const int grid = b->B < b->m->num_sms ? b->B : b->m->num_sms;
     if (b->m->use_double) {
+#ifdef SFX_DEV_F32_ONLY
+        SFX_NO_F64();
+#else
         size_t smem = fit_smem<double>(rm);
         CUDA_TRY(cudaFuncSetAttribute(fit_pipeline_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fit_pipeline_kernel<double><<<grid, SFX_THREADS, smem, s>>>(
             b->m->vd, b->view<double>(order_dev), (const SfxPipeline*)b->pipe.p, flip_dev, b->B,
             (int*)b->counter.p, rm, (double*)b->cam_loss.p, (double*)b->params_last.p, 1, (int)smem,
             (double*)b->params_alt.p);
+#endif
     } else {
         size_t smem = fit_smem<float>(rm);
         CUDA_TRY(cudaFuncSetAttribute(fit_pipeline_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1284,6 +1301,9 @@ static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev,
     cudaStream_t s = (cudaStream_t)stream;
     const sfx_model* m = b->m;
     if (m->use_double) {
+#ifdef SFX_DEV_F32_ONLY
+        SFX_NO_F64();
+#else
         size_t smem = fit_smem<double>(0);
         CUDA_TRY(cudaFuncSetAttribute(mesh_coef_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mesh_coef_kernel<double><<<b->B, SFX_THREADS, smem, s>>>(m->vd, b->view<double>(nullptr), b->use_vposer,
@@ -1293,6 +1313,7 @@ static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev,
                                                   (const double*)b->Ccoef.p, (double*)b->vposed.p,
                                                   (double*)vertices_dev, s);
         if (!e.empty()) return fail(SFX_ERR_CUDA, e);
+#endif
     } else {
         size_t smem = fit_smem<float>(0);
         CUDA_TRY(cudaFuncSetAttribute(mesh_coef_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

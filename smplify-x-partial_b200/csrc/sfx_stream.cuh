@@ -14,6 +14,7 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "sfx_core.cuh"
 
 namespace sfx {
@@ -695,10 +696,170 @@ __device__ __forceinline__ bool two_loop_staged(Scratch<T>& S, int k, int head, 
 
 // ---- scalar recurrences of the Gram two-loop (sfx_core.cuh gram_chain), float32, written against
 // shared-state-space addresses.  G is the packed [SFX_GRAM_ROWS][SFX_GRAM_LDF] block (zero outside
-// the live k x k part), so a column is one walking address + immediates, the history is cut
+// the live k x k part), so a column is one walking address + immediates and the history is cut
 // into four 32-pair segments whose owner register is known at compile time (no selects on the
-// dependent chain), and a step is ~30 instructions: broadcast, multiply, multiply-adds.
-// Same operations in the same order as gram_chain<float>: bit-identical to it.
+// dependent chain).
+//
+// Blocked by four: the recursion's critical path is  b_j -> broadcast -> al_j -> b_(j-1) -> ...,
+// one shuffle (~25 cycles) + two dependent floating-point operations per pair when taken pair by
+// pair.  Here the four values b_j .. b_(j-3) are broadcast at once and every lane runs the 4 x 4
+// triangular piece of the recurrence itself (six multiply-adds on values it loaded ahead of the
+// chain), so the chain pays one shuffle latency per FOUR pairs; the rank-4 update of the remaining
+// entries follows off the critical path.  Every entry still receives the same multiply-adds in
+// the same order as in gram_chain<float> (pair j descending in the first loop, ascending in the
+// second): bit-identical to it (tests/test_gpu_parity.py, staging variants).
+template <int JR>
+__device__ __forceinline__ void gram_first_step(float (&b)[4], float (&e)[4], uint32_t colA, uint32_t rowA,
+                                                uint32_t a_ro, uint32_t a_al, int j, int lane) {
+    constexpr uint32_t LDB = 4u * SFX_GRAM_LDF;
+    float colv[4], rowv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) colv[r] = lds_f32(colA + 32u * LDB * r);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) rowv[r] = r <= JR ? lds_f32(rowA + 128u * r) : 0.f;
+    const float ro_j = lds_f32(a_ro + 4u * j);
+    const float a = __shfl_sync(0xffffffffu, b[JR], j & 31) * ro_j;
+    if (lane == 0) sts_f32(a_al + 4u * j, a);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r < JR) {
+            b[r] -= a * colv[r];
+            e[r] -= a * rowv[r];
+        } else if (r == JR) {
+            const bool lo = lane < (j & 31);
+            b[r] -= a * (lo ? colv[r] : 0.f);
+            e[r] -= a * (lo ? rowv[r] : colv[r]);
+        } else {
+            e[r] -= a * colv[r];
+        }
+    }
+}
+
+// pairs j, j-1, j-2, j-3 (j % 4 == 3) of segment JR
+template <int JR>
+__device__ __forceinline__ void gram_first_block(float (&b)[4], float (&e)[4], uint32_t gA, uint32_t colA,
+                                                 uint32_t rowA, uint32_t a_ro, uint32_t a_al, int j, int lane) {
+    constexpr uint32_t LDB = 4u * SFX_GRAM_LDF;
+    float col[4][4], row[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) col[u][r] = lds_f32(colA - 4u * u + 32u * LDB * r);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) row[u][r] = r <= JR ? lds_f32(rowA - LDB * u + 128u * r) : 0.f;
+    }
+    // the 4 x 4 piece: G(j - v, j - u) for u < v (row below the column: s_i . y_j), and 1 / (y.s)
+    const uint32_t gjj = gA + LDB * (uint32_t)j + 4u * (uint32_t)j;
+    const float g10 = lds_f32(gjj - LDB), g20 = lds_f32(gjj - 2u * LDB), g30 = lds_f32(gjj - 3u * LDB);
+    const float g21 = lds_f32(gjj - 2u * LDB - 4u), g31 = lds_f32(gjj - 3u * LDB - 4u);
+    const float g32 = lds_f32(gjj - 3u * LDB - 8u);
+    const float ro0 = lds_f32(a_ro + 4u * j), ro1 = lds_f32(a_ro + 4u * j - 4u);
+    const float ro2 = lds_f32(a_ro + 4u * j - 8u), ro3 = lds_f32(a_ro + 4u * j - 12u);
+    const int l0 = j & 31;
+    float b0 = __shfl_sync(0xffffffffu, b[JR], l0), b1 = __shfl_sync(0xffffffffu, b[JR], l0 - 1);
+    float b2 = __shfl_sync(0xffffffffu, b[JR], l0 - 2), b3 = __shfl_sync(0xffffffffu, b[JR], l0 - 3);
+    float a[4];
+    a[0] = b0 * ro0;
+    b1 -= a[0] * g10;
+    b2 -= a[0] * g20;
+    b3 -= a[0] * g30;
+    a[1] = b1 * ro1;
+    b2 -= a[1] * g21;
+    b3 -= a[1] * g31;
+    a[2] = b2 * ro2;
+    b3 -= a[2] * g32;
+    a[3] = b3 * ro3;
+    if (lane == 0) {
+        sts_f32(a_al + 4u * (uint32_t)j, a[0]);
+        sts_f32(a_al + 4u * (uint32_t)j - 4u, a[1]);
+        sts_f32(a_al + 4u * (uint32_t)j - 8u, a[2]);
+        sts_f32(a_al + 4u * (uint32_t)j - 12u, a[3]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (r < JR) {
+                b[r] -= a[u] * col[u][r];
+                e[r] -= a[u] * row[u][r];
+            } else if (r == JR) {
+                const bool lo = lane < l0 - u;
+                b[r] -= a[u] * (lo ? col[u][r] : 0.f);
+                e[r] -= a[u] * (lo ? row[u][r] : col[u][r]);
+            } else {
+                e[r] -= a[u] * col[u][r];
+            }
+        }
+    }
+}
+
+template <int JR>
+__device__ __forceinline__ void gram_second_step(float (&e)[4], uint32_t rowA, uint32_t a_ro, uint32_t a_al,
+                                                 uint32_t a_cf, int j, int lane) {
+    float rowv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) rowv[r] = r >= JR ? lds_f32(rowA + 128u * r) : 0.f;
+    const float ro_j = lds_f32(a_ro + 4u * j), al_j = lds_f32(a_al + 4u * j);
+    const float c = al_j - __shfl_sync(0xffffffffu, e[JR], j & 31) * ro_j;
+    if (lane == 0) sts_f32(a_cf + 4u * j, c);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r > JR) e[r] += c * rowv[r];
+        else if (r == JR) e[r] += c * (lane > (j & 31) ? rowv[r] : 0.f);
+    }
+}
+
+// pairs j, j+1, j+2, j+3 (j % 4 == 0) of segment JR
+template <int JR>
+__device__ __forceinline__ void gram_second_block(float (&e)[4], uint32_t gA, uint32_t rowA, uint32_t a_ro,
+                                                  uint32_t a_al, uint32_t a_cf, int j, int lane) {
+    constexpr uint32_t LDB = 4u * SFX_GRAM_LDF;
+    float row[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) row[u][r] = r >= JR ? lds_f32(rowA + LDB * u + 128u * r) : 0.f;
+    // G(j + u, j + v) for u < v (above the diagonal: s . y)
+    const uint32_t gjj = gA + LDB * (uint32_t)j + 4u * (uint32_t)j;
+    const float g01 = lds_f32(gjj + 4u), g02 = lds_f32(gjj + 8u), g03 = lds_f32(gjj + 12u);
+    const float g12 = lds_f32(gjj + LDB + 8u), g13 = lds_f32(gjj + LDB + 12u);
+    const float g23 = lds_f32(gjj + 2u * LDB + 12u);
+    float ro[4], al[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        ro[u] = lds_f32(a_ro + 4u * (uint32_t)(j + u));
+        al[u] = lds_f32(a_al + 4u * (uint32_t)(j + u));
+    }
+    const int l0 = j & 31;
+    float e0 = __shfl_sync(0xffffffffu, e[JR], l0), e1 = __shfl_sync(0xffffffffu, e[JR], l0 + 1);
+    float e2 = __shfl_sync(0xffffffffu, e[JR], l0 + 2), e3 = __shfl_sync(0xffffffffu, e[JR], l0 + 3);
+    float c[4];
+    c[0] = al[0] - e0 * ro[0];
+    e1 += c[0] * g01;
+    e2 += c[0] * g02;
+    e3 += c[0] * g03;
+    c[1] = al[1] - e1 * ro[1];
+    e2 += c[1] * g12;
+    e3 += c[1] * g13;
+    c[2] = al[2] - e2 * ro[2];
+    e3 += c[2] * g23;
+    c[3] = al[3] - e3 * ro[3];
+    if (lane == 0) {
+        sts_f32(a_cf + 4u * (uint32_t)j, c[0]);
+        sts_f32(a_cf + 4u * (uint32_t)j + 4u, c[1]);
+        sts_f32(a_cf + 4u * (uint32_t)j + 8u, c[2]);
+        sts_f32(a_cf + 4u * (uint32_t)j + 12u, c[3]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (r > JR) e[r] += c[u] * row[u][r];
+            else if (r == JR) e[r] += c[u] * (lane > l0 + u ? row[u][r] : 0.f);
+        }
+    }
+}
+
 __device__ __forceinline__ void gram_chain_f32(Scratch<float>& S, int k, float hd, const float* G, int lane) {
     static_assert(SFX_HIST <= 128, "four 32-pair segments");
     constexpr uint32_t LDB = 4u * SFX_GRAM_LDF;          // bytes per row
@@ -711,59 +872,47 @@ __device__ __forceinline__ void gram_chain_f32(Scratch<float>& S, int k, float h
         b[r] = i < k ? -S.sg[i] : 0.f;
         e[r] = i < k ? -S.yg[i] : 0.f;
     }
-#pragma unroll
-    for (int jr = 3; jr >= 0; --jr) {
-        const int jlo = 32 * jr, jhi = k - 1 < jlo + 31 ? k - 1 : jlo + 31;
+    auto first_segment = [&](auto jr_c) {
+        constexpr int JR = decltype(jr_c)::value;
+        const int jlo = 32 * JR, jhi = k - 1 < jlo + 31 ? k - 1 : jlo + 31;
         uint32_t colA = gA + LDB * lane + 4u * jhi;      // element (lane, j); register r: + 32 rows
         uint32_t rowA = gA + LDB * jhi + 4u * lane;      // element (j, lane); register r: + 32 columns
-        for (int j = jhi; j >= jlo; --j) {
-            float colv[4], rowv[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) colv[r] = lds_f32(colA + 32u * LDB * r);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) rowv[r] = r <= jr ? lds_f32(rowA + 128u * r) : 0.f;
-            const float ro_j = lds_f32(a_ro + 4u * j);
-            const float a = __shfl_sync(0xffffffffu, b[jr], j & 31) * ro_j;
-            if (lane == 0) sts_f32(a_al + 4u * j, a);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (r < jr) {
-                    b[r] -= a * colv[r];
-                    e[r] -= a * rowv[r];
-                } else if (r == jr) {
-                    const bool lo = lane < (j & 31);
-                    b[r] -= a * (lo ? colv[r] : 0.f);
-                    e[r] -= a * (lo ? rowv[r] : colv[r]);
-                } else {
-                    e[r] -= a * colv[r];
-                }
-            }
+        int j = jhi;
+        for (; j >= jlo && (j & 3) != 3; --j) {          // ragged top of the segment
+            gram_first_step<JR>(b, e, colA, rowA, a_ro, a_al, j, lane);
             colA -= 4u;
             rowA -= LDB;
         }
-    }
+        for (; j >= jlo; j -= 4) {
+            gram_first_block<JR>(b, e, gA, colA, rowA, a_ro, a_al, j, lane);
+            colA -= 16u;
+            rowA -= 4u * LDB;
+        }
+    };
+    using C0 = std::integral_constant<int, 0>; using C1 = std::integral_constant<int, 1>;
+    using C2 = std::integral_constant<int, 2>; using C3 = std::integral_constant<int, 3>;
+    first_segment(C3()); first_segment(C2()); first_segment(C1()); first_segment(C0());
     __syncwarp();
+#ifdef SFX_CHAIN_PROBE
+    if (lane == 0) SFX_CHAIN_PROBE = clock64();
+#endif
 #pragma unroll
     for (int r = 0; r < 4; ++r) e[r] = e[r] * hd;
-#pragma unroll
-    for (int jr = 0; jr < 4; ++jr) {
-        const int jlo = 32 * jr, jhi = k - 1 < jlo + 31 ? k - 1 : jlo + 31;
+    auto second_segment = [&](auto jr_c) {
+        constexpr int JR = decltype(jr_c)::value;
+        const int jlo = 32 * JR, jhi = k - 1 < jlo + 31 ? k - 1 : jlo + 31;
         uint32_t rowA = gA + LDB * jlo + 4u * lane;
-        for (int j = jlo; j <= jhi; ++j) {
-            float rowv[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) rowv[r] = r >= jr ? lds_f32(rowA + 128u * r) : 0.f;
-            const float ro_j = lds_f32(a_ro + 4u * j), al_j = lds_f32(a_al + 4u * j);
-            const float c = al_j - __shfl_sync(0xffffffffu, e[jr], j & 31) * ro_j;
-            if (lane == 0) sts_f32(a_cf + 4u * j, c);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (r > jr) e[r] += c * rowv[r];
-                else if (r == jr) e[r] += c * (lane > (j & 31) ? rowv[r] : 0.f);
-            }
+        int j = jlo;
+        for (; j + 3 <= jhi; j += 4) {
+            gram_second_block<JR>(e, gA, rowA, a_ro, a_al, a_cf, j, lane);
+            rowA += 4u * LDB;
+        }
+        for (; j <= jhi; ++j) {                          // ragged end of the history
+            gram_second_step<JR>(e, rowA, a_ro, a_al, a_cf, j, lane);
             rowA += LDB;
         }
-    }
+    };
+    second_segment(C0()); second_segment(C1()); second_segment(C2()); second_segment(C3());
     __syncwarp();
 }
 

@@ -466,45 +466,154 @@ def run_staged(batch, plan, return_verts=True):
     return cam_loss, verts, joints, launches
 
 
-def download(batch, plan, cam_loss, verts, joints):
-    """Device -> host: fitted parameters, losses, counters and (optionally) the meshes."""
+class _LazyResults(object):
+    """``FitResult.results``: the reference's per-frame result dicts (fit_single_frame.py:644-660),
+    built when a frame is asked for -- a batch of thousands of frames does not pay for thousands of
+    small dicts it may never read.  Behaves like a list (len, index, iteration)."""
+
+    def __init__(self, plan, blocks, params, body_pose):
+        self._plan, self._blocks, self._params, self._body_pose = plan, blocks, params, body_pose
+        self._cache = {}
+
+    def __len__(self):
+        return self._plan.B
+
+    def __iter__(self):
+        return (self[b] for b in range(len(self)))
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(len(self)))]
+        if b < 0:
+            b += len(self)
+        if not 0 <= b < len(self):
+            raise IndexError(b)
+        r = self._cache.get(b)
+        if r is None:
+            plan, L, params, npd = self._plan, self._plan.L, self._params, self._plan.np_dtype
+            r = {'camera_rotation': plan.cam[b, 4:13].reshape(1, 3, 3).astype(npd),
+                 'camera_translation': params[b, L.off_camt:L.off_camt + 3].reshape(1, 3).copy(),
+                 'camera_center': plan.cam[b, 2:4].reshape(1, 2).astype(npd),
+                 'H': int(plan.H[b]), 'W': int(plan.W[b]), 'focal_length': float(plan.focal[b])}
+            for name in ('betas', 'global_orient', 'left_hand_pose', 'right_hand_pose', 'jaw_pose',
+                         'leye_pose', 'reye_pose', 'expression'):
+                off, n = self._blocks[name]
+                r[name] = params[b, off:off + n].reshape(1, n).copy()
+            if self._body_pose is not None:
+                r['body_pose'] = self._body_pose[b:b + 1].copy()
+            else:
+                off, n = self._blocks['pose_embedding']
+                r['body_pose'] = params[b, off:off + n].reshape(1, n).copy()
+            self._cache[b] = r
+        return r
+
+
+class PendingFit(object):
+    """A fit that has been queued on a CUDA stream (``submit``); ``finish`` waits for it and
+    returns the ``FitResult``.  Several may be in flight on different ``FrameBatch`` objects: the
+    straggler frames of one batch then overlap the next batch's frames."""
+
+    def __init__(self):
+        self.batch = self.plan = self.event = self.host = None
+        self.h2d_bytes = self.gpu_launches = 0
+        self.return_verts = True
+
+
+def _host_buffers(batch, return_verts):
+    """Pinned host buffers of one batch for the asynchronous device -> host copies (made once)."""
+    import torch
+    hb = getattr(batch, '_fit_host', None)
+    if hb is None:
+        B, dt = batch.B, batch.model.dtype
+        pin = lambda shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=True)
+        hb = {'params': pin((B, batch.L.np), dt), 'loss': pin((B,), dt), 'cam_loss': pin((B,), dt),
+              'n_evals': pin((B,), torch.int32), 'flags': pin((B,), torch.int32)}
+        batch._fit_host = hb
+    if return_verts and 'vertices' not in hb:
+        hb['vertices'] = torch.empty((batch.B, batch.model.V, 3), dtype=batch.model.dtype, pin_memory=True)
+        hb['joints'] = torch.empty((batch.B, batch.model.K, 3), dtype=batch.model.dtype, pin_memory=True)
+    return hb
+
+
+def submit(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_verts=True,
+           body_mean_pose=None, body_pose_prior=None, vposer=None, part_segm=None, pare=None):
+    """Plans and queues the whole fit of ``batch`` on the current CUDA stream -- host -> device
+    copies, the pipeline launch, the full-mesh forward, device -> host copies into pinned buffers
+    -- and returns a ``PendingFit`` without waiting for the device (only ``guess_init``, when a
+    frame has no usable camera prior, reads the model joints back first, as the reference does)."""
+    import torch
+    plan = FitPlan(batch.L, batch.model.K, np.asarray(keypoints), H, W, cfg, expose, pixie,
+                   body_mean_pose, batch.model.np_dtype, body_pose_prior, vposer, part_segm, pare)
+    p = PendingFit()
+    p.batch, p.plan, p.return_verts = batch, plan, return_verts
+    p.h2d_bytes = upload(batch, plan)
+    cam_loss, verts, joints, p.gpu_launches = run(batch, plan, return_verts)
+    p.host = _queue_download(batch, cam_loss, verts, joints)
+    p.event = torch.cuda.Event()
+    p.event.record()
+    return p
+
+
+def _queue_download(batch, cam_loss, verts, joints):
+    """Device -> host copies of a fit's outputs into the batch's pinned buffers, queued on the
+    current stream."""
+    hb = _host_buffers(batch, verts is not None)
+    hb['params'].copy_(batch.params_tensor(), non_blocking=True)
+    hb['loss'].copy_(batch.final_loss(), non_blocking=True)
+    hb['cam_loss'].copy_(cam_loss, non_blocking=True)
+    hb['n_evals'].copy_(batch.evals(), non_blocking=True)
+    hb['flags'].copy_(batch.flags(), non_blocking=True)
+    if verts is not None:
+        hb['vertices'].copy_(verts, non_blocking=True)
+        if joints is not None:
+            hb['joints'].copy_(joints, non_blocking=True)
+    return hb
+
+
+def _build_result(batch, plan, hb, return_verts):
+    """FitResult from the pinned buffers (arrays are copies: the buffers belong to the batch and
+    are reused by its next fit)."""
     out = FitResult()
-    L, B = plan.L, plan.B
-    npd = plan.np_dtype
-    out.params = params = batch.get_params()
-    out.loss = batch.final_loss().cpu().numpy().astype(np.float64)
-    out.cam_loss = cam_loss.cpu().numpy()
-    out.n_evals = batch.evals().cpu().numpy()
-    out.flags = batch.flags().cpu().numpy()
+    B = plan.B
+    out.params = params = hb['params'].numpy().copy()
+    out.loss = hb['loss'].numpy().astype(np.float64)
+    out.cam_loss = hb['cam_loss'].numpy().copy()
+    out.n_evals = hb['n_evals'].numpy().copy()
+    out.flags = hb['flags'].numpy().copy()
     out.n_orient = np.ones(B, dtype=np.int64)
     out.n_orient[plan.flip_ids] = 2
     out.d2h_bytes = params.nbytes + 4 * B * 4
-    if verts is not None:
-        out.vertices = verts.cpu().numpy()
-        out.joints = joints.cpu().numpy()
+    if return_verts:
+        out.vertices = hb['vertices'].numpy().copy()
+        out.joints = hb['joints'].numpy().copy()
         out.d2h_bytes += out.vertices.nbytes + out.joints.nbytes
-    blocks = batch.blocks
-    for b in range(B):
-        r = {'camera_rotation': plan.cam[b, 4:13].reshape(1, 3, 3).astype(npd),
-             'camera_translation': params[b, L.off_camt:L.off_camt + 3].reshape(1, 3).copy(),
-             'camera_center': plan.cam[b, 2:4].reshape(1, 2).astype(npd),
-             'H': int(plan.H[b]), 'W': int(plan.W[b]), 'focal_length': float(plan.focal[b])}
-        for name in ('betas', 'global_orient', 'left_hand_pose', 'right_hand_pose', 'jaw_pose',
-                     'leye_pose', 'reye_pose', 'expression'):
-            off, n = blocks[name]
-            r[name] = params[b, off:off + n].reshape(1, n).copy()
-        off, n = blocks['pose_embedding']
-        r['body_pose'] = params[b, off:off + n].reshape(1, n).copy()
-        out.results.append(r)
+    body_pose = None
     if plan.vposer is not None and plan.cfg.get('use_vposer', False):
         # result['body_pose'] = vposer.decode(pose_embedding, 'aa') (fit_single_frame.py:653-657)
         import torch
-        off, n = blocks['pose_embedding']
+        off, n = batch.blocks['pose_embedding']
         with torch.no_grad():
             z = torch.as_tensor(params[:, off:off + n], dtype=plan.vposer.dec_fc1_w.dtype)
-            bp = plan.vposer.decode(z, output_type='aa').reshape(B, -1).cpu().numpy().astype(npd)
-        for b in range(B):
-            out.results[b]['body_pose'] = bp[b:b + 1].copy()
+            body_pose = plan.vposer.decode(z, output_type='aa').reshape(B, -1).cpu().numpy().astype(plan.np_dtype)
+    out.results = _LazyResults(plan, batch.blocks, params, body_pose)
+    return out
+
+
+def download(batch, plan, cam_loss, verts, joints):
+    """Device -> host: fitted parameters, losses, counters and (optionally) the meshes; waits for
+    the current stream."""
+    import torch
+    hb = _queue_download(batch, cam_loss, verts, joints)
+    torch.cuda.current_stream().synchronize()
+    return _build_result(batch, plan, hb, verts is not None)
+
+
+def finish(p):
+    """Waits for a submitted fit and returns its ``FitResult``."""
+    p.event.synchronize()
+    out = _build_result(p.batch, p.plan, p.host, p.return_verts)
+    out.h2d_bytes = p.h2d_bytes
+    out.gpu_launches = p.gpu_launches
     return out
 
 
@@ -515,12 +624,7 @@ def fit_frames(batch, keypoints, H, W, cfg, expose=None, pixie=None, return_vert
     keypoints [B,K,3] (x, y, confidence) in the reference's row order; ``H``, ``W`` scalars or
     [B]; ``cfg`` the flat config dict of ``cmd_parser.parse_config`` (same keys as the
     reference's YAML files); ``expose`` / ``pixie`` lists of per-frame regression results.
+    Synchronous form of ``submit`` + ``finish``.
     """
-    plan = FitPlan(batch.L, batch.model.K, np.asarray(keypoints), H, W, cfg, expose, pixie,
-                   body_mean_pose, batch.model.np_dtype, body_pose_prior, vposer, part_segm, pare)
-    h2d = upload(batch, plan)
-    cam_loss, verts, joints, launches = run(batch, plan, return_verts)
-    out = download(batch, plan, cam_loss, verts, joints)
-    out.h2d_bytes = h2d
-    out.gpu_launches = launches
-    return out
+    return finish(submit(batch, keypoints, H, W, cfg, expose, pixie, return_verts, body_mean_pose,
+                         body_pose_prior, vposer, part_segm, pare))
