@@ -61,6 +61,9 @@ COLL_POSE_CORRECTIVE_SCALE = 0.1      # config 4: see synthetic.cached_smplx_lik
 # reference's two-loop recursion on the inner products of the history (same mathematics,
 # different rounding, ~2.4x shorter); 'exact' reproduces the reference's operation order.
 TWO_LOOP = os.environ.get('SFX_TWO_LOOP', 'gram')
+# frames on clusters of blocks (fit_frames cfg key wide_frames) only while one step runs at a time:
+# with several steps in flight every SM is busy and a cluster's helpers would take SMs from frames
+WIDE_IN_FLIGHT = 'off'
 
 
 def bench_cfg(interpenetration=False, vposer=False, regression_prior=False, two_loop=None):
@@ -455,17 +458,18 @@ def run_reference(args):
 
 
 def steps_in_flight(args):
-    return 1 if args.interpenetration else max(1, int(getattr(args, 'depth', 2)))
+    return 1 if args.interpenetration else max(1, int(getattr(args, 'depth', 4)))
 
 
-def workload_config(B, n_gpus, interpenetration=False, vposer=False, regression_prior=False, depth=2):
+def workload_config(B, n_gpus, interpenetration=False, vposer=False, regression_prior=False, depth=4):
     common = {'frames_per_gpu': B, 'global_frames': B * n_gpus,
               'steps_in_flight': '{} (engine arm: consecutive steps alternate between that many '
                                  'FrameBatch objects on their own CUDA streams, so the straggler '
-                                 'frames of one step overlap the next step\'s frames; every step is a '
-                                 'complete fit of its own batch, value_one_step_at_a_time is the same '
-                                 'measurement with one step in flight; the reference arm fits one '
-                                 'frame per process)'.format(depth),
+                                 'frames of one step overlap the next steps\' frames; every step is a '
+                                 'complete fit of its own batch, one block per frame; '
+                                 'value_one_step_at_a_time is the same measurement with one step in '
+                                 'flight, where the frames that fit two orientations run on clusters of '
+                                 '8 blocks; the reference arm fits one frame per process)'.format(depth),
               'parallelism': 'frames sharded, dp{}'.format(n_gpus),
               'l2': 'flushed between timed steps (256 MiB write)',
               'two_loop': TWO_LOOP + ' (engine option for the L-BFGS direction, value_exact is '
@@ -613,8 +617,26 @@ def run_b200(args):
     depth = steps_in_flight(args)                   # (config 4: one step, 0.6 GB of workspace per batch)
     batches = [batch] + [engine.FrameBatch(model, B, use_vposer=args.vposer) for _ in range(depth - 1)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+    # the single NCCL all-gather of a step's fitted parameters reads a copy of the rows
+    # and runs on NCCL's own stream: the next step of that slot does not wait for the other ranks
     gathered_k = [torch.empty((world * B, L.np), dtype=torch.float32, device=dev) if world > 1 else None
                   for _ in range(depth)]
+    staged_k = [torch.empty((B, L.np), dtype=torch.float32, device=dev) if world > 1 else None
+                for _ in range(depth)]
+    gather_work = [None] * depth
+
+    def gather_params(k):
+        if world > 1:
+            if gather_work[k] is not None:
+                gather_work[k].wait()                 # the slot's previous gather has read its copy
+            staged_k[k].copy_(batches[k].params_tensor())
+            gather_work[k] = dist.all_gather_into_tensor(gathered_k[k], staged_k[k], async_op=True)
+
+    def gather_drain():
+        for k in range(depth):
+            if gather_work[k] is not None:
+                gather_work[k].wait()
+                gather_work[k] = None
 
     def timed_steps(step_fn, d, steps):
         """`steps` steps, step i on stream i % d; device time of the whole region (ms)."""
@@ -631,6 +653,7 @@ def run_b200(args):
                 n += step_fn(k)
         for st_ in streams[:d]:
             torch.cuda.current_stream().wait_stream(st_)
+        gather_drain()
         end.record()
         barrier()
         return start.elapsed_time(end), n
@@ -642,33 +665,44 @@ def run_b200(args):
     timed, timed_serial, plans = {}, {}, {}
     launches = 0
     for mi, mode in enumerate(modes):
-        mcfg = dict(cfg, two_loop=mode)
-        mplans, x0s = [], []
-        for bk in batches:
-            pl = FF.FitPlan(L, K, kp, H_IMG, W_IMG, mcfg, expose, pixie, None, np.float32,
-                            part_segm=part_segm, vposer=vp)
-            FF.upload(bk, pl)
-            mplans.append(pl)
-            x0s.append(bk.params_tensor().clone())
-        plans[mode] = mplans[0]
+        # steps in flight keep every SM busy, so a frame gets one block there (wide_frames off: a
+        # cluster's helper blocks would only take SMs from other frames); one step at a time runs
+        # the frames that fit two orientations on clusters (wide_frames auto)
+        def make_plans(wide):
+            mcfg = dict(cfg, two_loop=mode, wide_frames=wide)
+            pls, xs = [], []
+            for bk in batches:
+                pl = FF.FitPlan(L, K, kp, H_IMG, W_IMG, mcfg, expose, pixie, None, np.float32,
+                                part_segm=part_segm, vposer=vp)
+                FF.upload(bk, pl)
+                pls.append(pl)
+                xs.append(bk.params_tensor().clone())
+            return pls, xs
 
-        def resident_step(k):
-            batches[k].params_tensor().copy_(x0s[k])
-            _, verts, joints, n = FF.run(batches[k], mplans[k], return_verts=True)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered_k[k], batches[k].params_tensor())
-            return n
+        def make_step(pls, xs):
+            def resident_step(k):
+                batches[k].params_tensor().copy_(xs[k])
+                _, verts, joints, n = FF.run(batches[k], pls[k], return_verts=True)
+                gather_params(k)
+                return n
+            return resident_step
 
-        timed_steps(resident_step, depth, args.warmup)
+        mplans, x0s = make_plans(WIDE_IN_FLIGHT if depth > 1 else 'auto')
+        step = make_step(mplans, x0s)
+        timed_steps(step, depth, args.warmup)
         if rank == 0 and mi == 0:
             sampler.start()
-        timed[mode], n = timed_steps(resident_step, depth, args.steps)
+        timed[mode], n = timed_steps(step, depth, args.steps)
         if mi == 0:
             launches += n
         if depth > 1:
-            timed_serial[mode], _ = timed_steps(resident_step, 1, args.steps)
+            mplans, x0s = make_plans('auto')
+            step = make_step(mplans, x0s)
+            timed_steps(step, 1, 1)
+            timed_serial[mode], _ = timed_steps(step, 1, args.steps)
         else:
             timed_serial[mode] = timed[mode]
+        plans[mode] = mplans[0]
     total_ms_rank = timed[TWO_LOOP]
     total_ms = reduce_max(total_ms_rank)
     total_ms_serial = reduce_max(timed_serial[TWO_LOOP])
@@ -683,6 +717,7 @@ def run_b200(args):
     # results over.  With `depth` steps in flight the host reads step i - depth + 1 while step i runs.
     def e2e_steps(d, steps):
         import collections
+        ecfg = dict(cfg, wide_frames=WIDE_IN_FLIGHT if d > 1 else 'auto')
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pending = collections.deque()
         res = None
@@ -696,15 +731,15 @@ def run_b200(args):
                 res = FF.finish(pending.popleft())
             with torch.cuda.stream(streams[k]):
                 flush.fill_(i & 0xff)
-                pf = FF.submit(batches[k], kp, H_IMG, W_IMG, cfg, expose, pixie, return_verts=True,
+                pf = FF.submit(batches[k], kp, H_IMG, W_IMG, ecfg, expose, pixie, return_verts=True,
                                part_segm=part_segm, vposer=vp)
-                if world > 1:
-                    dist.all_gather_into_tensor(gathered_k[k], batches[k].params_tensor())
+                gather_params(k)
             pending.append(pf)
         while pending:
             res = FF.finish(pending.popleft())
         for st_ in streams[:d]:
             torch.cuda.current_stream().wait_stream(st_)
+        gather_drain()
         end.record()
         barrier()
         return start.elapsed_time(end), res
@@ -891,7 +926,7 @@ def main():
                          "recursion) or 'exact' (the reference's operation order); the other "
                          "one is reported as value_<mode>")
     ap.add_argument('--single-mode', action='store_true', help='time only the default two-loop mode')
-    ap.add_argument('--depth', type=int, default=2,
+    ap.add_argument('--depth', type=int, default=4,
                     help='steps in flight (each on its own FrameBatch and CUDA stream); 1 = one batch '
                          'at a time')
     ap.add_argument('--traffic', type=float, default=None,

@@ -15,11 +15,12 @@ import bench
 from smplifyx_b200 import engine, fit_frames as FF, synthetic, utils as U
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 128
-STEPS = 12
+STEPS = 24
 jm = U.smpl_to_annotation('smplx', True, True, True, 'coco25')
 md = synthetic.cached_smplx_like(0, 1.0)
 model = engine.Model(md, jm, dtype=torch.float32, **bench.MODEL_KW)
-batches = [engine.FrameBatch(model, B) for _ in range(3)]
+MAXD = 4
+batches = [engine.FrameBatch(model, B) for _ in range(MAXD)]
 L = batches[0].L
 gt, rng = bench.ground_truth(B, 0, 1.0)
 cam_st = N.make_stage(L, N.CAMERA_STAGE_BLOCKS, loss_kind=N.LOSS_CAMERA_INIT)
@@ -31,31 +32,34 @@ b0.set_targets(np.zeros((B, 135, 3)), np.zeros((B, 135)), np.zeros((B, 135), np.
 b0.set_params(xg)
 _, _, j3 = b0.eval(cam_st, want_joints=True)
 kp, ex, px = bench.observations(gt, j3.cpu().numpy().astype(np.float64), rng)
-cfg = bench.bench_cfg(False, False, False)
-plans, x0 = [], []
-for b in batches:
+streams = [torch.cuda.Stream() for _ in range(MAXD)]
+for wide in ('auto', 'off'):
+  cfg = bench.bench_cfg(False, False, False)
+  cfg['wide_frames'] = wide
+  plans, x0 = [], []
+  for b in batches:
     plan = FF.FitPlan(L, 135, kp, 600, 800, cfg, None, None, None, np.float32)
     FF.upload(b, plan)
     plans.append(plan)
     x0.append(b.params_tensor().clone())
-torch.cuda.synchronize()
-streams = [torch.cuda.Stream() for _ in range(3)]
-for depth in (1, 2, 3):
-    for rep in range(2):
-        torch.cuda.synchronize()
-        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for s in streams[:depth]:
-            s.wait_event(a)
-        for i in range(STEPS):
-            k = i % depth
-            with torch.cuda.stream(streams[k]):
-                batches[k].params_tensor().copy_(x0[k])
-                FF.run(batches[k], plans[k], True)
-        for s in streams[:depth]:
-            torch.cuda.current_stream().wait_stream(s)
-        e.record()
-        torch.cuda.synchronize()
-    ms = a.elapsed_time(e) / STEPS
-    h = [hashlib.sha1(b.params_tensor().cpu().numpy().tobytes()).hexdigest()[:12] for b in batches[:depth]]
-    print('depth %d: %.2f ms per step, %.0f frames/s   params %s' % (depth, ms, B / ms * 1e3, ' '.join(h)), flush=True)
+  torch.cuda.synchronize()
+  print('wide frames', wide)
+  for depth in (1, 2, 3, 4):
+      for rep in range(2):
+          torch.cuda.synchronize()
+          a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          a.record()
+          for s in streams[:depth]:
+              s.wait_event(a)
+          for i in range(STEPS):
+              k = i % depth
+              with torch.cuda.stream(streams[k]):
+                  batches[k].params_tensor().copy_(x0[k])
+                  FF.run(batches[k], plans[k], True)
+          for s in streams[:depth]:
+              torch.cuda.current_stream().wait_stream(s)
+          e.record()
+          torch.cuda.synchronize()
+      ms = a.elapsed_time(e) / STEPS
+      h = [hashlib.sha1(b.params_tensor().cpu().numpy().tobytes()).hexdigest()[:12] for b in batches[:depth]]
+      print('depth %d: %.2f ms per step, %.0f frames/s   params %s' % (depth, ms, B / ms * 1e3, ' '.join(h)), flush=True)

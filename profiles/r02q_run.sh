@@ -2,10 +2,10 @@
 # steps in flight: default bench line (depth 2), depth 1 and 3 beside it, GPU suite
 mkdir -p gpurun_out
 T=${1:-r02q}
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_gpu_tests.log 2>&1; echo "pytest rc=$?"
-tail -3 gpurun_out/${T}_gpu_tests.log
-for d in 2 3; do
-timeout 900 python bench.py --steps 10 --warmup 3 --depth $d $( [ $d != 2 ] && echo --no-cpu-baseline ) > gpurun_out/${T}_bench_depth$d.json 2> gpurun_out/${T}_bench_depth$d.err; echo "bench depth $d rc=$?"
+echo skip tests
+
+for d in 4 6; do
+timeout 900 python bench.py --steps 10 --warmup 3 --depth $d $( [ $d != 4 ] && echo --no-cpu-baseline ) > gpurun_out/${T}_bench_depth$d.json 2> gpurun_out/${T}_bench_depth$d.err; echo "bench depth $d rc=$?"
 tail -2 gpurun_out/${T}_bench_depth$d.err
 python -c "
 import json;d=json.loads(open('gpurun_out/${T}_bench_depth$d.json').read().strip().splitlines()[-1])

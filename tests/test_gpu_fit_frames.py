@@ -269,3 +269,41 @@ def test_float64_full_fit_matches_the_reference_fit():
             assert np.allclose(r['camera_translation'], ref['result/camera_translation'], atol=0.1)
         if b == 0:
             assert abs(out.loss[b] - loss_at_ref[b]) <= 1e-6 * abs(loss_at_ref[b])
+
+
+def test_fits_in_flight_equal_one_at_a_time():
+    """``submit`` / ``finish``: two fits queued on different FrameBatch objects and CUDA streams
+    (what bench.py's steps in flight and a service fed batch after batch do) give, bit for bit,
+    the results of the synchronous call; the result dicts are built on demand."""
+    from smplifyx_b200 import engine, fit_frames as FF
+    inp = Cm.golden('demo_inputs.npz')
+    ref = Cm.golden('ref_fit_02.npz')
+    cfg = json.loads(str(ref['cfg_json']))
+    cfg['wide_frames'] = 'off'
+    model = engine.Model(Cm.model_data(), Cm.joint_map(), dtype=torch.float32, **Cm.MODEL_KW)
+    sets = [['02_cropped', '18_cropped'], ['18_cropped', '02_cropped']]
+    args = []
+    for frames in sets:
+        data = [_frame_inputs(inp, f) for f in frames]
+        args.append((np.stack([d[0] for d in data]), [d[1] for d in data], [d[2] for d in data],
+                     dict(expose=[d[3] for d in data], pixie=[d[4] for d in data])))
+    batches = [engine.FrameBatch(model, 2) for _ in sets]
+    one = [FF.fit_frames(b, a[0], a[1], a[2], cfg, **a[3]) for b, a in zip(batches, args)]
+    streams = [torch.cuda.Stream() for _ in sets]
+    pending = []
+    for b, a, s in zip(batches, args, streams):
+        with torch.cuda.stream(s):
+            pending.append(FF.submit(b, a[0], a[1], a[2], cfg, **a[3]))
+    two = [FF.finish(p) for p in pending]
+    for o, t in zip(one, two):
+        assert np.array_equal(o.params, t.params)
+        assert np.array_equal(o.vertices, t.vertices)
+        assert np.array_equal(o.joints, t.joints)
+        assert np.array_equal(o.n_evals, t.n_evals) and np.array_equal(o.loss, t.loss)
+        assert t.h2d_bytes > 0 and t.d2h_bytes > t.vertices.nbytes
+    # same frame, other batch position and other batch: same fit
+    assert np.array_equal(two[0].params[0], two[1].params[1])
+    res = two[0].results
+    assert len(res) == 2 and res[-1] is res[1] and [r['H'] for r in res] == [int(h) for h in args[0][1]]
+    assert np.array_equal(res[0]['body_pose'].reshape(-1),
+                          two[0].params[0, batches[0].blocks['pose_embedding'][0]:][:res[0]['body_pose'].size])
