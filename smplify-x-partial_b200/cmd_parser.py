@@ -69,6 +69,9 @@ _FLAGS = [
     ('confidence_threshold', float, 0, None),
     # engine option (not in the reference): how the L-BFGS direction is computed, _native.TWO_LOOP_MODES
     ('two_loop', str, None, None),
+    # engine options (not in the reference): batches kept in flight by main.py (default 2), frames
+    # that fit two orientations on clusters of blocks ('auto' / 'off', fit_frames.upload)
+    ('batches_in_flight', int, None, None), ('wide_frames', str, None, None),
 ]
 
 

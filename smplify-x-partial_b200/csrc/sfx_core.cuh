@@ -78,6 +78,25 @@
 namespace sfx {
 
 // ------------------------------------------------------------------------------ views
+// Support tables of the 51 dynamic-contour slots for ONE row of the yaw look-up table, exactly as
+// support_slots() + support_by_joint() build them: prepared once per model for all 79 rows, so an
+// evaluation whose head yaw crossed into another row copies 5 KB instead of rebuilding them
+// (that rebuild was ~6 % of the average frame's time).
+#define SFX_NDYNSLOT (3 * SFX_NDYN)
+template <typename T>
+struct DynRowPack {
+    int vid[SFX_NDYNSLOT];
+    int jtd_ptr[SFX_NJ + 1];                 // offsets into jt_slot / jt_w (first entry SFX_NSTATIC * SFX_NW)
+    int overflow, pad;
+    T bary[SFX_NDYNSLOT];
+    T vt_s[SFX_NDYNSLOT * 3];
+    float ww[SFX_NDYNSLOT * SFX_NW];
+    float jt_w[SFX_NDYNSLOT * SFX_NW];
+    unsigned char wn[SFX_NDYNSLOT + 1];
+    unsigned char wj[SFX_NDYNSLOT * SFX_NW];
+    unsigned char jt_slot[SFX_NDYNSLOT * SFX_NW];
+};
+
 template <typename T>
 struct ModelView {
     int V, NS, NB, NE, NH, K, NJOUT, use_contour, n_neck, nlev;
@@ -96,6 +115,7 @@ struct ModelView {
     const T* lmk_bary;   // [51*3]
     const int* dyn_vid;  // [79][51]        vertex ids of the contour landmarks per yaw row
     const T* dyn_bary;   // [79][51]
+    const DynRowPack<T>* dyn_pack;   // [79] (one entry without the contour) prepared support tables, or nullptr
     const int* joint_map;   // [K]  keypoint -> model joint (JointMapper, utils.py:68-81)
     const int* inv_ptr;     // [NJOUT+1]  model joint -> keypoints (CSR)
     const int* inv_idx;     // [K]
@@ -337,8 +357,36 @@ SFX_FN T block_reduce(int n, F f, Op op, T init, T* slot) {
 
 template <typename T>
 struct OpAdd { SFX_MFN T operator()(T a, T b) const { return a + b; } };
+
 template <typename T>
 struct OpMax { SFX_MFN T operator()(T a, T b) const { return a > b ? a : b; } };
+
+// Two reductions over the same index range in one pair of barriers: warp 0 takes the first,
+// warp 1 the second, each exactly as block_reduce() would (same partial sums, same butterfly).
+template <typename T, typename F0, typename Op0, typename F1, typename Op1>
+SFX_FN void block_reduce2(int n, F0 f0, Op0 op0, T init0, F1 f1, Op1 op1, T init1, T* slots) {
+#ifdef __CUDACC__
+    SFX_SYNC();
+    if (threadIdx.x < 64) {
+        const int lane = threadIdx.x & 31;
+        if (threadIdx.x < 32) {
+            T p = init0;
+            for (int i = lane; i < n; i += 32) p = op0(p, f0(i));
+            for (int o = 16; o > 0; o >>= 1) p = op0(p, __shfl_xor_sync(0xffffffffu, p, o));
+            if (lane == 0) slots[0] = p;
+        } else {
+            T p = init1;
+            for (int i = lane; i < n; i += 32) p = op1(p, f1(i));
+            for (int o = 16; o > 0; o >>= 1) p = op1(p, __shfl_xor_sync(0xffffffffu, p, o));
+            if (lane == 0) slots[1] = p;
+        }
+    }
+    SFX_SYNC();
+#else
+    block_reduce<T>(n, f0, op0, init0, slots);
+    block_reduce<T>(n, f1, op1, init1, slots + 1);
+#endif
+}
 
 template <typename T>
 SFX_FN T block_dot(const T* a, const T* b, int n, T* slot) {
@@ -531,6 +579,27 @@ SFX_FN void support_by_joint(Scratch<T>& S, int s_begin, int s_end, int* ptr, in
                     ++pos;
                 }
     }
+    SFX_SYNC();
+}
+
+// The dynamic slots' tables of one yaw row from the model's prepared copy (same contents as
+// support_slots + support_by_joint over [NSTATIC, NSLOT)).  Ends synchronised.
+template <typename T>
+SFX_FN void support_load_dyn_row(const DynRowPack<T>& P, Scratch<T>& S) {
+    SFX_FOR(i, SFX_NDYNSLOT) {
+        S.vid[SFX_NSTATIC + i] = P.vid[i];
+        S.bary[SFX_NSTATIC + i] = P.bary[i];
+        S.wn[SFX_NSTATIC + i] = P.wn[i];
+    }
+    SFX_FOR_FROM(i, SFX_NDYNSLOT * 3, 64) S.vt_s[3 * SFX_NSTATIC + i] = P.vt_s[i];
+    SFX_FOR_FROM(i, SFX_NJ + 1, 256) S.jtd_ptr[i] = P.jtd_ptr[i];
+    SFX_FOR(i, SFX_NDYNSLOT * SFX_NW) {
+        S.wj[SFX_NSTATIC * SFX_NW + i] = P.wj[i];
+        S.ww[SFX_NSTATIC * SFX_NW + i] = P.ww[i];
+        S.jt_slot[SFX_NSTATIC * SFX_NW + i] = P.jt_slot[i];
+        S.jt_w[SFX_NSTATIC * SFX_NW + i] = P.jt_w[i];
+    }
+    if (SFX_TID == 0 && P.overflow) S.w_overflow = 1;
     SFX_SYNC();
 }
 
@@ -836,8 +905,12 @@ SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>&
     }
     if (S.dynrow != S.dynrow_cached) {          // uniform: dynrow was written before the barrier
         SFX_SYNC();
-        support_slots(M, S, SFX_NSTATIC, SFX_NSLOT);
-        support_by_joint(S, SFX_NSTATIC, SFX_NSLOT, S.jtd_ptr, SFX_NSTATIC * SFX_NW);
+        if (M.dyn_pack) {
+            support_load_dyn_row(M.dyn_pack[M.use_contour ? S.dynrow : 0], S);
+        } else {
+            support_slots(M, S, SFX_NSTATIC, SFX_NSLOT);
+            support_by_joint(S, SFX_NSTATIC, SFX_NSLOT, S.jtd_ptr, SFX_NSTATIC * SFX_NW);
+        }
         if (SFX_TID == 0) {
             S.dynrow_cached = S.dynrow;
             S.rows_dirty = 1;
@@ -1629,14 +1702,13 @@ SFX_FN void vcopy(T* dst, const T* src, int n) {
 // Gradient slots: g_prev (bracket phase "previous"), bg0 / bg1 (bracket ends), q (new probe).
 template <typename T>
 SFX_FN double strong_wolfe(const EvalCtx<T>& E, Scratch<T>& S, double* t_io, double f, double gtd,
-                           int* n_evals_out) {
+                           double d_norm, int* n_evals_out) {
     const SfxStage& st = *E.st;
     const int D = st.n_active;
     const double c1 = 1e-4, c2 = 0.9;
     const int max_ls = 25;
     const int max_iter = st.max_iter;
     double t = *t_io;
-    const double d_norm = (double)block_absmax(S.d, D, &S.red[2]);
     double gtd_new;
     double f_new = probe(E, S, t, S.q, &gtd_new);
     int evals = 1;
@@ -2259,7 +2331,14 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
                 S.q[i] = S.g[i] - S.prev_g[i];
                 S.x0[i] = S.d[i] * tt;
             }
-            T ys = block_dot(S.q, S.x0, D, &S.red[2]);
+            // y.s and y.y in one pass (y.y is only used when the pair is accepted)
+            {
+                const T* qv = S.q;
+                const T* sv = S.x0;
+                block_reduce2<T>(D, [=](int i) { return qv[i] * sv[i]; }, OpAdd<T>(), (T)0,
+                                 [=](int i) { return qv[i] * qv[i]; }, OpAdd<T>(), (T)0, &S.red[2]);
+            }
+            const T ys = S.red[2], yy_pair = S.red[3];
             bool has_new = false;
             if (ys > (T)1e-10) {
                 has_new = true;
@@ -2287,8 +2366,7 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
                 asm volatile("fence.proxy.async.global;" ::: "memory");
 #endif
                 if (SFX_TID == 0) S.ro[ls.num_old - 1] = (T)1 / ys;
-                T yy = block_dot(S.q, S.q, D, &S.red[2]);
-                ls.H_diag = ys / yy;
+                ls.H_diag = ys / yy_pair;
             }
             // two-loop recursion
             SFX_LAP(S, 24);               // history update (y, s, ys, yy)
@@ -2345,7 +2423,14 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
         } else {
             t = st.lr;
         }
-        double gtd = (double)block_dot(S.g, S.d, D, &S.red[2]);
+        // g.d and max |d| (the line search's d_norm) in one pass
+        {
+            const T* gv = S.g;
+            const T* dv = S.d;
+            block_reduce2<T>(D, [=](int i) { return gv[i] * dv[i]; }, OpAdd<T>(), (T)0,
+                             [=](int i) { return sfx_abs(dv[i]); }, OpMax<T>(), (T)0, &S.red[2]);
+        }
+        const double gtd = (double)S.red[2], d_norm = (double)S.red[3];
         if (gtd > -st.tol_change) {
             ls.t = t;
             break;
@@ -2353,7 +2438,7 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
         vcopy(S.x0, S.xa, D);      // x_init
         SFX_LAP(S, 26);                   // step length, gtd, copies before the line search
         int ls_evals = 0;
-        loss = strong_wolfe(E, S, &t, loss, gtd, &ls_evals);
+        loss = strong_wolfe(E, S, &t, loss, gtd, d_norm, &ls_evals);
         SFX_LAP(S, 27);                   // line-search epilogue (after the last probe)
         {
             const T tt = (T)t;
@@ -2361,18 +2446,21 @@ SFX_FN double lbfgs_step(const EvalCtx<T>& E, Scratch<T>& S, LbfgsState<T>& ls, 
             SFX_SYNC();
         }
         ls.t = t;
-        bool opt_cond = (double)block_absmax(S.g, D, &S.red[2]) <= st.tol_grad;
+        // max |g| (optimality) and max |d t| (step size test) in one pass
+        {
+            const T tt = (T)t;
+            const T* gv = S.g;
+            const T* dd = S.d;
+            block_reduce2<T>(D, [=](int i) { return sfx_abs(gv[i]); }, OpMax<T>(), (T)0,
+                             [=](int i) { return sfx_abs(dd[i] * tt); }, OpMax<T>(), (T)0, &S.red[2]);
+        }
+        const bool opt_cond = (double)S.red[2] <= st.tol_grad;
+        const double step_max = (double)S.red[3];
         current_evals += ls_evals;
         if (n_iter == st.max_iter) break;
         if (current_evals >= st.max_eval) break;
         if (opt_cond) break;
-        {
-            const T tt = (T)t;
-            const T* dd = S.d;
-            T mx = block_reduce<T>(D, [=](int i) { return sfx_abs(dd[i] * tt); }, OpMax<T>(), (T)0,
-                                   &S.red[2]);
-            if ((double)mx <= st.tol_change) break;
-        }
+        if (step_max <= st.tol_change) break;
         if (fabs(loss - ls.prev_loss) < st.tol_change) break;
     }
     scatter_active(S, D);

@@ -576,7 +576,7 @@ struct sfx_model {
     ModelView<float> vf;
     ModelView<double> vd;
     DevBuf PK, vt, J0, JS, Wd, hand_l, hand_r, pose_mean, sv_vid, lmk_bary, dyn_vid, dyn_bary,
-        joint_map, inv_ptr, inv_idx, faces, gmm_means, gmm_prec, gmm_logw, vp_w1, vp_b1, vp_w2,
+        joint_map, inv_ptr, inv_idx, faces, dyn_pack, gmm_means, gmm_prec, gmm_logw, vp_w1, vp_b1, vp_w2,
         vp_b2, vp_w3, vp_b3, part_ptr, part_faces, face_part, part_allow, vf_ptr, vf_idx, sk_ptr,
         sk_j, sk_w, cl_ptr, part_cl_ptr;
     std::vector<int> faces_host;
@@ -614,6 +614,8 @@ static int upload_model(const sfx_model_desc& d, sfx_model* m, ModelView<T>& vie
     CUDA_TRY(m->sk_ptr.upload(h.sk_ptr));
     CUDA_TRY(m->sk_j.upload(h.sk_j));
     CUDA_TRY(m->sk_w.upload(h.sk_w));
+    CUDA_TRY(m->dyn_pack.upload(h.dyn_pack));
+    view.dyn_pack = (const DynRowPack<T>*)m->dyn_pack.p;
     view.sk_ptr = (const int*)m->sk_ptr.p; view.sk_j = (const unsigned char*)m->sk_j.p;
     view.sk_w = (const T*)m->sk_w.p;
     m->faces_host = h.faces;

@@ -1,6 +1,7 @@
 // Host-side re-layout of the raw SMPL-X arrays (sfx_model_desc) into the tables the kernels
 // read.  Pure C++ (no CUDA) so the library and the host-simulation tests share it.
 #pragma once
+#include <string.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -17,6 +18,7 @@ struct HostModel {
     std::vector<int> sv_vid, dyn_vid, joint_map, inv_ptr, inv_idx, faces, sk_ptr;
     std::vector<unsigned char> sk_j;
     std::vector<T> sk_w;
+    std::vector<DynRowPack<T>> dyn_pack;     // support tables of the dynamic-contour slots per yaw row
     int parents[SFX_NJ], order[SFX_NJ], level_off[16], nlev = 0;
     int child_off[SFX_NJ + 1], child_idx[SFX_NJ], neck[8], n_neck = 0;
 
@@ -30,6 +32,7 @@ struct HostModel {
         m.part_faces = nullptr; m.n_clusters = 0; m.cl_ptr = nullptr; m.part_cl_ptr = nullptr;
         m.face_part = nullptr; m.part_allow = nullptr; m.vf_ptr = nullptr;
         m.vf_idx = nullptr;
+        m.dyn_pack = nullptr;
         for (int i = 0; i < SFX_NJ; ++i) { m.parents[i] = parents[i]; m.order[i] = order[i]; }
         for (int i = 0; i < 16; ++i) m.level_off[i] = level_off[i];
         for (int i = 0; i <= SFX_NJ; ++i) m.child_off[i] = child_off[i];
@@ -45,6 +48,7 @@ struct HostModel {
         m.dyn_bary = dyn_bary.data(); m.joint_map = joint_map.data();
         m.inv_ptr = inv_ptr.data(); m.inv_idx = inv_idx.data();
         m.sk_ptr = sk_ptr.data(); m.sk_j = sk_j.data(); m.sk_w = sk_w.data();
+        m.dyn_pack = dyn_pack.empty() ? nullptr : dyn_pack.data();
         return m;
     }
 };
@@ -192,6 +196,41 @@ std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
                         (T)d.dyn_lmk_bary_coords[(y * SFX_NDYN + i) * 3 + k];
                 }
             }
+    }
+    // --- support tables of the dynamic-contour slots, one per yaw row: what the evaluation's
+    //     support_slots() + support_by_joint() would build (sfx_core.cuh), done once here ---
+    {
+        const int rows = h.use_contour ? SFX_NDYNROWS : 1;
+        h.dyn_pack.assign(rows, DynRowPack<T>());
+        for (int y = 0; y < rows; ++y) {
+            DynRowPack<T>& P = h.dyn_pack[y];
+            memset(&P, 0, sizeof(P));
+            for (int i = 0; i < SFX_NDYNSLOT; ++i) {
+                const int vid = h.use_contour ? h.dyn_vid[y * 51 + i] : h.sv_vid[0];
+                P.vid[i] = vid;
+                P.bary[i] = h.use_contour ? h.dyn_bary[y * 51 + i] : (T)0;
+                for (int k = 0; k < 3; ++k) P.vt_s[3 * i + k] = h.vt[3L * vid + k];
+                const int e0 = h.sk_ptr[vid], n = h.sk_ptr[vid + 1] - e0;
+                for (int e = 0; e < n && e < SFX_NW; ++e) {
+                    P.wj[i * SFX_NW + e] = h.sk_j[e0 + e];
+                    P.ww[i * SFX_NW + e] = (float)h.sk_w[e0 + e];
+                }
+                P.wn[i] = (unsigned char)(n <= SFX_NW ? n : SFX_NW);
+                if (n > SFX_NW) P.overflow = 1;
+            }
+            int pos = SFX_NSTATIC * SFX_NW;
+            for (int j = 0; j < SFX_NJ; ++j) {
+                P.jtd_ptr[j] = pos;
+                for (int i = 0; i < SFX_NDYNSLOT; ++i)
+                    for (int e = 0; e < P.wn[i]; ++e)
+                        if (P.wj[i * SFX_NW + e] == j) {
+                            P.jt_slot[pos - SFX_NSTATIC * SFX_NW] = (unsigned char)(SFX_NSTATIC + i);
+                            P.jt_w[pos - SFX_NSTATIC * SFX_NW] = P.ww[i * SFX_NW + e];
+                            ++pos;
+                        }
+            }
+            P.jtd_ptr[SFX_NJ] = pos;
+        }
     }
     // --- joint mapper and its inverse ---
     h.joint_map.resize(h.K);

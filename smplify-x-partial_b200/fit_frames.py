@@ -418,7 +418,7 @@ def upload(batch, plan):
     # (the library takes as many as fit next to the one-block frames).  cfg['wide_frames']: 'auto'
     # (default) or 'off' (every frame by one block: the bit-reproducible reference path)
     n_wide = 0
-    if plan.cfg.get('wide_frames', 'auto') != 'off' and plan.order_dev is not None \
+    if (plan.cfg.get('wide_frames') or 'auto') != 'off' and plan.order_dev is not None \
             and plan.collision is None and plan.np_dtype == np.float32:
         n_wide = len(plan.flip_ids)
     plan.pipeline = N.make_pipeline(plan.cam_stage, plan.stages, n_wide)

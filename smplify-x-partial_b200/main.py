@@ -6,7 +6,8 @@
 Same YAML keys / flags, same outputs (``<output>/results/<fn>/000.pkl``, ``vertices.ply``,
 ``conf.yaml``).  Unlike the reference, which fits image after image, the frames of the data
 folder are packed ``batch_size`` at a time and each batch is fitted in one persistent CUDA
-launch (``fit_frames.fit_frames``); with ``torchrun`` the image list is sharded over the ranks
+launch (``fit_frames.submit`` / ``finish``, ``batches_in_flight`` of them overlapping on their own
+CUDA streams); with ``torchrun`` the image list is sharded over the ranks
 (each rank reads only its own frames), and the fitted parameter rows are all-gathered once at the
 end (``sharding.gather_frames``): rank 0 writes ``<output>/fitted_params.npz`` (frame names,
 [n, np] parameter table, layout offsets) next to the per-frame pickles every rank writes.
@@ -97,25 +98,19 @@ def main(**args):
     args.setdefault('device_ingest', True)       # masks / thresholds on the device (sfx_keypoint_masks)
     names, rows = [], []
     L = None
-    for lo in range(0, len(paths), bs):
-        chunk = [d for d in (dataset.read_meta(p) for p in paths[lo:lo + bs]) if d]
-        if not chunk:
-            continue
-        B = len(chunk)
-        kp = np.stack([d['keypoints'][0] for d in chunk])          # person 0 only (main.py:242-246)
-        H = [d['H'] for d in chunk]
-        W = [d['W'] for d in chunk]
-        if args.get('focal_length') is None:
-            # the reference stores the first image's focal length back into its arguments
-            # (main.py:212-218): every later image of the folder re-uses it
-            args['focal_length'] = float((W[0] ** 2 + H[0] ** 2) ** 0.5)
-        reg = [_load_regression(args, d['fn']) for d in chunk]
-        batch = engine.FrameBatch(model, B, use_vposer=bool(args.get('use_vposer')))
-        L = batch.L
-        out = FF.fit_frames(batch, kp, H, W, args, expose=[r[1] for r in reg],
-                            pixie=[r[0] for r in reg], pare=[r[2] for r in reg],
-                            return_verts=bool(args.get('save_vertices')),
-                            body_pose_prior=body_pose_prior, vposer=vposer)
+    # batches in flight (key batches_in_flight, default 2): batch i + 1 is read, planned and queued
+    # on its own FrameBatch / CUDA stream while batch i is being fitted, so the straggler frames
+    # of one batch overlap the next batch's frames and the host work hides behind the device
+    in_flight = max(1, int(args.get('batches_in_flight') or 2))
+    if args.get('interpenetration'):
+        in_flight = 1                               # 4.9 MB of workspace per frame and batch
+    use_vposer = bool(args.get('use_vposer'))
+    slots = [None] * in_flight                      # FrameBatch per slot (re-made when B changes)
+    streams = [torch.cuda.Stream(device=model.device) for _ in range(in_flight)]
+    pending = []
+
+    def write_results(chunk, pf):
+        out = FF.finish(pf)
         for b, d in enumerate(chunk):
             print('Processing: {}'.format(d['img_path']))
             fl = int(out.flags[b])
@@ -133,7 +128,41 @@ def main(**args):
                 write_ply_vertices(os.path.join(folder, 'vertices.ply'), out.vertices[b])
             names.append(d['fn'])
             rows.append(out.params[b])
-        batch.close()
+
+    step = 0
+    for lo in range(0, len(paths), bs):
+        chunk = [d for d in (dataset.read_meta(p) for p in paths[lo:lo + bs]) if d]
+        if not chunk:
+            continue
+        B = len(chunk)
+        kp = np.stack([d['keypoints'][0] for d in chunk])          # person 0 only (main.py:242-246)
+        H = [d['H'] for d in chunk]
+        W = [d['W'] for d in chunk]
+        if args.get('focal_length') is None:
+            # the reference stores the first image's focal length back into its arguments
+            # (main.py:212-218): every later image of the folder re-uses it
+            args['focal_length'] = float((W[0] ** 2 + H[0] ** 2) ** 0.5)
+        reg = [_load_regression(args, d['fn']) for d in chunk]
+        k = step % in_flight
+        step += 1
+        if len(pending) == in_flight:                              # slot k's previous fit
+            write_results(*pending.pop(0))
+        if slots[k] is None or slots[k].B != B:
+            if slots[k] is not None:
+                slots[k].close()
+            slots[k] = engine.FrameBatch(model, B, use_vposer=use_vposer)
+        L = slots[k].L
+        with torch.cuda.stream(streams[k]):
+            pf = FF.submit(slots[k], kp, H, W, args, expose=[r[1] for r in reg],
+                           pixie=[r[0] for r in reg], pare=[r[2] for r in reg],
+                           return_verts=bool(args.get('save_vertices')),
+                           body_pose_prior=body_pose_prior, vposer=vposer)
+        pending.append((chunk, pf))
+    while pending:
+        write_results(*pending.pop(0))
+    for sl in slots:
+        if sl is not None:
+            sl.close()
     # one all-gather of the fitted parameter rows: rank 0 writes the whole job's table
     if world > 1:
         dev = model.device
