@@ -1385,8 +1385,20 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
     SFX_FOR(t, 512) {
         const int sidx = t & 31, part = t >> 5;
         T acc = 0;
-        if (sidx < NS)
-            for (int i = part; i < SFX_NJ * 3; i += 16) acc += M.JS[i * 32 + sidx] * S.gl[i];
+        if (sidx < NS) {
+            constexpr int NT = (SFX_NJ * 3 + 15) / 16;     // terms per thread (global loads: all in flight)
+            T jv[NT];
+#pragma unroll
+            for (int u = 0; u < NT; ++u) {
+                const int i = part + 16 * u;
+                jv[u] = i < SFX_NJ * 3 ? M.JS[i * 32 + sidx] : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < NT; ++u) {
+                const int i = part + 16 * u;
+                if (i < SFX_NJ * 3) acc += jv[u] * S.gl[i];
+            }
+        }
         S.c[t] = acc;
     }
     SFX_SYNC();
@@ -1479,8 +1491,16 @@ SFX_FN_NOINLINE void eval_frame(const ModelView<T>& M, const SfxLayout& L, const
             T acc = 0;
             if (S.hand_cached) {
                 const float* C = S.hand_c + (h * L.n_hand + k) * 45;
-                for (int e = 0; e < 45; ++e)
-                    acc += (T)C[e] * (dh[e] + (body ? (T)2 * hw2 * hv[e] : (T)0));
+                for (int e0 = 0; e0 < 45; e0 += 5) {       // operands of five terms first, sums in order
+                    T cv[5], tv[5];
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) {
+                        cv[u] = (T)C[e0 + u];
+                        tv[u] = dh[e0 + u] + (body ? (T)2 * hw2 * hv[e0 + u] : (T)0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) acc += cv[u] * tv[u];
+                }
             } else {
                 const T* C = (h ? M.hand_r : M.hand_l) + k * 45;
                 for (int e = 0; e < 45; ++e)
