@@ -52,7 +52,8 @@ ROW_BYTES = 512 * 4
 NCU_TRAFFIC_BYTES = {'gram_reg': (24584448.0, 'profiles/r01v_ncu_raw_pipeline_kernel.csv'),
                      'exact_reg': (12591616.0, 'profiles/r01p_ncu_raw_pipeline_kernel.csv'),
                      # default workload, round 2: one-block grid 11.02 + 13.34 MB, wide grid 2.24 + 0.06 MB
-                     'gram': (26652928.0, 'profiles/r02l_ncu_raw_pipeline_kernel.csv')}
+                     # default workload, round 2, one-block grid (what runs with steps in flight): 11.46 + 12.04 MB
+                     'gram': (23501568.0, 'profiles/r02u_ncu_raw_pipeline_kernel.csv')}
 
 
 # ------------------------------------------------------------------------------ workload
@@ -64,6 +65,7 @@ TWO_LOOP = os.environ.get('SFX_TWO_LOOP', 'gram')
 # frames on clusters of blocks (fit_frames cfg key wide_frames) only while one step runs at a time:
 # with several steps in flight every SM is busy and a cluster's helpers would take SMs from frames
 WIDE_IN_FLIGHT = 'off'
+SM_CLOCK_KHZ = 1965.0e3      # clock64 ticks per millisecond at the 1965 MHz SM clock of the B200 (see clocks.sm_mhz)
 
 
 def bench_cfg(interpenetration=False, vposer=False, regression_prior=False, two_loop=None):
@@ -688,6 +690,7 @@ def run_b200(args):
             return resident_step
 
         mplans, x0s = make_plans(WIDE_IN_FLIGHT if depth > 1 else 'auto')
+        plans[mode] = mplans[0]                     # the launch configuration `value` is measured with
         step = make_step(mplans, x0s)
         timed_steps(step, depth, args.warmup)
         if rank == 0 and mi == 0:
@@ -702,7 +705,6 @@ def run_b200(args):
             timed_serial[mode], _ = timed_steps(step, 1, args.steps)
         else:
             timed_serial[mode] = timed[mode]
-        plans[mode] = mplans[0]
     total_ms_rank = timed[TWO_LOOP]
     total_ms = reduce_max(total_ms_rank)
     total_ms_serial = reduce_max(timed_serial[TWO_LOOP])
@@ -761,6 +763,7 @@ def run_b200(args):
     b_.record()
     torch.cuda.synchronize()
     kern_ms = a.elapsed_time(b_)
+    frame_cycles = batch.frame_cycles().cpu().numpy().astype(np.float64)
     passes = batch.passes().cpu().numpy().astype(np.int64)
     evals = batch.evals().cpu().numpy().astype(np.int64)
     row_bytes = float(passes.sum()) * ROW_BYTES        # rows of the blend matrix streamed x 2 KiB
@@ -802,12 +805,16 @@ def run_b200(args):
                                     'sweeping a 48 MiB L2-resident buffer)'},
         'evals_max_frame': int(evals.max()), 'evals_min_frame': int(evals.min()),
         'sm_time_busy_frac': float(evals.sum()) / (float(evals.max()) * model_sms(batch)),
+        'frame_ms_mean_max': [float(frame_cycles.mean() / SM_CLOCK_KHZ), float(frame_cycles.max() / SM_CLOCK_KHZ)],
         'note': 'per-frame serial latency bound (DESIGN.md section 4): executed flops = blend '
                 'rows streamed x 1024 + evaluations x {:.0f}; skipped full-mesh work is not '
                 'credited.  The blend rows are shared by all frames and served from L2: '
                 'l2_to_sm is that stream against the measured L2 read peak; hbm is the ncu '
                 'dram traffic of the launch.  sm_time_busy_frac = sum of evaluations / '
-                '(evaluations of the longest frame x SMs): the single-wave tail'.format(
+                '(evaluations of the longest frame x SMs): the single-wave tail of ONE launch '
+                '(kernel_ms_per_step, this launch alone); sm_time_busy_frac_measured the same from '
+                'the per-frame cycle counters; sm_time_busy_frac_in_flight = the frames\' SM-time '
+                'over SMs x ms_per_step with the steps overlapping'.format(
                     EVAL_FIXED_FLOPS)}
     coll_stats = batch.coll_stats()
     if coll_stats is not None:
@@ -830,8 +837,10 @@ def run_b200(args):
 
     value = world * B * args.steps / (total_ms * 1e-3)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
-    roofline['sm_time_busy_frac_in_flight'] = min(1.0, roofline['sm_time_busy_frac'] * kern_ms /
-                                                 (total_ms / args.steps))
+    # SM-time the frames of one step occupy (clock64 per frame, one block each) over SMs x step time
+    sm_ms = float(frame_cycles.sum() / SM_CLOCK_KHZ)
+    roofline['sm_time_busy_frac_measured'] = sm_ms / (model_sms(batch) * kern_ms)
+    roofline['sm_time_busy_frac_in_flight'] = sm_ms / (model_sms(batch) * (total_ms / args.steps))
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,

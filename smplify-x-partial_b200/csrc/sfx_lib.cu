@@ -436,6 +436,7 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> Mp, const __grid_consta
         const int f = Bv.frame_ids ? Bv.frame_ids[idx] : idx;
         load_frame(Bv, f, S);
         T* alt = alt_rows + (size_t)f * np;      // first orientation's result (global: one row per frame)
+        const long long t_frame = clock64();     // SM cycles this block spends on the frame (slot 4 of prof)
         SFX_PROF_BEGIN(total);
         support_begin_frame(M, S);
         if (threadIdx.x == 0) {
@@ -513,6 +514,8 @@ fit_pipeline_kernel(const __grid_constant__ ModelView<T> Mp, const __grid_consta
             S.prof[4] += clock64() - _t_total;
             for (int i = 0; i < 16; ++i) Bv.prof[(size_t)f * 64 + i] = S.prof[i];
             for (int i = 0; i < SFX_NLAP; ++i) Bv.prof[(size_t)f * 64 + 16 + i] = S.lap[i];
+#else
+            if (Bv.prof) Bv.prof[(size_t)f * 64 + 4] = clock64() - t_frame;
 #endif
         }
     }

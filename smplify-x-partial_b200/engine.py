@@ -322,6 +322,15 @@ class FrameBatch(object):
         ptr = self.lib.sfx_batch_flags_dev(self.h)
         return _wrap(ptr, (self.B,), torch.int32, self.model.device, self)
 
+    def frame_cycles(self):
+        """[B] int64: SM cycles the block(s) of the last pipeline launch spent on each frame (the
+        leader block of a frame that ran on a cluster)."""
+        self.lib.sfx_batch_prof_dev.restype = C.c_void_p
+        self.lib.sfx_batch_prof_dev.argtypes = [C.c_void_p]
+        ptr = self.lib.sfx_batch_prof_dev(self.h)
+        raw = _wrap(ptr, (self.B * 128,), torch.int32, self.model.device, self)
+        return raw.view(torch.int64).view(self.B, 64)[:, 4]
+
     def coll_stats(self):
         """[B, 4] int32 per frame, largest over its evaluations of the interpenetration term:
         candidate faces, touched vertices, sweep iterations and listed partners of warp 0 (None
