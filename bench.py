@@ -460,10 +460,10 @@ def run_reference(args):
 
 
 def steps_in_flight(args):
-    return 1 if args.interpenetration else max(1, int(getattr(args, 'depth', 4)))
+    return 1 if args.interpenetration else max(1, int(getattr(args, 'depth', 6)))
 
 
-def workload_config(B, n_gpus, interpenetration=False, vposer=False, regression_prior=False, depth=4):
+def workload_config(B, n_gpus, interpenetration=False, vposer=False, regression_prior=False, depth=6):
     common = {'frames_per_gpu': B, 'global_frames': B * n_gpus,
               'steps_in_flight': '{} (engine arm: consecutive steps alternate between that many '
                                  'FrameBatch objects on their own CUDA streams, so the straggler '
@@ -935,7 +935,7 @@ def main():
                          "recursion) or 'exact' (the reference's operation order); the other "
                          "one is reported as value_<mode>")
     ap.add_argument('--single-mode', action='store_true', help='time only the default two-loop mode')
-    ap.add_argument('--depth', type=int, default=4,
+    ap.add_argument('--depth', type=int, default=6,
                     help='steps in flight (each on its own FrameBatch and CUDA stream); 1 = one batch '
                          'at a time')
     ap.add_argument('--traffic', type=float, default=None,

@@ -124,6 +124,16 @@ int sfx_batch_set_params(sfx_batch* b, const void* host_params, void* stream);
 int sfx_batch_get_params(const sfx_batch* b, void* host_params, void* stream);
 void* sfx_batch_params_dev(sfx_batch* b);
 
+/* fitting.guess_init (fitting.py:36-110) on the device, for the frames with need[b] != 0: camera
+ * translation (0, 0, focal[b] * mean 3-D edge length / mean_len2d[b]) written into the frame's
+ * parameter vector and into its depth-prior target (cam row, trans_estimation z,
+ * fit_single_frame.py:404-411).  joints_dev: the mapped model joints [B,K,3] at the initial
+ * parameters (sfx_eval); edge_idxs: n_edges pairs of keypoint indices (body_tri_idxs); focal,
+ * mean_len2d, need: HOST arrays of B entries (copied before the call returns).  Double
+ * arithmetic in the order of the host formula, so no host round trip is needed before the fit. */
+int sfx_batch_guess_init(sfx_batch* b, const void* joints_dev, const int32_t* edge_idxs, int32_t n_edges,
+                         const double* focal, const double* mean_len2d, const uint8_t* need, void* stream);
+
 /* One closure evaluation for every frame: loss [B] and gradient [B,np] w.r.t. the whole
  * parameter vector.  Stands in for FittingMonitor.create_fitting_closure's fitting_func
  * (fitting.py:232-273): SMPL-X forward + SMPLifyLoss / SMPLifyCameraInitLoss + backward.

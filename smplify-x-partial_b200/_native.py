@@ -311,6 +311,7 @@ def load_library(path=None):
     lib.sfx_batch_passes_dev.restype = vp
     lib.sfx_batch_reset_counters.argtypes = [vp, vp]
     lib.sfx_aligned_errors.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.sfx_batch_guess_init.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     lib.sfx_pack_keypoints.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.sfx_keypoint_masks.argtypes = [vp, vp, vp, i32, i32, C.c_float, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.sfx_blend_keypoints.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]

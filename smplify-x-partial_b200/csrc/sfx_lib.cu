@@ -351,6 +351,35 @@ __global__ void select_orientation_kernel(BatchView<T> Bv, const T* params_alt, 
     }
 }
 
+// fitting.guess_init (fitting.py:36-110): similar-triangles depth from the mean 3-D and 2-D edge
+// lengths, one thread per frame, double arithmetic without contraction in the order of the host
+// mirror (fit_frames.guess_init_depth: numpy float64), result rounded to the batch dtype.
+#define SFX_GUESS_EDGES_MAX 16
+struct GuessEdges { int n; int idx[2 * SFX_GUESS_EDGES_MAX]; };
+template <typename T>
+__global__ void guess_init_kernel(BatchView<T> Bv, const T* __restrict__ joints, int K, GuessEdges E,
+                                  const double* __restrict__ focal, const double* __restrict__ len2d,
+                                  const unsigned char* __restrict__ need, T* cam) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Bv.B || !need[f]) return;
+    const T* J = joints + (size_t)f * K * 3;
+    double sum = 0.0;
+    for (int e = 0; e < E.n; ++e) {
+        const T* a = J + 3 * E.idx[2 * e];
+        const T* b = J + 3 * E.idx[2 * e + 1];
+        const double dx = __dsub_rn((double)a[0], (double)b[0]);
+        const double dy = __dsub_rn((double)a[1], (double)b[1]);
+        const double dz = __dsub_rn((double)a[2], (double)b[2]);
+        const double l = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        sum = e == 0 ? l : __dadd_rn(sum, l);
+    }
+    const double mean3 = __ddiv_rn(sum, (double)E.n);
+    const T est = (T)__dmul_rn(focal[f], __ddiv_rn(mean3, len2d[f]));
+    T* x = Bv.params + (size_t)f * Bv.lay.np + Bv.lay.off_camt;
+    x[0] = 0; x[1] = 0; x[2] = est;
+    cam[(size_t)f * SFX_CAM_STRIDE + SFX_CAM_TZ] = est;
+}
+
 // ---- the whole per-frame pipeline in one launch -----------------------------------------------
 // Persistent blocks pull frames from a counter (frames that need the second orientation are
 // listed first by the host); a frame never waits for the slowest frame of a stage, and the
@@ -640,7 +669,7 @@ struct sfx_batch {
     size_t es = 4;        // element size of the batch dtype
     DevBuf params, gt, conf, jw, lowconf, init_mask, cam, reg_pose, hist_s, hist_y, gram, final_loss,
         n_evals, n_passes, flags, Acoef, Ccoef, vposed, ahi, alo, go_saved, params_alt, loss_alt, pipe, counter,
-        cam_loss, params_last, prof, coll_vals, coll_idx, coll_stat;
+        cam_loss, params_last, prof, coll_vals, coll_idx, coll_stat, guess;
     bool last_valid = false;
     bool has_reg = false;
 
@@ -896,6 +925,7 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     ALLOC(cam_loss, (size_t)B * es);
     ALLOC(prof, (size_t)B * 64 * sizeof(long long));
     ALLOC(params_last, (size_t)B * b->lay.np * es);
+    ALLOC(guess, (size_t)B * (2 * sizeof(double) + 8));
 #undef ALLOC
     *out = b;
     return SFX_OK;
@@ -1025,6 +1055,36 @@ static int check_stage(const sfx_batch* b, const SfxStage* st) {
                                      "sfx_batch_enable_collisions");
         if (!(st->coll_sigma > 0)) return fail(SFX_ERR_ARG, "stage: coll_sigma (df_cone_height) must be positive");
     }
+    return SFX_OK;
+}
+
+int sfx_batch_guess_init(sfx_batch* b, const void* joints_dev, const int32_t* edge_idxs, int32_t n_edges,
+                         const double* focal, const double* mean_len2d, const uint8_t* need, void* stream) {
+    if (!b || !joints_dev || !edge_idxs || !focal || !mean_len2d || !need)
+        return fail(SFX_ERR_ARG, "null argument");
+    if (n_edges < 1 || n_edges > SFX_GUESS_EDGES_MAX) return fail(SFX_ERR_ARG, "guess_init: 1..16 edges");
+    GuessEdges E;
+    E.n = n_edges;
+    for (int i = 0; i < 2 * n_edges; ++i) {
+        if (edge_idxs[i] < 0 || edge_idxs[i] >= b->m->K) return fail(SFX_ERR_ARG, "guess_init: edge index out of range");
+        E.idx[i] = edge_idxs[i];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = b->B;
+    double* d_focal = (double*)b->guess.p;
+    double* d_len = d_focal + B;
+    unsigned char* d_need = (unsigned char*)(d_len + B);
+    CUDA_TRY(cudaMemcpyAsync(d_focal, focal, B * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_len, mean_len2d, B * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_need, need, B, cudaMemcpyHostToDevice, s));
+    const int grid = (int)((B + 127) / 128);
+    if (b->m->use_double)
+        guess_init_kernel<double><<<grid, 128, 0, s>>>(b->view<double>(nullptr), (const double*)joints_dev, b->m->K, E,
+                                                       d_focal, d_len, d_need, (double*)b->cam.p);
+    else
+        guess_init_kernel<float><<<grid, 128, 0, s>>>(b->view<float>(nullptr), (const float*)joints_dev, b->m->K, E,
+                                                      d_focal, d_len, d_need, (float*)b->cam.p);
+    CUDA_TRY(cudaGetLastError());
     return SFX_OK;
 }
 

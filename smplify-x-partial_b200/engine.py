@@ -322,6 +322,20 @@ class FrameBatch(object):
         ptr = self.lib.sfx_batch_flags_dev(self.h)
         return _wrap(ptr, (self.B,), torch.int32, self.model.device, self)
 
+    def guess_init(self, joints, edge_idxs, focal, mean_len2d, need):
+        """fitting.guess_init on the device (``sfx_batch_guess_init``): writes the estimated camera
+        translation of the frames flagged in ``need`` into the parameters and the depth-prior
+        target.  ``joints``: device tensor [B,K,3] from ``eval(..., want_joints=True)``."""
+        e = np.ascontiguousarray(np.asarray(edge_idxs, dtype=np.int32).reshape(-1, 2))
+        f = np.ascontiguousarray(np.broadcast_to(np.asarray(focal, dtype=np.float64), (self.B,)))
+        l2 = np.ascontiguousarray(mean_len2d, dtype=np.float64)
+        nd = np.ascontiguousarray(need, dtype=np.uint8)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        with torch.cuda.device(self.model.device):
+            N.check(self.lib, self.lib.sfx_batch_guess_init(self.h, _ptr(joints), p(e), int(e.shape[0]),
+                                                            p(f), p(l2), p(nd), _stream()))
+        return f.nbytes + l2.nbytes + nd.nbytes
+
     def frame_cycles(self):
         """[B] int64: SM cycles the block(s) of the last pipeline launch spent on each frame (the
         leader block of a frame that ran on a cluster)."""

@@ -392,16 +392,28 @@ def upload(batch, plan):
     n = _set_targets(batch, plan)
     n += batch.set_params(plan.x0)
     if plan.need_guess:
-        # guess_init needs the model joints at the initial parameters (fitting.py:36-110)
+        # guess_init needs the model joints at the initial parameters (fitting.py:36-110): evaluated
+        # and turned into the camera depth on the device (sfx_batch_guess_init, the arithmetic of
+        # guess_init_depth below), so nothing waits for the host here.  cfg['guess_init_host'] keeps
+        # the round trip (cross-check); plan.x0 / plan.cam hold the depth only on that path.
         L = plan.L
         _, _, j3 = batch.eval(plan.cam_stage, want_joints=True)
-        t = guess_init_depth(j3.cpu().numpy().astype(np.float64), plan.keypoints[:, :, :2],
-                             plan.cfg.get('body_tri_idxs', [(5, 12), (2, 9)]), plan.focal)
-        g = plan.need_guess
-        plan.x0[g, L.off_camt:L.off_camt + 3] = t[g].astype(plan.np_dtype)
-        plan.cam[:, N.SFX_CAM_TZ] = plan.x0[:, L.off_camt + 2]
-        n += _set_targets(batch, plan)
-        n += batch.set_params(plan.x0)
+        edges = plan.cfg.get('body_tri_idxs', [(5, 12), (2, 9)])
+        if plan.cfg.get('guess_init_host', False):
+            t = guess_init_depth(j3.cpu().numpy().astype(np.float64), plan.keypoints[:, :, :2],
+                                 edges, plan.focal)
+            g = plan.need_guess
+            plan.x0[g, L.off_camt:L.off_camt + 3] = t[g].astype(plan.np_dtype)
+            plan.cam[:, N.SFX_CAM_TZ] = plan.x0[:, L.off_camt + 2]
+            n += _set_targets(batch, plan)
+            n += batch.set_params(plan.x0)
+        else:
+            e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+            d2 = plan.keypoints[:, e[:, 0], :2] - plan.keypoints[:, e[:, 1], :2]
+            len2d = np.sqrt((d2 ** 2).sum(-1)).mean(axis=1)
+            need = np.zeros(plan.B, dtype=np.uint8)
+            need[plan.need_guess] = 1
+            n += batch.guess_init(j3, e, plan.focal, len2d, need)
     plan.flip_dev = plan.flip_mask_dev = plan.order_dev = None
     if len(plan.flip_ids):
         dev = batch.model.device

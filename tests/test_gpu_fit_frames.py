@@ -307,3 +307,32 @@ def test_fits_in_flight_equal_one_at_a_time():
     assert len(res) == 2 and res[-1] is res[1] and [r['H'] for r in res] == [int(h) for h in args[0][1]]
     assert np.array_equal(res[0]['body_pose'].reshape(-1),
                           two[0].params[0, batches[0].blocks['pose_embedding'][0]:][:res[0]['body_pose'].size])
+
+
+def test_guess_init_on_the_device_equals_the_host_formula():
+    """fitting.guess_init (fitting.py:36-110): the device kernel (double arithmetic in the order of
+    ``fit_frames.guess_init_depth``) writes the same camera depth, to the bit, as the host round
+    trip it replaces -- parameters, depth-prior target and the whole fit after it."""
+    import bench
+    from smplifyx_b200 import engine, fit_frames as FF, synthetic
+    G = Cm.golden('bench_parity.npz')
+    kp = G['cfg2/keypoints'][:6]
+    model = engine.Model(synthetic.cached_smplx_like(0), Cm.joint_map(), dtype=torch.float32,
+                         **bench.MODEL_KW)
+    outs = []
+    for host in (True, False):
+        cfg = bench.bench_cfg(two_loop='exact')
+        cfg['guess_init_host'] = host
+        batch = engine.FrameBatch(model, kp.shape[0])
+        plan = FF.FitPlan(batch.L, model.K, kp, 600, 800, cfg, None, None, None, np.float32)
+        assert len(plan.need_guess) == kp.shape[0]
+        FF.upload(batch, plan)
+        x0 = batch.get_params()
+        cam_loss, verts, joints, _ = FF.run(batch, plan, True)
+        outs.append((x0, FF.download(batch, plan, cam_loss, verts, joints)))
+    L = batch.L
+    assert np.all(outs[0][0][:, L.off_camt + 2] > 0.5)
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1].params, outs[1][1].params)
+    assert np.array_equal(outs[0][1].loss, outs[1][1].loss)
+    assert np.array_equal(outs[0][1].vertices, outs[1][1].vertices)
