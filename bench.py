@@ -448,7 +448,7 @@ def run_reference(args):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
         'config': workload_config(B, args.gpus, args.interpenetration, args.vposer,
-                                  args.regression_prior, steps_in_flight(args)),
+                                  args.regression_prior, steps_in_flight(args), distinct_batches(args)),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port',
                          'sample': '{} frame(s) of the batch per step, {} (the reference asserts '
                                    'batch_size == 1); mean evals/frame {:.0f}'.format(
@@ -463,8 +463,14 @@ def steps_in_flight(args):
     return 1 if args.interpenetration else max(1, int(getattr(args, 'depth', 6)))
 
 
-def workload_config(B, n_gpus, interpenetration=False, vposer=False, regression_prior=False, depth=6):
+def distinct_batches(args):
+    return 1 if args.interpenetration else max(1, int(getattr(args, 'batches', 2))) * steps_in_flight(args)
+
+
+def workload_config(B, n_gpus, interpenetration=False, vposer=False, regression_prior=False, depth=6, nb=12):
     common = {'frames_per_gpu': B, 'global_frames': B * n_gpus,
+              'batches': '{} distinct synthetic batches per rank (seed + 1000 rank + 7919 j), cycled step '
+                         'after step; the reference arm, cpu_baseline and the parity block use batch 0'.format(nb),
               'steps_in_flight': '{} (engine arm: consecutive steps alternate between that many '
                                  'FrameBatch objects on their own CUDA streams, so the straggler '
                                  'frames of one step overlap the next steps\' frames; every step is a '
@@ -572,8 +578,11 @@ def run_b200(args):
     batch = engine.FrameBatch(model, B, use_vposer=args.vposer)
     L = batch.L
 
-    # ---- synthetic inputs: GT parameters -> model joints (engine forward) -> noisy keypoints
-    gt, rng = ground_truth(B, args.seed + 1000 * rank, 0.2 if args.interpenetration else 1.0)
+    # ---- synthetic inputs: GT parameters -> model joints (engine forward) -> noisy keypoints.
+    # NB distinct batches (seeds seed + 1000 rank + 7919 j), cycled step after step: a stream of
+    # different batches, as a service sees it; batch 0 is the one the CPU arm and the parity block use
+    depth = steps_in_flight(args)                   # (config 4: one step, 0.6 GB of workspace per batch)
+    NB = distinct_batches(args)
     K = model.K
     gbatch = engine.FrameBatch(model, B) if args.vposer else batch     # axis-angle pose block
     Lg = gbatch.L
@@ -581,18 +590,23 @@ def run_b200(args):
     zero_cam = np.zeros((B, N.SFX_CAM_STRIDE))
     zero_cam[:, 0:2] = 1.0
     zero_cam[:, 4:13] = np.eye(3).reshape(-1)
-    xg = gt_param_matrix(Lg, gt)
-    xg[:, Lg.off_camt + 2] = 1.0
-    gbatch.set_targets(np.zeros((B, K, 3)), np.zeros((B, K)), np.zeros((B, K), np.uint8),
-                       np.zeros((B, K), np.uint8), zero_cam, None)
-    gbatch.set_params(xg)
-    _, _, j3 = gbatch.eval(cam_st, want_joints=True)
+    inputs = []
+    for j in range(NB):
+        gt, rng = ground_truth(B, args.seed + 1000 * rank + 7919 * j, 0.2 if args.interpenetration else 1.0)
+        xg = gt_param_matrix(Lg, gt)
+        xg[:, Lg.off_camt + 2] = 1.0
+        gbatch.set_targets(np.zeros((B, K, 3)), np.zeros((B, K)), np.zeros((B, K), np.uint8),
+                           np.zeros((B, K), np.uint8), zero_cam, None)
+        gbatch.set_params(xg)
+        _, _, j3 = gbatch.eval(cam_st, want_joints=True)
+        kp_j, expose_j, pixie_j = observations(gt, j3.cpu().numpy().astype(np.float64), rng,
+                                               cfg.get('focal_length'))
+        if not cfg.get('regression_prior'):
+            expose_j = pixie_j = None
+        inputs.append((kp_j, expose_j, pixie_j))
     if args.vposer:
         gbatch.close()
-    kp, expose, pixie = observations(gt, j3.cpu().numpy().astype(np.float64), rng,
-                                     cfg.get('focal_length'))
-    if not cfg.get('regression_prior'):
-        expose = pixie = None
+    kp, expose, pixie = inputs[0]
     focal = float(cfg.get('focal_length') or np.sqrt(H_IMG ** 2 + W_IMG ** 2))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -616,29 +630,33 @@ def run_b200(args):
     # (a few SMs busy) overlap the first frames of step i + 1, the way a service that is fed batch
     # after batch runs.  Every step still fits its own 128 frames from scratch and the timed region
     # ends only when all of them are complete.  depth 1 = one batch at a time (also reported).
-    depth = steps_in_flight(args)                   # (config 4: one step, 0.6 GB of workspace per batch)
-    batches = [batch] + [engine.FrameBatch(model, B, use_vposer=args.vposer) for _ in range(depth - 1)]
+    batches = [batch] + [engine.FrameBatch(model, B, use_vposer=args.vposer) for _ in range(NB - 1)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
     # the single NCCL all-gather of a step's fitted parameters reads a copy of the rows
-    # and runs on NCCL's own stream: the next step of that slot does not wait for the other ranks
+    # and runs on NCCL's own stream: the next step of that batch slot does not wait for the other
+    # ranks.  The copies rotate through NG buffers (a buffer is waited for when it comes round again)
+    NG = 32
     gathered_k = [torch.empty((world * B, L.np), dtype=torch.float32, device=dev) if world > 1 else None
-                  for _ in range(depth)]
+                  for _ in range(NG)]
     staged_k = [torch.empty((B, L.np), dtype=torch.float32, device=dev) if world > 1 else None
-                for _ in range(depth)]
-    gather_work = [None] * depth
+                for _ in range(NG)]
+    gather_work = [None] * NG
+    gather_count = [0]
 
     def gather_params(k):
         if world > 1:
-            if gather_work[k] is not None:
-                gather_work[k].wait()                 # the slot's previous gather has read its copy
-            staged_k[k].copy_(batches[k].params_tensor())
-            gather_work[k] = dist.all_gather_into_tensor(gathered_k[k], staged_k[k], async_op=True)
+            g = gather_count[0] % NG
+            gather_count[0] += 1
+            if gather_work[g] is not None:
+                gather_work[g].wait()                 # the buffer's previous gather has completed
+            staged_k[g].copy_(batches[k].params_tensor())
+            gather_work[g] = dist.all_gather_into_tensor(gathered_k[g], staged_k[g], async_op=True)
 
     def gather_drain():
-        for k in range(depth):
-            if gather_work[k] is not None:
-                gather_work[k].wait()
-                gather_work[k] = None
+        for g in range(NG):
+            if gather_work[g] is not None:
+                gather_work[g].wait()
+                gather_work[g] = None
 
     def timed_steps(step_fn, d, steps):
         """`steps` steps, step i on stream i % d; device time of the whole region (ms)."""
@@ -649,8 +667,8 @@ def run_b200(args):
             st_.wait_event(start)
         n = 0
         for i in range(steps):
-            k = i % d
-            with torch.cuda.stream(streams[k]):
+            k = i % NB                              # the batch (and its FrameBatch object) of this step
+            with torch.cuda.stream(streams[k % d]):
                 flush.fill_(i & 0xff)
                 n += step_fn(k)
         for st_ in streams[:d]:
@@ -673,8 +691,8 @@ def run_b200(args):
         def make_plans(wide):
             mcfg = dict(cfg, two_loop=mode, wide_frames=wide)
             pls, xs = [], []
-            for bk in batches:
-                pl = FF.FitPlan(L, K, kp, H_IMG, W_IMG, mcfg, expose, pixie, None, np.float32,
+            for bk, (kp_j, expose_j, pixie_j) in zip(batches, inputs):
+                pl = FF.FitPlan(L, K, kp_j, H_IMG, W_IMG, mcfg, expose_j, pixie_j, None, np.float32,
                                 part_segm=part_segm, vposer=vp)
                 FF.upload(bk, pl)
                 pls.append(pl)
@@ -728,17 +746,21 @@ def run_b200(args):
         for st_ in streams[:d]:
             st_.wait_event(start)
         for i in range(steps):
-            k = i % d
+            k = i % NB
             if len(pending) == d:
-                res = FF.finish(pending.popleft())
-            with torch.cuda.stream(streams[k]):
+                r_ = FF.finish(pending.popleft())
+                res = r_ if (res is None or r_.batch_index == 0) else res
+            with torch.cuda.stream(streams[k % d]):
                 flush.fill_(i & 0xff)
-                pf = FF.submit(batches[k], kp, H_IMG, W_IMG, ecfg, expose, pixie, return_verts=True,
+                kp_j, expose_j, pixie_j = inputs[k]
+                pf = FF.submit(batches[k], kp_j, H_IMG, W_IMG, ecfg, expose_j, pixie_j, return_verts=True,
                                part_segm=part_segm, vposer=vp)
+                pf.batch_index = k
                 gather_params(k)
             pending.append(pf)
         while pending:
-            res = FF.finish(pending.popleft())
+            r_ = FF.finish(pending.popleft())
+            res = r_ if (res is None or r_.batch_index == 0) else res
         for st_ in streams[:d]:
             torch.cuda.current_stream().wait_stream(st_)
         gather_drain()
@@ -746,7 +768,7 @@ def run_b200(args):
         barrier()
         return start.elapsed_time(end), res
 
-    e2e_steps(depth, min(args.warmup, 2 * depth))
+    e2e_steps(depth, max(min(args.warmup, 2 * depth), 1))
     e2e_ms_rank, out = e2e_steps(depth, args.steps)
     e2e_serial_rank = e2e_steps(1, args.steps)[0] if depth > 1 else e2e_ms_rank
     clocks = sampler.stop() if rank == 0 else None
@@ -846,7 +868,7 @@ def run_b200(args):
         'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(B, world, args.interpenetration, args.vposer,
-                                  args.regression_prior, depth),
+                                  args.regression_prior, depth, NB),
         'value_one_step_at_a_time': world * B * args.steps / (total_ms_serial * 1e-3),
         'ms_per_step_one_step_at_a_time': total_ms_serial / args.steps,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(out.h2d_bytes),
@@ -935,6 +957,9 @@ def main():
                          "recursion) or 'exact' (the reference's operation order); the other "
                          "one is reported as value_<mode>")
     ap.add_argument('--single-mode', action='store_true', help='time only the default two-loop mode')
+    ap.add_argument('--batches', type=int, default=2,
+                    help='distinct synthetic batches per step slot: steps cycle through batches x depth '
+                         'different batches')
     ap.add_argument('--depth', type=int, default=6,
                     help='steps in flight (each on its own FrameBatch and CUDA stream); 1 = one batch '
                          'at a time')

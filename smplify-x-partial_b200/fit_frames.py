@@ -626,6 +626,7 @@ def finish(p):
     out = _build_result(p.batch, p.plan, p.host, p.return_verts)
     out.h2d_bytes = p.h2d_bytes
     out.gpu_launches = p.gpu_launches
+    out.batch_index = getattr(p, 'batch_index', None)
     return out
 
 
