@@ -603,6 +603,16 @@ SFX_FN void support_load_dyn_row(const DynRowPack<T>& P, Scratch<T>& S) {
     SFX_SYNC();
 }
 
+// small model constants every evaluation reads (hand PCA components, mean pose): kept next to the data
+template <typename T>
+SFX_FN void frame_constants(const ModelView<T>& M, Scratch<T>& S) {
+    if (SFX_TID == 0) S.hand_cached = M.NH <= 12;
+    if (M.NH <= 12)
+        SFX_FOR(i, 2 * M.NH * 45)
+            S.hand_c[i] = (float)(i < M.NH * 45 ? M.hand_l[i] : M.hand_r[i - M.NH * 45]);
+    SFX_FOR(i, SFX_NPOSE) S.pose_mean_c[i] = (float)M.pose_mean[i];
+}
+
 // once per frame (and per kernel launch): static slots; the dynamic ones follow the yaw row
 template <typename T>
 SFX_FN void support_begin_frame(const ModelView<T>& M, Scratch<T>& S) {
@@ -612,12 +622,7 @@ SFX_FN void support_begin_frame(const ModelView<T>& M, Scratch<T>& S) {
         S.dynrow_cached = -1;
     }
     SFX_SYNC();
-    // small model constants every evaluation reads: keep them next to the data
-    if (SFX_TID == 0) S.hand_cached = M.NH <= 12;
-    if (M.NH <= 12)
-        SFX_FOR(i, 2 * M.NH * 45)
-            S.hand_c[i] = (float)(i < M.NH * 45 ? M.hand_l[i] : M.hand_r[i - M.NH * 45]);
-    SFX_FOR(i, SFX_NPOSE) S.pose_mean_c[i] = (float)M.pose_mean[i];
+    frame_constants(M, S);
     support_slots(M, S, 0, SFX_NSTATIC);
     support_by_joint(S, 0, SFX_NSTATIC, S.jt_ptr, 0);
 }
@@ -824,7 +829,7 @@ SFX_FN void vposer_adjoint(const ModelView<T>& M, Scratch<T>& S, T* out, void* w
 // of the contour table.  Reads S.x.  Ends synchronised.
 template <typename T>
 SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>& S,
-                          bool use_vposer = false, void* wsp = nullptr) {
+                          bool use_vposer = false, void* wsp = nullptr, bool support_tables = true) {
     const int NS = M.NS;
     if (use_vposer) vposer_decode(M, S.x + L.off_pose, S, wsp);     // body pose = decode(z)
     SFX_FOR(i, SFX_NPOSE) {
@@ -903,7 +908,7 @@ SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>&
         int j = i / 3, p = M.parents[j];
         S.rel[i] = p < 0 ? S.Jr[i] : S.Jr[i] - S.Jr[3 * p + (i % 3)];
     }
-    if (S.dynrow != S.dynrow_cached) {          // uniform: dynrow was written before the barrier
+    if (support_tables && S.dynrow != S.dynrow_cached) {   // uniform: dynrow was written before the barrier
         SFX_SYNC();
         if (M.dyn_pack) {
             support_load_dyn_row(M.dyn_pack[M.use_contour ? S.dynrow : 0], S);

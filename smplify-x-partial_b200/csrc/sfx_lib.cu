@@ -253,8 +253,9 @@ mesh_coef_kernel(const __grid_constant__ ModelView<T> Mp, const __grid_constant_
     stage_block_ctx(C, Mp, Bv.lay);
     const int f = blockIdx.x;
     load_frame(Bv, f, S);
-    support_begin_frame(M, S);
-    pose_prologue(M, C.L, S, use_vposer != 0, &C.ws);
+    frame_constants(M, S);                       // (no support tables: only A and c leave this kernel)
+    __syncthreads();
+    pose_prologue(M, C.L, S, use_vposer != 0, &C.ws, false);
     if (threadIdx.x < 32) chain_forward(M, S);
     __syncthreads();
     for (int i = threadIdx.x; i < SFX_NJ * 12; i += blockDim.x) Aout[(size_t)f * SFX_NJ * 12 + i] = S.A[i];

@@ -10,14 +10,15 @@
 // vertex): columns [0,384) the three K1 accumulators (component c at 128 c, column = frame),
 // columns [384,480) the K2 accumulator of one chunk of 8 frames (column = 12 f + e).
 //
-//   warp 4 / lane 0   TMA producer.  K1: 16 k-blocks of {3 x [128 v][32 k] of PK through a 3-D
+//   warp 8 / lane 0   TMA producer.  K1: 16 k-blocks of {3 x [128 v][32 k] of PK through a 3-D
 //                     tensor map over PK viewed as [V][3][512], [128 f][32 k] of C}, 3-stage ring.
 //                     K2 (re-using the ring's memory once K1's MMAs have drained): the two W tiles
 //                     (hi / lo) once, then per chunk the hi / lo tiles of A^T for 8 frames.
-//   warp 5 / lane 0   MMA issuer.  K1: 4 x tcgen05.mma m128 n128 k8 per component and k-block;
+//   warp 9 / lane 0   MMA issuer.  K1: 4 x tcgen05.mma m128 n128 k8 per component and k-block;
 //                     K2 per chunk: 8 k-steps x {Whi.Ahi, Wlo.Ahi, Whi.Alo} m128 n96 k8.
-//   warps 0..3        epilogue, a thread per vertex: tcgen05.ld of T (96 columns) and of the chunk's
-//                     8 frames of the three K1 accumulators, 8 x (3x4 transform), staged in shared
+//   warps 0..7        epilogue, a thread per vertex and half chunk (warps w and w + 4 share a TMEM lane
+//                     quadrant and take 4 frames each; 16 warps measured no faster): tcgen05.ld of T (48 columns) and of the chunk's
+//                     frames of the three K1 accumulators, 4 x (3x4 transform), staged in shared
 //                     memory and written as 1536-byte contiguous runs per frame (coalesced 128-byte
 //                     warp stores; a TMA tensor store cannot address [B][V][3] float rows of
 //                     3 * 10475 * 4 = 125 700 bytes: the row pitch is not a multiple of 16).
@@ -51,7 +52,8 @@ constexpr int FU_A2_BOX = FU_N2 * FU_KB * 4;                        // 12 KB: on
 constexpr int FU_A2_BYTES = 4 * FU_A2_BOX;                          // hi | lo, two boxes each: 48 KB
 constexpr int FU_OUT_BYTES = FU_CH * 3 * FU_TV * 4;                 // 12 KB staging per chunk
 constexpr int FU_SMEM_BYTES = FU_RING_BYTES + 2 * FU_OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int FU_THREADS = 192;
+constexpr int FU_EPW = 2;                    // epilogue warps per TMEM lane quadrant (each takes FU_CH / FU_EPW frames of a chunk)
+constexpr int FU_THREADS = 32 * (4 * FU_EPW + 2);   // epilogue warps, then the TMA warp and the MMA warp
 constexpr int FU_WJ = 64;                   // padded joint count (K of K2)
 static_assert(FU_W_BYTES + 2 * FU_A2_BYTES <= FU_RING_BYTES, "K2 operands re-use the K1 ring");
 
@@ -159,7 +161,7 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
             mbar_init(a2_empty + s, 1);
         }
         mbar_init(d2_full, 1);
-        mbar_init(d2_empty, 128);
+        mbar_init(d2_empty, 128 * FU_EPW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -179,7 +181,7 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
     unsigned char* wbuf = smem;                          // Whi k0..31 | Whi k32..63 | Wlo .. | Wlo ..
     unsigned char* a2buf = smem + FU_W_BYTES;            // two slots of {Ahi, Ahi', Alo, Alo'}
 
-    if (warp == 4 && lane == 0) {
+    if (warp == 4 * FU_EPW && lane == 0) {
         // ===== TMA producer =====
         for (int kb = 0; kb < NUM_KB; ++kb) {
             const int s = kb % FU_STAGES;
@@ -207,7 +209,7 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
                 tma_load_2d(a + (2 + h) * FU_A2_BOX, &map_alo, h * FU_KB, row0, a2_full + s);
             }
         }
-    } else if (warp == 5 && lane == 0) {
+    } else if (warp == 4 * FU_EPW + 1 && lane == 0) {
         // ===== MMA issuer =====
         const uint32_t idesc1 = umma_idesc_tf32_n(FU_TF);
         for (int kb = 0; kb < NUM_KB; ++kb) {
@@ -252,20 +254,24 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
             tc_commit(a2_empty + s);
             tc_commit(d2_full);
         }
-    } else if (warp < 4) {
-        // ===== epilogue: thread = vertex (TMEM lane 32 warp + lane) =====
-        const int vloc = warp * 32 + lane, v = v0 + vloc;
+    } else if (warp < 4 * FU_EPW) {
+        // ===== epilogue: thread = vertex (TMEM lane 32 (warp % 4) + lane) x part of the chunk's frames =====
+        const int quad = warp & 3, half = warp >> 2;       // `half`: which part of the chunk (0 .. FU_EPW-1)
+        constexpr int HF = FU_CH / FU_EPW;                 // frames per thread and chunk
+        static_assert(FU_CH % FU_EPW == 0 && (12 * HF) % 8 == 0, "whole 8-column loads per thread");
+        const int vloc = quad * 32 + lane, v = v0 + vloc;
         float t0 = 0, t1 = 0, t2 = 0;
         if (v < V) { t0 = vt[3 * v]; t1 = vt[3 * v + 1]; t2 = vt[3 * v + 2]; }
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const int tile_floats = (V - v0 < FU_TV ? V - v0 : FU_TV) * 3;     // valid floats of a frame run
         mbar_wait(d1_full, 0);
         for (int q = 0; q < nchunk; ++q) {
             mbar_wait(d2_full, q & 1);
             tc_fence_after();
-            uint32_t T[FU_N2], P[3 * FU_CH];
+            uint32_t T[12 * HF], P[3 * FU_CH];
 #pragma unroll
-            for (int c8 = 0; c8 < FU_N2 / 8; ++c8) SFX_TMEM_LD(8, tmem_d2 + lane_addr + 8 * c8, T, 8 * c8);
+            for (int c8 = 0; c8 < 12 * HF / 8; ++c8)
+                SFX_TMEM_LD(8, tmem_d2 + lane_addr + 12 * HF * half + 8 * c8, T, 8 * c8);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 SFX_TMEM_LD(8, tmem_base + lane_addr + c * FU_TF + q * FU_CH, P, 8 * c);
@@ -274,20 +280,30 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
             mbar_arrive(d2_empty);                         // D2 may be overwritten by the next chunk
             float* ob = reinterpret_cast<float*>(outbuf + (q & 1) * FU_OUT_BYTES);
 #pragma unroll
-            for (int f = 0; f < FU_CH; ++f) {
-                const float x = t0 + __uint_as_float(P[f]);
-                const float y = t1 + __uint_as_float(P[8 + f]);
-                const float z = t2 + __uint_as_float(P[16 + f]);
+            for (int fh = 0; fh < HF; ++fh) {
+                const int f = half * HF + fh;
+                // (selects over compile-time indices: a register array cannot be indexed by `half`)
+                float px = 0, py = 0, pz = 0;
+#pragma unroll
+                for (int h2 = 0; h2 < FU_EPW; ++h2)
+                    if (half == h2) {
+                        px = __uint_as_float(P[h2 * HF + fh]);
+                        py = __uint_as_float(P[8 + h2 * HF + fh]);
+                        pz = __uint_as_float(P[16 + h2 * HF + fh]);
+                    }
+                const float x = t0 + px, y = t1 + py, z = t2 + pz;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const float* Tr = reinterpret_cast<const float*>(T) + 12 * f + 4 * r;
+                    const float* Tr = reinterpret_cast<const float*>(T) + 12 * fh + 4 * r;
                     ob[f * 3 * FU_TV + 3 * vloc + r] = Tr[0] * x + Tr[1] * y + Tr[2] * z + Tr[3];
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // the 128 threads of this part wrote its frames: named barrier 1 + part
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
             // coalesced copy-out: per frame one contiguous run of up to 384 floats
 #pragma unroll
-            for (int f = 0; f < FU_CH; ++f) {
+            for (int fh = 0; fh < HF; ++fh) {
+                const int f = half * HF + fh;
                 const int fr = m0 + q * FU_CH + f;
                 if (fr < B) {
                     float* dst = verts + ((size_t)fr * V + v0) * 3;

@@ -324,3 +324,35 @@ def test_dataset_read_meta_equals_read_item_without_pixels(tmp_path):
     for m, i in zip(metas[:2], items[:2]):
         assert m['fn'] == i['fn'] and np.array_equal(m['keypoints'], i['keypoints'])
         assert (m['H'], m['W']) == i['img'].shape[:2]
+
+
+def test_lazy_result_dicts():
+    """FitResult.results builds the reference's result dict (fit_single_frame.py:644-660) of a
+    frame when it is asked for: list-like (len, negative index, slice, iteration), cached, with
+    the parameter blocks cut out of the fitted rows."""
+    inp = Cm.golden('demo_inputs.npz')
+    ref = Cm.golden('ref_fit_02.npz')
+    cfg = json.loads(str(ref['cfg_json']))
+    fr = '02_cropped'
+    expose = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr + '/expose/')}
+    pixie = {k.split('/')[-1]: inp[k] for k in inp if k.startswith(fr + '/pixie/')}
+    L = Cm.layout()
+    kp = np.stack([inp[fr + '/keypoints']] * 3)
+    plan = FF.FitPlan(L, 135, kp, [600, 610, 620], 800, cfg, [expose] * 3, [pixie] * 3)
+    params = np.arange(3 * L.np, dtype=np.float32).reshape(3, L.np)
+    blocks = {'betas': (L.off_betas, L.n_betas), 'global_orient': (L.off_go, 3),
+              'left_hand_pose': (L.off_lh, L.n_hand), 'right_hand_pose': (L.off_rh, L.n_hand),
+              'jaw_pose': (L.off_jaw, 3), 'leye_pose': (L.off_leye, 3), 'reye_pose': (L.off_reye, 3),
+              'expression': (L.off_expr, L.n_expr), 'pose_embedding': (L.off_pose, L.n_pose)}
+    res = FF._LazyResults(plan, blocks, params, None)
+    assert len(res) == 3 and not res._cache
+    r = res[1]
+    assert res[1] is r and res[-2] is r and list(res._cache) == [1]
+    assert r['H'] == 610 and r['W'] == 800 and r['betas'].shape == (1, L.n_betas)
+    assert np.array_equal(r['body_pose'][0], params[1, L.off_pose:L.off_pose + L.n_pose])
+    assert np.array_equal(r['camera_translation'][0], params[1, L.off_camt:L.off_camt + 3])
+    assert [x['H'] for x in res] == [600, 610, 620] and [x['H'] for x in res[1:]] == [610, 620]
+    with pytest.raises(IndexError):
+        res[3]
+    decoded = np.ones((3, 63), dtype=np.float32)
+    assert np.array_equal(FF._LazyResults(plan, blocks, params, decoded)[2]['body_pose'], decoded[2:3])
