@@ -460,11 +460,12 @@ def run_reference(args):
 
 
 def steps_in_flight(args):
-    return 1 if args.interpenetration else max(1, int(getattr(args, 'depth', 6)))
+    # (config 4: 0.6 GB of collision workspace per 128-frame batch in flight)
+    return max(1, int(getattr(args, 'depth', 6)))
 
 
 def distinct_batches(args):
-    return 1 if args.interpenetration else max(1, int(getattr(args, 'batches', 2))) * steps_in_flight(args)
+    return (1 if args.interpenetration else max(1, int(getattr(args, 'batches', 2)))) * steps_in_flight(args)
 
 
 def workload_config(B, n_gpus, interpenetration=False, vposer=False, regression_prior=False, depth=6, nb=12):
@@ -581,7 +582,7 @@ def run_b200(args):
     # ---- synthetic inputs: GT parameters -> model joints (engine forward) -> noisy keypoints.
     # NB distinct batches (seeds seed + 1000 rank + 7919 j), cycled step after step: a stream of
     # different batches, as a service sees it; batch 0 is the one the CPU arm and the parity block use
-    depth = steps_in_flight(args)                   # (config 4: one step, 0.6 GB of workspace per batch)
+    depth = steps_in_flight(args)
     NB = distinct_batches(args)
     K = model.K
     gbatch = engine.FrameBatch(model, B) if args.vposer else batch     # axis-angle pose block

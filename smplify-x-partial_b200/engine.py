@@ -84,11 +84,12 @@ class Model(object):
         """Installs the face segmentation of the interpenetration term: ``segm`` / ``parents``
         of ``part_segm_fn`` (reference fit_single_frame.py:317-328) and ``ign_part_pairs``
         (strings "a,b" as in the yaml files, or pairs of ints)."""
-        key = (id(faces_segm), id(faces_parents), tuple(map(str, ign_part_pairs or ())))
-        if getattr(self, '_coll_key', None) == key:
-            return
         segm = np.ascontiguousarray(np.asarray(faces_segm), dtype=np.int32).reshape(-1)
         par = np.ascontiguousarray(np.asarray(faces_parents), dtype=np.int32).reshape(-1)
+        # same tables as the ones installed (by content: every FitPlan builds its own arrays): nothing to do
+        key = (hash(segm.tobytes()), hash(par.tobytes()), tuple(map(str, ign_part_pairs or ())))
+        if getattr(self, '_coll_key', None) == key:
+            return
         if segm.shape[0] != self.faces.shape[0] or par.shape[0] != segm.shape[0]:
             raise ValueError('part segmentation has {} faces, the model {}'.format(
                 segm.shape[0], self.faces.shape[0]))

@@ -102,8 +102,6 @@ def main(**args):
     # on its own FrameBatch / CUDA stream while batch i is being fitted, so the straggler frames
     # of one batch overlap the next batch's frames and the host work hides behind the device
     in_flight = max(1, int(args.get('batches_in_flight') or 2))
-    if args.get('interpenetration'):
-        in_flight = 1                               # 4.9 MB of workspace per frame and batch
     use_vposer = bool(args.get('use_vposer'))
     slots = [None] * in_flight                      # FrameBatch per slot (re-made when B changes)
     streams = [torch.cuda.Stream(device=model.device) for _ in range(in_flight)]
