@@ -683,7 +683,7 @@ def run_b200(args):
     other = {'gram': 'exact', 'exact': 'gram'}[TWO_LOOP]
     modes = [TWO_LOOP] if (args.interpenetration or args.single_mode) else [TWO_LOOP, other]
     sampler = ClockSampler(local)
-    timed, timed_serial, plans = {}, {}, {}
+    timed, timed_serial, plans, by_depth = {}, {}, {}, {}
     launches = 0
     for mi, mode in enumerate(modes):
         # steps in flight keep every SM busy, so a frame gets one block there (wide_frames off: a
@@ -717,6 +717,10 @@ def run_b200(args):
         timed[mode], n = timed_steps(step, depth, args.steps)
         if mi == 0:
             launches += n
+            # the same launches with fewer steps in flight (the curve behind `value`)
+            for d_ in (2, 4):
+                if d_ < depth:
+                    by_depth[d_] = reduce_max(timed_steps(step, d_, args.steps)[0])
         if depth > 1:
             mplans, x0s = make_plans('auto')
             step = make_step(mplans, x0s)
@@ -870,6 +874,10 @@ def run_b200(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(B, world, args.interpenetration, args.vposer,
                                   args.regression_prior, depth, NB),
+        'value_by_steps_in_flight': dict(
+            [('1 (clusters on)', world * B * args.steps / (total_ms_serial * 1e-3))] +
+            [(str(d_), world * B * args.steps / (ms_ * 1e-3)) for d_, ms_ in sorted(by_depth.items())] +
+            [(str(depth), world * B * args.steps / (total_ms * 1e-3))]),
         'value_one_step_at_a_time': world * B * args.steps / (total_ms_serial * 1e-3),
         'ms_per_step_one_step_at_a_time': total_ms_serial / args.steps,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(out.h2d_bytes),
