@@ -32,35 +32,38 @@ typedef enum {
 typedef struct sfx_model sfx_model;
 typedef struct sfx_batch sfx_batch;
 
-/* Raw SMPL-X arrays as stored in SMPLX_{NEUTRAL,MALE,FEMALE}.npz (host pointers, float32 /
- * int32).  Stands in for the constructor arguments of smplx.create (reference
- * smplifyx/main.py:109-127) plus JointMapper(dataset.get_model2data()) (main.py:107). */
+/* Raw SMPL-X arrays as stored in SMPLX_{NEUTRAL,MALE,FEMALE}.npz (host pointers; the
+ * floating-point arrays are float32, or float64 when arrays_float64 is set -- the shipped files
+ * hold float64 and the reference's float_dtype: float64 path keeps them so; integers are int32).
+ * Stands in for the constructor arguments of smplx.create (reference smplifyx/main.py:109-127)
+ * plus JointMapper(dataset.get_model2data()) (main.py:107). */
 typedef struct {
     int32_t num_verts, num_faces;
-    const float* v_template;         /* [V,3] */
-    const float* shapedirs;          /* [V,3,shape_stride] */
+    const void* v_template;          /* [V,3] */
+    const void* shapedirs;           /* [V,3,shape_stride] */
     int32_t shape_stride;            /* 400 in the shipped files */
     int32_t num_betas;               /* columns [0, num_betas) */
     int32_t expr_offset, num_expr;   /* columns [expr_offset, expr_offset + num_expr) */
-    const float* posedirs;           /* [V,3,486] */
-    const float* J_regressor;        /* [55,V] */
-    const float* lbs_weights;        /* [V,55] */
+    const void* posedirs;            /* [V,3,486] */
+    const void* J_regressor;         /* [55,V] */
+    const void* lbs_weights;         /* [V,55] */
     const int32_t* parents;          /* [55], root = -1 */
     const int32_t* faces;            /* [F,3] */
     int32_t n_hand;                  /* num_pca_comps, or 45 when use_pca is False */
-    const float* hand_components_l;  /* [n_hand,45] (identity rows when use_pca is False) */
-    const float* hand_components_r;  /* [n_hand,45] */
-    const float* hand_mean_l;        /* [45] (zeros when flat_hand_mean) */
-    const float* hand_mean_r;        /* [45] */
+    const void* hand_components_l;   /* [n_hand,45] (identity rows when use_pca is False) */
+    const void* hand_components_r;   /* [n_hand,45] */
+    const void* hand_mean_l;         /* [45] (zeros when flat_hand_mean) */
+    const void* hand_mean_r;         /* [45] */
     const int32_t* extra_vertex_ids; /* [21] smplx vertex_ids['smplx'] in selector order */
     const int32_t* lmk_faces_idx;    /* [51] */
-    const float* lmk_bary_coords;    /* [51,3] */
+    const void* lmk_bary_coords;     /* [51,3] */
     int32_t use_face_contour;
     const int32_t* dyn_lmk_faces_idx;   /* [79,17] or NULL */
-    const float* dyn_lmk_bary_coords;   /* [79,17,3] or NULL */
+    const void* dyn_lmk_bary_coords;    /* [79,17,3] or NULL */
     const int32_t* joint_map;        /* [num_keypoints] model joint index per keypoint */
     int32_t num_keypoints;
     int32_t use_double;              /* float_dtype float64 (reference main.py:99-105) */
+    int32_t arrays_float64;          /* the floating-point arrays above are double, not float */
 } sfx_model_desc;
 
 /* smplx.create(...).to(device) -- copies and re-lays the constants on the current device. */

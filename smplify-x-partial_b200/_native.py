@@ -96,6 +96,7 @@ class SfxModelDesc(C.Structure):
         ('lmk_bary_coords', C.c_void_p), ('use_face_contour', C.c_int32),
         ('dyn_lmk_faces_idx', C.c_void_p), ('dyn_lmk_bary_coords', C.c_void_p),
         ('joint_map', C.c_void_p), ('num_keypoints', C.c_int32), ('use_double', C.c_int32),
+        ('arrays_float64', C.c_int32),
     ]
 
 
@@ -110,13 +111,16 @@ def build_model_desc(model_data, joint_map, num_betas=10, num_expression_coeffs=
         keep.append(a)
         return a.ctypes.data_as(C.c_void_p)
 
+    # float64 batches take the model arrays as the npz holds them (the licensed files store float64);
+    # float32 batches the float32 values the reference's float_dtype: float32 path works with
+    fdt = np.float64 if use_double else np.float32
     d = SfxModelDesc()
     vt = np.asarray(model_data['v_template'])
     d.num_verts = vt.shape[0]
     d.num_faces = np.asarray(model_data['f']).shape[0]
-    d.v_template = arr(vt, np.float32)
+    d.v_template = arr(vt, fdt)
     sd = np.asarray(model_data['shapedirs'])
-    d.shapedirs = arr(sd, np.float32)
+    d.shapedirs = arr(sd, fdt)
     d.shape_stride = sd.shape[2]
     d.num_betas = num_betas
     d.expr_offset = 300
@@ -124,9 +128,9 @@ def build_model_desc(model_data, joint_map, num_betas=10, num_expression_coeffs=
     if sd.shape[2] < 300 + num_expression_coeffs:
         raise ValueError('shapedirs has {} columns; expression block needs [300, {})'.format(
             sd.shape[2], 300 + num_expression_coeffs))
-    d.posedirs = arr(model_data['posedirs'], np.float32)
-    d.J_regressor = arr(model_data['J_regressor'], np.float32)
-    d.lbs_weights = arr(model_data['weights'], np.float32)
+    d.posedirs = arr(model_data['posedirs'], fdt)
+    d.J_regressor = arr(model_data['J_regressor'], fdt)
+    d.lbs_weights = arr(model_data['weights'], fdt)
     parents = np.asarray(model_data['kintree_table'])[0].astype(np.int64).copy()
     parents[0] = -1
     d.parents = arr(parents, np.int32)
@@ -139,22 +143,23 @@ def build_model_desc(model_data, joint_map, num_betas=10, num_expression_coeffs=
         n_hand = 45
         cl = cr = np.eye(45)
     d.n_hand = n_hand
-    d.hand_components_l = arr(cl, np.float32)
-    d.hand_components_r = arr(cr, np.float32)
+    d.hand_components_l = arr(cl, fdt)
+    d.hand_components_r = arr(cr, fdt)
     zeros = np.zeros(45)
-    d.hand_mean_l = arr(zeros if flat_hand_mean else model_data['hands_meanl'], np.float32)
-    d.hand_mean_r = arr(zeros if flat_hand_mean else model_data['hands_meanr'], np.float32)
+    d.hand_mean_l = arr(zeros if flat_hand_mean else model_data['hands_meanl'], fdt)
+    d.hand_mean_r = arr(zeros if flat_hand_mean else model_data['hands_meanr'], fdt)
     d.extra_vertex_ids = arr(EXTRA_VERTEX_IDS, np.int32)
     d.lmk_faces_idx = arr(model_data['lmk_faces_idx'], np.int32)
-    d.lmk_bary_coords = arr(model_data['lmk_bary_coords'], np.float32)
+    d.lmk_bary_coords = arr(model_data['lmk_bary_coords'], fdt)
     d.use_face_contour = 1 if use_face_contour else 0
     if use_face_contour:
         d.dyn_lmk_faces_idx = arr(model_data['dynamic_lmk_faces_idx'], np.int32)
-        d.dyn_lmk_bary_coords = arr(model_data['dynamic_lmk_bary_coords'], np.float32)
+        d.dyn_lmk_bary_coords = arr(model_data['dynamic_lmk_bary_coords'], fdt)
     jm = np.asarray(joint_map, dtype=np.int32)
     d.joint_map = arr(jm, np.int32)
     d.num_keypoints = jm.shape[0]
     d.use_double = 1 if use_double else 0
+    d.arrays_float64 = 1 if use_double else 0
     return d, keep
 
 

@@ -100,6 +100,9 @@ struct DynRowPack {
 template <typename T>
 struct ModelView {
     int V, NS, NB, NE, NH, K, NJOUT, use_contour, n_neck, nlev;
+    int wide_model;      // float64 arrays in a float64 model: the per-frame float32 copies (skinning weights
+                         // by slot / by joint, hand components, mean pose) would truncate them, so the
+                         // evaluation reads the model's own tables (dense-weight path of every frame)
     const T* PK;         // [3V][SFX_KPAD]  row 3v+c: 486 pose-corrective dirs | NS shape dirs | 0
     const T* vt;         // [3V]            template
     const T* J0;         // [165]           J_regressor . v_template
@@ -606,8 +609,8 @@ SFX_FN void support_load_dyn_row(const DynRowPack<T>& P, Scratch<T>& S) {
 // small model constants every evaluation reads (hand PCA components, mean pose): kept next to the data
 template <typename T>
 SFX_FN void frame_constants(const ModelView<T>& M, Scratch<T>& S) {
-    if (SFX_TID == 0) S.hand_cached = M.NH <= 12;
-    if (M.NH <= 12)
+    if (SFX_TID == 0) S.hand_cached = M.NH <= 12 && !M.wide_model;
+    if (M.NH <= 12 && !M.wide_model)
         SFX_FOR(i, 2 * M.NH * 45)
             S.hand_c[i] = (float)(i < M.NH * 45 ? M.hand_l[i] : M.hand_r[i - M.NH * 45]);
     SFX_FOR(i, SFX_NPOSE) S.pose_mean_c[i] = (float)M.pose_mean[i];
@@ -618,7 +621,7 @@ template <typename T>
 SFX_FN void support_begin_frame(const ModelView<T>& M, Scratch<T>& S) {
     SFX_SYNC();
     if (SFX_TID == 0) {
-        S.w_overflow = 0;
+        S.w_overflow = M.wide_model ? 1 : 0;
         S.dynrow_cached = -1;
     }
     SFX_SYNC();
@@ -853,7 +856,7 @@ SFX_FN void pose_prologue(const ModelView<T>& M, const SfxLayout& L, Scratch<T>&
             S.hand[h * 45 + e] = acc;
             v = acc;
         }
-        S.fp[i] = v + (T)S.pose_mean_c[i];
+        S.fp[i] = v + (M.wide_model ? M.pose_mean[i] : (T)S.pose_mean_c[i]);
     }
     SFX_FOR_FROM(i, 32, 192) {
         T v = 0;

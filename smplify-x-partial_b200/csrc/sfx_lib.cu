@@ -772,7 +772,10 @@ int sfx_model_create(const sfx_model_desc* desc, sfx_model** out) {
             std::vector<float> whi((size_t)Vpad * FU_WJ, 0.f), wlo((size_t)Vpad * FU_WJ, 0.f);
             for (int v = 0; v < m->V; ++v)
                 for (int j = 0; j < SFX_NJ; ++j)
-                    tf32_split(desc->lbs_weights[(size_t)v * SFX_NJ + j], &whi[(size_t)v * FU_WJ + j],
+                    tf32_split(desc->arrays_float64
+                                   ? (float)static_cast<const double*>(desc->lbs_weights)[(size_t)v * SFX_NJ + j]
+                                   : static_cast<const float*>(desc->lbs_weights)[(size_t)v * SFX_NJ + j],
+                               &whi[(size_t)v * FU_WJ + j],
                                &wlo[(size_t)v * FU_WJ + j]);
             cudaError_t ce = m->whi.upload(whi);
             if (ce == cudaSuccess) ce = m->wlo.upload(wlo);

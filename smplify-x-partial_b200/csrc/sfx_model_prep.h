@@ -14,6 +14,7 @@ namespace sfx {
 template <typename T>
 struct HostModel {
     int V = 0, F = 0, NS = 0, NB = 0, NE = 0, NH = 0, K = 0, NJOUT = 0, use_contour = 0;
+    int wide_model = 0;      // the model arrays were given in float64 and T is double: no float32 caches
     std::vector<T> PK, vt, J0, JS, Wd, hand_l, hand_r, pose_mean, lmk_bary, dyn_bary;
     std::vector<int> sv_vid, dyn_vid, joint_map, inv_ptr, inv_idx, faces, sk_ptr;
     std::vector<unsigned char> sk_j;
@@ -26,6 +27,7 @@ struct HostModel {
     void fill_scalars(ModelView<T>& m) const {
         m.V = V; m.NS = NS; m.NB = NB; m.NE = NE; m.NH = NH; m.K = K; m.NJOUT = NJOUT;
         m.use_contour = use_contour; m.n_neck = n_neck; m.nlev = nlev;
+        m.wide_model = wide_model;
         m.vp_ready = 0; m.vp_w1 = m.vp_b1 = m.vp_w2 = m.vp_b2 = m.vp_w3 = m.vp_b3 = nullptr;
         m.gmm_M = 0; m.gmm_D = 0; m.gmm_means = nullptr; m.gmm_prec = nullptr; m.gmm_logw = nullptr;
         m.coll_ready = 0; m.F = F; m.n_parts = 0; m.faces = nullptr; m.part_ptr = nullptr;
@@ -65,6 +67,12 @@ std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
     if (d.num_keypoints < 1 || d.num_keypoints > SFX_KMAX) return "num_keypoints out of range";
     if (d.use_face_contour && (!d.dyn_lmk_faces_idx || !d.dyn_lmk_bary_coords))
         return "use_face_contour needs the dynamic landmark tables";
+    // floating-point arrays of the description: float32 or float64 (arrays_float64)
+    const bool f64 = d.arrays_float64 != 0;
+    auto rd = [f64](const void* p, size_t i) -> double {
+        return f64 ? static_cast<const double*>(p)[i] : (double)static_cast<const float*>(p)[i];
+    };
+    h.wide_model = (f64 && sizeof(T) == 8) ? 1 : 0;
     h.V = V; h.F = d.num_faces; h.NB = d.num_betas; h.NE = d.num_expr; h.NS = h.NB + h.NE;
     h.NH = d.n_hand; h.K = d.num_keypoints; h.use_contour = d.use_face_contour ? 1 : 0;
     h.NJOUT = SFX_NJ + SFX_NEXTRA + SFX_NLMK + (h.use_contour ? SFX_NDYN : 0);
@@ -103,12 +111,11 @@ std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
     h.vt.resize((size_t)3 * V);
     for (long r = 0; r < 3L * V; ++r) {
         T* row = h.PK.data() + r * SFX_KPAD;
-        const float* pd = d.posedirs + r * SFX_NPF;
-        for (int k = 0; k < SFX_NPF; ++k) row[k] = (T)pd[k];
-        const float* sd = d.shapedirs + r * d.shape_stride;
-        for (int s = 0; s < h.NB; ++s) row[SFX_NPF + s] = (T)sd[s];
-        for (int s = 0; s < h.NE; ++s) row[SFX_NPF + h.NB + s] = (T)sd[d.expr_offset + s];
-        h.vt[r] = (T)d.v_template[r];
+        const size_t pd = (size_t)r * SFX_NPF, sd = (size_t)r * d.shape_stride;
+        for (int k = 0; k < SFX_NPF; ++k) row[k] = (T)rd(d.posedirs, pd + k);
+        for (int s = 0; s < h.NB; ++s) row[SFX_NPF + s] = (T)rd(d.shapedirs, sd + s);
+        for (int s = 0; s < h.NE; ++s) row[SFX_NPF + h.NB + s] = (T)rd(d.shapedirs, sd + d.expr_offset + s);
+        h.vt[r] = (T)rd(d.v_template, r);
     }
     // --- rest joints: J0 = Jreg . v_template, JS = Jreg . shapedirs (accumulated in double) ---
     h.J0.assign(SFX_NJ * 3, (T)0);
@@ -117,17 +124,16 @@ std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
         std::vector<double> acc(SFX_NJ * 3 * 33);
         std::fill(acc.begin(), acc.end(), 0.0);
         for (int j = 0; j < SFX_NJ; ++j) {
-            const float* jr = d.J_regressor + (long)j * V;
             for (int v = 0; v < V; ++v) {
-                double w = jr[v];
+                double w = rd(d.J_regressor, (size_t)j * V + v);
                 if (w == 0.0) continue;
                 for (int c = 0; c < 3; ++c) {
                     long r = 3L * v + c;
                     double* a = acc.data() + (j * 3 + c) * 33;
-                    a[32] += w * d.v_template[r];
-                    const float* sd = d.shapedirs + r * d.shape_stride;
-                    for (int s = 0; s < h.NB; ++s) a[s] += w * sd[s];
-                    for (int s = 0; s < h.NE; ++s) a[h.NB + s] += w * sd[d.expr_offset + s];
+                    a[32] += w * rd(d.v_template, r);
+                    const size_t sd = (size_t)r * d.shape_stride;
+                    for (int s = 0; s < h.NB; ++s) a[s] += w * rd(d.shapedirs, sd + s);
+                    for (int s = 0; s < h.NE; ++s) a[h.NB + s] += w * rd(d.shapedirs, sd + d.expr_offset + s);
                 }
             }
         }
@@ -139,15 +145,15 @@ std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
     // --- dense skinning weights, padded rows ---
     h.Wd.assign((size_t)V * SFX_WROW, (T)0);
     for (long v = 0; v < V; ++v)
-        for (int j = 0; j < SFX_NJ; ++j) h.Wd[v * SFX_WROW + j] = (T)d.lbs_weights[v * SFX_NJ + j];
+        for (int j = 0; j < SFX_NJ; ++j) h.Wd[v * SFX_WROW + j] = (T)rd(d.lbs_weights, v * SFX_NJ + j);
     h.sk_ptr.assign(V + 1, 0);
     h.sk_j.clear();
     h.sk_w.clear();
     for (long v = 0; v < V; ++v) {
         for (int j = 0; j < SFX_NJ; ++j)
-            if (d.lbs_weights[v * SFX_NJ + j] != 0.f) {
+            if (rd(d.lbs_weights, v * SFX_NJ + j) != 0.0) {
                 h.sk_j.push_back((unsigned char)j);
-                h.sk_w.push_back((T)d.lbs_weights[v * SFX_NJ + j]);
+                h.sk_w.push_back((T)rd(d.lbs_weights, v * SFX_NJ + j));
             }
         h.sk_ptr[v + 1] = (int)h.sk_j.size();
     }
@@ -155,13 +161,13 @@ std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
     h.hand_l.resize((size_t)h.NH * 45);
     h.hand_r.resize((size_t)h.NH * 45);
     for (int i = 0; i < h.NH * 45; ++i) {
-        h.hand_l[i] = (T)d.hand_components_l[i];
-        h.hand_r[i] = (T)d.hand_components_r[i];
+        h.hand_l[i] = (T)rd(d.hand_components_l, i);
+        h.hand_r[i] = (T)rd(d.hand_components_r, i);
     }
     h.pose_mean.assign(SFX_NPOSE, (T)0);
     for (int i = 0; i < 45; ++i) {
-        h.pose_mean[75 + i] = d.hand_mean_l ? (T)d.hand_mean_l[i] : (T)0;
-        h.pose_mean[120 + i] = d.hand_mean_r ? (T)d.hand_mean_r[i] : (T)0;
+        h.pose_mean[75 + i] = d.hand_mean_l ? (T)rd(d.hand_mean_l, i) : (T)0;
+        h.pose_mean[120 + i] = d.hand_mean_r ? (T)rd(d.hand_mean_r, i) : (T)0;
     }
     // --- support vertices ---
     h.faces.resize((size_t)3 * h.F);
@@ -180,7 +186,7 @@ std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
         if (f < 0 || f >= h.F) return "lmk_faces_idx out of range";
         for (int k = 0; k < 3; ++k) {
             h.sv_vid[SFX_NEXTRA + 3 * l + k] = h.faces[3L * f + k];
-            h.lmk_bary[3 * l + k] = (T)d.lmk_bary_coords[3 * l + k];
+            h.lmk_bary[3 * l + k] = (T)rd(d.lmk_bary_coords, 3 * l + k);
         }
     }
     h.dyn_vid.assign(SFX_NDYNROWS * 51, 0);
@@ -193,7 +199,7 @@ std::string prepare_model(const sfx_model_desc& d, HostModel<T>& h) {
                 for (int k = 0; k < 3; ++k) {
                     h.dyn_vid[y * 51 + 3 * i + k] = h.faces[3L * f + k];
                     h.dyn_bary[y * 51 + 3 * i + k] =
-                        (T)d.dyn_lmk_bary_coords[(y * SFX_NDYN + i) * 3 + k];
+                        (T)rd(d.dyn_lmk_bary_coords, (size_t)(y * SFX_NDYN + i) * 3 + k);
                 }
             }
     }

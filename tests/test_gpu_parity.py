@@ -403,3 +403,30 @@ def test_gram_two_loop_f32_staging_variants_bit_identical(model32, monkeypatch):
     assert np.array_equal(outs[0][1], outs[1][1])
     assert np.array_equal(outs[0][2], outs[1][2])
     assert outs[0][2].min() > 60
+
+
+def test_float64_model_keeps_the_arrays_of_the_npz():
+    """float_dtype: float64 (reference main.py:99-105): the model arrays reach the device as the
+    npz holds them (the licensed files store float64), not through float32.  A template shifted by
+    1e-9 m -- far below float32 resolution at body scale -- moves every vertex and every joint of
+    the float64 model by 1e-9 m, and the evaluation (whose per-frame float32 copies of the
+    skinning weights are bypassed for such a model) follows."""
+    ev = Cm.golden('ref_eval_f64.npz')
+    I = Cm.eval_case_inputs(ev, 'l2')
+    md = dict(Cm.model_data())
+    base = _engine().Model(md, Cm.joint_map(), dtype=torch.float64, **Cm.MODEL_KW)
+    md['v_template'] = np.asarray(md['v_template'], dtype=np.float64) + np.array([1e-9, 0.0, 0.0])
+    moved = _engine().Model(md, Cm.joint_map(), dtype=torch.float64, **Cm.MODEL_KW)
+    out = []
+    for model in (base, moved):
+        batch = _engine().FrameBatch(model, 2)
+        _load(batch, I, 2)
+        v, j = batch.forward_mesh()
+        loss, grad, joints = batch.eval(I['stage'], want_joints=True)
+        out.append((v.cpu().numpy(), joints.cpu().numpy(), loss.cpu().numpy()))
+    dv = np.linalg.norm(out[1][0] - out[0][0], axis=-1)
+    dj = np.linalg.norm(out[1][1] - out[0][1], axis=-1)
+    assert np.all(np.abs(dv - 1e-9) < 1e-12), (dv.min(), dv.max())       # a rigid shift survives skinning
+    assert 0.2e-9 < dj[:, 55:].mean() < 5e-9                              # vertex-derived joints move with it
+    # the unshifted float64 model still reproduces the reference's float64 loss
+    assert abs(out[0][2][0] - float(ev['l2/loss'])) <= 1e-9 * abs(float(ev['l2/loss']))
