@@ -87,10 +87,17 @@ int sfx_model_set_gmm(sfx_model* m, int32_t num_gaussians, int32_t dim, const vo
  * `parents` [F] = kinematic parent of that part; parts 0..63) and its ign_part_pairs option
  * ([n,2] part ids) -- the inputs of mesh_intersection.FilterFaces.  Stands in for the
  * construction of BVH / FilterFaces / DistanceFieldPenetrationLoss at fit_single_frame.py:300-328.
- * The device path needs the segmentation (it is its broad phase); point2plane = False and
- * penalize_outside = True, the values of every shipped configuration, are what is built. */
+ * This entry takes the segmentation (sfx_model_set_collision_unfiltered below runs without);
+ * point2plane = False and penalize_outside = True, the values of every shipped configuration,
+ * are what is built. */
 int sfx_model_set_collision(sfx_model* m, const int32_t* faces_segm, const int32_t* faces_parents,
                             const int32_t* ign_part_pairs, int32_t n_ign_pairs);
+/* The same term WITHOUT FilterFaces -- the reference's path when part_segm_fn is empty
+ * (fit_single_frame.py:317-328: filter_faces = None; fitting.py:449-450 then keeps every pair the
+ * search tree reports): every intersecting pair of triangles that share no vertex is penalised.
+ * faces_group [F] (0..63) only groups the faces for the broad phase (any spatially coherent
+ * grouping, e.g. the joint with the largest skinning weight); it does not change the result. */
+int sfx_model_set_collision_unfiltered(sfx_model* m, const int32_t* faces_group);
 
 /* Per-batch workspace: parameters, targets, L-BFGS history (154 KB per frame in float32) and its
  * inner products (80 KB per frame; SfxStage.generic_two_loop = 2) for B independent frames.

@@ -282,6 +282,7 @@ def load_library(path=None):
     lib.sfx_model_set_vposer.argtypes = [vp] * 7
     lib.sfx_model_set_gmm.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.sfx_model_set_collision.argtypes = [vp, vp, vp, vp, i32]
+    lib.sfx_model_set_collision_unfiltered.argtypes = [vp, vp]
     lib.sfx_batch_enable_collisions.argtypes = [vp]
     lib.sfx_batch_coll_stat_dev.argtypes = [vp]
     lib.sfx_batch_coll_stat_dev.restype = vp

@@ -832,13 +832,26 @@ int sfx_model_set_gmm(sfx_model* m, int32_t num_gaussians, int32_t dim, const vo
     return SFX_OK;
 }
 
+static int set_collision_impl(sfx_model* m, const int32_t* faces_segm, const int32_t* faces_parents,
+                              const int32_t* ign_part_pairs, int32_t n_ign_pairs, bool unfiltered);
+
 int sfx_model_set_collision(sfx_model* m, const int32_t* faces_segm, const int32_t* faces_parents,
                             const int32_t* ign_part_pairs, int32_t n_ign_pairs) {
     if (!m || !faces_segm || !faces_parents || (n_ign_pairs > 0 && !ign_part_pairs) || n_ign_pairs < 0)
         return fail(SFX_ERR_ARG, "bad argument");
+    return set_collision_impl(m, faces_segm, faces_parents, ign_part_pairs, n_ign_pairs, false);
+}
+
+int sfx_model_set_collision_unfiltered(sfx_model* m, const int32_t* faces_group) {
+    if (!m || !faces_group) return fail(SFX_ERR_ARG, "bad argument");
+    return set_collision_impl(m, faces_group, nullptr, nullptr, 0, true);
+}
+
+static int set_collision_impl(sfx_model* m, const int32_t* faces_segm, const int32_t* faces_parents,
+                              const int32_t* ign_part_pairs, int32_t n_ign_pairs, bool unfiltered) {
     HostCollision c;
     std::string e = prepare_collision(m->V, m->F, m->faces_host.data(), m->vt_host.data(), faces_segm,
-                                      faces_parents, ign_part_pairs, n_ign_pairs, c);
+                                      faces_parents, ign_part_pairs, n_ign_pairs, c, unfiltered);
     if (!e.empty()) return fail(SFX_ERR_ARG, e);
     CUDA_TRY(m->part_ptr.upload(c.part_ptr));
     CUDA_TRY(m->part_faces.upload(c.part_faces));

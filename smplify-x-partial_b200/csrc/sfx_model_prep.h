@@ -271,7 +271,15 @@ struct HostCollision {
 template <typename TV>
 inline std::string prepare_collision(int V, int F, const int* faces, const TV* vt, const int32_t* segm,
                                      const int32_t* parents, const int32_t* ign_pairs, int n_ign,
-                                     HostCollision& c) {
+                                     HostCollision& c, bool unfiltered = false) {
+    // unfiltered: no FilterFaces (fit_single_frame.py:317-328 with an empty part_segm_fn) -- `segm`
+    // only groups the faces for the broad phase and every pair of groups is admissible, a group
+    // with itself included; faces that share a vertex are sorted out by the narrow phase
+    std::vector<int32_t> no_parents;
+    if (unfiltered && !parents && segm && F >= 1) {
+        no_parents.assign(F, -1);
+        parents = no_parents.data();
+    }
     if (!faces || !segm || !parents || F < 1) return "collision tables: missing array";
     if (F > 65535) return "collision tables: more than 65535 faces";
     int np = 0;
@@ -287,7 +295,7 @@ inline std::string prepare_collision(int V, int F, const int* faces, const TV* v
     c.part_allow.assign(SFX_NPART_MAX, 0ull);
     for (int p = 0; p < np; ++p)
         for (int q = 0; q < np; ++q)
-            if (p != q && parent_of[p] != q && parent_of[q] != p) c.part_allow[p] |= 1ull << q;
+            if (unfiltered || (p != q && parent_of[p] != q && parent_of[q] != p)) c.part_allow[p] |= 1ull << q;
     for (int i = 0; i < n_ign; ++i) {
         const int a = ign_pairs[2 * i], b = ign_pairs[2 * i + 1];
         if (a < 0 || b < 0) return "ign_part_pairs entry out of range";

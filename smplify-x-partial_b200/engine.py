@@ -36,6 +36,8 @@ class Model(object):
         faces = np.asarray(model_data['f']).astype(np.int64)
         self.faces = faces
         self.V = int(np.asarray(model_data['v_template']).shape[0])
+        # joint with the largest skinning weight per vertex (face grouping of the unfiltered collision search)
+        self.dominant_joint = np.asarray(model_data['weights']).argmax(axis=1).astype(np.int64)
         desc, keep = N.build_model_desc(model_data, joint_map, use_double=dtype == torch.float64,
                                         **model_kw)
         h = C.c_void_p()
@@ -101,6 +103,26 @@ class Model(object):
             N.check(self.lib, self.lib.sfx_model_set_collision(
                 self.h, C.c_void_p(segm.ctypes.data), C.c_void_p(par.ctypes.data),
                 C.c_void_p(ign.ctypes.data) if ign.shape[0] else None, int(ign.shape[0])))
+        self._coll_key = key
+        self.has_collision = True
+
+    def set_collision_unfiltered(self, faces_group=None):
+        """The interpenetration term without FilterFaces (the reference's path when no
+        ``part_segm_fn`` is given, fit_single_frame.py:317-328): every intersecting pair of
+        triangles that share no vertex counts.  ``faces_group`` [F] in 0..63 only groups the faces
+        for the search; default: the joint with the largest skinning weight of a face's first
+        vertex, folded into 64 groups."""
+        if faces_group is None:
+            faces_group = (self.dominant_joint[self.faces[:, 0]] % 64)
+        grp = np.ascontiguousarray(np.asarray(faces_group), dtype=np.int32).reshape(-1)
+        if grp.shape[0] != self.faces.shape[0]:
+            raise ValueError('face grouping has {} faces, the model {}'.format(grp.shape[0], self.faces.shape[0]))
+        key = ('unfiltered', hash(grp.tobytes()))
+        if getattr(self, '_coll_key', None) == key:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            N.check(self.lib, self.lib.sfx_model_set_collision_unfiltered(self.h, C.c_void_p(grp.ctypes.data)))
         self._coll_key = key
         self.has_collision = True
 

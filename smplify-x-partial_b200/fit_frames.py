@@ -299,11 +299,10 @@ class FitPlan(object):
                 penalize_outside=cfg.get('penalize_outside', True),
                 part_segm_fn=cfg.get('part_segm_fn', ''),
                 ign_part_pairs=cfg.get('ign_part_pairs'), part_segm=part_segm)
-            if ff is None:
-                raise NotImplementedError(
-                    'interpenetration on the device needs the face segmentation: pass '
-                    'part_segm_fn (reference README.md:55) or part_segm=')
-            self.collision = ff
+            # no segmentation: the reference runs the term without FilterFaces
+            # (fit_single_frame.py:317-328, fitting.py:449-450) -- so does the device search
+            self.collision = ff if ff is not None else 'unfiltered'
+
         self.cam_stage, self.stages = make_stages(cfg, L)
         self.jw, self.lowconf, self.init_mask = keypoint_masks(
             keypoints, cfg, base_joint_weights(cfg, K))
@@ -387,7 +386,10 @@ def upload(batch, plan):
         batch.model.set_gmm(plan.body_pose_prior)
     if plan.collision is not None:
         ff = plan.collision
-        batch.model.set_collision(ff.faces_segm, ff.faces_parents, ff.ign_part_pairs)
+        if isinstance(ff, str):
+            batch.model.set_collision_unfiltered()
+        else:
+            batch.model.set_collision(ff.faces_segm, ff.faces_parents, ff.ign_part_pairs)
         batch.enable_collisions()
     n = _set_targets(batch, plan)
     n += batch.set_params(plan.x0)

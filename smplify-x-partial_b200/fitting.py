@@ -115,12 +115,12 @@ class SMPLifyLoss(_WeightedLoss):
         """Weights + pose-prior branch of forward() (fitting.py:389-401) as SfxStage fields."""
         coll_w, coll_sigma = 0.0, 0.5
         if self.interpenetration and _as_float(getattr(self, 'coll_loss_weight', 0.0)) > 0:
-            # fitting.py:439-455; the device search needs the face segmentation (it is its
-            # broad phase), i.e. the reference's --part_segm_fn option
-            if self.pen_distance is None or self.tri_filtering_module is None:
+            # fitting.py:439-455; tri_filtering_module = None is the reference's path without
+            # --part_segm_fn: every pair the search reports is penalised
+            if self.pen_distance is None:
                 raise NotImplementedError(
-                    'interpenetration on the device needs pen_distance and tri_filtering_module '
-                    '(mesh_intersection.create_term with part_segm_fn, reference README.md:55)')
+                    'interpenetration on the device needs pen_distance '
+                    '(mesh_intersection.create_term, reference fit_single_frame.py:300-328)')
             coll_w = _as_float(self.coll_loss_weight)
             coll_sigma = float(self.pen_distance.sigma)
         if use_vposer:
@@ -256,8 +256,11 @@ class _FitBundle(object):
         if getattr(getattr(loss, 'body_pose_prior', None), 'kind', '') == 'gmm':
             bm.engine_model.set_gmm(loss.body_pose_prior)
         ff = getattr(loss, 'tri_filtering_module', None)
-        if getattr(loss, 'interpenetration', False) and ff is not None:
-            bm.engine_model.set_collision(ff.faces_segm, ff.faces_parents, ff.ign_part_pairs)
+        if getattr(loss, 'interpenetration', False):
+            if ff is not None:
+                bm.engine_model.set_collision(ff.faces_segm, ff.faces_parents, ff.ign_part_pairs)
+            else:
+                bm.engine_model.set_collision_unfiltered()     # fit_single_frame.py:317-328: no filter
             batch.enable_collisions()
         self._keep = (gt, conf, jw, lowconf, init_mask, camrow, reg)
         batch.set_targets_dev(gt, conf, jw, lowconf, init_mask, camrow, reg)

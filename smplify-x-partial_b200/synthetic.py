@@ -454,6 +454,27 @@ def cached_smplx_like(seed=0, pose_corrective_scale=1.0):
     return _CACHE[key]
 
 
+def without_degenerate_faces(model_data):
+    """Copy of ``model_data`` whose faces with a repeated corner (the tube-man's cap fans hold 98
+    of them) are replaced by a copy of the preceding proper face.  A triangle without area has no
+    circumscribed cone: the reference's penalty (and ours) differentiates it to NaN.  With
+    FilterFaces those faces never pair up on the test poses; without it they do, which no licensed
+    body mesh can show -- the unfiltered interpenetration tests use this copy."""
+    f = np.array(model_data['f'])
+    bad = (f[:, 0] == f[:, 1]) | (f[:, 1] == f[:, 2]) | (f[:, 0] == f[:, 2])
+    last = None
+    for i in range(f.shape[0]):
+        if bad[i]:
+            if last is None:
+                last = int(np.nonzero(~bad)[0][0])
+            f[i] = f[last]
+        else:
+            last = i
+    m = dict(model_data)
+    m['f'] = f
+    return m
+
+
 def parts_segm_like(model_data):
     """Face segmentation with the keys of ``smplx_parts_segm.pkl`` (reference
     fit_single_frame.py:317-328) for a model of this module: the real file describes the

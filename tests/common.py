@@ -162,7 +162,7 @@ def coll_case_inputs(ev, case):
         bending_prior_weight=w['bending_prior_weight'], hand_prior_weight=w['hand_prior_weight'],
         expr_prior_weight=w['expr_prior_weight'], jaw_prior_weight=w['jaw_prior_weight'],
         hand_joint_weight=0.1, face_joint_weight=2.0,
-        coll_loss_weight=w['coll_loss_weight'] if case == 'coll' else 0.0,
+        coll_loss_weight=w['coll_loss_weight'] if case != 'nocoll' else 0.0,
         coll_sigma=float(ev['sigma']))
     return dict(L=L, x=x, gt=kp[:, :2].copy(), conf=kp[:, 2].copy(), jw=jw_base, lowconf=lowconf,
                 init_mask=np.zeros(K, np.uint8), cam=cam, reg_pose=None, stage=st)

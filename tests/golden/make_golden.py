@@ -88,10 +88,10 @@ def demo_inputs():
     return out
 
 
-def build_reference_objects(cfg, dtype=torch.float32, use_vposer=False):
+def build_reference_objects(cfg, dtype=torch.float32, use_vposer=False, md=None):
     """Body model (restated smplx), reference priors, reference joint weights."""
     ref = ref_bridge.load()
-    md = synthetic.cached_smplx_like(0)
+    md = synthetic.cached_smplx_like(0) if md is None else md
     jm = U.smpl_to_annotation('smplx', use_hands=True, use_face=True,
                               use_face_contour=cfg.get('use_face_contour', True),
                               format=cfg.get('format', 'coco25'))
@@ -337,15 +337,21 @@ def coll_modules(md, max_collisions=128, sigma=1e-4):
                            ign_part_pairs=ign))
 
 
-def ref_eval_coll(inputs, dtype=torch.float64, tag='f64'):
+def ref_eval_coll(inputs, dtype=torch.float64, tag='f64', cases=(('coll', 0.1, True), ('nocoll', 0.0, True)),
+                  fname='ref_eval_coll', clean_faces=False):
     """One closure evaluation of the reference's SMPLifyLoss WITH the interpenetration term
     (fitting.py:437-455) driving the restated mesh_intersection package (oracle/isect_port.py),
-    at a pose whose arms cut into the torso."""
+    at a pose whose arms cut into the torso.  ``cases``: (key, coll_loss_weight, with FilterFaces);
+    without the filter (fit_single_frame.py:317-328 when part_segm_fn is empty) every intersecting
+    pair that shares no vertex is penalised (``fname`` = 'ref_eval_collnf', case 'collnf');
+    ``clean_faces``: on synthetic.without_degenerate_faces (a face without area has no cone)."""
     ref = ref_bridge.load()
     cfg = cfg_combined()
     frame = '18_cropped'
-    body_model, pri, jw, _ = build_reference_objects(cfg, dtype)
     md = synthetic.cached_smplx_like(0)
+    if clean_faces:
+        md = synthetic.without_degenerate_faces(md)
+    body_model, pri, jw, _ = build_reference_objects(cfg, dtype, md=md)
     rng = np.random.default_rng(11)
     P = _rand_params(rng, scale=0.5)
     pe = P['pose_embedding']
@@ -384,11 +390,11 @@ def ref_eval_coll(inputs, dtype=torch.float64, tag='f64'):
     out['sigma'] = np.array(1e-4)
     search_tree, pen_distance, filter_faces = coll_modules(md, sigma=1e-4)
     faces = body_model.faces_tensor.view(-1)
-    for case, w_coll in (('coll', 0.1), ('nocoll', 0.0)):
+    for case, w_coll, filtered in cases:
         loss = ref.fitting.create_loss(
             loss_type='smplify', rho=100, use_joints_conf=True, use_face=True, use_hands=True,
             vposer=None, interpenetration=True, search_tree=search_tree,
-            pen_distance=pen_distance, tri_filtering_module=filter_faces, dtype=dtype,
+            pen_distance=pen_distance, tri_filtering_module=filter_faces if filtered else None, dtype=dtype,
             regression_pose=None, num_stages=3, **pri)
         ww = dict(weights)
         ww['coll_loss_weight'] = w_coll
@@ -405,15 +411,17 @@ def ref_eval_coll(inputs, dtype=torch.float64, tag='f64'):
                 out[case + '/grad/' + name] = p.grad.numpy().copy()
         out[case + '/grad/pose_embedding'] = emb.grad.numpy().copy()
         out[case + '/grad/camera_translation'] = camera.translation.grad.numpy().copy()
-        if case == 'coll':
+        if w_coll > 0:
             tri = o.vertices[:, faces].view(1, -1, 3, 3)
-            ci = filter_faces(search_tree(tri))
+            ci = search_tree(tri)
+            if filtered:
+                ci = filter_faces(ci)
             pairs = ci[0][ci[0, :, 0] >= 0].numpy()
-            out['coll/pairs'] = pairs.astype(np.int32)
-            out['coll/vertices'] = o.vertices.detach().numpy()[0]
-    np.savez_compressed(os.path.join(HERE, 'ref_eval_coll_{}.npz'.format(tag)), **out)
-    print('ref_eval_coll', tag, float(out['coll/loss']), float(out['nocoll/loss']),
-          'pairs', len(out['coll/pairs']))
+            out[case + '/pairs'] = pairs.astype(np.int32)
+            out[case + '/vertices'] = o.vertices.detach().numpy()[0]
+    np.savez_compressed(os.path.join(HERE, '{}_{}.npz'.format(fname, tag)), **out)
+    print(fname, tag, {c[0]: float(out[c[0] + '/loss']) for c in cases},
+          'pairs', {c[0]: len(out[c[0] + '/pairs']) for c in cases if c[1] > 0})
     return out
 
 
@@ -674,6 +682,11 @@ if __name__ == '__main__':
             out['cfg_json'] = np.array(json.dumps(c))
             np.savez_compressed(os.path.join(HERE, tag + '.npz'), **out)
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'collnf':
+        nf = (('collnf', 0.1, False), ('nocoll', 0.0, True))
+        ref_eval_coll(inp, torch.float64, 'f64', nf, 'ref_eval_collnf', clean_faces=True)
+        ref_eval_coll(inp, torch.float32, 'f32', nf, 'ref_eval_collnf', clean_faces=True)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'coll':
         ref_eval_coll(inp, torch.float64, 'f64')
         ref_eval_coll(inp, torch.float32, 'f32')

@@ -78,14 +78,14 @@ class HostSim(object):
 
     def set_collision(self, faces_segm, faces_parents, ign_part_pairs=(), work_bytes=None):
         segm = np.ascontiguousarray(faces_segm, dtype=np.int32)
-        par = np.ascontiguousarray(faces_parents, dtype=np.int32)
+        par = np.ascontiguousarray(faces_parents, dtype=np.int32) if faces_parents is not None else None
         ign = np.ascontiguousarray(np.asarray(ign_part_pairs, dtype=np.int32).reshape(-1, 2))
         if work_bytes is None:          # what the device has: the idle blend ring
             work_bytes = 131072 if self.dt == np.float32 else 65536
         err = C.create_string_buffer(256)
         self.lib.hs_set_collision.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_char_p, C.c_int]
         rc = self.lib.hs_set_collision(self.h, segm.ctypes.data_as(C.c_void_p),
-                                       par.ctypes.data_as(C.c_void_p),
+                                       par.ctypes.data_as(C.c_void_p) if par is not None else None,
                                        ign.ctypes.data_as(C.c_void_p), ign.shape[0],
                                        int(work_bytes), err, 256)
         if rc:

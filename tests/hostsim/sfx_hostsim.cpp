@@ -188,16 +188,17 @@ void hs_set_vposer(void* p, const void* w1, const void* b1, const void* w2, cons
                           (const float*)b2, (const float*)w3, (const float*)b3);
 }
 // face segmentation + ignored part pairs of the interpenetration term; work_bytes = size of the
-// candidate area (the device uses the idle blend ring: 128 KB in float, 64 KB in double)
+// candidate area (the device uses the idle blend ring: 128 KB in float, 64 KB in double);
+// parents == NULL: the term without FilterFaces (segm only groups the faces)
 int hs_set_collision(void* p, const int32_t* segm, const int32_t* parents, const int32_t* ign,
                      int n_ign, int work_bytes, char* err, int errlen) {
     SimHandle* h = (SimHandle*)p;
     std::string e;
     if (h->use_double) {
-        e = prepare_collision(h->d.h.V, h->d.h.F, h->d.h.faces.data(), h->d.h.vt.data(), segm, parents, ign, n_ign, h->d.coll);
+        e = prepare_collision(h->d.h.V, h->d.h.F, h->d.h.faces.data(), h->d.h.vt.data(), segm, parents, ign, n_ign, h->d.coll, parents == nullptr);
         h->d.has_coll = e.empty(); h->d.coll_work_bytes = work_bytes;
     } else {
-        e = prepare_collision(h->f.h.V, h->f.h.F, h->f.h.faces.data(), h->f.h.vt.data(), segm, parents, ign, n_ign, h->f.coll);
+        e = prepare_collision(h->f.h.V, h->f.h.F, h->f.h.faces.data(), h->f.h.vt.data(), segm, parents, ign, n_ign, h->f.coll, parents == nullptr);
         h->f.has_coll = e.empty(); h->f.coll_work_bytes = work_bytes;
     }
     if (!e.empty()) { std::strncpy(err, e.c_str(), errlen - 1); return -1; }

@@ -173,6 +173,32 @@ def test_eval_with_interpenetration_hostsim(dt, tol_loss, tol_g):
         (0 if dt == 'f64' else 1e-6 * np.abs(res['coll']['grad']).max())
 
 
+@pytest.mark.parametrize('dt,tol_loss,tol_g', [('f64', 1e-13, 1e-10), ('f32', 1e-5, 2e-3)])
+def test_eval_without_the_face_filter_hostsim(dt, tol_loss, tol_g):
+    """The reference's path without part_segm_fn (fit_single_frame.py:317-328: filter_faces =
+    None): 109 412 pairs instead of 8 343; the faces are only grouped for the broad phase."""
+    ev = Cm.golden('ref_eval_collnf_{}.npz'.format(dt))
+    md = Cm.synthetic.without_degenerate_faces(Cm.model_data())
+    hs = HostSim(md, Cm.joint_map(), use_double=(dt == 'f64'), **Cm.MODEL_KW)
+    faces = np.asarray(md['f']).astype(np.int64)
+    hs.set_collision(np.asarray(md['weights']).argmax(1)[faces[:, 0]] % 64, None, [])
+    L = Cm.layout()
+    res = {}
+    for case in ('nocoll', 'collnf'):
+        I = Cm.coll_case_inputs(ev, case)
+        r = hs.eval(I['stage'], I['x'], I['gt'], I['conf'], I['jw'], I['cam'], I['lowconf'],
+                    I['init_mask'], None)
+        ref = float(ev[case + '/loss'])
+        assert abs(r['loss'] - ref) <= tol_loss * abs(ref) and r['flags'] == 0
+        res[case] = r
+    assert hs.last_touched() > 9000 and len(ev['collnf/pairs']) > 100000
+    g = res['collnf']['grad'] - res['nocoll']['grad']
+    g_ref = Cm.golden_grad_vector(L, ev, 'collnf') - Cm.golden_grad_vector(L, ev, 'nocoll')
+    assert np.abs(g_ref).max() > 1000.0
+    assert np.abs(g - g_ref).max() <= tol_g * np.abs(g_ref).max() + \
+        (0 if dt == 'f64' else 1e-6 * np.abs(res['collnf']['grad']).max())
+
+
 def test_candidate_overflow_falls_back_to_the_global_area():
     """With a tiny shared work area the candidates spill to the block's global arrays and the
     result does not change."""

@@ -206,9 +206,15 @@ def test_closure_with_interpenetration_objects():
         # weight 0 switches the term off (fitting.py:439)
         loss.reset_loss_weights(dict(w, coll_loss_weight=0.0))
         assert float(closure(stage=1, backward=False)) == pytest.approx(float(ev['nocoll/loss']), rel=1e-11)
-    # without the face filter the device path refuses instead of dropping the term
+    # without the face filter the term keeps every pair (reference fitting.py:449-450); without a
+    # penalty object the device path refuses instead of dropping the term
+    nofilter = fitting.create_loss('smplify', interpenetration=True, search_tree=search_tree,
+                                   pen_distance=pen_distance, tri_filtering_module=None, dtype=dtype,
+                                   num_stages=3, **pri).to(dev)
+    nofilter.reset_loss_weights(w)
+    assert nofilter.stage_kwargs(False, 1)['coll_loss_weight'] == w['coll_loss_weight']
     bad = fitting.create_loss('smplify', interpenetration=True, search_tree=search_tree,
-                              pen_distance=pen_distance, tri_filtering_module=None, dtype=dtype,
+                              pen_distance=None, tri_filtering_module=None, dtype=dtype,
                               num_stages=3, **pri).to(dev)
     bad.reset_loss_weights(w)
     with pytest.raises(NotImplementedError):

@@ -98,10 +98,17 @@ def test_cli_end_to_end(tmp_path):
     assert err.mean() <= float(env['fit/vertex_pairwise_mean'])
     assert r['body_pose'].shape == (1, 63) and r['betas'].dtype == np.float32
 
-    # the profile as shipped (interpenetration True) needs the face segmentation ...
-    with pytest.raises(NotImplementedError, match='part_segm_fn'):
-        _run(tmp_path, 'out_refused', [])
-    # ... and runs with it
+    # the profile as shipped (interpenetration True, no part_segm_fn) runs the term without
+    # FilterFaces, as the reference does (fit_single_frame.py:317-328) -- on a mesh whose faces
+    # all have area (the tube-man's area-less cap faces turn the reference's penalty into NaN too)
+    (tmp_path / 'models_clean' / 'smplx').mkdir(parents=True)
+    np.savez(str(tmp_path / 'models_clean' / 'smplx' / 'SMPLX_NEUTRAL.npz'),
+             **Cm.synthetic.without_degenerate_faces(Cm.model_data()))
+    out = _run(tmp_path, 'out_unfiltered', ['--model_folder', str(tmp_path / 'models_clean'),
+                                            '--maxiters', '3'])
+    res3 = _check_outputs(out, want_keys)
+    assert not np.array_equal(res3['02_cropped'][1], res['02_cropped'][1])
+    # ... and with the face segmentation
     segm, par, ign = Cm.coll_segmentation()
     seg_fn = tmp_path / 'parts_segm.pkl'
     with open(seg_fn, 'wb') as f:

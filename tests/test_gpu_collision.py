@@ -133,7 +133,47 @@ def test_fit_frames_with_interpenetration_pipeline_equals_staged():
     assert a.flags.max() == 0 and np.all(np.isfinite(a.params))
     assert np.array_equal(a.params, b.params) and np.array_equal(a.loss, b.loss)
     assert np.array_equal(a.n_evals, b.n_evals) and np.array_equal(a.vertices, b.vertices)
-    # without part_segm the device path refuses instead of silently dropping the term
-    with pytest.raises(NotImplementedError, match='segmentation'):
-        FF.FitPlan(batch.L, model.K, kp, 600, 800, cfg, [d[3] for d in data],
-                   [d[4] for d in data], None, np.float32)
+    # without part_segm the plan carries the reference's unfiltered term (fit_single_frame.py:317-328)
+    assert FF.FitPlan(batch.L, model.K, kp, 600, 800, cfg, [d[3] for d in data],
+                      [d[4] for d in data], None, np.float32).collision == 'unfiltered'
+
+
+@pytest.mark.parametrize('dt,tol_loss,tol_pen,tol_grad', [('f64', 1e-12, 1e-9, 1e-9),
+                                                          ('f32', 1e-5, 2e-3, 2e-3)])
+def test_eval_with_interpenetration_without_the_face_filter(dt, tol_loss, tol_pen, tol_grad):
+    """The reference's path when no part_segm_fn is given (fit_single_frame.py:317-328,
+    fitting.py:449-450: filter_faces = None): every intersecting pair of triangles that share no
+    vertex is penalised -- 109 412 pairs on the golden pose against 8 343 with the filter
+    (tests/golden/ref_eval_collnf_*.npz, the reference's SMPLifyLoss on the restated package; on
+    the synthetic mesh without its 98 area-less cap faces, whose cones are NaN on both sides).  On
+    the device the faces are only grouped (by dominant joint) for the broad phase; every face is a
+    candidate, so the sweep arrays live in the block's global workspace."""
+    from smplifyx_b200 import engine
+    dtype = torch.float64 if dt == 'f64' else torch.float32
+    ev = Cm.golden('ref_eval_collnf_{}.npz'.format(dt))
+    B = 2
+    model = engine.Model(Cm.synthetic.without_degenerate_faces(Cm.model_data()), Cm.joint_map(),
+                         dtype=dtype, **Cm.MODEL_KW)
+    model.set_collision_unfiltered()
+    batch = engine.FrameBatch(model, B)
+    batch.enable_collisions()
+    out = {}
+    for case in ('nocoll', 'collnf'):
+        I = Cm.coll_case_inputs(ev, case)
+        _load(batch, I, B)
+        loss, grad, _ = batch.eval(I['stage'])
+        out[case] = (loss.cpu().numpy().astype(np.float64), grad.cpu().numpy().astype(np.float64))
+        ref = float(ev[case + '/loss'])
+        assert np.all(np.abs(out[case][0] - ref) <= tol_loss * abs(ref)), (case, out[case][0], ref)
+    assert int(batch.flags().cpu().numpy().max()) & N.SFX_FLAG_COLL_OVERFLOW == 0
+    L = Cm.layout()
+    pen_ref = float(ev['collnf/loss']) - float(ev['nocoll/loss'])
+    g_ref = Cm.golden_grad_vector(L, ev, 'collnf') - Cm.golden_grad_vector(L, ev, 'nocoll')
+    assert pen_ref > 1000 and len(ev['collnf/pairs']) > 100000
+    for f in range(B):
+        pen = out['collnf'][0][f] - out['nocoll'][0][f]
+        g = out['collnf'][1][f] - out['nocoll'][1][f]
+        assert abs(pen - pen_ref) <= tol_pen * pen_ref + tol_loss * abs(float(ev['collnf/loss'])), (pen, pen_ref)
+        assert np.abs(g - g_ref).max() <= tol_grad * np.abs(g_ref).max() + \
+            tol_loss * np.abs(out['collnf'][1][f]).max(), np.abs(g - g_ref).max()
+    assert np.array_equal(out['collnf'][1][0], out['collnf'][1][1])

@@ -156,7 +156,8 @@ def test_pare_regression_and_camera_prior():
 
 def test_plan_carries_the_interpenetration_settings():
     """The shipped profile's interpenetration keys reach the stages (coll weights per stage,
-    df_cone_height) and the face filter; without a segmentation the plan refuses."""
+    df_cone_height) and the face filter; without a segmentation the plan carries the reference's
+    unfiltered term (fit_single_frame.py:317-328: filter_faces = None)."""
     from smplifyx_b200.cmd_parser import parse_config
     cfg = parse_config(['-c', os.path.join(Cm.ROOT, 'cfg_files', 'fit_smplx_combined_coco25.yaml')])
     cfg.pop('config')
@@ -165,8 +166,8 @@ def test_plan_carries_the_interpenetration_settings():
     kp = np.zeros((2, 135, 3))
     kp[:, :, :2] = 300.0
     kp[:, :, 2] = 0.9
-    with pytest.raises(NotImplementedError, match='part_segm_fn'):
-        FF.FitPlan(L, 135, kp, 600, 800, cfg, None, None, None, np.float32)
+    plan = FF.FitPlan(L, 135, kp, 600, 800, cfg, None, None, None, np.float32)
+    assert plan.collision == 'unfiltered' and [st.coll_loss_weight for st in plan.stages] == [0.0, 0.1, 1.0]
     segm, par, ign = Cm.coll_segmentation()
     plan = FF.FitPlan(L, 135, kp, 600, 800, cfg, None, None, None, np.float32,
                       part_segm={'segm': segm, 'parents': par})
