@@ -841,7 +841,11 @@ def run_b200(args):
                 '(evaluations of the longest frame x SMs): the single-wave tail of ONE launch '
                 '(kernel_ms_per_step, this launch alone); sm_time_busy_frac_measured the same from '
                 'the per-frame cycle counters; sm_time_busy_frac_in_flight = the frames\' SM-time '
-                'over SMs x ms_per_step with the steps overlapping'.format(
+                'over SMs x ms_per_step with the steps overlapping; achieved_in_flight / '
+                'frac_in_flight (also under l2_to_sm) = the same flops / rows over ms_per_step, '
+                'the launch configuration of value.  While a block streams rows it draws its '
+                'SM\'s share of the L2 peak (about 88 of 84 GB/s per SM: DESIGN.md section 4); '
+                'the passes are a third of an evaluation'.format(
                     EVAL_FIXED_FLOPS)}
     coll_stats = batch.coll_stats()
     if coll_stats is not None:
@@ -868,6 +872,13 @@ def run_b200(args):
     sm_ms = float(frame_cycles.sum() / SM_CLOCK_KHZ)
     roofline['sm_time_busy_frac_measured'] = sm_ms / (model_sms(batch) * kern_ms)
     roofline['sm_time_busy_frac_in_flight'] = sm_ms / (model_sms(batch) * (total_ms / args.steps))
+    # the same accounting at the launch configuration of `value` (steps overlapping): this batch's
+    # executed flops / streamed rows over the in-flight step time
+    step_s = total_ms / args.steps * 1e-3
+    roofline['achieved_in_flight'] = flops / step_s / 1e12
+    roofline['frac_in_flight'] = flops / step_s / 1e12 / tf_peak
+    roofline['l2_to_sm']['achieved_in_flight'] = row_bytes / step_s / 1e9
+    roofline['l2_to_sm']['frac_in_flight'] = row_bytes / step_s / 1e9 / max(float(l2_gbs.value), 1e-9)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
@@ -943,8 +954,9 @@ def model_sms(batch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=None,
+                    help='timed steps (default 20; 5 for --impl reference: 14 s of CPU work each)')
+    ap.add_argument('--warmup', type=int, default=None, help='untimed steps (default 5; 3 for --impl reference)')
     ap.add_argument('--frames', type=int, default=128, help='frames per GPU')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
@@ -975,6 +987,12 @@ def main():
     ap.add_argument('--traffic', type=float, default=None,
                     help='dram bytes per launch from an ncu capture (profiles/), recorded as-is')
     args = ap.parse_args()
+    # with six steps in flight a short run is mostly pipeline fill and drain (the timed region is
+    # bracketed by synchronisations): the engine arm defaults to the driver's 20 / 5
+    if args.steps is None:
+        args.steps = 5 if args.impl == 'reference' else 20
+    if args.warmup is None:
+        args.warmup = 3 if args.impl == 'reference' else 5
     global TWO_LOOP
     if args.two_loop:
         TWO_LOOP = args.two_loop
