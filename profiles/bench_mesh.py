@@ -5,7 +5,9 @@ import os, sys
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 import bench
-from smplifyx_b200 import engine, synthetic, utils as U
+from smplifyx_b200 import engine, synthetic, utils as U, _native as N
+if '--lib' in sys.argv:     # another build of the library (csrc/<name>), e.g. -DSFX_FU_TF=48
+    N.LIB_PATH = os.path.join(os.path.dirname(N.LIB_PATH), sys.argv[sys.argv.index('--lib') + 1])
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 jm = U.smpl_to_annotation('smplx', True, True, True, 'coco25')
 model = engine.Model(synthetic.cached_smplx_like(0), jm, dtype=torch.float32, **bench.MODEL_KW)

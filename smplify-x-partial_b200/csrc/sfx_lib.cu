@@ -618,7 +618,7 @@ struct sfx_model {
     int num_sms = 0;
     MeshPlan mesh;        // TMA descriptor of the blend matrix for the tensor-core mesh kernel
     FusedPlan fused;      // descriptors of the fused blend + skinning kernel (sfx_mesh_fused.cuh)
-    DevBuf whi, wlo;      // skinning weights [Vpad][64], tf32 hi / lo split
+    DevBuf whi, wlo;      // skinning weights [Vpad][64], float16 hi / lo split
 };
 
 template <typename T>
@@ -769,10 +769,10 @@ int sfx_model_create(const sfx_model_desc* desc, sfx_model** out) {
         if (e.empty()) {
             // skinning weights for the tensor-core kernel: 64 padded joints, split x = hi + lo
             const int Vpad = (m->V + FU_TV - 1) / FU_TV * FU_TV;
-            std::vector<float> whi((size_t)Vpad * FU_WJ, 0.f), wlo((size_t)Vpad * FU_WJ, 0.f);
+            std::vector<__half> whi((size_t)Vpad * FU_WJ, __float2half_rn(0.f)), wlo((size_t)Vpad * FU_WJ, __float2half_rn(0.f));
             for (int v = 0; v < m->V; ++v)
                 for (int j = 0; j < SFX_NJ; ++j)
-                    tf32_split(desc->arrays_float64
+                    f16_split(desc->arrays_float64
                                    ? (float)static_cast<const double*>(desc->lbs_weights)[(size_t)v * SFX_NJ + j]
                                    : static_cast<const float*>(desc->lbs_weights)[(size_t)v * SFX_NJ + j],
                                &whi[(size_t)v * FU_WJ + j],
@@ -780,8 +780,8 @@ int sfx_model_create(const sfx_model_desc* desc, sfx_model** out) {
             cudaError_t ce = m->whi.upload(whi);
             if (ce == cudaSuccess) ce = m->wlo.upload(wlo);
             if (ce != cudaSuccess) e = std::string("upload skinning weights: ") + cudaGetErrorString(ce);
-            else e = fused_plan_create(m->fused, (const float*)m->PK.p, m->V, (const float*)m->whi.p,
-                                       (const float*)m->wlo.p, Vpad);
+            else e = fused_plan_create(m->fused, (const float*)m->PK.p, m->V, (const __half*)m->whi.p,
+                                       (const __half*)m->wlo.p, Vpad);
         }
         if (!e.empty()) rc = fail(SFX_ERR_CUDA, e);
     }
@@ -932,8 +932,8 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     ALLOC(Acoef, (size_t)B * SFX_NJ * 12 * es);
     ALLOC(Ccoef, (size_t)mesh_padded_frames(B) * SFX_KPAD * es);
     ALLOC(vposed, (size_t)mesh_padded_frames(B) * 3 * m->V * es);
-    ALLOC(ahi, (size_t)mesh_padded_frames(B) * 12 * FU_WJ * sizeof(float));
-    ALLOC(alo, (size_t)mesh_padded_frames(B) * 12 * FU_WJ * sizeof(float));
+    ALLOC(ahi, (size_t)mesh_padded_frames(B) * 12 * FU_WJ * sizeof(__half));
+    ALLOC(alo, (size_t)mesh_padded_frames(B) * 12 * FU_WJ * sizeof(__half));
     ALLOC(go_saved, (size_t)B * 3 * es);
     ALLOC(params_alt, (size_t)B * b->lay.np * es);
     ALLOC(loss_alt, (size_t)B * es);
@@ -1412,9 +1412,9 @@ static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev,
                                          (const float*)b->Ccoef.p, (float*)b->vposed.p,
                                          (float*)vertices_dev, s);
         } else if (!(unfused && unfused[0] == '1')) {
-            // one tensor-core kernel: blend (tf32) + skinning (3 x tf32) + transform epilogue
+            // one tensor-core kernel: blend (tf32) + skinning (3 x f16 split) + transform epilogue
             e = mesh_fused_tc(m->fused, b->B, (const float*)b->Ccoef.p, (const float*)b->Acoef.p,
-                              (float*)b->ahi.p, (float*)b->alo.p, (const float*)m->vt.p,
+                              (__half*)b->ahi.p, (__half*)b->alo.p, (const float*)m->vt.p,
                               (float*)vertices_dev, s);
         } else {
             e = mesh_blend_tc(m->mesh, b->B, (const float*)b->Ccoef.p, (const float*)m->vt.p,

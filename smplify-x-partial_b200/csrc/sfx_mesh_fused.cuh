@@ -3,7 +3,7 @@
 // tcgen05 with TMA-fed operands, the posed offsets never leaving tensor memory.
 //
 //   K1  blend     vp[v][c][f]  = sum_k PK[3v+c][k] . C[f][k]          k < 512   (kind::tf32)
-//   K2  skinning  T[v][f][e]   = sum_j W[v][j] . A[f][j][e]           j < 64, e < 12  (3 x tf32 split)
+//   K2  skinning  T[v][f][e]   = sum_j W[v][j] . A[f][j][e]           j < 64, e < 12  (3 x f16 split)
 //   epilogue      vert[f][v][r] = T[v][f][4r..4r+2] . (vt[v] + vp[v][.][f]) + T[v][f][4r+3]
 //
 // One CTA owns a tile of 128 vertices x 128 frames.  TMEM (512 columns x 128 lanes, lane =
@@ -13,9 +13,12 @@
 //   warp 8 / lane 0   TMA producer.  K1: 16 k-blocks of {3 x [128 v][32 k] of PK through a 3-D
 //                     tensor map over PK viewed as [V][3][512], [128 f][32 k] of C}, 3-stage ring.
 //                     K2 (re-using the ring's memory once K1's MMAs have drained): the two W tiles
-//                     (hi / lo) once, then per chunk the hi / lo tiles of A^T for 8 frames.
-//   warp 9 / lane 0   MMA issuer.  K1: 4 x tcgen05.mma m128 n128 k8 per component and k-block;
-//                     K2 per chunk: 8 k-steps x {Whi.Ahi, Wlo.Ahi, Whi.Alo} m128 n96 k8.
+//                     (hi / lo, float16: 64 joints = one 128-byte swizzle row) once, then per
+//                     chunk the hi / lo tiles of A^T for 8 frames.
+//   warp 9 / lane 0   MMA issuer.  K1: 4 x tcgen05.mma m128 n128 k8 (kind::tf32) per component
+//                     and k-block; K2 per chunk: 4 k-steps x {Whi.Ahi, Wlo.Ahi, Whi.Alo} m128 n96
+//                     k16 (kind::f16): half the instructions of a tf32 split (k8) for the same
+//                     products.
 //   warps 0..7        epilogue, a thread per vertex and half chunk (warps w and w + 4 share a TMEM lane
 //                     quadrant and take 4 frames each; 16 warps measured no faster): tcgen05.ld of T (48 columns) and of the chunk's
 //                     frames of the three K1 accumulators, 4 x (3x4 transform), staged in shared
@@ -25,10 +28,23 @@
 //
 // tf32 keeps 10 mantissa bits.  K1 multiplies centimetre-sized blend offsets: error ~5e-6 m.  K2
 // multiplies metre-sized transforms, so W and A are split x = hi + lo with hi = x rounded to
-// tf32 and the three significant products are accumulated (the lo.lo term is 2^-22 relative):
-// measured against the float32 SIMT kernel in tests/test_gpu_parity.py.
+// float16 (11 significant bits, like tf32; weights lie in [0, 1] and transforms within a few
+// metres, far inside the float16 range) and lo = the remainder rounded to float16; the products
+// of float16 values are exact in the float32 accumulator and the three significant ones are
+// accumulated (the lo.lo term is 2^-22 relative): measured against the float32 SIMT kernel in
+// tests/test_gpu_parity.py.
+//
+// Measured and not adopted (128 frames, whole forward 56 us with this kernel at 33.8 us):
+//   * frame tiles of 64 or 48 frames (164 / 246 CTAs instead of 82 on 148 SMs): 66 us -- every
+//     extra frame tile streams the blend matrix again;
+//   * a tiled copy of PK whose TMA boxes are 16 KB of consecutive bytes (instead of 128-byte
+//     pieces 6 KB apart): no change -- the K1 phase is bound by what one SM draws (1 MB per CTA at
+//     ~88 GB/s), not by the DRAM access pattern;
+//   * chunks of 4 frames with two alternating K2 accumulators: 62 us -- the epilogue's chain per
+//     chunk (tensor-memory load, wait, staging, barrier, copy-out) is latency, not throughput.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -47,19 +63,21 @@ constexpr int FU_STAGES = 3;
 constexpr int FU_A_BYTES = FU_TV * FU_KB * 4;                       // 16 KB: one [128][32] tile
 constexpr int FU_STAGE_BYTES = 3 * FU_A_BYTES + FU_TF * FU_KB * 4;  // 64 KB
 constexpr int FU_RING_BYTES = FU_STAGES * FU_STAGE_BYTES;           // 192 KB
-constexpr int FU_W_BYTES = 4 * FU_A_BYTES;                          // Whi | Wlo, two 32-wide boxes each
-constexpr int FU_A2_BOX = FU_N2 * FU_KB * 4;                        // 12 KB: one [96][32] tile
-constexpr int FU_A2_BYTES = 4 * FU_A2_BOX;                          // hi | lo, two boxes each: 48 KB
+constexpr int FU_WJ = 64;                   // padded joint count (K of K2): 64 float16 = one 128-byte swizzle row
+constexpr int FU_K2 = 16;                   // float16 MMA depth (32 bytes)
+constexpr int FU_W_BOX = FU_TV * FU_WJ * 2;                         // 16 KB: one [128 v][64 j] float16 tile
+constexpr int FU_W_BYTES = 2 * FU_W_BOX;                            // Whi | Wlo
+constexpr int FU_A2_BOX = FU_N2 * FU_WJ * 2;                        // 12 KB: one [96][64 j] float16 tile
+constexpr int FU_A2_BYTES = 2 * FU_A2_BOX;                          // hi | lo: 24 KB
 constexpr int FU_OUT_BYTES = FU_CH * 3 * FU_TV * 4;                 // 12 KB staging per chunk
 constexpr int FU_SMEM_BYTES = FU_RING_BYTES + 2 * FU_OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int FU_EPW = 2;                    // epilogue warps per TMEM lane quadrant (each takes FU_CH / FU_EPW frames of a chunk)
 constexpr int FU_THREADS = 32 * (4 * FU_EPW + 2);   // epilogue warps, then the TMA warp and the MMA warp
-constexpr int FU_WJ = 64;                   // padded joint count (K of K2)
 static_assert(FU_W_BYTES + 2 * FU_A2_BYTES <= FU_RING_BYTES, "K2 operands re-use the K1 ring");
 
 struct FusedPlan {
     CUtensorMap map_pk3;      // PK as [V][3][512] fp32, box {32, 1, 128}, SWIZZLE_128B
-    CUtensorMap map_whi, map_wlo;   // [Vpad][64] fp32, box {32, 128}
+    CUtensorMap map_whi, map_wlo;   // [Vpad][64] float16, box {64, 128}
     bool ready = false;
     int V = 0;
 };
@@ -85,21 +103,41 @@ static std::string make_map3(CUtensorMap* map, const float* base, uint64_t V) {
     return "";
 }
 
-// x -> (hi, lo): hi keeps the 10 mantissa bits the tensor core reads, lo the remainder
-static inline void tf32_split(float x, float* hi, float* lo) {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    u &= 0xffffe000u;
-    memcpy(hi, &u, 4);
-    *lo = x - *hi;
+// [rows][64] float16, K-major: a row is one 128-byte swizzle row
+static std::string make_tile_map_f16(CUtensorMap* map, const __half* base, uint64_t rows, uint32_t box_rows) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+            return "cuTensorMapEncodeTiled is not available from this driver";
+        fn = (PFN_encodeTiled)p;
+    }
+    cuuint64_t dims[2] = {FU_WJ, rows};
+    cuuint64_t strides[1] = {FU_WJ * sizeof(__half)};
+    cuuint32_t box[2] = {FU_WJ, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled (float16) failed with code " + std::to_string((int)r);
+    return "";
 }
 
-static std::string fused_plan_create(FusedPlan& plan, const float* PK, int V, const float* whi_dev,
-                                     const float* wlo_dev, int Vpad) {
+// x -> (hi, lo): hi = x rounded to float16 (the 11 bits one tensor-core product keeps), lo the
+// remainder, rounded to float16
+__host__ __device__ inline void f16_split(float x, __half* hi, __half* lo) {
+    *hi = __float2half_rn(x);
+    *lo = __float2half_rn(x - __half2float(*hi));
+}
+
+static std::string fused_plan_create(FusedPlan& plan, const float* PK, int V, const __half* whi_dev,
+                                     const __half* wlo_dev, int Vpad) {
     plan.V = V;
     std::string e = make_map3(&plan.map_pk3, PK, (uint64_t)V);
-    if (e.empty()) e = make_tile_map(&plan.map_whi, whi_dev, Vpad, FU_WJ, FU_TV, FU_KB);
-    if (e.empty()) e = make_tile_map(&plan.map_wlo, wlo_dev, Vpad, FU_WJ, FU_TV, FU_KB);
+    if (e.empty()) e = make_tile_map_f16(&plan.map_whi, whi_dev, Vpad, FU_TV);
+    if (e.empty()) e = make_tile_map_f16(&plan.map_wlo, wlo_dev, Vpad, FU_TV);
     plan.ready = e.empty();
     return e;
 }
@@ -114,6 +152,21 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 }
 __device__ __forceinline__ uint32_t umma_idesc_tf32_n(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// kind::f16 with float16 operands, fp32 accumulate, A and B K-major, M = 128
+__device__ __forceinline__ uint32_t umma_idesc_f16_n(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -178,8 +231,8 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
     const uint32_t tmem_d2 = tmem_base + 3 * FU_TF;
 
     // K2 operand layout inside the (re-used) ring
-    unsigned char* wbuf = smem;                          // Whi k0..31 | Whi k32..63 | Wlo .. | Wlo ..
-    unsigned char* a2buf = smem + FU_W_BYTES;            // two slots of {Ahi, Ahi', Alo, Alo'}
+    unsigned char* wbuf = smem;                          // Whi | Wlo, [128 v][64 j] float16 each
+    unsigned char* a2buf = smem + FU_W_BYTES;            // two slots of {Ahi, Alo}, [96][64 j] float16 each
 
     if (warp == 4 * FU_EPW && lane == 0) {
         // ===== TMA producer =====
@@ -194,20 +247,16 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
         // K2 operands go where the K1 stages were: wait until K1's MMAs have read them all
         mbar_wait(d1_full, 0);
         mbar_expect_tx(w_full, FU_W_BYTES);
-        for (int h = 0; h < 2; ++h) {
-            tma_load_2d(wbuf + h * FU_A_BYTES, &map_whi, h * FU_KB, v0, w_full);
-            tma_load_2d(wbuf + (2 + h) * FU_A_BYTES, &map_wlo, h * FU_KB, v0, w_full);
-        }
+        tma_load_2d(wbuf, &map_whi, 0, v0, w_full);
+        tma_load_2d(wbuf + FU_W_BOX, &map_wlo, 0, v0, w_full);
         for (int q = 0; q < nchunk; ++q) {
             const int s = q & 1;
             if (q >= 2) mbar_wait(a2_empty + s, ((q >> 1) - 1) & 1);
             unsigned char* a = a2buf + s * FU_A2_BYTES;
             const int row0 = (m0 + q * FU_CH) * 12;
             mbar_expect_tx(a2_full + s, FU_A2_BYTES);
-            for (int h = 0; h < 2; ++h) {
-                tma_load_2d(a + h * FU_A2_BOX, &map_ahi, h * FU_KB, row0, a2_full + s);
-                tma_load_2d(a + (2 + h) * FU_A2_BOX, &map_alo, h * FU_KB, row0, a2_full + s);
-            }
+            tma_load_2d(a, &map_ahi, 0, row0, a2_full + s);
+            tma_load_2d(a + FU_A2_BOX, &map_alo, 0, row0, a2_full + s);
         }
     } else if (warp == 4 * FU_EPW + 1 && lane == 0) {
         // ===== MMA issuer =====
@@ -228,7 +277,8 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
             tc_commit(empty + s);
         }
         tc_commit(d1_full);                  // K1 accumulators complete, K1 operands consumed
-        const uint32_t idesc2 = umma_idesc_tf32_n(FU_N2);
+        const uint32_t idesc2 = umma_idesc_f16_n(FU_N2);
+        const uint64_t whi = umma_desc_sw128(wbuf), wlo = umma_desc_sw128(wbuf + FU_W_BOX);
         mbar_wait(w_full, 0);
         for (int q = 0; q < nchunk; ++q) {
             const int s = q & 1;
@@ -236,20 +286,13 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
             if (q >= 1) mbar_wait(d2_empty, (q - 1) & 1);      // the epilogue has read the previous chunk
             tc_fence_after();
             unsigned char* a = a2buf + s * FU_A2_BYTES;
-            bool first = true;
+            const uint64_t ahi = umma_desc_sw128(a), alo = umma_desc_sw128(a + FU_A2_BOX);
+            // 55 joints: the k-step of joints 48 .. 63 still holds seven of them
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint64_t whi = umma_desc_sw128(wbuf + h * FU_A_BYTES);
-                const uint64_t wlo = umma_desc_sw128(wbuf + (2 + h) * FU_A_BYTES);
-                const uint64_t ahi = umma_desc_sw128(a + h * FU_A2_BOX);
-                const uint64_t alo = umma_desc_sw128(a + (2 + h) * FU_A2_BOX);
-#pragma unroll
-                for (int k = 0; k < FU_KB / 8; ++k) {
-                    umma_tf32(tmem_d2, whi + 2 * k, ahi + 2 * k, idesc2, first ? 0u : 1u);
-                    first = false;
-                    umma_tf32(tmem_d2, wlo + 2 * k, ahi + 2 * k, idesc2, 1u);
-                    umma_tf32(tmem_d2, whi + 2 * k, alo + 2 * k, idesc2, 1u);
-                }
+            for (int k = 0; k < FU_WJ / FU_K2; ++k) {
+                umma_f16(tmem_d2, whi + 2 * k, ahi + 2 * k, idesc2, k == 0 ? 0u : 1u);
+                umma_f16(tmem_d2, wlo + 2 * k, ahi + 2 * k, idesc2, 1u);
+                umma_f16(tmem_d2, whi + 2 * k, alo + 2 * k, idesc2, 1u);
             }
             tc_commit(a2_empty + s);
             tc_commit(d2_full);
@@ -327,26 +370,24 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
 
 // A^T tiles of K2: per frame 12 rows x 64 joints (hi and lo), row 12 f + e, from the skinning
 // transforms A [B][55][12] of the pose prologue
-__global__ void mesh_at_split_kernel(const float* __restrict__ A, int B, int Bpad, float* __restrict__ ahi,
-                                     float* __restrict__ alo) {
+__global__ void mesh_at_split_kernel(const float* __restrict__ A, int B, int Bpad, __half* __restrict__ ahi,
+                                     __half* __restrict__ alo) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= Bpad * 12 * FU_WJ) return;
     const int j = idx % FU_WJ, row = idx / FU_WJ, f = row / 12, e = row % 12;
     float x = 0.f;
     if (f < B && j < SFX_NJ) x = A[((size_t)f * SFX_NJ + j) * 12 + e];
-    const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-    ahi[idx] = hi;
-    alo[idx] = x - hi;
+    f16_split(x, ahi + idx, alo + idx);
 }
 
-static std::string mesh_fused_tc(const FusedPlan& plan, int B, const float* C, const float* A, float* ahi,
-                                 float* alo, const float* vt, float* verts, cudaStream_t s) {
+static std::string mesh_fused_tc(const FusedPlan& plan, int B, const float* C, const float* A, __half* ahi,
+                                 __half* alo, const float* vt, float* verts, cudaStream_t s) {
     if (!plan.ready) return "fused tensor-core mesh plan was not created";
     const int Bpad = (B + FU_TF - 1) / FU_TF * FU_TF;
     CUtensorMap map_c, map_ahi, map_alo;
     std::string e = make_tile_map(&map_c, C, Bpad, SFX_KPAD, FU_TF, FU_KB);
-    if (e.empty()) e = make_tile_map(&map_ahi, ahi, (uint64_t)Bpad * 12, FU_WJ, FU_N2, FU_KB);
-    if (e.empty()) e = make_tile_map(&map_alo, alo, (uint64_t)Bpad * 12, FU_WJ, FU_N2, FU_KB);
+    if (e.empty()) e = make_tile_map_f16(&map_ahi, ahi, (uint64_t)Bpad * 12, FU_N2);
+    if (e.empty()) e = make_tile_map_f16(&map_alo, alo, (uint64_t)Bpad * 12, FU_N2);
     if (!e.empty()) return e;
     const int n = Bpad * 12 * FU_WJ;
     mesh_at_split_kernel<<<(n + 255) / 256, 256, 0, s>>>(A, B, Bpad, ahi, alo);
