@@ -177,8 +177,8 @@ def test_two_loop_variants_agree(model32, monkeypatch):
 
 
 def test_tensor_core_mesh_against_simt(model32, monkeypatch):
-    """Fused tcgen05 / TMA mesh kernel (blend in tf32, skinning in 3 x tf32, fp32 accumulation in
-    tensor memory; csrc/sfx_mesh_fused.cuh) and the round-1 pair (tcgen05 blend + SIMT skinning)
+    """Fused tcgen05 / TMA mesh kernel (blend in tf32, skinning in three products of float16
+    hi / lo halves, fp32 accumulation in tensor memory; csrc/sfx_mesh_fused.cuh) and the round-1 pair (tcgen05 blend + SIMT skinning)
     against the fp32 SIMT kernel on 130 frames (two frame tiles, ragged) with distinct
     parameters: the tf32 rounding of the blend inputs bounds the vertex error by ~1e-4 m;
     structure errors would be centimetres."""
