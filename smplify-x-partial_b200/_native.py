@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libsfx.so')
+# SFX_LIB: another build of the library in csrc/ (development A/B runs only)
+LIB_PATH = os.path.join(_HERE, 'csrc', os.environ.get('SFX_LIB', 'libsfx.so'))
 
 SFX_MAX_BLOCKS = 12
 SFX_NP_MAX = 192

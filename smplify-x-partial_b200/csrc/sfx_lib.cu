@@ -619,6 +619,7 @@ struct sfx_model {
     MeshPlan mesh;        // TMA descriptor of the blend matrix for the tensor-core mesh kernel
     FusedPlan fused;      // descriptors of the fused blend + skinning kernel (sfx_mesh_fused.cuh)
     DevBuf whi, wlo;      // skinning weights [Vpad][64], float16 hi / lo split
+    DevBuf pk16;          // float16 copy of PK: K1 operand of the fused mesh kernel (32 MB)
 };
 
 template <typename T>
@@ -669,7 +670,7 @@ struct sfx_batch {
     SfxLayout lay;
     size_t es = 4;        // element size of the batch dtype
     DevBuf params, gt, conf, jw, lowconf, init_mask, cam, reg_pose, hist_s, hist_y, gram, final_loss,
-        n_evals, n_passes, flags, Acoef, Ccoef, vposed, ahi, alo, go_saved, params_alt, loss_alt, pipe, counter,
+        n_evals, n_passes, flags, Acoef, Ccoef, c16, vposed, ahi, alo, go_saved, params_alt, loss_alt, pipe, counter,
         cam_loss, params_last, prof, coll_vals, coll_idx, coll_stat, guess;
     bool last_valid = false;
     bool has_reg = false;
@@ -779,8 +780,9 @@ int sfx_model_create(const sfx_model_desc* desc, sfx_model** out) {
                                &wlo[(size_t)v * FU_WJ + j]);
             cudaError_t ce = m->whi.upload(whi);
             if (ce == cudaSuccess) ce = m->wlo.upload(wlo);
+            if (ce == cudaSuccess) ce = m->pk16.alloc((size_t)3 * m->V * SFX_KPAD * sizeof(__half));
             if (ce != cudaSuccess) e = std::string("upload skinning weights: ") + cudaGetErrorString(ce);
-            else e = fused_plan_create(m->fused, (const float*)m->PK.p, m->V, (const __half*)m->whi.p,
+            else e = fused_plan_create(m->fused, (const float*)m->PK.p, (__half*)m->pk16.p, m->V, (const __half*)m->whi.p,
                                        (const __half*)m->wlo.p, Vpad);
         }
         if (!e.empty()) rc = fail(SFX_ERR_CUDA, e);
@@ -932,6 +934,7 @@ int sfx_batch_create(const sfx_model* m, int32_t B, int32_t use_vposer, sfx_batc
     ALLOC(Acoef, (size_t)B * SFX_NJ * 12 * es);
     ALLOC(Ccoef, (size_t)mesh_padded_frames(B) * SFX_KPAD * es);
     ALLOC(vposed, (size_t)mesh_padded_frames(B) * 3 * m->V * es);
+    ALLOC(c16, (size_t)mesh_padded_frames(B) * SFX_KPAD * sizeof(__half));
     ALLOC(ahi, (size_t)mesh_padded_frames(B) * 12 * FU_WJ * sizeof(__half));
     ALLOC(alo, (size_t)mesh_padded_frames(B) * 12 * FU_WJ * sizeof(__half));
     ALLOC(go_saved, (size_t)B * 3 * es);
@@ -1412,9 +1415,12 @@ static int forward_mesh_impl(sfx_batch* b, void* vertices_dev, void* joints_dev,
                                          (const float*)b->Ccoef.p, (float*)b->vposed.p,
                                          (float*)vertices_dev, s);
         } else if (!(unfused && unfused[0] == '1')) {
-            // one tensor-core kernel: blend (tf32) + skinning (3 x f16 split) + transform epilogue
+            // one tensor-core kernel: blend (float16 operands; SFX_MESH_K1_TF32=1: tf32) + skinning
+            // (3 x f16 split) + transform epilogue
+            const char* k1tf32 = getenv("SFX_MESH_K1_TF32");
             e = mesh_fused_tc(m->fused, b->B, (const float*)b->Ccoef.p, (const float*)b->Acoef.p,
-                              (__half*)b->ahi.p, (__half*)b->alo.p, (const float*)m->vt.p,
+                              (__half*)b->ahi.p, (__half*)b->alo.p, (__half*)b->c16.p,
+                              !(k1tf32 && k1tf32[0] == '1'), (const float*)m->vt.p,
                               (float*)vertices_dev, s);
         } else {
             e = mesh_blend_tc(m->mesh, b->B, (const float*)b->Ccoef.p, (const float*)m->vt.p,

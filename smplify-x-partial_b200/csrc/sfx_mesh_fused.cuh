@@ -2,7 +2,7 @@
 // third-party smplx lbs.lbs) as ONE tensor-core kernel for sm_100a: both dense contractions on
 // tcgen05 with TMA-fed operands, the posed offsets never leaving tensor memory.
 //
-//   K1  blend     vp[v][c][f]  = sum_k PK[3v+c][k] . C[f][k]          k < 512   (kind::tf32)
+//   K1  blend     vp[v][c][f]  = sum_k PK[3v+c][k] . C[f][k]          k < 512   (kind::f16 on float16 copies; kind::tf32 optional)
 //   K2  skinning  T[v][f][e]   = sum_j W[v][j] . A[f][j][e]           j < 64, e < 12  (3 x f16 split)
 //   epilogue      vert[f][v][r] = T[v][f][4r..4r+2] . (vt[v] + vp[v][.][f]) + T[v][f][4r+3]
 //
@@ -34,7 +34,14 @@
 // accumulated (the lo.lo term is 2^-22 relative): measured against the float32 SIMT kernel in
 // tests/test_gpu_parity.py.
 //
-// Measured and not adopted (128 frames, whole forward 56 us with this kernel at 33.8 us):
+// K1 runs on float16 copies of PK (made once per model, 32 MB) and of the coefficients (made by the
+// split kernel): 8 k-blocks of 64 instead of 16 of 32, half the bytes and half the MMA
+// instructions, and float16 ROUNDS to the 11 significant bits that tf32 TRUNCATES to -- 5.6e-5 m
+// against 1.3e-4 m worst-case difference to the float32 SIMT kernel, 26.2 us against 33.8 us
+// (SFX_MESH_K1_TF32=1 selects the tf32 variant).  Entries of PK below 6e-5 become float16
+// subnormals: an absolute error of at most 3e-8 m per term.
+//
+// Measured and not adopted (128 frames, with K1 in tf32: whole forward 56 us, this kernel 33.8 us):
 //   * frame tiles of 64 or 48 frames (164 / 246 CTAs instead of 82 on 148 SMs): 66 us -- every
 //     extra frame tile streams the blend matrix again;
 //   * a tiled copy of PK whose TMA boxes are 16 KB of consecutive bytes (instead of 128-byte
@@ -59,6 +66,7 @@ constexpr int FU_TF = 128;                  // frames per tile (UMMA N of K1)
 constexpr int FU_CH = 8;                    // frames per K2 chunk
 constexpr int FU_N2 = 12 * FU_CH;           // UMMA N of K2 (96)
 constexpr int FU_KB = 32;                   // tf32 elements per k-block (one 128-byte swizzle row)
+constexpr int FU_KB16 = 64;                 // float16 elements per k-block (K1 on float16 operands)
 constexpr int FU_STAGES = 3;
 constexpr int FU_A_BYTES = FU_TV * FU_KB * 4;                       // 16 KB: one [128][32] tile
 constexpr int FU_STAGE_BYTES = 3 * FU_A_BYTES + FU_TF * FU_KB * 4;  // 64 KB
@@ -77,12 +85,13 @@ static_assert(FU_W_BYTES + 2 * FU_A2_BYTES <= FU_RING_BYTES, "K2 operands re-use
 
 struct FusedPlan {
     CUtensorMap map_pk3;      // PK as [V][3][512] fp32, box {32, 1, 128}, SWIZZLE_128B
+    CUtensorMap map_pk3h;     // the float16 copy of PK, same view, box {64, 1, 128}
     CUtensorMap map_whi, map_wlo;   // [Vpad][64] float16, box {64, 128}
     bool ready = false;
     int V = 0;
 };
 
-static std::string make_map3(CUtensorMap* map, const float* base, uint64_t V) {
+static std::string make_map3(CUtensorMap* map, const void* base, uint64_t V, bool f16 = false) {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -92,11 +101,13 @@ static std::string make_map3(CUtensorMap* map, const float* base, uint64_t V) {
             return "cuTensorMapEncodeTiled is not available from this driver";
         fn = (PFN_encodeTiled)p;
     }
+    const cuuint64_t es = f16 ? 2 : 4;
     cuuint64_t dims[3] = {SFX_KPAD, 3, V};
-    cuuint64_t strides[2] = {SFX_KPAD * sizeof(float), 3ull * SFX_KPAD * sizeof(float)};
-    cuuint32_t box[3] = {FU_KB, 1, FU_TV};
+    cuuint64_t strides[2] = {SFX_KPAD * es, 3ull * SFX_KPAD * es};
+    cuuint32_t box[3] = {(cuuint32_t)(f16 ? FU_KB16 : FU_KB), 1, FU_TV};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+    CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base,
+                    dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled (3-D) failed with code " + std::to_string((int)r);
@@ -104,7 +115,8 @@ static std::string make_map3(CUtensorMap* map, const float* base, uint64_t V) {
 }
 
 // [rows][64] float16, K-major: a row is one 128-byte swizzle row
-static std::string make_tile_map_f16(CUtensorMap* map, const __half* base, uint64_t rows, uint32_t box_rows) {
+static std::string make_tile_map_f16(CUtensorMap* map, const __half* base, uint64_t rows, uint32_t box_rows,
+                                     uint64_t cols = 64) {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -114,9 +126,9 @@ static std::string make_tile_map_f16(CUtensorMap* map, const __half* base, uint6
             return "cuTensorMapEncodeTiled is not available from this driver";
         fn = (PFN_encodeTiled)p;
     }
-    cuuint64_t dims[2] = {FU_WJ, rows};
-    cuuint64_t strides[1] = {FU_WJ * sizeof(__half)};
-    cuuint32_t box[2] = {FU_WJ, box_rows};
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(__half)};
+    cuuint32_t box[2] = {64, box_rows};        // 64 float16 = one 128-byte swizzle row
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -132,10 +144,21 @@ __host__ __device__ inline void f16_split(float x, __half* hi, __half* lo) {
     *lo = __float2half_rn(x - __half2float(*hi));
 }
 
-static std::string fused_plan_create(FusedPlan& plan, const float* PK, int V, const __half* whi_dev,
+// float16 copy of the blend matrix (K1 operand of the fused kernel), made once per model
+__global__ void mesh_pk_half_kernel(const float* __restrict__ PK, long n, __half* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2half_rn(PK[i]);
+}
+
+static std::string fused_plan_create(FusedPlan& plan, const float* PK, __half* pk16_dev, int V, const __half* whi_dev,
                                      const __half* wlo_dev, int Vpad) {
     plan.V = V;
+    const long n = 3L * V * SFX_KPAD;
+    mesh_pk_half_kernel<<<(unsigned)((n + 255) / 256), 256>>>(PK, n, pk16_dev);
+    cudaError_t ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) return std::string("mesh_pk_half_kernel: ") + cudaGetErrorString(ce);
     std::string e = make_map3(&plan.map_pk3, PK, (uint64_t)V);
+    if (e.empty()) e = make_map3(&plan.map_pk3h, pk16_dev, (uint64_t)V, true);
     if (e.empty()) e = make_tile_map_f16(&plan.map_whi, whi_dev, Vpad, FU_TV);
     if (e.empty()) e = make_tile_map_f16(&plan.map_wlo, wlo_dev, Vpad, FU_TV);
     plan.ready = e.empty();
@@ -178,6 +201,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
                  : "r"(taddr)                                                                       \
                  : "memory")
 
+// K1F16: K1 on float16 operands (the float16 copy of PK and of the coefficients, kind::f16 k16
+// steps, 8 k-blocks of 64) instead of tf32 (fp32 operands, k8 steps, 16 k-blocks of 32): half the
+// bytes and half the MMA instructions; float16 rounds to the 11 significant bits tf32 truncates to
+template <bool K1F16>
 __global__ void __launch_bounds__(FU_THREADS, 1)
 mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_constant__ CUtensorMap map_c,
                      const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
@@ -198,7 +225,8 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int v0 = blockIdx.x * FU_TV;       // first vertex of the tile
     const int m0 = blockIdx.y * FU_TF;       // first frame of the tile
-    constexpr int NUM_KB = SFX_KPAD / FU_KB;
+    constexpr int KBE = K1F16 ? FU_KB16 : FU_KB;       // elements per k-block (128 bytes either way)
+    constexpr int NUM_KB = SFX_KPAD / KBE;
     const int nfr = B - m0 < FU_TF ? B - m0 : FU_TF;
     const int nchunk = (nfr + FU_CH - 1) / FU_CH;
 
@@ -241,8 +269,8 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
             if (kb >= FU_STAGES) mbar_wait(empty + s, ((kb / FU_STAGES) - 1) & 1);
             unsigned char* a = smem + s * FU_STAGE_BYTES;
             mbar_expect_tx(full + s, FU_STAGE_BYTES);
-            for (int c = 0; c < 3; ++c) tma_load_3d(a + c * FU_A_BYTES, &map_pk3, kb * FU_KB, c, v0, full + s);
-            tma_load_2d(a + 3 * FU_A_BYTES, &map_c, kb * FU_KB, m0, full + s);
+            for (int c = 0; c < 3; ++c) tma_load_3d(a + c * FU_A_BYTES, &map_pk3, kb * KBE, c, v0, full + s);
+            tma_load_2d(a + 3 * FU_A_BYTES, &map_c, kb * KBE, m0, full + s);
         }
         // K2 operands go where the K1 stages were: wait until K1's MMAs have read them all
         mbar_wait(d1_full, 0);
@@ -260,7 +288,7 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
         }
     } else if (warp == 4 * FU_EPW + 1 && lane == 0) {
         // ===== MMA issuer =====
-        const uint32_t idesc1 = umma_idesc_tf32_n(FU_TF);
+        const uint32_t idesc1 = K1F16 ? umma_idesc_f16_n(FU_TF) : umma_idesc_tf32_n(FU_TF);
         for (int kb = 0; kb < NUM_KB; ++kb) {
             const int s = kb % FU_STAGES;
             mbar_wait(full + s, (kb / FU_STAGES) & 1);
@@ -271,8 +299,10 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
             for (int c = 0; c < 3; ++c) {
                 const uint64_t da = umma_desc_sw128(a + c * FU_A_BYTES);
 #pragma unroll
-                for (int k = 0; k < FU_KB / 8; ++k)
-                    umma_tf32(tmem_base + c * FU_TF, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+                for (int k = 0; k < 4; ++k) {           // four 32-byte k-steps per 128-byte row
+                    if (K1F16) umma_f16(tmem_base + c * FU_TF, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+                    else umma_tf32(tmem_base + c * FU_TF, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+                }
             }
             tc_commit(empty + s);
         }
@@ -369,34 +399,44 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
 }
 
 // A^T tiles of K2: per frame 12 rows x 64 joints (hi and lo), row 12 f + e, from the skinning
-// transforms A [B][55][12] of the pose prologue
+// transforms A [B][55][12] of the pose prologue; behind them (c16 != nullptr) the float16 copy of the
+// blend coefficients C [Bpad][512] for K1
 __global__ void mesh_at_split_kernel(const float* __restrict__ A, int B, int Bpad, __half* __restrict__ ahi,
-                                     __half* __restrict__ alo) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= Bpad * 12 * FU_WJ) return;
-    const int j = idx % FU_WJ, row = idx / FU_WJ, f = row / 12, e = row % 12;
-    float x = 0.f;
-    if (f < B && j < SFX_NJ) x = A[((size_t)f * SFX_NJ + j) * 12 + e];
-    f16_split(x, ahi + idx, alo + idx);
+                                     __half* __restrict__ alo, const float* __restrict__ C,
+                                     __half* __restrict__ c16) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_split = Bpad * 12 * FU_WJ;
+    if (idx < n_split) {
+        const int j = idx % FU_WJ, row = idx / FU_WJ, f = row / 12, e = row % 12;
+        float x = 0.f;
+        if (f < B && j < SFX_NJ) x = A[((size_t)f * SFX_NJ + j) * 12 + e];
+        f16_split(x, ahi + idx, alo + idx);
+        return;
+    }
+    idx -= n_split;
+    if (c16 && idx < Bpad * SFX_KPAD) c16[idx] = __float2half_rn(idx / SFX_KPAD < B ? C[idx] : 0.f);
 }
 
+// k1_f16: K1 on the float16 copies (default); false: K1 in tf32 on the fp32 arrays (SFX_MESH_K1_TF32=1)
 static std::string mesh_fused_tc(const FusedPlan& plan, int B, const float* C, const float* A, __half* ahi,
-                                 __half* alo, const float* vt, float* verts, cudaStream_t s) {
+                                 __half* alo, __half* c16, bool k1_f16, const float* vt, float* verts,
+                                 cudaStream_t s) {
     if (!plan.ready) return "fused tensor-core mesh plan was not created";
     const int Bpad = (B + FU_TF - 1) / FU_TF * FU_TF;
     CUtensorMap map_c, map_ahi, map_alo;
-    std::string e = make_tile_map(&map_c, C, Bpad, SFX_KPAD, FU_TF, FU_KB);
+    std::string e = k1_f16 ? make_tile_map_f16(&map_c, c16, Bpad, FU_TF, SFX_KPAD)
+                           : make_tile_map(&map_c, C, Bpad, SFX_KPAD, FU_TF, FU_KB);
     if (e.empty()) e = make_tile_map_f16(&map_ahi, ahi, (uint64_t)Bpad * 12, FU_N2);
     if (e.empty()) e = make_tile_map_f16(&map_alo, alo, (uint64_t)Bpad * 12, FU_N2);
     if (!e.empty()) return e;
-    const int n = Bpad * 12 * FU_WJ;
-    mesh_at_split_kernel<<<(n + 255) / 256, 256, 0, s>>>(A, B, Bpad, ahi, alo);
-    cudaError_t ce = cudaFuncSetAttribute(mesh_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          FU_SMEM_BYTES);
+    const int n = Bpad * 12 * FU_WJ + (k1_f16 ? Bpad * SFX_KPAD : 0);
+    mesh_at_split_kernel<<<(n + 255) / 256, 256, 0, s>>>(A, B, Bpad, ahi, alo, C, k1_f16 ? c16 : nullptr);
+    auto kern = k1_f16 ? mesh_fused_tc_kernel<true> : mesh_fused_tc_kernel<false>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM_BYTES);
     if (ce != cudaSuccess) return std::string("mesh_fused_tc_kernel attr: ") + cudaGetErrorString(ce);
     dim3 grid((plan.V + FU_TV - 1) / FU_TV, Bpad / FU_TF);
-    mesh_fused_tc_kernel<<<grid, FU_THREADS, FU_SMEM_BYTES, s>>>(plan.map_pk3, map_c, plan.map_whi, plan.map_wlo,
-                                                                 map_ahi, map_alo, vt, verts, B, plan.V);
+    kern<<<grid, FU_THREADS, FU_SMEM_BYTES, s>>>(k1_f16 ? plan.map_pk3h : plan.map_pk3, map_c, plan.map_whi,
+                                                 plan.map_wlo, map_ahi, map_alo, vt, verts, B, plan.V);
     ce = cudaGetLastError();
     return ce == cudaSuccess ? "" : std::string("mesh_fused_tc_kernel: ") + cudaGetErrorString(ce);
 }

@@ -21,6 +21,9 @@ namespace sfx {
 
 #define SFX_NWARP 16
 #define SFX_NBUF 4
+#ifndef SFX_NFLY
+#define SFX_NFLY SFX_NBUF      // rows a warp keeps in flight (<= SFX_NBUF; profiles/microbench/l2_per_sm.cu)
+#endif
 
 struct StreamWS {
     unsigned char* ring;        // ring mode: [NWARP][NBUF][512*sizeof(T)]; else partials only
@@ -190,7 +193,7 @@ __device__ __forceinline__ void stream_rows_own(OWN own, RP rowptr, StreamWS& ws
         };
         if (lane == 0) {
             fence_proxy_async();
-            for (int i = 0; i < SFX_NBUF && i < count; ++i) issue(i);
+            for (int i = 0; i < SFX_NFLY && i < count; ++i) issue(i);
         }
         for (int i = 0; i < count; ++i) {
             const T aux = aux_at(i);
@@ -199,9 +202,9 @@ __device__ __forceinline__ void stream_rows_own(OWN own, RP rowptr, StreamWS& ws
             mbar_wait(mybar + b, (n / SFX_NBUF) & 1);
             load_row_regs<T>(reinterpret_cast<const T*>(mybuf + (size_t)b * ROWB), lane, vals);
             __syncwarp();
-            if (lane == 0 && i + SFX_NBUF < count) {
+            if (lane == 0 && i + SFX_NFLY < count) {
                 fence_proxy_async();
-                issue(i + SFX_NBUF);
+                issue(i + SFX_NFLY);
             }
             fn(own.index(warp, i), vals, aux);
         }
