@@ -12,6 +12,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'smplify-x-partial_b200', 'csrc', 'libsfx.so')
 COLS = ['UTCHMMA', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'LDTM', 'UTCBAR', 'MAPA', 'UCGABAR', 'HMMA', 'LDL', 'STL']
 
+def strip_params(name):
+    """'void f<(bool)1>(A, B)' -> 'void f<(bool)1>': drops the parameter list (last balanced group)."""
+    if not name.endswith(')'):
+        return name
+    depth = 0
+    for i in range(len(name) - 1, -1, -1):
+        depth += name[i] == ')'
+        depth -= name[i] == '('
+        if depth == 0:
+            return name[:i]
+    return name
+
+
 sass = subprocess.run(['cuobjdump', '-sass', LIB], capture_output=True, text=True, check=True).stdout
 names = subprocess.run(['cu++filt'], input='\n'.join(re.findall(r'Function : (\S+)', sass)), capture_output=True,
                        text=True).stdout.split('\n')
@@ -19,7 +32,7 @@ counts, order, cur, k = {}, [], None, 0
 for line in sass.splitlines():
     m = re.search(r'Function : (\S+)', line)
     if m:
-        cur = names[k].split('(')[0] if k < len(names) and names[k] else m.group(1)
+        cur = strip_params(names[k]) if k < len(names) and names[k] else m.group(1)
         k += 1
         counts[cur] = collections.Counter()
         order.append(cur)
