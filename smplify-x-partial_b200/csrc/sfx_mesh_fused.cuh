@@ -338,16 +338,19 @@ mesh_fused_tc_kernel(const __grid_constant__ CUtensorMap map_pk3, const __grid_c
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const int tile_floats = (V - v0 < FU_TV ? V - v0 : FU_TV) * 3;     // valid floats of a frame run
         mbar_wait(d1_full, 0);
+        tc_fence_after();
         for (int q = 0; q < nchunk; ++q) {
-            mbar_wait(d2_full, q & 1);
-            tc_fence_after();
+            // the chunk's frames of the K1 accumulators do not depend on K2: their loads are issued
+            // before the wait, so only the read of T stands between two chunks' MMAs
             uint32_t T[12 * HF], P[3 * FU_CH];
-#pragma unroll
-            for (int c8 = 0; c8 < 12 * HF / 8; ++c8)
-                SFX_TMEM_LD(8, tmem_d2 + lane_addr + 12 * HF * half + 8 * c8, T, 8 * c8);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 SFX_TMEM_LD(8, tmem_base + lane_addr + c * FU_TF + q * FU_CH, P, 8 * c);
+            mbar_wait(d2_full, q & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c8 = 0; c8 < 12 * HF / 8; ++c8)
+                SFX_TMEM_LD(8, tmem_d2 + lane_addr + 12 * HF * half + 8 * c8, T, 8 * c8);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(d2_empty);                         // D2 may be overwritten by the next chunk
