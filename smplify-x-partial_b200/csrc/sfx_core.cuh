@@ -970,53 +970,75 @@ SFX_FN void chain_forward(const ModelView<T>& M, Scratch<T>& S) {
 }
 
 // Adjoint of chain_forward (one warp): dA, dX[0..55) -> dR (chain part), drel, dJ (A part).
+// Three passes, so that only what a parent needs from its children sits on the level-by-level
+// chain: (1) every joint's own terms, all joints side by side; (2) deepest level first, the joints
+// WITH children add their children's terms (own terms first, children in table order -- the order
+// of the sums is that of the one-pass formulation); (3) dR / drel of every joint from its
+// finished dRw / dtw, all joints side by side.
 template <typename T>
 SFX_FN void chain_adjoint(const ModelView<T>& M, Scratch<T>& S) {
-    for (int lv = M.nlev - 1; lv >= 0; --lv) {
+    // ---- (1) own terms from A_j and the posed joint ----
+    SFX_LANE_FOR(j, SFX_NJ) {
+        T dA[12], J[3], Rwj[9];
+        for (int k = 0; k < 12; ++k) dA[k] = S.dA[12 * j + k];
+        for (int k = 0; k < 3; ++k) J[k] = S.Jr[3 * j + k];
+        for (int k = 0; k < 9; ++k) Rwj[k] = S.Rw[9 * j + k];
+        for (int r = 0; r < 3; ++r) {
+            const T dat = dA[4 * r + 3];
+            for (int k = 0; k < 3; ++k) S.dRw[9 * j + 3 * r + k] = dA[4 * r + k] - dat * J[k];
+            S.dtw[3 * j + r] = dat + S.dX[3 * j + r];
+        }
+        for (int k = 0; k < 3; ++k)
+            S.dJ[3 * j + k] = -(Rwj[k] * dA[3] + Rwj[3 + k] * dA[7] + Rwj[6 + k] * dA[11]);
+    }
+    SFX_SYNCWARP();
+    // ---- (2) children (complete: they sit one level deeper) ----
+    for (int lv = M.nlev - 2; lv >= 0; --lv) {
         int a = M.level_off[lv], b = M.level_off[lv + 1];
         SFX_LANE_FOR(i, b - a) {
-            const int j = M.order[a + i], p = M.parents[j];
-            // own terms from A_j and the posed joint
-            T dA[12], J[3], Rwj[9], dRw[9], dtw[3];
-            for (int k = 0; k < 12; ++k) dA[k] = S.dA[12 * j + k];
-            for (int k = 0; k < 3; ++k) J[k] = S.Jr[3 * j + k];
-            for (int k = 0; k < 9; ++k) Rwj[k] = S.Rw[9 * j + k];
-            for (int r = 0; r < 3; ++r) {
-                const T dat = dA[4 * r + 3];
-                for (int k = 0; k < 3; ++k) dRw[3 * r + k] = dA[4 * r + k] - dat * J[k];
-                dtw[r] = dat + S.dX[3 * j + r];
-            }
-            for (int k = 0; k < 3; ++k)
-                S.dJ[3 * j + k] = -(Rwj[k] * dA[3] + Rwj[3 + k] * dA[7] + Rwj[6 + k] * dA[11]);
-            // children (already complete: they sit one level deeper)
-            for (int e = M.child_off[j]; e < M.child_off[j + 1]; ++e) {
-                const int ch = M.child_idx[e];
-                T dRc[9], Rch[9], dtc[3], rl[3];
-                for (int k = 0; k < 9; ++k) { dRc[k] = S.dRw[9 * ch + k]; Rch[k] = S.R[9 * ch + k]; }
-                for (int k = 0; k < 3; ++k) { dtc[k] = S.dtw[3 * ch + k]; rl[k] = S.rel[3 * ch + k]; }
-                for (int r = 0; r < 3; ++r)
-                    for (int k = 0; k < 3; ++k)
-                        dRw[3 * r + k] += dRc[3 * r] * Rch[3 * k] + dRc[3 * r + 1] * Rch[3 * k + 1] +
-                                          dRc[3 * r + 2] * Rch[3 * k + 2] + dtc[r] * rl[k];
-                for (int r = 0; r < 3; ++r) dtw[r] += dtc[r];
-            }
-            for (int k = 0; k < 9; ++k) S.dRw[9 * j + k] = dRw[k];
-            for (int k = 0; k < 3; ++k) S.dtw[3 * j + k] = dtw[k];
-            if (p < 0) {
-                for (int k = 0; k < 9; ++k) S.dR[9 * j + k] = dRw[k];
-                for (int k = 0; k < 3; ++k) S.drel[3 * j + k] = dtw[k];
-            } else {
-                T Rp[9];
-                for (int k = 0; k < 9; ++k) Rp[k] = S.Rw[9 * p + k];
-                for (int r = 0; r < 3; ++r)
-                    for (int k = 0; k < 3; ++k)
-                        S.dR[9 * j + 3 * r + k] = Rp[r] * dRw[k] + Rp[3 + r] * dRw[3 + k] + Rp[6 + r] * dRw[6 + k];
-                for (int r = 0; r < 3; ++r)
-                    S.drel[3 * j + r] = Rp[r] * dtw[0] + Rp[3 + r] * dtw[1] + Rp[6 + r] * dtw[2];
+            const int j = M.order[a + i];
+            const int e0 = M.child_off[j], e1 = M.child_off[j + 1];
+            if (e0 < e1) {
+                T dRw[9], dtw[3];
+                for (int k = 0; k < 9; ++k) dRw[k] = S.dRw[9 * j + k];
+                for (int k = 0; k < 3; ++k) dtw[k] = S.dtw[3 * j + k];
+                for (int e = e0; e < e1; ++e) {
+                    const int ch = M.child_idx[e];
+                    T dRc[9], Rch[9], dtc[3], rl[3];
+                    for (int k = 0; k < 9; ++k) { dRc[k] = S.dRw[9 * ch + k]; Rch[k] = S.R[9 * ch + k]; }
+                    for (int k = 0; k < 3; ++k) { dtc[k] = S.dtw[3 * ch + k]; rl[k] = S.rel[3 * ch + k]; }
+                    for (int r = 0; r < 3; ++r)
+                        for (int k = 0; k < 3; ++k)
+                            dRw[3 * r + k] += dRc[3 * r] * Rch[3 * k] + dRc[3 * r + 1] * Rch[3 * k + 1] +
+                                              dRc[3 * r + 2] * Rch[3 * k + 2] + dtc[r] * rl[k];
+                    for (int r = 0; r < 3; ++r) dtw[r] += dtc[r];
+                }
+                for (int k = 0; k < 9; ++k) S.dRw[9 * j + k] = dRw[k];
+                for (int k = 0; k < 3; ++k) S.dtw[3 * j + k] = dtw[k];
             }
         }
         SFX_SYNCWARP();
     }
+    // ---- (3) dR (chain part) and drel ----
+    SFX_LANE_FOR(j, SFX_NJ) {
+        const int p = M.parents[j];
+        T dRw[9], dtw[3];
+        for (int k = 0; k < 9; ++k) dRw[k] = S.dRw[9 * j + k];
+        for (int k = 0; k < 3; ++k) dtw[k] = S.dtw[3 * j + k];
+        if (p < 0) {
+            for (int k = 0; k < 9; ++k) S.dR[9 * j + k] = dRw[k];
+            for (int k = 0; k < 3; ++k) S.drel[3 * j + k] = dtw[k];
+        } else {
+            T Rp[9];
+            for (int k = 0; k < 9; ++k) Rp[k] = S.Rw[9 * p + k];
+            for (int r = 0; r < 3; ++r)
+                for (int k = 0; k < 3; ++k)
+                    S.dR[9 * j + 3 * r + k] = Rp[r] * dRw[k] + Rp[3 + r] * dRw[3 + k] + Rp[6 + r] * dRw[6 + k];
+            for (int r = 0; r < 3; ++r)
+                S.drel[3 * j + r] = Rp[r] * dtw[0] + Rp[3 + r] * dtw[1] + Rp[6 + r] * dtw[2];
+        }
+    }
+    SFX_SYNCWARP();
 }
 
 // several sums at once: warp q (q, q + nwarps, ...) reduces quantity q over i < n in the fixed
